@@ -1,0 +1,84 @@
+/* oracle.h -- C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference
+ * (OpenImageIO 3.2.0.2-dev) filtered-resampling path.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+ * may load it.  The product (openimageio_b200/) never links or calls it.
+ *
+ * Parity status: PINNED.  The restatement is checked against
+ *   - the 17 known-answer images testsuite/filters/ref/<filter>.exr,
+ *   - testsuite/oiiotool-xform/ref/{resize,resize2,resize64,resize512}.tif,
+ *     resized-offset.exr, fit*.tif, resample*.tif,
+ *   - the reference's own src/libutil/filter.cpp object code compiled
+ *     unmodified into oracle/_ref/ (bit-exact weight comparison),
+ * see tests/test_oracle_golden.py and tests/golden/make_golden.py.
+ * MIP levels >= 1 are not pinned by any reference test.
+ */
+#ifndef OIIO_ORACLE_H
+#define OIIO_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TypeDesc::BASETYPE values (src/include/OpenImageIO/typedesc.h:57-84) */
+enum { ORC_UINT8 = 2, ORC_UINT16 = 4, ORC_HALF = 10, ORC_FLOAT = 11 };
+
+typedef struct {
+    void* pixels;     /* address of the data-window origin pixel (x,y) */
+    int32_t basetype; /* ORC_* */
+    int32_t nchannels;
+    int32_t x, y, width, height;                       /* data window  */
+    int32_t full_x, full_y, full_width, full_height;   /* display window */
+    int64_t xstride, ystride;                          /* bytes */
+} orc_image;
+
+typedef struct {
+    int32_t xbegin, xend, ybegin, yend;
+} orc_roi;
+
+/* Filter evaluation (restates src/libutil/filter.cpp). Returns NaN-free float;
+ * unknown name -> returns -1 from orc_filter_lookup. */
+int orc_filter_count(void);
+const char* orc_filter_name(int index);
+float orc_filter_default_width(int index);
+int orc_filter_lookup(const char* name); /* exact FilterDesc name, else -1 */
+int orc_filter_separable(const char* name, float w, float h);
+float orc_filter_xfilt(const char* name, float w, float h, float x);
+float orc_filter_yfilt(const char* name, float w, float h, float y);
+float orc_filter_eval2d(const char* name, float w, float h, float x, float y);
+float orc_filter1d_eval(const char* name, float w, float x);
+
+/* ImageBufAlgo::resize restated (imagebufalgo_xform.cpp:595-918).
+ * filtername NULL/"" -> default rule; filterwidth 0 -> default rule.
+ * nthreads <= 0 -> hardware concurrency.  Returns 0 on success, else nonzero
+ * and a message in err. */
+int orc_resize(const orc_image* dst, const orc_image* src,
+               const char* filtername, float filterwidth, orc_roi roi,
+               int nthreads, char* err, int errlen);
+
+/* ImageBufAlgo::resample restated (imagebufalgo_xform.cpp:1107-1186).  */
+int orc_resample(const orc_image* dst, const orc_image* src, int interpolate,
+                 orc_roi roi, int nthreads, char* err, int errlen);
+
+/* ImageBufAlgo::fit geometry (imagebufalgo_xform.cpp:962-997).  Writes the
+ * resize target size and the data-window offset of the result. */
+void orc_fit_geometry(int src_full_w, int src_full_h, int fit_w, int fit_h,
+                      const char* fillmode, int* resize_w, int* resize_h,
+                      int* xoffset, int* yoffset);
+
+/* maketexture.cpp resize_block (box fast path, :141-334): float images only.
+ * dst/src are float, same nchannels.  */
+int orc_resize_block(const orc_image* dst, const orc_image* src,
+                     int envlatlmode, int allow_shift, int nthreads);
+
+/* float -> dst-type store and src-type -> float load used by the above
+ * (fmath.h:753-764, 1009-1031); exposed for unit tests. */
+float orc_load_as_float(const void* p, int basetype);
+void orc_store_from_float(void* p, int basetype, float v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

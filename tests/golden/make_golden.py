@@ -1,0 +1,76 @@
+#!/usr/bin/env python
+"""Convert the reference's own golden images for the resize/resample/fit path
+into compact .npz fixtures (the GPU box has no /root/reference).
+
+Run in the build container:   python tests/golden/make_golden.py
+
+Sources (all under /root/reference/testsuite, OpenImageIO 3.2.0.2-dev):
+  filters/ref/<filter>.exr            17 known-answer images written by
+                                      filters/run.py (delta 16x16 -> 80x80, half)
+  common/grid.tif                     1000x1000 RGBA uint8 input
+  common/tahoe-tiny.tif               input of fit3
+  oiiotool-xform/ref/resize.tif       --resize 256x256
+  oiiotool-xform/ref/resize2.tif      --resize 25%
+  oiiotool-xform/ref/resize64.tif     --resize 64x64
+  oiiotool-xform/ref/resize512.tif    resize64 -> --resize 512x512
+  oiiotool-xform/ref/resized-offset.exr  nonzero origin, half
+  oiiotool-xform/ref/resample.tif, resample-nearest.tif   --resample 128x128
+  oiiotool-xform/ref/fit.tif, fit2.tif, fit3.tif           --fit
+Only pixel arrays are stored (no reference source code is copied).
+"""
+import os
+import sys
+
+os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+import cv2  # noqa: E402
+import numpy as np  # noqa: E402
+
+REF = "/root/reference/testsuite"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def read(path):
+    img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+    if img is None:
+        raise RuntimeError("cannot read " + path)
+    if img.ndim == 3:
+        if img.shape[2] == 3:
+            img = img[:, :, ::-1]
+        elif img.shape[2] == 4:
+            img = img[:, :, [2, 1, 0, 3]]
+    return np.ascontiguousarray(img)
+
+
+def main():
+    filt = {}
+    fdir = os.path.join(REF, "filters/ref")
+    for f in sorted(os.listdir(fdir)):
+        if f.endswith(".exr"):
+            a = read(os.path.join(fdir, f))
+            if a.ndim == 3:  # single-channel EXR may be expanded by cv2
+                assert np.array_equal(a[..., 0], a[..., 1])
+                a = a[..., 0]
+            # stored as half on disk; cv2 returns float32 -- exact
+            h = a.astype(np.float16)
+            assert np.array_equal(h.astype(np.float32), a)
+            filt[f[:-4]] = h
+    np.savez_compressed(os.path.join(HERE, "filters_ref.npz"), **filt)
+    print("filters:", sorted(filt))
+
+    x = {}
+    x["grid"] = read(os.path.join(REF, "common/grid.tif"))
+    x["tahoe_tiny"] = read(os.path.join(REF, "common/tahoe-tiny.tif"))
+    xdir = os.path.join(REF, "oiiotool-xform/ref")
+    for name in ["resize", "resize2", "resize64", "resize512", "resample",
+                 "resample-nearest", "fit", "fit2", "fit3"]:
+        x[name.replace("-", "_")] = read(os.path.join(xdir, name + ".tif"))
+    ro = read(os.path.join(xdir, "resized-offset.exr"))
+    x["resized_offset"] = ro.astype(np.float16)
+    assert np.array_equal(x["resized_offset"].astype(np.float32), ro)
+    for k, v in x.items():
+        print(k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(HERE, "xform_ref.npz"), **x)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

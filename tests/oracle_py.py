@@ -1,0 +1,209 @@
+"""ctypes access to the CPU oracle (oracle/liboiio_oracle.so) and, when built,
+to the reference's own filter object code (oracle/_ref/libref_filter.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference leg; never by openimageio_b200/.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+UINT8, UINT16, HALF, FLOAT = 2, 4, 10, 11
+_NP2BT = {np.dtype(np.uint8): UINT8, np.dtype(np.uint16): UINT16,
+          np.dtype(np.float16): HALF, np.dtype(np.float32): FLOAT}
+
+
+class OrcImage(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("basetype", C.c_int32),
+                ("nchannels", C.c_int32),
+                ("x", C.c_int32), ("y", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32),
+                ("full_x", C.c_int32), ("full_y", C.c_int32),
+                ("full_width", C.c_int32), ("full_height", C.c_int32),
+                ("xstride", C.c_int64), ("ystride", C.c_int64)]
+
+
+class OrcRoi(C.Structure):
+    _fields_ = [("xbegin", C.c_int32), ("xend", C.c_int32),
+                ("ybegin", C.c_int32), ("yend", C.c_int32)]
+
+
+_lib = None
+_ref = None
+
+
+def build_oracle():
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR])
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ORACLE_DIR, "liboiio_oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        L.orc_filter_name.restype = C.c_char_p
+        L.orc_filter_default_width.restype = C.c_float
+        for fn in (L.orc_filter_xfilt, L.orc_filter_yfilt):
+            fn.restype = C.c_float
+            fn.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_float]
+        L.orc_filter_eval2d.restype = C.c_float
+        L.orc_filter_eval2d.argtypes = [C.c_char_p, C.c_float, C.c_float,
+                                        C.c_float, C.c_float]
+        L.orc_filter1d_eval.restype = C.c_float
+        L.orc_filter1d_eval.argtypes = [C.c_char_p, C.c_float, C.c_float]
+        L.orc_filter_separable.argtypes = [C.c_char_p, C.c_float, C.c_float]
+        L.orc_filter_lookup.argtypes = [C.c_char_p]
+        L.orc_resize.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
+                                 C.c_char_p, C.c_float, OrcRoi, C.c_int,
+                                 C.c_char_p, C.c_int]
+        L.orc_resample.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
+                                   C.c_int, OrcRoi, C.c_int, C.c_char_p,
+                                   C.c_int]
+        L.orc_resize_block.argtypes = [C.POINTER(OrcImage),
+                                       C.POINTER(OrcImage), C.c_int, C.c_int,
+                                       C.c_int]
+        L.orc_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
+            [C.POINTER(C.c_int)] * 4
+        L.orc_load_as_float.restype = C.c_float
+        L.orc_load_as_float.argtypes = [C.c_void_p, C.c_int]
+        L.orc_store_from_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        _lib = L
+    return _lib
+
+
+def ref_filter_lib():
+    """The reference's own filter.cpp object code, or None if not built."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(ORACLE_DIR, "_ref", "libref_filter.so")
+        if not os.path.exists(path):
+            return None
+        R = C.CDLL(path)
+        R.ref_filter2d_name.restype = C.c_char_p
+        R.ref_filter1d_name.restype = C.c_char_p
+        R.ref_filter2d_default_width.restype = C.c_float
+        R.ref_filter2d_eval.argtypes = [
+            C.c_char_p, C.c_float, C.c_float, C.c_int, C.c_int,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int),
+            C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        R.ref_filter1d_eval.argtypes = [C.c_char_p, C.c_float, C.c_int,
+                                        C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_float)]
+        _ref = R
+    return _ref
+
+
+class Img:
+    """numpy pixels (H, W, C) + OpenImageIO-style data / full windows."""
+
+    def __init__(self, arr, x=0, y=0, full=None):
+        if arr.ndim == 2:
+            arr = arr[:, :, None]
+        assert arr.ndim == 3
+        self.arr = arr
+        self.x, self.y = x, y
+        h, w, _ = arr.shape
+        self.full = full if full is not None else (x, y, w, h)
+
+    @property
+    def nchannels(self):
+        return self.arr.shape[2]
+
+    def c(self):
+        a = self.arr
+        im = OrcImage()
+        im.pixels = a.ctypes.data
+        im.basetype = _NP2BT[a.dtype]
+        im.nchannels = a.shape[2]
+        im.x, im.y = self.x, self.y
+        im.width, im.height = a.shape[1], a.shape[0]
+        im.full_x, im.full_y, im.full_width, im.full_height = self.full
+        im.xstride = a.strides[1]
+        im.ystride = a.strides[0]
+        return im
+
+
+def resize(dst, src, filtername="", filterwidth=0.0, roi=None, nthreads=0):
+    """dst, src: Img.  Writes into dst.arr.  Raises on error."""
+    L = lib()
+    d, s = dst.c(), src.c()
+    if roi is None:
+        roi = (dst.x, dst.x + dst.arr.shape[1], dst.y, dst.y + dst.arr.shape[0])
+    err = C.create_string_buffer(512)
+    rc = L.orc_resize(C.byref(d), C.byref(s),
+                      (filtername or "").encode(), float(filterwidth),
+                      OrcRoi(*roi), int(nthreads), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return dst
+
+
+def resample(dst, src, interpolate=True, roi=None, nthreads=0):
+    L = lib()
+    d, s = dst.c(), src.c()
+    if roi is None:
+        roi = (dst.x, dst.x + dst.arr.shape[1], dst.y, dst.y + dst.arr.shape[0])
+    err = C.create_string_buffer(512)
+    rc = L.orc_resample(C.byref(d), C.byref(s), 1 if interpolate else 0,
+                        OrcRoi(*roi), int(nthreads), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return dst
+
+
+def resize_block(dst, src, allow_shift=False):
+    L = lib()
+    d, s = dst.c(), src.c()
+    rc = L.orc_resize_block(C.byref(d), C.byref(s), 0, int(allow_shift), 0)
+    if rc:
+        raise RuntimeError("orc_resize_block failed")
+    return dst
+
+
+def fit_geometry(sw, sh, fw, fh, fillmode="letterbox"):
+    L = lib()
+    v = [C.c_int() for _ in range(4)]
+    L.orc_fit_geometry(sw, sh, fw, fh, fillmode.encode(), *[C.byref(i) for i in v])
+    return tuple(i.value for i in v)
+
+
+def mip_chain(level0, filtername="box"):
+    """write_mipmap level loop (maketexture.cpp:823-986) on a float32 HxWxC
+    array, no file output.  Returns [level1, level2, ...]."""
+    assert level0.dtype == np.float32
+    out = []
+    img = level0
+    while img.shape[1] > 1 or img.shape[0] > 1:
+        h, w, c = img.shape
+        sw = w // 2 if w > 1 else w
+        sh = h // 2 if h > 1 else h
+        small = np.empty((sh, sw, c), np.float32)
+        if filtername == "box":
+            resize_block(Img(small), Img(img))
+        else:
+            resize(Img(small), Img(img), filtername)
+        out.append(small)
+        img = small
+    return out
+
+
+def quantize(arr_f32, dtype):
+    """convert_type<float, D> on a whole array through the oracle's store."""
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return arr_f32.copy()
+    if dtype == np.float16:
+        return arr_f32.astype(np.float16)
+    mx = 255.0 if dtype == np.uint8 else 65535.0
+    s = arr_f32.astype(np.float32) * np.float32(mx)
+    s = s + np.where(s < 0, np.float32(-0.5), np.float32(0.5)).astype(np.float32)
+    s = np.where(np.isnan(s), np.float32(0), s)
+    s = np.clip(s, np.float32(0), np.float32(mx))
+    return s.astype(dtype)
