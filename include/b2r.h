@@ -1,0 +1,210 @@
+/* b2r.h -- C ABI of the B200-native filtered resampler (libb2r.so).
+ *
+ * This is the drop-in boundary for ONE hot path of OpenImageIO 3.2: the
+ * compute kernel behind ImageBufAlgo::resize / fit / resample and the
+ * per-level MIP downsample of make_texture.  Every entry point names the
+ * reference interface it replaces (paths relative to the OpenImageIO tree).
+ * Plain C: pointers, sizes, PODs; no C++ or torch types cross it.
+ *
+ * There is no CPU fallback: every compute entry point fails with
+ * B2R_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Conventions kept from the reference:
+ *  - the caller owns all pixel memory; dst is already allocated (IBAprep,
+ *    src/libOpenImageIO/imagebufalgo_xform.cpp:882-884);
+ *  - functions return 0 on success, else a B2R_ERR_* code and a
+ *    human-readable message in `err` (the text ImageBuf::errorfmt would have
+ *    received, e.g. `Filter "foo" not recognized`, xform.cpp:857); they never
+ *    throw and never abort;
+ *  - calls are synchronous for host pixel memory (dst is complete on return)
+ *    and stream-ordered for device pixel memory;
+ *  - re-entrant: concurrent calls on distinct dst images are allowed.
+ */
+#ifndef B2R_H
+#define B2R_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#    define B2R_API __declspec(dllexport)
+#else
+#    define B2R_API __attribute__((visibility("default")))
+#endif
+
+/* TypeDesc::BASETYPE values, src/include/OpenImageIO/typedesc.h:57-84 */
+enum b2r_basetype {
+    B2R_UINT8  = 2,
+    B2R_UINT16 = 4,
+    B2R_HALF   = 10,
+    B2R_FLOAT  = 11
+};
+
+enum b2r_memspace {
+    B2R_MEM_AUTO   = 0, /* ask the CUDA runtime (cudaPointerGetAttributes) */
+    B2R_MEM_HOST   = 1, /* pageable or pinned host memory */
+    B2R_MEM_DEVICE = 2  /* device memory on `device` */
+};
+
+enum b2r_error {
+    B2R_OK                = 0,
+    B2R_ERR_INVALID       = 1, /* bad argument / uninitialized image */
+    B2R_ERR_FILTER        = 2, /* Filter "..." not recognized */
+    B2R_ERR_TYPES         = 3, /* (dst,src) pixel type pair not on the path */
+    B2R_ERR_NO_DEVICE     = 4, /* no usable CUDA device: there is no fallback */
+    B2R_ERR_CUDA          = 5, /* CUDA runtime error (message has details) */
+    B2R_ERR_UNSUPPORTED   = 6  /* volumes / deep images */
+};
+
+/* What resize_<D,S> reads from an ImageBuf + ImageSpec
+ * (src/libOpenImageIO/imagebufalgo_xform.cpp:601-625, imagebuf.h:1383-1385). */
+typedef struct b2r_image {
+    void* pixels;      /* address of the data-window origin pixel (x,y) */
+    int32_t basetype;  /* enum b2r_basetype */
+    int32_t nchannels;
+    int32_t x, y, width, height;                      /* data window */
+    int32_t full_x, full_y, full_width, full_height;  /* display window */
+    int64_t xstride, ystride; /* bytes: pixel_stride(), scanline_stride() */
+    int32_t memspace;         /* enum b2r_memspace */
+    int32_t device;           /* CUDA ordinal when memspace == DEVICE */
+} b2r_image;
+
+/* ROI, src/include/OpenImageIO/imageio.h:93-108 (z dropped: no volumes). */
+typedef struct b2r_roi {
+    int32_t xbegin, xend, ybegin, yend, chbegin, chend;
+} b2r_roi;
+
+enum b2r_path {
+    B2R_PATH_AUTO  = 0, /* fused two-pass kernel when eligible, else exact */
+    B2R_PATH_EXACT = 1, /* single-pass kernel in the reference's tap order */
+    B2R_PATH_FUSED = 2  /* fail (B2R_ERR_UNSUPPORTED) if not eligible */
+};
+
+typedef struct b2r_options {
+    int32_t device;    /* CUDA ordinal for host-memory calls (default 0) */
+    int32_t path;      /* enum b2r_path */
+    void* cuda_stream; /* cudaStream_t; NULL = default stream */
+    int32_t reserved[4];
+} b2r_options;
+
+/* Filled on request: what ran, for tests and benchmarks. */
+typedef struct b2r_report {
+    int32_t path_used;       /* B2R_PATH_EXACT or B2R_PATH_FUSED */
+    int32_t kernels_launched;
+    int32_t xtaps, ytaps;    /* reference tap counts 2*radi+1, 2*radj+1 */
+    int32_t fused_vmode;     /* ring size K (>0) or 0 = gather */
+    int32_t fused_htaps;
+    int64_t h2d_bytes, d2h_bytes;
+    float kernel_ms;         /* CUDA-event time of the kernels, host calls only */
+    int32_t nonfinite_redo;  /* 1 if the exact kernel re-did the image */
+} b2r_report;
+
+/* ---- library ---------------------------------------------------------- */
+B2R_API const char* b2r_version(void);
+/* Number of usable CUDA devices (0 = none; compute calls will fail). */
+B2R_API int b2r_device_count(void);
+
+/* ---- Filter1D / Filter2D by name --------------------------------------
+ * Replaces the statics of src/include/OpenImageIO/filter.h:59-78,130-152 as
+ * implemented in src/libutil/filter.cpp:841-1047.  Host arithmetic, float32,
+ * identical expression order to the reference. */
+B2R_API int b2r_filter_count(int dim /*1 or 2*/);
+/* FilterDesc (filter.h:19-27).  Returns 0, or B2R_ERR_INVALID. */
+B2R_API int b2r_filter_desc(int dim, int index, const char** name,
+                            float* width, int* fixedwidth, int* scalable,
+                            int* separable);
+/* Opaque filter handles: Filter2D::create / destroy (filter.cpp:1000-1047). */
+typedef struct b2r_filter2d b2r_filter2d;
+typedef struct b2r_filter1d b2r_filter1d;
+B2R_API b2r_filter2d* b2r_filter2d_create(const char* name, float width,
+                                          float height);
+B2R_API void b2r_filter2d_destroy(b2r_filter2d* f);
+B2R_API float b2r_filter2d_width(const b2r_filter2d* f);
+B2R_API float b2r_filter2d_height(const b2r_filter2d* f);
+B2R_API int b2r_filter2d_separable(const b2r_filter2d* f);
+B2R_API const char* b2r_filter2d_name(const b2r_filter2d* f);
+B2R_API float b2r_filter2d_eval(const b2r_filter2d* f, float x, float y);
+B2R_API float b2r_filter2d_xfilt(const b2r_filter2d* f, float x);
+B2R_API float b2r_filter2d_yfilt(const b2r_filter2d* f, float y);
+B2R_API b2r_filter1d* b2r_filter1d_create(const char* name, float width);
+B2R_API void b2r_filter1d_destroy(b2r_filter1d* f);
+B2R_API float b2r_filter1d_width(const b2r_filter1d* f);
+B2R_API const char* b2r_filter1d_name(const b2r_filter1d* f);
+B2R_API float b2r_filter1d_eval(const b2r_filter1d* f, float x);
+
+/* ---- resize ----------------------------------------------------------- */
+/* Replaces ImageBufAlgo::resize(dst, src, KWArgs{filtername, filterwidth},
+ * roi, nthreads) from the point after IBAprep:
+ * src/libOpenImageIO/imagebufalgo_xform.cpp:885-917 (get_resize_filter
+ * :830-860 + the OIIO_DISPATCH_COMMON_TYPES2 call into resize_<D,S> :595-826).
+ * filtername NULL or "" -> lanczos3 when both ratios <= 1, else
+ * blackman-harris; filterwidth <= 0 -> FilterDesc.width * max(1, ratio).
+ * roi NULL -> dst's data window; otherwise intersected with it. */
+B2R_API int b2r_resize(const b2r_image* dst, const b2r_image* src,
+                       const char* filtername, float filterwidth,
+                       const b2r_roi* roi, const b2r_options* opt,
+                       b2r_report* report, char* err, size_t errlen);
+
+/* Same, with a caller-supplied filter: the KWArgs "filterptr" form
+ * (xform.cpp:888, get_filterptr_option :456-465).  The filter is borrowed. */
+B2R_API int b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
+                              const b2r_filter2d* filter, const b2r_roi* roi,
+                              const b2r_options* opt, b2r_report* report,
+                              char* err, size_t errlen);
+
+/* ---- resample --------------------------------------------------------- */
+/* Replaces resample_<D,S> (xform.cpp:1663-1687 and the kernels it picks,
+ * :1107-1186, :1379-1493): interpolate=0 nearest, else bilinear. */
+B2R_API int b2r_resample(const b2r_image* dst, const b2r_image* src,
+                         int interpolate, const b2r_roi* roi,
+                         const b2r_options* opt, b2r_report* report, char* err,
+                         size_t errlen);
+
+/* ---- fit -------------------------------------------------------------- */
+/* The integer geometry of ImageBufAlgo::fit (xform.cpp:962-997): for a
+ * source display window sw x sh fitted into fw x fh with fillmode
+ * "letterbox" | "width" | "height", the size to resize to and the offset of
+ * the result's data window.  The resize itself is b2r_resize. */
+B2R_API void b2r_fit_geometry(int src_full_width, int src_full_height,
+                              int fit_width, int fit_height,
+                              const char* fillmode, int* resize_width,
+                              int* resize_height, int* xoffset, int* yoffset);
+
+/* ---- device-resident MIP chain ---------------------------------------- */
+/* Replaces the level loop of write_mipmap,
+ * src/libOpenImageIO/maketexture.cpp:823-986: each level is computed on the
+ * device from the previous one (no host round trip), float32 pixels
+ * (maketx:forcefloat), windows zeroed per level (:848-879).
+ * filtername "box" takes the resize_block path (:881-887 -> :141-334), any
+ * other name the resize path with setup_filter's width rule (:38-66).
+ * clamp_half != 0 clamps each level to +-HALF_MAX and, like
+ * ImageBufAlgo::clamp(..., clampalpha01=true), the alpha channel
+ * (alpha_channel >= 0) to [0,1] (:943-945). */
+typedef struct b2r_mipchain b2r_mipchain;
+/* level0: float32 image (host or device).  The chain copies/adopts it on
+ * `device` and computes every level down to 1x1. */
+B2R_API int b2r_mipchain_create(b2r_mipchain** chain, const b2r_image* level0,
+                                const char* filtername, int clamp_half,
+                                int alpha_channel, const b2r_options* opt,
+                                char* err, size_t errlen);
+B2R_API int b2r_mipchain_nlevels(const b2r_mipchain* chain);
+/* Dimensions and device pointer of a level (level 0 = the input). */
+B2R_API int b2r_mipchain_level(const b2r_mipchain* chain, int level,
+                               int* width, int* height, void** device_pixels);
+/* Copy a finished level into host (or device) memory described by `out`
+ * (float32, same nchannels).  Synchronous. */
+B2R_API int b2r_mipchain_download(const b2r_mipchain* chain, int level,
+                                  const b2r_image* out, char* err,
+                                  size_t errlen);
+/* Device time of the level loop (CUDA events), ms. */
+B2R_API float b2r_mipchain_kernel_ms(const b2r_mipchain* chain);
+B2R_API void b2r_mipchain_destroy(b2r_mipchain* chain);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2R_H */

@@ -1,0 +1,678 @@
+"""openimageio_b200 -- B200-native filtered resampling behind OpenImageIO's API.
+
+Host-side mirror of the reference's Python surface for ONE path
+(`OpenImageIO.ImageBufAlgo.resize / fit / resample`, `Filter2D` by name, the
+maketx MIP loop), forwarding to the C ABI in `libb2r.so` (include/b2r.h), which
+launches hand-written sm_100a CUDA kernels.  There is no CPU fallback: without
+the built extension or without a GPU every compute call raises / returns an
+error.
+
+Reference interfaces mirrored (paths in the OpenImageIO tree):
+  src/python/py_imagebufalgo.cpp:1470-1560   IBA_resize / IBA_fit / IBA_resample
+  src/include/OpenImageIO/imagebufalgo.h:667-762
+  src/libOpenImageIO/imagebufalgo.cpp:64-281  IBAprep (ROI / dst allocation)
+  src/include/OpenImageIO/imageio.h:93-230    ROI
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["ROI", "ImageSpec", "ImageBuf", "ImageBufAlgo", "Filter2D",
+           "MipChain", "lib", "get_string_attribute", "B2RError"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libb2r.so")
+
+UINT8, UINT16, HALF, FLOAT = 2, 4, 10, 11
+_NAME2BT = {"uint8": UINT8, "uint16": UINT16, "half": HALF, "float": FLOAT}
+_BT2NP = {UINT8: np.uint8, UINT16: np.uint16, HALF: np.float16, FLOAT: np.float32}
+_NP2BT = {np.dtype(v): k for k, v in _BT2NP.items()}
+
+PATH_AUTO, PATH_EXACT, PATH_FUSED = 0, 1, 2
+MEM_AUTO, MEM_HOST, MEM_DEVICE = 0, 1, 2
+
+
+class B2RError(RuntimeError):
+    pass
+
+
+class _Image(C.Structure):
+    _fields_ = [("pixels", C.c_void_p), ("basetype", C.c_int32),
+                ("nchannels", C.c_int32),
+                ("x", C.c_int32), ("y", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32),
+                ("full_x", C.c_int32), ("full_y", C.c_int32),
+                ("full_width", C.c_int32), ("full_height", C.c_int32),
+                ("xstride", C.c_int64), ("ystride", C.c_int64),
+                ("memspace", C.c_int32), ("device", C.c_int32)]
+
+
+class _Roi(C.Structure):
+    _fields_ = [("xbegin", C.c_int32), ("xend", C.c_int32),
+                ("ybegin", C.c_int32), ("yend", C.c_int32),
+                ("chbegin", C.c_int32), ("chend", C.c_int32)]
+
+
+class _Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("path", C.c_int32),
+                ("cuda_stream", C.c_void_p), ("reserved", C.c_int32 * 4)]
+
+
+class Report(C.Structure):
+    _fields_ = [("path_used", C.c_int32), ("kernels_launched", C.c_int32),
+                ("xtaps", C.c_int32), ("ytaps", C.c_int32),
+                ("fused_vmode", C.c_int32), ("fused_htaps", C.c_int32),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_ms", C.c_float), ("nonfinite_redo", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2r.so (built in-tree by __graft_entry__.build / csrc/Makefile).
+    Fails loudly when the extension is missing: there is no other path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        raise B2RError(
+            "openimageio_b200: %s not built (run `python -c 'import "
+            "__graft_entry__ as g; g.build()'` or `make -C "
+            "openimageio_b200/csrc`); there is no CPU fallback" % _LIBPATH)
+    L = C.CDLL(_LIBPATH)
+    L.b2r_version.restype = C.c_char_p
+    L.b2r_filter_desc.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_char_p),
+                                  C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.b2r_filter2d_create.restype = C.c_void_p
+    L.b2r_filter2d_create.argtypes = [C.c_char_p, C.c_float, C.c_float]
+    L.b2r_filter2d_destroy.argtypes = [C.c_void_p]
+    for n in ("width", "height"):
+        f = getattr(L, "b2r_filter2d_" + n)
+        f.restype = C.c_float
+        f.argtypes = [C.c_void_p]
+    L.b2r_filter2d_separable.argtypes = [C.c_void_p]
+    L.b2r_filter2d_name.restype = C.c_char_p
+    L.b2r_filter2d_name.argtypes = [C.c_void_p]
+    L.b2r_filter2d_eval.restype = C.c_float
+    L.b2r_filter2d_eval.argtypes = [C.c_void_p, C.c_float, C.c_float]
+    for n in ("xfilt", "yfilt"):
+        f = getattr(L, "b2r_filter2d_" + n)
+        f.restype = C.c_float
+        f.argtypes = [C.c_void_p, C.c_float]
+    L.b2r_filter1d_create.restype = C.c_void_p
+    L.b2r_filter1d_create.argtypes = [C.c_char_p, C.c_float]
+    L.b2r_filter1d_destroy.argtypes = [C.c_void_p]
+    L.b2r_filter1d_width.restype = C.c_float
+    L.b2r_filter1d_width.argtypes = [C.c_void_p]
+    L.b2r_filter1d_name.restype = C.c_char_p
+    L.b2r_filter1d_name.argtypes = [C.c_void_p]
+    L.b2r_filter1d_eval.restype = C.c_float
+    L.b2r_filter1d_eval.argtypes = [C.c_void_p, C.c_float]
+    L.b2r_resize.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_char_p,
+                             C.c_float, C.POINTER(_Roi), C.POINTER(_Options),
+                             C.POINTER(Report), C.c_char_p, C.c_size_t]
+    L.b2r_resize_filter.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
+                                    C.c_void_p, C.POINTER(_Roi),
+                                    C.POINTER(_Options), C.POINTER(Report),
+                                    C.c_char_p, C.c_size_t]
+    L.b2r_resample.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int,
+                               C.POINTER(_Roi), C.POINTER(_Options),
+                               C.POINTER(Report), C.c_char_p, C.c_size_t]
+    L.b2r_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
+        [C.POINTER(C.c_int)] * 4
+    L.b2r_mipchain_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
+                                      C.c_char_p, C.c_int, C.c_int,
+                                      C.POINTER(_Options), C.c_char_p,
+                                      C.c_size_t]
+    L.b2r_mipchain_nlevels.argtypes = [C.c_void_p]
+    L.b2r_mipchain_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.b2r_mipchain_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Image),
+                                        C.c_char_p, C.c_size_t]
+    L.b2r_mipchain_kernel_ms.restype = C.c_float
+    L.b2r_mipchain_kernel_ms.argtypes = [C.c_void_p]
+    L.b2r_mipchain_destroy.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def get_string_attribute(name):
+    """OIIO.get_string_attribute: only "filter_list" is on this path
+    (imageio.cpp builds it from Filter2D::get_filterdesc)."""
+    if name == "filter_list":
+        L = lib()
+        names = []
+        for i in range(L.b2r_filter_count(2)):
+            nm = C.c_char_p()
+            L.b2r_filter_desc(2, i, C.byref(nm), None, None, None, None)
+            names.append(nm.value.decode())
+        return ";".join(names)
+    if name == "library_list":
+        return "b2r:" + lib().b2r_version().decode()
+    return ""
+
+
+# --------------------------------------------------------------------------
+class ROI:
+    """imageio.h:93-230 (z kept for signature compatibility; depth 1 only)."""
+    __slots__ = ("xbegin", "xend", "ybegin", "yend", "zbegin", "zend",
+                 "chbegin", "chend")
+    All = None  # set below
+
+    def __init__(self, xbegin=-(2**31), xend=0, ybegin=0, yend=0, zbegin=0,
+                 zend=1, chbegin=0, chend=10000):
+        self.xbegin, self.xend = xbegin, xend
+        self.ybegin, self.yend = ybegin, yend
+        self.zbegin, self.zend = zbegin, zend
+        self.chbegin, self.chend = chbegin, chend
+
+    @property
+    def defined(self):
+        return self.xbegin != -(2**31)
+
+    @property
+    def width(self):
+        return self.xend - self.xbegin
+
+    @property
+    def height(self):
+        return self.yend - self.ybegin
+
+    @property
+    def nchannels(self):
+        return self.chend - self.chbegin
+
+    def copy(self):
+        return ROI(self.xbegin, self.xend, self.ybegin, self.yend, self.zbegin,
+                   self.zend, self.chbegin, self.chend)
+
+    def __repr__(self):
+        if not self.defined:
+            return "ROI.All"
+        return "ROI(%d,%d,%d,%d,ch %d-%d)" % (self.xbegin, self.xend,
+                                               self.ybegin, self.yend,
+                                               self.chbegin, self.chend)
+
+
+ROI.All = ROI()
+
+
+class ImageSpec:
+    """The subset of ImageSpec the resize path reads (imageio.h: x, y, width,
+    height, full_*, nchannels, format, alpha_channel)."""
+
+    def __init__(self, width=0, height=0, nchannels=0, format="float"):
+        self.x = self.y = 0
+        self.width, self.height = width, height
+        self.full_x = self.full_y = 0
+        self.full_width, self.full_height = width, height
+        self.nchannels = nchannels
+        self.depth = 1
+        self.deep = False
+        self.alpha_channel = 3 if nchannels == 4 else -1
+        self.set_format(format)
+
+    def set_format(self, format):
+        if isinstance(format, str):
+            if format not in _NAME2BT:
+                raise ValueError("unsupported format " + format)
+            self.basetype = _NAME2BT[format]
+        elif isinstance(format, int):
+            self.basetype = format
+        else:
+            self.basetype = _NP2BT[np.dtype(format)]
+
+    @property
+    def format(self):
+        return {v: k for k, v in _NAME2BT.items()}[self.basetype]
+
+    def copy(self):
+        s = ImageSpec(self.width, self.height, self.nchannels, self.basetype)
+        for k in ("x", "y", "full_x", "full_y", "full_width", "full_height",
+                  "depth", "deep", "alpha_channel"):
+            setattr(s, k, getattr(self, k))
+        return s
+
+    @property
+    def roi(self):
+        return ROI(self.x, self.x + self.width, self.y, self.y + self.height,
+                   0, 1, 0, self.nchannels)
+
+    @property
+    def roi_full(self):
+        return ROI(self.full_x, self.full_x + self.full_width, self.full_y,
+                   self.full_y + self.full_height, 0, 1, 0, self.nchannels)
+
+    def set_roi(self, r):
+        self.x, self.y = r.xbegin, r.ybegin
+        self.width, self.height = r.width, r.height
+
+    def set_roi_full(self, r):
+        self.full_x, self.full_y = r.xbegin, r.ybegin
+        self.full_width, self.full_height = r.width, r.height
+
+
+def _is_torch(t):
+    return type(t).__module__.startswith("torch")
+
+
+class ImageBuf:
+    """Pixel container: a spec plus an (H, W, C) array that is either a numpy
+    array (host) or a torch CUDA tensor (device-resident, HBM).  Only what the
+    resize path needs from src/include/OpenImageIO/imagebuf.h."""
+
+    def __init__(self, spec_or_pixels=None, spec=None):
+        self._err = ""
+        self.pixels = None
+        self.spec_ = None
+        if isinstance(spec_or_pixels, ImageSpec):
+            self.reset(spec_or_pixels)
+        elif spec_or_pixels is not None:
+            px = spec_or_pixels
+            if px.ndim == 2:
+                px = px[:, :, None]
+            h, w, c = px.shape
+            if spec is None:
+                dt = (px.dtype if not _is_torch(px)
+                      else np.dtype(str(px.dtype).replace("torch.", "")))
+                spec = ImageSpec(w, h, c, dt)
+            assert (spec.width, spec.height, spec.nchannels) == (w, h, c)
+            self.spec_ = spec
+            self.pixels = px
+
+    # -- reference-style accessors ----------------------------------------
+    @property
+    def initialized(self):
+        return self.pixels is not None
+
+    def spec(self):
+        return self.spec_
+
+    def specmod(self):
+        return self.spec_
+
+    @property
+    def nchannels(self):
+        return self.spec_.nchannels
+
+    @property
+    def roi(self):
+        return self.spec_.roi
+
+    @property
+    def roi_full(self):
+        return self.spec_.roi_full
+
+    @property
+    def has_error(self):
+        return bool(self._err)
+
+    def geterror(self, clear=True):
+        e = self._err
+        if clear:
+            self._err = ""
+        return e
+
+    def errorfmt(self, msg):
+        self._err = msg
+
+    def reset(self, spec, device=None):
+        self.spec_ = spec.copy()
+        shape = (spec.height, spec.width, spec.nchannels)
+        if device is None:
+            self.pixels = np.zeros(shape, _BT2NP[spec.basetype])
+        else:
+            import torch
+            tdt = {UINT8: torch.uint8, UINT16: torch.uint16,
+                   HALF: torch.float16, FLOAT: torch.float32}[spec.basetype]
+            self.pixels = torch.zeros(shape, dtype=tdt, device=device)
+
+    @property
+    def on_device(self):
+        return self.pixels is not None and _is_torch(self.pixels) \
+            and self.pixels.is_cuda
+
+    def get_pixels(self):
+        """Host numpy copy of the pixels."""
+        if _is_torch(self.pixels):
+            t = self.pixels
+            if str(t.dtype) == "torch.uint16":
+                return t.view(__import__("torch").int16).cpu().numpy().view(np.uint16)
+            return t.cpu().numpy()
+        return self.pixels
+
+    def copy(self, src):
+        self.spec_ = src.spec_.copy()
+        self.pixels = (src.pixels.clone() if _is_torch(src.pixels)
+                       else src.pixels.copy())
+        return True
+
+    # -- C view --------------------------------------------------------------
+    def _c(self):
+        s = self.spec_
+        im = _Image()
+        px = self.pixels
+        if _is_torch(px):
+            im.pixels = px.data_ptr()
+            es = px.element_size()
+            st = px.stride()
+            im.ystride, im.xstride = st[0] * es, st[1] * es
+            if px.is_cuda:
+                im.memspace, im.device = MEM_DEVICE, px.device.index or 0
+            else:
+                im.memspace = MEM_HOST
+        else:
+            im.pixels = px.ctypes.data
+            im.ystride, im.xstride = px.strides[0], px.strides[1]
+            im.memspace = MEM_HOST
+        im.basetype, im.nchannels = s.basetype, s.nchannels
+        im.x, im.y, im.width, im.height = s.x, s.y, s.width, s.height
+        im.full_x, im.full_y = s.full_x, s.full_y
+        im.full_width, im.full_height = s.full_width, s.full_height
+        return im
+
+
+class Filter2D:
+    """Filter2D by name (src/include/OpenImageIO/filter.h:88-156)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def create(name, width, height=0.0):
+        h = lib().b2r_filter2d_create(name.encode(), float(width), float(height))
+        return Filter2D(h) if h else None
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2r_filter2d_destroy(self._h)
+        except Exception:
+            pass
+
+    def width(self):
+        return lib().b2r_filter2d_width(self._h)
+
+    def height(self):
+        return lib().b2r_filter2d_height(self._h)
+
+    def separable(self):
+        return bool(lib().b2r_filter2d_separable(self._h))
+
+    def name(self):
+        return lib().b2r_filter2d_name(self._h).decode()
+
+    def __call__(self, x, y):
+        return lib().b2r_filter2d_eval(self._h, float(x), float(y))
+
+    def xfilt(self, x):
+        return lib().b2r_filter2d_xfilt(self._h, float(x))
+
+    def yfilt(self, y):
+        return lib().b2r_filter2d_yfilt(self._h, float(y))
+
+
+# --------------------------------------------------------------------------
+def _ibaprep(roi, dst, src):
+    """IBAprep with IBAprep_NO_SUPPORT_VOLUME | IBAprep_NO_COPY_ROI_FULL
+    (imagebufalgo.cpp:64-348), restricted to one input image."""
+    if src is None or not src.initialized:
+        dst.errorfmt("Uninitialized input image")
+        return None
+    roi = roi.copy() if roi is not None and roi.defined else None
+    if dst.initialized:
+        d = dst.spec_.roi
+        if roi is not None:
+            roi = ROI(max(roi.xbegin, d.xbegin), min(roi.xend, d.xend),
+                      max(roi.ybegin, d.ybegin), min(roi.yend, d.yend), 0, 1,
+                      max(roi.chbegin, 0), min(roi.chend, d.chend))
+        else:
+            roi = d
+    else:
+        full = None
+        if roi is None:
+            roi, full = src.roi, src.roi_full
+        else:
+            roi.chend = min(roi.chend, src.nchannels)
+        spec = src.spec_.copy()
+        spec.set_roi(roi)
+        spec.set_roi_full(full if full is not None else roi)
+        dev = src.pixels.device if src.on_device else None
+        dst.reset(spec, device=dev)
+    if dst.spec_.depth > 1 or src.spec_.depth > 1:
+        dst.errorfmt("volumes not supported")
+        return None
+    if dst.spec_.deep or src.spec_.deep:
+        dst.errorfmt("deep images not supported")
+        return None
+    roi.chend = min(roi.chend, max(dst.nchannels, src.nchannels))
+    return roi
+
+
+def _options(device=0, path=PATH_AUTO, stream=None):
+    o = _Options()
+    o.device = device
+    o.path = path
+    o.cuda_stream = stream
+    return o
+
+
+def _current_stream(buf):
+    if buf.on_device:
+        import torch
+        return torch.cuda.current_stream(buf.pixels.device).cuda_stream
+    return None
+
+
+class _IBA:
+    """ImageBufAlgo functions on this path.  Two call shapes, like the
+    reference's Python binding: f(dst, src, ...) -> bool, f(src, ...) ->
+    ImageBuf (py_imagebufalgo.cpp:1470-1560)."""
+
+    last_report = None
+
+    # ---- resize -----------------------------------------------------------
+    def resize(self, *args, filtername="", filterwidth=0.0, roi=None,
+               nthreads=0, filterptr=None, path=PATH_AUTO, device=0):
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:  # positional filtername / filterwidth
+            filtername = rest[0]
+            if len(rest) > 1:
+                filterwidth = rest[1]
+        if len(bufs) == 2:
+            return self._resize(bufs[0], bufs[1], filtername, filterwidth, roi,
+                                filterptr, path, device)
+        result = ImageBuf()
+        ok = self._resize(result, bufs[0], filtername, filterwidth, roi,
+                          filterptr, path, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::resize() error")
+        return result
+
+    def _resize(self, dst, src, filtername, filterwidth, roi, filterptr, path,
+                device):
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        L = lib()
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        stream = _current_stream(dst) or _current_stream(src)
+        o = _options(device, path, stream)
+        rep = Report()
+        err = C.create_string_buffer(512)
+        want_report = not (dst.on_device and src.on_device)
+        if filterptr is not None:
+            rc = L.b2r_resize_filter(C.byref(d), C.byref(s), filterptr._h,
+                                     C.byref(r), C.byref(o),
+                                     C.byref(rep) if want_report else None,
+                                     err, 512)
+        else:
+            rc = L.b2r_resize(C.byref(d), C.byref(s),
+                              (filtername or "").encode(), float(filterwidth),
+                              C.byref(r), C.byref(o),
+                              C.byref(rep) if want_report else None, err, 512)
+        self.last_report = rep if want_report else None
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    # ---- resample ---------------------------------------------------------
+    def resample(self, *args, interpolate=True, roi=None, nthreads=0, device=0):
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:
+            interpolate = bool(rest[0])
+        if len(bufs) == 2:
+            return self._resample(bufs[0], bufs[1], interpolate, roi, device)
+        result = ImageBuf()
+        ok = self._resample(result, bufs[0], interpolate, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::resample() error")
+        return result
+
+    def _resample(self, dst, src, interpolate, roi, device):
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        L = lib()
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        stream = _current_stream(dst) or _current_stream(src)
+        o = _options(device, PATH_AUTO, stream)
+        err = C.create_string_buffer(512)
+        rc = L.b2r_resample(C.byref(d), C.byref(s), 1 if interpolate else 0,
+                            C.byref(r), C.byref(o), None, err, 512)
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    # ---- fit --------------------------------------------------------------
+    def fit(self, *args, filtername="", filterwidth=0.0, fillmode="letterbox",
+            exact=False, roi=None, nthreads=0, device=0):
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:
+            filtername = rest[0]
+            if len(rest) > 1:
+                filterwidth = rest[1]
+        if len(bufs) == 2:
+            return self._fit(bufs[0], bufs[1], filtername, filterwidth, fillmode,
+                             exact, roi, device)
+        result = ImageBuf()
+        ok = self._fit(result, bufs[0], filtername, filterwidth, fillmode, exact,
+                       roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::fit() error")
+        return result
+
+    def _fit(self, dst, src, filtername, filterwidth, fillmode, exact, roi,
+             device):
+        # imagebufalgo_xform.cpp:933-1062
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        if exact:
+            dst.errorfmt("fit: exact=1 takes the warp path, which is outside "
+                         "the B200 resize path")
+            return False
+        sspec = src.spec_
+        L = lib()
+        rw, rh, xo, yo = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.b2r_fit_geometry(sspec.full_width, sspec.full_height, roi.width,
+                           roi.height, fillmode.encode(), C.byref(rw),
+                           C.byref(rh), C.byref(xo), C.byref(yo))
+        fit_x, fit_y = roi.xbegin, roi.ybegin
+        ok = True
+        # the filter is chosen from the RESIZE ratios (:1005-1015)
+        if (rw.value != sspec.full_width or rh.value != sspec.full_height
+                or fit_x != sspec.full_x or fit_y != sspec.full_y):
+            resizeroi = ROI(fit_x, fit_x + rw.value, fit_y, fit_y + rh.value,
+                            0, 1, 0, sspec.nchannels)
+            newspec = sspec.copy()
+            newspec.set_roi(resizeroi)
+            newspec.set_roi_full(resizeroi)
+            dev = src.pixels.device if src.on_device else None
+            dst.reset(newspec, device=dev)
+            ok = self._resize(dst, src, filtername, filterwidth, resizeroi,
+                              None, PATH_AUTO, device)
+        else:
+            ok = dst.copy(src)
+        sp = dst.spec_
+        sp.full_width, sp.full_height = roi.width, roi.height
+        sp.full_x, sp.full_y = fit_x, fit_y
+        sp.x, sp.y = xo.value, yo.value
+        return ok
+
+
+ImageBufAlgo = _IBA()
+
+
+class MipChain:
+    """Device-resident MIP pyramid: the level loop of write_mipmap
+    (src/libOpenImageIO/maketexture.cpp:823-986) without host round trips."""
+
+    def __init__(self, level0, filtername="box", clamp_half=False, device=0):
+        if not isinstance(level0, ImageBuf):
+            level0 = ImageBuf(level0)
+        L = lib()
+        h = C.c_void_p()
+        im = level0._c()
+        o = _options(device, PATH_AUTO, _current_stream(level0))
+        err = C.create_string_buffer(512)
+        rc = L.b2r_mipchain_create(C.byref(h), C.byref(im), filtername.encode(),
+                                   1 if clamp_half else 0,
+                                   level0.spec_.alpha_channel, C.byref(o), err,
+                                   512)
+        if rc:
+            raise B2RError(err.value.decode())
+        self._h = h
+        self._keep = level0  # level 0 may be adopted, keep it alive
+        self.nchannels = level0.nchannels
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2r_mipchain_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def nlevels(self):
+        return lib().b2r_mipchain_nlevels(self._h)
+
+    @property
+    def kernel_ms(self):
+        return lib().b2r_mipchain_kernel_ms(self._h)
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        lib().b2r_mipchain_level(self._h, level, C.byref(w), C.byref(h), None)
+        return w.value, h.value
+
+    def level_ptr(self, level):
+        p = C.c_void_p()
+        lib().b2r_mipchain_level(self._h, level, None, None, C.byref(p))
+        return p.value
+
+    def download(self, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w, self.nchannels), np.float32)
+        ib = ImageBuf(out)
+        im = ib._c()
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_mipchain_download(self._h, level, C.byref(im), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        return out

@@ -1,0 +1,1295 @@
+// b2r_api.cpp -- the C ABI (include/b2r.h): argument checks in the reference's
+// words, host<->device staging, plan cache, kernel launches.
+//
+// Mirrors, for the resize path, what ImageBufAlgo::resize does after IBAprep:
+// get_resize_filter (imagebufalgo_xform.cpp:830-860), the (dst,src) type-pair
+// rule of OIIO_DISPATCH_COMMON_TYPES2 (imagebufalgo_util.h:463-552) and the
+// call into resize_<D,S> (:595-826) -- here two CUDA kernels instead.
+#include "b2r.h"
+
+#include "axis_plan.h"
+#include "fused_plan.h"
+#include "kernels.h"
+#include "recon_filter.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <list>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b2r;
+
+struct b2r_filter2d {
+    Filter2D* f;
+};
+struct b2r_filter1d {
+    Filter1D* f;
+};
+
+namespace {
+
+void
+set_err(char* err, size_t errlen, const char* fmt, ...)
+{
+    if (!err || !errlen)
+        return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, errlen, fmt, ap);
+    va_end(ap);
+}
+
+#define CUDA_TRY(call)                                                        \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) {                                              \
+            set_err(err, errlen, "CUDA error: %s (%s)", cudaGetErrorString(e_), \
+                    #call);                                                   \
+            return B2R_ERR_CUDA;                                              \
+        }                                                                     \
+    } while (0)
+
+bool
+valid_basetype(int bt)
+{
+    return bt == B2R_UINT8 || bt == B2R_UINT16 || bt == B2R_HALF
+           || bt == B2R_FLOAT;
+}
+
+// OIIO_DISPATCH_COMMON_TYPES2: the ten native (dst,src) pairs.
+bool
+legal_pair(int d, int s)
+{
+    if (d == B2R_FLOAT)
+        return valid_basetype(s);
+    return s == B2R_FLOAT || s == d;
+}
+
+int
+device_count_cached()
+{
+    static int n = -1;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess)
+            c = 0;
+        cudaGetLastError();
+        n = c;
+    });
+    return n;
+}
+
+struct DeviceInfo {
+    int sms = 0;
+    bool pool_ready = false;
+};
+DeviceInfo&
+device_info(int dev)
+{
+    static DeviceInfo info[64];
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    DeviceInfo& d = info[dev & 63];
+    if (!d.sms) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ull;  // keep freed blocks cached
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            d.pool_ready = true;
+        }
+    }
+    return d;
+}
+
+int
+memspace_of(const b2r_image* im, int* device)
+{
+    if (im->memspace == B2R_MEM_HOST)
+        return B2R_MEM_HOST;
+    if (im->memspace == B2R_MEM_DEVICE) {
+        *device = im->device;
+        return B2R_MEM_DEVICE;
+    }
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, im->pixels) == cudaSuccess
+        && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) {
+        *device = a.device;
+        return B2R_MEM_DEVICE;
+    }
+    cudaGetLastError();
+    return B2R_MEM_HOST;
+}
+
+DevImage
+to_dev(const b2r_image& im, void* pixels)
+{
+    DevImage d;
+    d.pixels      = pixels;
+    d.basetype    = im.basetype;
+    d.nchannels   = im.nchannels;
+    d.x           = im.x;
+    d.y           = im.y;
+    d.width       = im.width;
+    d.height      = im.height;
+    d.full_x      = im.full_x;
+    d.full_y      = im.full_y;
+    d.full_width  = im.full_width;
+    d.full_height = im.full_height;
+    d.xstride     = im.xstride;
+    d.ystride     = im.ystride;
+    return d;
+}
+
+int
+check_image(const b2r_image* im, bool is_src, char* err, size_t errlen)
+{
+    if (!im || !im->pixels || im->width <= 0 || im->height <= 0
+        || im->nchannels <= 0) {
+        set_err(err, errlen,
+                is_src ? "Uninitialized input image"
+                       : "Uninitialized destination image");
+        return B2R_ERR_INVALID;
+    }
+    if (!valid_basetype(im->basetype)) {
+        set_err(err, errlen, "unsupported pixel data type %d", im->basetype);
+        return B2R_ERR_TYPES;
+    }
+    if (im->full_width <= 0 || im->full_height <= 0) {
+        set_err(err, errlen, "image has an empty display window");
+        return B2R_ERR_INVALID;
+    }
+    return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------
+// A device blob holding every table of one resize shape.  Cached (LRU) so a
+// sequence of frames with the same geometry uploads once
+// ("precomputed on the host ... uploaded once per (src,dst,filter) shape").
+// ---------------------------------------------------------------------------
+struct PlanKey {
+    int device;
+    int g[16];
+    float fw, fh;
+    std::string fname;
+    int nch;
+    bool operator==(const PlanKey& o) const
+    {
+        return device == o.device && !memcmp(g, o.g, sizeof(g)) && fw == o.fw
+               && fh == o.fh && fname == o.fname && nch == o.nch;
+    }
+};
+
+struct DevicePlan {
+    PlanKey key;
+    int device = 0;
+    void* blob = nullptr;
+    // exact tables
+    int radi = 0, radj = 0, xtaps = 0, ytaps = 0;
+    float xratio = 1, yratio = 1;
+    const int* xcenter = nullptr;
+    const float* xw = nullptr;
+    const float* xwsum = nullptr;
+    const float* xfrac = nullptr;
+    const int* ycenter = nullptr;
+    const float* yw = nullptr;
+    const float* ywsum = nullptr;
+    const float* yfrac = nullptr;
+    // fused
+    bool fused = false;
+    FusedPlan fp;  // host copies of strips/bands kept for sizes only
+    const Strip* strips = nullptr;
+    const Band* bands = nullptr;
+    const int* hfirst = nullptr;
+    const float* hw = nullptr;
+    const float* vring = nullptr;
+    const int* vlast = nullptr;
+    const int* vfirst = nullptr;
+    const float* vw = nullptr;
+    ~DevicePlan()
+    {
+        if (blob) {
+            int cur = 0;
+            cudaGetDevice(&cur);
+            cudaSetDevice(device);
+            cudaFree(blob);
+            cudaSetDevice(cur);
+        }
+    }
+};
+
+std::mutex g_plan_mutex;
+std::list<std::shared_ptr<DevicePlan>> g_plans;  // most recent first
+const size_t kMaxPlans = 32;
+
+struct BlobBuilder {
+    std::vector<unsigned char> host;
+    size_t add(const void* p, size_t bytes)
+    {
+        size_t off = (host.size() + 255) & ~size_t(255);
+        host.resize(off + bytes);
+        if (bytes)
+            memcpy(host.data() + off, p, bytes);
+        return off;
+    }
+    template<class T> size_t add(const std::vector<T>& v)
+    {
+        return add(v.data(), v.size() * sizeof(T));
+    }
+};
+
+int
+get_plan(int device, const b2r_image& dst, const b2r_image& src,
+         const b2r_roi& roi, const Filter2D& filter, int nch, int cta_slots,
+         cudaStream_t stream, std::shared_ptr<DevicePlan>* out, char* err,
+         size_t errlen)
+{
+    PlanKey key;
+    key.device = device;
+    int g[16]  = { roi.xbegin, roi.xend, roi.ybegin, roi.yend,
+                   dst.full_x, dst.full_y, dst.full_width, dst.full_height,
+                   src.full_x, src.full_y, src.full_width, src.full_height,
+                   src.x, src.y, src.width, src.height };
+    memcpy(key.g, g, sizeof(g));
+    key.fw    = filter.width();
+    key.fh    = filter.height();
+    key.fname = std::string(filter.name());
+    key.nch   = nch;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
+            if ((*it)->key == key) {
+                *out = *it;
+                g_plans.splice(g_plans.begin(), g_plans, it);
+                return B2R_OK;
+            }
+        }
+    }
+    auto plan    = std::make_shared<DevicePlan>();
+    plan->key    = key;
+    plan->device = device;
+
+    AxisGeom gx { roi.xbegin, roi.xend, dst.full_x, dst.full_width, src.full_x,
+                  src.full_width, src.x, src.x + src.width };
+    AxisGeom gy { roi.ybegin, roi.yend, dst.full_y, dst.full_height, src.full_y,
+                  src.full_height, src.y, src.y + src.height };
+    AxisTaps tx = build_axis_taps(gx, filter, false);
+    AxisTaps ty = build_axis_taps(gy, filter, true);
+    plan->radi  = tx.rad;
+    plan->radj  = ty.rad;
+    plan->xtaps = tx.ntaps;
+    plan->ytaps = ty.ntaps;
+    plan->xratio = tx.ratio;
+    plan->yratio = ty.ratio;
+
+    BlobBuilder bb;
+    size_t o_xc = bb.add(tx.center), o_xw = bb.add(tx.w), o_xs = bb.add(tx.wsum),
+           o_xf = bb.add(tx.frac);
+    size_t o_yc = bb.add(ty.center), o_yw = bb.add(ty.w), o_ys = bb.add(ty.wsum),
+           o_yf = bb.add(ty.frac);
+
+    size_t o_strips = 0, o_bands = 0, o_hf = 0, o_hw = 0, o_vr = 0, o_vl = 0,
+           o_vf = 0, o_vw = 0;
+    if (filter.separable()) {
+        AxisGather ax, ay;
+        if (build_axis_gather(gx, tx, &ax) && build_axis_gather(gy, ty, &ay)
+            && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
+                          &plan->fp)
+            && fused_supported(nch, plan->fp.vk, plan->fp.ht)) {
+            plan->fused = true;
+            o_strips    = bb.add(plan->fp.strips);
+            o_bands     = bb.add(plan->fp.bands);
+            o_hf        = bb.add(plan->fp.hfirst);
+            o_hw        = bb.add(plan->fp.hw);
+            o_vr        = bb.add(plan->fp.vring);
+            o_vl        = bb.add(plan->fp.vlast);
+            o_vf        = bb.add(plan->fp.vfirst);
+            o_vw        = bb.add(plan->fp.vw);
+            // the big host tables are no longer needed
+            plan->fp.hw.clear();
+            plan->fp.hw.shrink_to_fit();
+            plan->fp.vring.clear();
+            plan->fp.vring.shrink_to_fit();
+        }
+    }
+    CUDA_TRY(cudaMalloc(&plan->blob, std::max<size_t>(bb.host.size(), 256)));
+    CUDA_TRY(cudaMemcpyAsync(plan->blob, bb.host.data(), bb.host.size(),
+                             cudaMemcpyHostToDevice, stream));
+    // the host blob is pageable: the copy has been staged when the call returns
+    unsigned char* base = (unsigned char*)plan->blob;
+    plan->xcenter = (const int*)(base + o_xc);
+    plan->xw      = (const float*)(base + o_xw);
+    plan->xwsum   = (const float*)(base + o_xs);
+    plan->xfrac   = (const float*)(base + o_xf);
+    plan->ycenter = (const int*)(base + o_yc);
+    plan->yw      = (const float*)(base + o_yw);
+    plan->ywsum   = (const float*)(base + o_ys);
+    plan->yfrac   = (const float*)(base + o_yf);
+    if (plan->fused) {
+        plan->strips = (const Strip*)(base + o_strips);
+        plan->bands  = (const Band*)(base + o_bands);
+        plan->hfirst = (const int*)(base + o_hf);
+        plan->hw     = (const float*)(base + o_hw);
+        plan->vring  = (const float*)(base + o_vr);
+        plan->vlast  = (const int*)(base + o_vl);
+        plan->vfirst = (const int*)(base + o_vf);
+        plan->vw     = (const float*)(base + o_vw);
+    }
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plans.push_front(plan);
+        while (g_plans.size() > kMaxPlans)
+            g_plans.pop_back();
+    }
+    *out = plan;
+    return B2R_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev)
+            cudaSetDevice(dev);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0)
+            cudaSetDevice(prev);
+    }
+};
+
+// Which source rows a dst ROI can touch (data-window rows, inclusive).
+void
+source_row_span(const DevicePlan& plan, const b2r_image& src, int roi_h,
+                const std::vector<int>& ycenter_host, int* r0, int* r1)
+{
+    (void)plan;
+    (void)roi_h;
+    (void)ycenter_host;
+    *r0 = 0;
+    *r1 = src.height - 1;
+}
+
+int
+resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
+            const Filter2D& filter, const b2r_roi* roi_in,
+            const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
+{
+    if (report)
+        memset(report, 0, sizeof(*report));
+    int rc = check_image(src_in, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst_in, false, err, errlen);
+    if (rc)
+        return rc;
+    const b2r_image& dst = *dst_in;
+    const b2r_image& src = *src_in;
+    if (!legal_pair(dst.basetype, src.basetype)) {
+        set_err(err, errlen,
+                "resize: (dst,src) pixel types (%d,%d) are not a native pair; "
+                "convert through float first",
+                dst.basetype, src.basetype);
+        return B2R_ERR_TYPES;
+    }
+    if (src.nchannels < dst.nchannels) {
+        set_err(err, errlen,
+                "resize: source has %d channels, destination %d",
+                src.nchannels, dst.nchannels);
+        return B2R_ERR_INVALID;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 resize path has no CPU "
+                "fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    // ROI: shrink-wrapped to dst's data window (IBAprep, imagebufalgo.cpp:105-111)
+    b2r_roi roi;
+    if (roi_in) {
+        roi        = *roi_in;
+        roi.xbegin = std::max(roi.xbegin, dst.x);
+        roi.xend   = std::min(roi.xend, dst.x + dst.width);
+        roi.ybegin = std::max(roi.ybegin, dst.y);
+        roi.yend   = std::min(roi.yend, dst.y + dst.height);
+    } else {
+        roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
+                        dst.nchannels };
+    }
+    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin)
+        return B2R_OK;
+    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+    const int nch = dst.nchannels;  // resize_ writes every dst channel (:603)
+    const int ses = basetype_size(src.basetype);
+    const int des = basetype_size(dst.basetype);
+
+    int sdev = opt ? opt->device : 0, ddev = sdev;
+    const int smem = memspace_of(&src, &sdev);
+    const int dmem = memspace_of(&dst, &ddev);
+    int device     = opt ? opt->device : 0;
+    if (smem == B2R_MEM_DEVICE)
+        device = sdev;
+    else if (dmem == B2R_MEM_DEVICE)
+        device = ddev;
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    DeviceInfo& di      = device_info(device);
+    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+    const int path      = opt ? opt->path : B2R_PATH_AUTO;
+
+    std::shared_ptr<DevicePlan> plan;
+    rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 2, stream, &plan,
+                  err, errlen);
+    if (rc)
+        return rc;
+
+    // ---- stage host images ------------------------------------------------
+    void* dsrc       = src.pixels;
+    void* ddst       = dst.pixels;
+    b2r_image srcd   = src;
+    b2r_image dstd   = dst;
+    size_t src_bytes = 0, dst_bytes = 0;
+    bool src_staged = false, dst_staged = false;
+    if (smem == B2R_MEM_HOST) {
+        if (src.xstride != (int64_t)src.nchannels * ses) {
+            set_err(err, errlen, "host source pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        size_t rowbytes = size_t(src.width) * src.xstride;
+        size_t pitch    = (rowbytes + 15) & ~size_t(15);
+        src_bytes       = pitch * src.height;
+        CUDA_TRY(cudaMallocAsync(&dsrc, src_bytes, stream));
+        src_staged = true;
+        CUDA_TRY(cudaMemcpy2DAsync(dsrc, pitch, src.pixels, src.ystride, rowbytes,
+                                   src.height, cudaMemcpyHostToDevice, stream));
+        srcd.ystride = (int64_t)pitch;
+        if (report)
+            report->h2d_bytes += (int64_t)rowbytes * src.height;
+    }
+    size_t dpitch = 0, drowbytes = 0;
+    if (dmem == B2R_MEM_HOST) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "host destination pixels must be contiguous in x");
+            if (src_staged)
+                cudaFreeAsync(dsrc, stream);
+            return B2R_ERR_UNSUPPORTED;
+        }
+        // stage only the ROI rectangle
+        drowbytes = size_t(roi_w) * dst.xstride;
+        dpitch    = (drowbytes + 15) & ~size_t(15);
+        dst_bytes = dpitch * roi_h;
+        CUDA_TRY(cudaMallocAsync(&ddst, dst_bytes, stream));
+        dst_staged   = true;
+        dstd.x       = roi.xbegin;
+        dstd.y       = roi.ybegin;
+        dstd.width   = roi_w;
+        dstd.height  = roi_h;
+        dstd.ystride = (int64_t)dpitch;
+    }
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const bool timed = report != nullptr;
+    if (timed) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+    }
+
+    // ---- launch -----------------------------------------------------------
+    DevImage D = to_dev(dstd, ddst);
+    DevImage S = to_dev(srcd, dsrc);
+    ExactParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.dst = D;
+    ep.src = S;
+    ep.roi_x0 = roi.xbegin;
+    ep.roi_x1 = roi.xend;
+    ep.roi_y0 = roi.ybegin;
+    ep.roi_y1 = roi.yend;
+    ep.nch    = nch;
+    ep.radi   = plan->radi;
+    ep.radj   = plan->radj;
+    ep.xtaps  = plan->xtaps;
+    ep.ytaps  = plan->ytaps;
+    ep.xratio = plan->xratio;
+    ep.yratio = plan->yratio;
+    ep.xcenter = plan->xcenter;
+    ep.xw      = plan->xw;
+    ep.xwsum   = plan->xwsum;
+    ep.xfrac   = plan->xfrac;
+    ep.ycenter = plan->ycenter;
+    ep.yw      = plan->yw;
+    ep.ywsum   = plan->ywsum;
+    ep.yfrac   = plan->yfrac;
+    ep.nonsep_kind = filter.nonseparable_kind();
+    ep.filt_w      = filter.width();
+    ep.filt_h      = filter.height();
+    ep.gate        = nullptr;
+
+    bool fused_ok = plan->fused && src.nchannels == dst.nchannels
+                    && srcd.xstride == (int64_t)nch * ses
+                    && dstd.xstride == (int64_t)nch * des;
+    int launched = 0;
+    int used     = B2R_PATH_EXACT;
+    int* flag    = nullptr;
+    if (path == B2R_PATH_FUSED && !fused_ok) {
+        set_err(err, errlen, "resize: shape is not eligible for the fused kernel");
+        if (src_staged)
+            cudaFreeAsync(dsrc, stream);
+        if (dst_staged)
+            cudaFreeAsync(ddst, stream);
+        return B2R_ERR_UNSUPPORTED;
+    }
+    const bool src_is_fp = src.basetype == B2R_FLOAT || src.basetype == B2R_HALF;
+    if (fused_ok && path != B2R_PATH_EXACT) {
+        FusedParams fp;
+        memset(&fp, 0, sizeof(fp));
+        fp.src         = (const unsigned char*)dsrc;
+        fp.src_ystride = srcd.ystride;
+        fp.srctype     = src.basetype;
+        fp.src_w       = src.width;
+        fp.src_h       = src.height;
+        fp.nch         = nch;
+        fp.dst         = (unsigned char*)ddst
+                 + (long long)(roi.ybegin - dstd.y) * dstd.ystride
+                 + (long long)(roi.xbegin - dstd.x) * dstd.xstride;
+        fp.dst_ystride = dstd.ystride;
+        fp.dsttype     = dst.basetype;
+        fp.src_vec_ok  = ((uintptr_t)dsrc % (4 * ses) == 0)
+                        && (srcd.ystride % (4 * ses) == 0);
+        fp.dst_vec_ok = ((uintptr_t)fp.dst % (4 * des) == 0)
+                        && (dstd.ystride % (4 * des) == 0);
+        // zero weights are multiplied, not skipped, in this kernel: if the
+        // source can hold Inf/NaN the outputs are screened and the exact
+        // kernel re-does the image when one shows up
+        fp.check_nonfinite = src_is_fp ? 1 : 0;
+        fp.nonfinite_flag  = nullptr;
+        fp.nstrips         = (int)plan->fp.strips.size();
+        fp.nbands          = (int)plan->fp.bands.size();
+        fp.strips          = plan->strips;
+        fp.bands           = plan->bands;
+        fp.hfirst          = plan->hfirst;
+        fp.hw              = plan->hw;
+        fp.ht              = plan->fp.ht;
+        fp.vk              = plan->fp.vk;
+        fp.vring           = plan->vring;
+        fp.vlast           = plan->vlast;
+        fp.vt              = plan->fp.vt;
+        fp.vfirst          = plan->vfirst;
+        fp.vw              = plan->vw;
+        if (src_is_fp) {
+            // per-call flag: plans are shared between concurrent calls
+            CUDA_TRY(cudaMallocAsync((void**)&flag, sizeof(int), stream));
+            CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+            fp.nonfinite_flag = flag;
+        }
+        launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_nvec, stream);
+        ++launched;
+        used = B2R_PATH_FUSED;
+        if (src_is_fp) {
+            ep.gate = flag;  // runs only if a non-finite output was seen
+            launch_resize_exact(ep, stream);
+            ++launched;
+        }
+        if (report) {
+            report->fused_vmode = fp.vk;
+            report->fused_htaps = fp.ht;
+        }
+    } else {
+        launch_resize_exact(ep, stream);
+        ++launched;
+    }
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
+            return B2R_ERR_CUDA;
+        }
+    }
+    if (timed)
+        cudaEventRecord(ev1, stream);
+
+    // ---- results back -----------------------------------------------------
+    if (dst_staged) {
+        unsigned char* hp = (unsigned char*)dst.pixels
+                            + (long long)(roi.ybegin - dst.y) * dst.ystride
+                            + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        CUDA_TRY(cudaMemcpy2DAsync(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h,
+                                   cudaMemcpyDeviceToHost, stream));
+        if (report)
+            report->d2h_bytes += (int64_t)drowbytes * roi_h;
+    }
+    int redo = 0;
+    if (report && used == B2R_PATH_FUSED && src_is_fp
+        && (dst_staged || src_staged))
+        CUDA_TRY(cudaMemcpyAsync(&redo, flag, sizeof(int),
+                                 cudaMemcpyDeviceToHost, stream));
+    if (flag)
+        CUDA_TRY(cudaFreeAsync(flag, stream));
+    if (src_staged)
+        CUDA_TRY(cudaFreeAsync(dsrc, stream));
+    if (dst_staged)
+        CUDA_TRY(cudaFreeAsync(ddst, stream));
+    if (dst_staged || src_staged || timed)
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    if (report) {
+        report->path_used        = used;
+        report->kernels_launched = launched;
+        report->xtaps            = plan->xtaps;
+        report->ytaps            = plan->ytaps;
+        report->nonfinite_redo   = redo;
+        if (timed) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            report->kernel_ms = ms;
+        }
+    }
+    if (ev0)
+        cudaEventDestroy(ev0);
+    if (ev1)
+        cudaEventDestroy(ev1);
+    return B2R_OK;
+}
+
+}  // namespace
+
+// =========================================================================
+extern "C" {
+
+const char*
+b2r_version(void)
+{
+    return "b2r 0.1 (sm_100a)";
+}
+
+int
+b2r_device_count(void)
+{
+    return device_count_cached();
+}
+
+int
+b2r_filter_count(int dim)
+{
+    return dim == 1 ? Filter1D::num_filters()
+                    : (dim == 2 ? Filter2D::num_filters() : 0);
+}
+
+int
+b2r_filter_desc(int dim, int index, const char** name, float* width,
+                int* fixedwidth, int* scalable, int* separable)
+{
+    if ((dim != 1 && dim != 2) || index < 0 || index >= b2r_filter_count(dim))
+        return B2R_ERR_INVALID;
+    const FilterDesc& d = dim == 1 ? Filter1D::get_filterdesc(index)
+                                   : Filter2D::get_filterdesc(index);
+    if (name)
+        *name = d.name;
+    if (width)
+        *width = d.width;
+    if (fixedwidth)
+        *fixedwidth = d.fixedwidth;
+    if (scalable)
+        *scalable = d.scalable;
+    if (separable)
+        *separable = d.separable;
+    return B2R_OK;
+}
+
+b2r_filter2d*
+b2r_filter2d_create(const char* name, float width, float height)
+{
+    Filter2D* f = Filter2D::create(name ? name : "", width, height);
+    if (!f)
+        return nullptr;
+    return new b2r_filter2d { f };
+}
+void
+b2r_filter2d_destroy(b2r_filter2d* f)
+{
+    if (f) {
+        Filter2D::destroy(f->f);
+        delete f;
+    }
+}
+float
+b2r_filter2d_width(const b2r_filter2d* f)
+{
+    return f->f->width();
+}
+float
+b2r_filter2d_height(const b2r_filter2d* f)
+{
+    return f->f->height();
+}
+int
+b2r_filter2d_separable(const b2r_filter2d* f)
+{
+    return f->f->separable() ? 1 : 0;
+}
+const char*
+b2r_filter2d_name(const b2r_filter2d* f)
+{
+    return f->f->name().data();
+}
+float
+b2r_filter2d_eval(const b2r_filter2d* f, float x, float y)
+{
+    return (*f->f)(x, y);
+}
+float
+b2r_filter2d_xfilt(const b2r_filter2d* f, float x)
+{
+    return f->f->xfilt(x);
+}
+float
+b2r_filter2d_yfilt(const b2r_filter2d* f, float y)
+{
+    return f->f->yfilt(y);
+}
+b2r_filter1d*
+b2r_filter1d_create(const char* name, float width)
+{
+    Filter1D* f = Filter1D::create(name ? name : "", width);
+    if (!f)
+        return nullptr;
+    return new b2r_filter1d { f };
+}
+void
+b2r_filter1d_destroy(b2r_filter1d* f)
+{
+    if (f) {
+        Filter1D::destroy(f->f);
+        delete f;
+    }
+}
+float
+b2r_filter1d_width(const b2r_filter1d* f)
+{
+    return f->f->width();
+}
+const char*
+b2r_filter1d_name(const b2r_filter1d* f)
+{
+    return f->f->name().data();
+}
+float
+b2r_filter1d_eval(const b2r_filter1d* f, float x)
+{
+    return (*f->f)(x);
+}
+
+int
+b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
+                  const b2r_filter2d* filter, const b2r_roi* roi,
+                  const b2r_options* opt, b2r_report* report, char* err,
+                  size_t errlen)
+{
+    if (!filter || !filter->f) {
+        set_err(err, errlen, "resize: null filter");
+        return B2R_ERR_INVALID;
+    }
+    return resize_impl(dst, src, *filter->f, roi, opt, report, err, errlen);
+}
+
+int
+b2r_resize(const b2r_image* dst, const b2r_image* src, const char* filtername,
+           float filterwidth, const b2r_roi* roi, const b2r_options* opt,
+           b2r_report* report, char* err, size_t errlen)
+{
+    int rc = check_image(src, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst, false, err, errlen);
+    if (rc)
+        return rc;
+    // get_resize_filter, imagebufalgo_xform.cpp:830-860
+    float wratio = float(dst->full_width) / float(src->full_width);
+    float hratio = float(dst->full_height) / float(src->full_height);
+    std::string name = filtername ? filtername : "";
+    if (name.empty())
+        name = (wratio > 1.0f || hratio > 1.0f) ? "blackman-harris" : "lanczos3";
+    std::unique_ptr<Filter2D, void (*)(Filter2D*)> filter(nullptr,
+                                                          Filter2D::destroy);
+    for (int i = 0, e = Filter2D::num_filters(); i < e; ++i) {
+        const FilterDesc& fd = Filter2D::get_filterdesc(i);
+        if (name == fd.name) {
+            float w = filterwidth > 0.0f ? filterwidth
+                                         : fd.width * std::max(1.0f, wratio);
+            float h = filterwidth > 0.0f ? filterwidth
+                                         : fd.width * std::max(1.0f, hratio);
+            filter.reset(Filter2D::create(name, w, h));
+            break;
+        }
+    }
+    if (!filter) {
+        set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
+        return B2R_ERR_FILTER;
+    }
+    return resize_impl(dst, src, *filter, roi, opt, report, err, errlen);
+}
+
+void
+b2r_fit_geometry(int src_full_width, int src_full_height, int fit_width,
+                 int fit_height, const char* fillmode, int* resize_width,
+                 int* resize_height, int* xoffset, int* yoffset)
+{
+    // imagebufalgo_xform.cpp:962-997
+    float oldaspect = float(src_full_width) / src_full_height;
+    float newaspect = float(fit_width) / fit_height;
+    int rw = fit_width, rh = fit_height, xo = 0, yo = 0;
+    std::string mode = fillmode ? fillmode : "letterbox";
+    if (mode != "height" && mode != "width")
+        mode = "letterbox";
+    if (mode == "letterbox")
+        mode = (newaspect >= oldaspect) ? "height" : "width";
+    if (mode == "height") {
+        rw = int(rh * oldaspect + 0.5f);
+        xo = (fit_width - rw) / 2;
+    } else {
+        rh = int(rw / oldaspect + 0.5f);
+        yo = (fit_height - rh) / 2;
+    }
+    if (resize_width)
+        *resize_width = rw;
+    if (resize_height)
+        *resize_height = rh;
+    if (xoffset)
+        *xoffset = xo;
+    if (yoffset)
+        *yoffset = yo;
+}
+
+}  // extern "C"
+
+// =========================================================================
+// resample
+// =========================================================================
+extern "C" int
+b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
+             const b2r_roi* roi_in, const b2r_options* opt, b2r_report* report,
+             char* err, size_t errlen)
+{
+    if (report)
+        memset(report, 0, sizeof(*report));
+    int rc = check_image(src_in, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst_in, false, err, errlen);
+    if (rc)
+        return rc;
+    const b2r_image& dst = *dst_in;
+    const b2r_image& src = *src_in;
+    if (!legal_pair(dst.basetype, src.basetype)) {
+        set_err(err, errlen,
+                "resample: (dst,src) pixel types (%d,%d) are not a native pair; "
+                "convert through float first",
+                dst.basetype, src.basetype);
+        return B2R_ERR_TYPES;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 resample path has no CPU "
+                "fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    b2r_roi roi;
+    if (roi_in) {
+        roi        = *roi_in;
+        roi.xbegin = std::max(roi.xbegin, dst.x);
+        roi.xend   = std::min(roi.xend, dst.x + dst.width);
+        roi.ybegin = std::max(roi.ybegin, dst.y);
+        roi.yend   = std::min(roi.yend, dst.y + dst.height);
+        roi.chbegin = std::max(roi.chbegin, 0);
+        roi.chend   = std::min(roi.chend, dst.nchannels);
+    } else {
+        roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
+                        dst.nchannels };
+    }
+    roi.chend = std::min(roi.chend, src.nchannels);
+    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin || roi.chend <= roi.chbegin)
+        return B2R_OK;
+    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+    const int ses = basetype_size(src.basetype);
+    const int des = basetype_size(dst.basetype);
+
+    int sdev = opt ? opt->device : 0, ddev = sdev;
+    const int smem = memspace_of(&src, &sdev);
+    const int dmem = memspace_of(&dst, &ddev);
+    int device     = opt ? opt->device : 0;
+    if (smem == B2R_MEM_DEVICE)
+        device = sdev;
+    else if (dmem == B2R_MEM_DEVICE)
+        device = ddev;
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    device_info(device);
+    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+
+    void* dsrc     = src.pixels;
+    void* ddst     = dst.pixels;
+    b2r_image srcd = src, dstd = dst;
+    bool src_staged = false, dst_staged = false;
+    size_t dpitch = 0, drowbytes = 0;
+    if (smem == B2R_MEM_HOST) {
+        if (src.xstride != (int64_t)src.nchannels * ses) {
+            set_err(err, errlen, "host source pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        size_t rowbytes = size_t(src.width) * src.xstride;
+        size_t pitch    = (rowbytes + 15) & ~size_t(15);
+        CUDA_TRY(cudaMallocAsync(&dsrc, pitch * src.height, stream));
+        src_staged = true;
+        CUDA_TRY(cudaMemcpy2DAsync(dsrc, pitch, src.pixels, src.ystride, rowbytes,
+                                   src.height, cudaMemcpyHostToDevice, stream));
+        srcd.ystride = (int64_t)pitch;
+        if (report)
+            report->h2d_bytes += (int64_t)rowbytes * src.height;
+    }
+    if (dmem == B2R_MEM_HOST) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "host destination pixels must be contiguous in x");
+            if (src_staged)
+                cudaFreeAsync(dsrc, stream);
+            return B2R_ERR_UNSUPPORTED;
+        }
+        drowbytes = size_t(roi_w) * dst.xstride;
+        dpitch    = (drowbytes + 15) & ~size_t(15);
+        CUDA_TRY(cudaMallocAsync(&ddst, dpitch * roi_h, stream));
+        dst_staged = true;
+        // channels outside [chbegin,chend) must survive: bring the ROI over
+        if (roi.chbegin > 0 || roi.chend < dst.nchannels) {
+            unsigned char* hp = (unsigned char*)dst.pixels
+                                + (long long)(roi.ybegin - dst.y) * dst.ystride
+                                + (long long)(roi.xbegin - dst.x) * dst.xstride;
+            CUDA_TRY(cudaMemcpy2DAsync(ddst, dpitch, hp, dst.ystride, drowbytes,
+                                       roi_h, cudaMemcpyHostToDevice, stream));
+        }
+        dstd.x       = roi.xbegin;
+        dstd.y       = roi.ybegin;
+        dstd.width   = roi_w;
+        dstd.height  = roi_h;
+        dstd.ystride = (int64_t)dpitch;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (report) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+    }
+    ResampleParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.dst          = to_dev(dstd, ddst);
+    rp.src          = to_dev(srcd, dsrc);
+    rp.roi_x0       = roi.xbegin;
+    rp.roi_x1       = roi.xend;
+    rp.roi_y0       = roi.ybegin;
+    rp.roi_y1       = roi.yend;
+    rp.nch          = roi.chend - roi.chbegin;
+    rp.interpolate  = interpolate ? 1 : 0;
+    rp.data_is_full = (src.x == src.full_x && src.y == src.full_y
+                       && src.width == src.full_width
+                       && src.height == src.full_height)
+                          ? 1
+                          : 0;
+    launch_resample(rp, roi.chbegin, roi.chend, stream);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
+            return B2R_ERR_CUDA;
+        }
+    }
+    if (report)
+        cudaEventRecord(ev1, stream);
+    if (dst_staged) {
+        unsigned char* hp = (unsigned char*)dst.pixels
+                            + (long long)(roi.ybegin - dst.y) * dst.ystride
+                            + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        CUDA_TRY(cudaMemcpy2DAsync(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h,
+                                   cudaMemcpyDeviceToHost, stream));
+        if (report)
+            report->d2h_bytes += (int64_t)drowbytes * roi_h;
+    }
+    if (src_staged)
+        CUDA_TRY(cudaFreeAsync(dsrc, stream));
+    if (dst_staged)
+        CUDA_TRY(cudaFreeAsync(ddst, stream));
+    if (dst_staged || src_staged || report)
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    if (report) {
+        report->path_used        = B2R_PATH_EXACT;
+        report->kernels_launched = 1;
+        float ms                 = 0.0f;
+        cudaEventElapsedTime(&ms, ev0, ev1);
+        report->kernel_ms = ms;
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
+    return B2R_OK;
+}
+
+// =========================================================================
+// device-resident MIP chain (write_mipmap level loop, maketexture.cpp:823-986)
+// =========================================================================
+struct b2r_mipchain {
+    int device = 0;
+    int nch    = 0;
+    struct Level {
+        int w, h;
+        void* px;
+        bool owned;
+    };
+    std::vector<Level> levels;
+    float kernel_ms = 0.0f;
+    int launches    = 0;
+};
+
+extern "C" int
+b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
+                    const char* filtername, int clamp_half, int alpha_channel,
+                    const b2r_options* opt, char* err, size_t errlen)
+{
+    if (!out) {
+        set_err(err, errlen, "mipchain: null output handle");
+        return B2R_ERR_INVALID;
+    }
+    *out   = nullptr;
+    int rc = check_image(level0, true, err, errlen);
+    if (rc)
+        return rc;
+    if (level0->basetype != B2R_FLOAT) {
+        set_err(err, errlen,
+                "mipchain: levels are float32 (maketx:forcefloat); convert first");
+        return B2R_ERR_TYPES;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 MIP path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    std::string fname = (filtername && filtername[0]) ? filtername : "box";
+    if (fname != "box") {
+        bool known = false;
+        for (int i = 0, e = Filter2D::num_filters(); i < e; ++i)
+            known |= (fname == Filter2D::get_filterdesc(i).name);
+        if (!known) {
+            set_err(err, errlen, "Could not make filter \"%s\"", fname.c_str());
+            return B2R_ERR_FILTER;
+        }
+    }
+    int dev0      = opt ? opt->device : 0;
+    const int mem = memspace_of(level0, &dev0);
+    int device    = (mem == B2R_MEM_DEVICE) ? dev0 : (opt ? opt->device : 0);
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    device_info(device);
+    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+
+    std::unique_ptr<b2r_mipchain> chain(new b2r_mipchain);
+    chain->device = device;
+    chain->nch    = level0->nchannels;
+    const int nch = level0->nchannels;
+    auto fail = [&](int code) {
+        for (auto& l : chain->levels)
+            if (l.owned && l.px)
+                cudaFree(l.px);
+        return code;
+    };
+
+    // level 0 on the device, contiguous
+    b2r_mipchain::Level l0 { level0->width, level0->height, nullptr, false };
+    const size_t row0 = size_t(level0->width) * nch * 4;
+    if (mem == B2R_MEM_DEVICE && level0->xstride == (int64_t)nch * 4
+        && level0->ystride == (int64_t)row0) {
+        l0.px = level0->pixels;  // adopted, not owned
+    } else {
+        if (level0->xstride != (int64_t)nch * 4) {
+            set_err(err, errlen, "mipchain: level 0 pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        if (cudaMalloc(&l0.px, row0 * level0->height) != cudaSuccess) {
+            set_err(err, errlen, "mipchain: out of device memory for level 0");
+            return B2R_ERR_CUDA;
+        }
+        l0.owned = true;
+        chain->levels.push_back(l0);
+        cudaError_t e = cudaMemcpy2DAsync(l0.px, row0, level0->pixels,
+                                          level0->ystride, row0, level0->height,
+                                          cudaMemcpyDefault, stream);
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+            return fail(B2R_ERR_CUDA);
+        }
+        chain->levels.pop_back();
+    }
+    chain->levels.push_back(l0);
+
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+    int w = l0.w, h = l0.h;
+    b2r_options sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.device      = device;
+    sub.path        = opt ? opt->path : B2R_PATH_AUTO;
+    sub.cuda_stream = (void*)stream;
+    while (w > 1 || h > 1) {
+        const int sw = w > 1 ? w / 2 : w;
+        const int sh = h > 1 ? h / 2 : h;
+        b2r_mipchain::Level lv { sw, sh, nullptr, true };
+        if (cudaMalloc(&lv.px, size_t(sw) * sh * nch * 4) != cudaSuccess) {
+            set_err(err, errlen, "mipchain: out of device memory");
+            cudaEventDestroy(ev0);
+            cudaEventDestroy(ev1);
+            return fail(B2R_ERR_CUDA);
+        }
+        const b2r_mipchain::Level& big = chain->levels.back();
+        // "Trick" of write_mipmap (:866-879): both images get zero-origin
+        // windows with display == data
+        b2r_image S;
+        memset(&S, 0, sizeof(S));
+        S.pixels     = big.px;
+        S.basetype   = B2R_FLOAT;
+        S.nchannels  = nch;
+        S.width      = S.full_width = w;
+        S.height     = S.full_height = h;
+        S.xstride    = (int64_t)nch * 4;
+        S.ystride    = (int64_t)w * nch * 4;
+        S.memspace   = B2R_MEM_DEVICE;
+        S.device     = device;
+        b2r_image D  = S;
+        D.pixels     = lv.px;
+        D.width      = D.full_width = sw;
+        D.height     = D.full_height = sh;
+        D.ystride    = (int64_t)sw * nch * 4;
+        chain->levels.push_back(lv);
+        if (fname == "box") {
+            BoxParams bp;
+            bp.dst = to_dev(D, D.pixels);
+            bp.src = to_dev(S, S.pixels);
+            // resize_block (:304-334): 2-pass needs 2*dw == sw and, without
+            // allow_pixel_shift, even source sizes (:265-266)
+            bp.two_pass = (2 * sw == w) && !(w % 2 || h % 2);
+            launch_box_downsample(bp, stream);
+            chain->launches += 1;
+        } else {
+            b2r_report rep;
+            rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
+                            err, errlen);
+            (void)rep;
+            if (rc) {
+                cudaEventDestroy(ev0);
+                cudaEventDestroy(ev1);
+                return fail(rc);
+            }
+            chain->launches += 2;
+        }
+        if (clamp_half) {
+            launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch, alpha_channel,
+                         -65504.0f, 65504.0f, stream);
+            chain->launches += 1;
+        }
+        w = sw;
+        h = sh;
+    }
+    cudaEventRecord(ev1, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess)
+        e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        return fail(B2R_ERR_CUDA);
+    }
+    cudaEventElapsedTime(&chain->kernel_ms, ev0, ev1);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    *out = chain.release();
+    return B2R_OK;
+}
+
+extern "C" int
+b2r_mipchain_nlevels(const b2r_mipchain* chain)
+{
+    return chain ? (int)chain->levels.size() : 0;
+}
+
+extern "C" int
+b2r_mipchain_level(const b2r_mipchain* chain, int level, int* width, int* height,
+                   void** device_pixels)
+{
+    if (!chain || level < 0 || level >= (int)chain->levels.size())
+        return B2R_ERR_INVALID;
+    if (width)
+        *width = chain->levels[level].w;
+    if (height)
+        *height = chain->levels[level].h;
+    if (device_pixels)
+        *device_pixels = chain->levels[level].px;
+    return B2R_OK;
+}
+
+extern "C" int
+b2r_mipchain_download(const b2r_mipchain* chain, int level, const b2r_image* out,
+                      char* err, size_t errlen)
+{
+    if (!chain || level < 0 || level >= (int)chain->levels.size() || !out
+        || !out->pixels) {
+        set_err(err, errlen, "mipchain: bad level or output image");
+        return B2R_ERR_INVALID;
+    }
+    const auto& l = chain->levels[level];
+    if (out->basetype != B2R_FLOAT || out->nchannels != chain->nch
+        || out->width != l.w || out->height != l.h
+        || out->xstride != (int64_t)chain->nch * 4) {
+        set_err(err, errlen, "mipchain: output image does not match level %d",
+                level);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(chain->device);
+    size_t row = size_t(l.w) * chain->nch * 4;
+    CUDA_TRY(cudaMemcpy2D(out->pixels, out->ystride, l.px, row, row, l.h,
+                          cudaMemcpyDefault));
+    return B2R_OK;
+}
+
+extern "C" float
+b2r_mipchain_kernel_ms(const b2r_mipchain* chain)
+{
+    return chain ? chain->kernel_ms : 0.0f;
+}
+
+extern "C" void
+b2r_mipchain_destroy(b2r_mipchain* chain)
+{
+    if (!chain)
+        return;
+    DeviceGuard guard(chain->device);
+    for (auto& l : chain->levels)
+        if (l.owned && l.px)
+            cudaFree(l.px);
+    delete chain;
+}

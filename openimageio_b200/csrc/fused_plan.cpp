@@ -1,0 +1,198 @@
+// fused_plan.cpp -- tiling of the dst ROI into column strips x row bands and
+// the table layouts resize_fused_kernel reads.  See kernels.cu for the
+// kernel and DESIGN.md for the reasoning.
+#include "fused_plan.h"
+
+#include <algorithm>
+#include <climits>
+
+namespace b2r {
+
+static int
+round_taps(int n)
+{
+    for (int t : { 4, 8, 12, 16 })
+        if (n <= t)
+            return t;
+    return 0;
+}
+
+static int
+round_ring(int k)
+{
+    for (int t : { 2, 4, 6, 8 })
+        if (k <= t)
+            return t;
+    return 0;
+}
+
+bool
+plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
+           int src_h, int cta_slots, FusedPlan* plan)
+{
+    if (nch < 1 || nch > 4 || gx.n <= 0 || gy.n <= 0)
+        return false;
+    FusedPlan& P = *plan;
+    P            = FusedPlan();
+    P.interior_zero = gx.interior_zero || gy.interior_zero;
+
+    // ---------------- H tables --------------------------------------------
+    P.ht = round_taps(std::max(1, gx.maxcount));
+    if (!P.ht)
+        return false;
+    const int W = gx.n, H = gy.n;
+    P.hfirst.resize(W);
+    P.hw.assign(size_t(W) * P.ht, 0.0f);
+    for (int k = 0; k < W; ++k) {
+        if (gx.count[k] > 0) {
+            P.hfirst[k] = gx.first[k];
+            for (int i = 0; i < gx.count[k]; ++i)
+                P.hw[size_t(k) * P.ht + i] = gx.w[gx.woff[k] + i];
+        } else {
+            P.hfirst[k] = k > 0 ? P.hfirst[k - 1] : 0;
+        }
+        if (k > 0 && P.hfirst[k] < P.hfirst[k - 1])
+            return false;  // not monotone: leave it to the exact kernel
+    }
+
+    // ---------------- column strips ---------------------------------------
+    for (int dx0 = 0; dx0 < W;) {
+        Strip s;
+        s.dx0  = dx0;
+        s.e0   = (P.hfirst[dx0] * nch) & ~3;
+        s.ndx  = 0;
+        s.nvec = 0;
+        while (dx0 + s.ndx < W && s.ndx < FUSED_HCOLS) {
+            int eend = (P.hfirst[dx0 + s.ndx] + P.ht) * nch;
+            int nvec = (eend - s.e0 + 3) / 4;
+            if (nvec > FUSED_THREADS)
+                break;
+            s.nvec = nvec;
+            ++s.ndx;
+        }
+        if (s.ndx == 0)
+            return false;  // one column's footprint does not fit a strip
+        P.max_nvec = std::max(P.max_nvec, s.nvec);
+        P.strips.push_back(s);
+        dx0 += s.ndx;
+    }
+
+    // ---------------- V tables --------------------------------------------
+    std::vector<int> first(H), last(H);
+    for (int k = 0; k < H; ++k) {
+        if (gy.count[k] > 0) {
+            first[k] = gy.first[k];
+            last[k]  = gy.first[k] + gy.count[k] - 1;
+        } else {
+            first[k] = last[k] = k > 0 ? last[k - 1] : 0;
+        }
+        if (k > 0) {
+            if (first[k] < first[k - 1])
+                return false;
+            last[k] = std::max(last[k], last[k - 1]);
+        }
+    }
+    // open rows: how many dst rows are waiting on source rows at once
+    int K = 1;
+    for (int k = 0, lo = 0; k < H; ++k) {
+        while (last[lo] < first[k])
+            ++lo;
+        K = std::max(K, k - lo + 1);
+    }
+    const int vk          = round_ring(K);
+    const long long rows_total = (long long)last[H - 1] - first[0] + 1;
+    const int vt          = gy.maxcount;
+    const bool ring_ok    = vk > 0;
+    const bool gather_ok  = vt >= 1 && vt <= 16;
+    bool use_ring         = ring_ok;
+    if (ring_ok && gather_ok) {
+        // FMA-quads per strip column: ring touches every source row vk times,
+        // gather touches vt rows per dst row (and re-reads them through L1)
+        long long ring_cost   = rows_total * vk;
+        long long gather_cost = (long long)H * vt * 2;
+        use_ring              = ring_cost <= gather_cost;
+    }
+    if (!use_ring && !gather_ok)
+        return false;
+
+    // ---------------- row bands -------------------------------------------
+    const int nstrips = int(P.strips.size());
+    int nbands        = std::max(1, cta_slots / std::max(1, nstrips));
+    const int min_rows = 8;
+    nbands             = std::min(nbands, std::max(1, H / min_rows));
+    // ring weights live in shared memory: keep a band's source rows bounded
+    const int max_rows_smem = use_ring ? (24 * 1024 / (4 * vk)) : INT_MAX;
+    for (;;) {
+        bool ok = true;
+        P.bands.clear();
+        P.max_band_rows = 0;
+        int woff        = 0;
+        for (int b = 0; b < nbands; ++b) {
+            Band bd;
+            bd.dy0 = int((long long)H * b / nbands);
+            int e  = int((long long)H * (b + 1) / nbands);
+            bd.ndy = e - bd.dy0;
+            if (bd.ndy <= 0)
+                continue;
+            bd.r0    = first[bd.dy0];
+            bd.nrows = last[e - 1] - bd.r0 + 1;
+            bd.woff  = woff;
+            if (use_ring) {
+                if (bd.nrows > max_rows_smem) {
+                    ok = false;
+                    break;
+                }
+                woff += bd.nrows;
+                P.max_band_rows = std::max(P.max_band_rows, bd.nrows);
+            }
+            P.bands.push_back(bd);
+        }
+        if (ok)
+            break;
+        nbands *= 2;
+        if (nbands > H)
+            return false;
+    }
+
+    if (use_ring) {
+        P.vk = vk;
+        P.vt = 0;
+        P.vlast.assign(last.begin(), last.end());
+        size_t total = 0;
+        for (const Band& b : P.bands)
+            total += size_t(b.nrows);
+        P.vring.assign(total * vk, 0.0f);
+        for (const Band& b : P.bands) {
+            for (int k = b.dy0; k < b.dy0 + b.ndy; ++k) {
+                int slot = (k - b.dy0) % vk;
+                for (int j = 0; j < gy.count[k]; ++j) {
+                    int r = gy.first[k] + j;
+                    P.vring[(size_t(b.woff) + (r - b.r0)) * vk + slot]
+                        = gy.w[gy.woff[k] + j];
+                }
+            }
+        }
+    } else {
+        P.vk = 0;
+        P.vt = vt;
+        P.vfirst.resize(H);
+        P.vw.assign(size_t(H) * vt, 0.0f);
+        for (int k = 0; k < H; ++k) {
+            int f = first[k];
+            // keep first+vt inside the image: shift the window up and pad in
+            // front when the run sits at the bottom edge
+            int shift = 0;
+            if (f + vt > src_h)
+                shift = std::min(f, f + vt - src_h);
+            P.vfirst[k] = f - shift;
+            for (int j = 0; j < gy.count[k]; ++j)
+                P.vw[size_t(k) * vt + shift + j] = gy.w[gy.woff[k] + j];
+        }
+        if (vt > src_h)
+            return false;
+    }
+    (void)src_w;
+    return true;
+}
+
+}  // namespace b2r

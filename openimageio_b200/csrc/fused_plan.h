@@ -1,0 +1,38 @@
+// fused_plan.h -- host-side tiling and table layout for resize_fused_kernel.
+#pragma once
+
+#include "axis_plan.h"
+#include "kernels.h"
+
+#include <vector>
+
+namespace b2r {
+
+struct FusedPlan {
+    std::vector<Strip> strips;
+    std::vector<Band> bands;
+    // H pass
+    int ht = 0;
+    std::vector<int32_t> hfirst;
+    std::vector<float> hw;
+    // V pass
+    int vk = 0;  // ring size, 0 = gather
+    std::vector<float> vring;
+    std::vector<int32_t> vlast;
+    int vt = 0;
+    std::vector<int32_t> vfirst;
+    std::vector<float> vw;
+    int max_band_rows = 0;
+    int max_nvec      = 0;
+    bool interior_zero = false;
+};
+
+// gx / gy: gather tables of the two axes over the dst ROI.  cta_slots: how
+// many CTAs the device keeps resident (SMs x CTAs per SM); the band count is
+// chosen so the grid fills one wave.  Returns false when the shape is outside
+// what the fused kernel instantiates (then the exact kernel runs).
+bool
+plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
+           int src_h, int cta_slots, FusedPlan* plan);
+
+}  // namespace b2r

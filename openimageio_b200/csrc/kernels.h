@@ -1,0 +1,138 @@
+// kernels.h -- launch interface between the host planner (b2r_api.cpp) and the
+// sm_100a kernels (kernels.cu).  Plain structs, device pointers.
+#pragma once
+
+#include <cstdint>
+
+namespace b2r {
+
+enum : int { BT_UINT8 = 2, BT_UINT16 = 4, BT_HALF = 10, BT_FLOAT = 11 };
+
+inline int
+basetype_size(int bt)
+{
+    return bt == BT_UINT8 ? 1 : (bt == BT_FLOAT ? 4 : 2);
+}
+
+// Image as the kernels see it: `pixels` is the data-window origin.
+struct DevImage {
+    void* pixels;
+    int basetype;
+    int nchannels;
+    int x, y, width, height;
+    int full_x, full_y, full_width, full_height;
+    long long xstride, ystride;  // bytes
+};
+
+// ---------------------------------------------------------------- exact ----
+// Single-pass kernel in the reference's own tap order (bit-exact path).
+struct ExactParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;  // dst coords
+    int nch;                             // channels to compute (= dst.nchannels)
+    int radi, radj, xtaps, ytaps;
+    float xratio, yratio;
+    // separable: virtual taps
+    const int* xcenter;    // [roi_w]
+    const float* xw;       // [roi_w * xtaps] normalised
+    const float* xwsum;    // [roi_w]
+    const int* ycenter;    // [roi_h]
+    const float* yw;       // [roi_h * ytaps]
+    const float* ywsum;    // [roi_h]
+    // non-separable: per-index fractions + filter description
+    const float* xfrac;    // [roi_w]
+    const float* yfrac;    // [roi_h]
+    int nonsep_kind;       // 0 separable, 1 disk, 2 radial-lanczos3
+    float filt_w, filt_h;
+    // when not null: run only if *gate != 0 (non-finite redo)
+    const int* gate;
+};
+void
+launch_resize_exact(const ExactParams& p, void* stream);
+
+// ---------------------------------------------------------------- fused ----
+// Two-pass (vertical then horizontal) kernel; the intermediate stays in
+// shared memory.  One CTA = one column strip x one row band of the dst ROI.
+struct Strip {
+    int dx0;    // first dst column (index into the ROI, 0-based)
+    int ndx;    // columns in this strip (<= FUSED_HCOLS)
+    int e0;     // first flat source element (px*nch + c) staged, multiple of 4
+    int nvec;   // number of 4-element groups staged (<= FUSED_THREADS)
+};
+struct Band {
+    int dy0;    // first dst row (index into the ROI)
+    int ndy;    // rows
+    int r0;     // first source row consumed (relative to src data origin)
+    int nrows;  // source rows consumed (ring mode)
+    int woff;   // ring mode: row offset of this band's weights in vring
+};
+
+constexpr int FUSED_THREADS = 256;
+constexpr int FUSED_HCOLS   = 128;  // dst columns per strip (H-pass threads per row)
+constexpr int FUSED_BATCH   = 8;    // V-filtered rows buffered between passes
+
+struct FusedParams {
+    const unsigned char* src;  // data-window origin, pixels contiguous in x
+    long long src_ystride;
+    int srctype, src_w, src_h, nch;
+    unsigned char* dst;  // address of the ROI's first pixel
+    long long dst_ystride;
+    int dsttype;
+    int src_vec_ok, dst_vec_ok;  // 4-element vector loads / stores allowed
+    int check_nonfinite;         // float/half sources: flag non-finite outputs
+    int* nonfinite_flag;
+
+    int nstrips, nbands;
+    const Strip* strips;
+    const Band* bands;
+
+    // H pass (gather, HT taps per dst column, zero padded)
+    const int* hfirst;  // [roi_w] first source pixel
+    const float* hw;    // [roi_w * HT]
+    int ht;             // taps in the table (== template HT)
+
+    // V pass, ring mode (vk > 0): per band, per source row, K slot weights
+    int vk;
+    const float* vring;  // [(woff + r - r0) * vk + slot]
+    const int* vlast;    // [roi_h] source row after which dst row completes
+    // V pass, gather mode (vk == 0)
+    int vt;
+    const int* vfirst;   // [roi_h]
+    const float* vw;     // [roi_h * vt]
+};
+// Returns false when no instantiation matches (nch, vk, ht).
+bool
+fused_supported(int nch, int vk, int ht);
+size_t
+fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_nvec);
+void
+launch_resize_fused(const FusedParams& p, int max_band_rows, int max_nvec,
+                    void* stream);
+
+// ------------------------------------------------------------- resample ----
+struct ResampleParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int nch;
+    int interpolate;
+    int data_is_full;
+};
+void
+launch_resample(const ResampleParams& p, int chbegin, int chend, void* stream);
+
+// ------------------------------------------------------------- box mip ----
+// maketx resize_block (maketexture.cpp:141-334) on float32 images.
+struct BoxParams {
+    DevImage dst, src;
+    int two_pass;  // 1: exact 2x2 average path (:260-300); 0: bilinear NDC
+};
+void
+launch_box_downsample(const BoxParams& p, void* stream);
+
+// clamp a float image to [lo, hi] in place (ImageBufAlgo::clamp with
+// clampalpha01=true as maketx calls it, maketexture.cpp:943-945).
+void
+launch_clamp(float* pixels, long long n, int nch, int alpha_channel, float lo,
+             float hi, void* stream);
+
+}  // namespace b2r

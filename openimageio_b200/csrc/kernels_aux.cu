@@ -1,0 +1,317 @@
+// kernels_aux.cu -- the small bandwidth-bound kernels around the resize:
+// resample (nearest / bilinear), maketx's box downsample, clamp.
+//
+// All index and blend arithmetic uses explicit round-to-nearest mul/add
+// intrinsics: the reference computes them unfused, and a fused multiply-add
+// moves results across integer / rounding boundaries
+// (imagebufalgo_xform.cpp:1337-1341 warns about exactly that).
+#include "kernels.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace b2r {
+
+namespace {
+
+__device__ __forceinline__ float
+ld_elem(const unsigned char* p, int bt)
+{
+    switch (bt) {
+    case BT_UINT8: return __fmul_rn(float(*p), 1.0f / 255.0f);
+    case BT_UINT16:
+        return __fmul_rn(float(*(const unsigned short*)p), 1.0f / 65535.0f);
+    case BT_HALF: return __half2float(*(const __half*)p);
+    default: return *(const float*)p;
+    }
+}
+
+__device__ __forceinline__ unsigned int
+q_int(float v, float mx)
+{
+    float s = __fmul_rn(v, mx);
+    s       = __fadd_rn(s, (s < 0.0f) ? -0.5f : 0.5f);
+    if (!(0.0f <= s))
+        s = 0.0f;
+    if (s > mx)
+        s = mx;
+    return (unsigned int)s;
+}
+
+__device__ __forceinline__ void
+st_elem(unsigned char* p, int bt, float v)
+{
+    switch (bt) {
+    case BT_UINT8: *p = (unsigned char)q_int(v, 255.0f); break;
+    case BT_UINT16: *(unsigned short*)p = (unsigned short)q_int(v, 65535.0f); break;
+    case BT_HALF: *(__half*)p = __float2half_rn(v); break;
+    default: *(float*)p = v; break;
+    }
+}
+
+__device__ __forceinline__ int
+esize(int bt)
+{
+    return bt == BT_UINT8 ? 1 : (bt == BT_FLOAT ? 4 : 2);
+}
+
+__device__ __forceinline__ bool
+in_data(const DevImage& im, int x, int y)
+{
+    return x >= im.x && x < im.x + im.width && y >= im.y && y < im.y + im.height;
+}
+
+// WrapBlack (wrap_clamp=false) or WrapClamp addressing; nullptr = black.
+__device__ __forceinline__ const unsigned char*
+src_px(const DevImage& im, int x, int y, bool wrap_clamp)
+{
+    if (!in_data(im, x, y)) {
+        if (!wrap_clamp)
+            return nullptr;
+        x = min(max(x, im.full_x), im.full_x + im.full_width - 1);
+        y = min(max(y, im.full_y), im.full_y + im.full_height - 1);
+        if (!in_data(im, x, y))
+            return nullptr;
+    }
+    return (const unsigned char*)im.pixels + (long long)(y - im.y) * im.ystride
+           + (long long)(x - im.x) * im.xstride;
+}
+
+// bilerp, fmath.h:430-440, unfused
+__device__ __forceinline__ float
+bilerp1(float v0, float v1, float v2, float v3, float s, float t)
+{
+    float s1 = __fsub_rn(1.0f, s);
+    float t1 = __fsub_rn(1.0f, t);
+    float top = __fadd_rn(__fmul_rn(v0, s1), __fmul_rn(v1, s));
+    float bot = __fadd_rn(__fmul_rn(v2, s1), __fmul_rn(v3, s));
+    return __fadd_rn(__fmul_rn(t1, top), __fmul_rn(t, bot));
+}
+
+// ---------------------------------------------------------------------------
+// resample: imagebufalgo_xform.cpp:1107-1186 (scalar), :1379-1493 (tables)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+resample_kernel(ResampleParams p, int chbegin, int chend)
+{
+    const int roi_w = p.roi_x1 - p.roi_x0;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long npix = (long long)roi_w * (p.roi_y1 - p.roi_y0);
+    if (idx >= npix)
+        return;
+    const int x = p.roi_x0 + int(idx % roi_w);
+    const int y = p.roi_y0 + int(idx / roi_w);
+
+    const float srcfx = float(p.src.full_x), srcfy = float(p.src.full_y);
+    const float srcfw = float(p.src.full_width), srcfh = float(p.src.full_height);
+    const float dstfx = float(p.dst.full_x), dstfy = float(p.dst.full_y);
+    const float dpw   = __fdiv_rn(1.0f, float(p.dst.full_width));
+    const float dph   = __fdiv_rn(1.0f, float(p.dst.full_height));
+
+    float t      = __fmul_rn(__fadd_rn(__fsub_rn(float(y), dstfy), 0.5f), dph);
+    float src_yf = __fadd_rn(srcfy, __fmul_rn(t, srcfh));
+    float s      = __fmul_rn(__fadd_rn(__fsub_rn(float(x), dstfx), 0.5f), dpw);
+    float src_xf = __fadd_rn(srcfx, __fmul_rn(s, srcfw));
+
+    const int ses = esize(p.src.basetype), des = esize(p.dst.basetype);
+    unsigned char* dp = (unsigned char*)p.dst.pixels
+                        + (long long)(y - p.dst.y) * p.dst.ystride
+                        + (long long)(x - p.dst.x) * p.dst.xstride;
+    if (!p.interpolate) {
+        int sx = (int)floorf(src_xf), sy = (int)floorf(src_yf);
+        const unsigned char* sp = src_px(p.src, sx, sy, false);
+        for (int c = chbegin; c < chend; ++c)
+            st_elem(dp + c * des, p.dst.basetype,
+                    sp ? ld_elem(sp + c * ses, p.src.basetype) : 0.0f);
+        return;
+    }
+    float xx = __fsub_rn(src_xf, 0.5f), yy = __fsub_rn(src_yf, 0.5f);
+    float fxf = floorf(xx), fyf = floorf(yy);
+    int xt = (int)fxf, yt = (int)fyf;
+    float xfrac = __fsub_rn(xx, fxf), yfrac = __fsub_rn(yy, fyf);
+    const unsigned char* q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int px = xt + (k & 1), py = yt + (k >> 1);
+        if (p.data_is_full) {
+            px   = min(max(px, p.src.x), p.src.x + p.src.width - 1);
+            py   = min(max(py, p.src.y), p.src.y + p.src.height - 1);
+            q[k] = src_px(p.src, px, py, false);
+        } else {
+            q[k] = src_px(p.src, px, py, true);
+        }
+    }
+    for (int c = chbegin; c < chend; ++c) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            v[k] = q[k] ? ld_elem(q[k] + c * ses, p.src.basetype) : 0.0f;
+        st_elem(dp + c * des, p.dst.basetype,
+                bilerp1(v[0], v[1], v[2], v[3], xfrac, yfrac));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// maketx box downsample (float32 only), maketexture.cpp:141-334
+// ---------------------------------------------------------------------------
+// resize_block_2pass (:260-300): 0.5f*(0.5f*(a+b) + 0.5f*(c+d)).  One thread
+// per 4 consecutive dst elements when the row is 16-byte friendly.
+__global__ void __launch_bounds__(256)
+box2_kernel(const float* __restrict__ src, long long src_ystride_f,
+            float* __restrict__ dst, long long dst_ystride_f, int dw, int dh,
+            int nch)
+{
+    const long long row_elems = (long long)dw * nch;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= row_elems * dh)
+        return;
+    const int y       = int(idx / row_elems);
+    const int e       = int(idx % row_elems);
+    const int x       = e / nch;
+    const int c       = e - x * nch;
+    const float* r0   = src + (long long)(2 * y) * src_ystride_f;
+    const float* r1   = r0 + src_ystride_f;
+    const int a       = (2 * x) * nch + c;
+    float h0 = __fmul_rn(0.5f, __fadd_rn(__ldg(r0 + a), __ldg(r0 + a + nch)));
+    float h1 = __fmul_rn(0.5f, __fadd_rn(__ldg(r1 + a), __ldg(r1 + a + nch)));
+    dst[(long long)y * dst_ystride_f + e] = __fmul_rn(0.5f, __fadd_rn(h0, h1));
+}
+
+// RGBA fast path of the same arithmetic: one thread per dst pixel, two
+// 32-byte source reads, one 16-byte store.
+__global__ void __launch_bounds__(256)
+box2_rgba_kernel(const float4* __restrict__ src, long long src_ystride_4,
+                 float4* __restrict__ dst, long long dst_ystride_4, int dw, int dh)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)dw * dh)
+        return;
+    const int y = int(idx / dw), x = int(idx % dw);
+    const float4* r0 = src + (long long)(2 * y) * src_ystride_4 + 2 * x;
+    const float4* r1 = r0 + src_ystride_4;
+    float4 a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r1), d = __ldg(r1 + 1);
+    float4 o;
+    o.x = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, __fadd_rn(a.x, b.x)),
+                                    __fmul_rn(0.5f, __fadd_rn(c.x, d.x))));
+    o.y = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, __fadd_rn(a.y, b.y)),
+                                    __fmul_rn(0.5f, __fadd_rn(c.y, d.y))));
+    o.z = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, __fadd_rn(a.z, b.z)),
+                                    __fmul_rn(0.5f, __fadd_rn(c.z, d.z))));
+    o.w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, __fadd_rn(a.w, b.w)),
+                                    __fmul_rn(0.5f, __fadd_rn(c.w, d.w))));
+    dst[(long long)y * dst_ystride_4 + x] = o;
+}
+
+// resize_block_ (:205-241) + interppixel_NDC (:141-198, non-envlatl)
+__global__ void __launch_bounds__(256)
+box_bilinear_kernel(BoxParams p)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)p.dst.width * p.dst.height)
+        return;
+    const int x = p.dst.x + int(idx % p.dst.width);
+    const int y = p.dst.y + int(idx / p.dst.width);
+    const DevImage& S = p.src;
+    const bool src_is_crop
+        = (S.x > S.full_x || S.y > S.full_y
+           || S.x + S.width < S.full_x + S.full_width
+           || S.y + S.height < S.full_y + S.full_height);
+    const float xoffset = float(p.dst.full_x), yoffset = float(p.dst.full_y);
+    const float xscale  = __fdiv_rn(1.0f, float(p.dst.full_width));
+    const float yscale  = __fdiv_rn(1.0f, float(p.dst.full_height));
+    float t  = __fadd_rn(__fmul_rn(__fadd_rn(float(y), 0.5f), yscale), yoffset);
+    float s  = __fadd_rn(__fmul_rn(__fadd_rn(float(x), 0.5f), xscale), xoffset);
+    float fx = __fadd_rn(float(S.full_x), __fmul_rn(s, float(S.full_width)));
+    float fy = __fadd_rn(float(S.full_y), __fmul_rn(t, float(S.full_height)));
+    fx       = __fsub_rn(fx, 0.5f);
+    fy       = __fsub_rn(fy, 0.5f);
+    float flx = floorf(fx), fly = floorf(fy);
+    int xt = (int)flx, yt = (int)fly;
+    float xfrac = __fsub_rn(fx, flx), yfrac = __fsub_rn(fy, fly);
+    const float* q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        q[k] = (const float*)src_px(S, xt + (k & 1), yt + (k >> 1), !src_is_crop);
+    float* d = (float*)((unsigned char*)p.dst.pixels
+                        + (long long)(y - p.dst.y) * p.dst.ystride
+                        + (long long)(x - p.dst.x) * p.dst.xstride);
+    for (int c = 0; c < p.dst.nchannels; ++c) {
+        float v0 = q[0] ? q[0][c] : 0.0f, v1 = q[1] ? q[1][c] : 0.0f;
+        float v2 = q[2] ? q[2][c] : 0.0f, v3 = q[3] ? q[3][c] : 0.0f;
+        d[c]     = bilerp1(v0, v1, v2, v3, xfrac, yfrac);
+    }
+}
+
+// ImageBufAlgo::clamp(img, img, lo, hi, clampalpha01=true)
+// (imagebufalgo_pixelmath.cpp:222-240) on contiguous float pixels.
+__global__ void __launch_bounds__(256)
+clamp_kernel(float* px, long long n, int nch, int alpha, float lo, float hi)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float v = px[i];
+    float r = v;
+    if (!(lo <= r))
+        r = lo;
+    if (r > hi)
+        r = hi;
+    if (alpha >= 0 && int(i % nch) == alpha) {
+        if (!(0.0f <= r))
+            r = 0.0f;
+        if (r > 1.0f)
+            r = 1.0f;
+    }
+    px[i] = r;
+}
+
+}  // namespace
+
+void
+launch_resample(const ResampleParams& p, int chbegin, int chend, void* stream)
+{
+    long long npix = (long long)(p.roi_x1 - p.roi_x0) * (p.roi_y1 - p.roi_y0);
+    if (npix <= 0 || chend <= chbegin)
+        return;
+    unsigned blocks = (unsigned)((npix + 255) / 256);
+    resample_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, chbegin, chend);
+}
+
+void
+launch_box_downsample(const BoxParams& p, void* stream)
+{
+    const DevImage& D = p.dst;
+    const DevImage& S = p.src;
+    cudaStream_t st   = (cudaStream_t)stream;
+    if (p.two_pass) {
+        const bool rgba = D.nchannels == 4 && ((uintptr_t)S.pixels % 16 == 0)
+                          && ((uintptr_t)D.pixels % 16 == 0) && S.ystride % 16 == 0
+                          && D.ystride % 16 == 0;
+        if (rgba) {
+            long long n = (long long)D.width * D.height;
+            box2_rgba_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const float4*)S.pixels, S.ystride / 16, (float4*)D.pixels,
+                D.ystride / 16, D.width, D.height);
+        } else {
+            long long n = (long long)D.width * D.nchannels * D.height;
+            box2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                (const float*)S.pixels, S.ystride / 4, (float*)D.pixels,
+                D.ystride / 4, D.width, D.height, D.nchannels);
+        }
+    } else {
+        long long n = (long long)D.width * D.height;
+        box_bilinear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+    }
+}
+
+void
+launch_clamp(float* pixels, long long n, int nch, int alpha, float lo, float hi,
+             void* stream)
+{
+    if (n <= 0)
+        return;
+    clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        pixels, n, nch, alpha, lo, hi);
+}
+
+}  // namespace b2r

@@ -1,0 +1,336 @@
+"""GPU parity: the CUDA path (through the C ABI, via the host mirror of
+ImageBufAlgo) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): uint8/uint16 bit-exact or +-1 LSB;
+half/float max abs error <= 1e-5 relative (to the value range of the image);
+the exact kernel is held to bit-exactness for float outputs.
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+def _np_dtype(name):
+    return {"uint8": np.uint8, "uint16": np.uint16, "half": np.float16,
+            "float": np.float32}[name]
+
+
+def run_both(oiio, oracle, src_arr, dst_shape, dst_dtype, filtername="",
+             filterwidth=0.0, src_win=None, dst_win=None, roi=None,
+             path=0, prefill=None):
+    """Returns (gpu_out, oracle_out, report).  *_win = (x, y, full tuple)."""
+    h, w = dst_shape
+    c = src_arr.shape[2]
+    g = np.zeros((h, w, c), dst_dtype) if prefill is None else prefill.copy()
+    o = g.copy()
+    sx, sy, sfull = src_win if src_win else (0, 0, None)
+    dx, dy, dfull = dst_win if dst_win else (0, 0, None)
+    # oracle
+    osrc = oracle.Img(src_arr, sx, sy, sfull)
+    odst = oracle.Img(o, dx, dy, dfull)
+    oracle.resize(odst, osrc, filtername, filterwidth, roi)
+    # product
+    S = oiio.ImageBuf(src_arr)
+    S.spec().x, S.spec().y = sx, sy
+    if sfull:
+        (S.spec().full_x, S.spec().full_y, S.spec().full_width,
+         S.spec().full_height) = sfull
+    else:
+        S.spec().full_x, S.spec().full_y = sx, sy
+    D = oiio.ImageBuf(g)
+    D.spec().x, D.spec().y = dx, dy
+    if dfull:
+        (D.spec().full_x, D.spec().full_y, D.spec().full_width,
+         D.spec().full_height) = dfull
+    else:
+        D.spec().full_x, D.spec().full_y = dx, dy
+    r = None
+    if roi:
+        r = oiio.ROI(roi[0], roi[1], roi[2], roi[3], 0, 1, 0, c)
+    ok = oiio.ImageBufAlgo.resize(D, S, filtername=filtername,
+                                  filterwidth=filterwidth, roi=r, path=path)
+    assert ok, D.geterror()
+    return g, o, oiio.ImageBufAlgo.last_report
+
+
+def check(g, o, exact=False):
+    if g.dtype in (np.uint8, np.uint16):
+        d = np.abs(g.astype(np.int64) - o.astype(np.int64))
+        assert d.max() <= (0 if exact else 1), "max LSB diff %d" % d.max()
+        return d.max()
+    gf, of = g.astype(np.float64), o.astype(np.float64)
+    assert np.array_equal(np.isnan(gf), np.isnan(of))
+    m = ~np.isnan(of)
+    assert np.array_equal(np.isinf(gf[m]), np.isinf(of[m]))
+    fin = np.isfinite(of)
+    if exact and g.dtype == np.float32:
+        assert np.array_equal(g[fin], o[fin])
+        return 0.0
+    scale = max(1.0, np.abs(of[fin]).max()) if fin.any() else 1.0
+    err = np.abs(gf[fin] - of[fin]).max() / scale if fin.any() else 0.0
+    tol = REL_TOL if g.dtype == np.float32 else 2.0 ** -10  # half: 1 ulp
+    assert err <= tol, "rel err %g" % err
+    return err
+
+
+# ---- the ten native (dst, src) type pairs --------------------------------
+PAIRS = [("float", "float"), ("float", "uint8"), ("float", "half"),
+         ("float", "uint16"), ("uint8", "float"), ("uint8", "uint8"),
+         ("half", "float"), ("half", "half"), ("uint16", "float"),
+         ("uint16", "uint16")]
+
+
+@pytest.mark.parametrize("dt,st", PAIRS)
+@pytest.mark.parametrize("nch", [1, 3, 4])
+def test_type_pairs_downsize(oiio, oracle, dt, st, nch):
+    src = synth.image(201, 157, nch, _np_dtype(st), seed=11)
+    g, o, rep = run_both(oiio, oracle, src, (75, 96), _np_dtype(dt))
+    check(g, o)
+    assert rep.path_used == oiio.PATH_FUSED
+
+
+@pytest.mark.parametrize("dt,st", [("float", "float"), ("uint8", "uint8"),
+                                   ("half", "half"), ("uint16", "uint16")])
+def test_exact_kernel_bitexact(oiio, oracle, dt, st):
+    src = synth.image(97, 83, 3, _np_dtype(st), seed=5)
+    g, o, rep = run_both(oiio, oracle, src, (40, 51), _np_dtype(dt),
+                         path=oiio.PATH_EXACT)
+    check(g, o, exact=True)
+    assert rep.path_used == oiio.PATH_EXACT
+
+
+FILTERS = ["box", "triangle", "gaussian", "sharp-gaussian", "catmull-rom",
+           "blackman-harris", "sinc", "lanczos3", "radial-lanczos3",
+           "nuke-lanczos6", "mitchell", "bspline", "disk", "cubic", "keys",
+           "simon", "rifman"]
+
+
+@pytest.mark.parametrize("filt", FILTERS)
+def test_all_filters_down_and_up(oiio, oracle, filt):
+    src = synth.image(64, 48, 4, np.float32, seed=3)
+    for shape in [(24, 32), (100, 130)]:
+        g, o, rep = run_both(oiio, oracle, src, shape, np.float32, filt)
+        if filt in ("radial-lanczos3", "disk"):
+            assert rep.path_used == oiio.PATH_EXACT
+            check(g, o)  # device sinf differs from glibc by ulps
+        else:
+            check(g, o)
+
+
+def test_filters_known_answer_golden(oiio):
+    """testsuite/filters/run.py: delta 16x16 -> 80x80 per filter, half."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden",
+                             "filters_ref.npz"))
+    names = oiio.get_string_attribute("filter_list").split(";")
+    assert len(names) == 17
+    for i, f in enumerate(names):
+        delta = np.zeros((16, 16, 1), np.float32)
+        delta[8, 8, 0] = 1.0
+        S = oiio.ImageBuf(delta)
+        R = oiio.ImageBufAlgo.resize(S, f, roi=oiio.ROI(0, 80, 0, 80, 0, 1, 0, 1))
+        assert not R.has_error, R.geterror()
+        out = R.get_pixels()[..., 0].copy()
+        out[0, i] = 1.0
+        h = out.astype(np.float16).astype(np.float32)
+        ref = G[f].astype(np.float32)
+        assert np.abs(h - ref).max() <= 2.0 ** -11, f  # <= 1 half ulp near 1
+
+
+@pytest.mark.parametrize("name,shape,tol", [("resize", (256, 256), 1),
+                                            ("resize2", (250, 250), 1),
+                                            ("resize64", (64, 64), 1)])
+def test_grid_goldens(oiio, name, shape, tol):
+    """testsuite/oiiotool-xform: grid.tif --resize; goldens are uint8 written
+    from a float resize, matched to 1 LSB (idiff 0.004)."""
+    import os
+    X = np.load(os.path.join(os.path.dirname(__file__), "golden", "xform_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    S = oiio.ImageBuf(gf)
+    R = oiio.ImageBufAlgo.resize(S, roi=oiio.ROI(0, shape[1], 0, shape[0], 0, 1, 0, 4))
+    assert not R.has_error, R.geterror()
+    import oracle_py
+    q = oracle_py.quantize(R.get_pixels(), np.uint8)
+    d = np.abs(q.astype(int) - X[name].astype(int))
+    assert d.max() <= tol
+
+
+def test_windows_offset_and_crop(oiio, oracle):
+    """Nonzero origins, data window inside the full window (black outside),
+    dst data window smaller than its full window, sub-ROI."""
+    src = synth.image(64, 64, 3, np.float32, seed=9)
+    g, o, _ = run_both(oiio, oracle, src, (32, 32), np.float16,
+                       src_win=(100, 100, (0, 0, 256, 256)),
+                       dst_win=(50, 50, (0, 0, 128, 128)))
+    check(g, o)
+    # dst window reaching outside the source data -> black taps + clamp
+    g, o, _ = run_both(oiio, oracle, src, (60, 60), np.float32,
+                       src_win=(100, 100, (0, 0, 256, 256)),
+                       dst_win=(40, 40, (0, 0, 128, 128)))
+    check(g, o)
+    # sub-ROI leaves the rest of dst untouched
+    pre = synth.image(90, 70, 3, np.float32, seed=1)
+    src2 = synth.image(180, 140, 3, np.float32, seed=2)
+    g, o, _ = run_both(oiio, oracle, src2, (70, 90), np.float32,
+                       roi=(10, 55, 5, 61), prefill=pre)
+    check(g, o)
+    assert np.array_equal(g[:5], pre[:5]) and np.array_equal(g[:, :10], pre[:, :10])
+
+
+def test_overscan_source_uses_exact(oiio, oracle):
+    """Data window larger than the display window: WrapClamp is not
+    separable, the exact kernel must take it."""
+    src = synth.image(80, 72, 4, np.float32, seed=4)
+    g, o, rep = run_both(oiio, oracle, src, (30, 34), np.float32,
+                         src_win=(-8, -4, (0, 0, 64, 64)),
+                         dst_win=(0, 0, (0, 0, 34, 30)))
+    check(g, o, exact=True)
+    assert rep.path_used == oiio.PATH_EXACT
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 37), (53, 1), (7, 5), (300, 2)])
+def test_ragged_sizes(oiio, oracle, shape):
+    src = synth.image(37, 29, 4, np.float32, seed=8)
+    g, o, _ = run_both(oiio, oracle, src, shape, np.float32)
+    check(g, o)
+    src = synth.image(3, 2, 3, np.uint8, seed=8)
+    g, o, _ = run_both(oiio, oracle, src, shape, np.uint8)
+    check(g, o)
+
+
+def test_extreme_ratio_wide_footprint(oiio, oracle):
+    """grid 1000 -> 64: 95 taps per axis (testsuite resize64)."""
+    src = synth.image(500, 400, 4, np.uint8, seed=6)
+    g, o, _ = run_both(oiio, oracle, src, (26, 32), np.uint8)
+    check(g, o)
+
+
+def test_upsample_mitchell_catrom_uint8(oiio, oracle):
+    """BASELINE config 3 at reduced size: RGB uint8 x4, +-1 LSB."""
+    src = synth.image(120, 68, 3, np.uint8, seed=12)
+    for f in ("mitchell", "catmull-rom"):
+        g, o, rep = run_both(oiio, oracle, src, (272, 480), np.uint8, f)
+        check(g, o)
+        assert rep.path_used == oiio.PATH_FUSED
+
+
+def test_nonfinite_zero_weight_skip(oiio, oracle):
+    """Inf/NaN under zero-weight taps must not poison the output: the fused
+    kernel flags the image and the exact kernel re-does it."""
+    src = synth.image(96, 80, 4, np.float32, seed=13)
+    src[10, 17, 1] = np.inf
+    src[40, 60, 2] = np.nan
+    src[70, 5, 0] = -np.inf
+    g, o, rep = run_both(oiio, oracle, src, (40, 48), np.float32)
+    check(g, o, exact=True)
+    assert rep.nonfinite_redo == 1
+    # ratio 1 with lanczos3: integer taps are exact zeros around the centre
+    g, o, rep = run_both(oiio, oracle, src, (80, 96), np.float32, "triangle")
+    check(g, o, exact=True)
+
+
+def test_explicit_filterwidth_and_errors(oiio, oracle):
+    src = synth.image(64, 64, 3, np.float32, seed=2)
+    g, o, _ = run_both(oiio, oracle, src, (40, 40), np.float32, "gaussian", 5.0)
+    check(g, o)
+    S = oiio.ImageBuf(src)
+    R = oiio.ImageBufAlgo.resize(S, "catrom", roi=oiio.ROI(0, 8, 0, 8, 0, 1, 0, 3))
+    assert R.has_error and R.geterror() == 'Filter "catrom" not recognized'
+    R = oiio.ImageBufAlgo.resize(oiio.ImageBuf(), "box")
+    assert R.has_error and "Uninitialized input image" in R.geterror()
+
+
+def test_device_resident_tensors(oiio, oracle):
+    """src and dst as torch CUDA tensors: no host copies, stream ordered."""
+    import torch
+    src = synth.image(256, 192, 4, np.float32, seed=21)
+    o = np.zeros((96, 128, 4), np.float32)
+    oracle.resize(oracle.Img(o), oracle.Img(src))
+    ts = torch.from_numpy(src).cuda()
+    td = torch.zeros((96, 128, 4), dtype=torch.float32, device="cuda")
+    ok = oiio.ImageBufAlgo.resize(oiio.ImageBuf(td), oiio.ImageBuf(ts))
+    assert ok
+    torch.cuda.synchronize()
+    check(td.cpu().numpy(), o)
+
+
+def test_resample(oiio, oracle):
+    for st, dt in [(np.uint8, np.uint8), (np.float32, np.float32),
+                   (np.float16, np.float32)]:
+        src = synth.image(100, 80, 4, st, seed=31)
+        for interp in (True, False):
+            for shape in [(37, 45), (160, 210)]:
+                o = np.zeros(shape + (4,), dt)
+                oracle.resample(oracle.Img(o), oracle.Img(src), interp)
+                g = np.zeros(shape + (4,), dt)
+                ok = oiio.ImageBufAlgo.resample(oiio.ImageBuf(g), oiio.ImageBuf(src),
+                                                interpolate=interp)
+                assert ok
+                check(g, o, exact=True)
+    # cropped source -> scalar path with WrapClamp / black
+    src = synth.image(40, 40, 3, np.float32, seed=32)
+    o = np.zeros((64, 64, 3), np.float32)
+    oracle.resample(oracle.Img(o, full=(0, 0, 64, 64)),
+                    oracle.Img(src, 30, 30, (0, 0, 128, 128)), True)
+    S = oiio.ImageBuf(src)
+    S.spec().x = S.spec().y = 30
+    S.spec().full_x = S.spec().full_y = 0
+    S.spec().full_width = S.spec().full_height = 128
+    g = np.zeros((64, 64, 3), np.float32)
+    assert oiio.ImageBufAlgo.resample(oiio.ImageBuf(g), S, interpolate=True)
+    check(g, o, exact=True)
+
+
+def test_resample_goldens(oiio):
+    import os
+    import oracle_py
+    X = np.load(os.path.join(os.path.dirname(__file__), "golden", "xform_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    for interp, name in [(True, "resample"), (False, "resample_nearest")]:
+        R = oiio.ImageBufAlgo.resample(oiio.ImageBuf(gf), interp,
+                                       roi=oiio.ROI(0, 128, 0, 128, 0, 1, 0, 4))
+        assert not R.has_error, R.geterror()
+        q = oracle_py.quantize(R.get_pixels(), np.uint8)
+        assert np.array_equal(q, X[name])
+
+
+def test_fit(oiio, oracle):
+    src = synth.image(200, 100, 3, np.float32, seed=41)
+    for (fw, fh), mode in [((90, 60), "letterbox"), ((60, 90), "letterbox"),
+                           ((90, 60), "width"), ((90, 60), "height")]:
+        R = oiio.ImageBufAlgo.fit(oiio.ImageBuf(src), fillmode=mode,
+                                  roi=oiio.ROI(0, fw, 0, fh, 0, 1, 0, 3))
+        assert not R.has_error, R.geterror()
+        rw, rh, xo, yo = oracle.fit_geometry(200, 100, fw, fh, mode)
+        sp = R.spec()
+        assert (sp.width, sp.height, sp.x, sp.y) == (rw, rh, xo, yo)
+        assert (sp.full_width, sp.full_height) == (fw, fh)
+        o = np.zeros((rh, rw, 3), np.float32)
+        oracle.resize(oracle.Img(o), oracle.Img(src))
+        check(R.get_pixels(), o)
+
+
+@pytest.mark.parametrize("filt", ["box", "lanczos3", "triangle"])
+@pytest.mark.parametrize("size", [(64, 64), (100, 37), (33, 130)])
+def test_mip_chain(oiio, oracle, filt, size):
+    """write_mipmap level loop, device resident; every level against the
+    oracle's level loop (levels >= 1 are not pinned by the reference)."""
+    w, h = size
+    lvl0 = synth.image(w, h, 4, np.float32, seed=51)
+    ref = oracle.mip_chain(lvl0, filt)
+    chain = oiio.MipChain(lvl0, filt)
+    assert chain.nlevels == len(ref) + 1
+    for i, r in enumerate(ref):
+        assert chain.level_size(i + 1) == (r.shape[1], r.shape[0])
+        g = chain.download(i + 1)
+        if filt == "box":
+            assert np.array_equal(g, r), "level %d" % (i + 1)
+        else:
+            # errors compound level to level; both sides take their own
+            # previous level as input
+            assert np.abs(g - r).max() <= 1e-5 * (i + 1), "level %d" % (i + 1)
