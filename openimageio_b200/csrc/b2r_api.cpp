@@ -181,11 +181,11 @@ struct PlanKey {
     int g[16];
     float fw, fh;
     std::string fname;
-    int nch;
+    int nch, st;
     bool operator==(const PlanKey& o) const
     {
         return device == o.device && !memcmp(g, o.g, sizeof(g)) && fw == o.fw
-               && fh == o.fh && fname == o.fname && nch == o.nch;
+               && fh == o.fh && fname == o.fname && nch == o.nch && st == o.st;
     }
 };
 
@@ -264,6 +264,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     key.fh    = filter.height();
     key.fname = std::string(filter.name());
     key.nch   = nch;
+    key.st    = src.basetype;
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
@@ -301,10 +302,30 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
            o_vf = 0, o_vw = 0;
     if (filter.separable()) {
         AxisGather ax, ay;
-        if (build_axis_gather(gx, tx, &ax) && build_axis_gather(gy, ty, &ay)
-            && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
-                          &plan->fp)
-            && fused_supported(nch, plan->fp.vk, plan->fp.ht)) {
+        bool ok = build_axis_gather(gx, tx, &ax) && build_axis_gather(gy, ty, &ay)
+                  && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
+                                &plan->fp)
+                  && fused_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht);
+        if (ok) {
+            // the band count was sized for an assumed number of resident CTAs
+            // per SM; ask the runtime what this shape really gets and re-plan
+            // when it differs (one wave, no ragged tail)
+            FusedParams q;
+            memset(&q, 0, sizeof(q));
+            q.srctype = src.basetype;
+            q.nch     = nch;
+            q.vk      = plan->fp.vk;
+            q.ht      = plan->fp.ht;
+            int per   = fused_ctas_per_sm(q, plan->fp.max_band_rows,
+                                          plan->fp.max_band_dy, plan->fp.max_nvec);
+            int sms   = cta_slots / 3;
+            if (per > 0 && per != 3)
+                ok = plan_fused(ax, ay, nch, src.width, src.height, sms * per,
+                                &plan->fp)
+                     && fused_supported(src.basetype, nch, plan->fp.vk,
+                                        plan->fp.ht);
+        }
+        if (ok) {
             plan->fused = true;
             o_strips    = bb.add(plan->fp.strips);
             o_bands     = bb.add(plan->fp.bands);
@@ -452,7 +473,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     const int path      = opt ? opt->path : B2R_PATH_AUTO;
 
     std::shared_ptr<DevicePlan> plan;
-    rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 2, stream, &plan,
+    rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 3, stream, &plan,
                   err, errlen);
     if (rc)
         return rc;
@@ -597,7 +618,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), stream));
             fp.nonfinite_flag = flag;
         }
-        launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_nvec, stream);
+        launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,
+                            plan->fp.max_nvec, stream);
         ++launched;
         used = B2R_PATH_FUSED;
         if (src_is_fp) {

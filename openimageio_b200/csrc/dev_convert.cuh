@@ -1,0 +1,58 @@
+// dev_convert.cuh -- device-side pixel type conversion shared by the kernels.
+#pragma once
+
+#include "kernels.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace b2r {
+
+// ------------------------------------------------------------------------
+// type conversion: convert_type<S,float> / convert_type<float,D>
+// (src/include/OpenImageIO/fmath.h:753-764, 1009-1031).  Explicit _rn
+// intrinsics keep nvcc from contracting v*max+0.5 into one FMA, which would
+// round differently from the reference's multiply-then-add.
+// ------------------------------------------------------------------------
+__device__ __forceinline__ float
+load_elem(const unsigned char* p, int bt)
+{
+    switch (bt) {
+    case BT_UINT8: return __fmul_rn(float(*p), 1.0f / 255.0f);
+    case BT_UINT16:
+        return __fmul_rn(float(*(const unsigned short*)p), 1.0f / 65535.0f);
+    case BT_HALF: return __half2float(*(const __half*)p);
+    default: return *(const float*)p;
+    }
+}
+
+__device__ __forceinline__ unsigned int
+quant_int(float v, float mx)
+{
+    float s = __fmul_rn(v, mx);
+    s       = __fadd_rn(s, (s < 0.0f) ? -0.5f : 0.5f);
+    if (!(0.0f <= s))  // also catches NaN -> 0
+        s = 0.0f;
+    if (s > mx)
+        s = mx;
+    return (unsigned int)s;  // truncation
+}
+
+__device__ __forceinline__ void
+store_elem(unsigned char* p, int bt, float v)
+{
+    switch (bt) {
+    case BT_UINT8: *p = (unsigned char)quant_int(v, 255.0f); break;
+    case BT_UINT16: *(unsigned short*)p = (unsigned short)quant_int(v, 65535.0f); break;
+    case BT_HALF: *(__half*)p = __float2half_rn(v); break;
+    default: *(float*)p = v; break;
+    }
+}
+
+__device__ __forceinline__ bool
+nonfinite(float v)
+{
+    return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;
+}
+
+}  // namespace b2r

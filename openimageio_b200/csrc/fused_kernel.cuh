@@ -1,0 +1,523 @@
+// fused_kernel.cuh -- the hot path: one kernel, vertical pass then horizontal
+// pass, the intermediate never leaves the SM.
+//
+// One CTA = one column strip x one row band of the destination ROI.
+//
+//  V pass  Thread t owns 4 consecutive source elements (one RGBA float pixel,
+//          or 4 flat elements of an N-channel row) of the strip.  Source rows
+//          stream HBM -> shared memory through a per-thread private cp.async
+//          FIFO (LDGSTS, 16 B per thread per row, FUSED_FIFO rows in flight,
+//          no CTA barrier because a thread only reads back what it fetched).
+//          "Ring" mode (downsizing): every source row is read ONCE and
+//          scattered into the VK destination rows that are open at that time
+//          (VK register accumulators, slot = dst row mod VK, weights per
+//          source row staged in shared memory).  "Gather" mode (upsizing):
+//          each destination row gathers its few source rows through L1.
+//  H pass  FUSED_BATCH V-filtered rows sit in shared memory; thread (column,
+//          row group) gathers HT taps with weights it keeps in registers for
+//          the whole band, quantises to the destination type and stores.
+//
+// Zero weights are multiplied rather than skipped (the reference skips them,
+// imagebufalgo_xform.cpp:749-759); for float/half sources the outputs are
+// screened for Inf/NaN and the exact kernel re-does the image if one appears.
+#pragma once
+
+#include "dev_convert.cuh"
+#include "kernels.h"
+
+namespace b2r {
+
+// source type index used as a template parameter
+enum : int { ST_U8 = 0, ST_U16 = 1, ST_HALF = 2, ST_FLOAT = 3 };
+
+template<int ST> struct SrcTraits;
+template<> struct SrcTraits<ST_U8> { static constexpr int es = 1, bt = BT_UINT8; };
+template<> struct SrcTraits<ST_U16> { static constexpr int es = 2, bt = BT_UINT16; };
+template<> struct SrcTraits<ST_HALF> { static constexpr int es = 2, bt = BT_HALF; };
+template<> struct SrcTraits<ST_FLOAT> { static constexpr int es = 4, bt = BT_FLOAT; };
+
+// ---- raw 4-element groups ------------------------------------------------
+// float -> 4 words, half/uint16 -> 2 words, uint8 -> 1 word.
+template<int ST>
+__device__ __forceinline__ float4
+convert_raw4(uint4 r)
+{
+    if (ST == ST_FLOAT) {
+        return make_float4(__uint_as_float(r.x), __uint_as_float(r.y),
+                           __uint_as_float(r.z), __uint_as_float(r.w));
+    } else if (ST == ST_HALF) {
+        __half2 a = *reinterpret_cast<__half2*>(&r.x);
+        __half2 b = *reinterpret_cast<__half2*>(&r.y);
+        float2 fa = __half22float2(a), fb = __half22float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    } else if (ST == ST_U16) {
+        const float s = 1.0f / 65535.0f;
+        return make_float4(__fmul_rn(float(r.x & 0xffffu), s),
+                           __fmul_rn(float(r.x >> 16), s),
+                           __fmul_rn(float(r.y & 0xffffu), s),
+                           __fmul_rn(float(r.y >> 16), s));
+    } else {
+        const float s = 1.0f / 255.0f;
+        return make_float4(__fmul_rn(float(r.x & 0xffu), s),
+                           __fmul_rn(float((r.x >> 8) & 0xffu), s),
+                           __fmul_rn(float((r.x >> 16) & 0xffu), s),
+                           __fmul_rn(float(r.x >> 24), s));
+    }
+}
+
+// Synchronous load of elements [e, e+4) of a row (gather mode and the
+// unaligned fallback): vector load when allowed, guarded scalars otherwise.
+template<int ST>
+__device__ __forceinline__ uint4
+load_raw4(const unsigned char* row, int e, int row_elems, bool vec_ok)
+{
+    constexpr int es = SrcTraits<ST>::es;
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (vec_ok && e + 4 <= row_elems) {
+        const void* q = row + (size_t)e * es;
+        if (es == 4) {
+            r = __ldg((const uint4*)q);
+        } else if (es == 2) {
+            uint2 t = __ldg((const uint2*)q);
+            r.x = t.x;
+            r.y = t.y;
+        } else {
+            r.x = __ldg((const unsigned int*)q);
+        }
+    } else {
+        unsigned int w[4] = { 0u, 0u, 0u, 0u };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (e + k < row_elems) {
+                if (es == 4)
+                    w[k] = __ldg((const unsigned int*)(row + (size_t)(e + k) * 4));
+                else if (es == 2)
+                    w[k] = __ldg((const unsigned short*)(row + (size_t)(e + k) * 2));
+                else
+                    w[k] = __ldg(row + e + k);
+            }
+        }
+        if (es == 4)
+            r = make_uint4(w[0], w[1], w[2], w[3]);
+        else if (es == 2) {
+            r.x = w[0] | (w[1] << 16);
+            r.y = w[2] | (w[3] << 16);
+        } else {
+            r.x = w[0] | (w[1] << 8) | (w[2] << 16) | (w[3] << 24);
+        }
+    }
+    return r;
+}
+
+// ---- cp.async (LDGSTS) ---------------------------------------------------
+template<int BYTES>
+__device__ __forceinline__ void
+cp_async_copy(unsigned smem_addr, const void* gsrc)
+{
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr),
+                     "l"(gsrc)
+                     : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr),
+                     "l"(gsrc)
+                     : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr),
+                     "l"(gsrc)
+                     : "memory");
+}
+__device__ __forceinline__ unsigned
+smem_u32(const void* p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+// volatile: the FIFO is written behind the compiler's back by cp.async
+__device__ __forceinline__ uint4
+lds_v4(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2
+lds_v2(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned
+lds_u32(unsigned addr)
+{
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void
+cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template<int N>
+__device__ __forceinline__ void
+cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Flip the low bit of a float4 slot in every other block of 8: a quarter-warp
+// of the H pass reads slots c, c+2, ... c+14 (2:1 downsample) -- slots c and
+// c+8 would share a 16-byte bank group, the flip separates them.  Stride-1
+// patterns stay (nearly) conflict-free as well.
+__device__ __forceinline__ int
+swz(int q)
+{
+    return q ^ ((q >> 3) & 1);
+}
+
+__device__ __forceinline__ void
+fma4(float4& a, float w, const float4& v)
+{
+    a.x = fmaf(w, v.x, a.x);
+    a.y = fmaf(w, v.y, a.y);
+    a.z = fmaf(w, v.z, a.z);
+    a.w = fmaf(w, v.w, a.w);
+}
+
+// ---- H pass over `nb` buffered rows; dst rows dyb .. dyb+nb-1 of the ROI ---
+// hoff[] are BYTE offsets into this thread's first V row (row hr).  The row
+// pitch is a compile-time constant so every LDS below is base + immediate.
+constexpr int FUSED_PITCH_B = FUSED_THREADS * 16;  // bytes per V row
+
+__device__ __forceinline__ bool
+any_nonfinite(float a, float b, float c, float d)
+{
+    float t = (a + b) + (c + d);  // Inf/NaN in any term survives the sum
+    return !(fabsf(t) <= 3.402823466e+38f);
+}
+
+template<int NCH, int HT>
+__device__ __forceinline__ void
+fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
+            int dxg, bool col_active, const int (&hoff)[HT],
+            const float (&hwt)[HT], int hr)
+{
+    if (!col_active)
+        return;
+    const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
+    constexpr int rstep = FUSED_THREADS / FUSED_HCOLS;
+    unsigned char* dp   = p.dst + (long long)(dyb + hr) * p.dst_ystride
+                        + (long long)dxg * (NCH * des);
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < (FUSED_BATCH + rstep - 1) / rstep; ++k) {
+        if (hr + k * rstep < nb) {
+            const unsigned char* row = vrows + k * rstep * FUSED_PITCH_B;
+            if (NCH == 4) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < HT; ++i)
+                    fma4(a, hwt[i], *reinterpret_cast<const float4*>(row + hoff[i]));
+                bad |= any_nonfinite(a.x, a.y, a.z, a.w);
+                if (p.dst_vec_ok) {
+                    if (p.dsttype == BT_FLOAT) {
+                        *reinterpret_cast<float4*>(dp) = a;
+                    } else if (p.dsttype == BT_HALF) {
+                        __half2 h0 = __floats2half2_rn(a.x, a.y);
+                        __half2 h1 = __floats2half2_rn(a.z, a.w);
+                        uint2 u;
+                        u.x = *reinterpret_cast<unsigned int*>(&h0);
+                        u.y = *reinterpret_cast<unsigned int*>(&h1);
+                        *reinterpret_cast<uint2*>(dp) = u;
+                    } else if (p.dsttype == BT_UINT16) {
+                        uint2 u;
+                        u.x = quant_int(a.x, 65535.0f) | (quant_int(a.y, 65535.0f) << 16);
+                        u.y = quant_int(a.z, 65535.0f) | (quant_int(a.w, 65535.0f) << 16);
+                        *reinterpret_cast<uint2*>(dp) = u;
+                    } else {
+                        unsigned int u = quant_int(a.x, 255.0f)
+                                         | (quant_int(a.y, 255.0f) << 8)
+                                         | (quant_int(a.z, 255.0f) << 16)
+                                         | (quant_int(a.w, 255.0f) << 24);
+                        *reinterpret_cast<unsigned int*>(dp) = u;
+                    }
+                } else {
+                    store_elem(dp, p.dsttype, a.x);
+                    store_elem(dp + des, p.dsttype, a.y);
+                    store_elem(dp + 2 * des, p.dsttype, a.z);
+                    store_elem(dp + 3 * des, p.dsttype, a.w);
+                }
+            } else {
+                float a[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    a[c] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < HT; ++i) {
+                    const float* t = reinterpret_cast<const float*>(row + hoff[i]);
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+                        a[c] = fmaf(hwt[i], t[c], a[c]);
+                }
+                float t = 0.0f;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    t += a[c];
+                    store_elem(dp + c * des, p.dsttype, a[c]);
+                }
+                bad |= !(fabsf(t) <= 3.402823466e+38f);
+            }
+            dp += (long long)rstep * p.dst_ystride;
+        }
+    }
+    if (p.check_nonfinite && bad)
+        *p.nonfinite_flag = 1;
+}
+
+// Shared memory carve-up (bytes):
+//   vrows  FUSED_BATCH x FUSED_PITCH_B           V-filtered rows for the H pass
+//   fifo   FUSED_FIFO x FUSED_THREADS x 16       per-thread prefetch   (ring)
+//   ringw  max_band_rows x VKP x 4               ring weights            "
+//   lastr  max_band_dy x 4                       completion rows         "
+template<int ST, int NCH, int VK, int HT>
+__global__ void __launch_bounds__(FUSED_THREADS, 3)
+resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char* vrows  = smem_raw;
+    constexpr int pitch_b = FUSED_PITCH_B;
+    constexpr int es      = SrcTraits<ST>::es;
+
+    const int tid     = threadIdx.x;
+    const Strip strip = p.strips[blockIdx.x];
+    const Band band   = p.bands[blockIdx.y];
+
+    // ---- H-pass per-thread constants: this thread's dst column ----------
+    const int hc          = tid % FUSED_HCOLS;
+    const int hr          = tid / FUSED_HCOLS;
+    const bool col_active = hc < strip.ndx;
+    const int dxg         = strip.dx0 + hc;
+    int hoff[HT];
+    float hwt[HT];
+    {
+        int f = col_active ? p.hfirst[dxg] : 0;
+#pragma unroll
+        for (int i = 0; i < HT; ++i) {
+            hwt[i] = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
+            if (NCH == 4) {
+                int q   = f + i - strip.e0 / 4;
+                hoff[i] = col_active ? swz(q) * 16 + hr * pitch_b : 0;
+            } else {
+                hoff[i] = col_active ? ((f + i) * NCH - strip.e0) * 4 + hr * pitch_b : 0;
+            }
+        }
+    }
+
+    // ---- V-pass per-thread constants: this thread's 4 source elements ---
+    const bool vactive  = tid < strip.nvec;
+    const int e         = strip.e0 + 4 * tid;
+    const int row_elems = p.src_w * NCH;
+    const bool vec_ok   = p.src_vec_ok != 0;
+    unsigned char* vdst = vrows + ((NCH == 4) ? swz(tid) * 16 : tid * 16);
+    const int dy_end    = band.dy0 + band.ndy;
+    int nb              = 0;
+
+    if constexpr (VK > 0) {
+        constexpr int VKP  = (VK + 3) & ~3;  // ring row stride (float4 loads)
+        constexpr int SLOT = FUSED_THREADS * 16;  // bytes between FIFO rows
+        // fixed-offset regions first, so their addresses are compile-time
+        // offsets from the dynamic shared memory base
+        unsigned char* fifo = smem_raw + FUSED_BATCH * FUSED_PITCH_B;
+        float* ringw = reinterpret_cast<float*>(fifo + FUSED_FIFO * SLOT);
+        int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
+
+        // stage this band's ring weights and completion rows
+        const float* gw = p.vring + (size_t)band.woff * VKP;
+        for (int i = tid; i < band.nrows * VKP; i += FUSED_THREADS)
+            ringw[i] = gw[i];
+        for (int i = tid; i < band.ndy; i += FUSED_THREADS)
+            lastr[i] = p.vlast[band.dy0 + i];
+
+        float4 acc[VK];
+#pragma unroll
+        for (int k = 0; k < VK; ++k)
+            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        const int rend = band.r0 + band.nrows;
+        // cp.async needs the global address aligned to the copy size (the host
+        // sets src_vec_ok only when rows and strips are 4-element aligned) and
+        // every staged group inside the row; a ragged last strip takes the
+        // synchronous guarded loads instead (uniform per CTA)
+        const bool async_ok
+            = vec_ok
+              && ((row_elems & 3) == 0 || strip.e0 + 4 * strip.nvec <= row_elems);
+        // groups that lie entirely past the end of the row (tap padding of the
+        // last strip) are never fetched: their FIFO slots stay zero
+        const bool vfetch = vactive && e + 4 <= row_elems;
+        // this thread's FIFO column, as a 32-bit shared-window address
+        unsigned fifo_s;
+        {
+            // opaque move: keeps the address in a register (under the register
+            // cap the compiler otherwise recomputes it every row)
+            unsigned t = smem_u32(fifo) + tid * 16;
+            asm volatile("mov.u32 %0, %1;" : "=r"(fifo_s) : "r"(t));
+        }
+
+        // running state of the prefetcher: next row to fetch, its address,
+        // its FIFO slot
+        const unsigned char* gnext = p.src + (size_t)e * es
+                                     + (long long)band.r0 * p.src_ystride;
+        int rnext     = band.r0;
+        int slot_next = 0;
+        auto issue_next = [&]() {
+            if (vfetch && rnext < rend)
+                cp_async_copy<4 * es>(fifo_s + slot_next, gnext);
+            cp_async_commit();
+            gnext += p.src_ystride;
+            ++rnext;
+            slot_next = (slot_next + SLOT) & (FUSED_FIFO * SLOT - 1);
+        };
+        int slot_cur = 0;
+        auto fifo_pop = [&]() -> uint4 {
+            uint4 raw;
+            if (es == 4)
+                raw = lds_v4(fifo_s + slot_cur);
+            else if (es == 2) {
+                uint2 t = lds_v2(fifo_s + slot_cur);
+                raw     = make_uint4(t.x, t.y, 0u, 0u);
+            } else {
+                raw = make_uint4(lds_u32(fifo_s + slot_cur), 0u, 0u, 0u);
+            }
+            slot_cur = (slot_cur + SLOT) & (FUSED_FIFO * SLOT - 1);
+            return raw;
+        };
+        // one source row: scatter it into the VK open destination rows
+        auto accumulate = [&](const uint4& raw, const float4* wr) {
+            const float4 v = convert_raw4<ST>(raw);
+            float w[VKP];
+#pragma unroll
+            for (int k = 0; k < VKP / 4; ++k) {
+                float4 t     = wr[k];
+                w[4 * k]     = t.x;
+                w[4 * k + 1] = t.y;
+                w[4 * k + 2] = t.z;
+                w[4 * k + 3] = t.w;
+            }
+#pragma unroll
+            for (int k = 0; k < VK; ++k)
+                fma4(acc[k], w[k], v);
+        };
+        // a destination row is complete: park it for the H pass
+        auto emit = [&](int s, int dy_done) {
+            if (vactive)
+                *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = acc[s];
+            acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ++nb;
+            if (nb == FUSED_BATCH || dy_done == dy_end) {
+                __syncthreads();
+                fused_hpass<NCH, HT>(p, vrows, nb, dy_done - nb, dxg, col_active, hoff,
+                                     hwt, hr);
+                __syncthreads();
+                nb = 0;
+            }
+        };
+
+        int r              = band.r0;
+        const float4* wrow = reinterpret_cast<const float4*>(ringw);
+        const int* lastp   = lastr;
+        if (async_ok) {
+            if (!vfetch) {
+#pragma unroll
+                for (int q = 0; q < FUSED_FIFO; ++q)
+                    *reinterpret_cast<uint4*>(fifo + tid * 16 + q * SLOT)
+                        = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int q = 0; q < FUSED_FIFO; ++q)
+                issue_next();
+            cp_async_wait<FUSED_FIFO - 1>();  // first row landed
+            uint4 rawA = fifo_pop(), rawB = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();  // ringw / lastr visible
+            // Software pipeline: the row being accumulated was popped one
+            // step earlier; its FIFO slot is refilled and the NEXT row popped
+            // before the FMAs so the LDS latency hides behind them.  Two
+            // steps per trip so the two register sets swap roles for free.
+            auto step = [&](const uint4& cur, uint4& nxt) {
+                issue_next();
+                cp_async_wait<FUSED_FIFO - 1>();
+                nxt = fifo_pop();
+                accumulate(cur, wrow);
+                wrow += VKP / 4;
+            };
+            for (int dy = band.dy0; dy < dy_end; dy += VK) {
+#pragma unroll
+                for (int s = 0; s < VK; ++s) {
+                    if (dy + s < dy_end) {
+                        const int last = *lastp++;
+                        for (; r < last; r += 2) {
+                            step(rawA, rawB);
+                            step(rawB, rawA);
+                        }
+                        if (r == last) {
+                            step(rawA, rawB);
+                            rawA = rawB;
+                            ++r;
+                        }
+                        emit(s, dy + s + 1);
+                    }
+                }
+            }
+        } else {
+            __syncthreads();  // ringw / lastr visible
+            for (int dy = band.dy0; dy < dy_end; dy += VK) {
+#pragma unroll
+                for (int s = 0; s < VK; ++s) {
+                    if (dy + s < dy_end) {
+                        const int last = *lastp++;
+                        for (; r <= last; ++r) {
+                            uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+                            if (vactive)
+                                raw = load_raw4<ST>(p.src + (long long)r * p.src_ystride,
+                                                    e, row_elems, false);
+                            accumulate(raw, wrow);
+                            wrow += VKP / 4;
+                        }
+                        emit(s, dy + s + 1);
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+    } else {
+        // gather mode: each dst row reads its own vt source rows (upsampling:
+        // consecutive dst rows share rows, which stay in L1/L2)
+        for (int dy = band.dy0; dy < dy_end; ++dy) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vactive) {
+                const int first = p.vfirst[dy];
+                const float* w  = p.vw + (size_t)dy * p.vt;
+                const unsigned char* rowp
+                    = p.src + (long long)first * p.src_ystride;
+                for (int j = 0; j < p.vt; ++j) {
+                    uint4 raw = load_raw4<ST>(rowp, e, row_elems, vec_ok);
+                    fma4(a, __ldg(w + j), convert_raw4<ST>(raw));
+                    rowp += p.src_ystride;
+                }
+                *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = a;
+            }
+            ++nb;
+            if (nb == FUSED_BATCH || dy + 1 == dy_end) {
+                __syncthreads();
+                fused_hpass<NCH, HT>(p, vrows, nb, dy + 1 - nb, dxg, col_active,
+                                     hoff, hwt, hr);
+                __syncthreads();
+                nb = 0;
+            }
+        }
+    }
+}
+
+}  // namespace b2r

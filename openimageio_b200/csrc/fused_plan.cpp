@@ -121,11 +121,13 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     const int min_rows = 8;
     nbands             = std::min(nbands, std::max(1, H / min_rows));
     // ring weights live in shared memory: keep a band's source rows bounded
-    const int max_rows_smem = use_ring ? (24 * 1024 / (4 * vk)) : INT_MAX;
+    const int vkp           = (vk + 3) & ~3;  // padded ring row (float4 loads)
+    const int max_rows_smem = use_ring ? (24 * 1024 / (4 * std::max(4, vkp))) : INT_MAX;
     for (;;) {
         bool ok = true;
         P.bands.clear();
         P.max_band_rows = 0;
+        P.max_band_dy   = 0;
         int woff        = 0;
         for (int b = 0; b < nbands; ++b) {
             Band bd;
@@ -137,6 +139,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
             bd.r0    = first[bd.dy0];
             bd.nrows = last[e - 1] - bd.r0 + 1;
             bd.woff  = woff;
+            P.max_band_dy = std::max(P.max_band_dy, bd.ndy);
             if (use_ring) {
                 if (bd.nrows > max_rows_smem) {
                     ok = false;
@@ -161,13 +164,13 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         size_t total = 0;
         for (const Band& b : P.bands)
             total += size_t(b.nrows);
-        P.vring.assign(total * vk, 0.0f);
+        P.vring.assign(total * vkp, 0.0f);
         for (const Band& b : P.bands) {
             for (int k = b.dy0; k < b.dy0 + b.ndy; ++k) {
                 int slot = (k - b.dy0) % vk;
                 for (int j = 0; j < gy.count[k]; ++j) {
                     int r = gy.first[k] + j;
-                    P.vring[(size_t(b.woff) + (r - b.r0)) * vk + slot]
+                    P.vring[(size_t(b.woff) + (r - b.r0)) * vkp + slot]
                         = gy.w[gy.woff[k] + j];
                 }
             }

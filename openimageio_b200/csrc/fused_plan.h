@@ -23,6 +23,7 @@ struct FusedPlan {
     std::vector<int32_t> vfirst;
     std::vector<float> vw;
     int max_band_rows = 0;
+    int max_band_dy   = 0;
     int max_nvec      = 0;
     bool interior_zero = false;
 };

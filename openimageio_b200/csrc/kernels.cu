@@ -16,60 +16,15 @@
 //
 // No tensor cores: this is a banded gather-FMA bounded by HBM bandwidth.
 #include "kernels.h"
+#include "dev_convert.cuh"
 
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 
 namespace b2r {
-
-// ------------------------------------------------------------------------
-// type conversion: convert_type<S,float> / convert_type<float,D>
-// (src/include/OpenImageIO/fmath.h:753-764, 1009-1031).  Explicit _rn
-// intrinsics keep nvcc from contracting v*max+0.5 into one FMA, which would
-// round differently from the reference's multiply-then-add.
-// ------------------------------------------------------------------------
-__device__ __forceinline__ float
-load_elem(const unsigned char* p, int bt)
-{
-    switch (bt) {
-    case BT_UINT8: return __fmul_rn(float(*p), 1.0f / 255.0f);
-    case BT_UINT16:
-        return __fmul_rn(float(*(const unsigned short*)p), 1.0f / 65535.0f);
-    case BT_HALF: return __half2float(*(const __half*)p);
-    default: return *(const float*)p;
-    }
-}
-
-__device__ __forceinline__ unsigned int
-quant_int(float v, float mx)
-{
-    float s = __fmul_rn(v, mx);
-    s       = __fadd_rn(s, (s < 0.0f) ? -0.5f : 0.5f);
-    if (!(0.0f <= s))  // also catches NaN -> 0
-        s = 0.0f;
-    if (s > mx)
-        s = mx;
-    return (unsigned int)s;  // truncation
-}
-
-__device__ __forceinline__ void
-store_elem(unsigned char* p, int bt, float v)
-{
-    switch (bt) {
-    case BT_UINT8: *p = (unsigned char)quant_int(v, 255.0f); break;
-    case BT_UINT16: *(unsigned short*)p = (unsigned short)quant_int(v, 65535.0f); break;
-    case BT_HALF: *(__half*)p = __float2half_rn(v); break;
-    default: *(float*)p = v; break;
-    }
-}
-
-__device__ __forceinline__ bool
-nonfinite(float v)
-{
-    return (__float_as_uint(v) & 0x7f800000u) == 0x7f800000u;
-}
 
 // ------------------------------------------------------------------------
 // exact kernel
@@ -130,13 +85,16 @@ resize_exact_kernel(ExactParams p)
 {
     if (p.gate && *p.gate == 0)
         return;
-    const int roi_w = p.roi_x1 - p.roi_x0;
+    const int roi_w   = p.roi_x1 - p.roi_x0;
+    const int roi_h   = p.roi_y1 - p.roi_y0;
     const int xblocks = (roi_w + blockDim.x - 1) / blockDim.x;
-    const int kx      = (blockIdx.x % xblocks) * blockDim.x + threadIdx.x;
-    const int ky      = blockIdx.x / xblocks;
-    const int c0    = blockIdx.z * EXACT_CH;
+    const int c0      = blockIdx.z * EXACT_CH;
+    for (long long tile = blockIdx.x; tile < (long long)xblocks * roi_h;
+         tile += gridDim.x) {
+    const int kx = int(tile % xblocks) * blockDim.x + threadIdx.x;
+    const int ky = int(tile / xblocks);
     if (kx >= roi_w)
-        return;
+        continue;
     const int nc  = min(EXACT_CH, p.nch - c0);
     const int ses = (p.src.basetype == BT_UINT8) ? 1 : (p.src.basetype == BT_FLOAT ? 4 : 2);
     const int des = (p.dst.basetype == BT_UINT8) ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
@@ -224,6 +182,7 @@ resize_exact_kernel(ExactParams p)
     for (int c = 0; c < EXACT_CH; ++c)
         if (c < nc)
             store_elem(dp + c * des, p.dst.basetype, zero_out ? 0.0f : pel[c]);
+    }  // tile loop
 }
 
 void
@@ -233,445 +192,108 @@ launch_resize_exact(const ExactParams& p, void* stream)
     if (roi_w <= 0 || roi_h <= 0)
         return;
     dim3 block(128, 1, 1);
-    dim3 grid(((roi_w + 127) / 128) * roi_h, 1, (p.nch + EXACT_CH - 1) / EXACT_CH);
+    long long tiles = (long long)((roi_w + 127) / 128) * roi_h;
+    // grid-stride: enough CTAs to fill the machine, few enough that a launch
+    // gated off by *p.gate == 0 retires in a few microseconds
+    dim3 grid((unsigned)std::min<long long>(tiles, 148 * 16), 1,
+              (p.nch + EXACT_CH - 1) / EXACT_CH);
     resize_exact_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
 }
 
 
+
 // ------------------------------------------------------------------------
-// fused two-pass kernel
+// fused kernel dispatch: the instantiations live in fused_inst.cu, compiled
+// once per (source type, channel count) so the build parallelises.
 // ------------------------------------------------------------------------
-// Raw 4-element group as loaded from global memory (not yet converted):
-// float -> 4 words, half/uint16 -> 2 words, uint8 -> 1 word.
-__device__ __forceinline__ uint4
-ldg_stream_v4(const void* p)
-{
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint2
-ldg_stream_v2(const void* p)
-{
-    uint2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
-                 : "=r"(r.x), "=r"(r.y)
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ unsigned int
-ldg_stream_u32(const void* p)
-{
-    unsigned int r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
+#define B2R_DECL_LOOKUP(ST, NCH) \
+    FusedKernel fused_lookup_##ST##_##NCH(int vk, int ht);
+#define B2R_DECL_ST(ST) \
+    B2R_DECL_LOOKUP(ST, 1) B2R_DECL_LOOKUP(ST, 2) B2R_DECL_LOOKUP(ST, 3) B2R_DECL_LOOKUP(ST, 4)
+B2R_DECL_ST(0) B2R_DECL_ST(1) B2R_DECL_ST(2) B2R_DECL_ST(3)
 
-// Load elements [e, e+4) of a source row.  STREAM: bypass L1 (each row is
-// read once per strip); otherwise allocate in L1 (gather mode re-reads rows).
-template<bool STREAM>
-__device__ __forceinline__ uint4
-load_raw4(const unsigned char* row, int e, int row_elems, int bt, bool vec_ok)
+static int
+st_index(int basetype)
 {
-    uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    if (vec_ok && e + 4 <= row_elems) {
-        if (bt == BT_FLOAT) {
-            const void* q = row + (size_t)e * 4;
-            r = STREAM ? ldg_stream_v4(q) : __ldg((const uint4*)q);
-        } else if (bt == BT_UINT8) {
-            const void* q = row + e;
-            r.x = STREAM ? ldg_stream_u32(q) : __ldg((const unsigned int*)q);
-        } else {
-            const void* q = row + (size_t)e * 2;
-            uint2 t = STREAM ? ldg_stream_v2(q) : __ldg((const uint2*)q);
-            r.x     = t.x;
-            r.y     = t.y;
-        }
-    } else {
-        unsigned int w[4] = { 0u, 0u, 0u, 0u };
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (e + k < row_elems) {
-                if (bt == BT_FLOAT)
-                    w[k] = __ldg((const unsigned int*)(row + (size_t)(e + k) * 4));
-                else if (bt == BT_UINT8)
-                    w[k] = __ldg(row + e + k);
-                else
-                    w[k] = __ldg((const unsigned short*)(row + (size_t)(e + k) * 2));
-            }
-        }
-        if (bt == BT_FLOAT)
-            r = make_uint4(w[0], w[1], w[2], w[3]);
-        else if (bt == BT_UINT8)
-            r.x = w[0] | (w[1] << 8) | (w[2] << 16) | (w[3] << 24);
-        else {
-            r.x = w[0] | (w[1] << 16);
-            r.y = w[2] | (w[3] << 16);
-        }
+    switch (basetype) {
+    case BT_UINT8: return 0;
+    case BT_UINT16: return 1;
+    case BT_HALF: return 2;
+    case BT_FLOAT: return 3;
     }
-    return r;
+    return -1;
 }
 
-__device__ __forceinline__ float4
-convert_raw4(uint4 r, int bt)
-{
-    float4 v;
-    if (bt == BT_FLOAT) {
-        v = make_float4(__uint_as_float(r.x), __uint_as_float(r.y),
-                        __uint_as_float(r.z), __uint_as_float(r.w));
-    } else if (bt == BT_HALF) {
-        __half2 a = *reinterpret_cast<__half2*>(&r.x);
-        __half2 b = *reinterpret_cast<__half2*>(&r.y);
-        float2 fa = __half22float2(a), fb = __half22float2(b);
-        v = make_float4(fa.x, fa.y, fb.x, fb.y);
-    } else if (bt == BT_UINT16) {
-        const float s = 1.0f / 65535.0f;
-        v = make_float4(__fmul_rn(float(r.x & 0xffffu), s),
-                        __fmul_rn(float(r.x >> 16), s),
-                        __fmul_rn(float(r.y & 0xffffu), s),
-                        __fmul_rn(float(r.y >> 16), s));
-    } else {
-        const float s = 1.0f / 255.0f;
-        v = make_float4(__fmul_rn(float(r.x & 0xffu), s),
-                        __fmul_rn(float((r.x >> 8) & 0xffu), s),
-                        __fmul_rn(float((r.x >> 16) & 0xffu), s),
-                        __fmul_rn(float(r.x >> 24), s));
-    }
-    return v;
-}
-
-// Rotate each block of 8 float4 slots by its block index so that the
-// stride-2 (2:1 downsample) and stride-1 access patterns of the H pass are
-// both free of bank conflicts.
-__device__ __forceinline__ int
-swz(int q)
-{
-    return (q & ~7) | ((q + (q >> 3)) & 7);
-}
-
-__device__ __forceinline__ void
-fma4(float4& a, float w, const float4& v)
-{
-    a.x = fmaf(w, v.x, a.x);
-    a.y = fmaf(w, v.y, a.y);
-    a.z = fmaf(w, v.z, a.z);
-    a.w = fmaf(w, v.w, a.w);
-}
-
-constexpr int FUSED_PREFETCH = 4;  // source rows in flight per thread
-
-// H pass over `nb` buffered rows; dst rows dyb .. dyb+nb-1 of the ROI.
-template<int NCH, int HT>
-__device__ __forceinline__ void
-fused_hpass(const FusedParams& p, const float* vrows, int pitch_f, int nb,
-            int dyb, int dxg, bool col_active, const int (&hoff)[HT],
-            const float (&hwt)[HT], int hr)
-{
-    if (!col_active)
-        return;
-    const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
-    for (int b = hr; b < nb; b += FUSED_THREADS / FUSED_HCOLS) {
-        const float* row = vrows + (size_t)b * pitch_f;
-        unsigned char* dp = p.dst + (long long)(dyb + b) * p.dst_ystride
-                            + (long long)dxg * (NCH * des);
-        if (NCH == 4) {
-            const float4* row4 = reinterpret_cast<const float4*>(row);
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < HT; ++i)
-                fma4(a, hwt[i], row4[hoff[i]]);
-            if (p.check_nonfinite
-                && (nonfinite(a.x) || nonfinite(a.y) || nonfinite(a.z)
-                    || nonfinite(a.w)))
-                *p.nonfinite_flag = 1;
-            if (p.dst_vec_ok) {
-                if (p.dsttype == BT_FLOAT) {
-                    *reinterpret_cast<float4*>(dp) = a;
-                } else if (p.dsttype == BT_HALF) {
-                    __half2 h0 = __floats2half2_rn(a.x, a.y);
-                    __half2 h1 = __floats2half2_rn(a.z, a.w);
-                    uint2 u;
-                    u.x = *reinterpret_cast<unsigned int*>(&h0);
-                    u.y = *reinterpret_cast<unsigned int*>(&h1);
-                    *reinterpret_cast<uint2*>(dp) = u;
-                } else if (p.dsttype == BT_UINT16) {
-                    uint2 u;
-                    u.x = quant_int(a.x, 65535.0f) | (quant_int(a.y, 65535.0f) << 16);
-                    u.y = quant_int(a.z, 65535.0f) | (quant_int(a.w, 65535.0f) << 16);
-                    *reinterpret_cast<uint2*>(dp) = u;
-                } else {
-                    unsigned int u = quant_int(a.x, 255.0f)
-                                     | (quant_int(a.y, 255.0f) << 8)
-                                     | (quant_int(a.z, 255.0f) << 16)
-                                     | (quant_int(a.w, 255.0f) << 24);
-                    *reinterpret_cast<unsigned int*>(dp) = u;
-                }
-            } else {
-                store_elem(dp, p.dsttype, a.x);
-                store_elem(dp + des, p.dsttype, a.y);
-                store_elem(dp + 2 * des, p.dsttype, a.z);
-                store_elem(dp + 3 * des, p.dsttype, a.w);
-            }
-        } else {
-            float a[NCH];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                a[c] = 0.0f;
-#pragma unroll
-            for (int i = 0; i < HT; ++i) {
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-                    a[c] = fmaf(hwt[i], row[hoff[i] + c], a[c]);
-            }
-            bool bad = false;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                bad |= nonfinite(a[c]);
-                store_elem(dp + c * des, p.dsttype, a[c]);
-            }
-            if (p.check_nonfinite && bad)
-                *p.nonfinite_flag = 1;
-        }
-    }
-}
-
-template<int NCH, int VK, int HT>
-__global__ void __launch_bounds__(FUSED_THREADS, 2)
-resize_fused_kernel(const FusedParams p, int pitch_f)
-{
-    extern __shared__ __align__(16) float smem[];
-    float* vrows  = smem;                                   // FUSED_BATCH * pitch_f
-    float* ringw  = smem + (size_t)FUSED_BATCH * pitch_f;   // band rows * VK
-
-    const int tid     = threadIdx.x;
-    const Strip strip = p.strips[blockIdx.x];
-    const Band band   = p.bands[blockIdx.y];
-
-    // ---- H-pass per-thread constants: this thread's dst column ----------
-    const int hc          = tid % FUSED_HCOLS;
-    const int hr          = tid / FUSED_HCOLS;
-    const bool col_active = hc < strip.ndx;
-    const int dxg         = strip.dx0 + hc;
-    int hoff[HT];
-    float hwt[HT];
-    {
-        int f = col_active ? p.hfirst[dxg] : 0;
-#pragma unroll
-        for (int i = 0; i < HT; ++i) {
-            hwt[i] = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
-            if (NCH == 4) {
-                int q   = f + i - strip.e0 / 4;
-                hoff[i] = col_active ? swz(q) : 0;
-            } else {
-                hoff[i] = col_active ? (f + i) * NCH - strip.e0 : 0;
-            }
-        }
-    }
-
-    // ---- V-pass per-thread constants: this thread's 4 source elements ---
-    const bool vactive   = tid < strip.nvec;
-    const int e          = strip.e0 + 4 * tid;
-    const int row_elems  = p.src_w * p.nch;
-    const bool vec_ok    = p.src_vec_ok != 0;
-    const int vslot      = (NCH == 4) ? swz(tid) * 4 : tid * 4;  // float index
-    const int dy_end     = band.dy0 + band.ndy;
-    int dy               = band.dy0;
-    int nb               = 0;
-
-    if (VK > 0) {
-        // stage this band's ring weights
-        const float* gw = p.vring + (size_t)band.woff * VK;
-        for (int i = tid; i < band.nrows * VK; i += FUSED_THREADS)
-            ringw[i] = gw[i];
-        __syncthreads();
-
-        float4 acc[VK > 0 ? VK : 1];
-#pragma unroll
-        for (int k = 0; k < VK; ++k)
-            acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        const int rend = band.r0 + band.nrows;
-        int slot       = 0;
-        int nextlast   = p.vlast[dy];
-        const unsigned char* rowp = p.src + (long long)band.r0 * p.src_ystride;
-
-        uint4 cur[FUSED_PREFETCH];
-#pragma unroll
-        for (int q = 0; q < FUSED_PREFETCH; ++q) {
-            cur[q] = make_uint4(0u, 0u, 0u, 0u);
-            if (vactive && band.r0 + q < rend)
-                cur[q] = load_raw4<true>(rowp + (long long)q * p.src_ystride, e,
-                                         row_elems, p.srctype, vec_ok);
-        }
-        for (int r = band.r0; r < rend; r += FUSED_PREFETCH) {
-            uint4 nxt[FUSED_PREFETCH];
-#pragma unroll
-            for (int q = 0; q < FUSED_PREFETCH; ++q) {
-                nxt[q] = make_uint4(0u, 0u, 0u, 0u);
-                if (vactive && r + FUSED_PREFETCH + q < rend)
-                    nxt[q] = load_raw4<true>(
-                        rowp + (long long)(FUSED_PREFETCH + q) * p.src_ystride, e,
-                        row_elems, p.srctype, vec_ok);
-            }
-            rowp += (long long)FUSED_PREFETCH * p.src_ystride;
-#pragma unroll
-            for (int q = 0; q < FUSED_PREFETCH; ++q) {
-                const int rr = r + q;
-                if (rr < rend) {
-                    const float4 v = convert_raw4(cur[q], p.srctype);
-                    const float* w = ringw + (size_t)(rr - band.r0) * VK;
-#pragma unroll
-                    for (int k = 0; k < VK; ++k)
-                        fma4(acc[k], w[k], v);
-                    while (dy < dy_end && nextlast == rr) {
-                        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                        switch (slot) {
-#define B2R_EMIT_CASE(K_)                                 \
-    case K_:                                              \
-        if (K_ < VK) {                                    \
-            o       = acc[K_ < VK ? K_ : 0];              \
-            acc[K_ < VK ? K_ : 0] = make_float4(0.f, 0.f, 0.f, 0.f); \
-        }                                                 \
-        break;
-                            B2R_EMIT_CASE(0)
-                            B2R_EMIT_CASE(1)
-                            B2R_EMIT_CASE(2)
-                            B2R_EMIT_CASE(3)
-                            B2R_EMIT_CASE(4)
-                            B2R_EMIT_CASE(5)
-                            B2R_EMIT_CASE(6)
-                            B2R_EMIT_CASE(7)
-#undef B2R_EMIT_CASE
-                        default: break;
-                        }
-                        slot = (slot + 1 == VK) ? 0 : slot + 1;
-                        if (vactive)
-                            *reinterpret_cast<float4*>(vrows + (size_t)nb * pitch_f
-                                                       + vslot)
-                                = o;
-                        ++nb;
-                        ++dy;
-                        nextlast = (dy < dy_end) ? p.vlast[dy] : -1;
-                        if (nb == FUSED_BATCH || dy == dy_end) {
-                            __syncthreads();
-                            fused_hpass<NCH, HT>(p, vrows, pitch_f, nb, dy - nb, dxg,
-                                                 col_active, hoff, hwt, hr);
-                            __syncthreads();
-                            nb = 0;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < FUSED_PREFETCH; ++q)
-                cur[q] = nxt[q];
-        }
-    } else {
-        // gather mode: each dst row reads its own vt source rows (upsampling:
-        // consecutive dst rows share rows, which stay in L1/L2)
-        for (; dy < dy_end; ++dy) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vactive) {
-                const int first = p.vfirst[dy];
-                const float* w  = p.vw + (size_t)dy * p.vt;
-                const unsigned char* rowp
-                    = p.src + (long long)first * p.src_ystride;
-                for (int j = 0; j < p.vt; ++j) {
-                    uint4 raw = load_raw4<false>(rowp, e, row_elems, p.srctype,
-                                                 vec_ok);
-                    fma4(a, __ldg(w + j), convert_raw4(raw, p.srctype));
-                    rowp += p.src_ystride;
-                }
-                *reinterpret_cast<float4*>(vrows + (size_t)nb * pitch_f + vslot) = a;
-            }
-            ++nb;
-            if (nb == FUSED_BATCH || dy + 1 == dy_end) {
-                __syncthreads();
-                fused_hpass<NCH, HT>(p, vrows, pitch_f, nb, dy + 1 - nb, dxg,
-                                     col_active, hoff, hwt, hr);
-                __syncthreads();
-                nb = 0;
-            }
-        }
-    }
-}
-
-typedef void (*FusedKernel)(const FusedParams, int);
-
-template<int NCH, int VK>
 static FusedKernel
-pick_ht(int ht)
+pick_fused(int srctype, int nch, int vk, int ht)
 {
-    switch (ht) {
-    case 4: return resize_fused_kernel<NCH, VK, 4>;
-    case 8: return resize_fused_kernel<NCH, VK, 8>;
-    case 12: return resize_fused_kernel<NCH, VK, 12>;
-    case 16: return resize_fused_kernel<NCH, VK, 16>;
-    }
-    return nullptr;
-}
-template<int NCH>
-static FusedKernel
-pick_vk(int vk, int ht)
-{
-    switch (vk) {
-    case 0: return pick_ht<NCH, 0>(ht);
-    case 2: return pick_ht<NCH, 2>(ht);
-    case 4: return pick_ht<NCH, 4>(ht);
-    case 6: return pick_ht<NCH, 6>(ht);
-    case 8: return pick_ht<NCH, 8>(ht);
-    }
-    return nullptr;
-}
-static FusedKernel
-pick_fused(int nch, int vk, int ht)
-{
-    switch (nch) {
-    case 1: return pick_vk<1>(vk, ht);
-    case 2: return pick_vk<2>(vk, ht);
-    case 3: return pick_vk<3>(vk, ht);
-    case 4: return pick_vk<4>(vk, ht);
-    }
-    return nullptr;
+    typedef FusedKernel (*Lookup)(int, int);
+#define B2R_ROW(ST) \
+    { fused_lookup_##ST##_1, fused_lookup_##ST##_2, fused_lookup_##ST##_3, fused_lookup_##ST##_4 }
+    static const Lookup table[4][4] = { B2R_ROW(0), B2R_ROW(1), B2R_ROW(2), B2R_ROW(3) };
+    int st = st_index(srctype);
+    if (st < 0 || nch < 1 || nch > 4)
+        return nullptr;
+    return table[st][nch - 1](vk, ht);
 }
 
 bool
-fused_supported(int nch, int vk, int ht)
+fused_supported(int srctype, int nch, int vk, int ht)
 {
-    return pick_fused(nch, vk, ht) != nullptr;
+    return pick_fused(srctype, nch, vk, ht) != nullptr;
 }
 
-static int
-fused_pitch(int max_nvec)
+int
+fused_ctas_per_sm(const FusedParams& p, int max_band_rows, int max_band_dy,
+                  int max_nvec)
 {
-    return ((max_nvec + 7) / 8) * 8 * 4;  // floats; multiple of 8 float4 slots
+    FusedKernel k = pick_fused(p.srctype, p.nch, p.vk, p.ht);
+    if (!k)
+        return 0;
+    size_t smem = fused_smem_bytes(p, max_band_rows, max_band_dy, max_nvec);
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute((const void*)k,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void*)k,
+                                                      FUSED_THREADS, smem)
+        != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
 }
 
 size_t
-fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_nvec)
+fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
+                 int max_nvec)
 {
-    size_t f = (size_t)FUSED_BATCH * fused_pitch(max_nvec);
-    if (p.vk > 0)
-        f += (size_t)max_band_rows * p.vk;
+    (void)max_nvec;
+    size_t f = (size_t)FUSED_BATCH * FUSED_THREADS * 4;
+    if (p.vk > 0) {
+        f += (size_t)max_band_rows * ((p.vk + 3) & ~3);
+        f += (size_t)((max_band_dy + 3) & ~3);
+        f += (size_t)FUSED_FIFO * FUSED_THREADS * 4;
+    }
     return f * sizeof(float);
 }
 
 void
-launch_resize_fused(const FusedParams& p, int max_band_rows, int max_nvec,
-                    void* stream)
+launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
+                    int max_nvec, void* stream)
 {
-    FusedKernel k = pick_fused(p.nch, p.vk, p.ht);
+    FusedKernel k = pick_fused(p.srctype, p.nch, p.vk, p.ht);
     if (!k || p.nstrips <= 0 || p.nbands <= 0)
         return;
-    size_t smem = fused_smem_bytes(p, max_band_rows, max_nvec);
+    size_t smem = fused_smem_bytes(p, max_band_rows, max_band_dy, max_nvec);
     if (smem > 48 * 1024)
         cudaFuncSetAttribute((const void*)k,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
     dim3 grid(p.nstrips, p.nbands, 1);
-    k<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p, fused_pitch(max_nvec));
+    k<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p, max_band_rows,
+                                                           max_band_dy);
 }
 
 }  // namespace b2r

@@ -69,7 +69,8 @@ struct Band {
 
 constexpr int FUSED_THREADS = 256;
 constexpr int FUSED_HCOLS   = 128;  // dst columns per strip (H-pass threads per row)
-constexpr int FUSED_BATCH   = 8;    // V-filtered rows buffered between passes
+constexpr int FUSED_BATCH   = 6;    // V-filtered rows buffered between passes
+constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
 
 struct FusedParams {
     const unsigned char* src;  // data-window origin, pixels contiguous in x
@@ -100,14 +101,20 @@ struct FusedParams {
     const int* vfirst;   // [roi_h]
     const float* vw;     // [roi_h * vt]
 };
-// Returns false when no instantiation matches (nch, vk, ht).
+// Returns false when no instantiation matches (srctype, nch, vk, ht).
 bool
-fused_supported(int nch, int vk, int ht);
+fused_supported(int srctype, int nch, int vk, int ht);
+typedef void (*FusedKernel)(const FusedParams, int, int);
+// resident CTAs per SM for this shape (occupancy query), 0 on error
+int
+fused_ctas_per_sm(const FusedParams& p, int max_band_rows, int max_band_dy,
+                  int max_nvec);
 size_t
-fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_nvec);
+fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
+                 int max_nvec);
 void
-launch_resize_fused(const FusedParams& p, int max_band_rows, int max_nvec,
-                    void* stream);
+launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
+                    int max_nvec, void* stream);
 
 // ------------------------------------------------------------- resample ----
 struct ResampleParams {
