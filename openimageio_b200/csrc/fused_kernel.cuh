@@ -168,29 +168,41 @@ cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// Flip the low bit of a float4 slot in every other block of 8: a quarter-warp
-// of the H pass reads slots c, c+2, ... c+14 (2:1 downsample) -- slots c and
-// c+8 would share a 16-byte bank group, the flip separates them.  Stride-1
-// patterns stay (nearly) conflict-free as well.
+// V rows of RGBA pixels are stored even/odd planar: pixel q of the strip goes
+// to plane (q & 1), index q >> 1; the odd plane starts 4 slots past a multiple
+// of 8 so the two planes sit in different 16-byte bank groups.  A quarter-warp
+// of the H pass reads pixels c, c+2, ... (2:1 downsample: one plane,
+// consecutive slots) or c, c+1, ... (1:1 / upsample: the planes interleave
+// bank groups 0,4,1,5,...): both conflict-free.  And a thread's taps become
+// base + immediate: even taps from one plane, odd taps from the other.
+constexpr int FUSED_PLANE_B = (FUSED_THREADS / 2 + 4) * 16;  // odd-plane offset
 __device__ __forceinline__ int
-swz(int q)
+planar_byte(int q)
 {
-    return q ^ ((q >> 3) & 1);
+    return (q >> 1) * 16 + (q & 1) * FUSED_PLANE_B;
 }
 
+// Blackwell packed FP32: one FFMA2 instruction does two fused multiply-adds
+// on 64-bit register pairs -- half the issue slots of scalar FFMA for the
+// same arithmetic (each lane result is the same correctly rounded fma).
+__device__ __forceinline__ void
+fma4(float4& a, float2 ww, const float4& v)
+{
+    float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y), make_float2(a.x, a.y));
+    float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w), make_float2(a.z, a.w));
+    a         = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
 __device__ __forceinline__ void
 fma4(float4& a, float w, const float4& v)
 {
-    a.x = fmaf(w, v.x, a.x);
-    a.y = fmaf(w, v.y, a.y);
-    a.z = fmaf(w, v.z, a.z);
-    a.w = fmaf(w, v.w, a.w);
+    fma4(a, make_float2(w, w), v);
 }
 
 // ---- H pass over `nb` buffered rows; dst rows dyb .. dyb+nb-1 of the ROI ---
-// hoff[] are BYTE offsets into this thread's first V row (row hr).  The row
-// pitch is a compile-time constant so every LDS below is base + immediate.
-constexpr int FUSED_PITCH_B = FUSED_THREADS * 16;  // bytes per V row
+// hbA / hbB are BYTE offsets of tap 0 / tap 1 in this thread's first V row
+// (row hr).  The row pitch is a compile-time constant so every LDS below is
+// base register + immediate.
+constexpr int FUSED_PITCH_B = FUSED_THREADS * 16 + 128;  // bytes per V row
 
 __device__ __forceinline__ bool
 any_nonfinite(float a, float b, float c, float d)
@@ -199,86 +211,110 @@ any_nonfinite(float a, float b, float c, float d)
     return !(fabsf(t) <= 3.402823466e+38f);
 }
 
-template<int NCH, int HT>
+template<int NCH>
+__device__ __forceinline__ void
+store_pixel(const FusedParams& p, unsigned char* dp, int des, const float (&a)[NCH])
+{
+    if (NCH == 4 && p.dst_vec_ok) {
+        if (p.dsttype == BT_FLOAT) {
+            *reinterpret_cast<float4*>(dp) = make_float4(a[0], a[1], a[2], a[NCH - 1]);
+        } else if (p.dsttype == BT_HALF) {
+            __half2 h0 = __floats2half2_rn(a[0], a[1]);
+            __half2 h1 = __floats2half2_rn(a[2], a[NCH - 1]);
+            uint2 u;
+            u.x = *reinterpret_cast<unsigned int*>(&h0);
+            u.y = *reinterpret_cast<unsigned int*>(&h1);
+            *reinterpret_cast<uint2*>(dp) = u;
+        } else if (p.dsttype == BT_UINT16) {
+            uint2 u;
+            u.x = quant_int(a[0], 65535.0f) | (quant_int(a[1], 65535.0f) << 16);
+            u.y = quant_int(a[2], 65535.0f) | (quant_int(a[NCH - 1], 65535.0f) << 16);
+            *reinterpret_cast<uint2*>(dp) = u;
+        } else {
+            unsigned int u = quant_int(a[0], 255.0f) | (quant_int(a[1], 255.0f) << 8)
+                             | (quant_int(a[2], 255.0f) << 16)
+                             | (quant_int(a[NCH - 1], 255.0f) << 24);
+            *reinterpret_cast<unsigned int*>(dp) = u;
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            store_elem(dp + c * des, p.dsttype, a[c]);
+    }
+}
+
+// The thread's rows of the batch (hr, hr+rstep, ...) are filtered
+// interleaved, tap by tap: independent LDS -> FFMA chains hide the shared
+// memory latency that a row-at-a-time loop exposes.
+template<int NCH, int HT, int BATCH>
 __device__ __forceinline__ void
 fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
-            int dxg, bool col_active, const int (&hoff)[HT],
-            const float (&hwt)[HT], int hr)
+            int dxg, bool col_active, int hbA, int hbB, const float (&hwt)[HT],
+            int hr)
 {
     if (!col_active)
         return;
     const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
     constexpr int rstep = FUSED_THREADS / FUSED_HCOLS;
-    unsigned char* dp   = p.dst + (long long)(dyb + hr) * p.dst_ystride
+    constexpr int NR    = (BATCH + rstep - 1) / rstep;  // rows per thread
+    float a[NR][NCH];
+#pragma unroll
+    for (int k = 0; k < NR; ++k)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+            a[k][c] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < HT; ++i) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            // rows past nb hold stale data from an earlier batch: computed
+            // and discarded
+            // tap i: RGBA even/odd planar (even taps off hbA, odd taps off hbB);
+            // other channel counts are flat floats, NCH*4 bytes per tap
+            const unsigned char* t
+                = vrows + k * rstep * FUSED_PITCH_B
+                  + ((NCH == 4) ? (((i & 1) ? hbB : hbA) + (i >> 1) * 16)
+                                : (hbA + i * NCH * 4));
+            if (NCH == 4) {
+                const float4 v  = *reinterpret_cast<const float4*>(t);
+                const float2 ww = make_float2(hwt[i], hwt[i]);
+                float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
+                                       make_float2(a[k][0], a[k][1]));
+                float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
+                                       make_float2(a[k][2], a[k][NCH - 1]));
+                a[k][0]       = lo.x;
+                a[k][1]       = lo.y;
+                a[k][2]       = hi.x;
+                a[k][NCH - 1] = hi.y;
+            } else {
+                const float* v = reinterpret_cast<const float*>(t);
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+                    a[k][c] = fmaf(hwt[i], v[c], a[k][c]);
+            }
+        }
+    }
+    unsigned char* dp = p.dst + (long long)(dyb + hr) * p.dst_ystride
                         + (long long)dxg * (NCH * des);
     bool bad = false;
 #pragma unroll
-    for (int k = 0; k < (FUSED_BATCH + rstep - 1) / rstep; ++k) {
+    for (int k = 0; k < NR; ++k) {
         if (hr + k * rstep < nb) {
-            const unsigned char* row = vrows + k * rstep * FUSED_PITCH_B;
-            if (NCH == 4) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            float t = 0.0f;
 #pragma unroll
-                for (int i = 0; i < HT; ++i)
-                    fma4(a, hwt[i], *reinterpret_cast<const float4*>(row + hoff[i]));
-                bad |= any_nonfinite(a.x, a.y, a.z, a.w);
-                if (p.dst_vec_ok) {
-                    if (p.dsttype == BT_FLOAT) {
-                        *reinterpret_cast<float4*>(dp) = a;
-                    } else if (p.dsttype == BT_HALF) {
-                        __half2 h0 = __floats2half2_rn(a.x, a.y);
-                        __half2 h1 = __floats2half2_rn(a.z, a.w);
-                        uint2 u;
-                        u.x = *reinterpret_cast<unsigned int*>(&h0);
-                        u.y = *reinterpret_cast<unsigned int*>(&h1);
-                        *reinterpret_cast<uint2*>(dp) = u;
-                    } else if (p.dsttype == BT_UINT16) {
-                        uint2 u;
-                        u.x = quant_int(a.x, 65535.0f) | (quant_int(a.y, 65535.0f) << 16);
-                        u.y = quant_int(a.z, 65535.0f) | (quant_int(a.w, 65535.0f) << 16);
-                        *reinterpret_cast<uint2*>(dp) = u;
-                    } else {
-                        unsigned int u = quant_int(a.x, 255.0f)
-                                         | (quant_int(a.y, 255.0f) << 8)
-                                         | (quant_int(a.z, 255.0f) << 16)
-                                         | (quant_int(a.w, 255.0f) << 24);
-                        *reinterpret_cast<unsigned int*>(dp) = u;
-                    }
-                } else {
-                    store_elem(dp, p.dsttype, a.x);
-                    store_elem(dp + des, p.dsttype, a.y);
-                    store_elem(dp + 2 * des, p.dsttype, a.z);
-                    store_elem(dp + 3 * des, p.dsttype, a.w);
-                }
-            } else {
-                float a[NCH];
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-                    a[c] = 0.0f;
-#pragma unroll
-                for (int i = 0; i < HT; ++i) {
-                    const float* t = reinterpret_cast<const float*>(row + hoff[i]);
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c)
-                        a[c] = fmaf(hwt[i], t[c], a[c]);
-                }
-                float t = 0.0f;
-#pragma unroll
-                for (int c = 0; c < NCH; ++c) {
-                    t += a[c];
-                    store_elem(dp + c * des, p.dsttype, a[c]);
-                }
-                bad |= !(fabsf(t) <= 3.402823466e+38f);
-            }
-            dp += (long long)rstep * p.dst_ystride;
+            for (int c = 0; c < NCH; ++c)
+                t += a[k][c];  // Inf/NaN in any channel survives the sum
+            bad |= !(fabsf(t) <= 3.402823466e+38f);
+            store_pixel<NCH>(p, dp, des, a[k]);
         }
+        dp += (long long)rstep * p.dst_ystride;
     }
     if (p.check_nonfinite && bad)
         *p.nonfinite_flag = 1;
 }
 
 // Shared memory carve-up (bytes):
-//   vrows  FUSED_BATCH x FUSED_PITCH_B           V-filtered rows for the H pass
+//   vrows  fused_batch(VK) x FUSED_PITCH_B       V-filtered rows for the H pass
 //   fifo   FUSED_FIFO x FUSED_THREADS x 16       per-thread prefetch   (ring)
 //   ringw  max_band_rows x VKP x 4               ring weights            "
 //   lastr  max_band_dy x 4                       completion rows         "
@@ -288,6 +324,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* vrows  = smem_raw;
+    constexpr int BATCH   = (VK == 6) ? 6 : 8;  // == fused_batch(VK), kernels.h
     constexpr int pitch_b = FUSED_PITCH_B;
     constexpr int es      = SrcTraits<ST>::es;
 
@@ -300,18 +337,20 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const int hr          = tid / FUSED_HCOLS;
     const bool col_active = hc < strip.ndx;
     const int dxg         = strip.dx0 + hc;
-    int hoff[HT];
     float hwt[HT];
+    int hbA = 0, hbB = 0;  // byte offsets of tap 0 / tap 1 in this thread's row
     {
         int f = col_active ? p.hfirst[dxg] : 0;
 #pragma unroll
-        for (int i = 0; i < HT; ++i) {
+        for (int i = 0; i < HT; ++i)
             hwt[i] = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
+        if (col_active) {
             if (NCH == 4) {
-                int q   = f + i - strip.e0 / 4;
-                hoff[i] = col_active ? swz(q) * 16 + hr * pitch_b : 0;
+                int q = f - strip.e0 / 4;
+                hbA   = planar_byte(q) + hr * pitch_b;
+                hbB   = planar_byte(q + 1) + hr * pitch_b;
             } else {
-                hoff[i] = col_active ? ((f + i) * NCH - strip.e0) * 4 + hr * pitch_b : 0;
+                hbA = (f * NCH - strip.e0) * 4 + hr * pitch_b;
             }
         }
     }
@@ -321,16 +360,18 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const int e         = strip.e0 + 4 * tid;
     const int row_elems = p.src_w * NCH;
     const bool vec_ok   = p.src_vec_ok != 0;
-    unsigned char* vdst = vrows + ((NCH == 4) ? swz(tid) * 16 : tid * 16);
+    unsigned char* vdst = vrows + ((NCH == 4) ? planar_byte(tid) : tid * 16);
     const int dy_end    = band.dy0 + band.ndy;
     int nb              = 0;
 
     if constexpr (VK > 0) {
-        constexpr int VKP  = (VK + 3) & ~3;  // ring row stride (float4 loads)
+        // ring row: VK (w,w) pairs, padded to float4 loads -- ready-made FFMA2
+        // operands
+        constexpr int VKP  = (2 * VK + 3) & ~3;
         constexpr int SLOT = FUSED_THREADS * 16;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
-        unsigned char* fifo = smem_raw + FUSED_BATCH * FUSED_PITCH_B;
+        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B;
         float* ringw = reinterpret_cast<float*>(fifo + FUSED_FIFO * SLOT);
         int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
 
@@ -397,29 +438,32 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // one source row: scatter it into the VK open destination rows
         auto accumulate = [&](const uint4& raw, const float4* wr) {
             const float4 v = convert_raw4<ST>(raw);
-            float w[VKP];
+            float2 w[VKP / 2];
 #pragma unroll
             for (int k = 0; k < VKP / 4; ++k) {
                 float4 t     = wr[k];
-                w[4 * k]     = t.x;
-                w[4 * k + 1] = t.y;
-                w[4 * k + 2] = t.z;
-                w[4 * k + 3] = t.w;
+                w[2 * k]     = make_float2(t.x, t.y);
+                w[2 * k + 1] = make_float2(t.z, t.w);
             }
 #pragma unroll
             for (int k = 0; k < VK; ++k)
                 fma4(acc[k], w[k], v);
         };
         // a destination row is complete: park it for the H pass
-        auto emit = [&](int s, int dy_done) {
+        auto emit = [&](int s) {
             if (vactive)
                 *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = acc[s];
             acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
             ++nb;
-            if (nb == FUSED_BATCH || dy_done == dy_end) {
+        };
+        // BATCH is a multiple of VK, so the buffer can only fill up at the end
+        // of a slot-unrolled group: the H pass is called from ONE place per
+        // loop instead of VK (its code is large; keep the kernel in I-cache)
+        auto flush_if_full = [&](int dy_done) {
+            if (nb + VK > BATCH || dy_done >= dy_end) {
                 __syncthreads();
-                fused_hpass<NCH, HT>(p, vrows, nb, dy_done - nb, dxg, col_active, hoff,
-                                     hwt, hr);
+                fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy_done - nb, dxg, col_active,
+                                            hbA, hbB, hwt, hr);
                 __syncthreads();
                 nb = 0;
             }
@@ -466,9 +510,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                             rawA = rawB;
                             ++r;
                         }
-                        emit(s, dy + s + 1);
+                        emit(s);
                     }
                 }
+                flush_if_full(min(dy + VK, dy_end));
             }
         } else {
             __syncthreads();  // ringw / lastr visible
@@ -485,9 +530,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                             accumulate(raw, wrow);
                             wrow += VKP / 4;
                         }
-                        emit(s, dy + s + 1);
+                        emit(s);
                     }
                 }
+                flush_if_full(min(dy + VK, dy_end));
             }
         }
         cp_async_wait<0>();
@@ -509,10 +555,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                 *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = a;
             }
             ++nb;
-            if (nb == FUSED_BATCH || dy + 1 == dy_end) {
+            if (nb == BATCH || dy + 1 == dy_end) {
                 __syncthreads();
-                fused_hpass<NCH, HT>(p, vrows, nb, dy + 1 - nb, dxg, col_active,
-                                     hoff, hwt, hr);
+                fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy + 1 - nb, dxg, col_active,
+                                            hbA, hbB, hwt, hr);
                 __syncthreads();
                 nb = 0;
             }

@@ -69,7 +69,13 @@ struct Band {
 
 constexpr int FUSED_THREADS = 256;
 constexpr int FUSED_HCOLS   = 128;  // dst columns per strip (H-pass threads per row)
-constexpr int FUSED_BATCH   = 6;    // V-filtered rows buffered between passes
+// V-filtered rows buffered between the passes: a multiple of the ring size so
+// the H pass sits outside the slot-unrolled row loop (one copy in the code)
+constexpr int
+fused_batch(int vk)
+{
+    return vk == 6 ? 6 : 8;
+}
 constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
 
 struct FusedParams {
