@@ -174,6 +174,23 @@ B2R_API void b2r_fit_geometry(int src_full_width, int src_full_height,
                               const char* fillmode, int* resize_width,
                               int* resize_height, int* xoffset, int* yoffset);
 
+/* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
+ * The reference parallelises resize by full-width row bands
+ * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The
+ * same split is used across GPUs: each device runs b2r_resize on its band of
+ * the dst ROI; only the source rows that band can touch (band + filter-radius
+ * halo, xform.cpp:626-633) are staged on that device, straight from the host
+ * source -- no collective, outputs are disjoint.  Host arithmetic only. */
+/* Band `band` of `nbands`: rows [ybegin + H*band/nbands, ybegin + H*(band+1)/nbands). */
+B2R_API int b2r_band_split(const b2r_roi* roi, int nbands, int band, b2r_roi* out);
+/* Source rows [row_begin, row_end), relative to src's data-window origin,
+ * that resizing into `roi` of dst reads (what b2r_resize stages for a host
+ * source).  Only the images' windows are read, not their pixels. */
+B2R_API int b2r_source_rows(const b2r_image* dst, const b2r_image* src,
+                            const char* filtername, float filterwidth,
+                            const b2r_roi* roi, int* row_begin, int* row_end,
+                            char* err, size_t errlen);
+
 /* ---- device-resident MIP chain ---------------------------------------- */
 /* Replaces the level loop of write_mipmap,
  * src/libOpenImageIO/maketexture.cpp:823-986: each level is computed on the

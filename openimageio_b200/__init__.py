@@ -21,7 +21,8 @@ import os
 import numpy as np
 
 __all__ = ["ROI", "ImageSpec", "ImageBuf", "ImageBufAlgo", "Filter2D",
-           "MipChain", "lib", "get_string_attribute", "B2RError"]
+           "MipChain", "lib", "get_string_attribute", "B2RError", "band_split",
+           "source_rows", "resize_banded", "shard_frames"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libb2r.so")
@@ -125,6 +126,12 @@ def lib():
                                C.POINTER(Report), C.c_char_p, C.c_size_t]
     L.b2r_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
         [C.POINTER(C.c_int)] * 4
+    L.b2r_band_split.argtypes = [C.POINTER(_Roi), C.c_int, C.c_int,
+                                 C.POINTER(_Roi)]
+    L.b2r_source_rows.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
+                                  C.c_char_p, C.c_float, C.POINTER(_Roi),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.c_char_p, C.c_size_t]
     L.b2r_mipchain_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
                                       C.c_char_p, C.c_int, C.c_int,
                                       C.POINTER(_Options), C.c_char_p,
@@ -616,6 +623,89 @@ class _IBA:
 
 
 ImageBufAlgo = _IBA()
+
+
+# --------------------------------------------------------------------------
+# Row-band sharding across GPUs / ranks.  The reference's only parallel
+# strategy is full-width row bands (parallel_image,
+# imagebufalgo_util.h:37-80); the same split is used across devices.  Bands
+# are independent: each device stages its band of source rows plus the filter
+# halo straight from the host image, so there is no collective in the data
+# path.
+def band_split(roi, nbands, band):
+    """Band `band` of `nbands` of a dst ROI (rows only)."""
+    r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend)
+    o = _Roi()
+    if lib().b2r_band_split(C.byref(r), nbands, band, C.byref(o)):
+        raise B2RError("band_split: bad arguments")
+    return ROI(o.xbegin, o.xend, o.ybegin, o.yend, 0, 1, o.chbegin, o.chend)
+
+
+def source_rows(dst, src, filtername="", filterwidth=0.0, roi=None):
+    """Source rows [begin, end) (relative to src's data window) that resizing
+    into `roi` of dst reads: the band plus its filter-radius halo.  Host
+    arithmetic only; works without a GPU."""
+    d, s = dst._c(), src._c()
+    if roi is None:
+        roi = dst.roi
+    r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend)
+    b, e = C.c_int(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = lib().b2r_source_rows(C.byref(d), C.byref(s),
+                               (filtername or "").encode(), float(filterwidth),
+                               C.byref(r), C.byref(b), C.byref(e), err, 512)
+    if rc:
+        raise B2RError(err.value.decode())
+    return b.value, e.value
+
+
+def resize_banded(dst, src, devices, filtername="", filterwidth=0.0, roi=None):
+    """ImageBufAlgo.resize of one large HOST image over several GPUs of a
+    box: dst rows are split into len(devices) bands, one synchronous
+    b2r_resize per band on its own device, issued from one host thread each
+    (ctypes releases the GIL).  Returns True / False like resize()."""
+    import threading
+    roi = _ibaprep(roi, dst, src)
+    if roi is None:
+        return False
+    if dst.on_device or src.on_device:
+        dst.errorfmt("resize_banded shards host images; device-resident "
+                     "images are already on one GPU")
+        return False
+    n = len(devices)
+    errs = [None] * n
+
+    def work(i):
+        band = band_split(roi, n, i)
+        if band.yend <= band.ybegin:
+            return
+        d, s = dst._c(), src._c()
+        r = _Roi(band.xbegin, band.xend, band.ybegin, band.yend, band.chbegin,
+                 band.chend)
+        o = _options(devices[i], PATH_AUTO, None)
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_resize(C.byref(d), C.byref(s), (filtername or "").encode(),
+                              float(filterwidth), C.byref(r), C.byref(o), None,
+                              err, 512)
+        if rc:
+            errs[i] = err.value.decode()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    bad = [e for e in errs if e]
+    if bad:
+        dst.errorfmt(bad[0])
+        return False
+    return True
+
+
+def shard_frames(nframes, world_size, rank):
+    """Frames of a batch are independent: round-robin over ranks (one
+    process per GPU), no exchange."""
+    return list(range(rank, nframes, world_size))
 
 
 class MipChain:

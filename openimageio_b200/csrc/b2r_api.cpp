@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -196,6 +197,8 @@ struct DevicePlan {
     // exact tables
     int radi = 0, radj = 0, xtaps = 0, ytaps = 0;
     float xratio = 1, yratio = 1;
+    int src_row0 = 0, src_row1 = 0;  // source rows the ROI can touch (data-window
+                                     // relative, inclusive): band + filter halo
     const int* xcenter = nullptr;
     const float* xw = nullptr;
     const float* xwsum = nullptr;
@@ -247,6 +250,35 @@ struct BlobBuilder {
     }
 };
 
+// Source rows (data-window relative, inclusive) a dst ROI can touch: rows
+// [min(center)-rad, max(center)+rad], resolved the way the taps are -- clamped
+// to the full window (WrapClamp), then cut to the data window.  The
+// non-separable branch walks a window that starts radi (not radj) above the
+// centre (xform.cpp:793-794), so it takes the larger radius and extent.
+void
+source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx,
+                const AxisTaps& ty, int* row0, int* row1)
+{
+    int lo = INT_MAX, hi = INT_MIN;
+    for (int c : ty.center) {
+        lo = std::min(lo, c);
+        hi = std::max(hi, c);
+    }
+    if (ty.center.empty())
+        lo = hi = src.y;
+    int rad = std::max(tx.rad, ty.rad);
+    lo -= rad;
+    hi += rad + (filter.separable() ? 0 : 2 * rad);
+    lo = std::min(std::max(lo, src.full_y), src.full_y + src.full_height - 1);
+    hi = std::min(std::max(hi, src.full_y), src.full_y + src.full_height - 1);
+    lo = std::max(lo, src.y);
+    hi = std::min(hi, src.y + src.height - 1);
+    if (hi < lo)
+        lo = hi = src.y;  // nothing but black is visible: stage one row
+    *row0 = lo - src.y;
+    *row1 = hi - src.y;
+}
+
 int
 get_plan(int device, const b2r_image& dst, const b2r_image& src,
          const b2r_roi& roi, const Filter2D& filter, int nch, int cta_slots,
@@ -291,6 +323,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     plan->ytaps = ty.ntaps;
     plan->xratio = tx.ratio;
     plan->yratio = ty.ratio;
+    source_row_span(src, filter, tx, ty, &plan->src_row0, &plan->src_row1);
 
     BlobBuilder bb;
     size_t o_xc = bb.add(tx.center), o_xw = bb.add(tx.w), o_xs = bb.add(tx.wsum),
@@ -390,18 +423,6 @@ struct DeviceGuard {
     }
 };
 
-// Which source rows a dst ROI can touch (data-window rows, inclusive).
-void
-source_row_span(const DevicePlan& plan, const b2r_image& src, int roi_h,
-                const std::vector<int>& ycenter_host, int* r0, int* r1)
-{
-    (void)plan;
-    (void)roi_h;
-    (void)ycenter_host;
-    *r0 = 0;
-    *r1 = src.height - 1;
-}
-
 int
 resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             const Filter2D& filter, const b2r_roi* roi_in,
@@ -485,28 +506,39 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     b2r_image dstd   = dst;
     size_t src_bytes = 0, dst_bytes = 0;
     bool src_staged = false, dst_staged = false;
+    void* src_alloc = nullptr;
     if (smem == B2R_MEM_HOST) {
         if (src.xstride != (int64_t)src.nchannels * ses) {
             set_err(err, errlen, "host source pixels must be contiguous in x");
             return B2R_ERR_UNSUPPORTED;
         }
+        // Only the rows this ROI can touch travel: its band plus the filter
+        // halo.  A caller that splits dst into row bands (one per GPU) gets
+        // band + halo staging for free, straight from the host source.
+        const int r0 = plan->src_row0, nrows = plan->src_row1 - plan->src_row0 + 1;
         size_t rowbytes = size_t(src.width) * src.xstride;
         size_t pitch    = (rowbytes + 15) & ~size_t(15);
-        src_bytes       = pitch * src.height;
-        CUDA_TRY(cudaMallocAsync(&dsrc, src_bytes, stream));
+        src_bytes       = pitch * nrows;
+        CUDA_TRY(cudaMallocAsync(&src_alloc, src_bytes, stream));
         src_staged = true;
-        CUDA_TRY(cudaMemcpy2DAsync(dsrc, pitch, src.pixels, src.ystride, rowbytes,
-                                   src.height, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch,
+                                   (const unsigned char*)src.pixels
+                                       + (long long)r0 * src.ystride,
+                                   src.ystride, rowbytes, nrows,
+                                   cudaMemcpyHostToDevice, stream));
+        // virtual origin: row r of the data window lives at dsrc + r*pitch;
+        // rows outside [r0, r0+nrows) are never addressed
+        dsrc         = (unsigned char*)src_alloc - (long long)r0 * (long long)pitch;
         srcd.ystride = (int64_t)pitch;
         if (report)
-            report->h2d_bytes += (int64_t)rowbytes * src.height;
+            report->h2d_bytes += (int64_t)rowbytes * nrows;
     }
     size_t dpitch = 0, drowbytes = 0;
     if (dmem == B2R_MEM_HOST) {
         if (dst.xstride != (int64_t)dst.nchannels * des) {
             set_err(err, errlen, "host destination pixels must be contiguous in x");
             if (src_staged)
-                cudaFreeAsync(dsrc, stream);
+                cudaFreeAsync(src_alloc, stream);
             return B2R_ERR_UNSUPPORTED;
         }
         // stage only the ROI rectangle
@@ -570,7 +602,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     if (path == B2R_PATH_FUSED && !fused_ok) {
         set_err(err, errlen, "resize: shape is not eligible for the fused kernel");
         if (src_staged)
-            cudaFreeAsync(dsrc, stream);
+            cudaFreeAsync(src_alloc, stream);
         if (dst_staged)
             cudaFreeAsync(ddst, stream);
         return B2R_ERR_UNSUPPORTED;
@@ -663,7 +695,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     if (flag)
         CUDA_TRY(cudaFreeAsync(flag, stream));
     if (src_staged)
-        CUDA_TRY(cudaFreeAsync(dsrc, stream));
+        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
     if (dst_staged)
         CUDA_TRY(cudaFreeAsync(ddst, stream));
     if (dst_staged || src_staged || timed)
@@ -863,6 +895,70 @@ b2r_resize(const b2r_image* dst, const b2r_image* src, const char* filtername,
         return B2R_ERR_FILTER;
     }
     return resize_impl(dst, src, *filter, roi, opt, report, err, errlen);
+}
+
+int
+b2r_band_split(const b2r_roi* roi, int nbands, int band, b2r_roi* out)
+{
+    if (!roi || !out || nbands <= 0 || band < 0 || band >= nbands)
+        return B2R_ERR_INVALID;
+    long long h = (long long)roi->yend - roi->ybegin;
+    *out        = *roi;
+    out->ybegin = roi->ybegin + int(h * band / nbands);
+    out->yend   = roi->ybegin + int(h * (band + 1) / nbands);
+    return B2R_OK;
+}
+
+int
+b2r_source_rows(const b2r_image* dst, const b2r_image* src, const char* filtername,
+                float filterwidth, const b2r_roi* roi_in, int* row_begin,
+                int* row_end, char* err, size_t errlen)
+{
+    if (!dst || !src || dst->full_width <= 0 || dst->full_height <= 0
+        || src->full_width <= 0 || src->full_height <= 0 || src->width <= 0
+        || src->height <= 0) {
+        set_err(err, errlen, "Uninitialized input image");
+        return B2R_ERR_INVALID;
+    }
+    float wratio = float(dst->full_width) / float(src->full_width);
+    float hratio = float(dst->full_height) / float(src->full_height);
+    std::string name = filtername ? filtername : "";
+    if (name.empty())
+        name = (wratio > 1.0f || hratio > 1.0f) ? "blackman-harris" : "lanczos3";
+    std::unique_ptr<Filter2D, void (*)(Filter2D*)> filter(nullptr,
+                                                          Filter2D::destroy);
+    for (int i = 0, e = Filter2D::num_filters(); i < e; ++i) {
+        const FilterDesc& fd = Filter2D::get_filterdesc(i);
+        if (name == fd.name) {
+            float w = filterwidth > 0.0f ? filterwidth
+                                         : fd.width * std::max(1.0f, wratio);
+            float h = filterwidth > 0.0f ? filterwidth
+                                         : fd.width * std::max(1.0f, hratio);
+            filter.reset(Filter2D::create(name, w, h));
+            break;
+        }
+    }
+    if (!filter) {
+        set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
+        return B2R_ERR_FILTER;
+    }
+    b2r_roi roi = roi_in ? *roi_in
+                         : b2r_roi { dst->x, dst->x + dst->width, dst->y,
+                                     dst->y + dst->height, 0, dst->nchannels };
+    // only the tap geometry is needed (centres and radii), for a 1-wide column
+    AxisGeom gx { roi.xbegin, roi.xbegin, dst->full_x, dst->full_width, src->full_x,
+                  src->full_width, src->x, src->x + src->width };
+    AxisGeom gy { roi.ybegin, roi.yend, dst->full_y, dst->full_height, src->full_y,
+                  src->full_height, src->y, src->y + src->height };
+    AxisTaps tx = build_axis_taps(gx, *filter, false);
+    AxisTaps ty = build_axis_taps(gy, *filter, true);
+    int r0 = 0, r1 = 0;
+    source_row_span(*src, *filter, tx, ty, &r0, &r1);
+    if (row_begin)
+        *row_begin = r0;
+    if (row_end)
+        *row_end = r1 + 1;
+    return B2R_OK;
 }
 
 void

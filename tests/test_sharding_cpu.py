@@ -1,0 +1,110 @@
+"""Host-side logic of the multi-GPU paths, on CPU: band split, band + halo
+source spans (checked by re-running the ORACLE on a source cropped to the
+span), and a world_size-2 gloo run of the rank-side arithmetic."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_band_split_covers_roi_exactly(oiio):
+    for h in (1, 7, 2160, 4321):
+        for n in (1, 2, 3, 8):
+            roi = oiio.ROI(5, 105, 10, 10 + h, 0, 1, 0, 4)
+            rows = []
+            for i in range(n):
+                b = oiio.band_split(roi, n, i)
+                assert (b.xbegin, b.xend) == (5, 105)
+                rows += list(range(b.ybegin, b.yend))
+            assert rows == list(range(10, 10 + h))
+
+
+@pytest.mark.parametrize("filt,shape", [("lanczos3", (120, 160)),
+                                        ("blackman-harris", (400, 300)),
+                                        ("box", (60, 80)),
+                                        ("radial-lanczos3", (100, 90))])
+def test_source_rows_are_sufficient_and_tight(oiio, oracle, filt, shape):
+    """Resizing a band from ONLY the rows b2r_source_rows names (source data
+    window cropped to them) must equal resizing it from the whole source."""
+    src = synth.image(200, 240, 3, np.float32, seed=77)
+    dh, dw = shape
+    full = np.zeros((dh, dw, 3), np.float32)
+    oracle.resize(oracle.Img(full), oracle.Img(src), filt)
+    S = oiio.ImageBuf(src)
+    D = oiio.ImageBuf(np.zeros((dh, dw, 3), np.float32))
+    n = 5
+    for i in range(n):
+        band = oiio.band_split(D.roi, n, i)
+        r0, r1 = oiio.source_rows(D, S, filt, roi=band)
+        assert 0 <= r0 < r1 <= 240
+        crop = np.ascontiguousarray(src[r0:r1])
+        out = np.zeros_like(full)
+        oracle.resize(oracle.Img(out), oracle.Img(crop, 0, r0, (0, 0, 200, 240)),
+                      filt, roi=(0, dw, band.ybegin, band.yend))
+        assert np.array_equal(out[band.ybegin:band.yend],
+                              full[band.ybegin:band.yend]), (i, r0, r1)
+        # tight: the halo is the filter radius, not the whole image
+        if filt == "lanczos3" and 0 < i < n - 1:
+            ratio = 240 / dh
+            assert (r1 - r0) <= (band.yend - band.ybegin) * ratio + 2 * 3 * max(1, ratio) + 4
+
+
+def test_shard_frames(oiio):
+    for n in (1, 7, 256):
+        for w in (1, 2, 4, 8):
+            got = sorted(sum((oiio.shard_frames(n, w, r) for r in range(w)), []))
+            assert got == list(range(n))
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import openimageio_b200 as oiio, oracle_py, synth
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+src = synth.image(96, 128, 4, np.float32, seed=5)      # same on every rank
+dh, dw = 64, 48
+S = oiio.ImageBuf(src); D = oiio.ImageBuf(np.zeros((dh, dw, 4), np.float32))
+band = oiio.band_split(D.roi, world, rank)
+r0, r1 = oiio.source_rows(D, S, "lanczos3", roi=band)
+# each rank resizes its band from its own band+halo rows only (oracle = CPU)
+crop = np.ascontiguousarray(src[r0:r1])
+out = np.zeros((dh, dw, 4), np.float32)
+oracle_py.resize(oracle_py.Img(out), oracle_py.Img(crop, 0, r0, (0, 0, 96, 128)),
+                 "lanczos3", roi=(0, dw, band.ybegin, band.yend))
+# bands are disjoint: a sum-reduce assembles the image (test plumbing only)
+t = torch.from_numpy(out); dist.all_reduce(t)
+spans = [None] * world
+dist.all_gather_object(spans, (band.ybegin, band.yend, r0, r1))
+frames = [None] * world
+dist.all_gather_object(frames, oiio.shard_frames(10, world, rank))
+if rank == 0:
+    ref = np.zeros((dh, dw, 4), np.float32)
+    oracle_py.resize(oracle_py.Img(ref), oracle_py.Img(src), "lanczos3")
+    assert np.array_equal(t.numpy(), ref)
+    assert [s[0] for s in spans] == [0, 32] and [s[1] for s in spans] == [32, 64]
+    assert spans[0][2] == 0 and spans[1][3] == 128 and spans[0][3] > spans[1][2]
+    assert sorted(sum(frames, [])) == list(range(10))
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_world_size_2_gloo(tmp_path):
+    import subprocess
+    w = tmp_path / "worker.py"
+    w.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+         "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+         "29611", str(w), ROOT],
+        capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
