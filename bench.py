@@ -56,6 +56,16 @@ def algorithmic_bytes(wl):
     return sw * sh * c * np.dtype(sdt).itemsize + dw * dh * c * np.dtype(ddt).itemsize
 
 
+def measured_traffic(wl):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel,
+    per launch, from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(wl)
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -120,7 +130,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(wl, nthreads=0, rows=None, repeat=1):
+def sample_rows(wl, cores):
+    """Rows of the workload one CPU sample covers: the whole frame on a box
+    with >= 16 cores (about 10-15 core-seconds for C0), proportionally fewer
+    rows on smaller hosts so a sample stays around a second of wall time."""
+    dh = WORKLOADS[wl][5]
+    return max(8, min(dh, int(dh * min(1.0, cores / 16.0))))
+
+
+def cpu_sample(wl, nthreads=0, rows=None, repeat=2):
     """Time the oracle (reference algorithm restated) on a row band of the
     workload.  Returns (Mpixel/s, cores, description)."""
     import oracle_py
@@ -128,8 +146,7 @@ def cpu_sample(wl, nthreads=0, rows=None, repeat=1):
     sw, sh, c, sdt, dw, dh, ddt, filt = WORKLOADS[wl]
     cores = nthreads or (os.cpu_count() or 1)
     if rows is None:
-        # about 10-30 s of single-core work spread over the cores
-        rows = max(8, min(dh, int(dh * min(1.0, cores / 64.0))))
+        rows = sample_rows(wl, cores)
     src = synth.image(sw, sh, c, np.dtype(sdt), seed=20261019)
     dst = np.zeros((dh, dw, c), np.dtype(ddt))
     y0 = (dh - rows) // 2
@@ -155,7 +172,7 @@ def run_reference(args):
     import oracle_py
     import synth
     cores = os.cpu_count() or 1
-    rows = max(8, min(dh, int(dh * min(1.0, cores / 96.0))))
+    rows = sample_rows(wl, cores)
     src = synth.image(sw, sh, c, np.dtype(sdt), seed=20261019)
     dst = np.zeros((dh, dw, c), np.dtype(ddt))
     y0 = (dh - rows) // 2
@@ -328,7 +345,7 @@ def main():
             "gpu_launches": args.steps * (2 if src_is_fp else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which,
+                         "traffic": measured_traffic(wl), "peak_source": which,
                          "algorithmic_bytes": abytes,
                          "kernel": "resize_fused_kernel"},
             "clocks": clocks,

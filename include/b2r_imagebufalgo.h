@@ -1,0 +1,399 @@
+// b2r_imagebufalgo.h -- header-only C++ host mirror of the reference's C++
+// surface for the resize path, over the C ABI (b2r.h).
+//
+// Same names, argument meaning and error behaviour as OpenImageIO 3.2:
+//   ROI                              src/include/OpenImageIO/imageio.h:93-230
+//   ImageSpec (the fields resize reads)                imageio.h:265-330
+//   ImageBuf  (local pixels + spec + error string)     imagebuf.h
+//   KWArgs / ParamValue ("filtername", "filterwidth", "filterptr",
+//                        "fillmode", "exact")          imagebufalgo.h:185-187
+//   ImageBufAlgo::resize / fit / resample              imagebufalgo.h:667-762,
+//       implemented in src/libOpenImageIO/imagebufalgo_xform.cpp:864-1074,
+//       1691-1723; IBAprep rules from imagebufalgo.cpp:64-348.
+// It exists so the parity tests and downstream code read like code written
+// against the reference; a maintainer integrating into OpenImageIO itself
+// only needs the ABI call shown in INTEGRATION.md.
+#pragma once
+
+#include "b2r.h"
+
+#include <algorithm>
+#include <climits>
+#include <cstring>
+#include <initializer_list>
+#include <string>
+#include <vector>
+
+namespace b2r {
+
+struct TypeDesc {
+    enum BASETYPE { UNKNOWN = 0, UINT8 = 2, UINT16 = 4, HALF = 10, FLOAT = 11 };
+    int basetype = FLOAT;
+    TypeDesc(int bt = FLOAT)
+        : basetype(bt)
+    {
+    }
+    size_t size() const
+    {
+        return basetype == UINT8 ? 1 : (basetype == FLOAT ? 4 : 2);
+    }
+    bool operator==(const TypeDesc& o) const { return basetype == o.basetype; }
+};
+
+struct ROI {
+    int xbegin, xend, ybegin, yend, zbegin, zend, chbegin, chend;
+    constexpr ROI()
+        : xbegin(INT_MIN), xend(0), ybegin(0), yend(0), zbegin(0), zend(0),
+          chbegin(0), chend(0)
+    {
+    }
+    constexpr ROI(int xb, int xe, int yb, int ye, int zb = 0, int ze = 1,
+                  int cb = 0, int ce = 10000)
+        : xbegin(xb), xend(xe), ybegin(yb), yend(ye), zbegin(zb), zend(ze),
+          chbegin(cb), chend(ce)
+    {
+    }
+    constexpr bool defined() const { return xbegin != INT_MIN; }
+    constexpr int width() const { return xend - xbegin; }
+    constexpr int height() const { return yend - ybegin; }
+    constexpr int nchannels() const { return chend - chbegin; }
+    static constexpr ROI All() { return ROI(); }
+};
+
+struct ImageSpec {
+    int x = 0, y = 0, z = 0, width = 0, height = 0, depth = 1;
+    int full_x = 0, full_y = 0, full_z = 0;
+    int full_width = 0, full_height = 0, full_depth = 1;
+    int nchannels = 0;
+    TypeDesc format;
+    int alpha_channel = -1;
+    bool deep = false;
+    ImageSpec() {}
+    ImageSpec(int w, int h, int nch, TypeDesc fmt = TypeDesc::FLOAT)
+        : width(w), height(h), full_width(w), full_height(h), nchannels(nch),
+          format(fmt), alpha_channel(nch == 4 ? 3 : -1)
+    {
+    }
+    ROI roi() const
+    {
+        return ROI(x, x + width, y, y + height, 0, 1, 0, nchannels);
+    }
+    ROI roi_full() const
+    {
+        return ROI(full_x, full_x + full_width, full_y, full_y + full_height, 0, 1,
+                   0, nchannels);
+    }
+    void set_roi(const ROI& r)
+    {
+        x = r.xbegin, y = r.ybegin, width = r.width(), height = r.height();
+    }
+    void set_roi_full(const ROI& r)
+    {
+        full_x = r.xbegin, full_y = r.ybegin, full_width = r.width(),
+        full_height = r.height();
+    }
+};
+
+class Filter2D;  // opaque: see b2r_filter2d_* in b2r.h
+
+/// Local-pixel ImageBuf: owns a contiguous host buffer, or wraps caller
+/// memory (host or device) without owning it.
+class ImageBuf {
+public:
+    ImageBuf() {}
+    explicit ImageBuf(const ImageSpec& spec) { reset(spec); }
+    /// Wrap existing pixels (like the ImageBuf(spec, buffer) constructor).
+    ImageBuf(const ImageSpec& spec, void* buffer, int memspace = B2R_MEM_AUTO,
+             int device = 0)
+        : m_spec(spec), m_pixels(buffer), m_memspace(memspace), m_device(device),
+          m_init(true)
+    {
+    }
+    void reset(const ImageSpec& spec)
+    {
+        m_spec = spec;
+        m_own.assign(size_t(spec.width) * spec.height * spec.nchannels
+                         * spec.format.size(),
+                     0);
+        m_pixels   = m_own.data();
+        m_memspace = B2R_MEM_HOST;
+        m_init     = true;
+    }
+    bool initialized() const { return m_init; }
+    const ImageSpec& spec() const { return m_spec; }
+    ImageSpec& specmod() { return m_spec; }
+    int nchannels() const { return m_spec.nchannels; }
+    ROI roi() const { return m_spec.roi(); }
+    ROI roi_full() const { return m_spec.roi_full(); }
+    void* localpixels() { return m_pixels; }
+    const void* localpixels() const { return m_pixels; }
+    bool has_error() const { return !m_err.empty(); }
+    std::string geterror(bool clear = true) const
+    {
+        std::string e = m_err;
+        if (clear)
+            m_err.clear();
+        return e;
+    }
+    void error(const std::string& msg) const { m_err = msg; }
+    bool copy(const ImageBuf& src)
+    {
+        if (!src.m_init || src.m_memspace == B2R_MEM_DEVICE)
+            return false;
+        reset(src.m_spec);
+        std::memcpy(m_pixels, src.m_pixels, m_own.size());
+        return true;
+    }
+    b2r_image c_image() const
+    {
+        b2r_image im;
+        std::memset(&im, 0, sizeof(im));
+        im.pixels      = m_pixels;
+        im.basetype    = m_spec.format.basetype;
+        im.nchannels   = m_spec.nchannels;
+        im.x           = m_spec.x;
+        im.y           = m_spec.y;
+        im.width       = m_spec.width;
+        im.height      = m_spec.height;
+        im.full_x      = m_spec.full_x;
+        im.full_y      = m_spec.full_y;
+        im.full_width  = m_spec.full_width;
+        im.full_height = m_spec.full_height;
+        im.xstride     = int64_t(m_spec.nchannels) * m_spec.format.size();
+        im.ystride     = im.xstride * m_spec.width;
+        im.memspace    = m_memspace;
+        im.device      = m_device;
+        return im;
+    }
+
+private:
+    ImageSpec m_spec;
+    std::vector<unsigned char> m_own;
+    void* m_pixels = nullptr;
+    int m_memspace = B2R_MEM_HOST;
+    int m_device   = 0;
+    bool m_init    = false;
+    mutable std::string m_err;
+};
+
+/// One optional argument: name + string / float / int / pointer value.
+struct ParamValue {
+    std::string name;
+    std::string sval;
+    float fval      = 0.0f;
+    int ival        = 0;
+    const void* ptr = nullptr;
+    ParamValue(const char* n, const char* v) : name(n), sval(v) {}
+    ParamValue(const char* n, const std::string& v) : name(n), sval(v) {}
+    ParamValue(const char* n, float v) : name(n), fval(v), ival(int(v)) {}
+    ParamValue(const char* n, double v) : name(n), fval(float(v)), ival(int(v)) {}
+    ParamValue(const char* n, int v) : name(n), fval(float(v)), ival(v) {}
+    ParamValue(const char* n, const b2r_filter2d* v) : name(n), ptr(v) {}
+};
+
+class KWArgs {
+public:
+    KWArgs() {}
+    KWArgs(std::initializer_list<ParamValue> l) : m_v(l) {}
+    std::string get_string(const char* n, const char* def = "") const
+    {
+        for (auto& p : m_v)
+            if (p.name == n)
+                return p.sval;
+        return def;
+    }
+    float get_float(const char* n, float def = 0.0f) const
+    {
+        for (auto& p : m_v)
+            if (p.name == n)
+                return p.fval;
+        return def;
+    }
+    int get_int(const char* n, int def = 0) const
+    {
+        for (auto& p : m_v)
+            if (p.name == n)
+                return p.ival;
+        return def;
+    }
+    const void* get_ptr(const char* n) const
+    {
+        for (auto& p : m_v)
+            if (p.name == n)
+                return p.ptr;
+        return nullptr;
+    }
+
+private:
+    std::vector<ParamValue> m_v;
+};
+
+namespace ImageBufAlgo {
+
+namespace detail {
+// IBAprep with IBAprep_NO_SUPPORT_VOLUME | IBAprep_NO_COPY_ROI_FULL and one
+// input image (imagebufalgo.cpp:64-348).
+inline bool
+prep(ROI& roi, ImageBuf& dst, const ImageBuf& src)
+{
+    if (!src.initialized()) {
+        dst.error("Uninitialized input image");
+        return false;
+    }
+    if (dst.initialized()) {
+        ROI d = dst.roi();
+        if (roi.defined()) {
+            roi.xbegin  = std::max(roi.xbegin, d.xbegin);
+            roi.xend    = std::min(roi.xend, d.xend);
+            roi.ybegin  = std::max(roi.ybegin, d.ybegin);
+            roi.yend    = std::min(roi.yend, d.yend);
+            roi.chbegin = std::max(roi.chbegin, 0);
+            roi.chend   = std::min(roi.chend, d.chend);
+        } else {
+            roi = d;
+        }
+    } else {
+        ROI full;
+        if (!roi.defined()) {
+            roi  = src.roi();
+            full = src.roi_full();
+        } else {
+            roi.chend = std::min(roi.chend, src.nchannels());
+        }
+        ImageSpec spec = src.spec();
+        spec.set_roi(roi);
+        spec.set_roi_full(full.defined() ? full : roi);
+        dst.reset(spec);
+    }
+    if (dst.spec().depth > 1 || src.spec().depth > 1) {
+        dst.error("volumes not supported");
+        return false;
+    }
+    if (dst.spec().deep || src.spec().deep) {
+        dst.error("deep images not supported");
+        return false;
+    }
+    roi.chend = std::min(roi.chend, std::max(dst.nchannels(), src.nchannels()));
+    return true;
+}
+}  // namespace detail
+
+/// ImageBufAlgo::resize(dst, src, KWArgs{filtername, filterwidth, filterptr},
+/// roi, nthreads) -- imagebufalgo_xform.cpp:864-918.  nthreads is accepted for
+/// signature compatibility (it caps CPU threads in the reference; there are
+/// none here).  Unrecognised options are ignored, as in the reference (:880).
+inline bool
+resize(ImageBuf& dst, const ImageBuf& src, const KWArgs& options = {}, ROI roi = {},
+       int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r { roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend };
+    char err[512] = "";
+    int rc;
+    if (const void* fp = options.get_ptr("filterptr"))
+        rc = b2r_resize_filter(&d, &s, (const b2r_filter2d*)fp, &r, nullptr, nullptr,
+                               err, sizeof(err));
+    else
+        rc = b2r_resize(&d, &s, options.get_string("filtername").c_str(),
+                        options.get_float("filterwidth"), &r, nullptr, nullptr, err,
+                        sizeof(err));
+    if (rc) {
+        dst.error(err);
+        return false;
+    }
+    return true;
+}
+
+inline ImageBuf
+resize(const ImageBuf& src, const KWArgs& options = {}, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = resize(result, src, options, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::resize() error");
+    return result;
+}
+
+/// ImageBufAlgo::resample -- imagebufalgo_xform.cpp:1691-1723.
+inline bool
+resample(ImageBuf& dst, const ImageBuf& src, bool interpolate = true, ROI roi = {},
+         int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r { roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend };
+    char err[512] = "";
+    if (b2r_resample(&d, &s, interpolate ? 1 : 0, &r, nullptr, nullptr, err,
+                     sizeof(err))) {
+        dst.error(err);
+        return false;
+    }
+    return true;
+}
+
+inline ImageBuf
+resample(const ImageBuf& src, bool interpolate = true, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = resample(result, src, interpolate, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::resample() error");
+    return result;
+}
+
+/// ImageBufAlgo::fit -- imagebufalgo_xform.cpp:933-1062.  exact=1 is the warp
+/// path and is refused (outside this library), not approximated.
+inline bool
+fit(ImageBuf& dst, const ImageBuf& src, const KWArgs& options = {}, ROI roi = {},
+    int nthreads = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    if (options.get_int("exact")) {
+        dst.error("fit: exact=1 takes the warp path, which is outside the B200 "
+                  "resize path");
+        return false;
+    }
+    const ImageSpec& sspec = src.spec();
+    int rw, rh, xo, yo;
+    std::string fillmode = options.get_string("fillmode", "letterbox");
+    b2r_fit_geometry(sspec.full_width, sspec.full_height, roi.width(), roi.height(),
+                     fillmode.c_str(), &rw, &rh, &xo, &yo);
+    const int fit_x = roi.xbegin, fit_y = roi.ybegin;
+    const int fit_w = roi.width(), fit_h = roi.height();
+    bool ok = true;
+    if (rw != sspec.full_width || rh != sspec.full_height || fit_x != sspec.full_x
+        || fit_y != sspec.full_y) {
+        ROI resizeroi(fit_x, fit_x + rw, fit_y, fit_y + rh, 0, 1, 0, sspec.nchannels);
+        ImageSpec newspec = sspec;
+        newspec.set_roi(resizeroi);
+        newspec.set_roi_full(resizeroi);
+        dst.reset(newspec);
+        ok = resize(dst, src, options, resizeroi, nthreads);
+    } else {
+        ok = dst.copy(src);
+    }
+    dst.specmod().full_width  = fit_w;
+    dst.specmod().full_height = fit_h;
+    dst.specmod().full_x      = fit_x;
+    dst.specmod().full_y      = fit_y;
+    dst.specmod().x           = xo;
+    dst.specmod().y           = yo;
+    return ok;
+}
+
+inline ImageBuf
+fit(const ImageBuf& src, const KWArgs& options = {}, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = fit(result, src, options, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::fit() error");
+    return result;
+}
+
+}  // namespace ImageBufAlgo
+}  // namespace b2r

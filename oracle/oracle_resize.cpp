@@ -199,6 +199,64 @@ parallel_bands(orc_roi roi, int nthreads,
         t.join();
 }
 
+template<int BT> struct TypedLoad;
+template<> struct TypedLoad<ORC_UINT8> {
+    static inline float get(const char* p, int c)
+    {
+        return float(((const uint8_t*)p)[c]) * (1.0f / 255.0f);
+    }
+};
+template<> struct TypedLoad<ORC_UINT16> {
+    static inline float get(const char* p, int c)
+    {
+        return float(((const uint16_t*)p)[c]) * (1.0f / 65535.0f);
+    }
+};
+template<> struct TypedLoad<ORC_HALF> {
+    static inline float get(const char* p, int c)
+    {
+        return float(((const _Float16*)p)[c]);
+    }
+};
+template<> struct TypedLoad<ORC_FLOAT> {
+    static inline float get(const char* p, int c) { return ((const float*)p)[c]; }
+};
+
+// The separable tap loop of resize_ (xform.cpp:747-761) for one output pixel.
+// Same order of operations as the generic code below; the source type is a
+// template parameter and, when the whole footprint lies inside the data
+// window, pixels are addressed directly instead of through the per-tap
+// WrapClamp test (what the reference's iterator does for in-window pixels).
+template<int BT>
+static inline void
+separable_taps(const SrcView& sv, const orc_image* src, int src_x, int src_y,
+               int radi, int radj, int xtaps, const float* xfiltval,
+               const float* yfiltval, int nchannels, float* pel)
+{
+    const bool interior = src_x - radi >= src->x && src_x + radi < src->x + src->width
+                          && src_y - radj >= src->y
+                          && src_y + radj < src->y + src->height;
+    for (int j = -radj; j <= radj; ++j) {
+        float wy = yfiltval[j + radj];
+        if (wy == 0.0f)
+            continue;
+        const char* row = nullptr;
+        if (interior)
+            row = (const char*)src->pixels + int64_t(src_y + j - src->y) * src->ystride
+                  + int64_t(src_x - radi - src->x) * src->xstride;
+        for (int i = 0; i < xtaps; ++i) {
+            float w = wy * xfiltval[i];
+            if (w) {
+                const char* sp = interior ? row + int64_t(i) * src->xstride
+                                          : sv.pixel(src_x - radi + i, src_y + j, false);
+                if (sp)
+                    for (int c = 0; c < nchannels; ++c)
+                        pel[c] += w * TypedLoad<BT>::get(sp, c);
+            }
+        }
+    }
+}
+
 void
 resize_band(const orc_image* dst, const orc_image* src,
             const OrcFilter2D& filter, orc_roi roi)
@@ -284,23 +342,27 @@ resize_band(const orc_image* dst, const orc_image* src,
                 for (int i = 0; i < xtaps; ++i)
                     totalweight_x += xfiltval[i];
                 if (totalweight_x != 0.0f) {
-                    for (int j = -radj; j <= radj; ++j) {
-                        float wy = yfiltval[j + radj];
-                        if (wy == 0.0f)
-                            continue;
-                        for (int i = 0; i < xtaps; ++i) {
-                            float w = wy * xfiltval[i];
-                            if (w) {
-                                const char* sp = sv.pixel(src_x - radi + i,
-                                                          src_y + j, false);
-                                if (sp)
-                                    for (int c = 0; c < nchannels; ++c)
-                                        pel[c] += w
-                                                  * load_as_float(sp + c * stsize,
-                                                                  src->basetype);
-                                // black pixel: adds w*0
-                            }
-                        }
+                    switch (src->basetype) {
+                    case ORC_UINT8:
+                        separable_taps<ORC_UINT8>(sv, src, src_x, src_y, radi, radj,
+                                                  xtaps, xfiltval, yfiltval.data(),
+                                                  nchannels, pel.data());
+                        break;
+                    case ORC_UINT16:
+                        separable_taps<ORC_UINT16>(sv, src, src_x, src_y, radi, radj,
+                                                   xtaps, xfiltval, yfiltval.data(),
+                                                   nchannels, pel.data());
+                        break;
+                    case ORC_HALF:
+                        separable_taps<ORC_HALF>(sv, src, src_x, src_y, radi, radj,
+                                                 xtaps, xfiltval, yfiltval.data(),
+                                                 nchannels, pel.data());
+                        break;
+                    default:
+                        separable_taps<ORC_FLOAT>(sv, src, src_x, src_y, radi, radj,
+                                                  xtaps, xfiltval, yfiltval.data(),
+                                                  nchannels, pel.data());
+                        break;
                     }
                 }
                 char* dp = dst_pixel(dst, x, y);
