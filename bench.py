@@ -138,7 +138,7 @@ def sample_rows(wl, cores):
     return max(8, min(dh, int(dh * min(1.0, cores / 16.0))))
 
 
-def cpu_sample(wl, nthreads=0, rows=None, repeat=2):
+def cpu_sample(wl, nthreads=0, rows=None, repeat=5):
     """Time the oracle (reference algorithm restated) on a row band of the
     workload.  Returns (Mpixel/s, cores, description)."""
     import oracle_py

@@ -269,10 +269,14 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
     int rad = std::max(tx.rad, ty.rad);
     lo -= rad;
     hi += rad + (filter.separable() ? 0 : 2 * rad);
-    lo = std::min(std::max(lo, src.full_y), src.full_y + src.full_height - 1);
-    hi = std::min(std::max(hi, src.full_y), src.full_y + src.full_height - 1);
-    lo = std::max(lo, src.y);
-    hi = std::min(hi, src.y + src.height - 1);
+    // a tap inside the data window is used where it is (even outside the
+    // display window: overscan); a tap outside it is clamped to the display
+    // window first.  Cover both readings of the extreme taps.
+    const int flo = src.full_y, fhi = src.full_y + src.full_height - 1;
+    int lo_c = std::min(std::max(lo, flo), fhi);
+    int hi_c = std::min(std::max(hi, flo), fhi);
+    lo = std::max(std::min(lo, lo_c), src.y);
+    hi = std::min(std::max(hi, hi_c), src.y + src.height - 1);
     if (hi < lo)
         lo = hi = src.y;  // nothing but black is visible: stage one row
     *row0 = lo - src.y;

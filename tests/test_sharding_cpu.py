@@ -108,3 +108,29 @@ def test_world_size_2_gloo(tmp_path):
         capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+def test_source_rows_with_overscan_and_crop(oiio, oracle):
+    """Data window larger than (overscan) or smaller than (crop) the display
+    window: the staged span must still cover every tap after WrapClamp."""
+    for (sx, sy, full) in [(-8, -6, (0, 0, 64, 64)), (20, 30, (0, 0, 128, 128))]:
+        src = synth.image(80, 76, 3, np.float32, seed=78)
+        dh, dw = 40, 36
+        dfull = (0, 0, dw, dh)
+        ref = np.zeros((dh, dw, 3), np.float32)
+        oracle.resize(oracle.Img(ref, 0, 0, dfull), oracle.Img(src, sx, sy, full))
+        S = oiio.ImageBuf(src)
+        sp = S.spec()
+        sp.x, sp.y = sx, sy
+        sp.full_x, sp.full_y, sp.full_width, sp.full_height = full
+        D = oiio.ImageBuf(np.zeros((dh, dw, 3), np.float32))
+        for i in range(4):
+            band = oiio.band_split(D.roi, 4, i)
+            r0, r1 = oiio.source_rows(D, S, "", roi=band)
+            crop = np.ascontiguousarray(src[r0:r1])
+            out = np.zeros_like(ref)
+            oracle.resize(oracle.Img(out, 0, 0, dfull),
+                          oracle.Img(crop, sx, sy + r0, full), "",
+                          roi=(0, dw, band.ybegin, band.yend))
+            assert np.array_equal(out[band.ybegin:band.yend],
+                                  ref[band.ybegin:band.yend]), (sx, i)
