@@ -502,6 +502,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                   err, errlen);
     if (rc)
         return rc;
+    if (opt && opt->reserved[0] == 1)
+        return B2R_OK;  // private: build + upload the tables only (MIP chain)
 
     // ---- stage host images ------------------------------------------------
     void* dsrc       = src.pixels;
@@ -1267,74 +1269,89 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
     }
     chain->levels.push_back(l0);
 
-    cudaEvent_t ev0, ev1;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventRecord(ev0, stream);
-    int w = l0.w, h = l0.h;
+    // Pass 1: allocate every level and build + upload every weight table
+    // (host work), so that pass 2 -- what kernel_ms times -- is back-to-back
+    // launches with no host gaps and no allocation on the stream.
+    {
+        int w = l0.w, h = l0.h;
+        while (w > 1 || h > 1) {
+            const int sw = w > 1 ? w / 2 : w;
+            const int sh = h > 1 ? h / 2 : h;
+            b2r_mipchain::Level lv { sw, sh, nullptr, true };
+            if (cudaMalloc(&lv.px, size_t(sw) * sh * nch * 4) != cudaSuccess) {
+                set_err(err, errlen, "mipchain: out of device memory");
+                return fail(B2R_ERR_CUDA);
+            }
+            chain->levels.push_back(lv);
+            w = sw;
+            h = sh;
+        }
+    }
     b2r_options sub;
     memset(&sub, 0, sizeof(sub));
     sub.device      = device;
     sub.path        = opt ? opt->path : B2R_PATH_AUTO;
     sub.cuda_stream = (void*)stream;
-    while (w > 1 || h > 1) {
-        const int sw = w > 1 ? w / 2 : w;
-        const int sh = h > 1 ? h / 2 : h;
-        b2r_mipchain::Level lv { sw, sh, nullptr, true };
-        if (cudaMalloc(&lv.px, size_t(sw) * sh * nch * 4) != cudaSuccess) {
-            set_err(err, errlen, "mipchain: out of device memory");
-            cudaEventDestroy(ev0);
-            cudaEventDestroy(ev1);
-            return fail(B2R_ERR_CUDA);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            cudaEventCreate(&ev0);
+            cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, stream);
         }
-        const b2r_mipchain::Level& big = chain->levels.back();
-        // "Trick" of write_mipmap (:866-879): both images get zero-origin
-        // windows with display == data
-        b2r_image S;
-        memset(&S, 0, sizeof(S));
-        S.pixels     = big.px;
-        S.basetype   = B2R_FLOAT;
-        S.nchannels  = nch;
-        S.width      = S.full_width = w;
-        S.height     = S.full_height = h;
-        S.xstride    = (int64_t)nch * 4;
-        S.ystride    = (int64_t)w * nch * 4;
-        S.memspace   = B2R_MEM_DEVICE;
-        S.device     = device;
-        b2r_image D  = S;
-        D.pixels     = lv.px;
-        D.width      = D.full_width = sw;
-        D.height     = D.full_height = sh;
-        D.ystride    = (int64_t)sw * nch * 4;
-        chain->levels.push_back(lv);
-        if (fname == "box") {
-            BoxParams bp;
-            bp.dst = to_dev(D, D.pixels);
-            bp.src = to_dev(S, S.pixels);
-            // resize_block (:304-334): 2-pass needs 2*dw == sw and, without
-            // allow_pixel_shift, even source sizes (:265-266)
-            bp.two_pass = (2 * sw == w) && !(w % 2 || h % 2);
-            launch_box_downsample(bp, stream);
-            chain->launches += 1;
-        } else {
-            b2r_report rep;
-            rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
-                            err, errlen);
-            (void)rep;
-            if (rc) {
-                cudaEventDestroy(ev0);
-                cudaEventDestroy(ev1);
-                return fail(rc);
+        sub.reserved[0] = (pass == 0) ? 1 : 0;  // private: plan only, no launch
+        for (size_t li = 1; li < chain->levels.size(); ++li) {
+            const b2r_mipchain::Level& big = chain->levels[li - 1];
+            const b2r_mipchain::Level& lv  = chain->levels[li];
+            const int w = big.w, h = big.h, sw = lv.w, sh = lv.h;
+            // "Trick" of write_mipmap (:866-879): both images get zero-origin
+            // windows with display == data
+            b2r_image S;
+            memset(&S, 0, sizeof(S));
+            S.pixels    = big.px;
+            S.basetype  = B2R_FLOAT;
+            S.nchannels = nch;
+            S.width = S.full_width = w;
+            S.height = S.full_height = h;
+            S.xstride  = (int64_t)nch * 4;
+            S.ystride  = (int64_t)w * nch * 4;
+            S.memspace = B2R_MEM_DEVICE;
+            S.device   = device;
+            b2r_image D = S;
+            D.pixels    = lv.px;
+            D.width = D.full_width = sw;
+            D.height = D.full_height = sh;
+            D.ystride = (int64_t)sw * nch * 4;
+            if (fname == "box") {
+                if (pass == 0)
+                    continue;
+                BoxParams bp;
+                bp.dst = to_dev(D, D.pixels);
+                bp.src = to_dev(S, S.pixels);
+                // resize_block (:304-334): 2-pass needs 2*dw == sw and, without
+                // allow_pixel_shift, even source sizes (:265-266)
+                bp.two_pass = (2 * sw == w) && !(w % 2 || h % 2);
+                launch_box_downsample(bp, stream);
+                chain->launches += 1;
+            } else {
+                rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
+                                err, errlen);
+                if (rc) {
+                    if (ev0)
+                        cudaEventDestroy(ev0);
+                    if (ev1)
+                        cudaEventDestroy(ev1);
+                    return fail(rc);
+                }
+                if (pass == 1)
+                    chain->launches += 2;
             }
-            chain->launches += 2;
+            if (pass == 1 && clamp_half) {
+                launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,
+                             alpha_channel, -65504.0f, 65504.0f, stream);
+                chain->launches += 1;
+            }
         }
-        if (clamp_half) {
-            launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch, alpha_channel,
-                         -65504.0f, 65504.0f, stream);
-            chain->launches += 1;
-        }
-        w = sw;
-        h = sh;
     }
     cudaEventRecord(ev1, stream);
     cudaError_t e = cudaStreamSynchronize(stream);

@@ -198,6 +198,40 @@ fma4(float4& a, float w, const float4& v)
     fma4(a, make_float2(w, w), v);
 }
 
+// Where a V thread parks its 4 filtered elements (group v of the strip) in a
+// V row: RGBA -> one planar float4; RGB -> scattered into RGBX planar pixels
+// (elements straddle pixels); 1-2 channels -> flat floats.
+template<int NCH> struct VPark {
+    int off[NCH == 3 ? 4 : 1];
+    __device__ __forceinline__ void init(int e0, int v)
+    {
+        if (NCH == 4) {
+            off[0] = planar_byte(v);
+        } else if (NCH == 3) {
+            const int px0 = e0 / 3;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int E  = e0 + 4 * v + k;
+                int px = E / 3;
+                off[NCH == 3 ? k : 0] = planar_byte(px - px0) + (E - 3 * px) * 4;
+            }
+        } else {
+            off[0] = v * 16;
+        }
+    }
+    __device__ __forceinline__ void store(unsigned char* row, const float4& a) const
+    {
+        if (NCH == 3) {
+            *reinterpret_cast<float*>(row + off[0])               = a.x;
+            *reinterpret_cast<float*>(row + off[NCH == 3 ? 1 : 0]) = a.y;
+            *reinterpret_cast<float*>(row + off[NCH == 3 ? 2 : 0]) = a.z;
+            *reinterpret_cast<float*>(row + off[NCH == 3 ? 3 : 0]) = a.w;
+        } else {
+            *reinterpret_cast<float4*>(row + off[0]) = a;
+        }
+    }
+};
+
 // ---- H pass over `nb` buffered rows; dst rows dyb .. dyb+nb-1 of the ROI ---
 // hbA / hbB are BYTE offsets of tap 0 / tap 1 in this thread's first V row
 // (row hr).  The row pitch is a compile-time constant so every LDS below is
@@ -257,35 +291,39 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
     const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
     constexpr int rstep = FUSED_THREADS / FUSED_HCOLS;
     constexpr int NR    = (BATCH + rstep - 1) / rstep;  // rows per thread
-    float a[NR][NCH];
+    // RGB rows are stored padded to RGBX (the V pass scatters its elements),
+    // so 3- and 4-channel images share the float4 / FFMA2 path
+    constexpr bool PADDED = (NCH >= 3);
+    constexpr int NA      = PADDED ? 4 : NCH;
+    float a[NR][NA];
 #pragma unroll
     for (int k = 0; k < NR; ++k)
 #pragma unroll
-        for (int c = 0; c < NCH; ++c)
+        for (int c = 0; c < NA; ++c)
             a[k][c] = 0.0f;
 #pragma unroll
     for (int i = 0; i < HT; ++i) {
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             // rows past nb hold stale data from an earlier batch: computed
-            // and discarded
-            // tap i: RGBA even/odd planar (even taps off hbA, odd taps off hbB);
-            // other channel counts are flat floats, NCH*4 bytes per tap
+            // and discarded.  Tap i: planar float4 rows take even taps off
+            // hbA and odd taps off hbB; flat rows (1-2 channels) are NCH*4
+            // bytes per tap.
             const unsigned char* t
                 = vrows + k * rstep * FUSED_PITCH_B
-                  + ((NCH == 4) ? (((i & 1) ? hbB : hbA) + (i >> 1) * 16)
-                                : (hbA + i * NCH * 4));
-            if (NCH == 4) {
+                  + (PADDED ? (((i & 1) ? hbB : hbA) + (i >> 1) * 16)
+                            : (hbA + i * NCH * 4));
+            if (PADDED) {
                 const float4 v  = *reinterpret_cast<const float4*>(t);
                 const float2 ww = make_float2(hwt[i], hwt[i]);
                 float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
                                        make_float2(a[k][0], a[k][1]));
                 float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
-                                       make_float2(a[k][2], a[k][NCH - 1]));
-                a[k][0]       = lo.x;
-                a[k][1]       = lo.y;
-                a[k][2]       = hi.x;
-                a[k][NCH - 1] = hi.y;
+                                       make_float2(a[k][2], a[k][NA - 1]));
+                a[k][0]      = lo.x;
+                a[k][1]      = lo.y;
+                a[k][2]      = hi.x;
+                a[k][NA - 1] = hi.y;
             } else {
                 const float* v = reinterpret_cast<const float*>(t);
 #pragma unroll
@@ -305,7 +343,11 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
             for (int c = 0; c < NCH; ++c)
                 t += a[k][c];  // Inf/NaN in any channel survives the sum
             bad |= !(fabsf(t) <= 3.402823466e+38f);
-            store_pixel<NCH>(p, dp, des, a[k]);
+            float o[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                o[c] = a[k][c];
+            store_pixel<NCH>(p, dp, des, o);
         }
         dp += (long long)rstep * p.dst_ystride;
     }
@@ -345,8 +387,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         for (int i = 0; i < HT; ++i)
             hwt[i] = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
         if (col_active) {
-            if (NCH == 4) {
-                int q = f - strip.e0 / 4;
+            if (NCH >= 3) {
+                int q = f - strip.e0 / NCH;  // pixel index within the strip
                 hbA   = planar_byte(q) + hr * pitch_b;
                 hbB   = planar_byte(q + 1) + hr * pitch_b;
             } else {
@@ -360,7 +402,15 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const int e         = strip.e0 + 4 * tid;
     const int row_elems = p.src_w * NCH;
     const bool vec_ok   = p.src_vec_ok != 0;
-    unsigned char* vdst = vrows + ((NCH == 4) ? planar_byte(tid) : tid * 16);
+    // where this thread parks its 4 V-filtered elements in a V row
+    VPark<NCH> park;
+    park.init(strip.e0, tid);
+    if (NCH == 3) {
+        // RGBX rows: the X lane is never written, it must read as zero
+        for (int i = tid; i < BATCH * (FUSED_PITCH_B / 16); i += FUSED_THREADS)
+            reinterpret_cast<uint4*>(vrows)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+    }
     const int dy_end    = band.dy0 + band.ndy;
     int nb              = 0;
 
@@ -452,7 +502,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // a destination row is complete: park it for the H pass
         auto emit = [&](int s) {
             if (vactive)
-                *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = acc[s];
+                park.store(vrows + (size_t)nb * pitch_b, acc[s]);
             acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
             ++nb;
         };
@@ -538,30 +588,34 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         }
         cp_async_wait<0>();
     } else {
-        // gather mode: each dst row reads its own vt source rows (upsampling:
-        // consecutive dst rows share rows, which stay in L1/L2)
-        for (int dy = band.dy0; dy < dy_end; ++dy) {
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vactive) {
+        // gather mode (upsizing): each dst row gathers its own vt source rows
+        // through L1 (consecutive dst rows share rows).  A strip holds few
+        // source pixels here, so the (row, group) items of a whole batch are
+        // spread over all threads instead of leaving most of the CTA idle.
+        const int nvec = strip.nvec;
+        for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
+            const int nrows = min(BATCH, dy_end - dyb);
+            for (int it = tid; it < nrows * nvec; it += FUSED_THREADS) {
+                const int row = it / nvec, v = it - row * nvec;
+                const int dy    = dyb + row;
+                const int ev    = strip.e0 + 4 * v;
                 const int first = p.vfirst[dy];
                 const float* w  = p.vw + (size_t)dy * p.vt;
-                const unsigned char* rowp
-                    = p.src + (long long)first * p.src_ystride;
+                const unsigned char* rowp = p.src + (long long)first * p.src_ystride;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                 for (int j = 0; j < p.vt; ++j) {
-                    uint4 raw = load_raw4<ST>(rowp, e, row_elems, vec_ok);
+                    uint4 raw = load_raw4<ST>(rowp, ev, row_elems, vec_ok);
                     fma4(a, __ldg(w + j), convert_raw4<ST>(raw));
                     rowp += p.src_ystride;
                 }
-                *reinterpret_cast<float4*>(vdst + (size_t)nb * pitch_b) = a;
+                VPark<NCH> pk;
+                pk.init(strip.e0, v);
+                pk.store(vrows + (size_t)row * pitch_b, a);
             }
-            ++nb;
-            if (nb == BATCH || dy + 1 == dy_end) {
-                __syncthreads();
-                fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy + 1 - nb, dxg, col_active,
-                                            hbA, hbB, hwt, hr);
-                __syncthreads();
-                nb = 0;
-            }
+            __syncthreads();
+            fused_hpass<NCH, HT, BATCH>(p, vrows, nrows, dyb, dxg, col_active, hbA,
+                                        hbB, hwt, hr);
+            __syncthreads();
         }
     }
 }

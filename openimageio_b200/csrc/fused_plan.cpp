@@ -65,7 +65,9 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         while (dx0 + s.ndx < W && s.ndx < FUSED_HCOLS) {
             int eend = (P.hfirst[dx0 + s.ndx] + P.ht) * nch;
             int nvec = (eend - s.e0 + 3) / 4;
-            if (nvec > FUSED_THREADS)
+            // RGB rows are parked padded to RGBX: a V row holds 256 pixels
+            if (nvec > FUSED_THREADS
+                || (nch == 3 && (4 * nvec + 2) / 3 + 1 > FUSED_THREADS))
                 break;
             s.nvec = nvec;
             ++s.ndx;

@@ -10,6 +10,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 namespace b2r {
 
 namespace {
@@ -183,10 +185,11 @@ __global__ void __launch_bounds__(256)
 box2_rgba_kernel(const float4* __restrict__ src, long long src_ystride_4,
                  float4* __restrict__ dst, long long dst_ystride_4, int dw, int dh)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)dw * dh)
+    // 2-D grid: no 64-bit div/mod per thread (they dominated a 1-D version)
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dw)
         return;
-    const int y = int(idx / dw), x = int(idx % dw);
+    for (int y = blockIdx.y; y < dh; y += gridDim.y) {
     const float4* r0 = src + (long long)(2 * y) * src_ystride_4 + 2 * x;
     const float4* r1 = r0 + src_ystride_4;
     float4 a = __ldg(r0), b = __ldg(r0 + 1), c = __ldg(r1), d = __ldg(r1 + 1);
@@ -200,6 +203,7 @@ box2_rgba_kernel(const float4* __restrict__ src, long long src_ystride_4,
     o.w = __fmul_rn(0.5f, __fadd_rn(__fmul_rn(0.5f, __fadd_rn(a.w, b.w)),
                                     __fmul_rn(0.5f, __fadd_rn(c.w, d.w))));
     dst[(long long)y * dst_ystride_4 + x] = o;
+    }
 }
 
 // resize_block_ (:205-241) + interppixel_NDC (:141-198, non-envlatl)
@@ -288,8 +292,8 @@ launch_box_downsample(const BoxParams& p, void* stream)
                           && ((uintptr_t)D.pixels % 16 == 0) && S.ystride % 16 == 0
                           && D.ystride % 16 == 0;
         if (rgba) {
-            long long n = (long long)D.width * D.height;
-            box2_rgba_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            dim3 grid((D.width + 255) / 256, std::min(D.height, 32768), 1);
+            box2_rgba_kernel<<<grid, 256, 0, st>>>(
                 (const float4*)S.pixels, S.ystride / 16, (float4*)D.pixels,
                 D.ystride / 16, D.width, D.height);
         } else {
