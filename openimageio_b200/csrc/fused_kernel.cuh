@@ -36,6 +36,14 @@ template<> struct SrcTraits<ST_U16> { static constexpr int es = 2, bt = BT_UINT1
 template<> struct SrcTraits<ST_HALF> { static constexpr int es = 2, bt = BT_HALF; };
 template<> struct SrcTraits<ST_FLOAT> { static constexpr int es = 4, bt = BT_FLOAT; };
 
+// Exact uint -> float for values below 2^23 without the (slow) I2F unit:
+// 0x4B000000 | v is the float 8388608 + v; subtracting 8388608 is exact.
+__device__ __forceinline__ float
+small_uint_to_float(unsigned v)
+{
+    return __fsub_rn(__uint_as_float(0x4B000000u | v), 8388608.0f);
+}
+
 // ---- raw 4-element groups ------------------------------------------------
 // float -> 4 words, half/uint16 -> 2 words, uint8 -> 1 word.
 template<int ST>
@@ -52,16 +60,16 @@ convert_raw4(uint4 r)
         return make_float4(fa.x, fa.y, fb.x, fb.y);
     } else if (ST == ST_U16) {
         const float s = 1.0f / 65535.0f;
-        return make_float4(__fmul_rn(float(r.x & 0xffffu), s),
-                           __fmul_rn(float(r.x >> 16), s),
-                           __fmul_rn(float(r.y & 0xffffu), s),
-                           __fmul_rn(float(r.y >> 16), s));
+        return make_float4(__fmul_rn(small_uint_to_float(r.x & 0xffffu), s),
+                           __fmul_rn(small_uint_to_float(r.x >> 16), s),
+                           __fmul_rn(small_uint_to_float(r.y & 0xffffu), s),
+                           __fmul_rn(small_uint_to_float(r.y >> 16), s));
     } else {
         const float s = 1.0f / 255.0f;
-        return make_float4(__fmul_rn(float(r.x & 0xffu), s),
-                           __fmul_rn(float((r.x >> 8) & 0xffu), s),
-                           __fmul_rn(float((r.x >> 16) & 0xffu), s),
-                           __fmul_rn(float(r.x >> 24), s));
+        return make_float4(__fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4440)), s),
+                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4441)), s),
+                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4442)), s),
+                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4443)), s));
     }
 }
 
@@ -593,10 +601,19 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // source pixels here, so the (row, group) items of a whole batch are
         // spread over all threads instead of leaving most of the CTA idle.
         const int nvec = strip.nvec;
+        // the thread's first item of every batch is the same (row, group):
+        // its parking offsets are computed once
+        const int row0 = tid / nvec, v0 = tid - row0 * nvec;
+        VPark<NCH> park0;
+        park0.init(strip.e0, v0);
         for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
             const int nrows = min(BATCH, dy_end - dyb);
             for (int it = tid; it < nrows * nvec; it += FUSED_THREADS) {
-                const int row = it / nvec, v = it - row * nvec;
+                int row = row0, v = v0;
+                if (it != tid) {
+                    row = it / nvec;
+                    v   = it - row * nvec;
+                }
                 const int dy    = dyb + row;
                 const int ev    = strip.e0 + 4 * v;
                 const int first = p.vfirst[dy];
@@ -608,9 +625,13 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                     fma4(a, __ldg(w + j), convert_raw4<ST>(raw));
                     rowp += p.src_ystride;
                 }
-                VPark<NCH> pk;
-                pk.init(strip.e0, v);
-                pk.store(vrows + (size_t)row * pitch_b, a);
+                if (it == tid) {
+                    park0.store(vrows + (size_t)row * pitch_b, a);
+                } else {
+                    VPark<NCH> pk;
+                    pk.init(strip.e0, v);
+                    pk.store(vrows + (size_t)row * pitch_b, a);
+                }
             }
             __syncthreads();
             fused_hpass<NCH, HT, BATCH>(p, vrows, nrows, dyb, dxg, col_active, hbA,
