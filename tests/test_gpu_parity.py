@@ -382,3 +382,40 @@ def test_full_size_configs_sampled_against_oracle(oiio, oracle, name):
     # no band left unwritten: a random image never resizes to all-zero rows
     rowsum = out.reshape(dh, -1).astype(np.float64).sum(axis=1)
     assert (rowsum != 0).all()
+
+
+@pytest.mark.parametrize("dt,nch", [(np.float32, 4), (np.uint8, 3), (np.float16, 4),
+                                    (np.uint16, 3), (np.float32, 1)])
+def test_device_strided_rows_and_canaries(oiio, oracle, dt, nch):
+    """Device-resident src/dst whose rows are padded (ystride > width) and
+    which sit inside larger allocations: results match the oracle and not one
+    byte outside the dst ROI rows is written (compute-sanitizer is closed on
+    this pool, so out-of-bounds stores are hunted with canaries)."""
+    import torch
+    tdt = {np.float32: torch.float32, np.uint8: torch.uint8,
+           np.float16: torch.float16, np.uint16: torch.uint16}[dt]
+    sw, sh, dw, dh = 211, 150, 97, 71
+    src = synth.image(sw, sh, nch, dt, seed=123)
+    ref = np.zeros((dh, dw, nch), dt)
+    oracle.resize(oracle.Img(ref), oracle.Img(src))
+    spad, dpad = 5, 7  # extra pixels per row
+    S = torch.zeros((sh + 4, sw + spad, nch), dtype=tdt, device="cuda")
+    host = torch.from_numpy(src.view(np.int16) if dt == np.uint16 else src)
+    if dt == np.uint16:
+        host = host.view(torch.uint16)
+    S[2:2 + sh, :sw] = host.cuda()
+    fill = 77 if dt in (np.uint8, np.uint16) else 0.5
+    D = torch.full((dh + 6, dw + dpad, nch), fill, dtype=tdt, device="cuda")
+    sview, dview = S[2:2 + sh, :sw], D[3:3 + dh, :dw]
+    ok = oiio.ImageBufAlgo.resize(oiio.ImageBuf(dview), oiio.ImageBuf(sview))
+    assert ok
+    torch.cuda.synchronize()
+    Dh = D.cpu()
+    if dt == np.uint16:
+        Dn = Dh.view(torch.int16).numpy().view(np.uint16)
+    else:
+        Dn = Dh.numpy()
+    check(Dn[3:3 + dh, :dw], ref)
+    canary = np.full_like(Dn, fill)
+    canary[3:3 + dh, :dw] = Dn[3:3 + dh, :dw]
+    assert np.array_equal(canary, Dn), "bytes outside the dst ROI were written"
