@@ -428,6 +428,14 @@ struct DeviceGuard {
 };
 
 int
+resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
+                      const Filter2D& filter, const b2r_roi& roi, int device,
+                      int path, b2r_report* report, char* err, size_t errlen);
+
+// options.reserved[] is private to the library:
+//   [0] == 1  build + upload the tables only, no launch (MIP chain pass 1)
+//   [1] == 1  sub-call of the pipelined host path: never time, never sync
+int
 resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             const Filter2D& filter, const b2r_roi* roi_in,
             const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
@@ -497,6 +505,19 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
     const int path      = opt ? opt->path : B2R_PATH_AUTO;
 
+    // Large host -> host resize: run it as a pipeline of row bands so the
+    // upload of later source rows, the kernels and the download of finished
+    // rows overlap (PCIe is full duplex; the copies dominate end to end).
+    if (smem == B2R_MEM_HOST && dmem == B2R_MEM_HOST && roi_h >= 256
+        && src.xstride == (int64_t)src.nchannels * ses
+        && dst.xstride == (int64_t)dst.nchannels * des
+        && std::max((int64_t)src.width * src.height * src.xstride,
+                    (int64_t)roi_w * roi_h * dst.xstride)
+               >= (int64_t(32) << 20)
+        && !(opt && (opt->reserved[0] || opt->reserved[1])))
+        return resize_host_pipelined(dst, src, filter, roi, device, path, report,
+                                     err, errlen);
+
     std::shared_ptr<DevicePlan> plan;
     rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 3, stream, &plan,
                   err, errlen);
@@ -561,7 +582,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    const bool timed = report != nullptr;
+    const bool timed = report != nullptr && !(opt && opt->reserved[1]);
     if (timed) {
         cudaEventCreate(&ev0);
         cudaEventCreate(&ev1);
@@ -723,6 +744,176 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     if (ev1)
         cudaEventDestroy(ev1);
     return B2R_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Host -> host resize as a 3-stream pipeline over row bands of the dst ROI:
+//   stream in : H2D of the source rows band i still needs (band + halo,
+//               each source row travels once)
+//   stream k  : the band's kernels (device-resident sub-call)
+//   stream out: D2H of the band's finished rows
+// ---------------------------------------------------------------------------
+struct PipeStreams {
+    cudaStream_t in = nullptr, k = nullptr, out = nullptr;
+};
+PipeStreams&
+pipe_streams(int dev)
+{
+    static PipeStreams s[64];
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    PipeStreams& p = s[dev & 63];
+    if (!p.in) {
+        cudaStreamCreateWithFlags(&p.in, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&p.k, cudaStreamNonBlocking);
+        cudaStreamCreateWithFlags(&p.out, cudaStreamNonBlocking);
+    }
+    return p;
+}
+
+int
+resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
+                      const Filter2D& filter, const b2r_roi& roi, int device,
+                      int path, b2r_report* report, char* err, size_t errlen)
+{
+    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+    const int nbands = std::max(2, std::min(16, roi_h / 128));
+    // one mutex per device: the three streams are shared by all callers
+    static std::mutex pipe_mutex[64];
+    std::lock_guard<std::mutex> lock(pipe_mutex[device & 63]);
+    PipeStreams& ps = pipe_streams(device);
+
+    // source rows each band touches (band + filter halo)
+    std::vector<b2r_roi> bands(nbands);
+    std::vector<int> r0(nbands), r1(nbands);
+    AxisGeom gx { roi.xbegin, roi.xbegin, dst.full_x, dst.full_width, src.full_x,
+                  src.full_width, src.x, src.x + src.width };
+    AxisTaps tx = build_axis_taps(gx, filter, false);
+    for (int i = 0; i < nbands; ++i) {
+        b2r_band_split(&roi, nbands, i, &bands[i]);
+        AxisGeom gy { bands[i].ybegin, bands[i].yend, dst.full_y, dst.full_height,
+                      src.full_y, src.full_height, src.y, src.y + src.height };
+        AxisTaps ty = build_axis_taps(gy, filter, true);
+        source_row_span(src, filter, tx, ty, &r0[i], &r1[i]);
+    }
+    int lo = r0[0], hi = r1[0];
+    for (int i = 1; i < nbands; ++i) {
+        lo = std::min(lo, r0[i]);
+        hi = std::max(hi, r1[i]);
+    }
+    const size_t srow = size_t(src.width) * src.xstride;
+    const size_t spitch = (srow + 15) & ~size_t(15);
+    const size_t drow = size_t(roi_w) * dst.xstride;
+    const size_t dpitch = (drow + 15) & ~size_t(15);
+    void *salloc = nullptr, *dalloc = nullptr;
+    CUDA_TRY(cudaMallocAsync(&salloc, spitch * size_t(hi - lo + 1), ps.k));
+    CUDA_TRY(cudaMallocAsync(&dalloc, dpitch * size_t(roi_h), ps.k));
+    cudaEvent_t ready;  // the allocations exist before any copy touches them
+    cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    cudaEventRecord(ready, ps.k);
+    cudaStreamWaitEvent(ps.in, ready, 0);
+    cudaStreamWaitEvent(ps.out, ready, 0);
+
+    b2r_image S = src, D = dst;
+    S.pixels   = (unsigned char*)salloc - (long long)lo * (long long)spitch;
+    S.ystride  = (int64_t)spitch;
+    S.memspace = B2R_MEM_DEVICE;
+    S.device   = device;
+    D.pixels   = dalloc;
+    D.x        = roi.xbegin;
+    D.y        = roi.ybegin;
+    D.width    = roi_w;
+    D.height   = roi_h;
+    D.ystride  = (int64_t)dpitch;
+    D.memspace = B2R_MEM_DEVICE;
+    D.device   = device;
+
+    b2r_options sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.device      = device;
+    sub.path        = path;
+    sub.cuda_stream = (void*)ps.k;
+    sub.reserved[1] = 1;
+
+    std::vector<cudaEvent_t> evs;
+    auto new_event = [&]() {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        evs.push_back(e);
+        return e;
+    };
+    int rc = B2R_OK;
+    int uploaded = lo;  // next source row to upload
+    b2r_report last;
+    memset(&last, 0, sizeof(last));
+    for (int i = 0; i < nbands && rc == B2R_OK; ++i) {
+        if (bands[i].yend <= bands[i].ybegin)
+            continue;
+        // bands go top to bottom and their spans are monotone: everything
+        // below `uploaded` is already on its way, only [uploaded, r1] is new
+        const int need = r1[i];
+        if (need >= uploaded) {
+            cudaError_t e = cudaMemcpy2DAsync(
+                (unsigned char*)salloc + size_t(uploaded - lo) * spitch, spitch,
+                (const unsigned char*)src.pixels + (long long)uploaded * src.ystride,
+                src.ystride, srow, size_t(need - uploaded + 1),
+                cudaMemcpyHostToDevice, ps.in);
+            if (e != cudaSuccess) {
+                set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+                rc = B2R_ERR_CUDA;
+                break;
+            }
+            if (report)
+                report->h2d_bytes += (int64_t)srow * (need - uploaded + 1);
+            uploaded = need + 1;
+        }
+        cudaEvent_t e_in = new_event();
+        cudaEventRecord(e_in, ps.in);
+        cudaStreamWaitEvent(ps.k, e_in, 0);
+        rc = resize_impl(&D, &S, filter, &bands[i], &sub, &last, err, errlen);
+        if (rc)
+            break;
+        cudaEvent_t e_k = new_event();
+        cudaEventRecord(e_k, ps.k);
+        cudaStreamWaitEvent(ps.out, e_k, 0);
+        const int by = bands[i].ybegin - roi.ybegin, bh = bands[i].yend - bands[i].ybegin;
+        unsigned char* hp = (unsigned char*)dst.pixels
+                            + (long long)(bands[i].ybegin - dst.y) * dst.ystride
+                            + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        cudaError_t e = cudaMemcpy2DAsync(hp, dst.ystride,
+                                          (unsigned char*)dalloc + size_t(by) * dpitch,
+                                          dpitch, drow, size_t(bh),
+                                          cudaMemcpyDeviceToHost, ps.out);
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+            rc = B2R_ERR_CUDA;
+            break;
+        }
+        if (report) {
+            report->d2h_bytes += (int64_t)drow * bh;
+            report->kernels_launched += last.kernels_launched;
+        }
+    }
+    cudaStreamSynchronize(ps.in);
+    cudaStreamSynchronize(ps.k);
+    cudaError_t es = cudaStreamSynchronize(ps.out);
+    cudaFreeAsync(salloc, ps.k);
+    cudaFreeAsync(dalloc, ps.k);
+    cudaEventDestroy(ready);
+    for (cudaEvent_t e : evs)
+        cudaEventDestroy(e);
+    if (rc == B2R_OK && es != cudaSuccess) {
+        set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(es));
+        rc = B2R_ERR_CUDA;
+    }
+    if (report && rc == B2R_OK) {
+        report->path_used   = last.path_used;
+        report->xtaps       = last.xtaps;
+        report->ytaps       = last.ytaps;
+        report->fused_vmode = last.fused_vmode;
+        report->fused_htaps = last.fused_htaps;
+    }
+    return rc;
 }
 
 }  // namespace
