@@ -419,3 +419,31 @@ def test_device_strided_rows_and_canaries(oiio, oracle, dt, nch):
     canary = np.full_like(Dn, fill)
     canary[3:3 + dh, :dw] = Dn[3:3 + dh, :dw]
     assert np.array_equal(canary, Dn), "bytes outside the dst ROI were written"
+
+
+def test_concurrent_calls_from_threads(oiio, oracle):
+    """The ABI is re-entrant: concurrent calls on distinct dst images (same
+    shape -> shared cached plan, and different shapes) give the same results
+    as serial calls."""
+    import threading
+    srcs = [synth.image(160, 120, 4, np.float32, seed=200 + i) for i in range(6)]
+    shapes = [(60, 80), (60, 80), (45, 70), (60, 80), (90, 33), (45, 70)]
+    outs = [np.zeros(s + (4,), np.float32) for s in shapes]
+    errs = []
+
+    def work(i):
+        for _ in range(5):
+            D = oiio.ImageBuf(outs[i])
+            if not oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(srcs[i])):
+                errs.append(D.geterror())
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(6)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(6):
+        ref = np.zeros_like(outs[i])
+        oracle.resize(oracle.Img(ref), oracle.Img(srcs[i]))
+        check(outs[i], ref)
