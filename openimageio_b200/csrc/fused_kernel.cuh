@@ -291,8 +291,7 @@ store_pixel(const FusedParams& p, unsigned char* dp, int des, const float (&a)[N
 template<int NCH, int HT, int BATCH>
 __device__ __forceinline__ void
 fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
-            int dxg, bool col_active, int hbA, int hbB, const float (&hwt)[HT],
-            int hr)
+            int dxg, bool col_active, int hbA, int hbB, const float* hws, int hr)
 {
     if (!col_active)
         return;
@@ -303,6 +302,13 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
     // so 3- and 4-channel images share the float4 / FFMA2 path
     constexpr bool PADDED = (NCH >= 3);
     constexpr int NA      = PADDED ? 4 : NCH;
+    // this column's HT weights: staged once per CTA in shared memory (lane ==
+    // column, conflict-free), re-read per call so they do not occupy
+    // registers across the V pass
+    float hwt[HT];
+#pragma unroll
+    for (int i = 0; i < HT; ++i)
+        hwt[i] = hws[i * FUSED_HCOLS];
     float a[NR][NA];
 #pragma unroll
     for (int k = 0; k < NR; ++k)
@@ -365,6 +371,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
 
 // Shared memory carve-up (bytes):
 //   vrows  fused_batch(VK) x FUSED_PITCH_B       V-filtered rows for the H pass
+//   hws    HT x FUSED_HCOLS x 4                  H weights, [tap][column]
 //   fifo   FUSED_FIFO x FUSED_THREADS x 16       per-thread prefetch   (ring)
 //   ringw  max_band_rows x VKP x 4               ring weights            "
 //   lastr  max_band_dy x 4                       completion rows         "
@@ -387,13 +394,17 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const int hr          = tid / FUSED_HCOLS;
     const bool col_active = hc < strip.ndx;
     const int dxg         = strip.dx0 + hc;
-    float hwt[HT];
     int hbA = 0, hbB = 0;  // byte offsets of tap 0 / tap 1 in this thread's row
+    float* hws_all = reinterpret_cast<float*>(smem_raw + BATCH * FUSED_PITCH_B);
+    const float* hws = hws_all + hc;
     {
         int f = col_active ? p.hfirst[dxg] : 0;
+        if (hr == 0) {
 #pragma unroll
-        for (int i = 0; i < HT; ++i)
-            hwt[i] = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
+            for (int i = 0; i < HT; ++i)
+                hws_all[i * FUSED_HCOLS + hc]
+                    = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
+        }
         if (col_active) {
             if (NCH >= 3) {
                 int q = f - strip.e0 / NCH;  // pixel index within the strip
@@ -429,7 +440,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         constexpr int SLOT = FUSED_THREADS * 16;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
-        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B;
+        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HCOLS * 4;
         float* ringw = reinterpret_cast<float*>(fifo + FUSED_FIFO * SLOT);
         int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
 
@@ -521,7 +532,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
             if (nb + VK > BATCH || dy_done >= dy_end) {
                 __syncthreads();
                 fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy_done - nb, dxg, col_active,
-                                            hbA, hbB, hwt, hr);
+                                            hbA, hbB, hws, hr);
                 __syncthreads();
                 nb = 0;
             }
@@ -635,7 +646,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
             }
             __syncthreads();
             fused_hpass<NCH, HT, BATCH>(p, vrows, nrows, dyb, dxg, col_active, hbA,
-                                        hbB, hwt, hr);
+                                        hbB, hws, hr);
             __syncthreads();
         }
     }

@@ -271,6 +271,7 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
 {
     (void)max_nvec;
     size_t f = (size_t)fused_batch(p.vk) * (FUSED_THREADS * 4 + 32);  // FUSED_PITCH_B
+    f += (size_t)p.ht * FUSED_HCOLS;  // H weights
     if (p.vk > 0) {
         f += (size_t)max_band_rows * ((2 * p.vk + 3) & ~3);
         f += (size_t)((max_band_dy + 3) & ~3);
