@@ -450,13 +450,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         return rc;
     const b2r_image& dst = *dst_in;
     const b2r_image& src = *src_in;
-    if (!legal_pair(dst.basetype, src.basetype)) {
-        set_err(err, errlen,
-                "resize: (dst,src) pixel types (%d,%d) are not a native pair; "
-                "convert through float first",
-                dst.basetype, src.basetype);
-        return B2R_ERR_TYPES;
-    }
     if (src.nchannels < dst.nchannels) {
         set_err(err, errlen,
                 "resize: source has %d channels, destination %d",
@@ -504,6 +497,66 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     DeviceInfo& di      = device_info(device);
     cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
     const int path      = opt ? opt->path : B2R_PATH_AUTO;
+
+    // (dst,src) pairs outside OIIO_DISPATCH_COMMON_TYPES2's ten native ones
+    // are computed through a float temporary and converted back
+    // (imagebufalgo_util.h:463-478, 540-546) -- here on the device: float
+    // ROI rectangle, then convert_type<float,D> into dst.
+    if (!legal_pair(dst.basetype, src.basetype)) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "destination pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        void* ftmp = nullptr;
+        const size_t frow = size_t(roi_w) * dst.nchannels * 4;
+        CUDA_TRY(cudaMallocAsync(&ftmp, frow * roi_h, stream));
+        b2r_image F = dst;
+        F.pixels    = ftmp;
+        F.basetype  = B2R_FLOAT;
+        F.x         = roi.xbegin;
+        F.y         = roi.ybegin;
+        F.width     = roi_w;
+        F.height    = roi_h;
+        F.xstride   = (int64_t)dst.nchannels * 4;
+        F.ystride   = (int64_t)frow;
+        F.memspace  = B2R_MEM_DEVICE;
+        F.device    = device;
+        b2r_options sub;
+        memset(&sub, 0, sizeof(sub));
+        sub.device      = device;
+        sub.path        = path;
+        sub.cuda_stream = (void*)stream;
+        sub.reserved[1] = 1;
+        rc = resize_impl(&F, &src, filter, &roi, &sub, report, err, errlen);
+        if (rc == B2R_OK) {
+            const size_t drow = size_t(roi_w) * dst.xstride;
+            unsigned char* out = (unsigned char*)dst.pixels
+                                 + (long long)(roi.ybegin - dst.y) * dst.ystride
+                                 + (long long)(roi.xbegin - dst.x) * dst.xstride;
+            if (dmem == B2R_MEM_DEVICE) {
+                launch_convert_from_float((const float*)ftmp, (long long)frow, out,
+                                          dst.ystride, roi_w * dst.nchannels, roi_h,
+                                          dst.basetype, stream);
+            } else {
+                void* dtmp = nullptr;
+                CUDA_TRY(cudaMallocAsync(&dtmp, drow * roi_h, stream));
+                launch_convert_from_float((const float*)ftmp, (long long)frow, dtmp,
+                                          (long long)drow, roi_w * dst.nchannels,
+                                          roi_h, dst.basetype, stream);
+                CUDA_TRY(cudaMemcpy2DAsync(out, dst.ystride, dtmp, drow, drow, roi_h,
+                                           cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaFreeAsync(dtmp, stream));
+                if (report)
+                    report->d2h_bytes += (int64_t)drow * roi_h;
+            }
+            if (report)
+                report->kernels_launched += 1;
+        }
+        cudaFreeAsync(ftmp, stream);
+        if (rc == B2R_OK && (dmem == B2R_MEM_HOST || smem == B2R_MEM_HOST))
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        return rc;
+    }
 
     // Large host -> host resize: run it as a pipeline of row bands so the
     // upload of later source rows, the kernels and the download of finished
@@ -1209,13 +1262,6 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
         return rc;
     const b2r_image& dst = *dst_in;
     const b2r_image& src = *src_in;
-    if (!legal_pair(dst.basetype, src.basetype)) {
-        set_err(err, errlen,
-                "resample: (dst,src) pixel types (%d,%d) are not a native pair; "
-                "convert through float first",
-                dst.basetype, src.basetype);
-        return B2R_ERR_TYPES;
-    }
     if (device_count_cached() <= 0) {
         set_err(err, errlen,
                 "no CUDA device available: the B200 resample path has no CPU "
@@ -1257,6 +1303,62 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
     DeviceGuard guard(device);
     device_info(device);
     cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+
+    // non-native (dst,src) pair: float temporary + convert back, as above
+    if (!legal_pair(dst.basetype, src.basetype)) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "destination pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        if (roi.chbegin != 0 || roi.chend < dst.nchannels) {
+            set_err(err, errlen,
+                    "resample: a channel sub-range needs a native (dst,src) pair");
+            return B2R_ERR_TYPES;
+        }
+        void* ftmp = nullptr;
+        const size_t frow = size_t(roi_w) * dst.nchannels * 4;
+        CUDA_TRY(cudaMallocAsync(&ftmp, frow * roi_h, stream));
+        b2r_image F = dst;
+        F.pixels    = ftmp;
+        F.basetype  = B2R_FLOAT;
+        F.x         = roi.xbegin;
+        F.y         = roi.ybegin;
+        F.width     = roi_w;
+        F.height    = roi_h;
+        F.xstride   = (int64_t)dst.nchannels * 4;
+        F.ystride   = (int64_t)frow;
+        F.memspace  = B2R_MEM_DEVICE;
+        F.device    = device;
+        b2r_options sub;
+        memset(&sub, 0, sizeof(sub));
+        sub.device      = device;
+        sub.cuda_stream = (void*)stream;
+        rc = b2r_resample(&F, &src, interpolate, &roi, &sub, nullptr, err, errlen);
+        if (rc == B2R_OK) {
+            const size_t drow = size_t(roi_w) * dst.xstride;
+            unsigned char* out = (unsigned char*)dst.pixels
+                                 + (long long)(roi.ybegin - dst.y) * dst.ystride
+                                 + (long long)(roi.xbegin - dst.x) * dst.xstride;
+            if (dmem == B2R_MEM_DEVICE) {
+                launch_convert_from_float((const float*)ftmp, (long long)frow, out,
+                                          dst.ystride, roi_w * dst.nchannels, roi_h,
+                                          dst.basetype, stream);
+            } else {
+                void* dtmp = nullptr;
+                CUDA_TRY(cudaMallocAsync(&dtmp, drow * roi_h, stream));
+                launch_convert_from_float((const float*)ftmp, (long long)frow, dtmp,
+                                          (long long)drow, roi_w * dst.nchannels,
+                                          roi_h, dst.basetype, stream);
+                CUDA_TRY(cudaMemcpy2DAsync(out, dst.ystride, dtmp, drow, drow, roi_h,
+                                           cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(cudaFreeAsync(dtmp, stream));
+            }
+        }
+        cudaFreeAsync(ftmp, stream);
+        if (rc == B2R_OK && (dmem == B2R_MEM_HOST || smem == B2R_MEM_HOST))
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        return rc;
+    }
 
     void* dsrc     = src.pixels;
     void* ddst     = dst.pixels;

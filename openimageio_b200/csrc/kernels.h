@@ -148,4 +148,11 @@ void
 launch_clamp(float* pixels, long long n, int nch, int alpha_channel, float lo,
              float hi, void* stream);
 
+// float -> dst type over a rectangle of `row_elems` x `height` elements
+// (the copy-back step for (dst,src) pairs computed through a float temporary)
+void
+launch_convert_from_float(const float* src, long long src_ystride_bytes, void* dst,
+                          long long dst_ystride_bytes, int row_elems, int height,
+                          int dst_basetype, void* stream);
+
 }  // namespace b2r

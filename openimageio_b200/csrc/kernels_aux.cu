@@ -306,7 +306,37 @@ clamp_kernel(float* px, long long n, int nch, int alpha, float lo, float hi)
     px[i] = r;
 }
 
+// convert_type<float, D> over a rectangle (fmath.h:753-764, 1009-1031): the
+// `R.copy(Rtmp, R.pixeltype())` step of OIIO_DISPATCH_COMMON_TYPES2 for
+// (dst,src) pairs that are computed through a float temporary.
+__global__ void __launch_bounds__(256)
+convert_from_float_kernel(const float* __restrict__ src, long long src_ystride_f,
+                          unsigned char* __restrict__ dst, long long dst_ystride,
+                          int row_elems, int h, int bt)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= row_elems)
+        return;
+    const int es = esize(bt);
+    for (int y = blockIdx.y; y < h; y += gridDim.y)
+        st_elem(dst + (long long)y * dst_ystride + (long long)e * es, bt,
+                src[(long long)y * src_ystride_f + e]);
+}
+
 }  // namespace
+
+void
+launch_convert_from_float(const float* src, long long src_ystride_bytes, void* dst,
+                          long long dst_ystride_bytes, int row_elems, int height,
+                          int dst_basetype, void* stream)
+{
+    if (row_elems <= 0 || height <= 0)
+        return;
+    dim3 grid((row_elems + 255) / 256, std::min(height, 32768), 1);
+    convert_from_float_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        src, src_ystride_bytes / 4, (unsigned char*)dst, dst_ystride_bytes, row_elems,
+        height, dst_basetype);
+}
 
 void
 launch_resample(const ResampleParams& p, int chbegin, int chend, void* stream)

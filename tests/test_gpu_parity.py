@@ -447,3 +447,26 @@ def test_concurrent_calls_from_threads(oiio, oracle):
         ref = np.zeros_like(outs[i])
         oracle.resize(oracle.Img(ref), oracle.Img(srcs[i]))
         check(outs[i], ref)
+
+
+@pytest.mark.parametrize("dt,st", [(np.uint8, np.uint16), (np.uint8, np.float16),
+                                   (np.float16, np.uint8), (np.float16, np.uint16),
+                                   (np.uint16, np.uint8), (np.uint16, np.float16)])
+def test_non_native_type_pairs_go_through_float(oiio, oracle, dt, st):
+    """OIIO_DISPATCH_COMMON_TYPES2 computes the six non-native (dst,src)
+    pairs into a float temporary and converts back (imagebufalgo_util.h:
+    463-478, 540-546); here the temporary lives on the device."""
+    src = synth.image(150, 110, 3, st, seed=301)
+    tmp = np.zeros((50, 70, 3), np.float32)
+    oracle.resize(oracle.Img(tmp), oracle.Img(src))
+    ref = oracle.quantize(tmp, dt)
+    out = np.zeros((50, 70, 3), dt)
+    assert oiio.ImageBufAlgo.resize(oiio.ImageBuf(out), oiio.ImageBuf(src))
+    check(out, ref)
+    # resample, nearest: exact
+    tmp = np.zeros((50, 70, 3), np.float32)
+    oracle.resample(oracle.Img(tmp), oracle.Img(src), False)
+    out = np.zeros((50, 70, 3), dt)
+    assert oiio.ImageBufAlgo.resample(oiio.ImageBuf(out), oiio.ImageBuf(src),
+                                      interpolate=False)
+    check(out, oracle.quantize(tmp, dt), exact=True)
