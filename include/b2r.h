@@ -221,6 +221,16 @@ B2R_API int b2r_mipchain_download(const b2r_mipchain* chain, int level,
 B2R_API float b2r_mipchain_kernel_ms(const b2r_mipchain* chain);
 B2R_API void b2r_mipchain_destroy(b2r_mipchain* chain);
 
+/* One level step of the chain on arbitrary windows: rows `roi` of level k+1
+ * (dst: data window = the rows held, display window = the whole level) from
+ * level k (src: data window = the rows available, display window = the whole
+ * level).  This is the loop body of write_mipmap (maketexture.cpp:881-922)
+ * for a row band; it is what a multi-GPU chain calls per band after the
+ * neighbour halo rows have arrived.  "box" levels must be device resident. */
+B2R_API int b2r_mip_level(const b2r_image* dst, const b2r_image* src,
+                          const char* filtername, const b2r_roi* roi,
+                          const b2r_options* opt, char* err, size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

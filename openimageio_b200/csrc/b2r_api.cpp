@@ -1624,6 +1624,7 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                 // resize_block (:304-334): 2-pass needs 2*dw == sw and, without
                 // allow_pixel_shift, even source sizes (:265-266)
                 bp.two_pass = (2 * sw == w) && !(w % 2 || h % 2);
+            bp.force_clamp = 0;
                 launch_box_downsample(bp, stream);
                 chain->launches += 1;
             } else {
@@ -1724,4 +1725,105 @@ b2r_mipchain_destroy(b2r_mipchain* chain)
         if (l.owned && l.px)
             cudaFree(l.px);
     delete chain;
+}
+
+// =========================================================================
+// one MIP level step on arbitrary windows (row-band sharding of the chain)
+// =========================================================================
+extern "C" int
+b2r_mip_level(const b2r_image* dst, const b2r_image* src, const char* filtername,
+              const b2r_roi* roi_in, const b2r_options* opt, char* err, size_t errlen)
+{
+    int rc = check_image(src, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst, false, err, errlen);
+    if (rc)
+        return rc;
+    std::string fname = (filtername && filtername[0]) ? filtername : "box";
+    if (fname != "box")
+        return b2r_resize(dst, src, fname.c_str(), 0.0f, roi_in, opt, nullptr, err,
+                          errlen);
+    if (dst->basetype != B2R_FLOAT || src->basetype != B2R_FLOAT
+        || dst->nchannels != src->nchannels) {
+        set_err(err, errlen, "mip_level: box levels are float32 with equal channels");
+        return B2R_ERR_TYPES;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 MIP path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    int sdev = 0, ddev = 0;
+    if (memspace_of(src, &sdev) != B2R_MEM_DEVICE
+        || memspace_of(dst, &ddev) != B2R_MEM_DEVICE || sdev != ddev) {
+        set_err(err, errlen, "mip_level: box levels must be device resident");
+        return B2R_ERR_UNSUPPORTED;
+    }
+    b2r_roi roi = roi_in ? *roi_in
+                         : b2r_roi { dst->x, dst->x + dst->width, dst->y,
+                                     dst->y + dst->height, 0, dst->nchannels };
+    roi.xbegin = std::max(roi.xbegin, dst->x);
+    roi.xend   = std::min(roi.xend, dst->x + dst->width);
+    roi.ybegin = std::max(roi.ybegin, dst->y);
+    roi.yend   = std::min(roi.yend, dst->y + dst->height);
+    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin)
+        return B2R_OK;
+    DeviceGuard guard(sdev);
+    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+    const int nch = dst->nchannels;
+    // resize_block (maketexture.cpp:304-334): the 2x2 average applies when the
+    // WHOLE level halves an even-sized, zero-origin image; a band of it is the
+    // same arithmetic on rows 2y, 2y+1
+    const bool two_pass
+        = 2 * dst->full_width == src->full_width && !(src->full_width % 2)
+          && !(src->full_height % 2) && dst->full_x == 0 && dst->full_y == 0
+          && src->full_x == 0 && src->full_y == 0 && roi.xbegin == 0
+          && roi.xend == dst->full_width && dst->x == 0 && src->x == 0
+          && src->width == src->full_width && dst->width == dst->full_width;
+    BoxParams bp;
+    if (two_pass) {
+        if (2 * roi.ybegin < src->y || 2 * roi.yend > src->y + src->height) {
+            set_err(err, errlen, "mip_level: source rows [%d,%d) not present",
+                    2 * roi.ybegin, 2 * roi.yend);
+            return B2R_ERR_INVALID;
+        }
+        b2r_image D = *dst, S = *src;
+        D.pixels = (unsigned char*)dst->pixels
+                   + (long long)(roi.ybegin - dst->y) * dst->ystride;
+        D.y      = 0;
+        D.height = roi.yend - roi.ybegin;
+        S.pixels = (unsigned char*)src->pixels
+                   + (long long)(2 * roi.ybegin - src->y) * src->ystride;
+        S.y      = 0;
+        S.height = 2 * D.height;
+        bp.dst      = to_dev(D, D.pixels);
+        bp.src      = to_dev(S, S.pixels);
+        bp.two_pass = 1;
+        bp.force_clamp = 0;
+    } else {
+        // bilinear at NDC centres over the ROI; the chain's images are never
+        // crops (windows are zeroed per level), so WrapClamp even though a
+        // band's data window is smaller than the level
+        b2r_image D = *dst;
+        D.pixels = (unsigned char*)dst->pixels
+                   + (long long)(roi.ybegin - dst->y) * dst->ystride
+                   + (long long)(roi.xbegin - dst->x) * dst->xstride;
+        D.x      = roi.xbegin;
+        D.y      = roi.ybegin;
+        D.width  = roi.xend - roi.xbegin;
+        D.height = roi.yend - roi.ybegin;
+        bp.dst      = to_dev(D, D.pixels);
+        bp.src      = to_dev(*src, src->pixels);
+        bp.two_pass = 0;
+        bp.force_clamp = 1;
+    }
+    (void)nch;
+    launch_box_downsample(bp, stream);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
+        return B2R_ERR_CUDA;
+    }
+    return B2R_OK;
 }

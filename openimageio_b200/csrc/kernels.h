@@ -138,6 +138,8 @@ launch_resample(const ResampleParams& p, int chbegin, int chend, void* stream);
 struct BoxParams {
     DevImage dst, src;
     int two_pass;  // 1: exact 2x2 average path (:260-300); 0: bilinear NDC
+    int force_clamp;  // bilinear: WrapClamp even if src's data window is a crop
+                      // (a row band of an uncropped level)
 };
 void
 launch_box_downsample(const BoxParams& p, void* stream);

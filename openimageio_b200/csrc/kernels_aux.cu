@@ -272,7 +272,8 @@ box_bilinear_kernel(BoxParams p)
     const float* q[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        q[k] = (const float*)src_px(S, xt + (k & 1), yt + (k >> 1), !src_is_crop);
+        q[k] = (const float*)src_px(S, xt + (k & 1), yt + (k >> 1),
+                                    p.force_clamp || !src_is_crop);
     float* d = (float*)((unsigned char*)p.dst.pixels
                         + (long long)(y - p.dst.y) * p.dst.ystride
                         + (long long)(x - p.dst.x) * p.dst.xstride);

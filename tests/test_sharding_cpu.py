@@ -134,3 +134,69 @@ def test_source_rows_with_overscan_and_crop(oiio, oracle):
                           roi=(0, dw, band.ybegin, band.yend))
             assert np.array_equal(out[band.ybegin:band.yend],
                                   ref[band.ybegin:band.yend]), (sx, i)
+
+
+_MIP_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import oracle_py, synth
+from openimageio_b200 import mipdist
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+
+def level_fn(dst_t, b0, sw, sh, src_t, r0, w, h, filt):
+    d, s = dst_t.numpy(), src_t.numpy()
+    if filt == "box":
+        assert 2 * sw == w and r0 == 2 * b0          # aligned 2x2 case only here
+        oracle_py.resize_block(oracle_py.Img(d), oracle_py.Img(s))
+    else:
+        oracle_py.resize(oracle_py.Img(d, 0, b0, (0, 0, sw, sh)),
+                         oracle_py.Img(s, 0, r0, (0, 0, w, h)), filt,
+                         roi=(0, sw, b0, b0 + d.shape[0]))
+
+def tail_fn(full_t, filt):
+    return [torch.from_numpy(a) for a in oracle_py.mip_chain(full_t.numpy(), filt)]
+
+ok = True
+for (W, H, filt) in [(96, 160, "lanczos3"), (64, 128, "box"), (80, 144, "triangle")]:
+    lvl0 = synth.image(W, H, 3, np.float32, seed=9)            # same on every rank
+    y0, y1 = mipdist.split_rows(H, world, rank)
+    chain = mipdist.DistributedMipChain(torch.from_numpy(lvl0[y0:y1].copy()), W, H, filt,
+                                        level_fn=level_fn, tail_fn=tail_fn,
+                                        min_band_rows=4)
+    ref = [lvl0] + oracle_py.mip_chain(lvl0, filt)
+    assert chain.nlevels == len(ref), (chain.nlevels, len(ref))
+    nb = len(chain.bands)
+    assert nb >= 3, nb                                        # really ran banded levels
+    for k in range(1, nb):
+        full = chain.gather_level(k)
+        if rank == 0:
+            # a banded level is computed from the SAME previous level as the
+            # reference chain, band by band: identical arithmetic
+            assert np.array_equal(full.numpy(), ref[k]), (filt, k)
+    if rank == 0:
+        for i, t in enumerate(chain.tail):
+            assert np.array_equal(t.numpy(), ref[nb + i]), (filt, nb + i)
+    if filt != "box":
+        assert chain.halo_bytes > 0                           # halos did travel
+if rank == 0:
+    print("OK")
+dist.destroy_process_group()
+'''
+
+
+def test_distributed_mip_chain_gloo(tmp_path):
+    """The banded MIP chain's halo exchange and gather-to-rank-0 logic with
+    the oracle as the compute step, world_size 2 over gloo."""
+    import subprocess
+    w = tmp_path / "mipworker.py"
+    w.write_text(_MIP_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+         "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+         "29612", str(w), ROOT],
+        capture_output=True, text=True, timeout=900, env=env)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "OK" in out.stdout
