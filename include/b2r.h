@@ -54,7 +54,7 @@ enum b2r_error {
     B2R_OK                = 0,
     B2R_ERR_INVALID       = 1, /* bad argument / uninitialized image */
     B2R_ERR_FILTER        = 2, /* Filter "..." not recognized */
-    B2R_ERR_TYPES         = 3, /* (dst,src) pixel type pair not on the path */
+    B2R_ERR_TYPES         = 3, /* pixel type outside uint8/uint16/half/float */
     B2R_ERR_NO_DEVICE     = 4, /* no usable CUDA device: there is no fallback */
     B2R_ERR_CUDA          = 5, /* CUDA runtime error (message has details) */
     B2R_ERR_UNSUPPORTED   = 6  /* volumes / deep images */
