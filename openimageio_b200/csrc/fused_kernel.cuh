@@ -372,7 +372,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
 // Shared memory carve-up (bytes):
 //   vrows  fused_batch(VK) x FUSED_PITCH_B       V-filtered rows for the H pass
 //   hws    HT x FUSED_HCOLS x 4                  H weights, [tap][column]
-//   fifo   FUSED_FIFO x FUSED_THREADS x 16       per-thread prefetch   (ring)
+//   fifo   FUSED_FIFO x FUSED_THREADS x 4*es     per-thread prefetch   (ring)
 //   ringw  max_band_rows x VKP x 4               ring weights            "
 //   lastr  max_band_dy x 4                       completion rows         "
 template<int ST, int NCH, int VK, int HT>
@@ -437,7 +437,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // ring row: VK (w,w) pairs, padded to float4 loads -- ready-made FFMA2
         // operands
         constexpr int VKP  = (2 * VK + 3) & ~3;
-        constexpr int SLOT = FUSED_THREADS * 16;  // bytes between FIFO rows
+        // FIFO geometry: thread t owns bytes [t*4*es, (t+1)*4*es) of every row
+        // slot (dense, so 8- and 4-byte accesses stay bank-conflict free)
+        constexpr int TB   = 4 * es;             // bytes per thread per row
+        constexpr int SLOT = FUSED_THREADS * TB;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
         unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HCOLS * 4;
@@ -472,7 +475,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         {
             // opaque move: keeps the address in a register (under the register
             // cap the compiler otherwise recomputes it every row)
-            unsigned t = smem_u32(fifo) + tid * 16;
+            unsigned t = smem_u32(fifo) + tid * TB;
             asm volatile("mov.u32 %0, %1;" : "=r"(fifo_s) : "r"(t));
         }
 
@@ -545,8 +548,14 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
             if (!vfetch) {
 #pragma unroll
                 for (int q = 0; q < FUSED_FIFO; ++q)
-                    *reinterpret_cast<uint4*>(fifo + tid * 16 + q * SLOT)
-                        = make_uint4(0u, 0u, 0u, 0u);
+                    if (es == 4)
+                        *reinterpret_cast<uint4*>(fifo + tid * TB + q * SLOT)
+                            = make_uint4(0u, 0u, 0u, 0u);
+                    else if (es == 2)
+                        *reinterpret_cast<uint2*>(fifo + tid * TB + q * SLOT)
+                            = make_uint2(0u, 0u);
+                    else
+                        *reinterpret_cast<unsigned*>(fifo + tid * TB + q * SLOT) = 0u;
             }
 #pragma unroll
             for (int q = 0; q < FUSED_FIFO; ++q)

@@ -275,7 +275,7 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
     if (p.vk > 0) {
         f += (size_t)max_band_rows * ((2 * p.vk + 3) & ~3);
         f += (size_t)((max_band_dy + 3) & ~3);
-        f += (size_t)FUSED_FIFO * FUSED_THREADS * 4;
+        f += (size_t)FUSED_FIFO * FUSED_THREADS * basetype_size(p.srctype);  // 4*es bytes per thread
     }
     return f * sizeof(float);
 }
