@@ -15,8 +15,10 @@ pick_ht(int ht)
 {
     switch (ht) {
     case 4: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 4>;
+    case 6: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 6>;
     case 8: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 8>;
-    case 12: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 12>;
+    case 10: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 10>;
+    case 14: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 14>;
     case 16: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 16>;
     }
     return nullptr;

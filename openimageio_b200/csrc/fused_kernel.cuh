@@ -176,18 +176,18 @@ cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// V rows of RGBA pixels are stored even/odd planar: pixel q of the strip goes
-// to plane (q & 1), index q >> 1; the odd plane starts 4 slots past a multiple
-// of 8 so the two planes sit in different 16-byte bank groups.  A quarter-warp
-// of the H pass reads pixels c, c+2, ... (2:1 downsample: one plane,
-// consecutive slots) or c, c+1, ... (1:1 / upsample: the planes interleave
-// bank groups 0,4,1,5,...): both conflict-free.  And a thread's taps become
-// base + immediate: even taps from one plane, odd taps from the other.
-constexpr int FUSED_PLANE_B = (FUSED_THREADS / 2 + 4) * 16;  // odd-plane offset
+// V rows are parked as float4 pixels in four planes by (pixel index mod 4);
+// plane p starts 66 slots (2 mod 8) after plane p-1, so planes sit in
+// different 16-byte bank groups.  The H pass handles two adjacent dst columns
+// per thread, i.e. a quarter-warp reads pixels c, c+4, c+8, ... (2:1
+// downsample: one plane, consecutive slots) or c, c+2, ... / c, c+1, ...
+// (milder ratios: the planes interleave bank groups) -- conflict free -- and a
+// thread's taps are base[j & 3] + immediate.
+constexpr int FUSED_PLANE_SLOTS = FUSED_THREADS / 4 + 2;
 __device__ __forceinline__ int
 planar_byte(int q)
 {
-    return (q >> 1) * 16 + (q & 1) * FUSED_PLANE_B;
+    return ((q >> 2) + (q & 3) * FUSED_PLANE_SLOTS) * 16;
 }
 
 // Blackwell packed FP32: one FFMA2 instruction does two fused multiply-adds
@@ -210,41 +210,48 @@ fma4(float4& a, float w, const float4& v)
 // V row: RGBA -> one planar float4; RGB -> scattered into RGBX planar pixels
 // (elements straddle pixels); 1-2 channels -> flat floats.
 template<int NCH> struct VPark {
-    int off[NCH == 3 ? 4 : 1];
+    int off[NCH == 4 ? 1 : 4];
     __device__ __forceinline__ void init(int e0, int v)
     {
         if (NCH == 4) {
             off[0] = planar_byte(v);
-        } else if (NCH == 3) {
-            const int px0 = e0 / 3;
+        } else {
+            const int px0 = e0 / NCH;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int E  = e0 + 4 * v + k;
-                int px = E / 3;
-                off[NCH == 3 ? k : 0] = planar_byte(px - px0) + (E - 3 * px) * 4;
+                int px = E / NCH;
+                off[NCH == 4 ? 0 : k] = planar_byte(px - px0) + (E - NCH * px) * 4;
             }
-        } else {
-            off[0] = v * 16;
         }
     }
     __device__ __forceinline__ void store(unsigned char* row, const float4& a) const
     {
-        if (NCH == 3) {
-            *reinterpret_cast<float*>(row + off[0])               = a.x;
-            *reinterpret_cast<float*>(row + off[NCH == 3 ? 1 : 0]) = a.y;
-            *reinterpret_cast<float*>(row + off[NCH == 3 ? 2 : 0]) = a.z;
-            *reinterpret_cast<float*>(row + off[NCH == 3 ? 3 : 0]) = a.w;
-        } else {
+        if (NCH == 4) {
             *reinterpret_cast<float4*>(row + off[0]) = a;
+        } else {
+            *reinterpret_cast<float*>(row + off[0])                  = a.x;
+            *reinterpret_cast<float*>(row + off[NCH == 4 ? 0 : 1]) = a.y;
+            *reinterpret_cast<float*>(row + off[NCH == 4 ? 0 : 2]) = a.z;
+            *reinterpret_cast<float*>(row + off[NCH == 4 ? 0 : 3]) = a.w;
         }
     }
 };
 
 // ---- H pass over `nb` buffered rows; dst rows dyb .. dyb+nb-1 of the ROI ---
-// hbA / hbB are BYTE offsets of tap 0 / tap 1 in this thread's first V row
-// (row hr).  The row pitch is a compile-time constant so every LDS below is
-// base register + immediate.
-constexpr int FUSED_PITCH_B = FUSED_THREADS * 16 + 128;  // bytes per V row
+// The row pitch is a compile-time constant so every LDS of the H pass is base
+// register + immediate.
+constexpr int FUSED_PITCH_B = 4 * FUSED_PLANE_SLOTS * 16;  // bytes per V row
+constexpr int FUSED_HPAIRS  = FUSED_HCOLS / 2;             // column pairs per strip
+constexpr int FUSED_HROWG_MAX = FUSED_THREADS / FUSED_HPAIRS;  // row groups (4)
+// row groups used for a batch of BATCH rows: a divisor of BATCH so no thread
+// filters rows that do not exist (6 rows -> 3 groups x 2 rows, a quarter of the
+// threads sit the H pass out; 8 rows -> 4 groups x 2 rows)
+__host__ __device__ constexpr int
+fused_hrowg(int batch)
+{
+    return batch % FUSED_HROWG_MAX == 0 ? FUSED_HROWG_MAX : 3;
+}
 
 __device__ __forceinline__ bool
 any_nonfinite(float a, float b, float c, float d)
@@ -285,85 +292,63 @@ store_pixel(const FusedParams& p, unsigned char* dp, int des, const float (&a)[N
     }
 }
 
-// The thread's rows of the batch (hr, hr+rstep, ...) are filtered
-// interleaved, tap by tap: independent LDS -> FFMA chains hide the shared
-// memory latency that a row-at-a-time loop exposes.
+// Two adjacent dst columns (A, B) per thread from one shared window of HT
+// source pixels; the thread's rows of the batch (hr, hr+4, ...) are filtered
+// interleaved, tap by tap, so independent LDS -> FFMA2 chains hide the
+// shared-memory latency.  hb[] are BYTE offsets of window taps 0..3 in this
+// thread's first V row (row hr); tap j is hb[j & 3] + (j >> 2) * 16, i.e. base
+// register + immediate.  hws points at this pair's (wA, wB) weights:
+// hws[j * FUSED_HPAIRS] for tap j (staged once per CTA, lane == pair).
 template<int NCH, int HT, int BATCH>
 __device__ __forceinline__ void
 fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
-            int dxg, bool col_active, int hbA, int hbB, const float* hws, int hr)
+            int dxA, bool pair_active, bool has_b, const int (&hb)[4],
+            const float2* hws, int hr)
 {
-    if (!col_active)
+    if (!pair_active)
         return;
     const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
-    constexpr int rstep = FUSED_THREADS / FUSED_HCOLS;
-    constexpr int NR    = (BATCH + rstep - 1) / rstep;  // rows per thread
-    // RGB rows are stored padded to RGBX (the V pass scatters its elements),
-    // so 3- and 4-channel images share the float4 / FFMA2 path
-    constexpr bool PADDED = (NCH >= 3);
-    constexpr int NA      = PADDED ? 4 : NCH;
-    // this column's HT weights: staged once per CTA in shared memory (lane ==
-    // column, conflict-free), re-read per call so they do not occupy
-    // registers across the V pass
-    float hwt[HT];
-#pragma unroll
-    for (int i = 0; i < HT; ++i)
-        hwt[i] = hws[i * FUSED_HCOLS];
-    float a[NR][NA];
+    constexpr int ROWG = fused_hrowg(BATCH);
+    constexpr int NR   = (BATCH + ROWG - 1) / ROWG;  // rows per thread
+    float4 aA[NR], aB[NR];
 #pragma unroll
     for (int k = 0; k < NR; ++k)
+        aA[k] = aB[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int c = 0; c < NA; ++c)
-            a[k][c] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < HT; ++i) {
+    for (int j = 0; j < HT; ++j) {
+        const float2 w   = hws[j * FUSED_HPAIRS];
+        const float2 wwA = make_float2(w.x, w.x), wwB = make_float2(w.y, w.y);
 #pragma unroll
         for (int k = 0; k < NR; ++k) {
             // rows past nb hold stale data from an earlier batch: computed
-            // and discarded.  Tap i: planar float4 rows take even taps off
-            // hbA and odd taps off hbB; flat rows (1-2 channels) are NCH*4
-            // bytes per tap.
-            const unsigned char* t
-                = vrows + k * rstep * FUSED_PITCH_B
-                  + (PADDED ? (((i & 1) ? hbB : hbA) + (i >> 1) * 16)
-                            : (hbA + i * NCH * 4));
-            if (PADDED) {
-                const float4 v  = *reinterpret_cast<const float4*>(t);
-                const float2 ww = make_float2(hwt[i], hwt[i]);
-                float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
-                                       make_float2(a[k][0], a[k][1]));
-                float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
-                                       make_float2(a[k][2], a[k][NA - 1]));
-                a[k][0]      = lo.x;
-                a[k][1]      = lo.y;
-                a[k][2]      = hi.x;
-                a[k][NA - 1] = hi.y;
-            } else {
-                const float* v = reinterpret_cast<const float*>(t);
-#pragma unroll
-                for (int c = 0; c < NCH; ++c)
-                    a[k][c] = fmaf(hwt[i], v[c], a[k][c]);
-            }
+            // and discarded
+            const float4 v = *reinterpret_cast<const float4*>(
+                vrows + k * ROWG * FUSED_PITCH_B + hb[j & 3] + (j >> 2) * 16);
+            fma4(aA[k], wwA, v);
+            fma4(aB[k], wwB, v);
         }
     }
     unsigned char* dp = p.dst + (long long)(dyb + hr) * p.dst_ystride
-                        + (long long)dxg * (NCH * des);
+                        + (long long)dxA * (NCH * des);
     bool bad = false;
 #pragma unroll
     for (int k = 0; k < NR; ++k) {
-        if (hr + k * rstep < nb) {
-            float t = 0.0f;
+        if (hr + k * ROWG < nb) {
+            const float ca[4] = { aA[k].x, aA[k].y, aA[k].z, aA[k].w };
+            const float cb[4] = { aB[k].x, aB[k].y, aB[k].z, aB[k].w };
+            float t = 0.0f, oa[NCH], ob[NCH];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                t += a[k][c];  // Inf/NaN in any channel survives the sum
+            for (int c = 0; c < NCH; ++c) {
+                oa[c] = ca[c];
+                ob[c] = cb[c];
+                t += ca[c] + cb[c];  // Inf/NaN in any channel survives the sum
+            }
             bad |= !(fabsf(t) <= 3.402823466e+38f);
-            float o[NCH];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c)
-                o[c] = a[k][c];
-            store_pixel<NCH>(p, dp, des, o);
+            store_pixel<NCH>(p, dp, des, oa);
+            if (has_b)
+                store_pixel<NCH>(p, dp + NCH * des, des, ob);
         }
-        dp += (long long)rstep * p.dst_ystride;
+        dp += (long long)ROWG * p.dst_ystride;
     }
     if (p.check_nonfinite && bad)
         *p.nonfinite_flag = 1;
@@ -371,7 +356,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
 
 // Shared memory carve-up (bytes):
 //   vrows  fused_batch(VK) x FUSED_PITCH_B       V-filtered rows for the H pass
-//   hws    HT x FUSED_HCOLS x 4                  H weights, [tap][column]
+//   hws    HT x FUSED_HPAIRS x 8                 H weights (wA,wB), [tap][pair]
 //   fifo   FUSED_FIFO x FUSED_THREADS x 4*es     per-thread prefetch   (ring)
 //   ringw  max_band_rows x VKP x 4               ring weights            "
 //   lastr  max_band_dy x 4                       completion rows         "
@@ -389,30 +374,26 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const Strip strip = p.strips[blockIdx.x];
     const Band band   = p.bands[blockIdx.y];
 
-    // ---- H-pass per-thread constants: this thread's dst column ----------
-    const int hc          = tid % FUSED_HCOLS;
-    const int hr          = tid / FUSED_HCOLS;
-    const bool col_active = hc < strip.ndx;
-    const int dxg         = strip.dx0 + hc;
-    int hbA = 0, hbB = 0;  // byte offsets of tap 0 / tap 1 in this thread's row
-    float* hws_all = reinterpret_cast<float*>(smem_raw + BATCH * FUSED_PITCH_B);
-    const float* hws = hws_all + hc;
+    // ---- H-pass per-thread constants: this thread's pair of dst columns --
+    const int hp           = tid % FUSED_HPAIRS;
+    const int hr           = tid / FUSED_HPAIRS;
+    const bool pair_active = 2 * hp < strip.ndx && hr < fused_hrowg(BATCH);
+    const bool has_b       = 2 * hp + 1 < strip.ndx;
+    const int dxA          = strip.dx0 + 2 * hp;
+    int hb[4] = { 0, 0, 0, 0 };  // byte offsets of window taps 0..3 (row hr)
+    float2* hws_all = reinterpret_cast<float2*>(smem_raw + BATCH * FUSED_PITCH_B);
+    const float2* hws = hws_all + hp;
     {
-        int f = col_active ? p.hfirst[dxg] : 0;
-        if (hr == 0) {
+        const int gp = (strip.dx0 >> 1) + hp;  // pair index in the ROI
+        for (int j = hr; j < HT; j += FUSED_HROWG_MAX)
+            hws_all[j * FUSED_HPAIRS + hp]
+                = (2 * hp < strip.ndx) ? reinterpret_cast<const float2*>(p.hw)[(size_t)gp * HT + j]
+                              : make_float2(0.f, 0.f);
+        if (pair_active) {
+            const int q = p.hfirst[gp] - strip.e0 / NCH;  // window start in the strip
 #pragma unroll
-            for (int i = 0; i < HT; ++i)
-                hws_all[i * FUSED_HCOLS + hc]
-                    = col_active ? p.hw[(size_t)dxg * HT + i] : 0.0f;
-        }
-        if (col_active) {
-            if (NCH >= 3) {
-                int q = f - strip.e0 / NCH;  // pixel index within the strip
-                hbA   = planar_byte(q) + hr * pitch_b;
-                hbB   = planar_byte(q + 1) + hr * pitch_b;
-            } else {
-                hbA = (f * NCH - strip.e0) * 4 + hr * pitch_b;
-            }
+            for (int k = 0; k < 4; ++k)
+                hb[k] = planar_byte(q + k) + hr * pitch_b;
         }
     }
 
@@ -424,8 +405,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     // where this thread parks its 4 V-filtered elements in a V row
     VPark<NCH> park;
     park.init(strip.e0, tid);
-    if (NCH == 3) {
-        // RGBX rows: the X lane is never written, it must read as zero
+    if (NCH < 4) {
+        // padded rows: the unused lanes are never written, they must read as zero
         for (int i = tid; i < BATCH * (FUSED_PITCH_B / 16); i += FUSED_THREADS)
             reinterpret_cast<uint4*>(vrows)[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
@@ -443,7 +424,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         constexpr int SLOT = FUSED_THREADS * TB;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
-        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HCOLS * 4;
+        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HPAIRS * 8;
         float* ringw = reinterpret_cast<float*>(fifo + FUSED_FIFO * SLOT);
         int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
 
@@ -534,8 +515,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         auto flush_if_full = [&](int dy_done) {
             if (nb + VK > BATCH || dy_done >= dy_end) {
                 __syncthreads();
-                fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy_done - nb, dxg, col_active,
-                                            hbA, hbB, hws, hr);
+                fused_hpass<NCH, HT, BATCH>(p, vrows, nb, dy_done - nb, dxA, pair_active,
+                                            has_b, hb, hws, hr);
                 __syncthreads();
                 nb = 0;
             }
@@ -654,8 +635,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                 }
             }
             __syncthreads();
-            fused_hpass<NCH, HT, BATCH>(p, vrows, nrows, dyb, dxg, col_active, hbA,
-                                        hbB, hws, hr);
+            fused_hpass<NCH, HT, BATCH>(p, vrows, nrows, dyb, dxA, pair_active, has_b,
+                                        hb, hws, hr);
             __syncthreads();
         }
     }

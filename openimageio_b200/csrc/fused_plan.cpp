@@ -11,7 +11,7 @@ namespace b2r {
 static int
 round_taps(int n)
 {
-    for (int t : { 4, 8, 12, 16 })
+    for (int t : { 4, 6, 8, 10, 14, 16 })
         if (n <= t)
             return t;
     return 0;
@@ -37,43 +37,69 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     P.interior_zero = gx.interior_zero || gy.interior_zero;
 
     // ---------------- H tables --------------------------------------------
-    P.ht = round_taps(std::max(1, gx.maxcount));
+    // The H pass computes TWO adjacent dst columns per thread from one shared
+    // window of source pixels (the taps of neighbouring columns overlap: 14
+    // loads instead of 24 for a 2:1 lanczos3).  Per pair: the first source
+    // pixel of the window and, per window tap, the weight of column A and of
+    // column B (B's taps shifted by first[B]-first[A], zero where they do not
+    // reach).
+    const int W = gx.n, H = gy.n;
+    std::vector<int32_t> cfirst(W);
+    for (int k = 0; k < W; ++k) {
+        cfirst[k] = gx.count[k] > 0 ? gx.first[k] : (k > 0 ? cfirst[k - 1] : 0);
+        if (k > 0 && cfirst[k] < cfirst[k - 1])
+            return false;  // not monotone: leave it to the exact kernel
+    }
+    const int npairs = (W + 1) / 2;
+    int window = 1;
+    for (int pr = 0; pr < npairs; ++pr) {
+        int a = 2 * pr, bcol = a + 1;
+        int span = std::max(1, gx.count[a]);
+        if (bcol < W)
+            span = std::max(span, cfirst[bcol] - cfirst[a] + std::max(1, gx.count[bcol]));
+        window = std::max(window, span);
+    }
+    P.ht = round_taps(window);
     if (!P.ht)
         return false;
-    const int W = gx.n, H = gy.n;
-    P.hfirst.resize(W);
-    P.hw.assign(size_t(W) * P.ht, 0.0f);
-    for (int k = 0; k < W; ++k) {
-        if (gx.count[k] > 0) {
-            P.hfirst[k] = gx.first[k];
-            for (int i = 0; i < gx.count[k]; ++i)
-                P.hw[size_t(k) * P.ht + i] = gx.w[gx.woff[k] + i];
-        } else {
-            P.hfirst[k] = k > 0 ? P.hfirst[k - 1] : 0;
+    P.hfirst.resize(npairs);
+    P.hw.assign(size_t(npairs) * P.ht * 2, 0.0f);
+    for (int pr = 0; pr < npairs; ++pr) {
+        int a = 2 * pr, bcol = a + 1;
+        P.hfirst[pr] = cfirst[a];
+        float* w     = &P.hw[size_t(pr) * P.ht * 2];
+        for (int i = 0; i < gx.count[a]; ++i)
+            w[2 * i] = gx.w[gx.woff[a] + i];
+        if (bcol < W) {
+            int s = cfirst[bcol] - cfirst[a];
+            for (int i = 0; i < gx.count[bcol]; ++i)
+                w[2 * (s + i) + 1] = gx.w[gx.woff[bcol] + i];
         }
-        if (k > 0 && P.hfirst[k] < P.hfirst[k - 1])
-            return false;  // not monotone: leave it to the exact kernel
     }
 
     // ---------------- column strips ---------------------------------------
+    // V rows are parked as float4 pixels (1-3 channel rows padded): a row
+    // holds FUSED_THREADS pixels, and a strip stages <= FUSED_THREADS
+    // four-element groups.  Strips hold an even number of columns (pairs).
     for (int dx0 = 0; dx0 < W;) {
         Strip s;
         s.dx0  = dx0;
-        s.e0   = (P.hfirst[dx0] * nch) & ~3;
+        s.e0   = (cfirst[dx0] * nch) & ~3;
         s.ndx  = 0;
         s.nvec = 0;
+        const int px0 = s.e0 / nch;
         while (dx0 + s.ndx < W && s.ndx < FUSED_HCOLS) {
-            int eend = (P.hfirst[dx0 + s.ndx] + P.ht) * nch;
-            int nvec = (eend - s.e0 + 3) / 4;
-            // RGB rows are parked padded to RGBX: a V row holds 256 pixels
-            if (nvec > FUSED_THREADS
-                || (nch == 3 && (4 * nvec + 2) / 3 + 1 > FUSED_THREADS))
+            // take columns two at a time: the pair's window end bounds both
+            int pr   = (dx0 + s.ndx) / 2;
+            int pend = P.hfirst[pr] + P.ht;          // one past the last px read
+            int nvec = (pend * nch - s.e0 + 3) / 4;
+            if (nvec > FUSED_THREADS || pend - px0 > FUSED_THREADS)
                 break;
             s.nvec = nvec;
-            ++s.ndx;
+            s.ndx += std::min(2, W - (dx0 + s.ndx));
         }
         if (s.ndx == 0)
-            return false;  // one column's footprint does not fit a strip
+            return false;  // one pair's footprint does not fit a strip
         P.max_nvec = std::max(P.max_nvec, s.nvec);
         P.strips.push_back(s);
         dx0 += s.ndx;

@@ -55,7 +55,7 @@ launch_resize_exact(const ExactParams& p, void* stream);
 // shared memory.  One CTA = one column strip x one row band of the dst ROI.
 struct Strip {
     int dx0;    // first dst column (index into the ROI, 0-based)
-    int ndx;    // columns in this strip (<= FUSED_HCOLS)
+    int ndx;    // columns in this strip (<= FUSED_HCOLS; even except the last)
     int e0;     // first flat source element (px*nch + c) staged, multiple of 4
     int nvec;   // number of 4-element groups staged (<= FUSED_THREADS)
 };
@@ -93,10 +93,11 @@ struct FusedParams {
     const Strip* strips;
     const Band* bands;
 
-    // H pass (gather, HT taps per dst column, zero padded)
-    const int* hfirst;  // [roi_w] first source pixel
-    const float* hw;    // [roi_w * HT]
-    int ht;             // taps in the table (== template HT)
+    // H pass: two adjacent dst columns (A, B) share a window of HT source
+    // pixels; per pair the window start and per tap the weights (wA, wB)
+    const int* hfirst;  // [ceil(roi_w/2)] first source pixel of the window
+    const float* hw;    // [ceil(roi_w/2) * HT * 2]
+    int ht;             // window taps (== template HT)
 
     // V pass, ring mode (vk > 0): per band, per source row, K slot weights
     int vk;

@@ -11,8 +11,8 @@ collective.  Once bands get shorter than the halo the remaining levels are
 gathered onto rank 0 and finished there with the single-GPU chain.
 
 The compute step and the row-span arithmetic are injectable so the exchange
-logic is testable on CPU (gloo) with the oracle standing in for the kernels
-(tests/test_sharding_cpu.py); the defaults call the C ABI (`b2r_mip_level`,
+logic is testable on CPU (gloo) with a CPU stand-in for the kernels supplied
+by the test (tests/test_sharding_cpu.py); the defaults call the C ABI (`b2r_mip_level`,
 `b2r_source_rows`).
 """
 from __future__ import annotations
