@@ -366,7 +366,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char* vrows  = smem_raw;
-    constexpr int BATCH   = (VK == 6) ? 6 : 8;  // == fused_batch(VK), kernels.h
+    constexpr int BATCH   = (VK == 6) ? 12 : 8;  // == fused_batch(VK), kernels.h
     constexpr int pitch_b = FUSED_PITCH_B;
     constexpr int es      = SrcTraits<ST>::es;
 
@@ -415,9 +415,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     int nb              = 0;
 
     if constexpr (VK > 0) {
-        // ring row: VK (w,w) pairs, padded to float4 loads -- ready-made FFMA2
-        // operands
-        constexpr int VKP  = (2 * VK + 3) & ~3;
+        // ring row: VK weights padded to float4 loads (duplicated into FFMA2
+        // operand pairs in registers: a MOV is cheaper than a shared-memory
+        // wavefront here)
+        constexpr int VKP  = (VK + 3) & ~3;
         // FIFO geometry: thread t owns bytes [t*4*es, (t+1)*4*es) of every row
         // slot (dense, so 8- and 4-byte accesses stay bank-conflict free)
         constexpr int TB   = 4 * es;             // bytes per thread per row
@@ -491,12 +492,14 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // one source row: scatter it into the VK open destination rows
         auto accumulate = [&](const uint4& raw, const float4* wr) {
             const float4 v = convert_raw4<ST>(raw);
-            float2 w[VKP / 2];
+            float w[VKP];
 #pragma unroll
             for (int k = 0; k < VKP / 4; ++k) {
                 float4 t     = wr[k];
-                w[2 * k]     = make_float2(t.x, t.y);
-                w[2 * k + 1] = make_float2(t.z, t.w);
+                w[4 * k]     = t.x;
+                w[4 * k + 1] = t.y;
+                w[4 * k + 2] = t.z;
+                w[4 * k + 3] = t.w;
             }
 #pragma unroll
             for (int k = 0; k < VK; ++k)

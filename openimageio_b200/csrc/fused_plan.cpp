@@ -149,8 +149,8 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     const int min_rows = 8;
     nbands             = std::min(nbands, std::max(1, H / min_rows));
     // ring weights live in shared memory: keep a band's source rows bounded
-    // ring row = vk duplicated (w,w) pairs padded to float4 loads (FFMA2 operands)
-    const int vkp           = (2 * vk + 3) & ~3;
+    // ring row = vk weights padded to float4 loads
+    const int vkp           = (vk + 3) & ~3;
     const int max_rows_smem = use_ring ? (24 * 1024 / (4 * std::max(4, vkp))) : INT_MAX;
     for (;;) {
         bool ok = true;
@@ -199,8 +199,8 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
                 int slot = (k - b.dy0) % vk;
                 for (int j = 0; j < gy.count[k]; ++j) {
                     int r = gy.first[k] + j;
-                    float* row = &P.vring[(size_t(b.woff) + (r - b.r0)) * vkp];
-                    row[2 * slot] = row[2 * slot + 1] = gy.w[gy.woff[k] + j];
+                    P.vring[(size_t(b.woff) + (r - b.r0)) * vkp + slot]
+                        = gy.w[gy.woff[k] + j];
                 }
             }
         }

@@ -273,7 +273,7 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
     size_t f = (size_t)fused_batch(p.vk) * (FUSED_THREADS * 4 + 32);  // FUSED_PITCH_B (4224 B)
     f += (size_t)p.ht * FUSED_HCOLS;  // H weights
     if (p.vk > 0) {
-        f += (size_t)max_band_rows * ((2 * p.vk + 3) & ~3);
+        f += (size_t)max_band_rows * ((p.vk + 3) & ~3);
         f += (size_t)((max_band_dy + 3) & ~3);
         f += (size_t)FUSED_FIFO * FUSED_THREADS * basetype_size(p.srctype);  // 4*es bytes per thread
     }

@@ -74,7 +74,7 @@ constexpr int FUSED_HCOLS   = 128;  // dst columns per strip (H-pass threads per
 constexpr int
 fused_batch(int vk)
 {
-    return vk == 6 ? 6 : 8;
+    return vk == 6 ? 12 : 8;
 }
 constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
 
