@@ -412,6 +412,32 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     return B2R_OK;
 }
 
+// Ring of redo flags per device.  A call gets a slot and a fresh, non-zero
+// epoch: the fused kernel writes the epoch into the slot when it sees a
+// non-finite output, the gated exact kernel runs only if the slot holds that
+// epoch.  Stale values of earlier calls never match, so nothing is cleared and
+// no memset node is needed per call.
+int*
+next_flag(int dev, int* epoch)
+{
+    struct Ring {
+        int* base = nullptr;
+        unsigned next = 0;
+    };
+    static Ring rings[64];
+    static std::mutex m;
+    std::lock_guard<std::mutex> lock(m);
+    Ring& r = rings[dev & 63];
+    if (!r.base) {
+        if (cudaMalloc((void**)&r.base, 256 * sizeof(int)) != cudaSuccess)
+            return nullptr;
+        cudaMemset(r.base, 0, 256 * sizeof(int));
+    }
+    unsigned n = r.next++;
+    *epoch     = int((n & 0x3fffffffu) + 1);
+    return r.base + (n & 255);
+}
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev)
@@ -679,6 +705,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     int launched = 0;
     int used     = B2R_PATH_EXACT;
     int* flag    = nullptr;
+    int epoch    = 0;
     if (path == B2R_PATH_FUSED && !fused_ok) {
         set_err(err, errlen, "resize: shape is not eligible for the fused kernel");
         if (src_staged)
@@ -725,17 +752,24 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         fp.vfirst          = plan->vfirst;
         fp.vw              = plan->vw;
         if (src_is_fp) {
-            // per-call flag: plans are shared between concurrent calls
-            CUDA_TRY(cudaMallocAsync((void**)&flag, sizeof(int), stream));
-            CUDA_TRY(cudaMemsetAsync(flag, 0, sizeof(int), stream));
-            fp.nonfinite_flag = flag;
+            // per-call flag from a per-device ring (plans are shared between
+            // concurrent calls); the gated exact kernel leaves it cleared, so
+            // no memset node is needed per call
+            flag = next_flag(device, &epoch);
+            if (!flag) {
+                set_err(err, errlen, "CUDA error: cannot allocate the redo flags");
+                return B2R_ERR_CUDA;
+            }
+            fp.nonfinite_flag  = flag;
+            fp.nonfinite_epoch = epoch;
         }
         launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,
                             plan->fp.max_nvec, stream);
         ++launched;
         used = B2R_PATH_FUSED;
         if (src_is_fp) {
-            ep.gate = flag;  // runs only if a non-finite output was seen
+            ep.gate       = flag;  // runs only if a non-finite output was seen
+            ep.gate_value = epoch;
             launch_resize_exact(ep, stream);
             ++launched;
         }
@@ -772,8 +806,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         && (dst_staged || src_staged))
         CUDA_TRY(cudaMemcpyAsync(&redo, flag, sizeof(int),
                                  cudaMemcpyDeviceToHost, stream));
-    if (flag)
-        CUDA_TRY(cudaFreeAsync(flag, stream));
     if (src_staged)
         CUDA_TRY(cudaFreeAsync(src_alloc, stream));
     if (dst_staged)
@@ -785,7 +817,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         report->kernels_launched = launched;
         report->xtaps            = plan->xtaps;
         report->ytaps            = plan->ytaps;
-        report->nonfinite_redo   = redo;
+        report->nonfinite_redo   = (epoch != 0 && redo == epoch) ? 1 : 0;
         if (timed) {
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, ev0, ev1);

@@ -351,7 +351,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
         dp += (long long)ROWG * p.dst_ystride;
     }
     if (p.check_nonfinite && bad)
-        *p.nonfinite_flag = 1;
+        *p.nonfinite_flag = p.nonfinite_epoch;
 }
 
 // Shared memory carve-up (bytes):

@@ -83,7 +83,7 @@ constexpr int EXACT_CH = 4;  // channels per thread
 __global__ void __launch_bounds__(128)
 resize_exact_kernel(ExactParams p)
 {
-    if (p.gate && *p.gate == 0)
+    if (p.gate && *p.gate != p.gate_value)
         return;
     const int roi_w   = p.roi_x1 - p.roi_x0;
     const int roi_h   = p.roi_y1 - p.roi_y0;
@@ -195,7 +195,10 @@ launch_resize_exact(const ExactParams& p, void* stream)
     long long tiles = (long long)((roi_w + 127) / 128) * roi_h;
     // grid-stride: enough CTAs to fill the machine, few enough that a launch
     // gated off by *p.gate == 0 retires in a few microseconds
-    dim3 grid((unsigned)std::min<long long>(tiles, 148 * 16), 1,
+    // a gated launch (redo path) uses a small grid so that the usual case --
+    // flag clear, every CTA exits at once -- costs as little as possible
+    const long long cap = p.gate ? 148 * 2 : 148 * 16;
+    dim3 grid((unsigned)std::min<long long>(tiles, cap), 1,
               (p.nch + EXACT_CH - 1) / EXACT_CH);
     resize_exact_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
 }

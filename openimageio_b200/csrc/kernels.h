@@ -44,8 +44,9 @@ struct ExactParams {
     const float* yfrac;    // [roi_h]
     int nonsep_kind;       // 0 separable, 1 disk, 2 radial-lanczos3
     float filt_w, filt_h;
-    // when not null: run only if *gate != 0 (non-finite redo)
+    // when not null: run only if *gate == gate_value (non-finite redo)
     const int* gate;
+    int gate_value;
 };
 void
 launch_resize_exact(const ExactParams& p, void* stream);
@@ -88,6 +89,7 @@ struct FusedParams {
     int src_vec_ok, dst_vec_ok;  // 4-element vector loads / stores allowed
     int check_nonfinite;         // float/half sources: flag non-finite outputs
     int* nonfinite_flag;
+    int nonfinite_epoch;         // value written to the flag (unique per call)
 
     int nstrips, nbands;
     const Strip* strips;
