@@ -283,6 +283,13 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
     *row1 = hi - src.y;
 }
 
+static bool
+plan_supported(int basetype, int nch, const FusedPlan& fp)
+{
+    return fp.expand ? expand_supported(basetype, nch, fp.ht)
+                     : fused_supported(basetype, nch, fp.vk, fp.ht);
+}
+
 int
 get_plan(int device, const b2r_image& dst, const b2r_image& src,
          const b2r_roi& roi, const Filter2D& filter, int nch, int cta_slots,
@@ -342,7 +349,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
         bool ok = build_axis_gather(gx, tx, &ax) && build_axis_gather(gy, ty, &ay)
                   && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
                                 &plan->fp)
-                  && fused_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht);
+                  && plan_supported(src.basetype, nch, plan->fp);
         if (ok) {
             // the band count was sized for an assumed number of resident CTAs
             // per SM; ask the runtime what this shape really gets and re-plan
@@ -353,14 +360,15 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             q.nch     = nch;
             q.vk      = plan->fp.vk;
             q.ht      = plan->fp.ht;
+            q.vt      = plan->fp.vt;
+            q.expand  = plan->fp.expand ? 1 : 0;
             int per   = fused_ctas_per_sm(q, plan->fp.max_band_rows,
                                           plan->fp.max_band_dy, plan->fp.max_nvec);
             int sms   = cta_slots / 3;
             if (per > 0 && per != 3)
                 ok = plan_fused(ax, ay, nch, src.width, src.height, sms * per,
                                 &plan->fp)
-                     && fused_supported(src.basetype, nch, plan->fp.vk,
-                                        plan->fp.ht);
+                     && plan_supported(src.basetype, nch, plan->fp);
         }
         if (ok) {
             plan->fused = true;
@@ -751,6 +759,14 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         fp.vt              = plan->fp.vt;
         fp.vfirst          = plan->vfirst;
         fp.vw              = plan->vw;
+        fp.expand          = plan->fp.expand ? 1 : 0;
+        fp.ngroups         = plan->fp.ngroups;
+        {
+            // alignment every group of four dst pixels is guaranteed to have
+            const uintptr_t a = (uintptr_t)fp.dst | (uintptr_t)dstd.ystride;
+            fp.dst_align = (a % 16 == 0 && (4 * nch * des) % 16 == 0) ? 16
+                           : (a % 4 == 0 ? 4 : 0);
+        }
         if (src_is_fp) {
             // per-call flag from a per-device ring (plans are shared between
             // concurrent calls); the gated exact kernel leaves it cleared, so

@@ -26,6 +26,151 @@ round_ring(int k)
     return 0;
 }
 
+
+// Gather-mode V tables: per dst row the first source row and vt weights.
+static bool
+build_v_gather(const AxisGather& gy, const std::vector<int>& first, int vt,
+               int src_h, FusedPlan& P)
+{
+    const int H = gy.n;
+    if (vt > src_h)
+        return false;
+    P.vk = 0;
+    P.vt = vt;
+    P.vfirst.resize(H);
+    P.vw.assign(size_t(H) * vt, 0.0f);
+    for (int k = 0; k < H; ++k) {
+        int f = first[k];
+        // keep first+vt inside the image: shift the window up and pad in
+        // front when the run sits at the bottom edge
+        int shift = 0;
+        if (f + vt > src_h)
+            shift = std::min(f, f + vt - src_h);
+        P.vfirst[k] = f - shift;
+        for (int j = 0; j < gy.count[k]; ++j)
+            P.vw[size_t(k) * vt + shift + j] = gy.w[gy.woff[k] + j];
+    }
+    return true;
+}
+
+// Tables for resize_expand_kernel (upsizing in y).  The H pass computes a
+// GROUP of four adjacent dst columns per thread from one shared window of HT
+// source pixels: when upsizing in x too the four footprints nearly coincide
+// (4x mitchell: 4-5 pixels for all four columns).  Strips are up to
+// EXPAND_GROUPS groups wide as long as their source span fits a V row.
+static bool
+plan_expand(const AxisGather& gx, const AxisGather& gy,
+            const std::vector<int32_t>& cfirst, const std::vector<int>& first,
+            int nch, int src_h, int cta_slots, FusedPlan* plan)
+{
+    FusedPlan& P = *plan;
+    const int W = gx.n, H = gy.n;
+    const int vt = gy.maxcount;
+    if (vt < 1 || vt > EXPAND_RING)
+        return false;
+    const int ngroups = (W + 3) / 4;
+    int window = 1;
+    for (int g = 0; g < ngroups; ++g) {
+        int a = 4 * g;
+        for (int k = a; k < std::min(W, a + 4); ++k)
+            window = std::max(window, cfirst[k] - cfirst[a] + std::max(1, gx.count[k]));
+    }
+    int ht = 0;
+    for (int t : { 4, 5, 6, 8 })
+        if (window <= t) {
+            ht = t;
+            break;
+        }
+    if (!ht)
+        return false;
+
+    // ---- strips: greedy to find how many are needed, then balanced -------
+    auto make_strips = [&](int cap, std::vector<Strip>* out, int* max_nvec) {
+        out->clear();
+        *max_nvec = 0;
+        for (int dx0 = 0; dx0 < W;) {
+            Strip s;
+            s.dx0  = dx0;
+            s.e0   = (cfirst[dx0] * nch) & ~3;
+            s.ndx  = 0;
+            s.nvec = 0;
+            const int px0 = s.e0 / nch;
+            while (dx0 + s.ndx < W && s.ndx < cap) {
+                int g    = (dx0 + s.ndx) / 4;
+                int pend = cfirst[4 * g] + ht;  // one past the last px read
+                int nvec = (pend * nch - s.e0 + 3) / 4;
+                if (nvec > FUSED_THREADS || pend - px0 > FUSED_THREADS)
+                    break;
+                s.nvec = nvec;
+                s.ndx += std::min(4, W - (dx0 + s.ndx));
+            }
+            if (s.ndx == 0)
+                return false;
+            *max_nvec = std::max(*max_nvec, s.nvec);
+            out->push_back(s);
+            dx0 += s.ndx;
+        }
+        return true;
+    };
+    std::vector<Strip> greedy, even;
+    int nv_greedy = 0, nv_even = 0;
+    if (!make_strips(4 * EXPAND_GROUPS, &greedy, &nv_greedy))
+        return false;
+    const int n1  = int(greedy.size());
+    const int cap = std::min(4 * EXPAND_GROUPS, ((W + n1 - 1) / n1 + 3) & ~3);
+    if (make_strips(cap, &even, &nv_even) && int(even.size()) <= n1) {
+        P.strips   = even;
+        P.max_nvec = nv_even;
+    } else {
+        P.strips   = greedy;
+        P.max_nvec = nv_greedy;
+    }
+
+    // ---- H tables ----------------------------------------------------------
+    P.expand  = true;
+    P.ngroups = ngroups;
+    P.ht      = ht;
+    P.hfirst.resize(ngroups);
+    P.hw.assign(size_t(ngroups) * ht * 4, 0.0f);
+    for (int g = 0; g < ngroups; ++g) {
+        int a       = 4 * g;
+        P.hfirst[g] = cfirst[a];
+        for (int k = a; k < std::min(W, a + 4); ++k) {
+            int s = cfirst[k] - cfirst[a];
+            for (int i = 0; i < gx.count[k]; ++i)
+                P.hw[(size_t(s + i) * ngroups + g) * 4 + (k - a)] = gx.w[gx.woff[k] + i];
+        }
+    }
+
+    // ---- V tables and bands -------------------------------------------------
+    if (!build_v_gather(gy, first, vt, src_h, P))
+        return false;
+    const int nstrips = int(P.strips.size());
+    int nbands        = std::max(1, cta_slots / std::max(1, nstrips));
+    nbands            = std::min(nbands, std::max(1, H / EXPAND_BATCH));
+    // a band's V weights and row offsets are staged in shared memory
+    const int max_dy = 16 * 1024 / (4 * (vt + 1));
+    nbands           = std::max(nbands, (H + max_dy - 1) / max_dy);
+    P.bands.clear();
+    P.max_band_rows = 0;
+    P.max_band_dy   = 0;
+    for (int b = 0; b < nbands; ++b) {
+        Band bd;
+        bd.dy0 = int((long long)H * b / nbands);
+        int e  = int((long long)H * (b + 1) / nbands);
+        bd.ndy = e - bd.dy0;
+        if (bd.ndy <= 0)
+            continue;
+        bd.r0    = P.vfirst[bd.dy0];
+        bd.nrows = P.vfirst[e - 1] + vt - bd.r0;
+        bd.woff  = 0;
+        P.max_band_dy   = std::max(P.max_band_dy, bd.ndy);
+        P.max_band_rows = std::max(P.max_band_rows, bd.nrows);
+        P.bands.push_back(bd);
+    }
+    return true;
+}
+
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
            int src_h, int cta_slots, FusedPlan* plan)
@@ -36,13 +181,6 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     P            = FusedPlan();
     P.interior_zero = gx.interior_zero || gy.interior_zero;
 
-    // ---------------- H tables --------------------------------------------
-    // The H pass computes TWO adjacent dst columns per thread from one shared
-    // window of source pixels (the taps of neighbouring columns overlap: 14
-    // loads instead of 24 for a 2:1 lanczos3).  Per pair: the first source
-    // pixel of the window and, per window tap, the weight of column A and of
-    // column B (B's taps shifted by first[B]-first[A], zero where they do not
-    // reach).
     const int W = gx.n, H = gy.n;
     std::vector<int32_t> cfirst(W);
     for (int k = 0; k < W; ++k) {
@@ -50,6 +188,57 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         if (k > 0 && cfirst[k] < cfirst[k - 1])
             return false;  // not monotone: leave it to the exact kernel
     }
+    // ---------------- V tables --------------------------------------------
+    std::vector<int> first(H), last(H);
+    for (int k = 0; k < H; ++k) {
+        if (gy.count[k] > 0) {
+            first[k] = gy.first[k];
+            last[k]  = gy.first[k] + gy.count[k] - 1;
+        } else {
+            first[k] = last[k] = k > 0 ? last[k - 1] : 0;
+        }
+        if (k > 0) {
+            if (first[k] < first[k - 1])
+                return false;
+            last[k] = std::max(last[k], last[k - 1]);
+        }
+    }
+    // open rows: how many dst rows are waiting on source rows at once
+    int K = 1;
+    for (int k = 0, lo = 0; k < H; ++k) {
+        while (last[lo] < first[k])
+            ++lo;
+        K = std::max(K, k - lo + 1);
+    }
+    const int vk          = round_ring(K);
+    const long long rows_total = (long long)last[H - 1] - first[0] + 1;
+    const int vt          = gy.maxcount;
+    const bool ring_ok    = vk > 0;
+    const bool gather_ok  = vt >= 1 && vt <= 16;
+    bool use_ring         = ring_ok;
+    if (ring_ok && gather_ok) {
+        // FMA-quads per strip column: ring touches every source row vk times,
+        // gather touches vt rows per dst row (and re-reads them through L1)
+        long long ring_cost   = rows_total * vk;
+        long long gather_cost = (long long)H * vt * 2;
+        use_ring              = ring_cost <= gather_cost;
+    }
+    if (!use_ring && !gather_ok)
+        return false;
+
+    // ---------------- expand variant ---------------------------------------
+    // Upsizing in y (gather mode): wide strips, a group of four dst columns
+    // per H-pass thread, source rows converted to float once per strip.
+    if (!use_ring && plan_expand(gx, gy, cfirst, first, nch, src_h, cta_slots, plan))
+        return true;
+
+    // ---------------- H tables --------------------------------------------
+    // The H pass computes TWO adjacent dst columns per thread from one shared
+    // window of source pixels (the taps of neighbouring columns overlap: 14
+    // loads instead of 24 for a 2:1 lanczos3).  Per pair: the first source
+    // pixel of the window and, per window tap, the weight of column A and of
+    // column B (B's taps shifted by first[B]-first[A], zero where they do not
+    // reach).
     const int npairs = (W + 1) / 2;
     int window = 1;
     for (int pr = 0; pr < npairs; ++pr) {
@@ -104,44 +293,6 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         P.strips.push_back(s);
         dx0 += s.ndx;
     }
-
-    // ---------------- V tables --------------------------------------------
-    std::vector<int> first(H), last(H);
-    for (int k = 0; k < H; ++k) {
-        if (gy.count[k] > 0) {
-            first[k] = gy.first[k];
-            last[k]  = gy.first[k] + gy.count[k] - 1;
-        } else {
-            first[k] = last[k] = k > 0 ? last[k - 1] : 0;
-        }
-        if (k > 0) {
-            if (first[k] < first[k - 1])
-                return false;
-            last[k] = std::max(last[k], last[k - 1]);
-        }
-    }
-    // open rows: how many dst rows are waiting on source rows at once
-    int K = 1;
-    for (int k = 0, lo = 0; k < H; ++k) {
-        while (last[lo] < first[k])
-            ++lo;
-        K = std::max(K, k - lo + 1);
-    }
-    const int vk          = round_ring(K);
-    const long long rows_total = (long long)last[H - 1] - first[0] + 1;
-    const int vt          = gy.maxcount;
-    const bool ring_ok    = vk > 0;
-    const bool gather_ok  = vt >= 1 && vt <= 16;
-    bool use_ring         = ring_ok;
-    if (ring_ok && gather_ok) {
-        // FMA-quads per strip column: ring touches every source row vk times,
-        // gather touches vt rows per dst row (and re-reads them through L1)
-        long long ring_cost   = rows_total * vk;
-        long long gather_cost = (long long)H * vt * 2;
-        use_ring              = ring_cost <= gather_cost;
-    }
-    if (!use_ring && !gather_ok)
-        return false;
 
     // ---------------- row bands -------------------------------------------
     const int nstrips = int(P.strips.size());
@@ -204,24 +355,8 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
                 }
             }
         }
-    } else {
-        P.vk = 0;
-        P.vt = vt;
-        P.vfirst.resize(H);
-        P.vw.assign(size_t(H) * vt, 0.0f);
-        for (int k = 0; k < H; ++k) {
-            int f = first[k];
-            // keep first+vt inside the image: shift the window up and pad in
-            // front when the run sits at the bottom edge
-            int shift = 0;
-            if (f + vt > src_h)
-                shift = std::min(f, f + vt - src_h);
-            P.vfirst[k] = f - shift;
-            for (int j = 0; j < gy.count[k]; ++j)
-                P.vw[size_t(k) * vt + shift + j] = gy.w[gy.woff[k] + j];
-        }
-        if (vt > src_h)
-            return false;
+    } else if (!build_v_gather(gy, first, vt, src_h, P)) {
+        return false;
     }
     (void)src_w;
     return true;

@@ -11,6 +11,8 @@ namespace b2r {
 struct FusedPlan {
     std::vector<Strip> strips;
     std::vector<Band> bands;
+    bool expand = false;  // tables are for resize_expand_kernel
+    int ngroups = 0;      // expand: groups of four dst columns in the ROI
     // H pass
     int ht = 0;
     std::vector<int32_t> hfirst;

@@ -240,17 +240,40 @@ pick_fused(int srctype, int nch, int vk, int ht)
     return table[st][nch - 1](vk, ht);
 }
 
+ExpandKernel expand_lookup_1(int), expand_lookup_2(int), expand_lookup_3(int),
+    expand_lookup_4(int);
+static ExpandKernel
+pick_expand(int srctype, int nch, int ht)
+{
+    if (st_index(srctype) < 0)
+        return nullptr;
+    switch (nch) {
+    case 1: return expand_lookup_1(ht);
+    case 2: return expand_lookup_2(ht);
+    case 3: return expand_lookup_3(ht);
+    case 4: return expand_lookup_4(ht);
+    }
+    return nullptr;
+}
+
 bool
 fused_supported(int srctype, int nch, int vk, int ht)
 {
     return pick_fused(srctype, nch, vk, ht) != nullptr;
 }
 
+bool
+expand_supported(int srctype, int nch, int ht)
+{
+    return pick_expand(srctype, nch, ht) != nullptr;
+}
+
 int
 fused_ctas_per_sm(const FusedParams& p, int max_band_rows, int max_band_dy,
                   int max_nvec)
 {
-    FusedKernel k = pick_fused(p.srctype, p.nch, p.vk, p.ht);
+    const void* k = p.expand ? (const void*)pick_expand(p.srctype, p.nch, p.ht)
+                             : (const void*)pick_fused(p.srctype, p.nch, p.vk, p.ht);
     if (!k)
         return 0;
     size_t smem = fused_smem_bytes(p, max_band_rows, max_band_dy, max_nvec);
@@ -273,6 +296,14 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
                  int max_nvec)
 {
     (void)max_nvec;
+    if (p.expand) {
+        size_t b = (size_t)EXPAND_BATCH * (FUSED_THREADS * 4 + 32) * 4;  // vrows
+        b += (size_t)p.ht * EXPAND_GROUPS * 16;                          // hws
+        b += (size_t)EXPAND_RING * FUSED_THREADS * 16;                   // ring
+        b += (size_t)EXPAND_FIFO * FUSED_THREADS * 4 * basetype_size(p.srctype);
+        b += (size_t)max_band_dy * (p.vt + 1) * 4;                       // vws, vfs
+        return (b + 15) & ~size_t(15);
+    }
     size_t f = (size_t)fused_batch(p.vk) * (FUSED_THREADS * 4 + 32);  // FUSED_PITCH_B (4224 B)
     f += (size_t)p.ht * FUSED_HCOLS;  // H weights
     if (p.vk > 0) {
@@ -287,6 +318,18 @@ void
 launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
                     int max_nvec, void* stream)
 {
+    if (p.expand) {
+        ExpandKernel k = pick_expand(p.srctype, p.nch, p.ht);
+        if (!k || p.nstrips <= 0 || p.nbands <= 0)
+            return;
+        size_t smem = fused_smem_bytes(p, max_band_rows, max_band_dy, max_nvec);
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute((const void*)k,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dim3 grid(p.nstrips, p.nbands, 1);
+        k<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p, max_band_dy);
+        return;
+    }
     FusedKernel k = pick_fused(p.srctype, p.nch, p.vk, p.ht);
     if (!k || p.nstrips <= 0 || p.nbands <= 0)
         return;

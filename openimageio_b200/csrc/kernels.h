@@ -79,6 +79,13 @@ fused_batch(int vk)
 }
 constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
 
+// Expand variant (upsizing in y: the V pass gathers): strips are up to
+// EXPAND_GROUPS groups of four dst columns wide, a group per H-pass thread.
+constexpr int EXPAND_GROUPS = 256;
+constexpr int EXPAND_BATCH  = 8;    // V-filtered rows between the passes
+constexpr int EXPAND_RING   = 8;    // converted source rows kept per thread (>= vt)
+constexpr int EXPAND_FIFO   = 4;    // raw source rows in flight per thread
+
 struct FusedParams {
     const unsigned char* src;  // data-window origin, pixels contiguous in x
     long long src_ystride;
@@ -87,6 +94,8 @@ struct FusedParams {
     long long dst_ystride;
     int dsttype;
     int src_vec_ok, dst_vec_ok;  // 4-element vector loads / stores allowed
+    int expand;                  // 1: resize_expand_kernel tables (groups of 4 columns)
+    int dst_align;               // expand: 16 / 4 / 0 = alignment dst rows guarantee
     int check_nonfinite;         // float/half sources: flag non-finite outputs
     int* nonfinite_flag;
     int nonfinite_epoch;         // value written to the flag (unique per call)
@@ -99,6 +108,8 @@ struct FusedParams {
     // pixels; per pair the window start and per tap the weights (wA, wB)
     const int* hfirst;  // [ceil(roi_w/2)] first source pixel of the window
     const float* hw;    // [ceil(roi_w/2) * HT * 2]
+    // expand: hfirst[ceil(roi_w/4)], hw[(tap * ngroups + group) * 4 + column]
+    int ngroups;
     int ht;             // window taps (== template HT)
 
     // V pass, ring mode (vk > 0): per band, per source row, K slot weights
@@ -113,7 +124,10 @@ struct FusedParams {
 // Returns false when no instantiation matches (srctype, nch, vk, ht).
 bool
 fused_supported(int srctype, int nch, int vk, int ht);
+bool
+expand_supported(int srctype, int nch, int ht);
 typedef void (*FusedKernel)(const FusedParams, int, int);
+typedef void (*ExpandKernel)(const FusedParams, int);
 // resident CTAs per SM for this shape (occupancy query), 0 on error
 int
 fused_ctas_per_sm(const FusedParams& p, int max_band_rows, int max_band_dy,
