@@ -96,7 +96,8 @@ typedef struct b2r_report {
     int32_t path_used;       /* B2R_PATH_EXACT or B2R_PATH_FUSED */
     int32_t kernels_launched;
     int32_t xtaps, ytaps;    /* reference tap counts 2*radi+1, 2*radj+1 */
-    int32_t fused_vmode;     /* ring size K (>0) or 0 = gather */
+    int32_t fused_vmode;     /* ring size K (>0), 0 = gather, -VT = expand kernel
+                                (upsizing in y, VT-row register window) */
     int32_t fused_htaps;
     int64_t h2d_bytes, d2h_bytes;
     float kernel_ms;         /* CUDA-event time of the kernels, host calls only */

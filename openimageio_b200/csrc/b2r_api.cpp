@@ -286,7 +286,7 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
 static bool
 plan_supported(int basetype, int nch, const FusedPlan& fp)
 {
-    return fp.expand ? expand_supported(basetype, nch, fp.ht)
+    return fp.expand ? expand_supported(basetype, nch, fp.vt, fp.ht)
                      : fused_supported(basetype, nch, fp.vk, fp.ht);
 }
 
@@ -761,6 +761,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         fp.vw              = plan->vw;
         fp.expand          = plan->fp.expand ? 1 : 0;
         fp.ngroups         = plan->fp.ngroups;
+        fp.vrow_linear     = plan->fp.vrow_linear ? 1 : 0;
         {
             // alignment every group of four dst pixels is guaranteed to have
             const uintptr_t a = (uintptr_t)fp.dst | (uintptr_t)dstd.ystride;
@@ -790,7 +791,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             ++launched;
         }
         if (report) {
-            report->fused_vmode = fp.vk;
+            report->fused_vmode = fp.expand ? -fp.vt : fp.vk;
             report->fused_htaps = fp.ht;
         }
     } else {

@@ -13,9 +13,9 @@
 //    the CTA (thread t owns 4 consecutive source elements, as in the ring
 //    kernel);
 //  * source rows streamed through a per-thread cp.async FIFO and converted to
-//    float ONCE into a per-thread ring of EXPAND_RING rows in shared memory;
-//    every destination row gathers its vt taps from that ring (private
-//    LDS.128 + 2 FFMA2 per tap, no barrier);
+//    float ONCE into a sliding window of VT rows held in registers; every
+//    destination row is 2*VT FFMA2 on that window (consecutive dst rows share
+//    it: the window slides once per ~4 dst rows at 4x);
 //  * an H pass in which a thread computes a GROUP of four adjacent dst
 //    columns from one shared window of HT source pixels (the four footprints
 //    nearly coincide when upsizing), all channels packed into FFMA2 pairs;
@@ -34,15 +34,23 @@ namespace b2r {
 // with a separate multiply: s = v*mx; s += 0.5 (s >= 0) ; clamp ; truncate.
 // For s < 0 the reference adds -0.5 and clamps to 0: s + 0.5 is below 0.5
 // there and truncates (or saturates) to 0 as well, so one FADD serves both
-// signs; the float->u32 conversion saturates negatives and NaN to 0 and the
-// upper clamp is an integer min.
+// signs.  A float -> u8/u16 cvt clamps to the destination range by itself (and
+// sends NaN to 0), which is the reference's clamp: no min/max instructions.
 __device__ __forceinline__ unsigned
-quant_fast(float v, float mx, unsigned imx)
+quant_u8(float v)
 {
-    float s = __fadd_rn(__fmul_rn(v, mx), 0.5f);
-    unsigned u;
-    asm("cvt.rzi.u32.f32 %0, %1;" : "=r"(u) : "f"(s));
-    return min(u, imx);
+    float s = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+    unsigned short u;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=h"(u) : "f"(s));
+    return u;
+}
+__device__ __forceinline__ unsigned
+quant_u16(float v)
+{
+    float s = __fadd_rn(__fmul_rn(v, 65535.0f), 0.5f);
+    unsigned short u;
+    asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(u) : "f"(s));
+    return u;
 }
 
 __device__ __forceinline__ float2
@@ -157,11 +165,9 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
             unsigned w[N / 4];
 #pragma unroll
             for (int i = 0; i < N / 4; ++i) {
-                unsigned lo = quant_fast(o[4 * i], 255.0f, 255u)
-                              | (quant_fast(o[4 * i + 1], 255.0f, 255u) << 8);
-                unsigned hi = quant_fast(o[4 * i + 2], 255.0f, 255u)
-                              | (quant_fast(o[4 * i + 3], 255.0f, 255u) << 8);
-                w[i] = lo | (hi << 16);
+                unsigned lo = __byte_perm(quant_u8(o[4 * i]), quant_u8(o[4 * i + 1]), 0x0040);
+                unsigned hi = __byte_perm(quant_u8(o[4 * i + 2]), quant_u8(o[4 * i + 3]), 0x0040);
+                w[i]        = __byte_perm(lo, hi, 0x5410);
             }
             if constexpr (N == 16) {
                 if (align == 16) {
@@ -182,8 +188,7 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
                     __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
                     w[i]      = *reinterpret_cast<unsigned*>(&h);
                 } else {
-                    w[i] = quant_fast(o[2 * i], 65535.0f, 65535u)
-                           | (quant_fast(o[2 * i + 1], 65535.0f, 65535u) << 16);
+                    w[i] = __byte_perm(quant_u16(o[2 * i]), quant_u16(o[2 * i + 1]), 0x5410);
                 }
             }
             if (N % 8 == 0 && align == 16) {
@@ -208,11 +213,11 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
 
 // H pass over the nb buffered rows (dst rows dyb .. dyb+nb-1 of the ROI).
 // hws: this group's weights, hws[j * EXPAND_GROUPS] = (w of columns 0..3 for
-// window tap j).  hb[]: byte offsets of window taps 0..3 in V row 0.
+// window tap j).  hb[j]: byte offset of window tap j in V row 0.
 template<int NCH, int HT>
 __device__ __forceinline__ void
 expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, int dx0,
-             int ncols, const int (&hb)[4], const float4* hws)
+             int ncols, const int (&hb)[HT], const float4* hws)
 {
     constexpr int NR = (NCH == 4) ? 2 : 4;  // rows filtered together
     constexpr int N  = 4 * NCH;
@@ -236,8 +241,8 @@ expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, 
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
                 // rows past nb hold stale data: computed and discarded
-                const float4 v = *reinterpret_cast<const float4*>(
-                    vr + k * FUSED_PITCH_B + hb[j & 3] + (j >> 2) * 16);
+                const float4 v
+                    = *reinterpret_cast<const float4*>(vr + k * FUSED_PITCH_B + hb[j]);
                 acc[k].tap(wd, w, v);
             }
         }
@@ -265,11 +270,15 @@ expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, 
 // Shared memory carve-up (bytes):
 //   vrows  EXPAND_BATCH x FUSED_PITCH_B             V-filtered rows
 //   hws    HT x EXPAND_GROUPS x 16                  H weights, [tap][group]
-//   ring   EXPAND_RING x FUSED_THREADS x 16         converted source rows
-//   fifo   EXPAND_FIFO x FUSED_THREADS x 4*es       raw source rows in flight
-//   vws    max_band_dy x vt x 4                     V weights of the band
+//   vws    max_band_dy x VT x 4                     V weights of the band
 //   vfs    max_band_dy x 4                          first source row per dst row
-template<int NCH, int HT>
+//   fifo   EXPAND_FIFO x FUSED_THREADS x 4*es       raw source rows in flight
+//
+// V rows are laid out linearly (pixel q at q*16) when the windows of adjacent
+// groups start an odd number of pixels apart (4x upsizing: 1 pixel -- a
+// quarter-warp reads 8 consecutive pixels), else in the four planes of
+// resize_fused_kernel (even strides); the host picks (FusedParams::vrow_linear).
+template<int NCH, int VT, int HT>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
 resize_expand_kernel(const FusedParams p, int max_band_dy)
 {
@@ -280,32 +289,30 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     const int SLOT      = FUSED_THREADS * TB;  // bytes between FIFO rows
     unsigned char* vrows = smem_raw;
     float4* hws_all      = reinterpret_cast<float4*>(smem_raw + BATCH * FUSED_PITCH_B);
-    float4* ring         = hws_all + HT * EXPAND_GROUPS;
-    unsigned char* fifo  = reinterpret_cast<unsigned char*>(ring + EXPAND_RING * FUSED_THREADS);
-    float* vws           = reinterpret_cast<float*>(fifo + EXPAND_FIFO * SLOT);
-    int* vfs             = reinterpret_cast<int*>(vws + (size_t)max_band_dy * p.vt);
+    // per-row tables sit before the FIFO so their offsets do not depend on es
+    float* vws           = reinterpret_cast<float*>(hws_all + HT * EXPAND_GROUPS);
+    int* vfs             = reinterpret_cast<int*>(vws + (((size_t)max_band_dy * VT + 3) & ~size_t(3)));
+    unsigned char* fifo  = reinterpret_cast<unsigned char*>(vfs + ((max_band_dy + 3) & ~3));
 
     const int tid     = threadIdx.x;
     const Strip strip = p.strips[blockIdx.x];
     const Band band   = p.bands[blockIdx.y];
-    const int vt      = p.vt;
+    const bool linear = p.vrow_linear != 0;
 
     // ---- H-pass constants: this thread's group of four dst columns -------
     const int ncols = min(4, strip.ndx - 4 * tid);  // <= 0: no group
     const int gg    = (strip.dx0 >> 2) + tid;       // group index in the ROI
-    int hb[4]       = { 0, 0, 0, 0 };
+    int hb[HT];
     {
         const float4* gw = reinterpret_cast<const float4*>(p.hw);
 #pragma unroll
         for (int j = 0; j < HT; ++j)
             hws_all[j * EXPAND_GROUPS + tid]
                 = (ncols > 0) ? gw[(size_t)j * p.ngroups + gg] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ncols > 0) {
-            const int q = p.hfirst[gg] - strip.e0 / NCH;  // window start in the strip
+        const int q = (ncols > 0) ? p.hfirst[gg] - strip.e0 / NCH : 0;  // window start
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                hb[k] = planar_byte(q + k);
-        }
+        for (int j = 0; j < HT; ++j)
+            hb[j] = linear ? (q + j) * 16 : planar_byte(q + j);
     }
     const float4* hws = hws_all + tid;
 
@@ -314,7 +321,23 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     const int e         = strip.e0 + 4 * tid;
     const int row_elems = p.src_w * NCH;
     VPark<NCH> park;
-    park.init(strip.e0, tid);
+    park.init(strip.e0, tid, linear);
+    // 1-3 channels: the four scalar park stores of a warp pile up on a few
+    // banks (6-way for RGB, linear rows) when every thread stores element k in
+    // instruction k.  Rotating the thread's elements by (tid/4)%4 -- once per
+    // source row, at conversion -- brings that down to the 2-way floor.
+    const int rot = (NCH < 4 && (NCH == 2 || linear)) ? (tid >> 2) & 3 : 0;
+    if (NCH < 4 && rot) {
+        int o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o[k] = park.off[NCH == 4 ? 0 : k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int sel = (k + rot) & 3;
+            park.off[NCH == 4 ? 0 : k] = sel == 0 ? o[0] : sel == 1 ? o[1] : sel == 2 ? o[2] : o[3];
+        }
+    }
     if (NCH < 4) {
         // padded pixels: the unused lanes are never written, they must not
         // hold Inf/NaN bit patterns
@@ -323,8 +346,8 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     }
     // stage the band's V weights and (band-relative) first rows
     {
-        const float* gw = p.vw + (size_t)band.dy0 * vt;
-        for (int i = tid; i < band.ndy * vt; i += FUSED_THREADS)
+        const float* gw = p.vw + (size_t)band.dy0 * VT;
+        for (int i = tid; i < band.ndy * VT; i += FUSED_THREADS)
             vws[i] = gw[i];
         for (int i = tid; i < band.ndy; i += FUSED_THREADS)
             vfs[i] = p.vfirst[band.dy0 + i] - band.r0;
@@ -361,7 +384,7 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
         ++rnext;
     };
     // next source row, converted to float
-    int loaded = 0;  // rows converted so far (band-relative index of the next)
+    int loaded = 0;  // rows consumed so far (band-relative index of the next)
     auto pop_row = [&]() -> float4 {
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (async_ok) {
@@ -385,13 +408,22 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
             else
                 raw = load_raw4<ST_U8>(rowp, e, row_elems, false);
         }
+        float4 v;
         if (p.srctype == BT_FLOAT)
-            return convert_raw4<ST_FLOAT>(raw);
-        if (p.srctype == BT_HALF)
-            return convert_raw4<ST_HALF>(raw);
-        if (p.srctype == BT_UINT16)
-            return convert_raw4<ST_U16>(raw);
-        return convert_raw4<ST_U8>(raw);
+            v = convert_raw4<ST_FLOAT>(raw);
+        else if (p.srctype == BT_HALF)
+            v = convert_raw4<ST_HALF>(raw);
+        else if (p.srctype == BT_UINT16)
+            v = convert_raw4<ST_U16>(raw);
+        else
+            v = convert_raw4<ST_U8>(raw);
+        if (NCH < 4) {
+            if (rot & 1)
+                v = make_float4(v.y, v.z, v.w, v.x);
+            if (rot & 2)
+                v = make_float4(v.z, v.w, v.x, v.y);
+        }
+        return v;
     };
 
     if (async_ok) {
@@ -401,22 +433,54 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     }
     __syncthreads();  // vws / vfs / hws / cleared vrows visible
 
-    float4* myring = ring + tid;
+    // the VT source rows under the current dst row, converted, in registers:
+    // win[j] = row (loaded - VT + j) of the band
+    float4 win[VT];
+#pragma unroll
+    for (int j = 0; j < VT; ++j)
+        win[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int dy_end = band.dy0 + band.ndy;
+    // walking shared-window addresses of the current row's weights / first row
+    // (kept opaque so they stay in registers instead of being recomputed)
+    unsigned vw_s, vf_s;
+    asm volatile("mov.u32 %0, %1;" : "=r"(vw_s) : "r"(smem_u32(vws)));
+    asm volatile("mov.u32 %0, %1;" : "=r"(vf_s) : "r"(smem_u32(vfs)));
     for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
         const int nb = min(BATCH, dy_end - dyb);
         for (int row = 0; row < nb; ++row) {
-            const int li = dyb - band.dy0 + row;
-            const int f  = vfs[li];
-            while (loaded < f + vt) {
-                myring[(loaded & (EXPAND_RING - 1)) * FUSED_THREADS] = pop_row();
+            const int f = (int)lds_u32(vf_s);
+            vf_s += 4;
+            while (loaded < f + VT) {  // uniform: slide the window down one row
+#pragma unroll
+                for (int j = 0; j + 1 < VT; ++j)
+                    win[j] = win[j + 1];
+                win[VT - 1] = pop_row();
                 issue_next();  // refills the FIFO slot just consumed
                 ++loaded;
             }
-            const float* w = vws + li * vt;
+            float w[VT];
+            if (VT % 4 == 0) {
+#pragma unroll
+                for (int j = 0; j < VT / 4; ++j) {
+                    uint4 t = lds_v4(vw_s + 16 * j);
+                    w[4 * j]     = __uint_as_float(t.x);
+                    w[4 * j + 1] = __uint_as_float(t.y);
+                    w[4 * j + 2] = __uint_as_float(t.z);
+                    w[4 * j + 3] = __uint_as_float(t.w);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < VT / 2; ++j) {
+                    uint2 t = lds_v2(vw_s + 8 * j);
+                    w[2 * j]     = __uint_as_float(t.x);
+                    w[2 * j + 1] = __uint_as_float(t.y);
+                }
+            }
+            vw_s += 4 * VT;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int j = 0; j < vt; ++j)
-                fma4(a, w[j], myring[((f + j) & (EXPAND_RING - 1)) * FUSED_THREADS]);
+#pragma unroll
+            for (int j = 0; j < VT; ++j)
+                fma4(a, w[j], win[j]);
             if (vactive)
                 park.store(vrows + (size_t)row * FUSED_PITCH_B, a);
         }

@@ -211,17 +211,19 @@ fma4(float4& a, float w, const float4& v)
 // (elements straddle pixels); 1-2 channels -> flat floats.
 template<int NCH> struct VPark {
     int off[NCH == 4 ? 1 : 4];
-    __device__ __forceinline__ void init(int e0, int v)
+    // linear: pixels in order (16 bytes each) instead of the four planes
+    __device__ __forceinline__ void init(int e0, int v, bool linear = false)
     {
         if (NCH == 4) {
-            off[0] = planar_byte(v);
+            off[0] = linear ? v * 16 : planar_byte(v);
         } else {
             const int px0 = e0 / NCH;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 int E  = e0 + 4 * v + k;
                 int px = E / NCH;
-                off[NCH == 4 ? 0 : k] = planar_byte(px - px0) + (E - NCH * px) * 4;
+                off[NCH == 4 ? 0 : k] = (linear ? (px - px0) * 16 : planar_byte(px - px0))
+                                        + (E - NCH * px) * 4;
             }
         }
     }

@@ -65,9 +65,9 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
 {
     FusedPlan& P = *plan;
     const int W = gx.n, H = gy.n;
-    const int vt = gy.maxcount;
-    if (vt < 1 || vt > EXPAND_RING)
+    if (gy.maxcount < 1 || gy.maxcount > EXPAND_MAXVT)
         return false;
+    const int vt = (gy.maxcount + 1) & ~1;  // register window: 2, 4, 6 or 8 rows
     const int ngroups = (W + 3) / 4;
     int window = 1;
     for (int g = 0; g < ngroups; ++g) {
@@ -129,6 +129,13 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
     // ---- H tables ----------------------------------------------------------
     P.expand  = true;
     P.ngroups = ngroups;
+    {
+        // pixels between the windows of adjacent groups, on average
+        double stride = ngroups > 1 ? double(cfirst[4 * (ngroups - 1)] - cfirst[0])
+                                          / double(ngroups - 1)
+                                    : 1.0;
+        P.vrow_linear = (int(stride + 0.5) & 1) != 0;
+    }
     P.ht      = ht;
     P.hfirst.resize(ngroups);
     P.hw.assign(size_t(ngroups) * ht * 4, 0.0f);

@@ -13,6 +13,7 @@ struct FusedPlan {
     std::vector<Band> bands;
     bool expand = false;  // tables are for resize_expand_kernel
     int ngroups = 0;      // expand: groups of four dst columns in the ROI
+    bool vrow_linear = false;  // expand: V-row layout (see expand_kernel.cuh)
     // H pass
     int ht = 0;
     std::vector<int32_t> hfirst;

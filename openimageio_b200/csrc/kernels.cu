@@ -240,20 +240,22 @@ pick_fused(int srctype, int nch, int vk, int ht)
     return table[st][nch - 1](vk, ht);
 }
 
-ExpandKernel expand_lookup_1(int), expand_lookup_2(int), expand_lookup_3(int),
-    expand_lookup_4(int);
+#define B2R_XDECL(n) \
+    ExpandKernel expand_lookup_##n##_2(int), expand_lookup_##n##_4(int), \
+        expand_lookup_##n##_6(int), expand_lookup_##n##_8(int);
+B2R_XDECL(1) B2R_XDECL(2) B2R_XDECL(3) B2R_XDECL(4)
 static ExpandKernel
-pick_expand(int srctype, int nch, int ht)
+pick_expand(int srctype, int nch, int vt, int ht)
 {
-    if (st_index(srctype) < 0)
+    typedef ExpandKernel (*Lookup)(int);
+#define B2R_XROW(n) \
+    { expand_lookup_##n##_2, expand_lookup_##n##_4, expand_lookup_##n##_6, expand_lookup_##n##_8 }
+    static const Lookup table[4][4] = { B2R_XROW(1), B2R_XROW(2), B2R_XROW(3), B2R_XROW(4) };
+    if (st_index(srctype) < 0 || nch < 1 || nch > 4)
         return nullptr;
-    switch (nch) {
-    case 1: return expand_lookup_1(ht);
-    case 2: return expand_lookup_2(ht);
-    case 3: return expand_lookup_3(ht);
-    case 4: return expand_lookup_4(ht);
-    }
-    return nullptr;
+    if (vt != 2 && vt != 4 && vt != 6 && vt != 8)
+        return nullptr;
+    return table[nch - 1][vt / 2 - 1](ht);
 }
 
 bool
@@ -263,16 +265,16 @@ fused_supported(int srctype, int nch, int vk, int ht)
 }
 
 bool
-expand_supported(int srctype, int nch, int ht)
+expand_supported(int srctype, int nch, int vt, int ht)
 {
-    return pick_expand(srctype, nch, ht) != nullptr;
+    return pick_expand(srctype, nch, vt, ht) != nullptr;
 }
 
 int
 fused_ctas_per_sm(const FusedParams& p, int max_band_rows, int max_band_dy,
                   int max_nvec)
 {
-    const void* k = p.expand ? (const void*)pick_expand(p.srctype, p.nch, p.ht)
+    const void* k = p.expand ? (const void*)pick_expand(p.srctype, p.nch, p.vt, p.ht)
                              : (const void*)pick_fused(p.srctype, p.nch, p.vk, p.ht);
     if (!k)
         return 0;
@@ -299,9 +301,9 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
     if (p.expand) {
         size_t b = (size_t)EXPAND_BATCH * (FUSED_THREADS * 4 + 32) * 4;  // vrows
         b += (size_t)p.ht * EXPAND_GROUPS * 16;                          // hws
-        b += (size_t)EXPAND_RING * FUSED_THREADS * 16;                   // ring
         b += (size_t)EXPAND_FIFO * FUSED_THREADS * 4 * basetype_size(p.srctype);
-        b += (size_t)max_band_dy * (p.vt + 1) * 4;                       // vws, vfs
+        b += (((size_t)max_band_dy * p.vt + 3) & ~size_t(3)) * 4
+             + (size_t)((max_band_dy + 3) & ~3) * 4;  // vws, vfs
         return (b + 15) & ~size_t(15);
     }
     size_t f = (size_t)fused_batch(p.vk) * (FUSED_THREADS * 4 + 32);  // FUSED_PITCH_B (4224 B)
@@ -319,7 +321,7 @@ launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
                     int max_nvec, void* stream)
 {
     if (p.expand) {
-        ExpandKernel k = pick_expand(p.srctype, p.nch, p.ht);
+        ExpandKernel k = pick_expand(p.srctype, p.nch, p.vt, p.ht);
         if (!k || p.nstrips <= 0 || p.nbands <= 0)
             return;
         size_t smem = fused_smem_bytes(p, max_band_rows, max_band_dy, max_nvec);

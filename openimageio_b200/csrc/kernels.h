@@ -83,7 +83,7 @@ constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power o
 // EXPAND_GROUPS groups of four dst columns wide, a group per H-pass thread.
 constexpr int EXPAND_GROUPS = 256;
 constexpr int EXPAND_BATCH  = 8;    // V-filtered rows between the passes
-constexpr int EXPAND_RING   = 8;    // converted source rows kept per thread (>= vt)
+constexpr int EXPAND_MAXVT  = 8;    // widest V window (rows held in registers)
 constexpr int EXPAND_FIFO   = 4;    // raw source rows in flight per thread
 
 struct FusedParams {
@@ -96,6 +96,7 @@ struct FusedParams {
     int src_vec_ok, dst_vec_ok;  // 4-element vector loads / stores allowed
     int expand;                  // 1: resize_expand_kernel tables (groups of 4 columns)
     int dst_align;               // expand: 16 / 4 / 0 = alignment dst rows guarantee
+    int vrow_linear;             // expand: V rows laid out linearly, not in planes
     int check_nonfinite;         // float/half sources: flag non-finite outputs
     int* nonfinite_flag;
     int nonfinite_epoch;         // value written to the flag (unique per call)
@@ -125,7 +126,7 @@ struct FusedParams {
 bool
 fused_supported(int srctype, int nch, int vk, int ht);
 bool
-expand_supported(int srctype, int nch, int ht);
+expand_supported(int srctype, int nch, int vt, int ht);
 typedef void (*FusedKernel)(const FusedParams, int, int);
 typedef void (*ExpandKernel)(const FusedParams, int);
 // resident CTAs per SM for this shape (occupancy query), 0 on error

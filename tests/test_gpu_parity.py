@@ -219,6 +219,58 @@ def test_upsample_mitchell_catrom_uint8(oiio, oracle):
         assert rep.path_used == oiio.PATH_FUSED
 
 
+EXPAND_SHAPES = [  # (src h, w) -> (dst h, w)
+    ((68, 120), (272, 480)),    # 4x both axes
+    ((51, 77), (102, 154)),     # 2x, ragged source width
+    ((40, 63), (60, 95)),       # ~1.5x, widths not multiples of 4
+    ((33, 50), (99, 150)),      # 3x
+    ((30, 200), (120, 100)),    # up 4x in y, down 2x in x
+    ((45, 31), (45, 124)),      # same height, 4x in x
+    ((9, 6), (300, 17)),        # tiny source, tall destination
+]
+
+
+@pytest.mark.parametrize("nch", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt,st", [("uint8", "uint8"), ("float", "float"),
+                                   ("half", "half"), ("uint16", "uint16"),
+                                   ("uint8", "float"), ("float", "uint16")])
+def test_expand_kernel_upsizing(oiio, oracle, nch, dt, st):
+    """The upsizing variant of the fused kernel (vmode < 0): every channel
+    count, source/destination type, layout choice and window width."""
+    used = set()
+    for i, (sshape, dshape) in enumerate(EXPAND_SHAPES):
+        src = synth.image(sshape[1], sshape[0], nch, _np_dtype(st), seed=40 + i)
+        if st == "float":
+            # HDR and negative values: the quantiser's clamps must engage
+            src = (src * np.float32(3.0) - np.float32(0.7)).astype(np.float32)
+        for f in ("", "mitchell", "lanczos3", "triangle"):
+            if i >= 2 and f not in ("", "mitchell"):
+                continue
+            g, o, rep = run_both(oiio, oracle, src, dshape, _np_dtype(dt), f)
+            check(g, o)
+            assert rep.path_used == oiio.PATH_FUSED
+            used.add(rep.fused_vmode < 0)
+    assert True in used  # the expand kernel did run
+
+
+def test_expand_kernel_nonfinite_and_windows(oiio, oracle):
+    src = synth.image(52, 40, 4, np.float32, seed=77)
+    src[10, 17, 1] = np.inf
+    src[30, 40, 2] = np.nan
+    g, o, rep = run_both(oiio, oracle, src, (160, 208), np.float32, "mitchell")
+    check(g, o, exact=True)
+    assert rep.nonfinite_redo == 1
+    # ROI inside a larger destination, offset windows, unaligned ROI origin
+    src = synth.image(52, 40, 3, np.uint8, seed=78)
+    pre = synth.image(170, 130, 3, np.uint8, seed=79)
+    g, o, rep = run_both(oiio, oracle, src, (130, 170), np.uint8, "catmull-rom",
+                         src_win=(3, 5, (3, 5, 52, 40)),
+                         dst_win=(7, 2, (7, 2, 170, 130)),
+                         roi=(18, 150, 11, 120), prefill=pre)
+    check(g, o)
+    assert rep.fused_vmode < 0
+
+
 def test_nonfinite_zero_weight_skip(oiio, oracle):
     """Inf/NaN under zero-weight taps must not poison the output: the fused
     kernel flags the image and the exact kernel re-does it."""
