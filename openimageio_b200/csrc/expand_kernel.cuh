@@ -40,16 +40,16 @@ __device__ __forceinline__ unsigned
 quant_u8(float v)
 {
     float s = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
-    unsigned short u;
-    asm("cvt.rzi.u8.f32 %0, %1;" : "=h"(u) : "f"(s));
+    unsigned u;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(u) : "f"(s));
     return u;
 }
 __device__ __forceinline__ unsigned
 quant_u16(float v)
 {
     float s = __fadd_rn(__fmul_rn(v, 65535.0f), 0.5f);
-    unsigned short u;
-    asm("cvt.rzi.u16.f32 %0, %1;" : "=h"(u) : "f"(s));
+    unsigned u;
+    asm("cvt.rzi.u16.f32 %0, %1;" : "=r"(u) : "f"(s));
     return u;
 }
 
@@ -291,8 +291,8 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     float4* hws_all      = reinterpret_cast<float4*>(smem_raw + BATCH * FUSED_PITCH_B);
     // per-row tables sit before the FIFO so their offsets do not depend on es
     float* vws           = reinterpret_cast<float*>(hws_all + HT * EXPAND_GROUPS);
-    int* vfs             = reinterpret_cast<int*>(vws + (((size_t)max_band_dy * VT + 3) & ~size_t(3)));
-    unsigned char* fifo  = reinterpret_cast<unsigned char*>(vfs + ((max_band_dy + 3) & ~3));
+    int* vfs             = reinterpret_cast<int*>(vws + (((size_t)(max_band_dy + 1) * VT + 3) & ~size_t(3)));
+    unsigned char* fifo  = reinterpret_cast<unsigned char*>(vfs + ((max_band_dy + 1 + 3) & ~3));
 
     const int tid     = threadIdx.x;
     const Strip strip = p.strips[blockIdx.x];
@@ -445,10 +445,38 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     unsigned vw_s, vf_s;
     asm volatile("mov.u32 %0, %1;" : "=r"(vw_s) : "r"(smem_u32(vws)));
     asm volatile("mov.u32 %0, %1;" : "=r"(vf_s) : "r"(smem_u32(vfs)));
+    // a row's first-source-row entry is fetched one row ahead (the loop
+    // branches on it; one entry past the band is read and unused)
+    auto load_w = [&](float (&w)[VT]) {
+        if (VT % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < VT / 4; ++j) {
+                uint4 t = lds_v4(vw_s + 16 * j);
+                w[4 * j]     = __uint_as_float(t.x);
+                w[4 * j + 1] = __uint_as_float(t.y);
+                w[4 * j + 2] = __uint_as_float(t.z);
+                w[4 * j + 3] = __uint_as_float(t.w);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VT / 2; ++j) {
+                uint2 t = lds_v2(vw_s + 8 * j);
+                w[2 * j]     = __uint_as_float(t.x);
+                w[2 * j + 1] = __uint_as_float(t.y);
+            }
+        }
+        vw_s += 4 * VT;
+    };
+    int fn = (int)lds_u32(vf_s);
+    vf_s += 4;
+    const unsigned vrows_s = smem_u32(vrows);
     for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
         const int nb = min(BATCH, dy_end - dyb);
         for (int row = 0; row < nb; ++row) {
-            const int f = (int)lds_u32(vf_s);
+            const int f = fn;
+            float w[VT];
+            load_w(w);
+            fn = (int)lds_u32(vf_s);
             vf_s += 4;
             while (loaded < f + VT) {  // uniform: slide the window down one row
 #pragma unroll
@@ -458,31 +486,12 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
                 issue_next();  // refills the FIFO slot just consumed
                 ++loaded;
             }
-            float w[VT];
-            if (VT % 4 == 0) {
-#pragma unroll
-                for (int j = 0; j < VT / 4; ++j) {
-                    uint4 t = lds_v4(vw_s + 16 * j);
-                    w[4 * j]     = __uint_as_float(t.x);
-                    w[4 * j + 1] = __uint_as_float(t.y);
-                    w[4 * j + 2] = __uint_as_float(t.z);
-                    w[4 * j + 3] = __uint_as_float(t.w);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < VT / 2; ++j) {
-                    uint2 t = lds_v2(vw_s + 8 * j);
-                    w[2 * j]     = __uint_as_float(t.x);
-                    w[2 * j + 1] = __uint_as_float(t.y);
-                }
-            }
-            vw_s += 4 * VT;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < VT; ++j)
                 fma4(a, w[j], win[j]);
             if (vactive)
-                park.store(vrows + (size_t)row * FUSED_PITCH_B, a);
+                park.store_s(vrows_s + row * FUSED_PITCH_B, a);
         }
         __syncthreads();
         if (ncols > 0)

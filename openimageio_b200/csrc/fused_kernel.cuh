@@ -227,6 +227,23 @@ template<int NCH> struct VPark {
             }
         }
     }
+    // same, `row` given as a 32-bit shared-window address
+    __device__ __forceinline__ void store_s(unsigned row, const float4& a) const
+    {
+        if (NCH == 4) {
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[0]), "f"(a.x),
+                         "f"(a.y), "f"(a.z), "f"(a.w)
+                         : "memory");
+        } else {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[0]), "f"(a.x) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[NCH == 4 ? 0 : 1]), "f"(a.y)
+                         : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[NCH == 4 ? 0 : 2]), "f"(a.z)
+                         : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[NCH == 4 ? 0 : 3]), "f"(a.w)
+                         : "memory");
+        }
+    }
     __device__ __forceinline__ void store(unsigned char* row, const float4& a) const
     {
         if (NCH == 4) {

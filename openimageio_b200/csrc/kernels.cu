@@ -302,8 +302,8 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
         size_t b = (size_t)EXPAND_BATCH * (FUSED_THREADS * 4 + 32) * 4;  // vrows
         b += (size_t)p.ht * EXPAND_GROUPS * 16;                          // hws
         b += (size_t)EXPAND_FIFO * FUSED_THREADS * 4 * basetype_size(p.srctype);
-        b += (((size_t)max_band_dy * p.vt + 3) & ~size_t(3)) * 4
-             + (size_t)((max_band_dy + 3) & ~3) * 4;  // vws, vfs
+        b += (((size_t)(max_band_dy + 1) * p.vt + 3) & ~size_t(3)) * 4
+             + (size_t)((max_band_dy + 1 + 3) & ~3) * 4;  // vws, vfs (+1 row read ahead)
         return (b + 15) & ~size_t(15);
     }
     size_t f = (size_t)fused_batch(p.vk) * (FUSED_THREADS * 4 + 32);  // FUSED_PITCH_B (4224 B)
