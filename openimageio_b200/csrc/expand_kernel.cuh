@@ -142,15 +142,15 @@ template<> struct GroupAcc<1> {
     }
 };
 
-// Quantise the N = 4*NCH elements of a group to the dst type and store them.
-// dp: address of the group's first element.  `align`: 16 / 4 / 0 as
+// Quantise the N = 4*NCH elements of a group to the dst type DT and store
+// them.  dp: address of the group's first element.  `align`: 16 / 4 / 0 as
 // guaranteed by the host for every group address (FusedParams::dst_align).
-template<int N>
+template<int N, int DT>
 __device__ __forceinline__ void
-store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (&o)[N])
+store_group(unsigned char* dp, int align, int nvalid, const float (&o)[N])
 {
     if (nvalid == N && align >= 4) {
-        if (dsttype == BT_FLOAT) {
+        if (DT == BT_FLOAT) {
             if (align == 16) {
 #pragma unroll
                 for (int i = 0; i < N / 4; ++i)
@@ -161,7 +161,7 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
                 for (int i = 0; i < N; ++i)
                     reinterpret_cast<float*>(dp)[i] = o[i];
             }
-        } else if (dsttype == BT_UINT8) {
+        } else if (DT == BT_UINT8) {
             unsigned w[N / 4];
 #pragma unroll
             for (int i = 0; i < N / 4; ++i) {
@@ -175,16 +175,14 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
                     return;
                 }
             }
-            {
 #pragma unroll
-                for (int i = 0; i < N / 4; ++i)
-                    reinterpret_cast<unsigned*>(dp)[i] = w[i];
-            }
+            for (int i = 0; i < N / 4; ++i)
+                reinterpret_cast<unsigned*>(dp)[i] = w[i];
         } else {
             unsigned w[N / 2];
 #pragma unroll
             for (int i = 0; i < N / 2; ++i) {
-                if (dsttype == BT_HALF) {
+                if (DT == BT_HALF) {
                     __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
                     w[i]      = *reinterpret_cast<unsigned*>(&h);
                 } else {
@@ -203,12 +201,39 @@ store_group(unsigned char* dp, int dsttype, int align, int nvalid, const float (
             }
         }
     } else {
-        const int des = (dsttype == BT_UINT8) ? 1 : (dsttype == BT_FLOAT ? 4 : 2);
+        constexpr int des = (DT == BT_UINT8) ? 1 : (DT == BT_FLOAT ? 4 : 2);
 #pragma unroll
         for (int i = 0; i < N; ++i)
             if (i < nvalid)
-                store_elem(dp + i * des, dsttype, o[i]);
+                store_elem(dp + i * des, DT, o[i]);
     }
+}
+
+// The NR rows a thread has just filtered: screen, quantise, store.
+template<int NCH, int NR, int DT>
+__device__ __forceinline__ bool
+store_rows(const FusedParams& p, const GroupAcc<NCH> (&acc)[NR], unsigned char* dp,
+           int nrows, int ncols)
+{
+    constexpr int N = 4 * NCH;
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        if (k < nrows) {
+            float o[N];
+            acc[k].get(o);
+            if (p.check_nonfinite) {
+                float t = 0.0f;
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    t += o[i];  // Inf/NaN in any element survives the sum
+                bad |= !(fabsf(t) <= 3.402823466e+38f);
+            }
+            store_group<N, DT>(dp, p.dst_align, ncols * NCH, o);
+        }
+        dp += p.dst_ystride;
+    }
+    return bad;
 }
 
 // H pass over the nb buffered rows (dst rows dyb .. dyb+nb-1 of the ROI).
@@ -219,9 +244,9 @@ __device__ __forceinline__ void
 expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, int dx0,
              int ncols, const int (&hb)[HT], const float4* hws)
 {
-    constexpr int NR = (NCH == 4) ? 2 : 4;  // rows filtered together
-    constexpr int N  = 4 * NCH;
-    const int des    = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
+    constexpr int NR = (NCH >= 3) ? 2 : 4;  // rows filtered together
+    const int dt     = p.dsttype;
+    const int des    = (dt == BT_UINT8) ? 1 : (dt == BT_FLOAT ? 4 : 2);
     unsigned char* dp = p.dst + (long long)dyb * p.dst_ystride + (long long)dx0 * (NCH * des);
     bool bad = false;
 #pragma unroll 1
@@ -246,22 +271,17 @@ expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, 
                 acc[k].tap(wd, w, v);
             }
         }
-#pragma unroll
-        for (int k = 0; k < NR; ++k) {
-            if (rb + k < nb) {
-                float o[N];
-                acc[k].get(o);
-                if (p.check_nonfinite) {
-                    float t = 0.0f;
-#pragma unroll
-                    for (int i = 0; i < N; ++i)
-                        t += o[i];  // Inf/NaN in any element survives the sum
-                    bad |= !(fabsf(t) <= 3.402823466e+38f);
-                }
-                store_group<N>(dp + (long long)(rb + k) * p.dst_ystride, p.dsttype,
-                               p.dst_align, ncols * NCH, o);
-            }
-        }
+        // one type dispatch per NR rows
+        const int nrows = nb - rb;
+        if (dt == BT_UINT8)
+            bad |= store_rows<NCH, NR, BT_UINT8>(p, acc, dp, nrows, ncols);
+        else if (dt == BT_FLOAT)
+            bad |= store_rows<NCH, NR, BT_FLOAT>(p, acc, dp, nrows, ncols);
+        else if (dt == BT_HALF)
+            bad |= store_rows<NCH, NR, BT_HALF>(p, acc, dp, nrows, ncols);
+        else
+            bad |= store_rows<NCH, NR, BT_UINT16>(p, acc, dp, nrows, ncols);
+        dp += (long long)NR * p.dst_ystride;
     }
     if (bad)
         *p.nonfinite_flag = p.nonfinite_epoch;
