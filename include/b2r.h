@@ -89,6 +89,16 @@ typedef struct b2r_options {
     int32_t path;      /* enum b2r_path */
     void* cuda_stream; /* cudaStream_t; NULL = default stream */
     int32_t reserved[4];
+    /* Highlight compensation, as oiiotool --resize/--fit ":highlightcomp=1"
+     * (src/oiiotool/oiiotool.cpp:4636-4665) and maketx --hicomp
+     * (maketexture.cpp:907-935) wrap it around the resize: rangecompress the
+     * source into a temporary of its own type, resize, rangeexpand the
+     * result in place -- all on the device.  alpha_channel1 / z_channel1 are
+     * 1 + the index of the channel rangecompress must leave alone
+     * (ImageSpec::alpha_channel / z_channel), 0 = none. */
+    int32_t highlightcomp;
+    int32_t alpha_channel1, z_channel1;
+    int32_t reserved2;
 } b2r_options;
 
 /* Filled on request: what ran, for tests and benchmarks. */
@@ -156,6 +166,25 @@ B2R_API int b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
                               const b2r_filter2d* filter, const b2r_roi* roi,
                               const b2r_options* opt, b2r_report* report,
                               char* err, size_t errlen);
+
+/* ---- rangecompress / rangeexpand ---------------------------------------
+ * Replaces rangecompress_<R,A> / rangeexpand_<R,A>
+ * (src/libOpenImageIO/imagebufalgo_pixelmath.cpp:560-735): the log-curve
+ * point ops used for highlight compensation around a resize.  Any of the
+ * four pixel types on either side; dst may be src (in place).  useluma,
+ * alpha_channel and z_channel (-1 = none) as in the reference; roi NULL =
+ * dst data window, channel range clamped to both images
+ * (IBAprep_CLAMP_MUTUAL_NCHANNELS, :763).  logf/expf are the device's
+ * (<= 2 ulp from glibc's), so float results agree to ~1e-6 relative, not to
+ * the bit. */
+B2R_API int b2r_rangecompress(const b2r_image* dst, const b2r_image* src,
+                              int useluma, int alpha_channel, int z_channel,
+                              const b2r_roi* roi, const b2r_options* opt,
+                              b2r_report* report, char* err, size_t errlen);
+B2R_API int b2r_rangeexpand(const b2r_image* dst, const b2r_image* src,
+                            int useluma, int alpha_channel, int z_channel,
+                            const b2r_roi* roi, const b2r_options* opt,
+                            b2r_report* report, char* err, size_t errlen);
 
 /* ---- resample --------------------------------------------------------- */
 /* Replaces resample_<D,S> (xform.cpp:1663-1687 and the kernels it picks,

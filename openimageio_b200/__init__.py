@@ -59,7 +59,9 @@ class _Roi(C.Structure):
 
 class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("path", C.c_int32),
-                ("cuda_stream", C.c_void_p), ("reserved", C.c_int32 * 4)]
+                ("cuda_stream", C.c_void_p), ("reserved", C.c_int32 * 4),
+                ("highlightcomp", C.c_int32), ("alpha_channel1", C.c_int32),
+                ("z_channel1", C.c_int32), ("reserved2", C.c_int32)]
 
 
 class Report(C.Structure):
@@ -124,6 +126,10 @@ def lib():
     L.b2r_resample.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int,
                                C.POINTER(_Roi), C.POINTER(_Options),
                                C.POINTER(Report), C.c_char_p, C.c_size_t]
+    for f in (L.b2r_rangecompress, L.b2r_rangeexpand):
+        f.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int, C.c_int,
+                      C.c_int, C.POINTER(_Roi), C.POINTER(_Options),
+                      C.POINTER(Report), C.c_char_p, C.c_size_t]
     L.b2r_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
         [C.POINTER(C.c_int)] * 4
     L.b2r_band_split.argtypes = [C.POINTER(_Roi), C.c_int, C.c_int,
@@ -222,6 +228,7 @@ class ImageSpec:
         self.depth = 1
         self.deep = False
         self.alpha_channel = 3 if nchannels == 4 else -1
+        self.z_channel = -1
         self.set_format(format)
 
     def set_format(self, format):
@@ -241,7 +248,7 @@ class ImageSpec:
     def copy(self):
         s = ImageSpec(self.width, self.height, self.nchannels, self.basetype)
         for k in ("x", "y", "full_x", "full_y", "full_width", "full_height",
-                  "depth", "deep", "alpha_channel"):
+                  "depth", "deep", "alpha_channel", "z_channel"):
             setattr(s, k, getattr(self, k))
         return s
 
@@ -461,11 +468,15 @@ def _ibaprep(roi, dst, src):
     return roi
 
 
-def _options(device=0, path=PATH_AUTO, stream=None):
+def _options(device=0, path=PATH_AUTO, stream=None, highlightcomp=False,
+             alpha_channel=-1, z_channel=-1):
     o = _Options()
     o.device = device
     o.path = path
     o.cuda_stream = stream
+    o.highlightcomp = 1 if highlightcomp else 0
+    o.alpha_channel1 = alpha_channel + 1 if alpha_channel >= 0 else 0
+    o.z_channel1 = z_channel + 1 if z_channel >= 0 else 0
     return o
 
 
@@ -485,7 +496,10 @@ class _IBA:
 
     # ---- resize -----------------------------------------------------------
     def resize(self, *args, filtername="", filterwidth=0.0, roi=None,
-               nthreads=0, filterptr=None, path=PATH_AUTO, device=0):
+               nthreads=0, filterptr=None, path=PATH_AUTO, device=0,
+               highlightcomp=False):
+        """highlightcomp: oiiotool's `--resize:highlightcomp=1` recipe
+        (oiiotool.cpp:4644-4663) run on the device around the resize."""
         bufs = [a for a in args if isinstance(a, ImageBuf)]
         rest = [a for a in args if not isinstance(a, ImageBuf)]
         if rest:  # positional filtername / filterwidth
@@ -494,16 +508,16 @@ class _IBA:
                 filterwidth = rest[1]
         if len(bufs) == 2:
             return self._resize(bufs[0], bufs[1], filtername, filterwidth, roi,
-                                filterptr, path, device)
+                                filterptr, path, device, highlightcomp)
         result = ImageBuf()
         ok = self._resize(result, bufs[0], filtername, filterwidth, roi,
-                          filterptr, path, device)
+                          filterptr, path, device, highlightcomp)
         if not ok and not result.has_error:
             result.errorfmt("ImageBufAlgo::resize() error")
         return result
 
     def _resize(self, dst, src, filtername, filterwidth, roi, filterptr, path,
-                device):
+                device, highlightcomp=False):
         roi = _ibaprep(roi, dst, src)
         if roi is None:
             return False
@@ -512,7 +526,8 @@ class _IBA:
         r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
                  roi.chend)
         stream = _current_stream(dst) or _current_stream(src)
-        o = _options(device, path, stream)
+        o = _options(device, path, stream, highlightcomp,
+                     src.spec_.alpha_channel, src.spec_.z_channel)
         rep = Report()
         err = C.create_string_buffer(512)
         want_report = not (dst.on_device and src.on_device)
@@ -527,6 +542,51 @@ class _IBA:
                               C.byref(r), C.byref(o),
                               C.byref(rep) if want_report else None, err, 512)
         self.last_report = rep if want_report else None
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    # ---- rangecompress / rangeexpand -------------------------------------
+    def rangecompress(self, *args, useluma=False, roi=None, nthreads=0,
+                      device=0):
+        """ImageBufAlgo::rangecompress (imagebufalgo_pixelmath.cpp:748-759)."""
+        return self._range_call(False, args, useluma, roi, device)
+
+    def rangeexpand(self, *args, useluma=False, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::rangeexpand (imagebufalgo_pixelmath.cpp:763-774)."""
+        return self._range_call(True, args, useluma, roi, device)
+
+    def _range_call(self, expand, args, useluma, roi, device):
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:
+            useluma = bool(rest[0])
+        if len(bufs) == 2:
+            return self._range(expand, bufs[0], bufs[1], useluma, roi, device)
+        result = ImageBuf()
+        ok = self._range(expand, result, bufs[0], useluma, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::%s() error"
+                            % ("rangeexpand" if expand else "rangecompress"))
+        return result
+
+    def _range(self, expand, dst, src, useluma, roi, device):
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        roi.chend = min(roi.chend, dst.nchannels, src.nchannels)
+        L = lib()
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        stream = _current_stream(dst) or _current_stream(src)
+        o = _options(device, PATH_AUTO, stream)
+        err = C.create_string_buffer(512)
+        f = L.b2r_rangeexpand if expand else L.b2r_rangecompress
+        rc = f(C.byref(d), C.byref(s), 1 if useluma else 0,
+               src.spec_.alpha_channel, src.spec_.z_channel, C.byref(r),
+               C.byref(o), None, err, 512)
         if rc:
             dst.errorfmt(err.value.decode())
             return False
@@ -712,13 +772,18 @@ class MipChain:
     """Device-resident MIP pyramid: the level loop of write_mipmap
     (src/libOpenImageIO/maketexture.cpp:823-986) without host round trips."""
 
-    def __init__(self, level0, filtername="box", clamp_half=False, device=0):
+    def __init__(self, level0, filtername="box", clamp_half=False, device=0,
+                 highlightcomp=False):
+        """highlightcomp: maketx --hicomp (rangecompress / rangeexpand around
+        every filtered level, maketexture.cpp:907-935)."""
         if not isinstance(level0, ImageBuf):
             level0 = ImageBuf(level0)
         L = lib()
         h = C.c_void_p()
         im = level0._c()
-        o = _options(device, PATH_AUTO, _current_stream(level0))
+        o = _options(device, PATH_AUTO, _current_stream(level0), highlightcomp,
+                     level0.spec_.alpha_channel,
+                     getattr(level0.spec_, "z_channel", -1))
         err = C.create_string_buffer(512)
         rc = L.b2r_mipchain_create(C.byref(h), C.byref(im), filtername.encode(),
                                    1 if clamp_half else 0,

@@ -1146,6 +1146,23 @@ b2r_filter1d_eval(const b2r_filter1d* f, float x)
     return (*f->f)(x);
 }
 
+namespace {
+int
+resize_highlightcomp(const b2r_image* dst, const b2r_image* src, const Filter2D& filter,
+                     const b2r_roi* roi, const b2r_options* opt, b2r_report* report,
+                     char* err, size_t errlen);
+
+int
+resize_entry(const b2r_image* dst, const b2r_image* src, const Filter2D& filter,
+             const b2r_roi* roi, const b2r_options* opt, b2r_report* report, char* err,
+             size_t errlen)
+{
+    if (opt && opt->highlightcomp)
+        return resize_highlightcomp(dst, src, filter, roi, opt, report, err, errlen);
+    return resize_impl(dst, src, filter, roi, opt, report, err, errlen);
+}
+}  // namespace
+
 int
 b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
                   const b2r_filter2d* filter, const b2r_roi* roi,
@@ -1156,7 +1173,7 @@ b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
         set_err(err, errlen, "resize: null filter");
         return B2R_ERR_INVALID;
     }
-    return resize_impl(dst, src, *filter->f, roi, opt, report, err, errlen);
+    return resize_entry(dst, src, *filter->f, roi, opt, report, err, errlen);
 }
 
 int
@@ -1193,7 +1210,7 @@ b2r_resize(const b2r_image* dst, const b2r_image* src, const char* filtername,
         set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
         return B2R_ERR_FILTER;
     }
-    return resize_impl(dst, src, *filter, roi, opt, report, err, errlen);
+    return resize_entry(dst, src, *filter, roi, opt, report, err, errlen);
 }
 
 int
@@ -1292,6 +1309,353 @@ b2r_fit_geometry(int src_full_width, int src_full_height, int fit_width,
 }
 
 }  // extern "C"
+
+// =========================================================================
+// rangecompress / rangeexpand
+// =========================================================================
+namespace {
+
+// Device-side worker shared by the two entry points and by the
+// highlight-compensated resize: images already resident on `device`.
+void
+range_on_device(bool expand, const b2r_image& dst, void* dpix, const b2r_image& src,
+                const void* spix, const b2r_roi& roi, bool useluma, int alpha_channel,
+                int z_channel, cudaStream_t stream)
+{
+    RangeParams rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.dst    = to_dev(dst, dpix);
+    rp.src    = to_dev(src, const_cast<void*>(spix));
+    rp.roi_x0 = roi.xbegin;
+    rp.roi_x1 = roi.xend;
+    rp.roi_y0 = roi.ybegin;
+    rp.roi_y1 = roi.yend;
+    rp.chbegin = roi.chbegin;
+    rp.chend   = roi.chend;
+    rp.expand  = expand ? 1 : 0;
+    // "No way to use luma" (pixelmath.cpp:614-621, 682-689)
+    const int nc = roi.chend - roi.chbegin;
+    if (nc < 3 || (alpha_channel >= roi.chbegin && alpha_channel < roi.chbegin + 3)
+        || (z_channel >= roi.chbegin && z_channel < roi.chbegin + 3))
+        useluma = false;
+    rp.useluma       = useluma ? 1 : 0;
+    rp.alpha_channel = alpha_channel;
+    rp.z_channel     = z_channel;
+    rp.in_place      = (dpix == spix) ? 1 : 0;
+    launch_range(rp, stream);
+}
+
+int
+range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int useluma,
+           int alpha_channel, int z_channel, const b2r_roi* roi_in,
+           const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
+{
+    if (report)
+        memset(report, 0, sizeof(*report));
+    int rc = check_image(src_in, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst_in, false, err, errlen);
+    if (rc)
+        return rc;
+    const b2r_image& dst = *dst_in;
+    const b2r_image& src = *src_in;
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 range compression path has no "
+                "CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    b2r_roi roi;
+    if (roi_in) {
+        roi         = *roi_in;
+        roi.xbegin  = std::max(roi.xbegin, dst.x);
+        roi.xend    = std::min(roi.xend, dst.x + dst.width);
+        roi.ybegin  = std::max(roi.ybegin, dst.y);
+        roi.yend    = std::min(roi.yend, dst.y + dst.height);
+        roi.chbegin = std::max(roi.chbegin, 0);
+        roi.chend   = std::min(roi.chend, dst.nchannels);
+    } else {
+        roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
+                        dst.nchannels };
+    }
+    roi.chend = std::min(roi.chend, src.nchannels);  // IBAprep_CLAMP_MUTUAL_NCHANNELS
+    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin || roi.chend <= roi.chbegin)
+        return B2R_OK;
+    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+    const int ses = basetype_size(src.basetype);
+    const int des = basetype_size(dst.basetype);
+
+    int sdev = opt ? opt->device : 0, ddev = sdev;
+    const int smem = memspace_of(&src, &sdev);
+    const int dmem = memspace_of(&dst, &ddev);
+    int device     = opt ? opt->device : 0;
+    if (smem == B2R_MEM_DEVICE)
+        device = sdev;
+    else if (dmem == B2R_MEM_DEVICE)
+        device = ddev;
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    device_info(device);
+    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+
+    // host images: stage the part of the ROI that exists on each side
+    b2r_image srcd = src, dstd = dst;
+    void* dsrc = src.pixels;
+    void* ddst = dst.pixels;
+    void *src_alloc = nullptr, *dst_alloc = nullptr;
+    size_t dpitch = 0, drowbytes = 0;
+    if (smem == B2R_MEM_HOST) {
+        if (src.xstride != (int64_t)src.nchannels * ses) {
+            set_err(err, errlen, "host source pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        const int x0 = std::max(roi.xbegin, src.x), x1 = std::min(roi.xend, src.x + src.width);
+        const int y0 = std::max(roi.ybegin, src.y), y1 = std::min(roi.yend, src.y + src.height);
+        srcd.x = x0, srcd.y = y0;
+        srcd.width = std::max(0, x1 - x0), srcd.height = std::max(0, y1 - y0);
+        if (srcd.width > 0 && srcd.height > 0) {
+            size_t rowbytes = size_t(srcd.width) * src.xstride;
+            size_t pitch    = (rowbytes + 15) & ~size_t(15);
+            CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * srcd.height, stream));
+            const unsigned char* hp = (const unsigned char*)src.pixels
+                                      + (long long)(y0 - src.y) * src.ystride
+                                      + (long long)(x0 - src.x) * src.xstride;
+            CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, hp, src.ystride, rowbytes,
+                                       srcd.height, cudaMemcpyHostToDevice, stream));
+            srcd.ystride = (int64_t)pitch;
+            if (report)
+                report->h2d_bytes += (int64_t)rowbytes * srcd.height;
+        } else {
+            srcd.width = srcd.height = 0;  // every pixel reads as black
+            CUDA_TRY(cudaMallocAsync(&src_alloc, 16, stream));
+        }
+        dsrc = src_alloc;
+    }
+    unsigned char* host_out = nullptr;
+    if (dmem == B2R_MEM_HOST) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "host destination pixels must be contiguous in x");
+            if (src_alloc)
+                cudaFreeAsync(src_alloc, stream);
+            return B2R_ERR_UNSUPPORTED;
+        }
+        drowbytes = size_t(roi_w) * dst.xstride;
+        dpitch    = (drowbytes + 15) & ~size_t(15);
+        CUDA_TRY(cudaMallocAsync(&dst_alloc, dpitch * roi_h, stream));
+        host_out = (unsigned char*)dst.pixels + (long long)(roi.ybegin - dst.y) * dst.ystride
+                   + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
+            // channels outside the range keep what dst holds
+            CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
+                                       roi_h, cudaMemcpyHostToDevice, stream));
+            if (report)
+                report->h2d_bytes += (int64_t)drowbytes * roi_h;
+        }
+        ddst         = dst_alloc;
+        dstd.x       = roi.xbegin;
+        dstd.y       = roi.ybegin;
+        dstd.width   = roi_w;
+        dstd.height  = roi_h;
+        dstd.ystride = (int64_t)dpitch;
+    }
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    const bool timed = report != nullptr;
+    if (timed) {
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, stream);
+    }
+    range_on_device(expand, dstd, ddst, srcd, dsrc, roi, useluma != 0, alpha_channel,
+                    z_channel, stream);
+    if (timed)
+        cudaEventRecord(ev1, stream);
+    {
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
+            return B2R_ERR_CUDA;
+        }
+    }
+    if (dst_alloc) {
+        CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
+                                   roi_h, cudaMemcpyDeviceToHost, stream));
+        if (report)
+            report->d2h_bytes += (int64_t)drowbytes * roi_h;
+        CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
+    }
+    if (src_alloc)
+        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
+    if (dst_alloc || src_alloc || timed)
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    if (timed) {
+        cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        report->kernels_launched = 1;
+    }
+    return B2R_OK;
+}
+
+}  // namespace
+
+namespace {
+// oiiotool's ":highlightcomp=1" recipe (oiiotool.cpp:4644-4663) on the device:
+// tmp = rangecompress(src) in src's own type, resize(dst, tmp),
+// rangeexpand(dst, dst) over the ROI just written.
+int
+resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Filter2D& filter,
+                     const b2r_roi* roi_in, const b2r_options* opt, b2r_report* report,
+                     char* err, size_t errlen)
+{
+    if (report)
+        memset(report, 0, sizeof(*report));
+    int rc = check_image(src_in, true, err, errlen);
+    if (rc)
+        return rc;
+    rc = check_image(dst_in, false, err, errlen);
+    if (rc)
+        return rc;
+    const b2r_image& dst = *dst_in;
+    const b2r_image& src = *src_in;
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 resize path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    b2r_roi roi;
+    if (roi_in) {
+        roi        = *roi_in;
+        roi.xbegin = std::max(roi.xbegin, dst.x);
+        roi.xend   = std::min(roi.xend, dst.x + dst.width);
+        roi.ybegin = std::max(roi.ybegin, dst.y);
+        roi.yend   = std::min(roi.yend, dst.y + dst.height);
+    } else {
+        roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
+                        dst.nchannels };
+    }
+    roi.chbegin = 0;
+    roi.chend   = dst.nchannels;
+    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin)
+        return B2R_OK;
+    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+    const int ses = basetype_size(src.basetype), des = basetype_size(dst.basetype);
+    int sdev = opt->device, ddev = sdev;
+    const int smem = memspace_of(&src, &sdev);
+    const int dmem = memspace_of(&dst, &ddev);
+    int device     = opt->device;
+    if (smem == B2R_MEM_DEVICE)
+        device = sdev;
+    else if (dmem == B2R_MEM_DEVICE)
+        device = ddev;
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    device_info(device);
+    cudaStream_t stream = (cudaStream_t)opt->cuda_stream;
+    const int alpha = opt->alpha_channel1 - 1, z = opt->z_channel1 - 1;
+
+    b2r_options sub = *opt;
+    sub.highlightcomp = 0;
+    sub.device        = device;
+
+    // compressed copy of the source, same type and windows, on the device
+    b2r_image T = src;
+    void* tpix  = nullptr;
+    const size_t trow = (size_t(src.width) * src.nchannels * ses + 15) & ~size_t(15);
+    CUDA_TRY(cudaMallocAsync(&tpix, trow * src.height, stream));
+    T.pixels   = tpix;
+    T.xstride  = (int64_t)src.nchannels * ses;
+    T.ystride  = (int64_t)trow;
+    T.memspace = B2R_MEM_DEVICE;
+    T.device   = device;
+    b2r_report sub_report;
+    rc = b2r_rangecompress(&T, &src, 0, alpha, z, nullptr, &sub, report ? &sub_report : nullptr,
+                           err, errlen);
+    if (rc == B2R_OK && report)
+        report->h2d_bytes += sub_report.h2d_bytes;
+
+    // the destination ROI on the device
+    b2r_image D = dst;
+    void* dpix  = nullptr;
+    if (rc == B2R_OK && dmem == B2R_MEM_HOST) {
+        if (dst.xstride != (int64_t)dst.nchannels * des) {
+            set_err(err, errlen, "host destination pixels must be contiguous in x");
+            rc = B2R_ERR_UNSUPPORTED;
+        } else {
+            const size_t drow = (size_t(roi_w) * dst.xstride + 15) & ~size_t(15);
+            cudaError_t e = cudaMallocAsync(&dpix, drow * roi_h, stream);
+            if (e != cudaSuccess) {
+                set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+                rc = B2R_ERR_CUDA;
+            }
+            D.pixels   = dpix;
+            D.x        = roi.xbegin;
+            D.y        = roi.ybegin;
+            D.width    = roi_w;
+            D.height   = roi_h;
+            D.ystride  = (int64_t)drow;
+            D.memspace = B2R_MEM_DEVICE;
+            D.device   = device;
+        }
+    }
+    if (rc == B2R_OK) {
+        rc = resize_impl(&D, &T, filter, &roi, &sub, report ? &sub_report : nullptr, err,
+                         errlen);
+        if (rc == B2R_OK && report) {
+            int64_t h2d = report->h2d_bytes;
+            *report             = sub_report;
+            report->h2d_bytes  += h2d;
+            report->kernels_launched += 2;
+        }
+    }
+    if (rc == B2R_OK)
+        range_on_device(true, D, D.pixels, D, D.pixels, roi, false, alpha, z, stream);
+    if (rc == B2R_OK && dpix) {
+        unsigned char* hp = (unsigned char*)dst.pixels
+                            + (long long)(roi.ybegin - dst.y) * dst.ystride
+                            + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        cudaError_t e = cudaMemcpy2DAsync(hp, dst.ystride, dpix, D.ystride,
+                                          size_t(roi_w) * dst.xstride, roi_h,
+                                          cudaMemcpyDeviceToHost, stream);
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+            rc = B2R_ERR_CUDA;
+        } else if (report) {
+            report->d2h_bytes += (int64_t)roi_w * dst.xstride * roi_h;
+        }
+    }
+    if (dpix)
+        cudaFreeAsync(dpix, stream);
+    cudaFreeAsync(tpix, stream);
+    if (rc == B2R_OK && (dmem == B2R_MEM_HOST || smem == B2R_MEM_HOST))
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    return rc;
+}
+}  // namespace
+
+extern "C" int
+b2r_rangecompress(const b2r_image* dst, const b2r_image* src, int useluma,
+                  int alpha_channel, int z_channel, const b2r_roi* roi,
+                  const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
+{
+    return range_impl(false, dst, src, useluma, alpha_channel, z_channel, roi, opt, report,
+                      err, errlen);
+}
+
+extern "C" int
+b2r_rangeexpand(const b2r_image* dst, const b2r_image* src, int useluma, int alpha_channel,
+                int z_channel, const b2r_roi* roi, const b2r_options* opt,
+                b2r_report* report, char* err, size_t errlen)
+{
+    return range_impl(true, dst, src, useluma, alpha_channel, z_channel, roi, opt, report, err,
+                      errlen);
+}
 
 // =========================================================================
 // resample
@@ -1634,6 +1998,25 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
     sub.device      = device;
     sub.path        = opt ? opt->path : B2R_PATH_AUTO;
     sub.cuda_stream = (void*)stream;
+    // maketx --hicomp: only the filtered branch is wrapped (:889-935)
+    const bool hicomp = opt && opt->highlightcomp && fname != "box"
+                        && chain->levels.size() > 1;
+    const int hc_z    = opt ? opt->z_channel1 - 1 : -1;
+    void* hc_tmp      = nullptr;
+    if (hicomp
+        && cudaMalloc(&hc_tmp, size_t(l0.w) * l0.h * nch * 4) != cudaSuccess) {
+        set_err(err, errlen, "mipchain: out of device memory for the highlight "
+                             "compensation scratch image");
+        return fail(B2R_ERR_CUDA);
+    }
+    struct ScratchFree {
+        void* p;
+        ~ScratchFree()
+        {
+            if (p)
+                cudaFree(p);
+        }
+    } hc_free { hc_tmp };
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
@@ -1677,7 +2060,19 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                 launch_box_downsample(bp, stream);
                 chain->launches += 1;
             } else {
-                rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
+                b2r_image R = S;  // what the resize reads
+                if (hicomp) {
+                    // rangecompress(*img) (:907-909); the level itself stays
+                    // intact for the caller, the compressed copy is scratch
+                    R.pixels = hc_tmp;
+                    if (pass == 1) {
+                        b2r_roi all { 0, w, 0, h, 0, nch };
+                        range_on_device(false, R, R.pixels, S, S.pixels, all, false,
+                                        alpha_channel, hc_z, stream);
+                        chain->launches += 1;
+                    }
+                }
+                rc = b2r_resize(&D, &R, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
                                 err, errlen);
                 if (rc) {
                     if (ev0)
@@ -1688,6 +2083,13 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                 }
                 if (pass == 1)
                     chain->launches += 2;
+                if (hicomp && pass == 1) {
+                    // rangeexpand(*small) in place (:933-935)
+                    b2r_roi all { 0, sw, 0, sh, 0, nch };
+                    range_on_device(true, D, D.pixels, D, D.pixels, all, false,
+                                    alpha_channel, hc_z, stream);
+                    chain->launches += 1;
+                }
             }
             if (pass == 1 && clamp_half) {
                 launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,

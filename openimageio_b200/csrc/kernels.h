@@ -168,6 +168,19 @@ void
 launch_clamp(float* pixels, long long n, int nch, int alpha_channel, float lo,
              float hi, void* stream);
 
+// rangecompress / rangeexpand (imagebufalgo_pixelmath.cpp:560-735) over a ROI.
+struct RangeParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    int expand;    // 0: rangecompress, 1: rangeexpand
+    int useluma;   // caller has already applied the reference's "no way to use luma" rule
+    int alpha_channel, z_channel;  // copied through untouched (-1: none)
+    int in_place;  // dst and src are the same pixels: skipped channels are not rewritten
+};
+void
+launch_range(const RangeParams& p, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

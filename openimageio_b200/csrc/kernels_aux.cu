@@ -382,6 +382,162 @@ launch_box_downsample(const BoxParams& p, void* stream)
     }
 }
 
+// ------------------------------------------------------------------------
+// rangecompress / rangeexpand (imagebufalgo_pixelmath.cpp:560-735): the
+// highlight-compensation point ops oiiotool and maketx wrap around a resize.
+// ------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ float
+dev_rangecompress(float x)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absx = fabsf(x);
+    if (absx <= x1)
+        return x;
+    float t = __fadd_rn(__fmul_rn(c, absx), 1.0f);
+    return copysignf(__fadd_rn(a, __fmul_rn(b, logf(fabsf(t)))), x);
+}
+
+__device__ __forceinline__ float
+dev_rangeexpand(float y)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absy = fabsf(y);
+    if (absy <= x1)
+        return y;
+    float xi = expf(__fdiv_rn(__fsub_rn(absy, a), b));
+    float x  = __fdiv_rn(__fsub_rn(xi, 1.0f), c);
+    if (x < x1)
+        x = __fdiv_rn(__fsub_rn(-xi, 1.0f), c);
+    return copysignf(x, y);
+}
+
+template<bool EXPAND>
+__device__ __forceinline__ float
+dev_range(float v)
+{
+    return EXPAND ? dev_rangeexpand(v) : dev_rangecompress(v);
+}
+
+// one thread per pixel of the ROI, any of the four types on either side
+template<bool EXPAND>
+__global__ void __launch_bounds__(256)
+range_kernel(const RangeParams p)
+{
+    const int w = p.roi_x1 - p.roi_x0;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w)
+        return;
+    const int px = p.roi_x0 + x, py = p.roi_y0 + y;
+    unsigned char* dp = (unsigned char*)p.dst.pixels + (long long)(py - p.dst.y) * p.dst.ystride
+                        + (long long)(px - p.dst.x) * p.dst.xstride;
+    const bool inside = px >= p.src.x && px < p.src.x + p.src.width && py >= p.src.y
+                        && py < p.src.y + p.src.height;
+    const unsigned char* sp = (const unsigned char*)p.src.pixels
+                              + (long long)(py - p.src.y) * p.src.ystride
+                              + (long long)(px - p.src.x) * p.src.xstride;
+    const int ses = p.src.basetype == BT_UINT8 ? 1 : (p.src.basetype == BT_FLOAT ? 4 : 2);
+    const int des = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
+    float scale = 0.0f;
+    if (p.useluma) {
+        float r = inside ? ld_elem(sp + (p.chbegin) * ses, p.src.basetype) : 0.0f;
+        float g = inside ? ld_elem(sp + (p.chbegin + 1) * ses, p.src.basetype) : 0.0f;
+        float b = inside ? ld_elem(sp + (p.chbegin + 2) * ses, p.src.basetype) : 0.0f;
+        float luma = __fadd_rn(__fadd_rn(__fmul_rn(0.21264f, r), __fmul_rn(0.71517f, g)),
+                               __fmul_rn(0.07219f, b));
+        scale = luma > 0.0f ? __fdiv_rn(dev_range<EXPAND>(luma), luma) : 0.0f;
+    }
+    for (int c = p.chbegin; c < p.chend; ++c) {
+        float v = inside ? ld_elem(sp + c * ses, p.src.basetype) : 0.0f;
+        if (c == p.alpha_channel || c == p.z_channel) {
+            if (p.in_place)
+                continue;
+        } else if (p.useluma) {
+            v = __fmul_rn(v, scale);
+        } else {
+            v = dev_range<EXPAND>(v);
+        }
+        st_elem(dp + c * des, p.dst.basetype, v);
+    }
+}
+
+// contiguous float rows, no luma: one thread per 4 elements
+template<bool EXPAND>
+__global__ void __launch_bounds__(256)
+range_f32_vec4_kernel(float* dst, long long dst_ystride, const float* src,
+                      long long src_ystride, int row_vec4, int nch, int alpha, int z)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= row_vec4)
+        return;
+    const float4 v = reinterpret_cast<const float4*>(
+        (const unsigned char*)src + blockIdx.y * src_ystride)[i];
+    float o[4] = { v.x, v.y, v.z, v.w };
+    int c = (4 * i) % nch;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (c != alpha && c != z)
+            o[k] = dev_range<EXPAND>(o[k]);
+        c = (c + 1 == nch) ? 0 : c + 1;
+    }
+    reinterpret_cast<float4*>((unsigned char*)dst + blockIdx.y * dst_ystride)[i]
+        = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+}  // namespace
+
+void
+launch_range(const RangeParams& p, void* stream)
+{
+    const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
+    if (w <= 0 || h <= 0 || p.chend <= p.chbegin)
+        return;
+    cudaStream_t st = (cudaStream_t)stream;
+    // fast path: whole-pixel float rows, every channel, both sides 16-byte aligned
+    const int nch = p.dst.nchannels;
+    const bool vec = !p.useluma && p.dst.basetype == BT_FLOAT && p.src.basetype == BT_FLOAT
+                     && p.src.nchannels == nch && p.chbegin == 0 && p.chend == nch
+                     && p.dst.xstride == 4LL * nch && p.src.xstride == 4LL * nch
+                     && (w * nch) % 4 == 0 && p.roi_x0 >= p.src.x
+                     && p.roi_x1 <= p.src.x + p.src.width && p.roi_y0 >= p.src.y
+                     && p.roi_y1 <= p.src.y + p.src.height && h <= 65535;
+    if (vec) {
+        float* d = (float*)((unsigned char*)p.dst.pixels
+                            + (long long)(p.roi_y0 - p.dst.y) * p.dst.ystride
+                            + (long long)(p.roi_x0 - p.dst.x) * p.dst.xstride);
+        const float* s = (const float*)((const unsigned char*)p.src.pixels
+                                        + (long long)(p.roi_y0 - p.src.y) * p.src.ystride
+                                        + (long long)(p.roi_x0 - p.src.x) * p.src.xstride);
+        if (((uintptr_t)d | (uintptr_t)s | (uintptr_t)p.dst.ystride | (uintptr_t)p.src.ystride)
+                % 16
+            == 0) {
+            const int n4 = w * nch / 4;
+            dim3 grid((n4 + 255) / 256, h);
+            if (p.expand)
+                range_f32_vec4_kernel<true><<<grid, 256, 0, st>>>(
+                    d, p.dst.ystride, s, p.src.ystride, n4, nch, p.alpha_channel, p.z_channel);
+            else
+                range_f32_vec4_kernel<false><<<grid, 256, 0, st>>>(
+                    d, p.dst.ystride, s, p.src.ystride, n4, nch, p.alpha_channel, p.z_channel);
+            return;
+        }
+    }
+    for (int y0 = 0; y0 < h; y0 += 65535) {
+        RangeParams q = p;
+        q.roi_y0      = p.roi_y0 + y0;
+        q.roi_y1      = std::min(p.roi_y1, q.roi_y0 + 65535);
+        dim3 grid((w + 255) / 256, q.roi_y1 - q.roi_y0);
+        if (p.expand)
+            range_kernel<true><<<grid, 256, 0, st>>>(q);
+        else
+            range_kernel<false><<<grid, 256, 0, st>>>(q);
+    }
+}
+
 void
 launch_clamp(float* pixels, long long n, int nch, int alpha, float lo, float hi,
              void* stream)

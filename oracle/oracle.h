@@ -9,6 +9,7 @@
  *   - the 17 known-answer images testsuite/filters/ref/<filter>.exr,
  *   - testsuite/oiiotool-xform/ref/{resize,resize2,resize64,resize512}.tif,
  *     resized-offset.exr, fit*.tif, resample*.tif,
+ *   - testsuite/oiiotool/ref/range{compress,expand}{,-luma}.tif,
  *   - the reference's own src/libutil/filter.cpp object code compiled
  *     unmodified into oracle/_ref/ (bit-exact weight comparison),
  * see tests/test_oracle_golden.py and tests/golden/make_golden.py.
@@ -72,6 +73,16 @@ void orc_fit_geometry(int src_full_w, int src_full_h, int fit_w, int fit_h,
  * dst/src are float, same nchannels.  */
 int orc_resize_block(const orc_image* dst, const orc_image* src,
                      int envlatlmode, int allow_shift, int nthreads);
+
+/* ImageBufAlgo::rangecompress / rangeexpand restated
+ * (imagebufalgo_pixelmath.cpp:560-735).  alpha_channel / z_channel: -1 = none.
+ * Pinned against testsuite/oiiotool/ref/range{compress,expand}{,-luma}.tif. */
+int orc_rangecompress(const orc_image* dst, const orc_image* src, int useluma,
+                      int alpha_channel, int z_channel, orc_roi roi, int chbegin,
+                      int chend);
+int orc_rangeexpand(const orc_image* dst, const orc_image* src, int useluma,
+                    int alpha_channel, int z_channel, orc_roi roi, int chbegin,
+                    int chend);
 
 /* float -> dst-type store and src-type -> float load used by the above
  * (fmath.h:753-764, 1009-1031); exposed for unit tests. */

@@ -1,0 +1,116 @@
+// oracle_pixelmath.cpp -- CPU restatement of ImageBufAlgo::rangecompress /
+// rangeexpand (src/libOpenImageIO/imagebufalgo_pixelmath.cpp:560-735).
+//
+// TEST INFRASTRUCTURE ONLY (see oracle.h).  Pinned against
+// testsuite/oiiotool/ref/{rangecompress,rangeexpand}{,-luma}.tif
+// (tests/golden/pixelmath_ref.npz, tests/test_cpu.py).
+#include "oracle.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+// pixelmath.cpp:560-575
+inline float
+rangecompress(float x)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absx = fabsf(x);
+    if (absx <= x1)
+        return x;
+    return copysignf(a + b * logf(fabsf(c * absx + 1.0f)), x);
+}
+
+// pixelmath.cpp:580-603
+inline float
+rangeexpand(float y)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absy = fabsf(y);
+    if (absy <= x1)
+        return y;
+    float xIntermediate = expf((absy - a) / b);
+    float x             = (xIntermediate - 1.0f) / c;
+    if (x < x1)
+        x = (-xIntermediate - 1.0f) / c;
+    return copysignf(x, y);
+}
+
+int
+esize(int bt)
+{
+    return bt == ORC_UINT8 ? 1 : (bt == ORC_FLOAT ? 4 : 2);
+}
+
+// rangecompress_ / rangeexpand_ (:607-735); both branches (in place or not)
+// give the same pixels, the copy of the alpha / z channels aside.
+int
+range_op(bool expand, const orc_image* dst, const orc_image* src, int useluma,
+         int alpha_channel, int z_channel, orc_roi roi, int chbegin, int chend)
+{
+    if (!dst || !src || !dst->pixels || !src->pixels)
+        return 1;
+    chend = std::min(chend, std::min(dst->nchannels, src->nchannels));
+    if (chend - chbegin < 3 || (alpha_channel >= chbegin && alpha_channel < chbegin + 3)
+        || (z_channel >= chbegin && z_channel < chbegin + 3))
+        useluma = 0;
+    const bool in_place = dst->pixels == src->pixels;
+    const int ses = esize(src->basetype), des = esize(dst->basetype);
+    for (int y = roi.ybegin; y < roi.yend; ++y) {
+        for (int x = roi.xbegin; x < roi.xend; ++x) {
+            if (x < dst->x || x >= dst->x + dst->width || y < dst->y
+                || y >= dst->y + dst->height)
+                continue;
+            unsigned char* dp = (unsigned char*)dst->pixels + (y - dst->y) * dst->ystride
+                                + (x - dst->x) * dst->xstride;
+            const bool inside = x >= src->x && x < src->x + src->width && y >= src->y
+                                && y < src->y + src->height;
+            const unsigned char* sp = (const unsigned char*)src->pixels
+                                      + (y - src->y) * src->ystride
+                                      + (x - src->x) * src->xstride;
+            auto a = [&](int c) {
+                return inside ? orc_load_as_float(sp + c * ses, src->basetype) : 0.0f;
+            };
+            float scale = 0.0f;
+            if (useluma) {
+                float luma = 0.21264f * a(chbegin) + 0.71517f * a(chbegin + 1)
+                             + 0.07219f * a(chbegin + 2);
+                scale = luma > 0.0f
+                            ? (expand ? rangeexpand(luma) : rangecompress(luma)) / luma
+                            : 0.0f;
+            }
+            for (int c = chbegin; c < chend; ++c) {
+                float v = a(c);
+                if (c == alpha_channel || c == z_channel) {
+                    if (in_place)
+                        continue;
+                } else if (useluma) {
+                    v = v * scale;
+                } else {
+                    v = expand ? rangeexpand(v) : rangecompress(v);
+                }
+                orc_store_from_float(dp + c * des, dst->basetype, v);
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int
+orc_rangecompress(const orc_image* dst, const orc_image* src, int useluma,
+                  int alpha_channel, int z_channel, orc_roi roi, int chbegin, int chend)
+{
+    return range_op(false, dst, src, useluma, alpha_channel, z_channel, roi, chbegin, chend);
+}
+
+extern "C" int
+orc_rangeexpand(const orc_image* dst, const orc_image* src, int useluma, int alpha_channel,
+                int z_channel, orc_roi roi, int chbegin, int chend)
+{
+    return range_op(true, dst, src, useluma, alpha_channel, z_channel, roi, chbegin, chend);
+}

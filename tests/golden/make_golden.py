@@ -16,6 +16,7 @@ Sources (all under /root/reference/testsuite, OpenImageIO 3.2.0.2-dev):
   oiiotool-xform/ref/resized-offset.exr  nonzero origin, half
   oiiotool-xform/ref/resample.tif, resample-nearest.tif   --resample 128x128
   oiiotool-xform/ref/fit.tif, fit2.tif, fit3.tif           --fit
+  common/tahoe-small.tif + oiiotool/ref/range{compress,expand}{,-luma}.tif
 Only pixel arrays are stored (no reference source code is copied).
 """
 import os
@@ -70,6 +71,16 @@ def main():
     for k, v in x.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(os.path.join(HERE, "xform_ref.npz"), **x)
+
+    # rangecompress / rangeexpand known answers (testsuite/oiiotool/run.py:28-32)
+    pm = {"tahoe_small": read(os.path.join(REF, "common/tahoe-small.tif"))}
+    for name in ["rangecompress", "rangeexpand", "rangecompress-luma",
+                 "rangeexpand-luma"]:
+        pm[name.replace("-", "_")] = read(os.path.join(REF, "oiiotool/ref",
+                                                       name + ".tif"))
+    for k, v in pm.items():
+        print(k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(HERE, "pixelmath_ref.npz"), **pm)
 
 
 if __name__ == "__main__":

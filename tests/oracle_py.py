@@ -72,6 +72,10 @@ def lib():
         L.orc_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
             [C.POINTER(C.c_int)] * 4
         L.orc_load_as_float.restype = C.c_float
+        for fn in (L.orc_rangecompress, L.orc_rangeexpand):
+            fn.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage), C.c_int,
+                           C.c_int, C.c_int, OrcRoi, C.c_int, C.c_int]
+            fn.restype = C.c_int
         L.orc_load_as_float.argtypes = [C.c_void_p, C.c_int]
         L.orc_store_from_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
         _lib = L
@@ -158,6 +162,31 @@ def resample(dst, src, interpolate=True, roi=None, nthreads=0):
     return dst
 
 
+def _range(fn, dst, src, useluma, alpha_channel, z_channel, roi, chrange):
+    d, s = dst.c(), src.c()
+    if roi is None:
+        roi = (dst.x, dst.x + dst.arr.shape[1], dst.y, dst.y + dst.arr.shape[0])
+    ch0, ch1 = chrange if chrange else (0, dst.arr.shape[2])
+    rc = fn(C.byref(d), C.byref(s), int(bool(useluma)), int(alpha_channel),
+            int(z_channel), OrcRoi(*roi), int(ch0), int(ch1))
+    if rc:
+        raise RuntimeError("oracle range op failed")
+    return dst
+
+
+def rangecompress(dst, src, useluma=False, alpha_channel=-1, z_channel=-1,
+                  roi=None, chrange=None):
+    """dst, src: Img (may wrap the same array: in place)."""
+    return _range(lib().orc_rangecompress, dst, src, useluma, alpha_channel,
+                  z_channel, roi, chrange)
+
+
+def rangeexpand(dst, src, useluma=False, alpha_channel=-1, z_channel=-1,
+                roi=None, chrange=None):
+    return _range(lib().orc_rangeexpand, dst, src, useluma, alpha_channel,
+                  z_channel, roi, chrange)
+
+
 def resize_block(dst, src, allow_shift=False):
     L = lib()
     d, s = dst.c(), src.c()
@@ -174,12 +203,14 @@ def fit_geometry(sw, sh, fw, fh, fillmode="letterbox"):
     return tuple(i.value for i in v)
 
 
-def mip_chain(level0, filtername="box"):
+def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1):
     """write_mipmap level loop (maketexture.cpp:823-986) on a float32 HxWxC
-    array, no file output.  Returns [level1, level2, ...]."""
+    array, no file output.  Returns [level1, level2, ...].  highlightcomp:
+    maketx --hicomp, rangecompress(img) / rangeexpand(small) around every
+    filtered level (:907-935)."""
     assert level0.dtype == np.float32
     out = []
-    img = level0
+    img = level0.copy() if highlightcomp else level0
     while img.shape[1] > 1 or img.shape[0] > 1:
         h, w, c = img.shape
         sw = w // 2 if w > 1 else w
@@ -188,9 +219,15 @@ def mip_chain(level0, filtername="box"):
         if filtername == "box":
             resize_block(Img(small), Img(img))
         else:
+            if highlightcomp:
+                rangecompress(Img(img), Img(img), alpha_channel=alpha_channel)
             resize(Img(small), Img(img), filtername)
+            if highlightcomp:
+                rangeexpand(Img(small), Img(small), alpha_channel=alpha_channel)
         out.append(small)
-        img = small
+        # the reference compresses img in place AFTER the level was written
+        # to the file: keep the returned level intact
+        img = small.copy() if highlightcomp else small
     return out
 
 

@@ -78,6 +78,38 @@ def test_oracle_resized_offset_golden(oracle):
     assert np.abs(dst.astype(np.float16).astype(np.float32) - g).max() == 0.0
 
 
+def test_oracle_rangecompress_goldens(oracle):
+    """testsuite/oiiotool/ref/range{compress,expand}{,-luma}.tif: oiiotool reads
+    the uint8 input as float, applies the op and writes uint8 (run.py:28-32)."""
+    G = np.load(os.path.join(GOLD, "pixelmath_ref.npz"))
+
+    def run(fn, u8, luma):
+        f = u8.astype(np.float32) * np.float32(1 / 255.0)
+        out = np.empty_like(f)
+        fn(oracle.Img(out), oracle.Img(f), useluma=luma)
+        return oracle.quantize(out, np.uint8)
+
+    for luma, sfx in ((False, ""), (True, "_luma")):
+        c = run(oracle.rangecompress, G["tahoe_small"], luma)
+        assert np.array_equal(c, G["rangecompress" + sfx]), "rangecompress" + sfx
+        e = run(oracle.rangeexpand, G["rangecompress" + sfx], luma)
+        assert np.array_equal(e, G["rangeexpand" + sfx]), "rangeexpand" + sfx
+    # in place, alpha left alone, luma refused when alpha is among the first three
+    a = np.linspace(-2, 6, 4 * 5 * 7, dtype=np.float32).reshape(5, 7, 4)
+    b = a.copy()
+    oracle.rangecompress(oracle.Img(b), oracle.Img(b), useluma=True, alpha_channel=3)
+    assert np.array_equal(b[..., 3], a[..., 3]) and not np.array_equal(b[..., :3], a[..., :3])
+    c = a.copy()
+    oracle.rangecompress(oracle.Img(c), oracle.Img(c), useluma=True, alpha_channel=1)
+    d = a.copy()
+    oracle.rangecompress(oracle.Img(d), oracle.Img(d), useluma=False, alpha_channel=1)
+    assert np.array_equal(c, d)
+    # expand undoes compress to float precision
+    e = np.empty_like(a)
+    oracle.rangeexpand(oracle.Img(e), oracle.Img(d), alpha_channel=1)
+    assert np.allclose(e, a, rtol=2e-5, atol=1e-6)
+
+
 def _ref_eval(R, name, w, h, mode, xs):
     out = np.empty_like(xs)
     sep = C.c_int()

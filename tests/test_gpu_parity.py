@@ -522,3 +522,139 @@ def test_non_native_type_pairs_go_through_float(oiio, oracle, dt, st):
     assert oiio.ImageBufAlgo.resample(oiio.ImageBuf(out), oiio.ImageBuf(src),
                                       interpolate=False)
     check(out, oracle.quantize(tmp, dt), exact=True)
+
+
+# ---- rangecompress / rangeexpand and highlight compensation ---------------
+def _range_both(oiio, oracle, fn, src, dst_dtype, useluma, alpha, roi=None,
+                chrange=None, prefill=None):
+    h, w, c = src.shape
+    g = np.zeros((h, w, c), dst_dtype) if prefill is None else prefill.copy()
+    o = g.copy()
+    getattr(oracle, fn)(oracle.Img(o), oracle.Img(src), useluma=useluma,
+                        alpha_channel=alpha, roi=roi, chrange=chrange)
+    S, D = oiio.ImageBuf(src), oiio.ImageBuf(g)
+    S.spec().alpha_channel = alpha
+    r = None
+    if roi or chrange:
+        x0, x1, y0, y1 = roi if roi else (0, w, 0, h)
+        c0, c1 = chrange if chrange else (0, c)
+        r = oiio.ROI(x0, x1, y0, y1, 0, 1, c0, c1)
+    ok = getattr(oiio.ImageBufAlgo, fn)(D, S, useluma=useluma, roi=r)
+    assert ok, D.geterror()
+    return g, o
+
+
+@pytest.mark.parametrize("fn", ["rangecompress", "rangeexpand"])
+@pytest.mark.parametrize("dt,st", [("float", "float"), ("uint8", "uint8"),
+                                   ("half", "float"), ("uint16", "half"),
+                                   ("float", "uint16")])
+def test_range_kernels(oiio, oracle, fn, dt, st):
+    """logf / expf are the device's: float results to 2e-6 of the value range,
+    integers +-1 LSB."""
+    for nch, alpha, luma in [(4, 3, False), (4, 3, True), (3, -1, True),
+                             (3, 1, True), (1, -1, False), (5, 4, False)]:
+        src = synth.image(67, 41, nch, _np_dtype(st), seed=90 + nch)
+        if st == "float":
+            src = (src * np.float32(8.0) - np.float32(2.0)).astype(np.float32)
+            if fn == "rangeexpand":
+                src = (src * np.float32(0.25)).astype(np.float32)
+        g, o = _range_both(oiio, oracle, fn, src, _np_dtype(dt), luma, alpha)
+        if g.dtype in (np.uint8, np.uint16):
+            assert np.abs(g.astype(int) - o.astype(int)).max() <= 1
+        else:
+            fin = np.isfinite(o.astype(np.float64))
+            assert np.array_equal(fin, np.isfinite(g.astype(np.float64)))
+            scale = max(1.0, np.abs(o[fin]).astype(np.float64).max())
+            tol = 2e-6 if g.dtype == np.float32 else 2.0 ** -10
+            assert np.abs(g[fin].astype(np.float64) - o[fin]).max() <= tol * scale
+
+
+def test_range_roi_channels_inplace_and_goldens(oiio, oracle):
+    src = (synth.image(50, 30, 4, np.float32, seed=95) * np.float32(5)).astype(np.float32)
+    pre = synth.image(50, 30, 4, np.float32, seed=96)
+    g, o = _range_both(oiio, oracle, "rangecompress", src, np.float32, False, 3,
+                       roi=(5, 44, 3, 21), chrange=(1, 3), prefill=pre)
+    assert np.abs(g - o).max() <= 2e-6 * 5
+    assert np.array_equal(g[:3], pre[:3]) and np.array_equal(g[..., 0], pre[..., 0])
+    # in place on a device tensor: alpha untouched
+    import torch
+    t = torch.from_numpy(src).cuda()
+    T = oiio.ImageBuf(t)
+    assert oiio.ImageBufAlgo.rangecompress(T, T)
+    o2 = src.copy()
+    oracle.rangecompress(oracle.Img(o2), oracle.Img(o2), alpha_channel=3)
+    g2 = t.cpu().numpy()
+    assert np.array_equal(g2[..., 3], src[..., 3])
+    assert np.abs(g2 - o2).max() <= 2e-6 * 5
+    # the reference's known-answer images (oiiotool reads uint8 as float)
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "pixelmath_ref.npz"))
+    f = G["tahoe_small"].astype(np.float32) * np.float32(1 / 255.0)
+    for luma, sfx in ((False, ""), (True, "_luma")):
+        d = np.zeros(f.shape, np.uint8)
+        D, S = oiio.ImageBuf(d), oiio.ImageBuf(f)
+        assert oiio.ImageBufAlgo.rangecompress(D, S, useluma=luma)
+        assert np.abs(d.astype(int) - G["rangecompress" + sfx].astype(int)).max() <= 1
+        assert (d != G["rangecompress" + sfx]).mean() < 1e-3
+        f2 = G["rangecompress" + sfx].astype(np.float32) * np.float32(1 / 255.0)
+        d2 = np.zeros(f.shape, np.uint8)
+        assert oiio.ImageBufAlgo.rangeexpand(oiio.ImageBuf(d2), oiio.ImageBuf(f2),
+                                             useluma=luma)
+        assert np.abs(d2.astype(int) - G["rangeexpand" + sfx].astype(int)).max() <= 1
+        assert (d2 != G["rangeexpand" + sfx]).mean() < 1e-3
+
+
+@pytest.mark.parametrize("dt,st,nch", [("float", "float", 4), ("half", "half", 4),
+                                       ("uint8", "uint8", 3), ("float", "float", 3)])
+def test_resize_highlightcomp(oiio, oracle, dt, st, nch):
+    """oiiotool --resize:highlightcomp=1 (oiiotool.cpp:4644-4663): compress into
+    a temporary of the source type, resize, expand the result in place."""
+    src = synth.image(120, 90, nch, _np_dtype(st), seed=101)
+    if st in ("float", "half"):
+        src = (src.astype(np.float32) ** 4 * 40).astype(_np_dtype(st))  # HDR highlights
+    alpha = 3 if nch == 4 else -1
+    for shape in [(45, 60), (200, 260)]:
+        tmp = src.copy()
+        oracle.rangecompress(oracle.Img(tmp), oracle.Img(src), alpha_channel=alpha)
+        o = np.zeros(shape + (nch,), _np_dtype(dt))
+        oracle.resize(oracle.Img(o), oracle.Img(tmp), "lanczos3")
+        oracle.rangeexpand(oracle.Img(o), oracle.Img(o), alpha_channel=alpha)
+        g = np.zeros_like(o)
+        D, S = oiio.ImageBuf(g), oiio.ImageBuf(src)
+        S.spec().alpha_channel = alpha
+        assert oiio.ImageBufAlgo.resize(D, S, filtername="lanczos3",
+                                        highlightcomp=True), D.geterror()
+        if g.dtype == np.uint8:
+            # the resize's +-1 LSB sits under rangeexpand, whose slope reaches
+            # x/b = 5.4 at the top of the range: a handful of pixels move by up
+            # to 6 LSB there, the rest agree
+            d = np.abs(g.astype(int) - o.astype(int))
+            assert d.max() <= 6 and (d > 0).mean() < 2e-3
+        else:
+            # expf amplifies the resize's 1e-6 by 1/b = 5.4: 5e-5 of the range
+            scale = max(1.0, float(np.abs(o.astype(np.float64)).max()))
+            tol = 5e-5 if g.dtype == np.float32 else 2.0 ** -9
+            assert np.abs(g.astype(np.float64) - o.astype(np.float64)).max() <= tol * scale
+        # and it differs from the plain resize (the option is not ignored)
+        p = np.zeros_like(o)
+        assert oiio.ImageBufAlgo.resize(oiio.ImageBuf(p), S, filtername="lanczos3")
+        if st != "uint8":
+            assert np.abs(p.astype(np.float64) - g.astype(np.float64)).max() > 1e-3
+
+
+def test_mip_chain_highlightcomp(oiio, oracle):
+    lvl0 = (synth.image(96, 64, 4, np.float32, seed=111) ** 4 * np.float32(30)).astype(np.float32)
+    ref = oracle.mip_chain(lvl0, "lanczos3", highlightcomp=True, alpha_channel=3)
+    chain = oiio.MipChain(lvl0, "lanczos3", highlightcomp=True)
+    assert chain.nlevels == len(ref) + 1
+    # level 0 is left intact on the device
+    assert np.array_equal(chain.download(0), lvl0)
+    for i, r in enumerate(ref):
+        g = chain.download(i + 1)
+        scale = max(1.0, float(np.abs(r).max()))
+        assert np.abs(g - r).max() <= 5e-5 * (i + 1) * scale, "level %d" % (i + 1)
+    # box chains ignore the option, as maketx does
+    a = oiio.MipChain(lvl0, "box", highlightcomp=True).download(1)
+    b = oiio.MipChain(lvl0, "box").download(1)
+    assert np.array_equal(a, b)
