@@ -67,6 +67,7 @@ struct ImageSpec {
     int nchannels = 0;
     TypeDesc format;
     int alpha_channel = -1;
+    int z_channel     = -1;
     bool deep = false;
     ImageSpec() {}
     ImageSpec(int w, int h, int nch, TypeDesc fmt = TypeDesc::FLOAT)
@@ -313,6 +314,63 @@ resize(const ImageBuf& src, const KWArgs& options = {}, ROI roi = {}, int nthrea
     bool ok = resize(result, src, options, roi, nthreads);
     if (!ok && !result.has_error())
         result.error("ImageBufAlgo::resize() error");
+    return result;
+}
+
+/// ImageBufAlgo::rangecompress / rangeexpand --
+/// imagebufalgo_pixelmath.cpp:748-774 (IBAprep_CLAMP_MUTUAL_NCHANNELS).
+namespace detail {
+inline bool
+range_op(bool expand, ImageBuf& dst, const ImageBuf& src, bool useluma, ROI roi)
+{
+    if (!prep(roi, dst, src))
+        return false;
+    roi.chend = std::min(roi.chend, std::min(dst.nchannels(), src.nchannels()));
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r { roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend };
+    char err[512] = "";
+    int rc = (expand ? b2r_rangeexpand : b2r_rangecompress)(
+        &d, &s, useluma ? 1 : 0, src.spec().alpha_channel, src.spec().z_channel, &r,
+        nullptr, nullptr, err, sizeof(err));
+    if (rc) {
+        dst.error(err);
+        return false;
+    }
+    return true;
+}
+}  // namespace detail
+
+inline bool
+rangecompress(ImageBuf& dst, const ImageBuf& src, bool useluma = false, ROI roi = {},
+              int /*nthreads*/ = 0)
+{
+    return detail::range_op(false, dst, src, useluma, roi);
+}
+
+inline bool
+rangeexpand(ImageBuf& dst, const ImageBuf& src, bool useluma = false, ROI roi = {},
+            int /*nthreads*/ = 0)
+{
+    return detail::range_op(true, dst, src, useluma, roi);
+}
+
+inline ImageBuf
+rangecompress(const ImageBuf& src, bool useluma = false, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = rangecompress(result, src, useluma, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::rangecompress() error");
+    return result;
+}
+
+inline ImageBuf
+rangeexpand(const ImageBuf& src, bool useluma = false, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = rangeexpand(result, src, useluma, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::rangeexpand() error");
     return result;
 }
 

@@ -4,6 +4,8 @@
 //   ImageBufAlgo::resize(dst, src, {{"filtername", f}}, roi);
 // usage: iba_cli errors
 //        iba_cli resize in.raw w h nch basetype dw dh filter out.raw
+//        iba_cli hicomp in.raw w h nch basetype dw dh filter out.raw
+//            (oiiotool --resize:highlightcomp=1 spelled with three IBA calls)
 #include "b2r_imagebufalgo.h"
 
 #include <cstdio>
@@ -42,7 +44,8 @@ main(int argc, char** argv)
 {
     if (argc >= 2 && std::string(argv[1]) == "errors")
         return run_errors();
-    if (argc != 11 || std::string(argv[1]) != "resize") {
+    const bool hicomp = argc >= 2 && std::string(argv[1]) == "hicomp";
+    if (argc != 11 || (std::string(argv[1]) != "resize" && !hicomp)) {
         fprintf(stderr, "usage: see source\n");
         return 2;
     }
@@ -55,8 +58,17 @@ main(int argc, char** argv)
         return 3;
     fclose(f);
     ImageBuf src(sspec, px.data(), B2R_MEM_HOST);
-    ImageBuf dst = ImageBufAlgo::resize(src, { { "filtername", argv[9] } },
+    ImageBuf tmpimg;
+    const ImageBuf* in = &src;
+    if (hicomp) {  // oiiotool.cpp:4644-4650
+        if (!ImageBufAlgo::rangecompress(tmpimg, src))
+            return 5;
+        in = &tmpimg;
+    }
+    ImageBuf dst = ImageBufAlgo::resize(*in, { { "filtername", argv[9] } },
                                         ROI(0, dw, 0, dh, 0, 1, 0, c));
+    if (hicomp && !dst.has_error() && !ImageBufAlgo::rangeexpand(dst, dst))
+        return 6;
     if (dst.has_error()) {
         fprintf(stderr, "%s\n", dst.geterror().c_str());
         return 4;

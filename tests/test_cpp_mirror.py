@@ -42,3 +42,29 @@ def test_cpp_resize_matches_oracle(iba_cli, oracle, tmp_path):
     ref = np.zeros_like(got)
     oracle.resize(oracle.Img(ref), oracle.Img(src), "lanczos3")
     assert np.abs(got - ref).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_cpp_highlightcomp_three_calls_equal_the_fused_option(iba_cli, oracle, oiio,
+                                                               tmp_path):
+    """rangecompress -> resize -> rangeexpand written as three ImageBufAlgo
+    calls (what oiiotool does, oiiotool.cpp:4644-4663) against the oracle, and
+    against the one-call `highlightcomp` option of the ABI."""
+    src = (synth.image(180, 120, 4, np.float32, seed=92) ** 4 * np.float32(25)
+           ).astype(np.float32)
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    src.tofile(fin)
+    subprocess.check_call([iba_cli, "hicomp", fin, "180", "120", "4", "11",
+                           "90", "60", "lanczos3", fout])
+    got = np.fromfile(fout, np.float32).reshape(60, 90, 4)
+    tmp = src.copy()
+    oracle.rangecompress(oracle.Img(tmp), oracle.Img(src), alpha_channel=3)
+    ref = np.zeros_like(got)
+    oracle.resize(oracle.Img(ref), oracle.Img(tmp), "lanczos3")
+    oracle.rangeexpand(oracle.Img(ref), oracle.Img(ref), alpha_channel=3)
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(got - ref).max() <= 5e-5 * scale
+    one = np.zeros_like(got)
+    assert oiio.ImageBufAlgo.resize(oiio.ImageBuf(one), oiio.ImageBuf(src),
+                                    filtername="lanczos3", highlightcomp=True)
+    assert np.array_equal(one, got)

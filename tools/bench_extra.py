@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Secondary measurements (not the bench.py contract): device-resident MIP
 chain (BASELINE config 4) and the other BASELINE configs' kernels.
-usage: bench_extra.py mip [size] [filter] | bench_extra.py cfg <c1|c2|c3|c5> [steps]"""
+usage: bench_extra.py mip [size] [filter] [hicomp]
+       bench_extra.py range        rangecompress / rangeexpand / highlightcomp resize, 8K RGBA f32"""
 import json
 import os
 import sys
@@ -13,14 +14,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def mip(size=16384, filt="box", reps=3):
+def mip(size=16384, filt="box", reps=3, hicomp=False):
     import torch
     import openimageio_b200 as oiio
     g = torch.Generator(device="cuda").manual_seed(1)
     lvl0 = torch.rand((size, size, 4), dtype=torch.float32, device="cuda", generator=g)
     best = None
     for _ in range(reps):
-        chain = oiio.MipChain(oiio.ImageBuf(lvl0), filt)
+        chain = oiio.MipChain(oiio.ImageBuf(lvl0), filt, highlightcomp=hicomp)
         ms = chain.kernel_ms
         n = chain.nlevels
         del chain
@@ -28,12 +29,54 @@ def mip(size=16384, filt="box", reps=3):
     px = sum(max(1, size >> l) ** 2 for l in range(1, n))
     rd = sum(max(1, size >> l) ** 2 for l in range(0, n - 1)) * 16
     wr = px * 16
-    print(json.dumps({"workload": "mip %dx%d RGBA f32 %s" % (size, size, filt),
+    print(json.dumps({"workload": "mip %dx%d RGBA f32 %s%s" % (size, size, filt,
+                                                                " hicomp" if hicomp else ""),
                       "levels": n, "ms": best, "out_Mpix_s": px / best / 1e3,
                       "algorithmic_GBs": (rd + wr) / best / 1e6}))
+
+
+def _time(fn, steps=20, warmup=3):
+    import torch
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def range_ops():
+    """Streaming point ops: algorithmic bytes = read src + write dst."""
+    import torch
+    import openimageio_b200 as oiio
+    w, h = 7680, 4320
+    g = torch.Generator(device="cuda").manual_seed(2)
+    src = torch.rand((h, w, 4), dtype=torch.float32, device="cuda", generator=g) * 8
+    dst = torch.empty_like(src)
+    S, D = oiio.ImageBuf(src), oiio.ImageBuf(dst)
+    for name in ("rangecompress", "rangeexpand"):
+        fn = getattr(oiio.ImageBufAlgo, name)
+        for luma in (False, True):
+            ms = _time(lambda: fn(D, S, useluma=luma))
+            print(json.dumps({"workload": "%s 8K RGBA f32 luma=%d" % (name, luma),
+                              "ms": ms, "algorithmic_GBs": 2 * src.numel() * 4 / ms / 1e6}))
+    small = torch.empty((h // 2, w // 2, 4), dtype=torch.float32, device="cuda")
+    R = oiio.ImageBuf(small)
+    for hc in (False, True):
+        ms = _time(lambda: oiio.ImageBufAlgo.resize(R, S, filtername="lanczos3",
+                                                    highlightcomp=hc))
+        print(json.dumps({"workload": "8K->4K lanczos3 RGBA f32 highlightcomp=%d" % hc,
+                          "ms": ms}))
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "mip":
         mip(int(sys.argv[2]) if len(sys.argv) > 2 else 16384,
-            sys.argv[3] if len(sys.argv) > 3 else "box")
+            sys.argv[3] if len(sys.argv) > 3 else "box",
+            hicomp=len(sys.argv) > 4 and sys.argv[4] == "hicomp")
+    elif sys.argv[1] == "range":
+        range_ops()
