@@ -485,14 +485,15 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         const unsigned char* gnext = p.src + (size_t)e * es
                                      + (long long)band.r0 * p.src_ystride;
         int rnext     = band.r0;
-        int slot_next = 0;
+        // In steady state the FIFO is full: a fetch goes into the slot the
+        // previous pop freed, so one walking index serves both ends.
+        int slot_free = 0;
         auto issue_next = [&]() {
             if (vfetch && rnext < rend)
-                cp_async_copy<4 * es>(fifo_s + slot_next, gnext);
+                cp_async_copy<4 * es>(fifo_s + slot_free, gnext);
             cp_async_commit();
             gnext += p.src_ystride;
             ++rnext;
-            slot_next = (slot_next + SLOT) & (FUSED_FIFO * SLOT - 1);
         };
         int slot_cur = 0;
         auto fifo_pop = [&]() -> uint4 {
@@ -505,7 +506,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
             } else {
                 raw = make_uint4(lds_u32(fifo_s + slot_cur), 0u, 0u, 0u);
             }
-            slot_cur = (slot_cur + SLOT) & (FUSED_FIFO * SLOT - 1);
+            slot_free = slot_cur;
+            slot_cur  = (slot_cur + SLOT) & (FUSED_FIFO * SLOT - 1);
             return raw;
         };
         // one source row: scatter it into the VK open destination rows
@@ -561,8 +563,10 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                         *reinterpret_cast<unsigned*>(fifo + tid * TB + q * SLOT) = 0u;
             }
 #pragma unroll
-            for (int q = 0; q < FUSED_FIFO; ++q)
+            for (int q = 0; q < FUSED_FIFO; ++q) {
+                slot_free = q * SLOT;
                 issue_next();
+            }
             cp_async_wait<FUSED_FIFO - 1>();  // first row landed
             uint4 rawA = fifo_pop(), rawB = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();  // ringw / lastr visible
