@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2)
 resize_expand_kernel(const FusedParams p, int max_band_dy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_prologue();
     constexpr int BATCH = EXPAND_BATCH;
     const int es        = (p.srctype == BT_UINT8) ? 1 : (p.srctype == BT_FLOAT ? 4 : 2);
     const int TB        = 4 * es;              // raw bytes per thread per row

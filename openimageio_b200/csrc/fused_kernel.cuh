@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
 resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    pdl_prologue();
     unsigned char* vrows  = smem_raw;
     constexpr int BATCH   = (VK == 6) ? 12 : 8;  // == fused_batch(VK), kernels.h
     constexpr int pitch_b = FUSED_PITCH_B;

@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
 
 namespace b2r {
 
@@ -80,9 +81,30 @@ dev_nonsep_filter(int kind, float fw, float fh, float x, float y)
 
 constexpr int EXACT_CH = 4;  // channels per thread
 
+// Launch with programmatic stream serialization allowed (see kernels.h).
+template<class... KArgs, class... Args>
+static void
+launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+           cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim          = grid;
+    cfg.blockDim         = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs    = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 __global__ void __launch_bounds__(128)
 resize_exact_kernel(ExactParams p)
 {
+    pdl_prologue();
     if (p.gate && *p.gate != p.gate_value)
         return;
     const int roi_w   = p.roi_x1 - p.roi_x0;
@@ -200,7 +222,7 @@ launch_resize_exact(const ExactParams& p, void* stream)
     const long long cap = p.gate ? 148 * 2 : 148 * 16;
     dim3 grid((unsigned)std::min<long long>(tiles, cap), 1,
               (p.nch + EXACT_CH - 1) / EXACT_CH);
-    resize_exact_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(p);
+    launch_pdl(resize_exact_kernel, grid, block, 0, (cudaStream_t)stream, p);
 }
 
 
@@ -329,7 +351,7 @@ launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
             cudaFuncSetAttribute((const void*)k,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         dim3 grid(p.nstrips, p.nbands, 1);
-        k<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p, max_band_dy);
+        launch_pdl(k, grid, dim3(FUSED_THREADS), smem, (cudaStream_t)stream, p, max_band_dy);
         return;
     }
     FusedKernel k = pick_fused(p.srctype, p.nch, p.vk, p.ht);
@@ -341,8 +363,8 @@ launch_resize_fused(const FusedParams& p, int max_band_rows, int max_band_dy,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem);
     dim3 grid(p.nstrips, p.nbands, 1);
-    k<<<grid, FUSED_THREADS, smem, (cudaStream_t)stream>>>(p, max_band_rows,
-                                                           max_band_dy);
+    launch_pdl(k, grid, dim3(FUSED_THREADS), smem, (cudaStream_t)stream, p, max_band_rows,
+               max_band_dy);
 }
 
 }  // namespace b2r

@@ -6,6 +6,24 @@
 
 namespace b2r {
 
+// Programmatic dependent launch (PDL): every resize kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+//     griddepcontrol.launch_dependents   -- the next kernel may be scheduled now
+//     griddepcontrol.wait                -- predecessor grids complete + flushed
+// so the launch latency and CTA ramp-up of kernel n+1 overlap the tail of
+// kernel n (the fused kernel and the gated exact kernel behind it, the levels
+// of a MIP chain, back-to-back frames).  No global memory is touched before
+// the wait.  Both instructions are no-ops in a kernel launched without the
+// attribute.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void
+pdl_prologue()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 enum : int { BT_UINT8 = 2, BT_UINT16 = 4, BT_HALF = 10, BT_FLOAT = 11 };
 
 inline int
