@@ -81,26 +81,6 @@ dev_nonsep_filter(int kind, float fw, float fh, float x, float y)
 
 constexpr int EXACT_CH = 4;  // channels per thread
 
-// Launch with programmatic stream serialization allowed (see kernels.h).
-template<class... KArgs, class... Args>
-static void
-launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-           cudaStream_t stream, Args... args)
-{
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim          = grid;
-    cfg.blockDim         = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream           = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs    = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
-
 __global__ void __launch_bounds__(128)
 resize_exact_kernel(ExactParams p)
 {

@@ -3,6 +3,9 @@
 #pragma once
 
 #include <cstdint>
+#if defined(__CUDACC__)
+#    include <cuda_runtime.h>
+#endif
 
 namespace b2r {
 
@@ -21,6 +24,25 @@ pdl_prologue()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Launch with programmatic stream serialization allowed.
+template<class... KArgs, class... Args>
+static inline void
+launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+           cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = grid;
+    cfg.blockDim           = block;
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs    = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
 

@@ -97,6 +97,7 @@ bilerp1(float v0, float v1, float v2, float v3, float s, float t)
 __global__ void __launch_bounds__(256)
 resample_kernel(ResampleParams p, int chbegin, int chend, bool vec4)
 {
+    pdl_prologue();
     // 2-D grid (rows in blockIdx.y, grid-strided): no 64-bit div/mod
     const int kx = blockIdx.x * blockDim.x + threadIdx.x;
     if (kx >= p.roi_x1 - p.roi_x0)
@@ -200,6 +201,7 @@ box2_kernel(const float* __restrict__ src, long long src_ystride_f,
             float* __restrict__ dst, long long dst_ystride_f, int dw, int dh,
             int nch)
 {
+    pdl_prologue();
     const long long row_elems = (long long)dw * nch;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= row_elems * dh)
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(256)
 box2_rgba_kernel(const float4* __restrict__ src, long long src_ystride_4,
                  float4* __restrict__ dst, long long dst_ystride_4, int dw, int dh)
 {
+    pdl_prologue();
     // 2-D grid: no 64-bit div/mod per thread (they dominated a 1-D version)
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= dw)
@@ -247,6 +250,7 @@ box2_rgba_kernel(const float4* __restrict__ src, long long src_ystride_4,
 __global__ void __launch_bounds__(256)
 box_bilinear_kernel(BoxParams p)
 {
+    pdl_prologue();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)p.dst.width * p.dst.height)
         return;
@@ -289,6 +293,7 @@ box_bilinear_kernel(BoxParams p)
 __global__ void __launch_bounds__(256)
 clamp_kernel(float* px, long long n, int nch, int alpha, float lo, float hi)
 {
+    pdl_prologue();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
@@ -315,6 +320,7 @@ convert_from_float_kernel(const float* __restrict__ src, long long src_ystride_f
                           unsigned char* __restrict__ dst, long long dst_ystride,
                           int row_elems, int h, int bt)
 {
+    pdl_prologue();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= row_elems)
         return;
@@ -334,7 +340,7 @@ launch_convert_from_float(const float* src, long long src_ystride_bytes, void* d
     if (row_elems <= 0 || height <= 0)
         return;
     dim3 grid((row_elems + 255) / 256, std::min(height, 32768), 1);
-    convert_from_float_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(convert_from_float_kernel, grid, dim3(256), 0, (cudaStream_t)stream,
         src, src_ystride_bytes / 4, (unsigned char*)dst, dst_ystride_bytes, row_elems,
         height, dst_basetype);
 }
@@ -352,7 +358,7 @@ launch_resample(const ResampleParams& p, int chbegin, int chend, void* stream)
                       && (uintptr_t)p.src.pixels % 16 == 0
                       && (uintptr_t)p.dst.pixels % 16 == 0 && p.src.ystride % 16 == 0
                       && p.dst.ystride % 16 == 0;
-    resample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, chbegin, chend, vec4);
+    launch_pdl(resample_kernel, grid, dim3(256), 0, (cudaStream_t)stream, p, chbegin, chend, vec4);
 }
 
 void
@@ -367,18 +373,18 @@ launch_box_downsample(const BoxParams& p, void* stream)
                           && D.ystride % 16 == 0;
         if (rgba) {
             dim3 grid((D.width + 255) / 256, std::min(D.height, 32768), 1);
-            box2_rgba_kernel<<<grid, 256, 0, st>>>(
+            launch_pdl(box2_rgba_kernel, grid, dim3(256), 0, st,
                 (const float4*)S.pixels, S.ystride / 16, (float4*)D.pixels,
                 D.ystride / 16, D.width, D.height);
         } else {
             long long n = (long long)D.width * D.nchannels * D.height;
-            box2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            launch_pdl(box2_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st,
                 (const float*)S.pixels, S.ystride / 4, (float*)D.pixels,
                 D.ystride / 4, D.width, D.height, D.nchannels);
         }
     } else {
         long long n = (long long)D.width * D.height;
-        box_bilinear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p);
+        launch_pdl(box_bilinear_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p);
     }
 }
 
@@ -427,6 +433,7 @@ template<bool EXPAND>
 __global__ void __launch_bounds__(256)
 range_kernel(const RangeParams p)
 {
+    pdl_prologue();
     const int w = p.roi_x1 - p.roi_x0;
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
@@ -471,6 +478,7 @@ __global__ void __launch_bounds__(256)
 range_f32_vec4_kernel(float* dst, long long dst_ystride, const float* src,
                       long long src_ystride, int row_vec4, int nch, int alpha, int z)
 {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= row_vec4)
         return;
@@ -518,10 +526,10 @@ launch_range(const RangeParams& p, void* stream)
             const int n4 = w * nch / 4;
             dim3 grid((n4 + 255) / 256, h);
             if (p.expand)
-                range_f32_vec4_kernel<true><<<grid, 256, 0, st>>>(
+                launch_pdl(range_f32_vec4_kernel<true>, grid, dim3(256), 0, st,
                     d, p.dst.ystride, s, p.src.ystride, n4, nch, p.alpha_channel, p.z_channel);
             else
-                range_f32_vec4_kernel<false><<<grid, 256, 0, st>>>(
+                launch_pdl(range_f32_vec4_kernel<false>, grid, dim3(256), 0, st,
                     d, p.dst.ystride, s, p.src.ystride, n4, nch, p.alpha_channel, p.z_channel);
             return;
         }
@@ -532,9 +540,9 @@ launch_range(const RangeParams& p, void* stream)
         q.roi_y1      = std::min(p.roi_y1, q.roi_y0 + 65535);
         dim3 grid((w + 255) / 256, q.roi_y1 - q.roi_y0);
         if (p.expand)
-            range_kernel<true><<<grid, 256, 0, st>>>(q);
+            launch_pdl(range_kernel<true>, grid, dim3(256), 0, st, q);
         else
-            range_kernel<false><<<grid, 256, 0, st>>>(q);
+            launch_pdl(range_kernel<false>, grid, dim3(256), 0, st, q);
     }
 }
 
@@ -544,7 +552,7 @@ launch_clamp(float* pixels, long long n, int nch, int alpha, float lo, float hi,
 {
     if (n <= 0)
         return;
-    clamp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(clamp_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
         pixels, n, nch, alpha, lo, hi);
 }
 
