@@ -405,17 +405,34 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
     const float2* hws = hws_all + hp;
     {
         const int gp = (strip.dx0 >> 1) + hp;  // pair index in the ROI
-        for (int j = hr; j < HT; j += FUSED_HROWG_MAX)
-            hws_all[j * FUSED_HPAIRS + hp]
-                = (2 * hp < strip.ndx) ? reinterpret_cast<const float2*>(p.hw)[(size_t)gp * HT + j]
-                              : make_float2(0.f, 0.f);
+        // ring mode: staged with cp.async (joins the group of the ring
+        // weights below, completes with the first FIFO row) so the table
+        // loads overlap the first source rows' latency
+        for (int j = hr; j < HT; j += FUSED_HROWG_MAX) {
+            const float2* g = reinterpret_cast<const float2*>(p.hw) + (size_t)gp * HT + j;
+            if (2 * hp >= strip.ndx)
+                hws_all[j * FUSED_HPAIRS + hp] = make_float2(0.f, 0.f);
+            else if (VK > 0)
+                cp_async_copy<8>(smem_u32(hws_all + j * FUSED_HPAIRS + hp), g);
+            else
+                hws_all[j * FUSED_HPAIRS + hp] = *g;
+        }
+    }
+    // the pair's window start: loaded here, used after the first source rows
+    // have been requested (see hb[] below)
+    int hfirst_v = 0;
+    if (pair_active)
+        asm volatile("ld.global.nc.s32 %0, [%1];"
+                     : "=r"(hfirst_v)
+                     : "l"(p.hfirst + (strip.dx0 >> 1) + hp));
+    auto finish_hb = [&]() {
         if (pair_active) {
-            const int q = p.hfirst[gp] - strip.e0 / NCH;  // window start in the strip
+            const int q = hfirst_v - strip.e0 / NCH;  // window start in the strip
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 hb[k] = planar_byte(q + k) + hr * pitch_b;
         }
-    }
+    };
 
     // ---- V-pass per-thread constants: this thread's 4 source elements ---
     const bool vactive  = tid < strip.nvec;
@@ -451,10 +468,11 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
 
         // stage this band's ring weights and completion rows
         const float* gw = p.vring + (size_t)band.woff * VKP;
-        for (int i = tid; i < band.nrows * VKP; i += FUSED_THREADS)
-            ringw[i] = gw[i];
+        for (int i = tid; i < band.nrows * (VKP / 4); i += FUSED_THREADS)
+            cp_async_copy<16>(smem_u32(ringw + 4 * i), gw + 4 * i);
         for (int i = tid; i < band.ndy; i += FUSED_THREADS)
-            lastr[i] = p.vlast[band.dy0 + i];
+            cp_async_copy<4>(smem_u32(lastr + i), p.vlast + band.dy0 + i);
+        cp_async_commit();  // hws + ringw + lastr: one group, older than every FIFO row
 
         float4 acc[VK];
 #pragma unroll
@@ -568,7 +586,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                 slot_free = q * SLOT;
                 issue_next();
             }
-            cp_async_wait<FUSED_FIFO - 1>();  // first row landed
+            finish_hb();
+            cp_async_wait<FUSED_FIFO - 1>();  // tables and first row landed
             uint4 rawA = fifo_pop(), rawB = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();  // ringw / lastr visible
             // Software pipeline: the row being accumulated was popped one
@@ -602,6 +621,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                 flush_if_full(min(dy + VK, dy_end));
             }
         } else {
+            finish_hb();
+            cp_async_wait<0>();
             __syncthreads();  // ringw / lastr visible
             for (int dy = band.dy0; dy < dy_end; dy += VK) {
 #pragma unroll
@@ -624,6 +645,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         }
         cp_async_wait<0>();
     } else {
+        finish_hb();
         // gather mode (upsizing): each dst row gathers its own vt source rows
         // through L1 (consecutive dst rows share rows).  A strip holds few
         // source pixels here, so the (row, group) items of a whole batch are
