@@ -325,16 +325,21 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
     const int gg    = (strip.dx0 >> 2) + tid;       // group index in the ROI
     int hb[HT];
     {
+        // tables are staged with cp.async (one group, committed before the
+        // first source rows are requested) so their latency overlaps
         const float4* gw = reinterpret_cast<const float4*>(p.hw);
 #pragma unroll
-        for (int j = 0; j < HT; ++j)
-            hws_all[j * EXPAND_GROUPS + tid]
-                = (ncols > 0) ? gw[(size_t)j * p.ngroups + gg] : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int q = (ncols > 0) ? p.hfirst[gg] - strip.e0 / NCH : 0;  // window start
-#pragma unroll
-        for (int j = 0; j < HT; ++j)
-            hb[j] = linear ? (q + j) * 16 : planar_byte(q + j);
+        for (int j = 0; j < HT; ++j) {
+            if (ncols > 0)
+                cp_async_copy<16>(smem_u32(hws_all + j * EXPAND_GROUPS + tid),
+                                  gw + (size_t)j * p.ngroups + gg);
+            else
+                hws_all[j * EXPAND_GROUPS + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
+    int hfirst_v = 0;
+    if (ncols > 0)
+        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(hfirst_v) : "l"(p.hfirst + gg));
     const float4* hws = hws_all + tid;
 
     // ---- V-pass constants: this thread's 4 source elements ---------------
@@ -365,13 +370,14 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
         for (int i = tid; i < BATCH * (FUSED_PITCH_B / 16); i += FUSED_THREADS)
             reinterpret_cast<uint4*>(vrows)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    // stage the band's V weights and (band-relative) first rows
+    // stage the band's V weights and first rows (VT is even: 8-byte copies)
     {
         const float* gw = p.vw + (size_t)band.dy0 * VT;
-        for (int i = tid; i < band.ndy * VT; i += FUSED_THREADS)
-            vws[i] = gw[i];
+        for (int i = tid; i < band.ndy * (VT / 2); i += FUSED_THREADS)
+            cp_async_copy<8>(smem_u32(vws + 2 * i), gw + 2 * i);
         for (int i = tid; i < band.ndy; i += FUSED_THREADS)
-            vfs[i] = p.vfirst[band.dy0 + i] - band.r0;
+            cp_async_copy<4>(smem_u32(vfs + i), p.vfirst + band.dy0 + i);
+        cp_async_commit();
     }
 
     // cp.async needs aligned global addresses and groups inside the row (see
@@ -405,7 +411,7 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
         ++rnext;
     };
     // next source row, converted to float
-    int loaded = 0;  // rows consumed so far (band-relative index of the next)
+    int loaded = band.r0;  // next source row to consume
     auto pop_row = [&]() -> float4 {
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (async_ok) {
@@ -419,7 +425,7 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
                 raw.x = lds_u32(fifo_s + slot_cur);
             slot_cur = (slot_cur + SLOT == EXPAND_FIFO * SLOT) ? 0 : slot_cur + SLOT;
         } else if (vactive) {
-            const unsigned char* rowp = p.src + (long long)(band.r0 + loaded) * p.src_ystride;
+            const unsigned char* rowp = p.src + (long long)loaded * p.src_ystride;
             if (p.srctype == BT_FLOAT)
                 raw = load_raw4<ST_FLOAT>(rowp, e, row_elems, false);
             else if (p.srctype == BT_HALF)
@@ -451,6 +457,15 @@ resize_expand_kernel(const FusedParams p, int max_band_dy)
 #pragma unroll
         for (int q = 0; q < EXPAND_FIFO; ++q)
             issue_next();
+        cp_async_wait<EXPAND_FIFO>();  // the table group; source rows stay in flight
+    } else {
+        cp_async_wait<0>();
+    }
+    {
+        const int q = hfirst_v - strip.e0 / NCH;  // window start in the strip
+#pragma unroll
+        for (int j = 0; j < HT; ++j)
+            hb[j] = linear ? (q + j) * 16 : planar_byte(q + j);
     }
     __syncthreads();  // vws / vfs / hws / cleared vrows visible
 
