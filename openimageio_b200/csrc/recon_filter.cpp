@@ -358,6 +358,32 @@ Filter2D::nonseparable_kind() const
     return m_fam->scale == Scale::Disk ? 1
                                        : (m_fam->scale == Scale::RadialL3 ? 2 : 0);
 }
+Filter2D::DeviceDesc
+Filter2D::device_desc() const
+{
+    DeviceDesc d;
+    float (*const profs[])(float, float)
+        = { detail::p_box,  detail::p_tent,     detail::p_gauss,    detail::p_catrom,
+            detail::p_blackman_harris, detail::p_sinc, detail::p_lanczos3,
+            detail::p_mitchell, detail::p_bspline,  detail::p_cubic };
+    d.profile = 0;
+    for (int i = 0; i < int(sizeof(profs) / sizeof(profs[0])); ++i)
+        if (m_fam->profile == profs[i])
+            d.profile = i;
+    switch (m_fam->scale) {
+    case Scale::BoxEdge: d.scale = 0; break;
+    case Scale::Two: d.scale = 1; break;
+    case Scale::Four: d.scale = 2; break;
+    case Scale::Six: d.scale = 3; break;
+    case Scale::SincRad: d.scale = 4; break;
+    case Scale::Disk: d.scale = 5; break;
+    case Scale::RadialL3: d.scale = 6; break;
+    }
+    d.param = m_fam->param;
+    d.w     = m_w;
+    d.h     = m_h;
+    return d;
+}
 float
 Filter2D::operator()(float x, float y) const
 {

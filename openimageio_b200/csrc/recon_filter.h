@@ -86,6 +86,16 @@ public:
     // which one this is: 0 separable, 1 disk, 2 radial-lanczos3.
     int nonseparable_kind() const;
 
+    // Everything a device-side evaluation of operator() needs (warp kernel):
+    // profile 0 box, 1 tent, 2 gauss, 3 catrom, 4 blackman-harris, 5 sinc,
+    // 6 lanczos3, 7 mitchell, 8 b-spline, 9 cubic; scale 0 box-edge, 1 x*2/w,
+    // 2 x*4/w, 3 x*6/w, 4 sinc radius, 5 disk, 6 radial lanczos3.
+    struct DeviceDesc {
+        int profile, scale;
+        float param, w, h;
+    };
+    DeviceDesc device_desc() const;
+
 private:
     Filter2D(const detail::Family* fam, float w, float h)
         : m_fam(fam)

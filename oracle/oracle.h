@@ -84,6 +84,25 @@ int orc_rangeexpand(const orc_image* dst, const orc_image* src, int useluma,
                     int alpha_channel, int z_channel, orc_roi roi, int chbegin,
                     int chend);
 
+/* ImageBufAlgo::warp / rotate and fit(exact=1) restated
+ * (imagebufalgo_xform.cpp:263-418, 1012-1027, 1727-1760) with Imath's
+ * Matrix33<float> algebra.  M: row-major x[i][j] as Imath stores it.
+ * wrap: 0 default(black), 1 black, 2 clamp, 3 periodic, 4 mirror.  The filter
+ * is passed resolved (name, width, height).  Pinned against
+ * testsuite/oiiotool-xform/ref/{warped,rotated*,resizefrom*}.tif, fit4.exr and
+ * fit[wh]-<mode>-<size>.exr. */
+int orc_warp(const orc_image* dst, const orc_image* src, const float* M,
+             const char* filtername, float fw, float fh, int wrap, int edgeclamp,
+             orc_roi roi, int nthreads, char* err, int errlen);
+void orc_m33_inverse(const float* M, float* out);
+void orc_rotate_matrix(float angle, float cx, float cy, float* out);
+void orc_fromto_matrix(float from_x, float from_y, float from_w, float from_h,
+                       float to_x, float to_y, float to_w, float to_h, float* out);
+void orc_transform_roi(const float* M, orc_roi roi, orc_roi* out);
+void orc_fit_exact_matrix(int src_full_w, int src_full_h, int fit_w, int fit_h,
+                          const char* fillmode, float* M, int* resize_w,
+                          int* resize_h);
+
 /* float -> dst-type store and src-type -> float load used by the above
  * (fmath.h:753-764, 1009-1031); exposed for unit tests. */
 float orc_load_as_float(const void* p, int basetype);

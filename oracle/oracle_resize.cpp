@@ -620,3 +620,11 @@ orc_fit_geometry(int src_full_w, int src_full_h, int fit_w, int fit_h,
 }
 
 }  // extern "C"
+
+
+// row-band threading for the other oracle translation units
+void
+orc_parallel_bands(orc_roi roi, int nthreads, const std::function<void(orc_roi)>& f)
+{
+    parallel_bands(roi, nthreads, f);
+}

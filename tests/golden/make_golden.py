@@ -17,6 +17,8 @@ Sources (all under /root/reference/testsuite, OpenImageIO 3.2.0.2-dev):
   oiiotool-xform/ref/resample.tif, resample-nearest.tif   --resample 128x128
   oiiotool-xform/ref/fit.tif, fit2.tif, fit3.tif           --fit
   common/tahoe-small.tif + oiiotool/ref/range{compress,expand}{,-luma}.tif
+  oiiotool-xform/ref/{warped,rotated,rotated-offcenter,resizefrom*}.tif,
+  oiiotool-xform/src/target1.exr, ref/fit4.exr, two of ref/fit[wh]-*.exr
 Only pixel arrays are stored (no reference source code is copied).
 """
 import os
@@ -81,6 +83,25 @@ def main():
     for k, v in pm.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(os.path.join(HERE, "pixelmath_ref.npz"), **pm)
+
+    # warp / rotate / resize:from-to / fit:exact known answers
+    # (testsuite/oiiotool-xform/run.py); inputs resize.tif and grid.tif are in
+    # xform_ref.npz already
+    wp = {}
+    for name in ["warped", "rotated", "rotated-offcenter", "resizefrom",
+                 "resizefromto", "resizefromtooffset"]:
+        wp[name.replace("-", "_")] = read(os.path.join(xdir, name + ".tif"))
+    for name, path in [("target1", "oiiotool-xform/src/target1.exr"),
+                       ("fit4", "oiiotool-xform/ref/fit4.exr"),
+                       ("fitw_letterbox_200", "oiiotool-xform/ref/fitw-letterbox-200x200.exr"),
+                       ("fith_width_300", "oiiotool-xform/ref/fith-width-300x300.exr")]:
+        a = read(os.path.join(REF, path))
+        h = a.astype(np.float16)
+        assert np.array_equal(h.astype(np.float32), a), name
+        wp[name] = h
+    for k, v in wp.items():
+        print(k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(HERE, "warp_ref.npz"), **wp)
 
 
 if __name__ == "__main__":

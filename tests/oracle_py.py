@@ -76,6 +76,20 @@ def lib():
             fn.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage), C.c_int,
                            C.c_int, C.c_int, OrcRoi, C.c_int, C.c_int]
             fn.restype = C.c_int
+        F9 = C.POINTER(C.c_float)
+        L.orc_warp.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage), F9,
+                               C.c_char_p, C.c_float, C.c_float, C.c_int, C.c_int,
+                               OrcRoi, C.c_int, C.c_char_p, C.c_int]
+        L.orc_m33_inverse.argtypes = [F9, F9]
+        L.orc_rotate_matrix.argtypes = [C.c_float] * 3 + [F9]
+        L.orc_fromto_matrix.argtypes = [C.c_float] * 8 + [F9]
+        L.orc_transform_roi.argtypes = [F9, OrcRoi, C.POINTER(OrcRoi)]
+        L.orc_fit_exact_matrix.argtypes = [C.c_int] * 4 + [C.c_char_p, F9,
+                                                          C.POINTER(C.c_int),
+                                                          C.POINTER(C.c_int)]
+        for fn in (L.orc_m33_inverse, L.orc_rotate_matrix, L.orc_fromto_matrix,
+                   L.orc_transform_roi, L.orc_fit_exact_matrix):
+            fn.restype = None
         L.orc_load_as_float.argtypes = [C.c_void_p, C.c_int]
         L.orc_store_from_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
         _lib = L
@@ -185,6 +199,64 @@ def rangeexpand(dst, src, useluma=False, alpha_channel=-1, z_channel=-1,
                 roi=None, chrange=None):
     return _range(lib().orc_rangeexpand, dst, src, useluma, alpha_channel,
                   z_channel, roi, chrange)
+
+
+WRAP = {"default": 0, "black": 1, "clamp": 2, "periodic": 3, "mirror": 4}
+
+
+def _m9(M):
+    a = (C.c_float * 9)(*[float(v) for v in np.asarray(M, np.float32).reshape(9)])
+    return a
+
+
+def warp(dst, src, M, filtername="lanczos3", fw=0.0, fh=0.0, wrap="default",
+         edgeclamp=False, roi=None, nthreads=0):
+    """warp_<D,S> over roi of dst.  The filter is given resolved: width 0 =
+    the filter's default width."""
+    d, s = dst.c(), src.c()
+    if roi is None:
+        roi = (dst.x, dst.x + dst.arr.shape[1], dst.y, dst.y + dst.arr.shape[0])
+    err = C.create_string_buffer(512)
+    rc = lib().orc_warp(C.byref(d), C.byref(s), _m9(M), (filtername or "").encode(),
+                        float(fw), float(fh), WRAP[wrap], int(bool(edgeclamp)),
+                        OrcRoi(*roi), int(nthreads), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return dst
+
+
+def m33_inverse(M):
+    out = (C.c_float * 9)()
+    lib().orc_m33_inverse(_m9(M), out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def rotate_matrix(angle, cx, cy):
+    out = (C.c_float * 9)()
+    lib().orc_rotate_matrix(float(angle), float(cx), float(cy), out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def fromto_matrix(frm, to):
+    """frm, to: (x, y, w, h) as oiiotool --resize:from=:to= (oiiotool.cpp:4704-4707)."""
+    out = (C.c_float * 9)()
+    lib().orc_fromto_matrix(float(frm[0]), float(frm[1]), float(frm[2]), float(frm[3]),
+                            float(to[0]), float(to[1]), float(to[2]), float(to[3]), out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def transform_roi(M, roi):
+    out = OrcRoi()
+    lib().orc_transform_roi(_m9(M), OrcRoi(*roi), C.byref(out))
+    return (out.xbegin, out.xend, out.ybegin, out.yend)
+
+
+def fit_exact_matrix(src_full_w, src_full_h, fit_w, fit_h, fillmode="letterbox"):
+    out = (C.c_float * 9)()
+    rw, rh = C.c_int(), C.c_int()
+    lib().orc_fit_exact_matrix(src_full_w, src_full_h, fit_w, fit_h, fillmode.encode(),
+                               out, C.byref(rw), C.byref(rh))
+    return np.array(list(out), np.float32).reshape(3, 3), rw.value, rh.value
 
 
 def resize_block(dst, src, allow_shift=False):

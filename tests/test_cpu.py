@@ -259,3 +259,81 @@ def test_mip_level_sizes(oracle):
     """write_mipmap's level rule: floor halving until 1x1."""
     lv = oracle.mip_chain(np.zeros((5, 12, 1), np.float32), "box")
     assert [(a.shape[1], a.shape[0]) for a in lv] == [(6, 2), (3, 1), (1, 1)]
+
+
+# ------------------------------------------------ oracle: warp / rotate ----
+def _fit_pattern(w, h):
+    """oiiotool --pattern constant:color=.25,.25,.25,1 WxH 4 --box:color=1,1,1
+    0,0,W-1,H-1 --box:color=1,0,0 4,4,W-5,H-5 -d half (oiiotool-xform/run.py:73-78)."""
+    a = np.zeros((h, w, 4), np.float32)
+    a[..., :3] = 0.25
+    a[..., 3] = 1
+
+    def box(x1, y1, x2, y2, col):
+        a[y1, x1:x2 + 1] = col
+        a[y2, x1:x2 + 1] = col
+        a[y1:y2 + 1, x1] = col
+        a[y1:y2 + 1, x2] = col
+    box(0, 0, w - 1, h - 1, (1, 1, 1, 1))
+    box(4, 4, w - 5, h - 5, (1, 0, 0, 1))
+    return a.astype(np.float16)
+
+
+def test_oracle_warp_goldens(oracle):
+    """testsuite/oiiotool-xform: --warp, --rotate, --resize:from/to and
+    --fit:exact=1 known answers, all reproduced BIT FOR BIT.  (rotated.tif and
+    warped.tif were made from the resize.tif of the same run, which on the
+    machine that made them equals the oracle's resize of grid.tif, not the
+    stored ref/resize.tif -- so the source here is the oracle's own resize.)"""
+    import math
+    X = np.load(os.path.join(GOLD, "xform_ref.npz"))
+    W = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    d = np.zeros((256, 256, 4), np.float32)
+    oracle.resize(oracle.Img(d), oracle.Img(gf))
+    rs = oracle.quantize(d, np.uint8)
+    src = oracle.Img(rs)
+    M = [0.7071068, 0.7071068, 0, -0.7071068, 0.7071068, 0, 128, -53.01933, 1]
+    out = np.zeros_like(rs)
+    oracle.warp(oracle.Img(out), src, M)
+    assert np.array_equal(out, W["warped"])
+    ang = np.float32(45.0) * np.float32(math.pi / 180.0)  # oiiotool.cpp --rotate
+    for name, (cx, cy) in {"rotated": (128.0, 128.0),
+                           "rotated_offcenter": (50.0, 50.0)}.items():
+        out = np.zeros_like(rs)
+        oracle.warp(oracle.Img(out), src, oracle.rotate_matrix(ang, cx, cy),
+                    wrap="black")
+        assert np.array_equal(out, W[name]), name
+    G = oracle.Img(X["grid"].copy())
+    for name, to in [("resizefrom", (0, 0, 64, 64)), ("resizefromto", (0, 0, 32, 32)),
+                     ("resizefromtooffset", (5, -5, 32, 32))]:
+        Mf = oracle.fromto_matrix((300, 300, 200, 200), to)
+        out = np.zeros((64, 64, 4), np.uint8)
+        oracle.warp(oracle.Img(out, 0, 0, (0, 0, 64, 64)), G, Mf)
+        assert np.array_equal(out, W[name]), name
+    # --fit:exact=1
+    Mx, rw, rh = oracle.fit_exact_matrix(288, 216, 216, 162)
+    out = np.zeros((162, 216, 3), np.float16)
+    oracle.warp(oracle.Img(out), oracle.Img(W["target1"].copy()), Mx,
+                "blackman-harris", 3.0, 3.0, wrap="black", edgeclamp=True)
+    assert np.array_equal(out.view(np.uint16), W["fit4"].view(np.uint16))
+    for name, (sw, sh), size, mode in [("fitw_letterbox_200", (256, 128), 200, "letterbox"),
+                                       ("fith_width_300", (128, 256), 300, "width")]:
+        Mx, rw, rh = oracle.fit_exact_matrix(sw, sh, size, size, mode)
+        wr, hr = np.float32(rw) / np.float32(sw), np.float32(rh) / np.float32(sh)
+        fn, bw = ("blackman-harris", 3.0) if (wr > 1 or hr > 1) else ("lanczos3", 6.0)
+        fw = np.float32(bw) * max(np.float32(1), wr)
+        fh = np.float32(bw) * max(np.float32(1), hr)
+        out = np.zeros((size, size, 4), np.float16)
+        oracle.warp(oracle.Img(out), oracle.Img(_fit_pattern(sw, sh)), Mx, fn, fw, fh,
+                    wrap="black", edgeclamp=True)
+        assert np.array_equal(out.view(np.uint16), W[name].view(np.uint16)), name
+
+
+def test_oracle_warp_matrix_algebra(oracle):
+    M = oracle.rotate_matrix(0.3, 10.0, 20.0)
+    Mi = oracle.m33_inverse(M)
+    assert np.allclose(M.astype(np.float64) @ Mi.astype(np.float64), np.eye(3), atol=1e-5)
+    # transform(M, roi): bounding box of the pixel-centre corners
+    T = np.array([[1, 0, 0], [0, 1, 0], [10, -5, 1]], np.float32)
+    assert oracle.transform_roi(T, (0, 100, 0, 50)) == (10, 110, -5, 45)
