@@ -204,6 +204,49 @@ B2R_API void b2r_fit_geometry(int src_full_width, int src_full_height,
                               const char* fillmode, int* resize_width,
                               int* resize_height, int* xoffset, int* yoffset);
 
+/* ---- warp / rotate / fit(exact) / --resize:from/to -----------------------
+ * Replaces warp_<D,S> + filtered_sample<S> as dispatched by warp_impl
+ * (src/libOpenImageIO/imagebufalgo_xform.cpp:263-325, 353-418) -- the path
+ * ImageBufAlgo::warp, ImageBufAlgo::rotate (:1727-1760), fit(exact=1)
+ * (:1017-1027) and oiiotool --resize:from=/to= (src/oiiotool/oiiotool.cpp:
+ * 4652-4656, 4684-4720) all end in.  M: 9 floats, row-major Imath::M33f
+ * (p' = p * M, translation in M[6], M[7]).  dst must be allocated (warp_impl
+ * does that through IBAprep, :397); roi NULL = dst's data window.
+ * wrap: ImageBuf::WrapMode (imagebuf.h:  0 default, 1 black, 2 clamp,
+ * 3 periodic, 4 mirror).  Any of the four pixel types on either side.
+ * filtername NULL or "" -> lanczos3; filterwidth <= 0 -> the filter's default
+ * width (get_warp_filter, :329-349). */
+B2R_API int b2r_warp(const b2r_image* dst, const b2r_image* src, const float* M,
+                     const char* filtername, float filterwidth, int wrap,
+                     int edgeclamp, const b2r_roi* roi, const b2r_options* opt,
+                     b2r_report* report, char* err, size_t errlen);
+/* The KWArgs "filterptr" form (:478-480; also how fit(exact=1) passes the
+ * filter it resolved with get_resize_filter).  filter NULL -> lanczos3, 6x6
+ * (:403-408).  The filter is borrowed. */
+B2R_API int b2r_warp_filter(const b2r_image* dst, const b2r_image* src,
+                            const float* M, const b2r_filter2d* filter, int wrap,
+                            int edgeclamp, const b2r_roi* roi,
+                            const b2r_options* opt, b2r_report* report,
+                            char* err, size_t errlen);
+/* Host matrix helpers, float32 in Imath's operation order (Imath 3.1
+ * Matrix33<float>; Imath is an external dependency of the reference). */
+B2R_API void b2r_m33_inverse(const float* M, float* out);
+/* ImageBufAlgo::rotate: translate(-c) * rotate(angle) * translate(c), xform.cpp:1733-1737 */
+B2R_API void b2r_rotate_matrix(float angle_radians, float center_x,
+                               float center_y, float* out);
+/* oiiotool --resize:from=:to= : translate(to) scale(to/from) translate(-from),
+ * oiiotool.cpp:4704-4707 */
+B2R_API void b2r_fromto_matrix(float from_x, float from_y, float from_w,
+                               float from_h, float to_x, float to_y, float to_w,
+                               float to_h, float* out);
+/* transform(M, roi), xform.cpp:231-253 (warp's recompute_roi) */
+B2R_API void b2r_transform_roi(const float* M, const b2r_roi* roi, b2r_roi* out);
+/* fit(exact=1): the warp matrix (scale, centring offsets) and the size the
+ * filter is chosen for, xform.cpp:962-997, 1005-1023 */
+B2R_API void b2r_fit_exact(int src_full_width, int src_full_height,
+                           int fit_width, int fit_height, const char* fillmode,
+                           float* M, int* resize_width, int* resize_height);
+
 /* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
  * The reference parallelises resize by full-width row bands
  * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The

@@ -130,6 +130,25 @@ def lib():
         f.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int, C.c_int,
                       C.c_int, C.POINTER(_Roi), C.POINTER(_Options),
                       C.POINTER(Report), C.c_char_p, C.c_size_t]
+    F9 = C.POINTER(C.c_float)
+    L.b2r_warp.argtypes = [C.POINTER(_Image), C.POINTER(_Image), F9, C.c_char_p,
+                           C.c_float, C.c_int, C.c_int, C.POINTER(_Roi),
+                           C.POINTER(_Options), C.POINTER(Report), C.c_char_p,
+                           C.c_size_t]
+    L.b2r_warp_filter.argtypes = [C.POINTER(_Image), C.POINTER(_Image), F9,
+                                  C.c_void_p, C.c_int, C.c_int, C.POINTER(_Roi),
+                                  C.POINTER(_Options), C.POINTER(Report),
+                                  C.c_char_p, C.c_size_t]
+    L.b2r_m33_inverse.argtypes = [F9, F9]
+    L.b2r_rotate_matrix.argtypes = [C.c_float] * 3 + [F9]
+    L.b2r_fromto_matrix.argtypes = [C.c_float] * 8 + [F9]
+    L.b2r_transform_roi.argtypes = [F9, C.POINTER(_Roi), C.POINTER(_Roi)]
+    L.b2r_fit_exact.argtypes = [C.c_int] * 4 + [C.c_char_p, F9,
+                                                C.POINTER(C.c_int),
+                                                C.POINTER(C.c_int)]
+    for f in (L.b2r_m33_inverse, L.b2r_rotate_matrix, L.b2r_fromto_matrix,
+              L.b2r_transform_roi, L.b2r_fit_exact):
+        f.restype = None
     L.b2r_fit_geometry.argtypes = [C.c_int] * 4 + [C.c_char_p] + \
         [C.POINTER(C.c_int)] * 4
     L.b2r_band_split.argtypes = [C.POINTER(_Roi), C.c_int, C.c_int,
@@ -152,6 +171,17 @@ def lib():
     L.b2r_mipchain_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
+
+
+def _filter_descs():
+    """(name, default width) of every 2-D filter (Filter2D::get_filterdesc)."""
+    L = lib()
+    out = []
+    for i in range(L.b2r_filter_count(2)):
+        nm, w = C.c_char_p(), C.c_float()
+        L.b2r_filter_desc(2, i, C.byref(nm), C.byref(w), None, None, None)
+        out.append((nm.value.decode(), w.value))
+    return out
 
 
 def get_string_attribute(name):
@@ -649,12 +679,42 @@ class _IBA:
         roi = _ibaprep(roi, dst, src)
         if roi is None:
             return False
-        if exact:
-            dst.errorfmt("fit: exact=1 takes the warp path, which is outside "
-                         "the B200 resize path")
-            return False
         sspec = src.spec_
         L = lib()
+        if exact:
+            # :1017-1027: partial-pixel fit = a warp by (scale, centring
+            # offset) with black wrap and edgeclamp, through the filter
+            # get_resize_filter picks for the whole-pixel resize ratios
+            M = (C.c_float * 9)()
+            rw, rh = C.c_int(), C.c_int()
+            L.b2r_fit_exact(sspec.full_width, sspec.full_height, roi.width,
+                            roi.height, fillmode.encode(), M, C.byref(rw),
+                            C.byref(rh))
+            wratio = np.float32(rw.value) / np.float32(sspec.full_width)
+            hratio = np.float32(rh.value) / np.float32(sspec.full_height)
+            name = filtername or ("blackman-harris"
+                                  if (wratio > 1.0 or hratio > 1.0) else "lanczos3")
+            filt = None
+            for fd in _filter_descs():
+                if fd[0] == name:
+                    w = filterwidth if filterwidth > 0 else \
+                        np.float32(fd[1]) * max(np.float32(1), wratio)
+                    h = filterwidth if filterwidth > 0 else \
+                        np.float32(fd[1]) * max(np.float32(1), hratio)
+                    filt = Filter2D.create(name, float(w), float(h))
+                    break
+            if filt is None:
+                dst.errorfmt('Filter "%s" not recognized' % name)
+                return False
+            newroi = ROI(roi.xbegin, roi.xend, roi.ybegin, roi.yend, 0, 1, 0,
+                         sspec.nchannels)
+            newspec = sspec.copy()
+            newspec.set_roi(newroi)
+            newspec.set_roi_full(newroi)
+            dev = src.pixels.device if src.on_device else None
+            dst.reset(newspec, device=dev)
+            return self._warp(dst, src, list(M), "", 0.0, filt, False, "black",
+                              True, None, device)
         rw, rh, xo, yo = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         L.b2r_fit_geometry(sspec.full_width, sspec.full_height, roi.width,
                            roi.height, fillmode.encode(), C.byref(rw),
@@ -682,7 +742,210 @@ class _IBA:
         return ok
 
 
+    # ---- warp / rotate ----------------------------------------------------
+    def warp(self, *args, filtername="", filterwidth=0.0, recompute_roi=False,
+             wrap="default", edgeclamp=False, filterptr=None, roi=None,
+             nthreads=0, device=0):
+        """ImageBufAlgo::warp(dst, src, M, KWArgs{filtername, filterwidth,
+        wrap, edgeclamp, recompute_roi, filterptr}, roi, nthreads)
+        (imagebufalgo_xform.cpp:468-503).  M: 9 floats, Imath::M33f order."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        M = rest[0]
+        if len(rest) > 1:
+            filtername = rest[1]
+        if len(rest) > 2:
+            filterwidth = rest[2]
+        if len(bufs) == 2:
+            return self._warp(bufs[0], bufs[1], M, filtername, filterwidth,
+                              filterptr, recompute_roi, wrap, edgeclamp, roi,
+                              device)
+        result = ImageBuf()
+        ok = self._warp(result, bufs[0], M, filtername, filterwidth, filterptr,
+                        recompute_roi, wrap, edgeclamp, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::warp() error")
+        return result
+
+    def _warp(self, dst, src, M, filtername, filterwidth, filterptr,
+              recompute_roi, wrap, edgeclamp, roi, device):
+        # warp_impl (imagebufalgo_xform.cpp:379-418)
+        if src is None or not src.initialized:
+            dst.errorfmt("Uninitialized input image")
+            return False
+        L = lib()
+        m9 = (C.c_float * 9)(*[float(v) for v in np.asarray(M, np.float32).reshape(9)])
+        if filterptr is None:
+            name = filtername or "lanczos3"
+            if name not in [fd[0] for fd in _filter_descs()]:
+                dst.errorfmt('Filter "%s" not recognized' % name)
+                return False
+        if isinstance(wrap, str):
+            if wrap not in WRAP_MODES:
+                wrap = "default"  # WrapMode_from_string
+            wrap = WRAP_MODES[wrap]
+        have_roi = roi is not None and roi.defined
+        if dst.initialized:
+            dst_roi = roi.copy() if have_roi else dst.roi
+        elif have_roi:
+            dst_roi = roi.copy()
+        elif recompute_roi:
+            sr = src.roi
+            r = _Roi(sr.xbegin, sr.xend, sr.ybegin, sr.yend, sr.chbegin, sr.chend)
+            o = _Roi()
+            L.b2r_transform_roi(m9, C.byref(r), C.byref(o))
+            dst_roi = ROI(o.xbegin, o.xend, o.ybegin, o.yend, 0, 1, sr.chbegin,
+                          sr.chend)
+        else:
+            dst_roi = src.roi
+        dst_roi.chend = min(dst_roi.chend, src.nchannels)
+        if not dst.initialized:
+            # IBAprep sets full = src's full window for an uninitialized dst
+            spec = src.spec_.copy()
+            spec.set_roi(dst_roi)
+            spec.set_roi_full(src.roi_full)
+            spec.nchannels = dst_roi.chend
+            dev = src.pixels.device if src.on_device else None
+            dst.reset(spec, device=dev)
+        roi = _ibaprep(dst_roi, dst, src)
+        if roi is None:
+            return False
+        roi.chend = min(roi.chend, src.nchannels)
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        stream = _current_stream(dst) or _current_stream(src)
+        o = _options(device, PATH_AUTO, stream)
+        err = C.create_string_buffer(512)
+        rep = Report()
+        want_report = not (dst.on_device and src.on_device)
+        if filterptr is not None:
+            rc = L.b2r_warp_filter(C.byref(d), C.byref(s), m9, filterptr._h,
+                                   int(wrap), 1 if edgeclamp else 0, C.byref(r),
+                                   C.byref(o),
+                                   C.byref(rep) if want_report else None, err, 512)
+        else:
+            rc = L.b2r_warp(C.byref(d), C.byref(s), m9,
+                            (filtername or "").encode(), float(filterwidth),
+                            int(wrap), 1 if edgeclamp else 0, C.byref(r),
+                            C.byref(o), C.byref(rep) if want_report else None,
+                            err, 512)
+        self.last_report = rep if want_report else None
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    def rotate(self, *args, filtername="", filterwidth=0.0, recompute_roi=False,
+               center=None, filterptr=None, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::rotate(dst, src, angle[, center_x, center_y], ...)
+        (imagebufalgo_xform.cpp:1727-1830): angle in radians, default centre =
+        centre of src's display window, wrap black."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        angle = float(rest[0])
+        if len(rest) >= 3 and not isinstance(rest[1], str):
+            center = (float(rest[1]), float(rest[2]))
+            rest = rest[:1] + rest[3:]
+        if len(rest) > 1:
+            filtername = rest[1]
+        if len(rest) > 2:
+            filterwidth = rest[2]
+        src = bufs[-1]
+        if src is None or not src.initialized:
+            dst = bufs[0] if len(bufs) == 2 else ImageBuf()
+            dst.errorfmt("Uninitialized input image")
+            return False if len(bufs) == 2 else dst
+        if center is None:
+            f = src.roi_full
+            center = (np.float32(0.5) * np.float32(f.xbegin + f.xend),
+                      np.float32(0.5) * np.float32(f.ybegin + f.yend))
+        M = rotate_matrix(angle, center[0], center[1])
+        if len(bufs) == 2:
+            return self._warp(bufs[0], src, M, filtername, filterwidth,
+                              filterptr, recompute_roi, "black", False, roi,
+                              device)
+        result = ImageBuf()
+        ok = self._warp(result, src, M, filtername, filterwidth, filterptr,
+                        recompute_roi, "black", False, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::rotate() error")
+        return result
+
+
 ImageBufAlgo = _IBA()
+
+# ImageBuf::WrapMode (src/include/OpenImageIO/imagebuf.h)
+WRAP_MODES = {"default": 0, "black": 1, "clamp": 2, "periodic": 3, "mirror": 4}
+
+
+def _m9out():
+    return (C.c_float * 9)()
+
+
+def m33_inverse(M):
+    """Imath::M33f::inverse() as warp_ uses it."""
+    out = _m9out()
+    m = (C.c_float * 9)(*[float(v) for v in np.asarray(M, np.float32).reshape(9)])
+    lib().b2r_m33_inverse(m, out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def rotate_matrix(angle, center_x, center_y):
+    """The matrix ImageBufAlgo::rotate builds (imagebufalgo_xform.cpp:1733-1737)."""
+    out = _m9out()
+    lib().b2r_rotate_matrix(float(angle), float(center_x), float(center_y), out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def fromto_matrix(frm, to):
+    """oiiotool --resize:from=:to= matrix (oiiotool.cpp:4704-4707);
+    frm, to = (x, y, w, h)."""
+    out = _m9out()
+    lib().b2r_fromto_matrix(*[float(v) for v in frm], *[float(v) for v in to], out)
+    return np.array(list(out), np.float32).reshape(3, 3)
+
+
+def oiiotool_resize(src, width, height, filtername="", from_geom=None,
+                    to_geom=None, highlightcomp=False, edgeclamp=False,
+                    device=0):
+    """The compute step of `oiiotool --resize[:from=..][:to=..][:filter=..]
+    [:highlightcomp=1][:edgeclamp=1] WxH` (OpResize, src/oiiotool/oiiotool.cpp:
+    4581-4735) for an image whose display window starts at the origin:
+    a separable resize, or -- when from/to differ from the full windows -- a
+    warp by the from->to matrix.  from_geom / to_geom: (x, y, w, h)."""
+    A = src.spec_
+    newspec = A.copy()
+    newspec.full_width, newspec.full_height = width, height
+    newspec.x, newspec.y = newspec.full_x, newspec.full_y
+    newspec.width, newspec.height = width, height
+    frm = (A.full_x, A.full_y, A.full_width, A.full_height)
+    to = (newspec.full_x, newspec.full_y, width, height)
+    f = tuple(float(v) for v in (from_geom or frm))
+    t = tuple(float(v) for v in (to_geom or to))
+    do_warp = f != tuple(map(float, frm)) or t != tuple(map(float, to))
+    IBA = ImageBufAlgo
+    if not do_warp:
+        wr = np.float32(width) / np.float32(A.full_width)
+        hr = np.float32(height) / np.float32(A.full_height)
+        newspec.x = newspec.full_x + int(np.floor(np.float32(A.x - A.full_x) * wr))
+        newspec.y = newspec.full_y + int(np.floor(np.float32(A.y - A.full_y) * hr))
+        newspec.width = int(np.ceil(np.float32(A.width) * wr))
+        newspec.height = int(np.ceil(np.float32(A.height) * hr))
+    dst = ImageBuf()
+    dst.reset(newspec, device=src.pixels.device if src.on_device else None)
+    if not do_warp:
+        ok = IBA.resize(dst, src, filtername=filtername, roi=dst.roi,
+                        device=device, highlightcomp=highlightcomp)
+        return dst if ok else dst
+    s = src
+    if highlightcomp:
+        s = IBA.rangecompress(src, device=device)
+    ok = IBA.warp(dst, s, fromto_matrix(f, t), filtername=filtername,
+                  recompute_roi=False, edgeclamp=edgeclamp, device=device)
+    if highlightcomp and ok:
+        IBA.rangeexpand(dst, dst, device=device)
+    return dst
 
 
 # --------------------------------------------------------------------------

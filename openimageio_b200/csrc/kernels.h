@@ -221,6 +221,22 @@ struct RangeParams {
 void
 launch_range(const RangeParams& p, void* stream);
 
+// ----------------------------------------------------------------- warp ----
+// warp_<D,S> (imagebufalgo_xform.cpp:353-375): dst pixel -> Minv -> filtered
+// sample of src with a per-pixel footprint.
+struct WarpParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    float minv[9];  // inverse matrix, [i*3+j] = Imath x[i][j]
+    int filt_profile, filt_scale;  // Filter2D::DeviceDesc
+    float filt_param, filt_w, filt_h;
+    int wrap;       // 0 default, 1 black, 2 clamp, 3 periodic, 4 mirror
+    int edgeclamp;
+};
+void
+launch_warp(const WarpParams& p, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

@@ -1,0 +1,212 @@
+"""GPU parity for the warp path (ImageBufAlgo::warp / rotate / fit exact=1 /
+oiiotool --resize:from/to): the CUDA kernel through the C ABI against the CPU
+oracle on identical inputs, and against the reference's own golden images.
+
+Bars: uint8/uint16 +-1 LSB (and almost everywhere exact), float 1e-5 relative,
+half 1 ulp.  The footprint arithmetic is bit-identical by construction; only
+sinf/cosf inside the filter profiles can differ from glibc's."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+import synth
+from test_gpu_parity import check, _np_dtype
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _buf(oiio, arr, win=None):
+    B = oiio.ImageBuf(arr)
+    if win:
+        x, y, full = win
+        B.spec().x, B.spec().y = x, y
+        (B.spec().full_x, B.spec().full_y, B.spec().full_width,
+         B.spec().full_height) = full if full else (x, y, arr.shape[1], arr.shape[0])
+    return B
+
+
+def warp_both(oiio, oracle, src, dst_shape, dst_dtype, M, filtername="", fw=0.0,
+              wrap="default", edgeclamp=False, src_win=None, dst_win=None,
+              roi=None, prefill=None, device_resident=False):
+    h, w = dst_shape
+    c = src.shape[2]
+    g = np.zeros((h, w, c), dst_dtype) if prefill is None else prefill.copy()
+    o = g.copy()
+    sx, sy, sfull = src_win if src_win else (0, 0, None)
+    dx, dy, dfull = dst_win if dst_win else (0, 0, None)
+    # oracle: filter resolved the way get_warp_filter does
+    name = filtername or "lanczos3"
+    oracle.warp(oracle.Img(o, dx, dy, dfull), oracle.Img(src, sx, sy, sfull), M,
+                name, fw, fw, wrap, edgeclamp, roi)
+    S = _buf(oiio, src, src_win)
+    D = _buf(oiio, g, dst_win)
+    r = oiio.ROI(roi[0], roi[1], roi[2], roi[3], 0, 1, 0, c) if roi else None
+    if device_resident:
+        import torch
+
+        def up(a):
+            if a.dtype == np.uint16:
+                return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+            return torch.from_numpy(a).cuda()
+        S.pixels, D.pixels = up(src), up(g)
+    ok = oiio.ImageBufAlgo.warp(D, S, M, filtername=filtername, filterwidth=fw,
+                                wrap=wrap, edgeclamp=edgeclamp, roi=r)
+    assert ok, D.geterror()
+    if device_resident:
+        g = D.get_pixels()
+    return g, o
+
+
+def _rot(oiio, deg, cx, cy):
+    return oiio.rotate_matrix(np.float32(deg) * np.float32(math.pi / 180.0), cx, cy)
+
+
+PERSPECTIVE = np.array([[0.9, 0.12, 0.0006], [-0.2, 1.05, -0.0004],
+                        [9.0, -7.0, 1.0]], np.float32)
+
+
+def test_warp_goldens(oiio, oracle):
+    """oiiotool-xform warped.tif / rotated*.tif / resizefrom*.tif through the
+    CUDA path."""
+    X = np.load(os.path.join(GOLD, "xform_ref.npz"))
+    W = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    d = np.zeros((256, 256, 4), np.float32)
+    oracle.resize(oracle.Img(d), oracle.Img(gf))
+    rs = oracle.quantize(d, np.uint8)  # see test_cpu.test_oracle_warp_goldens
+    IBA = oiio.ImageBufAlgo
+    M = [0.7071068, 0.7071068, 0, -0.7071068, 0.7071068, 0, 128, -53.01933, 1]
+    out = IBA.warp(oiio.ImageBuf(rs), M)
+    assert not out.has_error, out.geterror()
+    dd = np.abs(out.pixels.astype(int) - W["warped"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+    ang = np.float32(45.0) * np.float32(math.pi / 180.0)
+    out = IBA.rotate(oiio.ImageBuf(rs), ang)
+    dd = np.abs(out.pixels.astype(int) - W["rotated"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+    out = IBA.rotate(oiio.ImageBuf(rs), ang, 50.0, 50.0)
+    dd = np.abs(out.pixels.astype(int) - W["rotated_offcenter"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+    G = oiio.ImageBuf(X["grid"].copy())
+    for name, to in [("resizefrom", None), ("resizefromto", (0, 0, 32, 32)),
+                     ("resizefromtooffset", (5, -5, 32, 32))]:
+        out = oiio.oiiotool_resize(G, 64, 64, from_geom=(300, 300, 200, 200),
+                                   to_geom=to)
+        assert not out.has_error, out.geterror()
+        dd = np.abs(out.pixels.astype(int) - W[name].astype(int))
+        assert dd.max() <= 1 and (dd != 0).mean() < 1e-3, name
+
+
+def test_fit_exact_goldens(oiio, oracle):
+    from test_cpu import _fit_pattern
+    W = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    IBA = oiio.ImageBufAlgo
+    out = IBA.fit(oiio.ImageBuf(W["target1"].copy()), filtername="blackman-harris",
+                  exact=True, roi=oiio.ROI(0, 216, 0, 162, 0, 1, 0, 3))
+    assert not out.has_error, out.geterror()
+    check(out.pixels, W["fit4"])
+    for name, (sw, sh), size, mode in [("fitw_letterbox_200", (256, 128), 200, "letterbox"),
+                                       ("fith_width_300", (128, 256), 300, "width")]:
+        out = IBA.fit(oiio.ImageBuf(_fit_pattern(sw, sh)), fillmode=mode, exact=True,
+                      roi=oiio.ROI(0, size, 0, size, 0, 1, 0, 4))
+        assert not out.has_error, out.geterror()
+        assert out.pixels.shape == (size, size, 4)
+        check(out.pixels, W[name])
+
+
+@pytest.mark.parametrize("dt,st", [("float", "float"), ("uint8", "uint8"),
+                                   ("uint16", "uint16"), ("half", "half"),
+                                   ("float", "uint8"), ("uint8", "float"),
+                                   ("half", "uint16"), ("uint16", "half")])
+@pytest.mark.parametrize("nch", [1, 3, 4])
+def test_warp_type_pairs(oiio, oracle, dt, st, nch):
+    src = synth.image(97, 61, nch, _np_dtype(st), seed=11 + nch)
+    g, o = warp_both(oiio, oracle, src, (70, 90), _np_dtype(dt),
+                     _rot(oiio, 17.0, 40.0, 30.0))
+    check(g, o)
+    if g.dtype in (np.uint8, np.uint16):
+        assert (g != o).mean() < 2e-3
+
+
+@pytest.mark.parametrize("filt", ["box", "triangle", "gaussian", "sharp-gaussian",
+                                  "catmull-rom", "blackman-harris", "sinc", "lanczos3",
+                                  "radial-lanczos3", "nuke-lanczos6", "mitchell",
+                                  "bspline", "disk", "cubic", "keys", "simon", "rifman"])
+def test_warp_every_filter(oiio, oracle, filt):
+    src = synth.image(64, 48, 3, np.float32, seed=5)
+    g, o = warp_both(oiio, oracle, src, (48, 64), np.float32, PERSPECTIVE, filt)
+    check(g, o)
+
+
+@pytest.mark.parametrize("wrap", ["default", "black", "clamp", "periodic", "mirror"])
+@pytest.mark.parametrize("cropped", [False, True])
+def test_warp_wrap_modes(oiio, oracle, wrap, cropped):
+    """Footprints that leave the image on every side, with the data window
+    equal to the display window and as a crop inside / overscan outside it."""
+    src = synth.image(40, 30, 4, np.float32, seed=9)
+    win = (7, -3, (0, 0, 50, 32)) if cropped else None
+    M = np.array([[0.5, 0.05, 0], [-0.04, 0.45, 0], [20, 14, 1]], np.float32)
+    g, o = warp_both(oiio, oracle, src, (64, 96), np.float32, M, "mitchell",
+                     wrap=wrap, src_win=win, dst_win=(-8, -6, (0, 0, 80, 52)))
+    check(g, o)
+
+
+@pytest.mark.parametrize("st", ["float", "uint8"])
+def test_warp_edgeclamp_and_minify(oiio, oracle, st):
+    """edgeclamp (fit exact / --resize:edgeclamp) and a 3.7x minification whose
+    footprint (23 columns) is wider than the kernel's weight cache... and one
+    wider still."""
+    src = synth.image(200, 160, 3, _np_dtype(st), seed=3)
+    for scale in (0.27, 0.11):
+        M = np.array([[scale, 0, 0], [0, scale, 0], [3.3, 2.1, 1]], np.float32)
+        g, o = warp_both(oiio, oracle, src, (50, 64), _np_dtype(st), M, "lanczos3",
+                         wrap="black", edgeclamp=True)
+        check(g, o)
+
+
+def test_warp_roi_channels_and_prefill(oiio, oracle):
+    """A dst ROI smaller than dst and a 5-channel image (two channel passes):
+    pixels outside the ROI keep their values."""
+    src = synth.image(50, 40, 5, np.float32, seed=21)
+    pre = synth.image(60, 44, 5, np.float32, seed=22)
+    g, o = warp_both(oiio, oracle, src, (44, 60), np.float32,
+                     _rot(oiio, -30.0, 25.0, 20.0), "catmull-rom",
+                     roi=(5, 41, 3, 40), prefill=pre)
+    check(g, o)
+    assert np.array_equal(g[:3], pre[:3]) and np.array_equal(g[:, :5], pre[:, :5])
+
+
+def test_warp_device_resident(oiio, oracle):
+    for st in ("float", "half", "uint16", "uint8"):
+        src = synth.image(128, 96, 4, _np_dtype(st), seed=31)
+        g, o = warp_both(oiio, oracle, src, (96, 128), _np_dtype(st), PERSPECTIVE,
+                         device_resident=True)
+        check(g, o)
+
+
+def test_warp_recompute_roi_and_errors(oiio, oracle):
+    IBA = oiio.ImageBufAlgo
+    src = oiio.ImageBuf(synth.image(32, 24, 3, np.float32, seed=1))
+    M = _rot(oiio, 45.0, 16.0, 12.0)
+    out = IBA.warp(src, M, recompute_roi=True)
+    assert not out.has_error
+    r = oracle.transform_roi(M, (0, 32, 0, 24))
+    assert (out.spec().x, out.spec().x + out.spec().width, out.spec().y,
+            out.spec().y + out.spec().height) == r
+    ref = np.zeros(out.pixels.shape, np.float32)
+    oracle.warp(oracle.Img(ref, r[0], r[2], (0, 0, 32, 24)), oracle.Img(src.pixels), M)
+    check(out.pixels, ref)
+    bad = IBA.warp(src, M, filtername="catrom")
+    assert bad.has_error and bad.geterror() == 'Filter "catrom" not recognized'
+    assert IBA.warp(oiio.ImageBuf(), oiio.ImageBuf(), M) is False
+
+
+def test_warp_singular_matrix(oiio, oracle):
+    """A singular matrix inverts to identity (Imath's non-throwing inverse)."""
+    src = synth.image(20, 20, 3, np.float32, seed=2)
+    M = np.zeros((3, 3), np.float32)
+    g, o = warp_both(oiio, oracle, src, (20, 20), np.float32, M, "triangle")
+    check(g, o)
