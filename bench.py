@@ -48,6 +48,8 @@ DESCR = {
     "c3": "1920x1080->7680x4320 mitchell RGB uint8",
     "c5": "4K->1080p lanczos3 RGB uint16 (one frame of the 256-frame batch)",
 }
+# frames in one step's batch, per GPU (each frame has its own buffers)
+FRAMES_PER_STEP = {"c0": 8, "c1": 8, "c2": 8, "c3": 8, "c5": 8}
 DT_SHORT = {"float32": "f32", "float16": "f16", "uint8": "u8", "uint16": "u16"}
 
 
@@ -93,7 +95,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "20"],
+                 "--format=csv,noheader,nounits", "-lms", "5"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -102,9 +104,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")]
+                             + [time.perf_counter()])
 
-    def stop(self):
+    def wait_first(self, timeout=2.0):
+        """Block until nvidia-smi has delivered its first sample."""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.005)
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock over the samples taken in [t0, t1] (host
+        perf_counter times of the timed region); all samples if none fell
+        inside."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.15)
@@ -116,7 +128,11 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[-1] <= t1 + 0.004]
+            rows = inside or rows
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -127,7 +143,8 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "samples_total": len(self.rows)}
 
 
 def sample_rows(wl, cores):
@@ -214,13 +231,19 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=25)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="c0", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--frames-per-step", type=int, default=0,
+                    help="frames in one step's batch per GPU (0 = workload default)")
+    ap.add_argument("--ramp-ms", type=float, default=0.0,
+                    help="extra untimed load after the warm-up steps (a long "
+                         "ramp drives the GPU into its 1 kW power cap: "
+                         "sustained rather than burst clocks)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -247,28 +270,45 @@ def main():
     tdt = {"float32": torch.float32, "float16": torch.float16,
            "uint8": torch.uint8, "uint16": torch.uint16}
 
-    # every rank has its own frame (same synthetic content, own seed)
+    # One step = one batch of `nfr` independent frames per GPU, each with its
+    # own source and destination in HBM (nothing is shared or reused between
+    # the frames of a batch); every rank has its own frames.
+    nfr = args.frames_per_step or FRAMES_PER_STEP[wl]
+
+    def to_torch(a):
+        t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        return t.view(torch.uint16) if a.dtype == np.uint16 else t
+
     src_np = synth.image(sw, sh, c, np.dtype(sdt), seed=20261019 + rank)
-    src_host = torch.from_numpy(src_np.view(np.int16) if sdt == "uint16" else src_np)
-    if sdt == "uint16":
-        src_host = src_host.view(torch.uint16)
-    src_host = src_host.pin_memory()
+    src_host = to_torch(src_np).pin_memory()
     dst_host = torch.empty((dh, dw, c), dtype=tdt[ddt]).pin_memory()
-    src_dev = src_host.to(dev, non_blocking=True)
-    dst_dev = torch.zeros((dh, dw, c), dtype=tdt[ddt], device=dev)
+    src_devs, dst_devs = [], []
+    for f in range(nfr):
+        t = src_host.to(dev, non_blocking=True)
+        if f:  # a different picture per frame: roll the rows
+            t = torch.roll(t.view(torch.uint8), shifts=137 * f, dims=0).view(t.dtype)
+        src_devs.append(t)
+        dst_devs.append(torch.zeros((dh, dw, c), dtype=tdt[ddt], device=dev))
     torch.cuda.synchronize()
 
-    S_dev, D_dev = oiio.ImageBuf(src_dev), oiio.ImageBuf(dst_dev)
+    S_devs = [oiio.ImageBuf(t) for t in src_devs]
+    D_devs = [oiio.ImageBuf(t) for t in dst_devs]
     S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
     IBA = oiio.ImageBufAlgo
+    dst_dev = dst_devs[0]
 
     def step_dev():
-        if not IBA.resize(D_dev, S_dev, filtername=filt):
-            raise RuntimeError(D_dev.geterror())
+        for S, D in zip(S_devs, D_devs):
+            if not IBA.resize(D, S, filtername=filt):
+                raise RuntimeError(D.geterror())
 
     def step_host():
-        if not IBA.resize(D_host, S_host, filtername=filt, device=local_rank):
-            raise RuntimeError(D_host.geterror())
+        # the batch through the host-memory API: every frame's source goes up
+        # and every result comes down (the same pinned host frame stands in
+        # for the nfr frames; a host->device copy cannot be cached)
+        for _ in range(nfr):
+            if not IBA.resize(D_host, S_host, filtername=filt, device=local_rank):
+                raise RuntimeError(D_host.geterror())
 
     def barrier():
         if world > 1:
@@ -282,16 +322,28 @@ def main():
     barrier()
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
+    # Optional extra untimed load (--ramp-ms).  The clock sampler runs from
+    # here to the end of the timed region ("under load").
+    t_ramp = time.perf_counter()
+    while (time.perf_counter() - t_ramp) * 1e3 < args.ramp_ms:
+        step_dev()
+        torch.cuda.synchronize()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
+    # a ~2 ms device-side spin in front of the first event: the K launches
+    # queue up behind it, so the timed region measures the device, not the
+    # host's launch rate (which matters when K is small)
+    t_host0 = time.perf_counter()
+    torch.cuda._sleep(4_000_000)
     ev0.record()
     for _ in range(args.steps):
         step_dev()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_host0, time.perf_counter()) if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -308,7 +360,7 @@ def main():
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
     rep = IBA.last_report
-    h2d, d2h = int(rep.h2d_bytes), int(rep.d2h_bytes)
+    h2d, d2h = int(rep.h2d_bytes) * nfr, int(rep.d2h_bytes) * nfr
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,11 +372,11 @@ def main():
 
     if rank == 0:
         mpix_frame = dw * dh / 1e6
-        value = mpix_frame * world / (ms_max * 1e-3)
-        e2e_value = mpix_frame * world / (e2e_ms_max * 1e-3)
+        value = mpix_frame * nfr * world / (ms_max * 1e-3)
+        e2e_value = mpix_frame * nfr * world / (e2e_ms_max * 1e-3)
         abytes = algorithmic_bytes(wl)
         peak, which = measured_peak()
-        achieved = abytes / (ms_max * 1e-3) / 1e9
+        achieved = abytes * nfr / (ms_max * 1e-3) / 1e9  # per launch = per frame
         src_is_fp = sdt in ("float32", "float16")
         line = {
             "metric": "output Mpixel/s", "value": value, "unit": "Mpixel/s",
@@ -332,21 +384,27 @@ def main():
             "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": DT_SHORT[sdt], "data": "synthetic",
             "config": {"workload": DESCR[wl], "name": wl,
-                       "frames_per_step": world,
+                       "frames_per_step": nfr * world,
+                       "frames_per_step_per_gpu": nfr,
                        "l2": "source frame (%.0f MB) larger than L2; no flush"
                              % (sw * sh * c * np.dtype(sdt).itemsize / 1e6)
                        if sw * sh * c * np.dtype(sdt).itemsize > 126e6 else
                        "working set fits L2; steps run back to back",
-                       "parallelism": "frame-per-gpu x%d" % world},
+                       "parallelism": "frame-per-gpu x%d" % world,
+                       "timing": "CUDA events on the launch stream; launches "
+                                 "queued behind a 2 ms device spin; %.0f ms "
+                                 "untimed clock ramp after the W warm-ups"
+                                 % args.ramp_ms},
             "e2e": {"value": e2e_value, "unit": "Mpixel/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max, "steps": e2e_steps,
                     "host_memory": "pinned"},
-            "gpu_launches": args.steps * (2 if src_is_fp else 1),
+            "gpu_launches": args.steps * nfr * (2 if src_is_fp else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(wl), "peak_source": which,
                          "algorithmic_bytes": abytes,
+                         "launch_us": ms_max * 1e3 / nfr,
                          "kernel": "resize_fused_kernel"},
             "clocks": clocks,
             "device_equals_host_result": same,
