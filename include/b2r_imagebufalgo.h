@@ -10,6 +10,8 @@
 //   ImageBufAlgo::resize / fit / resample              imagebufalgo.h:667-762,
 //       implemented in src/libOpenImageIO/imagebufalgo_xform.cpp:864-1074,
 //       1691-1723; IBAprep rules from imagebufalgo.cpp:64-348.
+//   ImageBufAlgo::warp / rotate (M33fParam = 9 floats here)
+//       imagebufalgo_xform.cpp:379-591, 1727-1830.
 // It exists so the parity tests and downstream code read like code written
 // against the reference; a maintainer integrating into OpenImageIO itself
 // only needs the ABI call shown in INTEGRATION.md.
@@ -402,22 +404,191 @@ resample(const ImageBuf& src, bool interpolate = true, ROI roi = {}, int nthread
     return result;
 }
 
-/// ImageBufAlgo::fit -- imagebufalgo_xform.cpp:933-1062.  exact=1 is the warp
-/// path and is refused (outside this library), not approximated.
+/// ImageBuf::WrapMode (imagebuf.h) and WrapMode_from_string.
+enum WrapMode { WrapDefault = 0, WrapBlack, WrapClamp, WrapPeriodic, WrapMirror };
+inline WrapMode
+WrapMode_from_string(const std::string& name)
+{
+    static const char* names[] = { "default", "black", "clamp", "periodic", "mirror" };
+    for (int i = 0; i < 5; ++i)
+        if (name == names[i])
+            return WrapMode(i);
+    return WrapDefault;
+}
+
+namespace detail {
+// warp_impl (imagebufalgo_xform.cpp:379-418).  filter may be null: then
+// (filtername, filterwidth) are resolved by the library like get_warp_filter.
+inline bool
+warp_impl(ImageBuf& dst, const ImageBuf& src, const float* M, const b2r_filter2d* filter,
+          const std::string& filtername, float filterwidth, bool recompute_roi, int wrap,
+          bool edgeclamp, ROI roi)
+{
+    if (!src.initialized()) {
+        dst.error("Uninitialized input image");
+        return false;
+    }
+    ROI dst_roi;
+    if (dst.initialized()) {
+        dst_roi = roi.defined() ? roi : dst.roi();
+    } else if (roi.defined()) {
+        dst_roi = roi;
+    } else if (recompute_roi) {
+        ROI sr = src.roi();
+        b2r_roi in { sr.xbegin, sr.xend, sr.ybegin, sr.yend, sr.chbegin, sr.chend }, out;
+        b2r_transform_roi(M, &in, &out);
+        dst_roi = ROI(out.xbegin, out.xend, out.ybegin, out.yend, 0, 1, sr.chbegin, sr.chend);
+    } else {
+        dst_roi = src.roi();
+    }
+    dst_roi.chend = std::min(dst_roi.chend, src.nchannels());
+    if (!dst.initialized()) {
+        ImageSpec spec = src.spec();
+        spec.set_roi(dst_roi);
+        spec.set_roi_full(src.roi_full());
+        spec.nchannels = dst_roi.chend;
+        dst.reset(spec);
+    }
+    if (!prep(dst_roi, dst, src))
+        return false;
+    dst_roi.chend = std::min(dst_roi.chend, src.nchannels());
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r { dst_roi.xbegin, dst_roi.xend, dst_roi.ybegin,
+                dst_roi.yend,   dst_roi.chbegin, dst_roi.chend };
+    char err[512] = "";
+    int rc = filter ? b2r_warp_filter(&d, &s, M, filter, wrap, edgeclamp, &r, nullptr, nullptr,
+                                      err, sizeof(err))
+                    : b2r_warp(&d, &s, M, filtername.c_str(), filterwidth, wrap, edgeclamp,
+                               &r, nullptr, nullptr, err, sizeof(err));
+    if (rc) {
+        dst.error(err);
+        return false;
+    }
+    return true;
+}
+}  // namespace detail
+
+/// ImageBufAlgo::warp(dst, src, M, KWArgs{filtername, filterwidth, wrap,
+/// edgeclamp, recompute_roi, filterptr}, roi, nthreads) --
+/// imagebufalgo_xform.cpp:468-503.  M: 9 floats in Imath::M33f order.
+inline bool
+warp(ImageBuf& dst, const ImageBuf& src, const float* M, const KWArgs& options = {},
+     ROI roi = {}, int /*nthreads*/ = 0)
+{
+    const b2r_filter2d* fp = (const b2r_filter2d*)options.get_ptr("filterptr");
+    int wrap               = WrapDefault;
+    std::string ws         = options.get_string("wrap", "");
+    if (!ws.empty())
+        wrap = WrapMode_from_string(ws);
+    else
+        wrap = options.get_int("wrap", WrapDefault);
+    return detail::warp_impl(dst, src, M, fp, options.get_string("filtername"),
+                             options.get_float("filterwidth"),
+                             options.get_int("recompute_roi") != 0, wrap,
+                             options.get_int("edgeclamp") != 0, roi);
+}
+
+inline ImageBuf
+warp(const ImageBuf& src, const float* M, const KWArgs& options = {}, ROI roi = {},
+     int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = warp(result, src, M, options, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::warp() error");
+    return result;
+}
+
+/// ImageBufAlgo::rotate(dst, src, angle, center_x, center_y, filtername,
+/// filterwidth, recompute_roi, roi, nthreads) -- imagebufalgo_xform.cpp:1727-1760.
+inline bool
+rotate(ImageBuf& dst, const ImageBuf& src, float angle, float center_x, float center_y,
+       const std::string& filtername = "", float filterwidth = 0.0f,
+       bool recompute_roi = false, ROI roi = {}, int nthreads = 0)
+{
+    float M[9];
+    b2r_rotate_matrix(angle, center_x, center_y, M);
+    return warp(dst, src, M,
+                { { "filtername", filtername },
+                  { "filterwidth", filterwidth },
+                  { "recompute_roi", int(recompute_roi) },
+                  { "wrap", "black" } },
+                roi, nthreads);
+}
+
+/// Rotation about the centre of src's display window (:1779-1790).
+inline bool
+rotate(ImageBuf& dst, const ImageBuf& src, float angle, const std::string& filtername = "",
+       float filterwidth = 0.0f, bool recompute_roi = false, ROI roi = {}, int nthreads = 0)
+{
+    ROI f          = src.roi_full();
+    float center_x = 0.5f * (f.xbegin + f.xend);
+    float center_y = 0.5f * (f.ybegin + f.yend);
+    return rotate(dst, src, angle, center_x, center_y, filtername, filterwidth, recompute_roi,
+                  roi, nthreads);
+}
+
+inline ImageBuf
+rotate(const ImageBuf& src, float angle, const std::string& filtername = "",
+       float filterwidth = 0.0f, bool recompute_roi = false, ROI roi = {}, int nthreads = 0)
+{
+    ImageBuf result;
+    bool ok = rotate(result, src, angle, filtername, filterwidth, recompute_roi, roi, nthreads);
+    if (!ok && !result.has_error())
+        result.error("ImageBufAlgo::rotate() error");
+    return result;
+}
+
+/// ImageBufAlgo::fit -- imagebufalgo_xform.cpp:933-1062.  exact=1 takes the
+/// warp path (:1017-1027) with the filter get_resize_filter picks.
 inline bool
 fit(ImageBuf& dst, const ImageBuf& src, const KWArgs& options = {}, ROI roi = {},
     int nthreads = 0)
 {
     if (!detail::prep(roi, dst, src))
         return false;
-    if (options.get_int("exact")) {
-        dst.error("fit: exact=1 takes the warp path, which is outside the B200 "
-                  "resize path");
-        return false;
-    }
-    const ImageSpec& sspec = src.spec();
+    const ImageSpec sspec = src.spec();
     int rw, rh, xo, yo;
     std::string fillmode = options.get_string("fillmode", "letterbox");
+    if (options.get_int("exact")) {
+        float M[9];
+        b2r_fit_exact(sspec.full_width, sspec.full_height, roi.width(), roi.height(),
+                      fillmode.c_str(), M, &rw, &rh);
+        // get_resize_filter on the whole-pixel resize ratios (:1005-1015)
+        const b2r_filter2d* fp = (const b2r_filter2d*)options.get_ptr("filterptr");
+        b2r_filter2d* made     = nullptr;
+        if (!fp) {
+            float wratio = float(rw) / float(sspec.full_width);
+            float hratio = float(rh) / float(sspec.full_height);
+            std::string name = options.get_string("filtername");
+            float fwidth     = options.get_float("filterwidth");
+            if (name.empty())
+                name = (wratio > 1.0f || hratio > 1.0f) ? "blackman-harris" : "lanczos3";
+            for (int i = 0, e = b2r_filter_count(2); i < e && !made; ++i) {
+                const char* nm = nullptr;
+                float w        = 0.0f;
+                b2r_filter_desc(2, i, &nm, &w, nullptr, nullptr, nullptr);
+                if (name == nm)
+                    made = b2r_filter2d_create(
+                        nm, fwidth > 0.0f ? fwidth : w * std::max(1.0f, wratio),
+                        fwidth > 0.0f ? fwidth : w * std::max(1.0f, hratio));
+            }
+            if (!made) {
+                dst.error("Filter \"" + name + "\" not recognized");
+                return false;
+            }
+            fp = made;
+        }
+        ROI newroi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, 0, 1, 0, sspec.nchannels);
+        ImageSpec newspec = sspec;
+        newspec.set_roi(newroi);
+        newspec.set_roi_full(newroi);
+        dst.reset(newspec);
+        bool ok = detail::warp_impl(dst, src, M, fp, "", 0.0f, false, WrapBlack, true, ROI());
+        if (made)
+            b2r_filter2d_destroy(made);
+        return ok;
+    }
     b2r_fit_geometry(sspec.full_width, sspec.full_height, roi.width(), roi.height(),
                      fillmode.c_str(), &rw, &rh, &xo, &yo);
     const int fit_x = roi.xbegin, fit_y = roi.ybegin;

@@ -4,10 +4,12 @@
 //   ImageBufAlgo::resize(dst, src, {{"filtername", f}}, roi);
 // usage: iba_cli errors
 //        iba_cli resize in.raw w h nch basetype dw dh filter out.raw
+//        iba_cli rotate | fitexact  (same arguments)
 //        iba_cli hicomp in.raw w h nch basetype dw dh filter out.raw
 //            (oiiotool --resize:highlightcomp=1 spelled with three IBA calls)
 #include "b2r_imagebufalgo.h"
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -29,8 +31,9 @@ run_errors()
     ImageBuf v(vol);
     ImageBuf r3 = ImageBufAlgo::resize(v, {}, ROI(0, 4, 0, 4, 0, 1, 0, 1));
     printf("3:%s\n", r3.geterror().c_str());
-    ImageBuf r4 = ImageBufAlgo::fit(src, { { "exact", 1 } }, ROI(0, 8, 0, 8, 0, 1, 0, 3));
-    printf("4:%s\n", r4.has_error() ? "refused" : "ok");
+    const float ident[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+    ImageBuf r4 = ImageBufAlgo::warp(src, ident, { { "filtername", "lanczos" } });
+    printf("4:%s\n", r4.geterror().c_str());
     // unrecognised options are ignored (xform.cpp:880)
     ImageBuf r5 = ImageBufAlgo::resize(src, { { "bogus", 1 }, { "filtername", "nope" } },
                                        ROI(0, 8, 0, 8, 0, 1, 0, 3));
@@ -45,7 +48,9 @@ main(int argc, char** argv)
     if (argc >= 2 && std::string(argv[1]) == "errors")
         return run_errors();
     const bool hicomp = argc >= 2 && std::string(argv[1]) == "hicomp";
-    if (argc != 11 || (std::string(argv[1]) != "resize" && !hicomp)) {
+    const bool rotate = argc >= 2 && std::string(argv[1]) == "rotate";
+    const bool fitx   = argc >= 2 && std::string(argv[1]) == "fitexact";
+    if (argc != 11 || (std::string(argv[1]) != "resize" && !hicomp && !rotate && !fitx)) {
         fprintf(stderr, "usage: see source\n");
         return 2;
     }
@@ -65,8 +70,17 @@ main(int argc, char** argv)
             return 5;
         in = &tmpimg;
     }
-    ImageBuf dst = ImageBufAlgo::resize(*in, { { "filtername", argv[9] } },
-                                        ROI(0, dw, 0, dh, 0, 1, 0, c));
+    ImageBuf dst;
+    if (rotate) {  // 30 degrees about the display-window centre, dst = src's window
+        dst = ImageBufAlgo::rotate(src, 30.0f * float(M_PI / 180.0), argv[9]);
+        dw = w, dh = h;
+    } else if (fitx) {
+        dst = ImageBufAlgo::fit(src, { { "exact", 1 }, { "filtername", argv[9] } },
+                                ROI(0, dw, 0, dh, 0, 1, 0, c));
+    } else {
+        dst = ImageBufAlgo::resize(*in, { { "filtername", argv[9] } },
+                                   ROI(0, dw, 0, dh, 0, 1, 0, c));
+    }
     if (hicomp && !dst.has_error() && !ImageBufAlgo::rangeexpand(dst, dst))
         return 6;
     if (dst.has_error()) {

@@ -27,7 +27,7 @@ def test_cpp_error_behaviour(iba_cli):
     assert out[0] == '1:Filter "catrom" not recognized'
     assert out[1] == "2:Uninitialized input image"
     assert out[2] == "3:volumes not supported"
-    assert out[3] == "4:refused"
+    assert out[3] == '4:Filter "lanczos" not recognized'
     assert out[4] == '5:Filter "nope" not recognized'
 
 
@@ -68,3 +68,26 @@ def test_cpp_highlightcomp_three_calls_equal_the_fused_option(iba_cli, oracle, o
     assert oiio.ImageBufAlgo.resize(oiio.ImageBuf(one), oiio.ImageBuf(src),
                                     filtername="lanczos3", highlightcomp=True)
     assert np.array_equal(one, got)
+
+
+@pytest.mark.gpu
+def test_cpp_rotate_and_fit_exact_match_oracle(iba_cli, oracle, tmp_path):
+    import math
+    src = synth.image(120, 90, 3, np.float32, seed=93)
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    src.tofile(fin)
+    subprocess.check_call([iba_cli, "rotate", fin, "120", "90", "3", "11", "120", "90",
+                           "lanczos3", fout])
+    got = np.fromfile(fout, np.float32).reshape(90, 120, 3)
+    ref = np.zeros_like(got)
+    M = oracle.rotate_matrix(np.float32(30.0) * np.float32(math.pi / 180.0), 60.0, 45.0)
+    oracle.warp(oracle.Img(ref), oracle.Img(src), M, "lanczos3", wrap="black")
+    assert np.abs(got - ref).max() <= 1e-5
+    subprocess.check_call([iba_cli, "fitexact", fin, "120", "90", "3", "11", "100", "50",
+                           "", fout])
+    got = np.fromfile(fout, np.float32).reshape(50, 100, 3)
+    Mx, rw, rh = oracle.fit_exact_matrix(120, 90, 100, 50)
+    ref = np.zeros_like(got)
+    oracle.warp(oracle.Img(ref), oracle.Img(src), Mx, "lanczos3", 6.0, 6.0, wrap="black",
+                edgeclamp=True)
+    assert np.abs(got - ref).max() <= 1e-5
