@@ -2,6 +2,7 @@
 """Secondary measurements (not the bench.py contract): device-resident MIP
 chain (BASELINE config 4) and the other BASELINE configs' kernels.
 usage: bench_extra.py mip [size] [filter] [hicomp]
+       bench_extra.py warp         rotate / resize:from-to / fit exact, 4K RGBA f32 and u8
        bench_extra.py range        rangecompress / rangeexpand / highlightcomp resize, 8K RGBA f32"""
 import json
 import os
@@ -73,6 +74,37 @@ def range_ops():
                           "ms": ms}))
 
 
+def warp_ops():
+    """warp kernel, device resident.  Reported per output pixel; the kernel
+    is FP32/L1 bound (taps x channels FMAs per pixel), not HBM bound."""
+    import math
+    import torch
+    import openimageio_b200 as oiio
+    IBA = oiio.ImageBufAlgo
+    w, h = 3840, 2160
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for dt in (torch.float32, torch.float16, torch.uint8):
+        if dt == torch.uint8:
+            src = torch.randint(0, 256, (h, w, 4), dtype=dt, device="cuda", generator=g)
+        else:
+            src = torch.rand((h, w, 4), dtype=torch.float32, device="cuda",
+                             generator=g).to(dt)
+        dst = torch.empty_like(src)
+        S, D = oiio.ImageBuf(src), oiio.ImageBuf(dst)
+        M = oiio.rotate_matrix(30.0 * math.pi / 180.0, w / 2, h / 2)
+        for filt in ("lanczos3", "mitchell", "triangle"):
+            ms = _time(lambda: IBA.warp(D, S, M, filtername=filt, wrap="black"))
+            print(json.dumps({"workload": "rotate 30deg 4K RGBA %s %s" % (dt, filt),
+                              "ms": ms, "out_Mpix_s": w * h / ms / 1e3}))
+        # 2x minification through the warp path (oiiotool --resize:from=...)
+        small = torch.empty((h // 2, w // 2, 4), dtype=dt, device="cuda")
+        R = oiio.ImageBuf(small)
+        Mh = oiio.fromto_matrix((0.5, 0.5, w - 1, h - 1), (0, 0, w // 2, h // 2))
+        ms = _time(lambda: IBA.warp(R, S, Mh, filtername="lanczos3", edgeclamp=True))
+        print(json.dumps({"workload": "warp 4K->2K (from/to) RGBA %s lanczos3" % dt,
+                          "ms": ms, "out_Mpix_s": w * h / 4 / ms / 1e3}))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "mip":
         mip(int(sys.argv[2]) if len(sys.argv) > 2 else 16384,
@@ -80,3 +112,5 @@ if __name__ == "__main__":
             hicomp=len(sys.argv) > 4 and sys.argv[4] == "hicomp")
     elif sys.argv[1] == "range":
         range_ops()
+    elif sys.argv[1] == "warp":
+        warp_ops()
