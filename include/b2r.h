@@ -247,6 +247,38 @@ B2R_API void b2r_fit_exact(int src_full_width, int src_full_height,
                            int fit_width, int fit_height, const char* fillmode,
                            float* M, int* resize_width, int* resize_height);
 
+/* ---- make_kernel / convolve / unsharp_mask ------------------------------
+ * Replaces ImageBufAlgo::make_kernel, convolve_<D,S> and unsharp_mask
+ * (src/libOpenImageIO/imagebufalgo.cpp:864-957, 772-838, 961-1031): the
+ * sharpening maketx wraps around each MIP level's resize (--sharpen,
+ * maketexture.cpp:909-931) and oiiotool --kernel / --convolve / --blur /
+ * --unsharp.  Kernel tables are built on the host with the same Filter2D code
+ * the resize tables use; the device multiplies and adds in the reference's tap
+ * order without contraction, so results match the CPU to the bit. */
+/* name: any Filter2D name, "binomial", "laplacian" (3x3).  The table is kh
+ * rows of kw floats (both odd), window origin (-kw/2, -kh/2).  out NULL =
+ * size query.  An unknown name fills a box AND returns B2R_ERR_FILTER with
+ * `Unknown kernel "name" WxH`, as the reference returns a box plus an error. */
+B2R_API int b2r_make_kernel(const char* name, float width, float height,
+                            int normalize, float* out, int* kw, int* kh,
+                            char* err, size_t errlen);
+/* dst = (normalize ? 1/sum(kernel) : 1) * sum_k kernel[k] * src, WrapClamp at
+ * the edges (:790-807).  kernel: host memory.  dst and src need the same
+ * channel count (IBAprep_REQUIRE_SAME_NCHANNELS) and must not alias. */
+B2R_API int b2r_convolve(const b2r_image* dst, const b2r_image* src,
+                         const float* kernel, int kw, int kh, int normalize,
+                         const b2r_roi* roi, const b2r_options* opt,
+                         b2r_report* report, char* err, size_t errlen);
+/* dst = src + contrast * (src - blur(src)) where |src - blur| > threshold.
+ * kernel NULL or "" -> "gaussian"; width <= 3: one 2-D pass with a
+ * width x width kernel, else two 1-D passes (:997-1019).  "median" is refused
+ * (B2R_ERR_UNSUPPORTED).  dst may be src (in place). */
+B2R_API int b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src,
+                             const char* kernel, float width, float contrast,
+                             float threshold, const b2r_roi* roi,
+                             const b2r_options* opt, b2r_report* report,
+                             char* err, size_t errlen);
+
 /* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
  * The reference parallelises resize by full-width row bands
  * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The
@@ -281,6 +313,24 @@ B2R_API int b2r_mipchain_create(b2r_mipchain** chain, const b2r_image* level0,
                                 const char* filtername, int clamp_half,
                                 int alpha_channel, const b2r_options* opt,
                                 char* err, size_t errlen);
+/* The same with maketx's remaining per-level options: --sharpen <contrast>
+ * (unsharp_mask with `sharpenfilt`, width 3, threshold 0, before or after
+ * each level's resize: maketexture.cpp:909-931; it also turns the "box" fast
+ * path off, :880-881).  With opt->highlightcomp the level is additionally
+ * clamped to [0, FLT_MAX] (alpha to [0,1]) after rangeexpand (:936-938). */
+typedef struct b2r_mip_options {
+    const char* filtername;  /* NULL / "" -> "box" */
+    int32_t clamp_half;
+    int32_t alpha_channel;   /* -1: none */
+    float sharpen;           /* <= 0: off */
+    int32_t sharpen_first;   /* maketx:sharpenfirst */
+    const char* sharpenfilt; /* NULL / "" -> "gaussian" */
+    int32_t reserved[4];
+} b2r_mip_options;
+B2R_API int b2r_mipchain_create_ex(b2r_mipchain** chain, const b2r_image* level0,
+                                   const b2r_mip_options* mip,
+                                   const b2r_options* opt, char* err,
+                                   size_t errlen);
 B2R_API int b2r_mipchain_nlevels(const b2r_mipchain* chain);
 /* Dimensions and device pointer of a level (level 0 = the input). */
 B2R_API int b2r_mipchain_level(const b2r_mipchain* chain, int level,

@@ -64,6 +64,13 @@ class _Options(C.Structure):
                 ("z_channel1", C.c_int32), ("reserved2", C.c_int32)]
 
 
+class _MipOptions(C.Structure):
+    _fields_ = [("filtername", C.c_char_p), ("clamp_half", C.c_int32),
+                ("alpha_channel", C.c_int32), ("sharpen", C.c_float),
+                ("sharpen_first", C.c_int32), ("sharpenfilt", C.c_char_p),
+                ("reserved", C.c_int32 * 4)]
+
+
 class Report(C.Structure):
     _fields_ = [("path_used", C.c_int32), ("kernels_launched", C.c_int32),
                 ("xtaps", C.c_int32), ("ytaps", C.c_int32),
@@ -161,6 +168,21 @@ def lib():
                                       C.c_char_p, C.c_int, C.c_int,
                                       C.POINTER(_Options), C.c_char_p,
                                       C.c_size_t]
+    L.b2r_mipchain_create_ex.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
+                                         C.POINTER(_MipOptions),
+                                         C.POINTER(_Options), C.c_char_p,
+                                         C.c_size_t]
+    L.b2r_make_kernel.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_int,
+                                  C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_int), C.c_char_p, C.c_size_t]
+    L.b2r_convolve.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
+                               C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
+                               C.POINTER(_Roi), C.POINTER(_Options),
+                               C.POINTER(Report), C.c_char_p, C.c_size_t]
+    L.b2r_unsharp_mask.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
+                                   C.c_char_p, C.c_float, C.c_float, C.c_float,
+                                   C.POINTER(_Roi), C.POINTER(_Options),
+                                   C.POINTER(Report), C.c_char_p, C.c_size_t]
     L.b2r_mipchain_nlevels.argtypes = [C.c_void_p]
     L.b2r_mipchain_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
@@ -742,6 +764,115 @@ class _IBA:
         return ok
 
 
+    # ---- make_kernel / convolve / unsharp_mask ---------------------------
+    def make_kernel(self, name, width, height=None, depth=1.0, normalize=True):
+        """ImageBufAlgo::make_kernel (imagebufalgo.cpp:864-957): a 1-channel
+        float ImageBuf whose data window is centred on the origin.  An
+        unknown name gives a box with the error set, like the reference."""
+        if height is None:
+            height = width
+        L = lib()
+        kw, kh = C.c_int(), C.c_int()
+        err = C.create_string_buffer(512)
+        L.b2r_make_kernel(name.encode(), float(width), float(height),
+                          1 if normalize else 0, None, C.byref(kw), C.byref(kh),
+                          err, 512)
+        arr = np.zeros((kh.value, kw.value, 1), np.float32)
+        rc = L.b2r_make_kernel(name.encode(), float(width), float(height),
+                               1 if normalize else 0,
+                               arr.ctypes.data_as(C.POINTER(C.c_float)),
+                               C.byref(kw), C.byref(kh), err, 512)
+        K = ImageBuf(arr)
+        sp = K.spec_
+        sp.x = sp.full_x = -(kw.value // 2)
+        sp.y = sp.full_y = -(kh.value // 2)
+        if rc:
+            K.errorfmt(err.value.decode())
+        return K
+
+    def convolve(self, *args, normalize=True, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::convolve(dst, src, kernel, normalize, roi, nthreads)
+        (imagebufalgo.cpp:817-850)."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:
+            normalize = bool(rest[0])
+        if len(bufs) == 3:
+            return self._convolve(bufs[0], bufs[1], bufs[2], normalize, roi, device)
+        result = ImageBuf()
+        ok = self._convolve(result, bufs[0], bufs[1], normalize, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::convolve() error")
+        return result
+
+    def _stencil_prep(self, roi, dst, src):
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return None
+        if dst.nchannels != src.nchannels:
+            dst.errorfmt("images must have the same number of channels")
+            return None
+        roi.chend = min(roi.chend, dst.nchannels)
+        return roi
+
+    def _convolve(self, dst, src, kernel, normalize, roi, device):
+        roi = self._stencil_prep(roi, dst, src)
+        if roi is None:
+            return False
+        k = np.ascontiguousarray(kernel.get_pixels()[..., 0], np.float32)
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        o = _options(device, PATH_AUTO,
+                     _current_stream(dst) or _current_stream(src))
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_convolve(C.byref(d), C.byref(s),
+                                k.ctypes.data_as(C.POINTER(C.c_float)),
+                                k.shape[1], k.shape[0], 1 if normalize else 0,
+                                C.byref(r), C.byref(o), None, err, 512)
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    def unsharp_mask(self, *args, kernel="gaussian", width=3.0, contrast=1.0,
+                     threshold=0.0, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::unsharp_mask(dst, src, kernel, width, contrast,
+        threshold, roi, nthreads) (imagebufalgo.cpp:975-1045)."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        names = ["kernel", "width", "contrast", "threshold"]
+        vals = dict(kernel=kernel, width=width, contrast=contrast,
+                    threshold=threshold)
+        for n, v in zip(names, rest):
+            vals[n] = v
+        if len(bufs) == 2:
+            return self._unsharp(bufs[0], bufs[1], vals, roi, device)
+        result = ImageBuf()
+        ok = self._unsharp(result, bufs[0], vals, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::unsharp_mask() error")
+        return result
+
+    def _unsharp(self, dst, src, v, roi, device):
+        roi = self._stencil_prep(roi, dst, src)
+        if roi is None:
+            return False
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        o = _options(device, PATH_AUTO,
+                     _current_stream(dst) or _current_stream(src))
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_unsharp_mask(C.byref(d), C.byref(s), v["kernel"].encode(),
+                                    float(v["width"]), float(v["contrast"]),
+                                    float(v["threshold"]), C.byref(r), C.byref(o),
+                                    None, err, 512)
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
     # ---- warp / rotate ----------------------------------------------------
     def warp(self, *args, filtername="", filterwidth=0.0, recompute_roi=False,
              wrap="default", edgeclamp=False, filterptr=None, roi=None,
@@ -1036,9 +1167,12 @@ class MipChain:
     (src/libOpenImageIO/maketexture.cpp:823-986) without host round trips."""
 
     def __init__(self, level0, filtername="box", clamp_half=False, device=0,
-                 highlightcomp=False):
-        """highlightcomp: maketx --hicomp (rangecompress / rangeexpand around
-        every filtered level, maketexture.cpp:907-935)."""
+                 highlightcomp=False, sharpen=0.0, sharpen_first=False,
+                 sharpenfilt="gaussian"):
+        """highlightcomp: maketx --hicomp (rangecompress / rangeexpand + clamp
+        around every filtered level, maketexture.cpp:907-938).  sharpen:
+        maketx --sharpen <contrast> (unsharp mask before / after each level's
+        resize, :909-931)."""
         if not isinstance(level0, ImageBuf):
             level0 = ImageBuf(level0)
         L = lib()
@@ -1048,10 +1182,15 @@ class MipChain:
                      level0.spec_.alpha_channel,
                      getattr(level0.spec_, "z_channel", -1))
         err = C.create_string_buffer(512)
-        rc = L.b2r_mipchain_create(C.byref(h), C.byref(im), filtername.encode(),
-                                   1 if clamp_half else 0,
-                                   level0.spec_.alpha_channel, C.byref(o), err,
-                                   512)
+        mo = _MipOptions()
+        mo.filtername = filtername.encode()
+        mo.clamp_half = 1 if clamp_half else 0
+        mo.alpha_channel = level0.spec_.alpha_channel
+        mo.sharpen = float(sharpen)
+        mo.sharpen_first = 1 if sharpen_first else 0
+        mo.sharpenfilt = (sharpenfilt or "gaussian").encode()
+        rc = L.b2r_mipchain_create_ex(C.byref(h), C.byref(im), C.byref(mo),
+                                      C.byref(o), err, 512)
         if rc:
             raise B2RError(err.value.decode())
         self._h = h

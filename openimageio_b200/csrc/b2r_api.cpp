@@ -11,6 +11,7 @@
 #include "fused_plan.h"
 #include "kernels.h"
 #include "recon_filter.h"
+#include "conv_kernel.h"
 
 #include <cuda_runtime.h>
 
@@ -1897,6 +1898,41 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                     const char* filtername, int clamp_half, int alpha_channel,
                     const b2r_options* opt, char* err, size_t errlen)
 {
+    b2r_mip_options mo;
+    memset(&mo, 0, sizeof(mo));
+    mo.filtername    = filtername;
+    mo.clamp_half    = clamp_half;
+    mo.alpha_channel = alpha_channel;
+    return b2r_mipchain_create_ex(out, level0, &mo, opt, err, errlen);
+}
+
+extern "C" int
+b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
+                       const b2r_mip_options* mo, const b2r_options* opt, char* err,
+                       size_t errlen)
+{
+    if (!mo) {
+        set_err(err, errlen, "mipchain: null options");
+        return B2R_ERR_INVALID;
+    }
+    const char* filtername  = mo->filtername;
+    const int clamp_half    = mo->clamp_half;
+    const int alpha_channel = mo->alpha_channel;
+    const float sharpen     = mo->sharpen;
+    const bool sharpen_first = mo->sharpen_first != 0;
+    const std::string sharpenfilt = (mo->sharpenfilt && mo->sharpenfilt[0]) ? mo->sharpenfilt
+                                                                             : "gaussian";
+    if (sharpen > 0.0f) {
+        if (sharpenfilt == "median") {
+            set_err(err, errlen, "mipchain: the median sharpening kernel is not supported");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        ConvKernel K = make_conv_kernel(sharpenfilt, 3.0f, 3.0f);
+        if (!K.known) {
+            set_err(err, errlen, "%s", K.error.c_str());
+            return B2R_ERR_FILTER;
+        }
+    }
     if (!out) {
         set_err(err, errlen, "mipchain: null output handle");
         return B2R_ERR_INVALID;
@@ -1999,11 +2035,15 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
     sub.path        = opt ? opt->path : B2R_PATH_AUTO;
     sub.cuda_stream = (void*)stream;
     // maketx --hicomp: only the filtered branch is wrapped (:889-935)
-    const bool hicomp = opt && opt->highlightcomp && fname != "box"
+    // sharpening takes the filtered branch even for "box" (:880-881)
+    const bool box_path = fname == "box" && !(sharpen > 0.0f);
+    const bool hicomp   = opt && opt->highlightcomp && !box_path
                         && chain->levels.size() > 1;
+    const bool scratch_needed = hicomp || (sharpen > 0.0f && sharpen_first && !box_path
+                                           && chain->levels.size() > 1);
     const int hc_z    = opt ? opt->z_channel1 - 1 : -1;
     void* hc_tmp      = nullptr;
-    if (hicomp
+    if (scratch_needed
         && cudaMalloc(&hc_tmp, size_t(l0.w) * l0.h * nch * 4) != cudaSuccess) {
         set_err(err, errlen, "mipchain: out of device memory for the highlight "
                              "compensation scratch image");
@@ -2047,7 +2087,7 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
             D.width = D.full_width = sw;
             D.height = D.full_height = sh;
             D.ystride = (int64_t)sw * nch * 4;
-            if (fname == "box") {
+            if (box_path) {
                 if (pass == 0)
                     continue;
                 BoxParams bp;
@@ -2072,8 +2112,28 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                         chain->launches += 1;
                     }
                 }
-                rc = b2r_resize(&D, &R, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
-                                err, errlen);
+                if (sharpen > 0.0f && sharpen_first && pass == 1) {
+                    // unsharp_mask(*sharp, *img, sharpenfilt, 3, sharpen, 0) and
+                    // swap (:910-918): the sharpened copy feeds the resize, the
+                    // level itself stays as it was written
+                    b2r_image T = S;
+                    T.pixels    = hc_tmp;
+                    rc = b2r_unsharp_mask(&T, &R, sharpenfilt.c_str(), 3.0f, sharpen, 0.0f,
+                                          nullptr, &sub, nullptr, err, errlen);
+                    R = T;
+                    chain->launches += 2;
+                } else if (sharpen > 0.0f && sharpen_first) {
+                    R.pixels = hc_tmp;
+                }
+                if (!rc)
+                    rc = b2r_resize(&D, &R, fname.c_str(), 0.0f, nullptr, &sub, nullptr,
+                                    err, errlen);
+                if (!rc && sharpen > 0.0f && !sharpen_first && pass == 1) {
+                    // sharpen the new level in place of itself (:923-931)
+                    rc = b2r_unsharp_mask(&D, &D, sharpenfilt.c_str(), 3.0f, sharpen, 0.0f,
+                                          nullptr, &sub, nullptr, err, errlen);
+                    chain->launches += 2;
+                }
                 if (rc) {
                     if (ev0)
                         cudaEventDestroy(ev0);
@@ -2088,7 +2148,10 @@ b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,
                     b2r_roi all { 0, sw, 0, sh, 0, nch };
                     range_on_device(true, D, D.pixels, D, D.pixels, all, false,
                                     alpha_channel, hc_z, stream);
-                    chain->launches += 1;
+                    // ... and clamp(*small, 0, FLT_MAX, clampalpha01) (:936-938)
+                    launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,
+                                 alpha_channel, 0.0f, 3.402823466e+38f, stream);
+                    chain->launches += 2;
                 }
             }
             if (pass == 1 && clamp_half) {
@@ -2556,4 +2619,370 @@ b2r_fit_exact(int src_full_width, int src_full_height, int fit_width, int fit_he
         *resize_width = rw;
     if (resize_height)
         *resize_height = rh;
+}
+
+// =========================================================================
+// make_kernel / convolve / unsharp_mask  (imagebufalgo.cpp:772-1031)
+// =========================================================================
+#include "conv_kernel.h"
+
+namespace {
+
+// Host<->device staging shared by the stencil entry points: the whole source
+// data window goes up (a stencil may read any of it), the dst ROI comes back.
+struct StencilIO {
+    b2r_roi roi;
+    b2r_image srcd, dstd;
+    void *dsrc = nullptr, *ddst = nullptr;
+    void *src_alloc = nullptr, *dst_alloc = nullptr;
+    unsigned char* host_out = nullptr;
+    size_t dpitch = 0, drowbytes = 0;
+    int roi_w = 0, roi_h = 0, device = 0;
+    bool empty       = false;
+    bool same_pixels = false;  // dst and src are one image (in place)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::unique_ptr<DeviceGuard> guard;
+
+    int begin(const b2r_image* dst_in, const b2r_image* src_in, const b2r_roi* roi_in,
+              const b2r_options* opt, b2r_report* report, const char* what, char* err,
+              size_t errlen)
+    {
+        if (report)
+            memset(report, 0, sizeof(*report));
+        int rc = check_image(src_in, true, err, errlen);
+        if (rc)
+            return rc;
+        rc = check_image(dst_in, false, err, errlen);
+        if (rc)
+            return rc;
+        const b2r_image& dst = *dst_in;
+        const b2r_image& src = *src_in;
+        if (dst.nchannels != src.nchannels) {
+            set_err(err, errlen, "images must have the same number of channels");
+            return B2R_ERR_INVALID;
+        }
+        if (device_count_cached() <= 0) {
+            set_err(err, errlen,
+                    "no CUDA device available: the B200 %s path has no CPU fallback", what);
+            return B2R_ERR_NO_DEVICE;
+        }
+        if (roi_in) {
+            roi         = *roi_in;
+            roi.xbegin  = std::max(roi.xbegin, dst.x);
+            roi.xend    = std::min(roi.xend, dst.x + dst.width);
+            roi.ybegin  = std::max(roi.ybegin, dst.y);
+            roi.yend    = std::min(roi.yend, dst.y + dst.height);
+            roi.chbegin = std::max(roi.chbegin, 0);
+            roi.chend   = std::min(roi.chend, dst.nchannels);
+        } else {
+            roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
+                            dst.nchannels };
+        }
+        if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin || roi.chend <= roi.chbegin) {
+            empty = true;
+            return B2R_OK;
+        }
+        roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
+        const int ses = basetype_size(src.basetype);
+        const int des = basetype_size(dst.basetype);
+        int sdev = opt ? opt->device : 0, ddev = sdev;
+        const int smem = memspace_of(&src, &sdev);
+        const int dmem = memspace_of(&dst, &ddev);
+        device         = opt ? opt->device : 0;
+        if (smem == B2R_MEM_DEVICE)
+            device = sdev;
+        else if (dmem == B2R_MEM_DEVICE)
+            device = ddev;
+        if (device < 0 || device >= device_count_cached()) {
+            set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+            return B2R_ERR_INVALID;
+        }
+        guard.reset(new DeviceGuard(device));
+        device_info(device);
+        stream      = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+        same_pixels = dst.pixels == src.pixels;
+        srcd = src, dstd = dst;
+        dsrc = src.pixels, ddst = dst.pixels;
+        if (smem == B2R_MEM_HOST) {
+            if (src.xstride != (int64_t)src.nchannels * ses) {
+                set_err(err, errlen, "host source pixels must be contiguous in x");
+                return B2R_ERR_UNSUPPORTED;
+            }
+            const size_t rowbytes = size_t(src.width) * src.xstride;
+            const size_t pitch    = (rowbytes + 15) & ~size_t(15);
+            CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * src.height, stream));
+            CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
+                                       src.height, cudaMemcpyHostToDevice, stream));
+            srcd.ystride = (int64_t)pitch;
+            dsrc         = src_alloc;
+            if (report)
+                report->h2d_bytes += (int64_t)rowbytes * src.height;
+        }
+        if (dmem == B2R_MEM_HOST) {
+            if (dst.xstride != (int64_t)dst.nchannels * des) {
+                set_err(err, errlen, "host destination pixels must be contiguous in x");
+                return B2R_ERR_UNSUPPORTED;
+            }
+            drowbytes = size_t(roi_w) * dst.xstride;
+            dpitch    = (drowbytes + 15) & ~size_t(15);
+            CUDA_TRY(cudaMallocAsync(&dst_alloc, dpitch * roi_h, stream));
+            host_out = (unsigned char*)dst.pixels
+                       + (long long)(roi.ybegin - dst.y) * dst.ystride
+                       + (long long)(roi.xbegin - dst.x) * dst.xstride;
+            if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
+                CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
+                                           roi_h, cudaMemcpyHostToDevice, stream));
+                if (report)
+                    report->h2d_bytes += (int64_t)drowbytes * roi_h;
+            }
+            ddst         = dst_alloc;
+            dstd.x       = roi.xbegin;
+            dstd.y       = roi.ybegin;
+            dstd.width   = roi_w;
+            dstd.height  = roi_h;
+            dstd.ystride = (int64_t)dpitch;
+        }
+        if (report) {
+            cudaEventCreate(&ev0);
+            cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, stream);
+        }
+        return B2R_OK;
+    }
+
+    int end(const b2r_image& dst, b2r_report* report, int launched, char* err, size_t errlen)
+    {
+        if (report)
+            cudaEventRecord(ev1, stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
+            return B2R_ERR_CUDA;
+        }
+        if (dst_alloc) {
+            CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
+                                       roi_h, cudaMemcpyDeviceToHost, stream));
+            if (report)
+                report->d2h_bytes += (int64_t)drowbytes * roi_h;
+        }
+        release();
+        if (dst_alloc || src_alloc || report)
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        if (report) {
+            cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
+            cudaEventDestroy(ev0);
+            cudaEventDestroy(ev1);
+            ev0 = ev1                = nullptr;
+            report->kernels_launched = launched;
+            report->path_used        = B2R_PATH_EXACT;
+        }
+        return B2R_OK;
+    }
+
+    void release()
+    {
+        if (dst_alloc)
+            cudaFreeAsync(dst_alloc, stream);
+        if (src_alloc)
+            cudaFreeAsync(src_alloc, stream);
+    }
+    ~StencilIO()
+    {
+        if (ev0)
+            cudaEventDestroy(ev0);
+        if (ev1)
+            cudaEventDestroy(ev1);
+    }
+};
+
+// upload a host float table; freed stream-ordered by the caller
+int
+upload_floats(const float* host, size_t n, cudaStream_t stream, float** out, char* err,
+              size_t errlen)
+{
+    CUDA_TRY(cudaMallocAsync((void**)out, n * sizeof(float), stream));
+    CUDA_TRY(cudaMemcpyAsync(*out, host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    return B2R_OK;
+}
+
+float
+kernel_scale(const float* k, int n, bool normalize)
+{
+    if (!normalize)
+        return 1.0f;
+    float s = 0.0f;
+    for (int i = 0; i < n; ++i)
+        s += k[i];
+    return 1.0f / s;
+}
+
+void
+run_convolve(const b2r_image& dstd, void* ddst, const b2r_image& srcd, void* dsrc,
+             const b2r_roi& roi, const float* dkernel, int kw, int kh, float scale,
+             cudaStream_t stream)
+{
+    ConvParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.dst     = to_dev(dstd, ddst);
+    cp.src     = to_dev(srcd, dsrc);
+    cp.roi_x0  = std::max(roi.xbegin, dstd.x);
+    cp.roi_x1  = std::min(roi.xend, dstd.x + dstd.width);
+    cp.roi_y0  = std::max(roi.ybegin, dstd.y);
+    cp.roi_y1  = std::min(roi.yend, dstd.y + dstd.height);
+    cp.chbegin = roi.chbegin;
+    cp.chend   = roi.chend;
+    cp.kernel  = dkernel;
+    cp.kw      = kw;
+    cp.kh      = kh;
+    cp.scale   = scale;
+    launch_convolve(cp, stream);
+}
+
+}  // namespace
+
+/* ImageBufAlgo::make_kernel (imagebufalgo.cpp:864-957), depth 1. */
+extern "C" int
+b2r_make_kernel(const char* name, float width, float height, int normalize, float* out,
+                int* kw, int* kh, char* err, size_t errlen)
+{
+    ConvKernel K = make_conv_kernel(name ? name : "", width, height, normalize != 0);
+    if (kw)
+        *kw = K.w;
+    if (kh)
+        *kh = K.h;
+    if (out)
+        memcpy(out, K.v.data(), K.v.size() * sizeof(float));
+    if (!K.known) {
+        set_err(err, errlen, "%s", K.error.c_str());
+        return B2R_ERR_FILTER;
+    }
+    return B2R_OK;
+}
+
+extern "C" int
+b2r_convolve(const b2r_image* dst, const b2r_image* src, const float* kernel, int kw, int kh,
+             int normalize, const b2r_roi* roi, const b2r_options* opt, b2r_report* report,
+             char* err, size_t errlen)
+{
+    if (!kernel || kw <= 0 || kh <= 0) {
+        set_err(err, errlen, "convolve: no kernel");
+        return B2R_ERR_INVALID;
+    }
+    StencilIO io;
+    int rc = io.begin(dst, src, roi, opt, report, "convolve", err, errlen);
+    if (rc || io.empty) {
+        io.release();
+        return rc;
+    }
+    if (io.same_pixels) {
+        io.release();
+        set_err(err, errlen, "convolve: dst and src must be different images");
+        return B2R_ERR_INVALID;
+    }
+    float* dk = nullptr;
+    rc        = upload_floats(kernel, (size_t)kw * kh, io.stream, &dk, err, errlen);
+    if (rc) {
+        io.release();
+        return rc;
+    }
+    run_convolve(io.dstd, io.ddst, io.srcd, io.dsrc, io.roi, dk, kw, kh,
+                 kernel_scale(kernel, kw * kh, normalize != 0), io.stream);
+    cudaFreeAsync(dk, io.stream);
+    return io.end(*dst, report, 1, err, errlen);
+}
+
+extern "C" int
+b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src, const char* kernel, float width,
+                 float contrast, float threshold, const b2r_roi* roi, const b2r_options* opt,
+                 b2r_report* report, char* err, size_t errlen)
+{
+    const std::string kname = (kernel && kernel[0]) ? kernel : "gaussian";
+    if (kname == "median") {
+        set_err(err, errlen,
+                "unsharp_mask: the median kernel is not part of the B200 resampling path");
+        return B2R_ERR_UNSUPPORTED;
+    }
+    // the kernels first: an unknown name is an error before anything is staged
+    const bool two_pass = width > 3.0;
+    ConvKernel K = two_pass ? make_conv_kernel(kname, 1, width) : make_conv_kernel(kname, width, width);
+    if (!K.known) {
+        set_err(err, errlen, "%s", K.error.c_str());
+        return B2R_ERR_FILTER;
+    }
+    StencilIO io;
+    int rc = io.begin(dst, src, roi, opt, report, "unsharp_mask", err, errlen);
+    if (rc || io.empty) {
+        io.release();
+        return rc;
+    }
+    // Blurry (and fst_pass): float images with src's windows, zero filled (:988-992)
+    const b2r_image& S = io.srcd;
+    const size_t brow  = size_t(S.width) * S.nchannels * sizeof(float);
+    const size_t bsize = brow * S.height;
+    void *blur = nullptr, *first = nullptr;
+    float* dk  = nullptr;
+    auto fail  = [&](int code) {
+        if (blur)
+            cudaFreeAsync(blur, io.stream);
+        if (first)
+            cudaFreeAsync(first, io.stream);
+        if (dk)
+            cudaFreeAsync(dk, io.stream);
+        io.release();
+        return code;
+    };
+    if (cudaMallocAsync(&blur, bsize, io.stream) != cudaSuccess
+        || cudaMemsetAsync(blur, 0, bsize, io.stream) != cudaSuccess) {
+        set_err(err, errlen, "CUDA error allocating the blur image");
+        return fail(B2R_ERR_CUDA);
+    }
+    b2r_image B = S;
+    B.pixels    = blur;
+    B.basetype  = B2R_FLOAT;
+    B.xstride   = (int64_t)S.nchannels * 4;
+    B.ystride   = (int64_t)brow;
+    B.memspace  = B2R_MEM_DEVICE;
+    rc          = upload_floats(K.v.data(), K.v.size(), io.stream, &dk, err, errlen);
+    if (rc)
+        return fail(rc);
+    b2r_roi croi  = io.roi;  // convolve runs over every channel (:1004-1019 pass roi as is)
+    const float s = kernel_scale(K.v.data(), K.w * K.h, true);
+    int launched  = 0;
+    if (two_pass) {
+        if (cudaMallocAsync(&first, bsize, io.stream) != cudaSuccess
+            || cudaMemsetAsync(first, 0, bsize, io.stream) != cudaSuccess) {
+            set_err(err, errlen, "CUDA error allocating the first-pass image");
+            return fail(B2R_ERR_CUDA);
+        }
+        b2r_image F = B;
+        F.pixels    = first;
+        run_convolve(F, first, S, io.dsrc, croi, dk, K.w, K.h, s, io.stream);
+        // Kt = transpose(K): same values, K.h wide and K.w tall
+        run_convolve(B, blur, F, first, croi, dk, K.h, K.w, s, io.stream);
+        launched += 2;
+    } else {
+        run_convolve(B, blur, S, io.dsrc, croi, dk, K.w, K.h, s, io.stream);
+        launched += 1;
+    }
+    UnsharpParams up;
+    memset(&up, 0, sizeof(up));
+    up.dst       = to_dev(io.dstd, io.ddst);
+    up.src       = to_dev(S, io.dsrc);
+    up.blur      = to_dev(B, blur);
+    up.roi_x0    = io.roi.xbegin;
+    up.roi_x1    = io.roi.xend;
+    up.roi_y0    = io.roi.ybegin;
+    up.roi_y1    = io.roi.yend;
+    up.chbegin   = io.roi.chbegin;
+    up.chend     = io.roi.chend;
+    up.contrast  = contrast;
+    up.threshold = threshold;
+    launch_unsharp_combine(up, io.stream);
+    ++launched;
+    cudaFreeAsync(blur, io.stream);
+    if (first)
+        cudaFreeAsync(first, io.stream);
+    cudaFreeAsync(dk, io.stream);
+    return io.end(*dst, report, launched, err, errlen);
 }

@@ -1,0 +1,155 @@
+// conv_kernels.cu -- ImageBufAlgo::convolve and the combine step of
+// unsharp_mask on the device (src/libOpenImageIO/imagebufalgo.cpp:772-812,
+// 961-985): what maketx's --sharpen wraps around every MIP level's resize
+// (maketexture.cpp:909-931) and oiiotool --convolve/--blur/--unsharp run.
+//
+// convolve: one thread per destination pixel, channels in passes of four,
+// taps in the reference's order (kernel rows outer, columns inner) with
+// multiply-then-add -- no contraction -- so results equal the CPU's to the bit
+// (the kernel table is built on the host).  Source pixels are wrapped like a
+// WrapClamp iterator: clamp to the display window, black if that still misses
+// the data window.  Neighbouring threads share almost all of their taps, so
+// the source goes through L1 (ld.global.nc); a 3x3 or 5x5 blur is HBM-bound
+// (one read + one write per pixel), 15x15 is FP32-bound.
+#include "dev_convert.cuh"
+
+#include <algorithm>
+
+namespace b2r {
+namespace {
+
+constexpr int CONV_BX = 32, CONV_BY = 8;
+
+template<bool VEC_F32>
+__global__ void __launch_bounds__(CONV_BX* CONV_BY)
+convolve_kernel(const ConvParams p)
+{
+    pdl_prologue();
+    const int x = p.roi_x0 + blockIdx.x * CONV_BX + threadIdx.x;
+    if (x >= p.roi_x1)
+        return;
+    const DevImage& S = p.src;
+    const int ses = S.basetype == BT_UINT8 ? 1 : (S.basetype == BT_FLOAT ? 4 : 2);
+    const int des = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
+    const int kx0 = -(p.kw / 2), ky0 = -(p.kh / 2);
+    const int fx0 = S.full_x, fx1 = S.full_x + S.full_width - 1;
+    const int fy0 = S.full_y, fy1 = S.full_y + S.full_height - 1;
+    for (int y = p.roi_y0 + blockIdx.y * CONV_BY + threadIdx.y; y < p.roi_y1;
+         y += gridDim.y * CONV_BY) {
+        unsigned char* dp = (unsigned char*)p.dst.pixels
+                            + (long long)(y - p.dst.y) * p.dst.ystride
+                            + (long long)(x - p.dst.x) * p.dst.xstride;
+        for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
+            float sum[4] = { 0.f, 0.f, 0.f, 0.f };
+            const float* k = p.kernel;
+#pragma unroll 1
+            for (int j = 0; j < p.kh; ++j) {
+                const int ty = y + ky0 + j;
+#pragma unroll 1
+                for (int i = 0; i < p.kw; ++i, ++k) {
+                    const float w = __ldg(k);
+                    int px = x + kx0 + i, py = ty;
+                    bool ok = px >= S.x && px < S.x + S.width && py >= S.y
+                              && py < S.y + S.height;
+                    if (!ok) {
+                        px = min(max(px, fx0), fx1);
+                        py = min(max(py, fy0), fy1);
+                        ok = px >= S.x && px < S.x + S.width && py >= S.y
+                             && py < S.y + S.height;
+                    }
+                    float v[4] = { 0.f, 0.f, 0.f, 0.f };
+                    if (ok) {
+                        const unsigned char* sp = (const unsigned char*)S.pixels
+                                                  + (long long)(py - S.y) * S.ystride
+                                                  + (long long)(px - S.x) * S.xstride
+                                                  + c0 * ses;
+                        if (VEC_F32) {
+                            const float4 q = __ldg((const float4*)sp);
+                            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                if (c0 + c < S.nchannels)
+                                    v[c] = load_elem(sp + c * ses, S.basetype);
+                        }
+                    }
+                    // a black tap still adds k * 0 (sign of zero aside: no effect)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ch = c0 + c;
+                if (ch >= p.chbegin && ch < p.chend)
+                    store_elem(dp + ch * des, p.dst.basetype, __fmul_rn(p.scale, sum[c]));
+            }
+        }
+    }
+}
+
+// unsharp_impl: d = s + contrast * (s - b) where |s - b| > threshold, else s
+__global__ void __launch_bounds__(256)
+unsharp_combine_kernel(const UnsharpParams p)
+{
+    pdl_prologue();
+    const int x = p.roi_x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= p.roi_x1)
+        return;
+    const DevImage &S = p.src, &B = p.blur;
+    const int ses = S.basetype == BT_UINT8 ? 1 : (S.basetype == BT_FLOAT ? 4 : 2);
+    const int des = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
+    for (int y = p.roi_y0 + blockIdx.y; y < p.roi_y1; y += gridDim.y) {
+        const bool in = x >= S.x && x < S.x + S.width && y >= S.y && y < S.y + S.height;
+        const unsigned char* sp = (const unsigned char*)S.pixels
+                                  + (long long)(y - S.y) * S.ystride
+                                  + (long long)(x - S.x) * S.xstride;
+        const float* bp = (const float*)((const unsigned char*)B.pixels
+                                         + (long long)(y - B.y) * B.ystride
+                                         + (long long)(x - B.x) * B.xstride);
+        unsigned char* dp = (unsigned char*)p.dst.pixels
+                            + (long long)(y - p.dst.y) * p.dst.ystride
+                            + (long long)(x - p.dst.x) * p.dst.xstride;
+        for (int c = p.chbegin; c < p.chend; ++c) {
+            const float s    = in ? load_elem(sp + c * ses, S.basetype) : 0.0f;
+            const float b    = in ? __ldg(bp + c) : 0.0f;
+            const float diff = __fsub_rn(s, b);
+            float v          = s;
+            if (fabsf(diff) > p.threshold)
+                v = __fadd_rn(s, __fmul_rn(p.contrast, diff));
+            store_elem(dp + c * des, p.dst.basetype, v);
+        }
+    }
+}
+
+}  // namespace
+
+void
+launch_convolve(const ConvParams& p, void* stream)
+{
+    const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
+    if (w <= 0 || h <= 0)
+        return;
+    dim3 grid((w + CONV_BX - 1) / CONV_BX, std::min((h + CONV_BY - 1) / CONV_BY, 32768), 1);
+    const bool vec = p.src.basetype == BT_FLOAT && p.src.nchannels == 4 && p.src.xstride == 16
+                     && (uintptr_t)p.src.pixels % 16 == 0 && p.src.ystride % 16 == 0;
+    if (vec)
+        launch_pdl(convolve_kernel<true>, grid, dim3(CONV_BX, CONV_BY), 0,
+                   (cudaStream_t)stream, p);
+    else
+        launch_pdl(convolve_kernel<false>, grid, dim3(CONV_BX, CONV_BY), 0,
+                   (cudaStream_t)stream, p);
+}
+
+void
+launch_unsharp_combine(const UnsharpParams& p, void* stream)
+{
+    const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
+    if (w <= 0 || h <= 0)
+        return;
+    dim3 grid((w + 255) / 256, std::min(h, 32768), 1);
+    launch_pdl(unsharp_combine_kernel, grid, dim3(256), 0, (cudaStream_t)stream, p);
+}
+
+}  // namespace b2r

@@ -237,6 +237,28 @@ struct WarpParams {
 void
 launch_warp(const WarpParams& p, void* stream);
 
+// ------------------------------------------------- convolve / unsharp ----
+// convolve_ (imagebufalgo.cpp:772-812): dst = scale * sum_k kernel[k] * src
+struct ConvParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    const float* kernel;  // device, kh rows of kw; window origin (-kw/2, -kh/2)
+    int kw, kh;
+    float scale;          // 1 / sum(kernel) when normalising, else 1
+};
+void
+launch_convolve(const ConvParams& p, void* stream);
+// unsharp_impl (imagebufalgo.cpp:961-985); blur is float32 with src's windows
+struct UnsharpParams {
+    DevImage dst, src, blur;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    float contrast, threshold;
+};
+void
+launch_unsharp_combine(const UnsharpParams& p, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

@@ -103,6 +103,20 @@ void orc_fit_exact_matrix(int src_full_w, int src_full_h, int fit_w, int fit_h,
                           const char* fillmode, float* M, int* resize_w,
                           int* resize_h);
 
+/* ImageBufAlgo::make_kernel / convolve / unsharp_mask restated
+ * (imagebufalgo.cpp:772-1031; "median" excluded).  Pinned against
+ * testsuite/oiiotool/ref/{bspline-blur,gauss5x5-blur,unsharp}.tif.
+ * orc_make_kernel: out == NULL queries the size; returns 1 for an unknown
+ * kernel name (the reference returns a box plus an error). */
+int orc_make_kernel(const char* name, float width, float height, int normalize,
+                    float* out, int* kw, int* kh);
+int orc_convolve(const orc_image* dst, const orc_image* src, const float* kernel,
+                 int kw, int kh, int normalize, orc_roi roi, int chbegin, int chend,
+                 int nthreads);
+int orc_unsharp_mask(const orc_image* dst, const orc_image* src, const char* kernel,
+                     float width, float contrast, float threshold, orc_roi roi,
+                     int nthreads, char* err, int errlen);
+
 /* float -> dst-type store and src-type -> float load used by the above
  * (fmath.h:753-764, 1009-1031); exposed for unit tests. */
 float orc_load_as_float(const void* p, int basetype);

@@ -19,6 +19,7 @@ Sources (all under /root/reference/testsuite, OpenImageIO 3.2.0.2-dev):
   common/tahoe-small.tif + oiiotool/ref/range{compress,expand}{,-luma}.tif
   oiiotool-xform/ref/{warped,rotated,rotated-offcenter,resizefrom*}.tif,
   oiiotool-xform/src/target1.exr, ref/fit4.exr, two of ref/fit[wh]-*.exr
+  oiiotool/ref/bspline-blur.tif, gauss5x5-blur.tif, unsharp.tif
 Only pixel arrays are stored (no reference source code is copied).
 """
 import os
@@ -102,6 +103,18 @@ def main():
     for k, v in wp.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(os.path.join(HERE, "warp_ref.npz"), **wp)
+
+    # make_kernel / convolve / blur / unsharp known answers
+    # (testsuite/oiiotool/run.py:159-182); the input tahoe-small.tif is in
+    # pixelmath_ref.npz
+    cv = {}
+    # (bsplinekernel.exr has a negative data-window origin that cv2's EXR
+    # reader refuses; bspline-blur.tif pins the same kernel through convolve)
+    for name in ["bspline-blur", "gauss5x5-blur", "unsharp"]:
+        cv[name.replace("-", "_")] = read(os.path.join(REF, "oiiotool/ref", name + ".tif"))
+    for k, v in cv.items():
+        print(k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(HERE, "conv_ref.npz"), **cv)
 
 
 if __name__ == "__main__":

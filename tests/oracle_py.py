@@ -90,6 +90,15 @@ def lib():
         for fn in (L.orc_m33_inverse, L.orc_rotate_matrix, L.orc_fromto_matrix,
                    L.orc_transform_roi, L.orc_fit_exact_matrix):
             fn.restype = None
+        L.orc_make_kernel.argtypes = [C.c_char_p, C.c_float, C.c_float, C.c_int,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]
+        L.orc_convolve.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
+                                   C.POINTER(C.c_float), C.c_int, C.c_int, C.c_int,
+                                   OrcRoi, C.c_int, C.c_int, C.c_int]
+        L.orc_unsharp_mask.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
+                                       C.c_char_p, C.c_float, C.c_float, C.c_float,
+                                       OrcRoi, C.c_int, C.c_char_p, C.c_int]
         L.orc_load_as_float.argtypes = [C.c_void_p, C.c_int]
         L.orc_store_from_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
         _lib = L
@@ -259,6 +268,50 @@ def fit_exact_matrix(src_full_w, src_full_h, fit_w, fit_h, fillmode="letterbox")
     return np.array(list(out), np.float32).reshape(3, 3), rw.value, rh.value
 
 
+def make_kernel(name, width, height, normalize=True):
+    """(kernel array (kh, kw) float32, known) -- ImageBufAlgo::make_kernel."""
+    kw, kh = C.c_int(), C.c_int()
+    lib().orc_make_kernel(name.encode(), float(width), float(height),
+                          int(normalize), None, C.byref(kw), C.byref(kh))
+    out = np.zeros((kh.value, kw.value), np.float32)
+    rc = lib().orc_make_kernel(name.encode(), float(width), float(height),
+                               int(normalize),
+                               out.ctypes.data_as(C.POINTER(C.c_float)),
+                               C.byref(kw), C.byref(kh))
+    return out, rc == 0
+
+
+def _full_roi(dst, roi):
+    if roi is None:
+        roi = (dst.x, dst.x + dst.arr.shape[1], dst.y, dst.y + dst.arr.shape[0])
+    return OrcRoi(*roi)
+
+
+def convolve(dst, src, kernel, normalize=True, roi=None, chrange=None, nthreads=0):
+    k = np.ascontiguousarray(kernel, np.float32)
+    d, s = dst.c(), src.c()
+    cb, ce = chrange if chrange else (0, dst.nchannels)
+    rc = lib().orc_convolve(C.byref(d), C.byref(s),
+                            k.ctypes.data_as(C.POINTER(C.c_float)), k.shape[1],
+                            k.shape[0], int(normalize), _full_roi(dst, roi), cb, ce,
+                            int(nthreads))
+    if rc:
+        raise RuntimeError("orc_convolve failed")
+    return dst
+
+
+def unsharp_mask(dst, src, kernel="gaussian", width=3.0, contrast=1.0,
+                 threshold=0.0, roi=None, nthreads=0):
+    d, s = dst.c(), src.c()
+    err = C.create_string_buffer(512)
+    rc = lib().orc_unsharp_mask(C.byref(d), C.byref(s), kernel.encode(), float(width),
+                                float(contrast), float(threshold),
+                                _full_roi(dst, roi), int(nthreads), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return dst
+
+
 def resize_block(dst, src, allow_shift=False):
     L = lib()
     d, s = dst.c(), src.c()
@@ -275,27 +328,42 @@ def fit_geometry(sw, sh, fw, fh, fillmode="letterbox"):
     return tuple(i.value for i in v)
 
 
-def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1):
+def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1,
+              sharpen=0.0, sharpen_first=False, sharpenfilt="gaussian"):
     """write_mipmap level loop (maketexture.cpp:823-986) on a float32 HxWxC
     array, no file output.  Returns [level1, level2, ...].  highlightcomp:
-    maketx --hicomp, rangecompress(img) / rangeexpand(small) around every
-    filtered level (:907-935)."""
+    maketx --hicomp, rangecompress(img) / rangeexpand(small) + clamp around
+    every filtered level (:907-938); sharpen: maketx --sharpen (:909-931)."""
     assert level0.dtype == np.float32
     out = []
+    fmax = np.float32(3.402823466e+38)
     img = level0.copy() if highlightcomp else level0
     while img.shape[1] > 1 or img.shape[0] > 1:
         h, w, c = img.shape
         sw = w // 2 if w > 1 else w
         sh = h // 2 if h > 1 else h
         small = np.empty((sh, sw, c), np.float32)
-        if filtername == "box":
+        if filtername == "box" and not sharpen > 0:
             resize_block(Img(small), Img(img))
         else:
             if highlightcomp:
                 rangecompress(Img(img), Img(img), alpha_channel=alpha_channel)
+            if sharpen > 0 and sharpen_first:
+                sharp = np.empty_like(img)
+                unsharp_mask(Img(sharp), Img(img), sharpenfilt, 3.0, sharpen, 0.0)
+                img = sharp
             resize(Img(small), Img(img), filtername)
+            if sharpen > 0 and not sharpen_first:
+                sharp = np.empty_like(small)
+                unsharp_mask(Img(sharp), Img(small), sharpenfilt, 3.0, sharpen, 0.0)
+                small = sharp
             if highlightcomp:
                 rangeexpand(Img(small), Img(small), alpha_channel=alpha_channel)
+                # ImageBufAlgo::clamp(small, small, 0, FLT_MAX, clampalpha01=true)
+                np.clip(small, np.float32(0), fmax, out=small)
+                if alpha_channel >= 0:
+                    np.clip(small[..., alpha_channel], 0, 1,
+                            out=small[..., alpha_channel])
         out.append(small)
         # the reference compresses img in place AFTER the level was written
         # to the file: keep the returned level intact

@@ -337,3 +337,41 @@ def test_oracle_warp_matrix_algebra(oracle):
     # transform(M, roi): bounding box of the pixel-centre corners
     T = np.array([[1, 0, 0], [0, 1, 0], [10, -5, 1]], np.float32)
     assert oracle.transform_roi(T, (0, 100, 0, 50)) == (10, 110, -5, 45)
+
+
+# ------------------------------------- oracle: make_kernel / convolve ------
+def test_oracle_convolve_goldens(oracle):
+    """testsuite/oiiotool: --kernel bspline 15x15 --convolve (bit for bit),
+    --blur 5x5 and --unsharp (1 LSB on < 2e-5 of the values: the stored images
+    come from a build whose float sums round differently in a handful of
+    places; idiff's tolerance is 1 LSB everywhere)."""
+    P = np.load(os.path.join(GOLD, "pixelmath_ref.npz"))
+    Cv = np.load(os.path.join(GOLD, "conv_ref.npz"))
+    t = P["tahoe_small"]
+    K, known = oracle.make_kernel("bspline", 15, 15)
+    assert known and K.shape == (15, 15) and abs(K.sum() - 1) < 1e-6
+    out = np.zeros_like(t)
+    oracle.convolve(oracle.Img(out), oracle.Img(t), K)
+    assert np.array_equal(out, Cv["bspline_blur"])
+    K, _ = oracle.make_kernel("gaussian", 5, 5)
+    out = np.zeros_like(t)
+    oracle.convolve(oracle.Img(out), oracle.Img(t), K)
+    d = np.abs(out.astype(int) - Cv["gauss5x5_blur"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 2e-5
+    out = np.zeros_like(t)
+    oracle.unsharp_mask(oracle.Img(out), oracle.Img(t))
+    d = np.abs(out.astype(int) - Cv["unsharp"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 2e-5
+
+
+def test_oracle_make_kernel_shapes(oracle):
+    K, known = oracle.make_kernel("gaussian", 3.0, 3.0)
+    assert known and K.shape == (3, 3) and K[1, 1] == K.max()
+    K, known = oracle.make_kernel("gaussian", 1, 5.0)       # unsharp width > 3
+    assert K.shape == (5, 1)
+    K, known = oracle.make_kernel("binomial", 5, 5)
+    assert known and np.allclose(K[2] * 256, np.array([6, 24, 36, 24, 6]))
+    K, known = oracle.make_kernel("laplacian", 3, 3)
+    assert known and K.sum() == 0 and K[1, 1] == -4
+    K, known = oracle.make_kernel("nonesuch", 4, 4)
+    assert not known and K.shape == (5, 5) and np.allclose(K, 1 / 25)
