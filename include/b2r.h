@@ -228,6 +228,23 @@ B2R_API int b2r_warp_filter(const b2r_image* dst, const b2r_image* src,
                             int edgeclamp, const b2r_roi* roi,
                             const b2r_options* opt, b2r_report* report,
                             char* err, size_t errlen);
+/* ---- st_warp -----------------------------------------------------------
+ * Replaces st_warp_<D,S,ST> (imagebufalgo_xform.cpp:1834-1925; argument
+ * checks :1929-1972): dst(x,y) = filtered sample of src around
+ * (S * src.full_width, T * src.full_height), S/T read from channels chan_s /
+ * chan_t of `st` at (x,y).  The ROI is intersected with st's data window.
+ * Filter as for b2r_warp. */
+B2R_API int b2r_st_warp(const b2r_image* dst, const b2r_image* src,
+                        const b2r_image* st, const char* filtername,
+                        float filterwidth, int chan_s, int chan_t, int flip_s,
+                        int flip_t, const b2r_roi* roi, const b2r_options* opt,
+                        b2r_report* report, char* err, size_t errlen);
+B2R_API int b2r_st_warp_filter(const b2r_image* dst, const b2r_image* src,
+                               const b2r_image* st, const b2r_filter2d* filter,
+                               int chan_s, int chan_t, int flip_s, int flip_t,
+                               const b2r_roi* roi, const b2r_options* opt,
+                               b2r_report* report, char* err, size_t errlen);
+
 /* Host matrix helpers, float32 in Imath's operation order (Imath 3.1
  * Matrix33<float>; Imath is an external dependency of the reference). */
 B2R_API void b2r_m33_inverse(const float* M, float* out);

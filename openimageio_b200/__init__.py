@@ -146,6 +146,12 @@ def lib():
                                   C.c_void_p, C.c_int, C.c_int, C.POINTER(_Roi),
                                   C.POINTER(_Options), C.POINTER(Report),
                                   C.c_char_p, C.c_size_t]
+    L.b2r_st_warp.argtypes = [C.POINTER(_Image)] * 3 + [C.c_char_p, C.c_float] + \
+        [C.c_int] * 4 + [C.POINTER(_Roi), C.POINTER(_Options), C.POINTER(Report),
+                         C.c_char_p, C.c_size_t]
+    L.b2r_st_warp_filter.argtypes = [C.POINTER(_Image)] * 3 + [C.c_void_p] + \
+        [C.c_int] * 4 + [C.POINTER(_Roi), C.POINTER(_Options), C.POINTER(Report),
+                         C.c_char_p, C.c_size_t]
     L.b2r_m33_inverse.argtypes = [F9, F9]
     L.b2r_rotate_matrix.argtypes = [C.c_float] * 3 + [F9]
     L.b2r_fromto_matrix.argtypes = [C.c_float] * 8 + [F9]
@@ -962,6 +968,74 @@ class _IBA:
                             C.byref(o), C.byref(rep) if want_report else None,
                             err, 512)
         self.last_report = rep if want_report else None
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    def st_warp(self, *args, filtername="", filterwidth=0.0, chan_s=0, chan_t=1,
+                flip_s=False, flip_t=False, filterptr=None, roi=None, nthreads=0,
+                device=0):
+        """ImageBufAlgo::st_warp(dst, src, stbuf, filtername, filterwidth,
+        chan_s, chan_t, flip_s, flip_t, roi, nthreads)
+        (imagebufalgo_xform.cpp:1976-2058)."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if rest:
+            filtername = rest[0]
+        if len(rest) > 1:
+            filterwidth = rest[1]
+        if len(bufs) == 3:
+            return self._st_warp(bufs[0], bufs[1], bufs[2], filtername, filterwidth,
+                                 filterptr, chan_s, chan_t, flip_s, flip_t, roi,
+                                 device)
+        result = ImageBuf()
+        ok = self._st_warp(result, bufs[0], bufs[1], filtername, filterwidth,
+                           filterptr, chan_s, chan_t, flip_s, flip_t, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::st_warp : Unknown error")
+        return result
+
+    def _st_warp(self, dst, src, st, filtername, filterwidth, filterptr, chan_s,
+                 chan_t, flip_s, flip_t, roi, device):
+        if filterptr is None:
+            name = filtername or "lanczos3"
+            if name not in [fd[0] for fd in _filter_descs()]:
+                dst.errorfmt('Filter "%s" not recognized' % name)
+                return False
+        # check_st_warp_args (:1929-1972)
+        if st is None or not st.initialized:
+            dst.errorfmt("ImageBufAlgo::st_warp : Uninitialized ST buffer")
+            return False
+        if chan_s >= st.nchannels:
+            dst.errorfmt("ImageBufAlgo::st_warp : Out-of-range S channel index: %d"
+                         % chan_s)
+            return False
+        if chan_t >= st.nchannels:
+            dst.errorfmt("ImageBufAlgo::st_warp : Out-of-range T channel index: %d"
+                         % chan_t)
+            return False
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        roi.chend = min(roi.chend, dst.nchannels, src.nchannels)
+        d, s, t = dst._c(), src._c(), st._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        stream = _current_stream(dst) or _current_stream(src)
+        o = _options(device, PATH_AUTO, stream)
+        err = C.create_string_buffer(512)
+        if filterptr is not None:
+            rc = lib().b2r_st_warp_filter(C.byref(d), C.byref(s), C.byref(t),
+                                          filterptr._h, chan_s, chan_t,
+                                          1 if flip_s else 0, 1 if flip_t else 0,
+                                          C.byref(r), C.byref(o), None, err, 512)
+        else:
+            rc = lib().b2r_st_warp(C.byref(d), C.byref(s), C.byref(t),
+                                   (filtername or "").encode(), float(filterwidth),
+                                   chan_s, chan_t, 1 if flip_s else 0,
+                                   1 if flip_t else 0, C.byref(r), C.byref(o), None,
+                                   err, 512)
         if rc:
             dst.errorfmt(err.value.decode())
             return False

@@ -2646,7 +2646,7 @@ struct StencilIO {
 
     int begin(const b2r_image* dst_in, const b2r_image* src_in, const b2r_roi* roi_in,
               const b2r_options* opt, b2r_report* report, const char* what, char* err,
-              size_t errlen)
+              size_t errlen, bool same_nchannels = true)
     {
         if (report)
             memset(report, 0, sizeof(*report));
@@ -2658,7 +2658,7 @@ struct StencilIO {
             return rc;
         const b2r_image& dst = *dst_in;
         const b2r_image& src = *src_in;
-        if (dst.nchannels != src.nchannels) {
+        if (same_nchannels && dst.nchannels != src.nchannels) {
             set_err(err, errlen, "images must have the same number of channels");
             return B2R_ERR_INVALID;
         }
@@ -2767,7 +2767,7 @@ struct StencilIO {
                 report->d2h_bytes += (int64_t)drowbytes * roi_h;
         }
         release();
-        if (dst_alloc || src_alloc || report)
+        if (dst_alloc || src_alloc || extra_alloc || report)
             CUDA_TRY(cudaStreamSynchronize(stream));
         if (report) {
             cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
@@ -2780,12 +2780,41 @@ struct StencilIO {
         return B2R_OK;
     }
 
+    // a further input image (st_warp's ST buffer): whole data window up
+    void* extra_alloc = nullptr;
+    int stage_extra(const b2r_image& im, b2r_image* imd, void** dpix, b2r_report* report,
+                    char* err, size_t errlen)
+    {
+        *imd  = im;
+        *dpix = im.pixels;
+        int dev = device;
+        if (memspace_of(&im, &dev) != B2R_MEM_HOST)
+            return B2R_OK;
+        const int es = basetype_size(im.basetype);
+        if (im.xstride != (int64_t)im.nchannels * es) {
+            set_err(err, errlen, "host pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        const size_t rowbytes = size_t(im.width) * im.xstride;
+        const size_t pitch    = (rowbytes + 15) & ~size_t(15);
+        CUDA_TRY(cudaMallocAsync(&extra_alloc, pitch * im.height, stream));
+        CUDA_TRY(cudaMemcpy2DAsync(extra_alloc, pitch, im.pixels, im.ystride, rowbytes,
+                                   im.height, cudaMemcpyHostToDevice, stream));
+        imd->ystride = (int64_t)pitch;
+        *dpix        = extra_alloc;
+        if (report)
+            report->h2d_bytes += (int64_t)rowbytes * im.height;
+        return B2R_OK;
+    }
+
     void release()
     {
         if (dst_alloc)
             cudaFreeAsync(dst_alloc, stream);
         if (src_alloc)
             cudaFreeAsync(src_alloc, stream);
+        if (extra_alloc)
+            cudaFreeAsync(extra_alloc, stream);
     }
     ~StencilIO()
     {
@@ -2985,4 +3014,136 @@ b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src, const char* kernel,
         cudaFreeAsync(first, io.stream);
     cudaFreeAsync(dk, io.stream);
     return io.end(*dst, report, launched, err, errlen);
+}
+
+
+// =========================================================================
+// st_warp (imagebufalgo_xform.cpp:1834-2058)
+// =========================================================================
+namespace {
+int
+st_warp_impl(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
+             const Filter2D& filter, int chan_s, int chan_t, int flip_s, int flip_t,
+             const b2r_roi* roi_in, const b2r_options* opt, b2r_report* report, char* err,
+             size_t errlen)
+{
+    // check_st_warp_args (:1929-1972)
+    if (!st || !st->pixels || st->width <= 0 || st->height <= 0 || st->nchannels <= 0) {
+        set_err(err, errlen, "ImageBufAlgo::st_warp : Uninitialized ST buffer");
+        return B2R_ERR_INVALID;
+    }
+    if (!valid_basetype(st->basetype)) {
+        set_err(err, errlen, "unsupported pixel data type %d", st->basetype);
+        return B2R_ERR_TYPES;
+    }
+    if (chan_s >= st->nchannels || chan_s < 0) {
+        set_err(err, errlen, "ImageBufAlgo::st_warp : Out-of-range S channel index: %d",
+                chan_s);
+        return B2R_ERR_INVALID;
+    }
+    if (chan_t >= st->nchannels || chan_t < 0) {
+        set_err(err, errlen, "ImageBufAlgo::st_warp : Out-of-range T channel index: %d",
+                chan_t);
+        return B2R_ERR_INVALID;
+    }
+    StencilIO io;
+    int rc = io.begin(dst, src, roi_in, opt, report, "st_warp", err, errlen, false);
+    if (rc || io.empty) {
+        io.release();
+        return rc;
+    }
+    io.roi.chend = std::min(io.roi.chend, src->nchannels);
+    // the warp is only defined where the ST image has pixels
+    b2r_roi r = io.roi;
+    r.xbegin  = std::max(r.xbegin, st->x), r.xend = std::min(r.xend, st->x + st->width);
+    r.ybegin  = std::max(r.ybegin, st->y), r.yend = std::min(r.yend, st->y + st->height);
+    if (r.xend <= r.xbegin || r.yend <= r.ybegin) {
+        io.release();
+        set_err(err, errlen,
+                "ImageBufAlgo::st_warp : Output ROI does not intersect ST buffer.");
+        return B2R_ERR_INVALID;
+    }
+    if (io.dst_alloc && (r.xbegin != io.roi.xbegin || r.xend != io.roi.xend
+                         || r.ybegin != io.roi.ybegin || r.yend != io.roi.yend
+                         || io.roi.chbegin != 0 || io.roi.chend != dst->nchannels)) {
+        // part of the staged dst ROI will not be written: bring its pixels over
+        cudaMemcpy2DAsync(io.dst_alloc, io.dpitch, io.host_out, dst->ystride, io.drowbytes,
+                          io.roi_h, cudaMemcpyHostToDevice, io.stream);
+    }
+    b2r_image std_;
+    void* dst_pix = nullptr;
+    rc = io.stage_extra(*st, &std_, &dst_pix, report, err, errlen);
+    if (rc) {
+        io.release();
+        return rc;
+    }
+    StWarpParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.dst     = to_dev(io.dstd, io.ddst);
+    sp.src     = to_dev(io.srcd, io.dsrc);
+    sp.st      = to_dev(std_, dst_pix);
+    sp.roi_x0  = r.xbegin;
+    sp.roi_x1  = r.xend;
+    sp.roi_y0  = r.ybegin;
+    sp.roi_y1  = r.yend;
+    sp.chbegin = io.roi.chbegin;
+    sp.chend   = io.roi.chend;
+    sp.chan_s  = chan_s;
+    sp.chan_t  = chan_t;
+    sp.flip_s  = flip_s ? 1 : 0;
+    sp.flip_t  = flip_t ? 1 : 0;
+    const float xscale = float(dst->full_width) / src->full_width;
+    const float yscale = float(dst->full_height) / src->full_height;
+    sp.filterrad_x     = (int)ceilf(filter.width() / 2.0f / xscale);
+    sp.filterrad_y     = (int)ceilf(filter.height() / 2.0f / yscale);
+    const Filter2D::DeviceDesc fd = filter.device_desc();
+    sp.filt_profile = fd.profile;
+    sp.filt_scale   = fd.scale;
+    sp.filt_param   = fd.param;
+    sp.filt_w       = fd.w;
+    sp.filt_h       = fd.h;
+    launch_st_warp(sp, io.stream);
+    return io.end(*dst, report, 1, err, errlen);
+}
+}  // namespace
+
+extern "C" int
+b2r_st_warp_filter(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
+                   const b2r_filter2d* filter, int chan_s, int chan_t, int flip_s,
+                   int flip_t, const b2r_roi* roi, const b2r_options* opt,
+                   b2r_report* report, char* err, size_t errlen)
+{
+    if (!filter || !filter->f) {  // :1994-1998
+        std::unique_ptr<Filter2D, void (*)(Filter2D*)> f(Filter2D::create("lanczos3", 6.0f,
+                                                                          6.0f),
+                                                         Filter2D::destroy);
+        return st_warp_impl(dst, src, st, *f, chan_s, chan_t, flip_s, flip_t, roi, opt, report,
+                            err, errlen);
+    }
+    return st_warp_impl(dst, src, st, *filter->f, chan_s, chan_t, flip_s, flip_t, roi, opt,
+                        report, err, errlen);
+}
+
+extern "C" int
+b2r_st_warp(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
+            const char* filtername, float filterwidth, int chan_s, int chan_t, int flip_s,
+            int flip_t, const b2r_roi* roi, const b2r_options* opt, b2r_report* report,
+            char* err, size_t errlen)
+{
+    std::string name = (filtername && filtername[0]) ? filtername : "lanczos3";
+    std::unique_ptr<Filter2D, void (*)(Filter2D*)> filter(nullptr, Filter2D::destroy);
+    for (int i = 0, e = Filter2D::num_filters(); i < e; ++i) {
+        const FilterDesc& fd = Filter2D::get_filterdesc(i);
+        if (name == fd.name) {
+            const float w = filterwidth > 0.0f ? filterwidth : fd.width;
+            filter.reset(Filter2D::create(name, w, w));
+            break;
+        }
+    }
+    if (!filter) {
+        set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
+        return B2R_ERR_FILTER;
+    }
+    return st_warp_impl(dst, src, st, *filter, chan_s, chan_t, flip_s, flip_t, roi, opt,
+                        report, err, errlen);
 }

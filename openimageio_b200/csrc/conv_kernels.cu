@@ -20,7 +20,9 @@ namespace {
 
 constexpr int CONV_BX = 32, CONV_BY = 8;
 
-template<bool VEC_F32>
+// KW, KH > 0: compile-time kernel extent (taps fully unrolled, weights in
+// registers); 0: run-time extent.
+template<bool VEC_F32, int KW, int KH>
 __global__ void __launch_bounds__(CONV_BX* CONV_BY)
 convolve_kernel(const ConvParams p)
 {
@@ -31,38 +33,39 @@ convolve_kernel(const ConvParams p)
     const DevImage& S = p.src;
     const int ses = S.basetype == BT_UINT8 ? 1 : (S.basetype == BT_FLOAT ? 4 : 2);
     const int des = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
-    const int kx0 = -(p.kw / 2), ky0 = -(p.kh / 2);
+    const int kw = KW > 0 ? KW : p.kw, kh = KH > 0 ? KH : p.kh;
+    const int kx0 = -(kw / 2), ky0 = -(kh / 2);
     const int fx0 = S.full_x, fx1 = S.full_x + S.full_width - 1;
     const int fy0 = S.full_y, fy1 = S.full_y + S.full_height - 1;
+    float wreg[KW > 0 ? KW * KH : 1];
+    if (KW > 0) {
+#pragma unroll
+        for (int i = 0; i < KW * KH; ++i)
+            wreg[i] = __ldg(p.kernel + i);
+    }
+    const bool x_inside = x + kx0 >= S.x && x + kx0 + kw <= S.x + S.width;
     for (int y = p.roi_y0 + blockIdx.y * CONV_BY + threadIdx.y; y < p.roi_y1;
          y += gridDim.y * CONV_BY) {
         unsigned char* dp = (unsigned char*)p.dst.pixels
                             + (long long)(y - p.dst.y) * p.dst.ystride
                             + (long long)(x - p.dst.x) * p.dst.xstride;
+        // the whole stencil inside the data window: no wrap tests
+        const bool interior = x_inside && y + ky0 >= S.y && y + ky0 + kh <= S.y + S.height;
         for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
             float sum[4] = { 0.f, 0.f, 0.f, 0.f };
-            const float* k = p.kernel;
-#pragma unroll 1
-            for (int j = 0; j < p.kh; ++j) {
-                const int ty = y + ky0 + j;
-#pragma unroll 1
-                for (int i = 0; i < p.kw; ++i, ++k) {
-                    const float w = __ldg(k);
-                    int px = x + kx0 + i, py = ty;
-                    bool ok = px >= S.x && px < S.x + S.width && py >= S.y
-                              && py < S.y + S.height;
-                    if (!ok) {
-                        px = min(max(px, fx0), fx1);
-                        py = min(max(py, fy0), fy1);
-                        ok = px >= S.x && px < S.x + S.width && py >= S.y
-                             && py < S.y + S.height;
-                    }
-                    float v[4] = { 0.f, 0.f, 0.f, 0.f };
-                    if (ok) {
-                        const unsigned char* sp = (const unsigned char*)S.pixels
-                                                  + (long long)(py - S.y) * S.ystride
-                                                  + (long long)(px - S.x) * S.xstride
-                                                  + c0 * ses;
+            if (interior) {
+                const unsigned char* rowp = (const unsigned char*)S.pixels
+                                            + (long long)(y + ky0 - S.y) * S.ystride
+                                            + (long long)(x + kx0 - S.x) * S.xstride
+                                            + c0 * ses;
+                const float* k = p.kernel;
+#pragma unroll(KH > 0 ? KH : 1)
+                for (int j = 0; j < kh; ++j, rowp += S.ystride) {
+                    const unsigned char* sp = rowp;
+#pragma unroll(KW > 0 ? KW : 1)
+                    for (int i = 0; i < kw; ++i, sp += S.xstride) {
+                        const float w = KW > 0 ? wreg[KW > 0 ? j * KW + i : 0] : __ldg(k++);
+                        float v[4] = { 0.f, 0.f, 0.f, 0.f };
                         if (VEC_F32) {
                             const float4 q = __ldg((const float4*)sp);
                             v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
@@ -72,11 +75,49 @@ convolve_kernel(const ConvParams p)
                                 if (c0 + c < S.nchannels)
                                     v[c] = load_elem(sp + c * ses, S.basetype);
                         }
-                    }
-                    // a black tap still adds k * 0 (sign of zero aside: no effect)
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                        for (int c = 0; c < 4; ++c)
+                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                    }
+                }
+            } else {
+                const float* k = p.kernel;
+#pragma unroll 1
+                for (int j = 0; j < kh; ++j) {
+                    const int ty = y + ky0 + j;
+#pragma unroll 1
+                    for (int i = 0; i < kw; ++i, ++k) {
+                        const float w = __ldg(k);
+                        int px = x + kx0 + i, py = ty;
+                        bool ok = px >= S.x && px < S.x + S.width && py >= S.y
+                                  && py < S.y + S.height;
+                        if (!ok) {
+                            px = min(max(px, fx0), fx1);
+                            py = min(max(py, fy0), fy1);
+                            ok = px >= S.x && px < S.x + S.width && py >= S.y
+                                 && py < S.y + S.height;
+                        }
+                        float v[4] = { 0.f, 0.f, 0.f, 0.f };
+                        if (ok) {
+                            const unsigned char* sp = (const unsigned char*)S.pixels
+                                                      + (long long)(py - S.y) * S.ystride
+                                                      + (long long)(px - S.x) * S.xstride
+                                                      + c0 * ses;
+                            if (VEC_F32) {
+                                const float4 q = __ldg((const float4*)sp);
+                                v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c)
+                                    if (c0 + c < S.nchannels)
+                                        v[c] = load_elem(sp + c * ses, S.basetype);
+                            }
+                        }
+                        // a black tap still adds k * 0 (sign of zero aside: no effect)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                    }
                 }
             }
 #pragma unroll
@@ -134,12 +175,18 @@ launch_convolve(const ConvParams& p, void* stream)
     dim3 grid((w + CONV_BX - 1) / CONV_BX, std::min((h + CONV_BY - 1) / CONV_BY, 32768), 1);
     const bool vec = p.src.basetype == BT_FLOAT && p.src.nchannels == 4 && p.src.xstride == 16
                      && (uintptr_t)p.src.pixels % 16 == 0 && p.src.ystride % 16 == 0;
-    if (vec)
-        launch_pdl(convolve_kernel<true>, grid, dim3(CONV_BX, CONV_BY), 0,
-                   (cudaStream_t)stream, p);
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 block(CONV_BX, CONV_BY);
+    if (vec && p.kw == 3 && p.kh == 3)  // unsharp_mask's default, maketx --sharpen
+        launch_pdl(convolve_kernel<true, 3, 3>, grid, block, 0, st, p);
+    else if (vec && p.kw == 5 && p.kh == 5)
+        launch_pdl(convolve_kernel<true, 5, 5>, grid, block, 0, st, p);
+    else if (vec)
+        launch_pdl(convolve_kernel<true, 0, 0>, grid, block, 0, st, p);
+    else if (p.kw == 3 && p.kh == 3)
+        launch_pdl(convolve_kernel<false, 3, 3>, grid, block, 0, st, p);
     else
-        launch_pdl(convolve_kernel<false>, grid, dim3(CONV_BX, CONV_BY), 0,
-                   (cudaStream_t)stream, p);
+        launch_pdl(convolve_kernel<false, 0, 0>, grid, block, 0, st, p);
 }
 
 void

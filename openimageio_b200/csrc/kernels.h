@@ -237,6 +237,19 @@ struct WarpParams {
 void
 launch_warp(const WarpParams& p, void* stream);
 
+// st_warp_<D,S,ST> (imagebufalgo_xform.cpp:1834-1925)
+struct StWarpParams {
+    DevImage dst, src, st;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    int chan_s, chan_t, flip_s, flip_t;
+    int filterrad_x, filterrad_y;  // ceil(filter extent / 2 / scale), source pixels
+    int filt_profile, filt_scale;
+    float filt_param, filt_w, filt_h;
+};
+void
+launch_st_warp(const StWarpParams& p, void* stream);
+
 // ------------------------------------------------- convolve / unsharp ----
 // convolve_ (imagebufalgo.cpp:772-812): dst = scale * sum_k kernel[k] * src
 struct ConvParams {

@@ -22,7 +22,8 @@
 // source goes through the read-only L1 path (ld.global.nc) from 32x8-pixel
 // thread blocks; whole pixels are fetched with one vector load when the
 // layout allows.  The kernel is FP32/L1 bound, not HBM bound (49 taps per
-// pixel at the default lanczos3).
+// pixel at the default lanczos3).  Pixels whose footprint lies inside the data
+// window (almost all of them) take a fast path without the per-tap wrap tests.
 #include "dev_convert.cuh"
 #include "dev_filters.cuh"
 
@@ -217,7 +218,33 @@ warp_kernel(const WarpParams p)
             const int ncs = min(4, S.nchannels - c0);  // source channels in this pass
             float sum[4]  = { 0.0f, 0.0f, 0.0f, 0.0f };
             float total_w = 0.0f;
-            if (!black) {
+            // Interior fast path: the whole footprint lies inside the data
+            // window and the column factors are cached -- no wrap tests, one
+            // row pointer per footprint row, the same taps in the same order.
+            const bool interior = cache && !black && smin >= sxb && smax <= sxe
+                                  && tmin >= syb && tmax <= sye;
+            if (interior) {
+                const unsigned char* rowp = (const unsigned char*)S.pixels
+                                            + (long long)(tmin - syb) * S.ystride
+                                            + (long long)(smin - sxb) * S.xstride + c0 * ses;
+#pragma unroll 1
+                for (int ty = tmin; ty < tmax; ++ty, rowp += S.ystride) {
+                    const float yarg
+                        = __fmul_rn(dt_inv, __fsub_rn(__fadd_rn(float(ty), 0.5f), t));
+                    const float wy          = dev_axis_value(filt, filt.h, yarg);
+                    const unsigned char* sp = rowp;
+#pragma unroll 1
+                    for (int i = 0; i < ntx; ++i, sp += S.xstride) {
+                        const float w = __fmul_rn(wxc[i], wy);
+                        float v[4];
+                        load_px<BT, VEC>(sp, ncs, v);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                        total_w = __fadd_rn(total_w, w);
+                    }
+                }
+            } else if (!black) {
 #pragma unroll 1
                 for (int ty = tmin; ty < tmax; ++ty) {
                     const float yarg
@@ -287,6 +314,113 @@ warp_kernel(const WarpParams p)
     }
 }
 
+// st_warp_<D,S,ST> (imagebufalgo_xform.cpp:1834-1925): the source position of
+// every destination pixel comes from two channels of an ST image; the
+// footprint is filter radius / scale source pixels around it, clipped to the
+// data window, inclusive of its upper bound (rerange(x_min, x_max + 1, ...)),
+// and a tap that falls outside the data window reads black.
+template<int BT, bool VEC>
+__global__ void __launch_bounds__(WARP_BX* WARP_BY)
+st_warp_kernel(const StWarpParams p)
+{
+    pdl_prologue();
+    const int x = p.roi_x0 + blockIdx.x * WARP_BX + threadIdx.x;
+    if (x >= p.roi_x1)
+        return;
+    const DevImage& S = p.src;
+    const int ses     = (BT == BT_UINT8) ? 1 : (BT == BT_FLOAT ? 4 : 2);
+    const int des     = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
+    const int tes     = p.st.basetype == BT_UINT8 ? 1 : (p.st.basetype == BT_FLOAT ? 4 : 2);
+    DevFilter filt;
+    filt.profile = p.filt_profile, filt.scale = p.filt_scale;
+    filt.param = p.filt_param, filt.w = p.filt_w, filt.h = p.filt_h;
+    const bool separable = p.filt_scale < 5;
+    const int sxb = S.x, sxe = S.x + S.width, syb = S.y, sye = S.y + S.height;
+    const float fsw = float(S.full_width), fsh = float(S.full_height);
+    const float radx = float(p.filterrad_x), rady = float(p.filterrad_y);
+
+    for (int y = p.roi_y0 + blockIdx.y * WARP_BY + threadIdx.y; y < p.roi_y1;
+         y += gridDim.y * WARP_BY) {
+        const unsigned char* tp = (const unsigned char*)p.st.pixels
+                                  + (long long)(y - p.st.y) * p.st.ystride
+                                  + (long long)(x - p.st.x) * p.st.xstride;
+        float src_s = load_elem(tp + p.chan_s * tes, p.st.basetype);
+        float src_t = load_elem(tp + p.chan_t * tes, p.st.basetype);
+        if (p.flip_s)
+            src_s = __fsub_rn(1.0f, src_s);
+        if (p.flip_t)
+            src_t = __fsub_rn(1.0f, src_t);
+        const float src_x = __fmul_rn(src_s, fsw), src_y = __fmul_rn(src_t, fsh);
+        const int x_min   = min(max((int)floorf(__fsub_rn(src_x, radx)), sxb), sxe);
+        const int x_max   = min(max((int)ceilf(__fadd_rn(src_x, radx)), sxb), sxe);
+        const int y_min   = min(max((int)floorf(__fsub_rn(src_y, rady)), syb), sye);
+        const int y_max   = min(max((int)ceilf(__fadd_rn(src_y, rady)), syb), sye);
+        unsigned char* dp = (unsigned char*)p.dst.pixels
+                            + (long long)(y - p.dst.y) * p.dst.ystride
+                            + (long long)(x - p.dst.x) * p.dst.xstride;
+        const int ntx    = x_max + 1 - x_min;
+        const bool cache = separable && ntx <= WARP_WXC;
+        float wxc[WARP_WXC];
+        if (cache) {
+#pragma unroll 1
+            for (int i = 0; i < ntx; ++i)
+                wxc[i] = dev_axis_value(filt, filt.w,
+                                        __fadd_rn(__fsub_rn(float(x_min + i), src_x), 0.5f));
+        }
+        for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
+            const int ncs = min(4, S.nchannels - c0);
+            float sum[4]  = { 0.0f, 0.0f, 0.0f, 0.0f };
+            float total_w = 0.0f;
+#pragma unroll 1
+            for (int ty = y_min; ty <= y_max; ++ty) {
+                const float yarg = __fadd_rn(__fsub_rn(float(ty), src_y), 0.5f);
+                const float wy   = separable ? dev_axis_value(filt, filt.h, yarg) : 0.0f;
+                const bool row_in = ty < sye;  // ty >= syb by construction
+                const unsigned char* sp = (const unsigned char*)S.pixels
+                                          + (long long)(ty - syb) * S.ystride
+                                          + (long long)(x_min - sxb) * S.xstride + c0 * ses;
+#pragma unroll 1
+                for (int tx = x_min; tx <= x_max; ++tx, sp += S.xstride) {
+                    float w;
+                    if (cache)
+                        w = __fmul_rn(wxc[tx - x_min], wy);
+                    else {
+                        const float xarg = __fadd_rn(__fsub_rn(float(tx), src_x), 0.5f);
+                        w = separable ? __fmul_rn(dev_axis_value(filt, filt.w, xarg), wy)
+                                      : dev_filter2d(filt, xarg, yarg);
+                    }
+                    total_w = __fadd_rn(total_w, w);
+                    if (row_in && tx < sxe) {
+                        float v[4];
+                        load_px<BT, VEC>(sp, ncs, v);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            sum[c] = __fadd_rn(sum[c], __fmul_rn(v[c], w));
+                    }
+                }
+            }
+            const bool norm = total_w > 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int ch = c0 + c;
+                if (ch >= p.chbegin && ch < p.chend)
+                    store_elem(dp + ch * des, p.dst.basetype,
+                               (norm && c < ncs) ? __fdiv_rn(sum[c], total_w) : 0.0f);
+            }
+        }
+    }
+}
+
+template<int BT>
+void
+launch_st_bt(const StWarpParams& p, bool vec, dim3 grid, cudaStream_t st)
+{
+    if (vec)
+        launch_pdl(st_warp_kernel<BT, true>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+    else
+        launch_pdl(st_warp_kernel<BT, false>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+}
+
 template<int BT>
 void
 launch_bt(const WarpParams& p, bool vec, dim3 grid, cudaStream_t st)
@@ -315,6 +449,25 @@ launch_warp(const WarpParams& p, void* stream)
     case BT_UINT16: launch_bt<BT_UINT16>(p, vec, grid, st); break;
     case BT_HALF: launch_bt<BT_HALF>(p, vec, grid, st); break;
     default: launch_bt<BT_FLOAT>(p, vec, grid, st); break;
+    }
+}
+
+void
+launch_st_warp(const StWarpParams& p, void* stream)
+{
+    const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
+    if (w <= 0 || h <= 0)
+        return;
+    dim3 grid((w + WARP_BX - 1) / WARP_BX, std::min((h + WARP_BY - 1) / WARP_BY, 32768), 1);
+    const int es   = basetype_size(p.src.basetype);
+    const bool vec = p.src.nchannels == 4 && p.src.xstride == 4 * es
+                     && (uintptr_t)p.src.pixels % (4 * es) == 0 && p.src.ystride % (4 * es) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p.src.basetype) {
+    case BT_UINT8: launch_st_bt<BT_UINT8>(p, vec, grid, st); break;
+    case BT_UINT16: launch_st_bt<BT_UINT16>(p, vec, grid, st); break;
+    case BT_HALF: launch_st_bt<BT_HALF>(p, vec, grid, st); break;
+    default: launch_st_bt<BT_FLOAT>(p, vec, grid, st); break;
     }
 }
 

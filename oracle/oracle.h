@@ -94,6 +94,13 @@ int orc_rangeexpand(const orc_image* dst, const orc_image* src, int useluma,
 int orc_warp(const orc_image* dst, const orc_image* src, const float* M,
              const char* filtername, float fw, float fh, int wrap, int edgeclamp,
              orc_roi roi, int nthreads, char* err, int errlen);
+/* ImageBufAlgo::st_warp restated (imagebufalgo_xform.cpp:1834-1925): every dst
+ * pixel looks its source position up in the ST image.  Pinned against
+ * testsuite/oiiotool-xform/ref/st_warped.tif. */
+int orc_st_warp(const orc_image* dst, const orc_image* src, const orc_image* st,
+                int chan_s, int chan_t, int flip_s, int flip_t,
+                const char* filtername, float fw, float fh, orc_roi roi,
+                int chbegin, int chend, int nthreads, char* err, int errlen);
 void orc_m33_inverse(const float* M, float* out);
 void orc_rotate_matrix(float angle, float cx, float cy, float* out);
 void orc_fromto_matrix(float from_x, float from_y, float from_w, float from_h,

@@ -429,3 +429,74 @@ orc_fit_exact_matrix(int src_full_w, int src_full_h, int fit_w, int fit_h, const
     *resize_w = rw;
     *resize_h = rh;
 }
+
+// st_warp_<D,S,ST> (xform.cpp:1834-1925).  The filter is given resolved.
+// Source pixels outside the data window read as black (the iterator's default
+// wrap); their weights still count in the normalisation.
+extern "C" int
+orc_st_warp(const orc_image* dst, const orc_image* src, const orc_image* st, int chan_s,
+            int chan_t, int flip_s, int flip_t, const char* filtername, float fw, float fh,
+            orc_roi roi, int chbegin, int chend, int nthreads, char* err, int errlen)
+{
+    OrcFilter2D filter;
+    if (!orc_make_filter2d(filtername && filtername[0] ? filtername : "lanczos3", fw, fh,
+                           &filter)) {
+        snprintf(err, errlen, "Filter \"%s\" not recognized", filtername ? filtername : "");
+        return 1;
+    }
+    const int src_width = src->full_width, src_height = src->full_height;
+    const float xscale = float(dst->full_width) / src_width;
+    const float yscale = float(dst->full_height) / src_height;
+    const int xbegin = src->x, xend = src->x + src->width;
+    const int ybegin = src->y, yend = src->y + src->height;
+    const int filterrad_x = (int)ceilf(filter.w / 2.0f / xscale);
+    const int filterrad_y = (int)ceilf(filter.h / 2.0f / yscale);
+    const int ses = esize(src->basetype), des = esize(dst->basetype), tes = esize(st->basetype);
+    // the ROI is intersected with the ST image's window (check_st_warp_args)
+    roi.xbegin = std::max(roi.xbegin, st->x), roi.xend = std::min(roi.xend, st->x + st->width);
+    roi.ybegin = std::max(roi.ybegin, st->y), roi.yend = std::min(roi.yend, st->y + st->height);
+    orc_parallel_bands(roi, nthreads, [&](orc_roi r) {
+        float acc[64];
+        for (int y = r.ybegin; y < r.yend; ++y)
+            for (int x = r.xbegin; x < r.xend; ++x) {
+                if (x < dst->x || x >= dst->x + dst->width || y < dst->y
+                    || y >= dst->y + dst->height)
+                    continue;
+                const unsigned char* tp = (const unsigned char*)st->pixels
+                                          + int64_t(y - st->y) * st->ystride
+                                          + int64_t(x - st->x) * st->xstride;
+                float src_s = orc_load_as_float(tp + chan_s * tes, st->basetype);
+                float src_t = orc_load_as_float(tp + chan_t * tes, st->basetype);
+                if (flip_s)
+                    src_s = 1.0f - src_s;
+                if (flip_t)
+                    src_t = 1.0f - src_t;
+                const float src_x = src_s * src_width;
+                const float src_y = src_t * src_height;
+                const int x_min = clampi((int)floorf(src_x - filterrad_x), xbegin, xend);
+                const int x_max = clampi((int)ceilf(src_x + filterrad_x), xbegin, xend);
+                const int y_min = clampi((int)floorf(src_y - filterrad_y), ybegin, yend);
+                const int y_max = clampi((int)ceilf(src_y + filterrad_y), ybegin, yend);
+                for (int c = chbegin; c < chend; ++c)
+                    acc[c] = 0.0f;
+                float total_weight = 0.0f;
+                for (int sy = y_min; sy < y_max + 1; ++sy)
+                    for (int sx = x_min; sx < x_max + 1; ++sx) {
+                        const float weight = orc_f2d_eval(filter, sx - src_x + 0.5f,
+                                                          sy - src_y + 0.5f);
+                        total_weight += weight;
+                        const unsigned char* p = wrapped_pixel(*src, sx, sy, 1);
+                        for (int c = chbegin; c < chend; ++c)
+                            acc[c] += (p ? orc_load_as_float(p + c * ses, src->basetype) : 0.0f)
+                                      * weight;
+                    }
+                unsigned char* dp = (unsigned char*)dst->pixels
+                                    + int64_t(y - dst->y) * dst->ystride
+                                    + int64_t(x - dst->x) * dst->xstride;
+                for (int c = chbegin; c < chend; ++c)
+                    orc_store_from_float(dp + c * des, dst->basetype,
+                                         total_weight > 0.0f ? acc[c] / total_weight : 0.0f);
+            }
+    });
+    return 0;
+}

@@ -89,7 +89,7 @@ def main():
     # (testsuite/oiiotool-xform/run.py); inputs resize.tif and grid.tif are in
     # xform_ref.npz already
     wp = {}
-    for name in ["warped", "rotated", "rotated-offcenter", "resizefrom",
+    for name in ["warped", "rotated", "rotated-offcenter", "st_warped", "resizefrom",
                  "resizefromto", "resizefromtooffset"]:
         wp[name.replace("-", "_")] = read(os.path.join(xdir, name + ".tif"))
     for name, path in [("target1", "oiiotool-xform/src/target1.exr"),

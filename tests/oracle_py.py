@@ -80,6 +80,9 @@ def lib():
         L.orc_warp.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage), F9,
                                C.c_char_p, C.c_float, C.c_float, C.c_int, C.c_int,
                                OrcRoi, C.c_int, C.c_char_p, C.c_int]
+        L.orc_st_warp.argtypes = [C.POINTER(OrcImage)] * 3 + [C.c_int] * 4 + \
+            [C.c_char_p, C.c_float, C.c_float, OrcRoi, C.c_int, C.c_int, C.c_int,
+             C.c_char_p, C.c_int]
         L.orc_m33_inverse.argtypes = [F9, F9]
         L.orc_rotate_matrix.argtypes = [C.c_float] * 3 + [F9]
         L.orc_fromto_matrix.argtypes = [C.c_float] * 8 + [F9]
@@ -229,6 +232,21 @@ def warp(dst, src, M, filtername="lanczos3", fw=0.0, fh=0.0, wrap="default",
     rc = lib().orc_warp(C.byref(d), C.byref(s), _m9(M), (filtername or "").encode(),
                         float(fw), float(fh), WRAP[wrap], int(bool(edgeclamp)),
                         OrcRoi(*roi), int(nthreads), err, 512)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    return dst
+
+
+def st_warp(dst, src, st, filtername="lanczos3", fw=0.0, fh=0.0, chan_s=0,
+            chan_t=1, flip_s=False, flip_t=False, roi=None, chrange=None,
+            nthreads=0):
+    d, s, t = dst.c(), src.c(), st.c()
+    cb, ce = chrange if chrange else (0, min(dst.nchannels, src.nchannels))
+    err = C.create_string_buffer(512)
+    rc = lib().orc_st_warp(C.byref(d), C.byref(s), C.byref(t), chan_s, chan_t,
+                           int(flip_s), int(flip_t), (filtername or "").encode(),
+                           float(fw), float(fh), _full_roi(dst, roi), cb, ce,
+                           int(nthreads), err, 512)
     if rc:
         raise RuntimeError(err.value.decode())
     return dst

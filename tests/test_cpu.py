@@ -375,3 +375,27 @@ def test_oracle_make_kernel_shapes(oracle):
     assert known and K.sum() == 0 and K[1, 1] == -4
     K, known = oracle.make_kernel("nonesuch", 4, 4)
     assert not known and K.shape == (5, 5) and np.allclose(K, 1 / 25)
+
+
+def test_oracle_st_warp_golden(oracle):
+    """testsuite/oiiotool-xform st_warped.tif: <= 1 LSB on < 2e-4 of the values
+    (the ST field goes through powf, whose last bit is platform dependent)."""
+    import ctypes as C
+    X = np.load(os.path.join(GOLD, "xform_ref.npz"))
+    W = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    d = np.zeros((256, 256, 4), np.float32)
+    oracle.resize(oracle.Img(d), oracle.Img(gf))
+    rs = oracle.quantize(d, np.uint8)
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    u = np.arange(256, dtype=np.float32) / np.float32(255)
+    g = np.array([libm.powf(float(v), 1.2) for v in u], np.float32)
+    st = np.zeros((256, 256, 3), np.float32)
+    st[..., 0] = g[None, :]
+    st[..., 1] = g[:, None]
+    out = np.zeros_like(rs)
+    oracle.st_warp(oracle.Img(out), oracle.Img(rs), oracle.Img(st))
+    dd = np.abs(out.astype(int) - W["st_warped"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 2e-4

@@ -210,3 +210,85 @@ def test_warp_singular_matrix(oiio, oracle):
     M = np.zeros((3, 3), np.float32)
     g, o = warp_both(oiio, oracle, src, (20, 20), np.float32, M, "triangle")
     check(g, o)
+
+
+# ---------------------------------------------------------------- st_warp ----
+def _st_identity_gamma(n=256, gamma=1.2):
+    """--pattern fill:topleft=0,0,0:topright=1,0,0:bottomleft=0,1,0:
+    bottomright=1,1,0 NxN 3 --powc 1.2 (oiiotool-xform/run.py:99-101), with
+    glibc's powf like the reference."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    u = np.arange(n, dtype=np.float32) / np.float32(n - 1)
+    one = np.float32(1)
+    ramp = (one - u) * np.float32(0) + u          # bilerp along one axis
+    g = np.array([libm.powf(float(v), gamma) for v in ramp], np.float32)
+    st = np.zeros((n, n, 3), np.float32)
+    st[..., 0] = g[None, :]
+    st[..., 1] = g[:, None]
+    return st
+
+
+def test_st_warp_golden(oiio, oracle):
+    X = np.load(os.path.join(GOLD, "xform_ref.npz"))
+    W = np.load(os.path.join(GOLD, "warp_ref.npz"))
+    gf = X["grid"].astype(np.float32) * np.float32(1 / 255.0)
+    d = np.zeros((256, 256, 4), np.float32)
+    oracle.resize(oracle.Img(d), oracle.Img(gf))
+    rs = oracle.quantize(d, np.uint8)
+    st = _st_identity_gamma()
+    ref = np.zeros_like(rs)
+    oracle.st_warp(oracle.Img(ref), oracle.Img(rs), oracle.Img(st))
+    dd = np.abs(ref.astype(int) - W["st_warped"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 2e-4           # oracle pinned
+    out = oiio.ImageBufAlgo.st_warp(oiio.ImageBuf(rs), oiio.ImageBuf(st))
+    assert not out.has_error, out.geterror()
+    dd = np.abs(out.pixels.astype(int) - W["st_warped"].astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+    dd = np.abs(out.pixels.astype(int) - ref.astype(int))
+    assert dd.max() <= 1 and (dd != 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("st_type", ["float", "half", "uint16"])
+@pytest.mark.parametrize("filt", ["lanczos3", "triangle", "disk"])
+def test_st_warp_parity(oiio, oracle, st_type, filt):
+    """Random smooth-ish ST field (positions that leave the image included),
+    a source with 3 channels, flips, non-default ST channels, a dst twice the
+    source's size (filter radius scales with 1 / scale)."""
+    src = synth.image(48, 40, 3, np.float32, seed=41)
+    h, w = 80, 96
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    s = (xx / w * 1.2 - 0.1 + 0.03 * np.sin(yy / 7)).astype(np.float32)
+    t = (yy / h * 1.2 - 0.1 + 0.03 * np.cos(xx / 5)).astype(np.float32)
+    if st_type != "float":
+        s, t = np.clip(s, 0, 1), np.clip(t, 0, 1)
+    st32 = np.stack([np.zeros_like(s), t, s], -1)            # chan_s=2, chan_t=1
+    st = (oracle.quantize(st32, np.uint16) if st_type == "uint16"
+          else st32.astype(_np_dtype(st_type)))
+    ref = np.zeros((h, w, 3), np.float32)
+    oracle.st_warp(oracle.Img(ref), oracle.Img(src), oracle.Img(st), filt, chan_s=2,
+                   chan_t=1, flip_t=True)
+    got = np.zeros_like(ref)
+    D = oiio.ImageBuf(got)
+    ok = oiio.ImageBufAlgo.st_warp(D, oiio.ImageBuf(src), oiio.ImageBuf(st),
+                                   filtername=filt, chan_s=2, chan_t=1, flip_t=True)
+    assert ok, D.geterror()
+    check(got, ref)
+
+
+def test_st_warp_errors(oiio):
+    IBA = oiio.ImageBufAlgo
+    src = oiio.ImageBuf(np.zeros((8, 8, 3), np.float32))
+    st = oiio.ImageBuf(np.zeros((8, 8, 2), np.float32))
+    assert IBA.st_warp(src, st, chan_t=2).geterror() == \
+        "ImageBufAlgo::st_warp : Out-of-range T channel index: 2"
+    assert IBA.st_warp(src, oiio.ImageBuf()).geterror() == \
+        "ImageBufAlgo::st_warp : Uninitialized ST buffer"
+    assert IBA.st_warp(src, st, filtername="nope").geterror() == \
+        'Filter "nope" not recognized'
+    far = oiio.ImageBuf(np.zeros((8, 8, 2), np.float32))
+    far.spec().x = 100
+    assert IBA.st_warp(src, far).geterror() == \
+        "ImageBufAlgo::st_warp : Output ROI does not intersect ST buffer."

@@ -3,6 +3,7 @@
 chain (BASELINE config 4) and the other BASELINE configs' kernels.
 usage: bench_extra.py mip [size] [filter] [hicomp]
        bench_extra.py warp         rotate / resize:from-to / fit exact, 4K RGBA f32 and u8
+       bench_extra.py conv         convolve / unsharp_mask / MIP chain with --sharpen
        bench_extra.py range        rangecompress / rangeexpand / highlightcomp resize, 8K RGBA f32"""
 import json
 import os
@@ -105,6 +106,40 @@ def warp_ops():
                           "ms": ms, "out_Mpix_s": w * h / 4 / ms / 1e3}))
 
 
+def conv_ops():
+    """convolve / unsharp_mask, 8K RGBA f32 device resident.  Algorithmic
+    bytes: convolve = src + dst; unsharp = src + dst (the blur image is a
+    device temporary: + one write and one read of it in this version)."""
+    import torch
+    import openimageio_b200 as oiio
+    IBA = oiio.ImageBufAlgo
+    w, h = 7680, 4320
+    g = torch.Generator(device="cuda").manual_seed(4)
+    src = torch.rand((h, w, 4), dtype=torch.float32, device="cuda", generator=g)
+    dst = torch.empty_like(src)
+    S, D = oiio.ImageBuf(src), oiio.ImageBuf(dst)
+    nbytes = 2 * src.numel() * 4
+    for name, kw in (("gaussian", 3), ("gaussian", 5), ("bspline", 15)):
+        K = IBA.make_kernel(name, kw, kw)
+        ms = _time(lambda: IBA.convolve(D, S, K))
+        print(json.dumps({"workload": "convolve %s %dx%d 8K RGBA f32" % (name, kw, kw),
+                          "ms": ms, "algorithmic_GBs": nbytes / ms / 1e6,
+                          "GFMA_s": w * h * 4 * kw * kw / ms / 1e6}))
+    for width in (3.0, 7.0):
+        ms = _time(lambda: IBA.unsharp_mask(D, S, width=width, contrast=0.6))
+        print(json.dumps({"workload": "unsharp_mask gaussian width %g 8K RGBA f32" % width,
+                          "ms": ms, "algorithmic_GBs": nbytes / ms / 1e6}))
+    lvl0 = torch.rand((8192, 8192, 4), dtype=torch.float32, device="cuda", generator=g)
+    for sh in (0.0, 0.6):
+        best = None
+        for _ in range(3):
+            chain = oiio.MipChain(oiio.ImageBuf(lvl0), "lanczos3", sharpen=sh)
+            best = chain.kernel_ms if best is None else min(best, chain.kernel_ms)
+            del chain
+        print(json.dumps({"workload": "mip 8192^2 RGBA f32 lanczos3 sharpen=%g" % sh,
+                          "ms": best}))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "mip":
         mip(int(sys.argv[2]) if len(sys.argv) > 2 else 16384,
@@ -114,3 +149,5 @@ if __name__ == "__main__":
         range_ops()
     elif sys.argv[1] == "warp":
         warp_ops()
+    elif sys.argv[1] == "conv":
+        conv_ops()
