@@ -296,6 +296,23 @@ B2R_API int b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src,
                              const b2r_options* opt, b2r_report* report,
                              char* err, size_t errlen);
 
+/* ---- fixNonFinite / check_nan ---------------------------------------------
+ * Replaces ImageBufAlgo::fixNonFinite (imagebufalgo_pixelmath.cpp:1424-1610)
+ * as maketx uses it (--fixnan, maketexture.cpp:1666-1686) and maketx's
+ * check_nan_block (--checknan, :340-360, 1690-1705 = mode 0's count).
+ * mode: ImageBufAlgo::NonFiniteFixMode -- 0 NONE (count only), 1 BLACK,
+ * 2 BOX3 (average of the finite values in the 3x3 neighbourhood), 100 ERROR
+ * (count; fails with "Nonfinite pixel values found" if any).  dst gets a copy
+ * of src (dst may be src); float and half images are repaired, the other
+ * types are only copied.  *pixels_fixed = pixels that held a NaN/Inf.
+ * BOX3 reads the neighbourhood from the UNREPAIRED source, so the result does
+ * not depend on a scan order; it equals the reference wherever two non-finite
+ * values are not neighbours (the reference repairs in place per thread band). */
+B2R_API int b2r_fix_nonfinite(const b2r_image* dst, const b2r_image* src,
+                              int mode, int* pixels_fixed, const b2r_roi* roi,
+                              const b2r_options* opt, b2r_report* report,
+                              char* err, size_t errlen);
+
 /* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
  * The reference parallelises resize by full-width row bands
  * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The

@@ -189,6 +189,10 @@ def lib():
                                    C.c_char_p, C.c_float, C.c_float, C.c_float,
                                    C.POINTER(_Roi), C.POINTER(_Options),
                                    C.POINTER(Report), C.c_char_p, C.c_size_t]
+    L.b2r_fix_nonfinite.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(_Roi),
+                                    C.POINTER(_Options), C.POINTER(Report),
+                                    C.c_char_p, C.c_size_t]
     L.b2r_mipchain_nlevels.argtypes = [C.c_void_p]
     L.b2r_mipchain_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
@@ -879,6 +883,51 @@ class _IBA:
             return False
         return True
 
+    # ---- fixNonFinite -----------------------------------------------------
+    last_pixels_fixed = 0
+
+    def fixNonFinite(self, *args, mode=None, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::fixNonFinite(dst, src, mode=NONFINITE_BOX3, roi,
+        nthreads) (imagebufalgo_pixelmath.cpp:1562-1625).  The number of
+        repaired pixels (the C++ `pixelsFixed` out-parameter) is left in
+        `ImageBufAlgo.last_pixels_fixed`."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        rest = [a for a in args if not isinstance(a, ImageBuf)]
+        if mode is None:
+            mode = rest[0] if rest else NONFINITE_BOX3
+        if len(bufs) == 2:
+            return self._fixnf(bufs[0], bufs[1], mode, roi, device)
+        result = ImageBuf()
+        ok = self._fixnf(result, bufs[0], mode, roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("fixNonFinite error")
+        return result
+
+    def _fixnf(self, dst, src, mode, roi, device):
+        if mode not in (NONFINITE_NONE, NONFINITE_BLACK, NONFINITE_BOX3,
+                        NONFINITE_ERROR):
+            dst.errorfmt("fixNonFinite: unknown repair mode")
+            return False
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        roi.chend = min(roi.chend, dst.nchannels, src.nchannels)
+        d, s = dst._c(), src._c()
+        r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                 roi.chend)
+        o = _options(device, PATH_AUTO,
+                     _current_stream(dst) or _current_stream(src))
+        err = C.create_string_buffer(512)
+        n = C.c_int(0)
+        rc = lib().b2r_fix_nonfinite(C.byref(d), C.byref(s), int(mode),
+                                     C.byref(n), C.byref(r), C.byref(o), None,
+                                     err, 512)
+        self.last_pixels_fixed = n.value
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
     # ---- warp / rotate ----------------------------------------------------
     def warp(self, *args, filtername="", filterwidth=0.0, recompute_roi=False,
              wrap="default", edgeclamp=False, filterptr=None, roi=None,
@@ -1079,6 +1128,11 @@ class _IBA:
 
 
 ImageBufAlgo = _IBA()
+
+# ImageBufAlgo::NonFiniteFixMode (imagebufalgo.h)
+NONFINITE_NONE, NONFINITE_BLACK, NONFINITE_BOX3, NONFINITE_ERROR = 0, 1, 2, 100
+# ImageBufAlgo::MakeTextureMode (imagebufalgo.h)
+MakeTxTexture, MakeTxShadow, MakeTxEnvLatl = 0, 1, 2
 
 # ImageBuf::WrapMode (src/include/OpenImageIO/imagebuf.h)
 WRAP_MODES = {"default": 0, "black": 1, "clamp": 2, "periodic": 3, "mirror": 4}
@@ -1307,3 +1361,166 @@ class MipChain:
         if rc:
             raise B2RError(err.value.decode())
         return out
+
+
+# --------------------------------------------------------------------------
+# make_texture: the pixel pipeline of make_texture_impl + write_mipmap
+# (src/libOpenImageIO/maketexture.cpp:1396-2040, 811-987) for plain textures,
+# without the file: every stage that touches pixels runs on the device and the
+# finished levels are handed back instead of being written.
+class Texture:
+    """What make_texture computed: `levels[0]` is the top level (after
+    --fixnan / --resize), `levels[1:]` the MIP chain; `format` the pixel type
+    the reference would write them as."""
+
+    def __init__(self):
+        self.levels = []
+        self.format = "float"
+        self.pixels_fixed = 0
+        self.error = ""
+
+    @property
+    def ok(self):
+        return not self.error
+
+
+def _ceil2(x):
+    p = 1
+    while p < x:
+        p <<= 1
+    return p
+
+
+def make_texture(mode, src, config=None, device=0):
+    """ImageBufAlgo::make_texture(mode, input, outputfilename, configspec) for
+    mode MakeTxTexture, returning a `Texture` instead of writing a file.
+    config: dict of the maketx attributes that select pixel work --
+    "maketx:filtername" ("box"; "post-" / "unsharp-<f>" prefixes as in
+    maketexture.cpp:759-768), "maketx:highlightcomp", "maketx:sharpen",
+    "maketx:fixnan" ("none" | "black" | "box3"), "maketx:checknan",
+    "maketx:resize" (round up to a power of two), "maketx:nomipmap",
+    "maketx:allow_pixel_shift", "format" (output type: levels written as half
+    are clamped to +-HALF_MAX, :709-714, 943-945)."""
+    cfg = dict(config or {})
+    T = Texture()
+    IBA = ImageBufAlgo
+    if mode != MakeTxTexture:
+        T.error = "make_texture: only MakeTxTexture is on the B200 resampling path"
+        return T
+    if src is None or not src.initialized:
+        T.error = "make_texture: uninitialized input image"
+        return T
+    sspec = src.spec_
+    # --fixnan / --checknan (:1666-1705)
+    fixnan = cfg.get("maketx:fixnan", "") or "none"
+    if fixnan not in ("none", "black", "box3"):
+        T.error = 'Unknown fixnan mode "%s"' % fixnan
+        return T
+    isfp = sspec.basetype in (HALF, FLOAT)
+    if fixnan != "none" and isfp:
+        fixed = IBA.fixNonFinite(src, {"black": NONFINITE_BLACK,
+                                       "box3": NONFINITE_BOX3}[fixnan],
+                                 device=device)
+        if fixed.has_error:
+            T.error = "Error fixing nans/infs."
+            return T
+        T.pixels_fixed = IBA.last_pixels_fixed
+        src = fixed
+    if cfg.get("maketx:checknan") and isfp:
+        probe = ImageBuf()
+        IBA.fixNonFinite(probe, src, NONFINITE_NONE, device=device)
+        if IBA.last_pixels_fixed:
+            T.error = "maketx ERROR: Nan/Inf at %d pixels" % IBA.last_pixels_fixed
+            return T
+    filtername = cfg.get("maketx:filtername", "box") or "box"
+    # top level: resize to a power of two and/or convert to float (:1791-1877)
+    dw, dh = sspec.width, sspec.height
+    if cfg.get("maketx:resize"):
+        dw, dh = _ceil2(dw), _ceil2(dh)
+    do_resize = (dw, dh) != (sspec.width, sspec.height)
+    allow_shift = bool(cfg.get("maketx:allow_pixel_shift"))
+    dev = src.pixels.device if src.on_device else None
+    top_spec = sspec.copy()
+    top_spec.width = top_spec.full_width = dw
+    top_spec.height = top_spec.full_height = dh
+    top_spec.x = top_spec.y = top_spec.full_x = top_spec.full_y = 0
+    top_spec.set_format("float")          # maketx:forcefloat (default 1)
+    s0 = src.spec_.copy()
+    s0.x = s0.y = s0.full_x = s0.full_y = 0
+    s0.full_width, s0.full_height = s0.width, s0.height
+    src0 = ImageBuf(src.pixels, s0)
+    # float copy of the source (maketx:forcefloat; resize_block needs float):
+    # copy_pixels == a nearest resample at 1:1
+    if s0.basetype != FLOAT:
+        fspec = s0.copy()
+        fspec.set_format("float")
+        srcf = ImageBuf()
+        srcf.reset(fspec, device=dev)
+        if not IBA.resample(srcf, src0, interpolate=False, device=device):
+            T.error = srcf.geterror()
+            return T
+    else:
+        srcf = src0
+    if not do_resize:
+        top = srcf
+    else:
+        top = ImageBuf()
+        rf = "lanczos3" if filtername.lower().startswith("unsharp-") else filtername
+        if rf in ("box", "triangle"):
+            # resize_block (:141-334) works on device-resident float levels
+            import torch
+            if srcf.on_device:
+                sdev = srcf
+            else:
+                sdev = ImageBuf(torch.from_numpy(srcf.pixels).to("cuda:%d" % device),
+                                srcf.spec_.copy())
+            top.reset(top_spec, device=sdev.pixels.device)
+            if not _mip_level(top, sdev, "box", device):
+                T.error = top.geterror()
+                return T
+            if not srcf.on_device:
+                top = ImageBuf(top.pixels.cpu().numpy(), top_spec)
+        else:
+            top.reset(top_spec, device=dev)
+            if not IBA.resize(top, srcf, filtername=rf, device=device):
+                T.error = top.geterror()
+                return T
+    out_format = cfg.get("format", None) or {UINT8: "uint8", UINT16: "uint16",
+                                             HALF: "half", FLOAT: "float"}[sspec.basetype]
+    T.format = out_format
+    clamp_half = out_format == "half"
+    T.levels = [top]
+    if cfg.get("maketx:nomipmap"):
+        return T
+    sharpen = float(cfg.get("maketx:sharpen", 0.0) or 0.0)
+    sharpen_first, sharpenfilt = True, "gaussian"
+    fn = filtername
+    if fn.lower().startswith("post-"):
+        sharpen_first, fn = False, fn[5:]
+    if fn.lower().startswith("unsharp-"):
+        sharpenfilt, fn = fn[8:], "lanczos3"
+    try:
+        chain = MipChain(top, fn, clamp_half=clamp_half, device=device,
+                         highlightcomp=bool(cfg.get("maketx:highlightcomp")),
+                         sharpen=sharpen, sharpen_first=sharpen_first,
+                         sharpenfilt=sharpenfilt)
+    except B2RError as e:
+        T.error = str(e)
+        return T
+    for lvl in range(1, chain.nlevels):
+        T.levels.append(ImageBuf(chain.download(lvl)))
+    T.chain = chain
+    return T
+
+
+def _mip_level(dst, src, filtername, device):
+    """One write_mipmap level step on whole images (b2r_mip_level)."""
+    d, s = dst._c(), src._c()
+    o = _options(device, PATH_AUTO, _current_stream(dst) or _current_stream(src))
+    err = C.create_string_buffer(512)
+    rc = lib().b2r_mip_level(C.byref(d), C.byref(s), filtername.encode(), None,
+                             C.byref(o), err, 512)
+    if rc:
+        dst.errorfmt(err.value.decode())
+        return False
+    return True

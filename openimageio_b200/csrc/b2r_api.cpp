@@ -3147,3 +3147,127 @@ b2r_st_warp(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
     return st_warp_impl(dst, src, st, *filter, chan_s, chan_t, flip_s, flip_t, roi, opt,
                         report, err, errlen);
 }
+
+
+// =========================================================================
+// fixNonFinite / check_nan  (imagebufalgo_pixelmath.cpp:1424-1610,
+// maketexture.cpp:340-360, 1666-1705)
+// =========================================================================
+extern "C" int
+b2r_fix_nonfinite(const b2r_image* dst, const b2r_image* src, int mode, int* pixels_fixed,
+                  const b2r_roi* roi, const b2r_options* opt, b2r_report* report, char* err,
+                  size_t errlen)
+{
+    if (pixels_fixed)
+        *pixels_fixed = 0;
+    if (mode != 0 && mode != 1 && mode != 2 && mode != 100) {
+        set_err(err, errlen, "fixNonFinite: unknown repair mode");
+        return B2R_ERR_INVALID;
+    }
+    StencilIO io;
+    int rc = io.begin(dst, src, roi, opt, report, "fixNonFinite", err, errlen);
+    if (rc || io.empty) {
+        io.release();
+        return rc;
+    }
+    if (dst->basetype != src->basetype) {
+        io.release();
+        set_err(err, errlen, "fixNonFinite: dst and src must have the same pixel type");
+        return B2R_ERR_TYPES;
+    }
+    const bool fp    = src->basetype == B2R_FLOAT || src->basetype == B2R_HALF;
+    const int es     = basetype_size(src->basetype);
+    const bool count_only = (mode == 0 || mode == 100);
+    int launched     = 0;
+    int* counter     = nullptr;
+    void* inplace_tmp = nullptr;
+    b2r_image S      = io.srcd;
+    void* spix       = io.dsrc;
+    // Integer types cannot hold NaN/Inf: fixNonFinite is just the copy
+    // (:1586-1587); the counting modes copy too.  (The repair kernel writes
+    // every channel of every ROI pixel itself.)
+    if ((!fp || count_only) && (io.dst_alloc || !io.same_pixels)) {
+        if (S.xstride != (int64_t)S.nchannels * es
+            || io.dstd.xstride != (int64_t)S.nchannels * es) {
+            io.release();
+            set_err(err, errlen, "fixNonFinite: pixels must be contiguous in x");
+            return B2R_ERR_UNSUPPORTED;
+        }
+        if (io.dst_alloc)
+            cudaMemset2DAsync(io.dst_alloc, io.dpitch, 0, io.drowbytes, io.roi_h, io.stream);
+        const int x0 = std::max(io.roi.xbegin, S.x), x1 = std::min(io.roi.xend, S.x + S.width);
+        const int y0 = std::max(io.roi.ybegin, S.y), y1 = std::min(io.roi.yend, S.y + S.height);
+        if (x1 > x0 && y1 > y0) {
+            unsigned char* dp = (unsigned char*)io.ddst
+                                + (long long)(y0 - io.dstd.y) * io.dstd.ystride
+                                + (long long)(x0 - io.dstd.x) * io.dstd.xstride;
+            const unsigned char* sp = (const unsigned char*)spix
+                                      + (long long)(y0 - S.y) * S.ystride
+                                      + (long long)(x0 - S.x) * S.xstride;
+            cudaMemcpy2DAsync(dp, io.dstd.ystride, sp, S.ystride, size_t(x1 - x0) * S.xstride,
+                              y1 - y0, cudaMemcpyDeviceToDevice, io.stream);
+        }
+    }
+    if (fp) {
+        if (cudaMallocAsync((void**)&counter, sizeof(int), io.stream) != cudaSuccess
+            || cudaMemsetAsync(counter, 0, sizeof(int), io.stream) != cudaSuccess) {
+            io.release();
+            set_err(err, errlen, "CUDA error allocating the counter");
+            return B2R_ERR_CUDA;
+        }
+        if (io.same_pixels && mode == 2 && !io.src_alloc) {
+            // box3 in place on the device: neighbours must be read unrepaired
+            const size_t rowb = size_t(S.width) * S.nchannels * es;
+            if (cudaMallocAsync(&inplace_tmp, rowb * S.height, io.stream) != cudaSuccess) {
+                cudaFreeAsync(counter, io.stream);
+                io.release();
+                set_err(err, errlen, "CUDA error allocating the in-place copy");
+                return B2R_ERR_CUDA;
+            }
+            cudaMemcpy2DAsync(inplace_tmp, rowb, spix, S.ystride, rowb, S.height,
+                              cudaMemcpyDeviceToDevice, io.stream);
+            S.ystride = (int64_t)rowb;
+            S.xstride = (int64_t)S.nchannels * es;
+            spix      = inplace_tmp;
+        }
+        NonFiniteParams np;
+        memset(&np, 0, sizeof(np));
+        np.dst     = to_dev(io.dstd, io.ddst);
+        np.src     = to_dev(S, spix);
+        np.roi_x0  = io.roi.xbegin;
+        np.roi_x1  = io.roi.xend;
+        np.roi_y0  = io.roi.ybegin;
+        np.roi_y1  = io.roi.yend;
+        np.chbegin = io.roi.chbegin;
+        np.chend   = io.roi.chend;
+        np.mode    = mode;
+        np.write   = count_only ? 0 : 1;
+        np.counter = counter;
+        launch_fix_nonfinite(np, io.stream);
+        launched = 1;
+    }
+    int host_count = 0;
+    if (counter) {
+        cudaMemcpyAsync(&host_count, counter, sizeof(int), cudaMemcpyDeviceToHost, io.stream);
+        cudaFreeAsync(counter, io.stream);
+    }
+    if (inplace_tmp)
+        cudaFreeAsync(inplace_tmp, io.stream);
+    rc = io.end(*dst, report, launched, err, errlen);
+    if (rc)
+        return rc;
+    if (counter) {
+        cudaError_t e = cudaStreamSynchronize(io.stream);  // the count is a return value
+        if (e != cudaSuccess) {
+            set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+            return B2R_ERR_CUDA;
+        }
+    }
+    if (pixels_fixed)
+        *pixels_fixed = host_count;
+    if (mode == 100 && host_count) {
+        set_err(err, errlen, "Nonfinite pixel values found");
+        return B2R_ERR_INVALID;
+    }
+    return B2R_OK;
+}

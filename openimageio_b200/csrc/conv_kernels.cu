@@ -200,3 +200,112 @@ launch_unsharp_combine(const UnsharpParams& p, void* stream)
 }
 
 }  // namespace b2r
+
+// ===========================================================================
+// fixNonFinite (imagebufalgo_pixelmath.cpp:1424-1500) and maketx's
+// check_nan_block (maketexture.cpp:340-360): count the pixels that hold a
+// NaN/Inf and, per mode, overwrite those values with 0 or with the average of
+// the finite values in the 3x3 neighbourhood (clipped to the image).  The
+// neighbourhood is read from the SOURCE image, so the result does not depend
+// on any scan order (the reference repairs in place, band by band; the two
+// agree wherever non-finite values are not adjacent).  Half images sum in
+// half precision like the reference's `T sum`.
+// ===========================================================================
+namespace b2r {
+namespace {
+
+template<bool HALF>
+__device__ __forceinline__ float
+nf_load(const unsigned char* p)
+{
+    return HALF ? __half2float(*(const __half*)p) : *(const float*)p;
+}
+
+template<bool HALF>
+__global__ void __launch_bounds__(256)
+fix_nonfinite_kernel(const NonFiniteParams p)
+{
+    pdl_prologue();
+    const int x = p.roi_x0 + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = x < p.roi_x1;
+    const int es    = HALF ? 2 : 4;
+    const DevImage& S = p.src;
+    int fixed_here    = 0;
+    for (int y = p.roi_y0 + blockIdx.y; y < p.roi_y1; y += gridDim.y) {
+        bool fixed = false;
+        if (live) {
+            const bool in = x >= S.x && x < S.x + S.width && y >= S.y && y < S.y + S.height;
+            const unsigned char* sp = (const unsigned char*)S.pixels
+                                      + (long long)(y - S.y) * S.ystride
+                                      + (long long)(x - S.x) * S.xstride;
+            unsigned char* dp = (unsigned char*)p.dst.pixels
+                                + (long long)(y - p.dst.y) * p.dst.ystride
+                                + (long long)(x - p.dst.x) * p.dst.xstride;
+            for (int c = 0; c < p.dst.nchannels; ++c) {
+                float v = in ? nf_load<HALF>(sp + c * es) : 0.0f;
+                if (c >= p.chbegin && c < p.chend && nonfinite(v)) {
+                    fixed = true;
+                    if (p.mode == 1) {
+                        v = 0.0f;
+                    } else if (p.mode == 2) {
+                        int numvals = 0;
+                        float sum   = 0.0f;
+                        // roi2 = 3x3 around the pixel, clipped to dst's window
+                        const int j0 = max(y - 1, p.dst.y), j1 = min(y + 2, p.dst.y + p.dst.height);
+                        const int i0 = max(x - 1, p.dst.x), i1 = min(x + 2, p.dst.x + p.dst.width);
+                        for (int j = j0; j < j1; ++j)
+                            for (int i = i0; i < i1; ++i) {
+                                const bool nin = i >= S.x && i < S.x + S.width && j >= S.y
+                                                 && j < S.y + S.height;
+                                const float nv
+                                    = nin ? nf_load<HALF>((const unsigned char*)S.pixels
+                                                          + (long long)(j - S.y) * S.ystride
+                                                          + (long long)(i - S.x) * S.xstride
+                                                          + c * es)
+                                          : 0.0f;
+                                if (!nonfinite(nv)) {
+                                    sum = __fadd_rn(sum, nv);
+                                    if (HALF)
+                                        sum = __half2float(__float2half_rn(sum));
+                                    ++numvals;
+                                }
+                            }
+                        v = numvals ? __fdiv_rn(sum, float(numvals)) : 0.0f;
+                    }
+                }
+                if (p.write) {
+                    if (HALF)
+                        *(__half*)(dp + c * es) = __float2half_rn(v);
+                    else
+                        *(float*)(dp + c * es) = v;
+                }
+            }
+        }
+        fixed_here += fixed ? 1 : 0;
+    }
+    // one atomic per warp
+    const unsigned m = __ballot_sync(0xffffffffu, fixed_here != 0);
+    int total = fixed_here;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (m && (threadIdx.x & 31) == 0)
+        atomicAdd(p.counter, total);
+}
+
+}  // namespace
+
+void
+launch_fix_nonfinite(const NonFiniteParams& p, void* stream)
+{
+    const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
+    if (w <= 0 || h <= 0)
+        return;
+    dim3 grid((w + 255) / 256, std::min(h, 4096), 1);
+    if (p.src.basetype == BT_HALF)
+        launch_pdl(fix_nonfinite_kernel<true>, grid, dim3(256), 0, (cudaStream_t)stream, p);
+    else
+        launch_pdl(fix_nonfinite_kernel<false>, grid, dim3(256), 0, (cudaStream_t)stream, p);
+}
+
+}  // namespace b2r

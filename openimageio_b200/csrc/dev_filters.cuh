@@ -138,18 +138,49 @@ struct DevFilter {
     float param, w, h;
 };
 
+// One axis of a separable filter with everything that does not depend on the
+// argument computed once (the argument scale is an IEEE division).
+struct DevAxis {
+    int profile, mode;  // mode 0: box edge, 1: scaled argument, 2: sinc (param = radius)
+    float k, param;
+};
+
+__device__ __forceinline__ DevAxis
+dev_make_axis(const DevFilter& f, float ext)
+{
+    DevAxis a;
+    a.profile = f.profile;
+    a.param   = f.param;
+    a.mode    = 1;
+    a.k       = 0.0f;
+    switch (f.scale) {
+    case 0: a.mode = 0, a.k = B2R_MUL(ext, 0.5f); break;
+    case 1: a.k = __fdiv_rn(2.0f, ext); break;
+    case 2: a.k = __fdiv_rn(4.0f, ext); break;
+    case 3:
+    case 6: a.k = __fdiv_rn(6.0f, ext); break;
+    case 4: a.mode = 2, a.param = __fdiv_rn(ext, 2.0f); break;
+    default: a.mode = 3; break;
+    }
+    return a;
+}
+
+__device__ __forceinline__ float
+dev_axis_eval(const DevAxis& a, float x)
+{
+    if (a.mode == 1)
+        return dev_profile(a.profile, B2R_MUL(x, a.k), a.param);
+    if (a.mode == 0)
+        return fabsf(x) <= a.k ? 1.0f : 0.0f;
+    if (a.mode == 2)
+        return dev_profile(a.profile, x, a.param);
+    return 0.0f;
+}
+
 __device__ __forceinline__ float
 dev_axis_value(const DevFilter& f, float ext, float x)
 {
-    switch (f.scale) {
-    case 0: return fabsf(x) <= B2R_MUL(ext, 0.5f) ? 1.0f : 0.0f;
-    case 1: return dev_profile(f.profile, B2R_MUL(x, __fdiv_rn(2.0f, ext)), f.param);
-    case 2: return dev_profile(f.profile, B2R_MUL(x, __fdiv_rn(4.0f, ext)), f.param);
-    case 3:
-    case 6: return dev_profile(f.profile, B2R_MUL(x, __fdiv_rn(6.0f, ext)), f.param);
-    case 4: return dev_profile(f.profile, x, __fdiv_rn(ext, 2.0f));
-    }
-    return 0.0f;
+    return dev_axis_eval(dev_make_axis(f, ext), x);
 }
 
 // Filter2D::operator()(x, y)

@@ -272,6 +272,19 @@ struct UnsharpParams {
 void
 launch_unsharp_combine(const UnsharpParams& p, void* stream);
 
+// fixNonFinite_ (imagebufalgo_pixelmath.cpp:1424-1500), float / half images of
+// one type.  mode 0 / 100: count only, 1: black, 2: 3x3 average of the finite
+// neighbours.  write == 0: nothing is stored (pure count).
+struct NonFiniteParams {
+    DevImage dst, src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend;
+    int mode, write;
+    int* counter;  // device; += pixels that held a non-finite value
+};
+void
+launch_fix_nonfinite(const NonFiniteParams& p, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

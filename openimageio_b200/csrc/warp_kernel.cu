@@ -159,6 +159,7 @@ warp_kernel(const WarpParams p)
     filt.profile = p.filt_profile, filt.scale = p.filt_scale;
     filt.param = p.filt_param, filt.w = p.filt_w, filt.h = p.filt_h;
     const bool separable = p.filt_scale < 5;
+    const DevAxis ax = dev_make_axis(filt, filt.w), ay = dev_make_axis(filt, filt.h);
     const int sxb = S.x, sxe = S.x + S.width, syb = S.y, sye = S.y + S.height;
 
     for (int y = p.roi_y0 + blockIdx.y * WARP_BY + threadIdx.y; y < p.roi_y1;
@@ -209,8 +210,8 @@ warp_kernel(const WarpParams p)
         if (cache && !black) {
 #pragma unroll 1
             for (int i = 0; i < ntx; ++i)
-                wxc[i] = dev_axis_value(
-                    filt, filt.w,
+                wxc[i] = dev_axis_eval(
+                    ax,
                     __fmul_rn(ds_inv, __fsub_rn(__fadd_rn(float(smin + i), 0.5f), s)));
         }
         // channels in passes of four (one pass for everything up to RGBA)
@@ -231,7 +232,7 @@ warp_kernel(const WarpParams p)
                 for (int ty = tmin; ty < tmax; ++ty, rowp += S.ystride) {
                     const float yarg
                         = __fmul_rn(dt_inv, __fsub_rn(__fadd_rn(float(ty), 0.5f), t));
-                    const float wy          = dev_axis_value(filt, filt.h, yarg);
+                    const float wy          = dev_axis_eval(ay, yarg);
                     const unsigned char* sp = rowp;
 #pragma unroll 1
                     for (int i = 0; i < ntx; ++i, sp += S.xstride) {
@@ -249,7 +250,7 @@ warp_kernel(const WarpParams p)
                 for (int ty = tmin; ty < tmax; ++ty) {
                     const float yarg
                         = __fmul_rn(dt_inv, __fsub_rn(__fadd_rn(float(ty), 0.5f), t));
-                    const float wy = separable ? dev_axis_value(filt, filt.h, yarg) : 0.0f;
+                    const float wy = separable ? dev_axis_eval(ay, yarg) : 0.0f;
                     // do_wrap: a pixel inside the data window is itself; one
                     // outside is wrapped in BOTH axes against the full window
                     // and is black if it still misses the data window
@@ -270,7 +271,7 @@ warp_kernel(const WarpParams p)
                             const float xarg = __fmul_rn(
                                 ds_inv, __fsub_rn(__fadd_rn(float(tx), 0.5f), s));
                             w = separable
-                                    ? __fmul_rn(dev_axis_value(filt, filt.w, xarg), wy)
+                                    ? __fmul_rn(dev_axis_eval(ax, xarg), wy)
                                     : dev_filter2d(filt, xarg, yarg);
                         }
                         int px = tx, py = ty;
@@ -335,6 +336,7 @@ st_warp_kernel(const StWarpParams p)
     filt.profile = p.filt_profile, filt.scale = p.filt_scale;
     filt.param = p.filt_param, filt.w = p.filt_w, filt.h = p.filt_h;
     const bool separable = p.filt_scale < 5;
+    const DevAxis ax = dev_make_axis(filt, filt.w), ay = dev_make_axis(filt, filt.h);
     const int sxb = S.x, sxe = S.x + S.width, syb = S.y, sye = S.y + S.height;
     const float fsw = float(S.full_width), fsh = float(S.full_height);
     const float radx = float(p.filterrad_x), rady = float(p.filterrad_y);
@@ -364,7 +366,7 @@ st_warp_kernel(const StWarpParams p)
         if (cache) {
 #pragma unroll 1
             for (int i = 0; i < ntx; ++i)
-                wxc[i] = dev_axis_value(filt, filt.w,
+                wxc[i] = dev_axis_eval(ax,
                                         __fadd_rn(__fsub_rn(float(x_min + i), src_x), 0.5f));
         }
         for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
@@ -374,7 +376,7 @@ st_warp_kernel(const StWarpParams p)
 #pragma unroll 1
             for (int ty = y_min; ty <= y_max; ++ty) {
                 const float yarg = __fadd_rn(__fsub_rn(float(ty), src_y), 0.5f);
-                const float wy   = separable ? dev_axis_value(filt, filt.h, yarg) : 0.0f;
+                const float wy   = separable ? dev_axis_eval(ay, yarg) : 0.0f;
                 const bool row_in = ty < sye;  // ty >= syb by construction
                 const unsigned char* sp = (const unsigned char*)S.pixels
                                           + (long long)(ty - syb) * S.ystride
@@ -386,7 +388,7 @@ st_warp_kernel(const StWarpParams p)
                         w = __fmul_rn(wxc[tx - x_min], wy);
                     else {
                         const float xarg = __fadd_rn(__fsub_rn(float(tx), src_x), 0.5f);
-                        w = separable ? __fmul_rn(dev_axis_value(filt, filt.w, xarg), wy)
+                        w = separable ? __fmul_rn(dev_axis_eval(ax, xarg), wy)
                                       : dev_filter2d(filt, xarg, yarg);
                     }
                     total_w = __fadd_rn(total_w, w);

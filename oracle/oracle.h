@@ -84,6 +84,12 @@ int orc_rangeexpand(const orc_image* dst, const orc_image* src, int useluma,
                     int alpha_channel, int z_channel, orc_roi roi, int chbegin,
                     int chend);
 
+/* ImageBufAlgo::fixNonFinite (imagebufalgo_pixelmath.cpp:1424-1610) and
+ * maketx's check_nan_block (maketexture.cpp:340-360).  mode: 0 none (count),
+ * 1 black, 2 box3, 100 error (count).  Raster order, single band. */
+int orc_fix_nonfinite(const orc_image* dst, const orc_image* src, int mode,
+                      orc_roi roi, int chbegin, int chend, int* pixels_fixed);
+
 /* ImageBufAlgo::warp / rotate and fit(exact=1) restated
  * (imagebufalgo_xform.cpp:263-418, 1012-1027, 1727-1760) with Imath's
  * Matrix33<float> algebra.  M: row-major x[i][j] as Imath stores it.

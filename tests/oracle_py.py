@@ -102,6 +102,9 @@ def lib():
         L.orc_unsharp_mask.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
                                        C.c_char_p, C.c_float, C.c_float, C.c_float,
                                        OrcRoi, C.c_int, C.c_char_p, C.c_int]
+        L.orc_fix_nonfinite.argtypes = [C.POINTER(OrcImage), C.POINTER(OrcImage),
+                                        C.c_int, OrcRoi, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int)]
         L.orc_load_as_float.argtypes = [C.c_void_p, C.c_int]
         L.orc_store_from_float.argtypes = [C.c_void_p, C.c_int, C.c_float]
         _lib = L
@@ -328,6 +331,21 @@ def unsharp_mask(dst, src, kernel="gaussian", width=3.0, contrast=1.0,
     if rc:
         raise RuntimeError(err.value.decode())
     return dst
+
+
+NONFINITE = {"none": 0, "black": 1, "box3": 2, "error": 100}
+
+
+def fix_nonfinite(dst, src, mode="box3", roi=None, chrange=None):
+    """Returns the number of pixels with a non-finite value (= repaired)."""
+    d, s = dst.c(), src.c()
+    cb, ce = chrange if chrange else (0, dst.nchannels)
+    n = C.c_int(0)
+    rc = lib().orc_fix_nonfinite(C.byref(d), C.byref(s), NONFINITE[mode],
+                                 _full_roi(dst, roi), cb, ce, C.byref(n))
+    if rc:
+        raise RuntimeError("orc_fix_nonfinite: bad arguments")
+    return n.value
 
 
 def resize_block(dst, src, allow_shift=False):

@@ -399,3 +399,32 @@ def test_oracle_st_warp_golden(oracle):
     oracle.st_warp(oracle.Img(out), oracle.Img(rs), oracle.Img(st))
     dd = np.abs(out.astype(int) - W["st_warped"].astype(int))
     assert dd.max() <= 1 and (dd != 0).mean() < 2e-4
+
+
+def test_oracle_fix_nonfinite(oracle):
+    """fixNonFinite_ (imagebufalgo_pixelmath.cpp:1424-1500): counts, black,
+    box3 with clipped neighbourhoods, half sums in half precision."""
+    a = np.arange(5 * 6 * 2, dtype=np.float32).reshape(5, 6, 2)
+    a[2, 3, 0] = np.nan
+    a[0, 0, 1] = np.inf
+    a[4, 5, :] = -np.inf
+    d = np.zeros_like(a)
+    assert oracle.fix_nonfinite(oracle.Img(d), oracle.Img(a), "box3") == 3
+    nb = [a[j, i, 0] for j in (1, 2, 3) for i in (2, 3, 4) if (j, i) != (2, 3)]
+    assert d[2, 3, 0] == np.float32(sum(nb)) / np.float32(8)
+    assert d[0, 0, 1] == (a[0, 1, 1] + a[1, 0, 1] + a[1, 1, 1]) / np.float32(3)
+    d = np.zeros_like(a)
+    assert oracle.fix_nonfinite(oracle.Img(d), oracle.Img(a), "black") == 3
+    assert d[2, 3, 0] == 0 and d[4, 5, 0] == 0 and d[4, 5, 1] == 0 and d[1, 1, 1] == a[1, 1, 1]
+    d = np.zeros_like(a)
+    assert oracle.fix_nonfinite(oracle.Img(d), oracle.Img(a), "none") == 3
+    assert np.isnan(d[2, 3, 0])
+    h = (a * 100).astype(np.float16)
+    d = np.zeros_like(h)
+    oracle.fix_nonfinite(oracle.Img(d), oracle.Img(h), "box3")
+    s = np.float16(0)
+    for j in (1, 2, 3):
+        for i in (2, 3, 4):
+            if (j, i) != (2, 3):
+                s = np.float16(np.float32(s) + np.float32(h[j, i, 0]))
+    assert d[2, 3, 0] == np.float16(np.float32(s) / np.float32(8))

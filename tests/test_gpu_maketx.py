@@ -1,0 +1,157 @@
+"""GPU parity for the maketx pixel pipeline around the MIP chain:
+fixNonFinite / check_nan and make_texture (fixnan -> power-of-two resize ->
+float top level -> MIP chain with highlight compensation / sharpening),
+against the oracle stages chained the way make_texture_impl chains them
+(maketexture.cpp:1666-1705, 1791-1877, 811-987)."""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _sprinkle(a, seed, n=40):
+    """Isolated NaN / +-Inf values (no two within a 3x3 window of each other:
+    there the reference's in-place scan and any parallel repair agree)."""
+    rng = np.random.RandomState(seed)
+    h, w, c = a.shape
+    used = np.zeros((h, w), bool)
+    bad = [np.nan, np.inf, -np.inf]
+    k = 0
+    while k < n:
+        y, x = rng.randint(0, h), rng.randint(0, w)
+        if used[max(0, y - 2):y + 3, max(0, x - 2):x + 3].any():
+            continue
+        used[y, x] = True
+        a[y, x, rng.randint(0, c)] = bad[k % 3]
+        k += 1
+    # corners and edges: clipped neighbourhoods
+    for (y, x) in [(0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1)]:
+        if not used[max(0, y - 2):y + 3, max(0, x - 2):x + 3].any():
+            a[y, x, 0] = np.nan
+            used[y, x] = True
+            k += 1
+    return k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float16])
+@pytest.mark.parametrize("mode", ["box3", "black", "none"])
+def test_fix_nonfinite(oiio, oracle, dtype, mode):
+    src = synth.image(61, 47, 3, dtype, seed=5, hdr=True)
+    n = _sprinkle(src, 7)
+    ref = np.zeros_like(src)
+    nref = oracle.fix_nonfinite(oracle.Img(ref), oracle.Img(src), mode)
+    assert nref == n
+    IBA = oiio.ImageBufAlgo
+    m = {"box3": oiio.NONFINITE_BOX3, "black": oiio.NONFINITE_BLACK,
+         "none": oiio.NONFINITE_NONE}[mode]
+    out = IBA.fixNonFinite(oiio.ImageBuf(src), m)
+    assert not out.has_error, out.geterror()
+    assert IBA.last_pixels_fixed == n
+    assert np.array_equal(out.pixels.view(np.uint8), ref.view(np.uint8))
+    if mode != "none":
+        assert np.isfinite(out.pixels.astype(np.float32)).all()
+
+
+def test_fix_nonfinite_in_place_device_roi_and_error_mode(oiio, oracle):
+    import torch
+    src = synth.image(64, 40, 4, np.float32, seed=9)
+    _sprinkle(src, 11, 25)
+    ref = src.copy()
+    roi = (4, 60, 3, 37)
+    nref = oracle.fix_nonfinite(oracle.Img(ref), oracle.Img(ref), "box3", roi=roi,
+                                chrange=(0, 3))
+    t = torch.from_numpy(src).cuda()
+    B = oiio.ImageBuf(t)
+    IBA = oiio.ImageBufAlgo
+    assert IBA.fixNonFinite(B, B, oiio.NONFINITE_BOX3,
+                            roi=oiio.ROI(roi[0], roi[1], roi[2], roi[3], 0, 1, 0, 3))
+    assert IBA.last_pixels_fixed == nref
+    got = t.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # NONFINITE_ERROR: counts and fails
+    bad = IBA.fixNonFinite(oiio.ImageBuf(src), oiio.NONFINITE_ERROR)
+    assert bad.geterror() == "Nonfinite pixel values found"
+    # integer images: a plain copy
+    u8 = synth.image(30, 20, 3, np.uint8, seed=3)
+    out = IBA.fixNonFinite(oiio.ImageBuf(u8), oiio.NONFINITE_BOX3)
+    assert np.array_equal(out.pixels, u8) and IBA.last_pixels_fixed == 0
+
+
+def _oracle_pipeline(oracle, src, cfg):
+    """make_texture_impl's pixel stages with the oracle."""
+    a = src
+    if cfg.get("maketx:fixnan", "none") != "none" and a.dtype in (np.float32, np.float16):
+        b = np.zeros_like(a)
+        oracle.fix_nonfinite(oracle.Img(b), oracle.Img(a), cfg["maketx:fixnan"])
+        a = b
+    h, w, c = a.shape
+    f = np.zeros((h, w, c), np.float32)
+    oracle.resample(oracle.Img(f), oracle.Img(a), False)       # copy_pixels to float
+    fn = cfg.get("maketx:filtername", "box")
+    if cfg.get("maketx:resize"):
+        p2 = lambda v: 1 << (int(v) - 1).bit_length()
+        top = np.zeros((p2(h), p2(w), c), np.float32)
+        if fn in ("box", "triangle"):
+            oracle.resize_block(oracle.Img(top), oracle.Img(f))
+        else:
+            oracle.resize(oracle.Img(top), oracle.Img(f), fn)
+    else:
+        top = f
+    sharpen_first = True
+    sfilt = "gaussian"
+    if fn.startswith("post-"):
+        sharpen_first, fn = False, fn[5:]
+    if fn.startswith("unsharp-"):
+        sfilt, fn = fn[8:], "lanczos3"
+    levels = oracle.mip_chain(top, fn, highlightcomp=bool(cfg.get("maketx:highlightcomp")),
+                              alpha_channel=3 if c == 4 else -1,
+                              sharpen=cfg.get("maketx:sharpen", 0.0),
+                              sharpen_first=sharpen_first, sharpenfilt=sfilt)
+    if cfg.get("format") == "half":
+        levels = [np.clip(l, -65504.0, 65504.0) for l in levels]
+        if c == 4:
+            for l in levels:
+                l[..., 3] = np.clip(l[..., 3], 0, 1)
+    return [top] + levels
+
+
+@pytest.mark.parametrize("cfg", [
+    {},                                                             # maketx defaults: box
+    {"maketx:filtername": "lanczos3", "maketx:resize": 1},
+    {"maketx:filtername": "box", "maketx:resize": 1},
+    {"maketx:filtername": "lanczos3", "maketx:highlightcomp": 1, "maketx:fixnan": "box3"},
+    {"maketx:filtername": "post-unsharp-gaussian", "maketx:sharpen": 0.5},
+    {"maketx:filtername": "blackman-harris", "maketx:sharpen": 0.4, "format": "half"},
+])
+@pytest.mark.parametrize("dtype,nch", [(np.float32, 4), (np.uint8, 3)])
+def test_make_texture_matches_oracle_pipeline(oiio, oracle, cfg, dtype, nch):
+    src = synth.image(100, 60, nch, dtype, seed=131)
+    if dtype == np.float32:
+        src = (src * np.float32(3)).astype(np.float32)
+        if cfg.get("maketx:fixnan"):
+            _sprinkle(src, 17, 12)
+    ref = _oracle_pipeline(oracle, src, cfg)
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src.copy()), cfg)
+    assert T.ok, T.error
+    assert len(T.levels) == len(ref)
+    for i, (g, r) in enumerate(zip(T.levels, ref)):
+        gp = g.get_pixels()
+        assert gp.shape == r.shape, i
+        scale = max(1.0, float(np.abs(r).max()))
+        tol = (1e-4 if cfg.get("maketx:highlightcomp") else 2e-5) * max(1, i) * scale
+        assert np.abs(gp - r).max() <= tol, "level %d" % i
+
+
+def test_make_texture_checknan_and_nomipmap(oiio):
+    src = synth.image(32, 32, 3, np.float32, seed=1)
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"maketx:nomipmap": 1})
+    assert T.ok and len(T.levels) == 1
+    src[5, 6, 1] = np.inf
+    src[9, 9, 0] = np.nan
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"maketx:checknan": 1})
+    assert T.error == "maketx ERROR: Nan/Inf at 2 pixels"
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src),
+                          {"maketx:checknan": 1, "maketx:fixnan": "black"})
+    assert T.ok and T.pixels_fixed == 2
