@@ -365,7 +365,8 @@ def fit_geometry(sw, sh, fw, fh, fillmode="letterbox"):
 
 
 def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1,
-              sharpen=0.0, sharpen_first=False, sharpenfilt="gaussian"):
+              sharpen=0.0, sharpen_first=False, sharpenfilt="gaussian",
+              clamp_half=False):
     """write_mipmap level loop (maketexture.cpp:823-986) on a float32 HxWxC
     array, no file output.  Returns [level1, level2, ...].  highlightcomp:
     maketx --hicomp, rangecompress(img) / rangeexpand(small) + clamp around
@@ -400,6 +401,12 @@ def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1,
                 if alpha_channel >= 0:
                     np.clip(small[..., alpha_channel], 0, 1,
                             out=small[..., alpha_channel])
+        if clamp_half:
+            # clamp(small, small, -HALF_MAX, HALF_MAX, clampalpha01) (:943-945):
+            # in place, so the next level is made from the clamped one
+            np.clip(small, np.float32(-65504.0), np.float32(65504.0), out=small)
+            if alpha_channel >= 0:
+                np.clip(small[..., alpha_channel], 0, 1, out=small[..., alpha_channel])
         out.append(small)
         # the reference compresses img in place AFTER the level was written
         # to the file: keep the returned level intact

@@ -108,12 +108,8 @@ def _oracle_pipeline(oracle, src, cfg):
     levels = oracle.mip_chain(top, fn, highlightcomp=bool(cfg.get("maketx:highlightcomp")),
                               alpha_channel=3 if c == 4 else -1,
                               sharpen=cfg.get("maketx:sharpen", 0.0),
-                              sharpen_first=sharpen_first, sharpenfilt=sfilt)
-    if cfg.get("format") == "half":
-        levels = [np.clip(l, -65504.0, 65504.0) for l in levels]
-        if c == 4:
-            for l in levels:
-                l[..., 3] = np.clip(l[..., 3], 0, 1)
+                              sharpen_first=sharpen_first, sharpenfilt=sfilt,
+                              clamp_half=cfg.get("format") == "half")
     return [top] + levels
 
 
