@@ -313,6 +313,19 @@ B2R_API int b2r_fix_nonfinite(const b2r_image* dst, const b2r_image* src,
                               const b2r_options* opt, b2r_report* report,
                               char* err, size_t errlen);
 
+/* ---- fillholes_pushpull ---------------------------------------------------
+ * Replaces ImageBufAlgo::fillholes_pushpull (src/libOpenImageIO/
+ * imagebufalgo.cpp:1600-1670), an in-library user of the same resize: a float
+ * pyramid built with the triangle-filter resize (each level divided by its
+ * alpha where that is nonzero), then pulled back up with level OVER blown-up
+ * next level; the finished top level is pasted back at src's origin in dst's
+ * type.  Everything stays on the device between the 2*levels resizes.
+ * alpha_channel: ImageSpec::alpha_channel ("images must have alpha channels"
+ * if < 0).  dst and src need the same channel count; dst may be src. */
+B2R_API int b2r_fillholes_pushpull(const b2r_image* dst, const b2r_image* src,
+                                   int alpha_channel, const b2r_options* opt,
+                                   b2r_report* report, char* err, size_t errlen);
+
 /* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
  * The reference parallelises resize by full-width row bands
  * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The

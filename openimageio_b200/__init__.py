@@ -193,6 +193,10 @@ def lib():
                                     C.POINTER(C.c_int), C.POINTER(_Roi),
                                     C.POINTER(_Options), C.POINTER(Report),
                                     C.c_char_p, C.c_size_t]
+    L.b2r_fillholes_pushpull.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
+                                         C.c_int, C.POINTER(_Options),
+                                         C.POINTER(Report), C.c_char_p,
+                                         C.c_size_t]
     L.b2r_mipchain_nlevels.argtypes = [C.c_void_p]
     L.b2r_mipchain_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
@@ -878,6 +882,41 @@ class _IBA:
                                     float(v["width"]), float(v["contrast"]),
                                     float(v["threshold"]), C.byref(r), C.byref(o),
                                     None, err, 512)
+        if rc:
+            dst.errorfmt(err.value.decode())
+            return False
+        return True
+
+    # ---- fillholes_pushpull ----------------------------------------------
+    def fillholes_pushpull(self, *args, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::fillholes_pushpull(dst, src, roi, nthreads)
+        (imagebufalgo.cpp:1600-1682)."""
+        bufs = [a for a in args if isinstance(a, ImageBuf)]
+        if len(bufs) == 2:
+            return self._fillholes(bufs[0], bufs[1], roi, device)
+        result = ImageBuf()
+        ok = self._fillholes(result, bufs[0], roi, device)
+        if not ok and not result.has_error:
+            result.errorfmt("ImageBufAlgo::fillholes_pushpull() error")
+        return result
+
+    def _fillholes(self, dst, src, roi, device):
+        roi = _ibaprep(roi, dst, src)
+        if roi is None:
+            return False
+        if dst.nchannels != src.nchannels:
+            dst.errorfmt("images must have the same number of channels")
+            return False
+        if src.spec_.alpha_channel < 0 or dst.spec_.alpha_channel < 0:
+            dst.errorfmt("images must have alpha channels")
+            return False
+        d, s = dst._c(), src._c()
+        o = _options(device, PATH_AUTO,
+                     _current_stream(dst) or _current_stream(src))
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_fillholes_pushpull(C.byref(d), C.byref(s),
+                                          src.spec_.alpha_channel, C.byref(o),
+                                          None, err, 512)
         if rc:
             dst.errorfmt(err.value.decode())
             return False

@@ -3271,3 +3271,141 @@ b2r_fix_nonfinite(const b2r_image* dst, const b2r_image* src, int mode, int* pix
     }
     return B2R_OK;
 }
+
+
+// =========================================================================
+// fillholes_pushpull (imagebufalgo.cpp:1600-1670): a float pyramid made with
+// the triangle-filter resize, pushed down (divide by alpha) and pulled back up
+// (over), entirely on the device.
+// =========================================================================
+extern "C" int
+b2r_fillholes_pushpull(const b2r_image* dst, const b2r_image* src, int alpha_channel,
+                       const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
+{
+    int rc = check_image(src, true, err, errlen);
+    if (rc)
+        return rc;
+    if (alpha_channel < 0 || alpha_channel >= src->nchannels) {
+        set_err(err, errlen, "images must have alpha channels");
+        return B2R_ERR_INVALID;
+    }
+    // the result is pasted back at the source's origin (:1659): the region
+    // written is src's data window (clipped to dst's)
+    b2r_roi roi { src->x, src->x + src->width, src->y, src->y + src->height, 0,
+                  src->nchannels };
+    StencilIO io;
+    rc = io.begin(dst, src, &roi, opt, report, "fillholes_pushpull", err, errlen);
+    if (rc || io.empty) {
+        io.release();
+        return rc;
+    }
+    const int nch = src->nchannels;
+    const int W = src->width, H = src->height;
+    struct Lv {
+        int w, h;
+        float* px;
+    };
+    std::vector<Lv> pyr;
+    float* blow = nullptr;
+    auto fail = [&](int code) {
+        for (auto& l : pyr)
+            if (l.px)
+                cudaFreeAsync(l.px, io.stream);
+        if (blow)
+            cudaFreeAsync(blow, io.stream);
+        io.release();
+        return code;
+    };
+    for (int w = W, h = H;;) {
+        Lv l { w, h, nullptr };
+        if (cudaMallocAsync((void**)&l.px, size_t(w) * h * nch * 4, io.stream) != cudaSuccess) {
+            set_err(err, errlen, "fillholes_pushpull: out of device memory");
+            return fail(B2R_ERR_CUDA);
+        }
+        pyr.push_back(l);
+        if (w <= 1 && h <= 1)
+            break;
+        w = std::max(1, w / 2);
+        h = std::max(1, h / 2);
+    }
+    auto describe = [&](const Lv& l) {
+        b2r_image im;
+        memset(&im, 0, sizeof(im));
+        im.pixels    = l.px;
+        im.basetype  = B2R_FLOAT;
+        im.nchannels = nch;
+        im.width = im.full_width = l.w;
+        im.height = im.full_height = l.h;
+        im.xstride  = (int64_t)nch * 4;
+        im.ystride  = (int64_t)l.w * nch * 4;
+        im.memspace = B2R_MEM_DEVICE;
+        im.device   = io.device;
+        return im;
+    };
+    b2r_options sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.device      = io.device;
+    sub.cuda_stream = (void*)io.stream;
+    int launched    = 0;
+    {   // top = float copy of src shifted to the origin (paste, :1620-1634):
+        // a nearest resample between equal windows is the identity + conversion
+        b2r_image T = describe(pyr[0]);
+        b2r_image S = io.srcd;
+        S.pixels    = io.dsrc;
+        S.x = S.y = S.full_x = S.full_y = 0;
+        S.full_width  = S.width;
+        S.full_height = S.height;
+        S.memspace    = B2R_MEM_DEVICE;
+        S.device      = io.device;
+        rc = b2r_resample(&T, &S, 0, nullptr, &sub, nullptr, err, errlen);
+        if (rc)
+            return fail(rc);
+        ++launched;
+    }
+    for (size_t i = 1; i < pyr.size(); ++i) {
+        b2r_image D = describe(pyr[i]), S = describe(pyr[i - 1]);
+        rc = b2r_resize(&D, &S, "triangle", 0.0f, nullptr, &sub, nullptr, err, errlen);
+        if (rc)
+            return fail(rc);
+        launch_divide_by_alpha(pyr[i].px, (long long)pyr[i].w * pyr[i].h, nch, alpha_channel,
+                               io.stream);
+        launched += 3;
+    }
+    if (pyr.size() > 1) {
+        if (cudaMallocAsync((void**)&blow, size_t(W) * H * nch * 4, io.stream) != cudaSuccess) {
+            set_err(err, errlen, "fillholes_pushpull: out of device memory");
+            return fail(B2R_ERR_CUDA);
+        }
+        for (int i = (int)pyr.size() - 2; i >= 0; --i) {
+            Lv b { pyr[i].w, pyr[i].h, blow };
+            b2r_image D = describe(b), S = describe(pyr[i + 1]);
+            rc = b2r_resize(&D, &S, "triangle", 0.0f, nullptr, &sub, nullptr, err, errlen);
+            if (rc)
+                return fail(rc);
+            launch_over_inplace(pyr[i].px, blow, (long long)pyr[i].w * pyr[i].h, nch,
+                                alpha_channel, io.stream);
+            launched += 3;
+        }
+    }
+    {   // paste the finished top level back at src's origin, in dst's type
+        const b2r_image& D = io.dstd;
+        const int x0 = io.roi.xbegin, y0 = io.roi.ybegin;  // inside src's window
+        if (D.xstride != (int64_t)nch * basetype_size(D.basetype)) {
+            set_err(err, errlen, "destination pixels must be contiguous in x");
+            return fail(B2R_ERR_UNSUPPORTED);
+        }
+        unsigned char* dp = (unsigned char*)io.ddst + (long long)(y0 - D.y) * D.ystride
+                            + (long long)(x0 - D.x) * D.xstride;
+        const float* sp = pyr[0].px + ((size_t)(y0 - src->y) * W + (x0 - src->x)) * nch;
+        launch_convert_from_float(sp, (long long)W * nch * 4, dp, D.ystride, io.roi_w * nch,
+                                  io.roi_h, D.basetype, io.stream);
+        ++launched;
+    }
+    for (auto& l : pyr)
+        cudaFreeAsync(l.px, io.stream);
+    pyr.clear();
+    if (blow)
+        cudaFreeAsync(blow, io.stream);
+    blow = nullptr;
+    return io.end(*dst, report, launched, err, errlen);
+}

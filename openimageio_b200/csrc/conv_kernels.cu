@@ -309,3 +309,69 @@ launch_fix_nonfinite(const NonFiniteParams& p, void* stream)
 }
 
 }  // namespace b2r
+
+// ===========================================================================
+// The two point ops of fillholes_pushpull (imagebufalgo.cpp:1578-1596 and
+// imagebufalgo_pixelmath.cpp:1687-1692, 1733-1739) on contiguous float
+// images: divide the pixels with nonzero alpha by their alpha, and
+// big = big OVER blowup (big + (1 - clamp(alpha_big, 0, 1)) * blowup).
+// ===========================================================================
+namespace b2r {
+namespace {
+
+__global__ void __launch_bounds__(256)
+divide_by_alpha_kernel(float* px, long long npixels, int nch, int alpha_channel)
+{
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npixels;
+         i += (long long)gridDim.x * blockDim.x) {
+        float* p      = px + i * nch;
+        const float a = p[alpha_channel];
+        if (a != 0.0f)
+            for (int c = 0; c < nch; ++c)
+                p[c] = __fdiv_rn(p[c], a);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+over_inplace_kernel(float* big, const float* blowup, long long npixels, int nch,
+                    int alpha_channel)
+{
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npixels;
+         i += (long long)gridDim.x * blockDim.x) {
+        float* a       = big + i * nch;
+        const float* b = blowup + i * nch;
+        const float alpha = fminf(fmaxf(a[alpha_channel], 0.0f), 1.0f);
+        const float oma   = __fsub_rn(1.0f, alpha);
+        for (int c = 0; c < nch; ++c)
+            a[c] = __fadd_rn(a[c], __fmul_rn(oma, b[c]));
+    }
+}
+
+unsigned
+point_grid(long long n)
+{
+    return (unsigned)std::min<long long>((n + 255) / 256, 148 * 16);
+}
+
+}  // namespace
+
+void
+launch_divide_by_alpha(float* px, long long npixels, int nch, int alpha_channel, void* stream)
+{
+    if (npixels > 0)
+        launch_pdl(divide_by_alpha_kernel, dim3(point_grid(npixels)), dim3(256), 0,
+                   (cudaStream_t)stream, px, npixels, nch, alpha_channel);
+}
+
+void
+launch_over_inplace(float* big, const float* blowup, long long npixels, int nch,
+                    int alpha_channel, void* stream)
+{
+    if (npixels > 0)
+        launch_pdl(over_inplace_kernel, dim3(point_grid(npixels)), dim3(256), 0,
+                   (cudaStream_t)stream, big, blowup, npixels, nch, alpha_channel);
+}
+
+}  // namespace b2r

@@ -285,6 +285,14 @@ struct NonFiniteParams {
 void
 launch_fix_nonfinite(const NonFiniteParams& p, void* stream);
 
+// fillholes_pushpull's point ops on contiguous float images
+// (imagebufalgo.cpp:1578-1596; imagebufalgo_pixelmath.cpp:1687-1692)
+void
+launch_divide_by_alpha(float* px, long long npixels, int nch, int alpha_channel, void* stream);
+void
+launch_over_inplace(float* big, const float* blowup, long long npixels, int nch,
+                    int alpha_channel, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

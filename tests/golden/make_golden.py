@@ -20,6 +20,7 @@ Sources (all under /root/reference/testsuite, OpenImageIO 3.2.0.2-dev):
   oiiotool-xform/ref/{warped,rotated,rotated-offcenter,resizefrom*}.tif,
   oiiotool-xform/src/target1.exr, ref/fit4.exr, two of ref/fit[wh]-*.exr
   oiiotool/ref/bspline-blur.tif, gauss5x5-blur.tif, unsharp.tif
+  oiiotool/src/hole.tif, oiiotool/ref/tahoe-filled.tif, growholes.tif
 Only pixel arrays are stored (no reference source code is copied).
 """
 import os
@@ -115,6 +116,14 @@ def main():
     for k, v in cv.items():
         print(k, v.shape, v.dtype)
     np.savez_compressed(os.path.join(HERE, "conv_ref.npz"), **cv)
+
+    # fillholes_pushpull known answers (testsuite/oiiotool/run.py:124-126)
+    fh = {"hole": read(os.path.join(REF, "oiiotool/src/hole.tif")),
+          "tahoe_filled": read(os.path.join(REF, "oiiotool/ref/tahoe-filled.tif")),
+          "growholes": read(os.path.join(REF, "oiiotool/ref/growholes.tif"))}
+    for k, v in fh.items():
+        print(k, v.shape, v.dtype)
+    np.savez_compressed(os.path.join(HERE, "fillholes_ref.npz"), **fh)
 
 
 if __name__ == "__main__":

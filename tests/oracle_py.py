@@ -414,6 +414,36 @@ def mip_chain(level0, filtername="box", highlightcomp=False, alpha_channel=-1,
     return out
 
 
+def fillholes_pushpull(src_arr, alpha_channel):
+    """ImageBufAlgo::fillholes_pushpull (imagebufalgo.cpp:1600-1670) on an
+    HxWxC array of any of the four types: float pyramid by triangle resize +
+    divide_by_alpha (:1578-1596), pulled back up with `over`
+    (imagebufalgo_pixelmath.cpp:1687-1692), converted back to the input type.
+    Composition of the oracle's resize with float32 numpy point ops."""
+    f32 = np.float32
+    h, w, c = src_arr.shape
+    top = np.zeros((h, w, c), f32)
+    resample(Img(top), Img(src_arr), False)          # paste: convert to float
+    pyramid = [top]
+    while w > 1 or h > 1:
+        w, h = max(1, w // 2), max(1, h // 2)
+        small = np.zeros((h, w, c), f32)
+        resize(Img(small), Img(pyramid[-1]), "triangle")
+        a = small[..., alpha_channel]
+        nz = a != 0
+        small[nz] = small[nz] / a[nz][:, None]
+        pyramid.append(small)
+    for i in range(len(pyramid) - 2, -1, -1):
+        big, small = pyramid[i], pyramid[i + 1]
+        blowup = np.zeros_like(big)
+        resize(Img(blowup), Img(small), "triangle")
+        alpha = np.clip(big[..., alpha_channel], f32(0), f32(1))
+        one_minus = (f32(1) - alpha)[..., None]
+        big[...] = big + one_minus * blowup
+    return quantize(pyramid[0], src_arr.dtype) if src_arr.dtype != np.float32 \
+        else pyramid[0]
+
+
 def quantize(arr_f32, dtype):
     """convert_type<float, D> on a whole array through the oracle's store."""
     dtype = np.dtype(dtype)

@@ -428,3 +428,11 @@ def test_oracle_fix_nonfinite(oracle):
             if (j, i) != (2, 3):
                 s = np.float16(np.float32(s) + np.float32(h[j, i, 0]))
     assert d[2, 3, 0] == np.float16(np.float32(s) / np.float32(8))
+
+
+def test_oracle_fillholes_golden(oracle):
+    """testsuite/oiiotool src/hole.tif --fillholes == ref/tahoe-filled.tif, bit
+    for bit (triangle resize pyramid + divide_by_alpha + over)."""
+    G = np.load(os.path.join(GOLD, "fillholes_ref.npz"))
+    out = oracle.fillholes_pushpull(G["hole"], 3)
+    assert np.array_equal(out, G["tahoe_filled"])

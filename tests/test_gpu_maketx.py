@@ -151,3 +151,45 @@ def test_make_texture_checknan_and_nomipmap(oiio):
     T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src),
                           {"maketx:checknan": 1, "maketx:fixnan": "black"})
     assert T.ok and T.pixels_fixed == 2
+
+
+# ------------------------------------------------------ fillholes_pushpull ----
+def test_fillholes_golden(oiio, oracle):
+    """testsuite/oiiotool: src/hole.tif --fillholes -> ref/tahoe-filled.tif (the
+    oracle composition reproduces it bit for bit, test_cpu)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                             "fillholes_ref.npz"))
+    out = oiio.ImageBufAlgo.fillholes_pushpull(oiio.ImageBuf(G["hole"].copy()))
+    assert not out.has_error, out.geterror()
+    d = np.abs(out.pixels.astype(int) - G["tahoe_filled"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16])
+@pytest.mark.parametrize("size", [(97, 61), (64, 64), (33, 1)])
+def test_fillholes_matches_oracle(oiio, oracle, dtype, size):
+    w, h = size
+    src = synth.image(w, h, 4, np.float32, seed=141)
+    hole = synth.image(w, h, 1, np.float32, seed=142)[..., 0] < 0.35
+    src[..., 3] = 1.0
+    src[hole] = 0.0                                   # premultiplied holes
+    if dtype != np.float32:
+        src = oracle.quantize(src, dtype)
+    ref = oracle.fillholes_pushpull(src, 3)
+    B = oiio.ImageBuf(src.copy())
+    B.spec().x, B.spec().y = 7, -3                    # data origin off the display origin
+    out = oiio.ImageBufAlgo.fillholes_pushpull(B)
+    assert not out.has_error, out.geterror()
+    if dtype == np.float32:
+        assert np.abs(out.pixels - ref).max() <= 5e-5
+        assert (out.pixels[..., 3] > 0.99).all() or hole.all()
+    else:
+        d = np.abs(out.pixels.astype(int) - ref.astype(int))
+        assert d.max() <= 3 and (d > 1).mean() < 1e-3
+
+
+def test_fillholes_errors(oiio):
+    rgb = oiio.ImageBuf(np.zeros((8, 8, 3), np.float32))
+    assert oiio.ImageBufAlgo.fillholes_pushpull(rgb).geterror() == \
+        "images must have alpha channels"
