@@ -326,6 +326,30 @@ B2R_API int b2r_fillholes_pushpull(const b2r_image* dst, const b2r_image* src,
                                    int alpha_channel, const b2r_options* opt,
                                    b2r_report* report, char* err, size_t errlen);
 
+/* ---- computePixelStats / isMonochrome -------------------------------------
+ * Replaces ImageBufAlgo::computePixelStats (src/libOpenImageIO/
+ * imagebufalgo_compare.cpp:81-215) and, in the same pass over the pixels,
+ * ImageBufAlgo::isMonochrome (:539-600): the whole-image reductions
+ * make_texture_impl starts with (maketexture.cpp:1396-1409 -- average colour,
+ * constant-colour detection as min == max -- and :1469-1476).  One
+ * b2r_pixel_stats_t per channel of src (ImageBufAlgo::PixelStats: sum and sum2
+ * in double, min/max/avg/stddev in float, counts).  roi NULL = the data
+ * window; channels outside [chbegin,chend) keep PixelStats::reset()'s zeros...
+ * (min/max are finalised to 0 for channels with no finite value, :103-108).
+ * is_monochrome may be NULL; threshold 0 compares exactly (:551-561).
+ * Sums are accumulated per thread and merged in a fixed order: deterministic,
+ * and equal to the reference's to double rounding (its own merge order depends
+ * on thread timing). */
+typedef struct b2r_pixel_stats_t {
+    float min, max, avg, stddev;
+    int64_t nancount, infcount, finitecount;
+    double sum, sum2;
+} b2r_pixel_stats_t;
+B2R_API int b2r_pixel_stats(const b2r_image* src, const b2r_roi* roi,
+                            b2r_pixel_stats_t* stats, int nstats,
+                            int* is_monochrome, float mono_threshold,
+                            const b2r_options* opt, char* err, size_t errlen);
+
 /* ---- row-band sharding (multi-GPU / multi-rank) --------------------------
  * The reference parallelises resize by full-width row bands
  * (parallel_image, src/include/OpenImageIO/imagebufalgo_util.h:37-80).  The

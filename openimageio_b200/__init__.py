@@ -71,6 +71,22 @@ class _MipOptions(C.Structure):
                 ("reserved", C.c_int32 * 4)]
 
 
+class _PixelStatsC(C.Structure):
+    _fields_ = [("min", C.c_float), ("max", C.c_float), ("avg", C.c_float),
+                ("stddev", C.c_float), ("nancount", C.c_int64),
+                ("infcount", C.c_int64), ("finitecount", C.c_int64),
+                ("sum", C.c_double), ("sum2", C.c_double)]
+
+
+class PixelStats:
+    """ImageBufAlgo::PixelStats (imagebufalgo.h): per-channel lists."""
+
+    def __init__(self, recs=(), monochrome=None):
+        for f, _ in _PixelStatsC._fields_:
+            setattr(self, f, [getattr(r, f) for r in recs])
+        self.monochrome = monochrome
+
+
 class Report(C.Structure):
     _fields_ = [("path_used", C.c_int32), ("kernels_launched", C.c_int32),
                 ("xtaps", C.c_int32), ("ytaps", C.c_int32),
@@ -197,6 +213,10 @@ def lib():
                                          C.c_int, C.POINTER(_Options),
                                          C.POINTER(Report), C.c_char_p,
                                          C.c_size_t]
+    L.b2r_pixel_stats.argtypes = [C.POINTER(_Image), C.POINTER(_Roi),
+                                  C.POINTER(_PixelStatsC), C.c_int,
+                                  C.POINTER(C.c_int), C.c_float,
+                                  C.POINTER(_Options), C.c_char_p, C.c_size_t]
     L.b2r_mipchain_nlevels.argtypes = [C.c_void_p]
     L.b2r_mipchain_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
                                      C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
@@ -887,6 +907,49 @@ class _IBA:
             return False
         return True
 
+    # ---- computePixelStats / isMonochrome ---------------------------------
+    def computePixelStats(self, src, roi=None, nthreads=0, device=0,
+                          mono_threshold=0.0):
+        """ImageBufAlgo::computePixelStats(src, roi, nthreads)
+        (imagebufalgo_compare.cpp:187-208); the same pass also answers
+        isMonochrome (`.monochrome`).  An empty PixelStats on error."""
+        if src is None or not src.initialized:
+            return PixelStats()
+        n = src.nchannels
+        recs = (_PixelStatsC * n)()
+        mono = C.c_int(1)
+        s = src._c()
+        o = _options(device, PATH_AUTO, _current_stream(src))
+        err = C.create_string_buffer(512)
+        r = None
+        if roi is not None and roi.defined:
+            r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
+                     min(roi.chend, n))
+        rc = lib().b2r_pixel_stats(C.byref(s), C.byref(r) if r else None, recs, n,
+                                   C.byref(mono), float(mono_threshold),
+                                   C.byref(o), err, 512)
+        if rc:
+            src.errorfmt(err.value.decode())
+            return PixelStats()
+        return PixelStats(list(recs), bool(mono.value))
+
+    def isMonochrome(self, src, threshold=0.0, roi=None, nthreads=0, device=0):
+        """ImageBufAlgo::isMonochrome (imagebufalgo_compare.cpp:579-600)."""
+        st = self.computePixelStats(src, roi, device=device,
+                                    mono_threshold=threshold)
+        return bool(st.monochrome)
+
+    def isConstantColor(self, src, threshold=0.0, roi=None, nthreads=0, device=0):
+        """The exact (threshold 0) form maketx uses: constant iff min == max
+        in every channel (maketexture.cpp:1425).  Returns the colour or None."""
+        if threshold != 0.0:
+            raise B2RError("isConstantColor: only threshold 0 is on this path")
+        st = self.computePixelStats(src, roi, device=device)
+        if st.min and st.min == st.max and not any(st.nancount) \
+                and not any(st.infcount):
+            return list(st.min)
+        return None
+
     # ---- fillholes_pushpull ----------------------------------------------
     def fillholes_pushpull(self, *args, roi=None, nthreads=0, device=0):
         """ImageBufAlgo::fillholes_pushpull(dst, src, roi, nthreads)
@@ -1416,6 +1479,10 @@ class Texture:
         self.levels = []
         self.format = "float"
         self.pixels_fixed = 0
+        self.stats = None           # PixelStats of the (repaired) source
+        self.average_color = None   # "oiio:AverageColor"
+        self.constant_color = None  # "oiio:ConstantColor" when min == max
+        self.monochrome = None
         self.error = ""
 
     @property
@@ -1471,6 +1538,20 @@ def make_texture(mode, src, config=None, device=0):
         if IBA.last_pixels_fixed:
             T.error = "maketx ERROR: Nan/Inf at %d pixels" % IBA.last_pixels_fixed
             return T
+    # pixel statistics (:1396-1409): average colour, constant-colour and
+    # monochrome detection, one pass on the device
+    if any(cfg.get(k, d) for k, d in (("maketx:compute_average", 1),
+                                      ("maketx:constant_color_detect", 0),
+                                      ("maketx:opaque_detect", 0),
+                                      ("maketx:monochrome_detect", 0))):
+        T.stats = IBA.computePixelStats(src, device=device)
+        if not T.stats.min:
+            T.error = src.geterror() or "computePixelStats failed"
+            return T
+        T.average_color = list(T.stats.avg)
+        T.constant_color = (list(T.stats.min) if T.stats.min == T.stats.max
+                            else None)
+        T.monochrome = T.stats.monochrome
     filtername = cfg.get("maketx:filtername", "box") or "box"
     # top level: resize to a power of two and/or convert to float (:1791-1877)
     dw, dh = sspec.width, sspec.height

@@ -3409,3 +3409,167 @@ b2r_fillholes_pushpull(const b2r_image* dst, const b2r_image* src, int alpha_cha
     blow = nullptr;
     return io.end(*dst, report, launched, err, errlen);
 }
+
+
+// =========================================================================
+// computePixelStats / isMonochrome (imagebufalgo_compare.cpp:81-215, 539-600)
+// =========================================================================
+extern "C" int
+b2r_pixel_stats(const b2r_image* src, const b2r_roi* roi_in, b2r_pixel_stats_t* stats,
+                int nstats, int* is_monochrome, float mono_threshold, const b2r_options* opt,
+                char* err, size_t errlen)
+{
+    int rc = check_image(src, true, err, errlen);
+    if (rc)
+        return rc;
+    if (!stats || nstats < src->nchannels) {
+        set_err(err, errlen, "pixel_stats: need one stats record per channel (%d)",
+                src->nchannels);
+        return B2R_ERR_INVALID;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 pixel statistics path has no CPU "
+                "fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    const int nch = src->nchannels;
+    b2r_roi roi;
+    if (roi_in) {
+        roi        = *roi_in;
+        roi.chbegin = std::max(roi.chbegin, 0);
+        roi.chend  = std::min(roi.chend, nch);
+    } else {
+        roi = b2r_roi { src->x, src->x + src->width, src->y, src->y + src->height, 0, nch };
+    }
+    // PixelStats::reset
+    for (int c = 0; c < nch; ++c) {
+        memset(&stats[c], 0, sizeof(stats[c]));
+    }
+    if (is_monochrome)
+        *is_monochrome = 1;
+    // pixels of the ROI outside the data window read as black through the
+    // iterator; restrict to the window and account for them as zeros below
+    const int x0 = std::max(roi.xbegin, src->x), x1 = std::min(roi.xend, src->x + src->width);
+    const int y0 = std::max(roi.ybegin, src->y), y1 = std::min(roi.yend, src->y + src->height);
+    const long long roi_px = (long long)std::max(0, roi.xend - roi.xbegin)
+                             * std::max(0, roi.yend - roi.ybegin);
+    const long long in_px = (long long)std::max(0, x1 - x0) * std::max(0, y1 - y0);
+    std::vector<StatsPartial> total((size_t)nch);
+    for (auto& t : total) {
+        t.sum = t.sum2 = 0.0;
+        t.mn  = INFINITY;
+        t.mx  = -INFINITY;
+        t.finite = t.nan = t.inf = 0;
+    }
+    bool mono = true;
+    if (in_px > 0 && roi.chend > roi.chbegin) {
+        int dev = opt ? opt->device : 0;
+        const int mem = memspace_of(src, &dev);
+        if (dev < 0 || dev >= device_count_cached()) {
+            set_err(err, errlen, "invalid CUDA device ordinal %d", dev);
+            return B2R_ERR_INVALID;
+        }
+        DeviceGuard guard(dev);
+        device_info(dev);
+        cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+        b2r_image S = *src;
+        void* spix  = src->pixels;
+        void* stage = nullptr;
+        const int es = basetype_size(src->basetype);
+        if (mem == B2R_MEM_HOST) {
+            if (src->xstride != (int64_t)nch * es) {
+                set_err(err, errlen, "host source pixels must be contiguous in x");
+                return B2R_ERR_UNSUPPORTED;
+            }
+            const size_t rowbytes = size_t(x1 - x0) * src->xstride;
+            const size_t pitch    = (rowbytes + 15) & ~size_t(15);
+            CUDA_TRY(cudaMallocAsync(&stage, pitch * (y1 - y0), stream));
+            const unsigned char* hp = (const unsigned char*)src->pixels
+                                      + (long long)(y0 - src->y) * src->ystride
+                                      + (long long)(x0 - src->x) * src->xstride;
+            CUDA_TRY(cudaMemcpy2DAsync(stage, pitch, hp, src->ystride, rowbytes, y1 - y0,
+                                       cudaMemcpyHostToDevice, stream));
+            S.x = x0, S.y = y0, S.width = x1 - x0, S.height = y1 - y0;
+            S.ystride = (int64_t)pitch;
+            spix      = stage;
+        }
+        const int nblocks = stats_grid_blocks(y1 - y0);
+        StatsPartial* dpart = nullptr;
+        int* dmono          = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&dpart, sizeof(StatsPartial) * nblocks * nch, stream));
+        CUDA_TRY(cudaMallocAsync((void**)&dmono, sizeof(int) * nblocks, stream));
+        StatsParams sp;
+        memset(&sp, 0, sizeof(sp));
+        sp.src       = to_dev(S, spix);
+        sp.roi_x0    = x0, sp.roi_x1 = x1, sp.roi_y0 = y0, sp.roi_y1 = y1;
+        sp.chbegin   = roi.chbegin;
+        sp.chend     = roi.chend;
+        sp.nchannels = nch;
+        sp.partials  = dpart;
+        sp.want_mono = is_monochrome ? 1 : 0;
+        sp.mono_threshold = mono_threshold;
+        sp.mono_flags     = dmono;
+        launch_pixel_stats(sp, nblocks, stream);
+        std::vector<StatsPartial> hpart((size_t)nblocks * nch);
+        std::vector<int> hmono((size_t)nblocks, 1);
+        CUDA_TRY(cudaMemcpyAsync(hpart.data(), dpart, sizeof(StatsPartial) * hpart.size(),
+                                 cudaMemcpyDeviceToHost, stream));
+        if (is_monochrome)
+            CUDA_TRY(cudaMemcpyAsync(hmono.data(), dmono, sizeof(int) * nblocks,
+                                     cudaMemcpyDeviceToHost, stream));
+        cudaFreeAsync(dpart, stream);
+        cudaFreeAsync(dmono, stream);
+        if (stage)
+            cudaFreeAsync(stage, stream);
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        {
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) {
+                set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+                return B2R_ERR_CUDA;
+            }
+        }
+        for (int b = 0; b < nblocks; ++b) {  // PixelStats::merge, in block order
+            for (int c = roi.chbegin; c < roi.chend; ++c) {
+                const StatsPartial& q = hpart[(size_t)b * nch + c];
+                StatsPartial& t       = total[c];
+                t.mn = std::min(t.mn, q.mn);
+                t.mx = std::max(t.mx, q.mx);
+                t.nan += q.nan, t.inf += q.inf, t.finite += q.finite;
+                t.sum += q.sum, t.sum2 += q.sum2;
+            }
+            mono = mono && hmono[b] != 0;
+        }
+    }
+    // black pixels of the ROI beyond the data window: value 0 in every channel
+    if (roi_px > in_px)
+        for (int c = roi.chbegin; c < roi.chend; ++c) {
+            total[c].finite += (unsigned long long)(roi_px - in_px);
+            total[c].mn = std::min(total[c].mn, 0.0f);
+            total[c].mx = std::max(total[c].mx, 0.0f);
+        }
+    for (int c = 0; c < nch; ++c) {  // finalize (:101-118)
+        const StatsPartial& t = total[c];
+        b2r_pixel_stats_t& o  = stats[c];
+        o.nancount    = (int64_t)t.nan;
+        o.infcount    = (int64_t)t.inf;
+        o.finitecount = (int64_t)t.finite;
+        o.sum         = t.sum;
+        o.sum2        = t.sum2;
+        if (t.finite == 0) {
+            o.min = o.max = o.avg = o.stddev = 0.0f;
+        } else {
+            const double count = double(t.finite);
+            const double davg  = t.sum / count;
+            const double var   = t.sum2 / count - davg * davg;
+            o.min    = t.mn;
+            o.max    = t.mx;
+            o.avg    = float(davg);
+            o.stddev = float(var > 0.0 ? sqrt(var) : 0.0);
+        }
+    }
+    if (is_monochrome)
+        *is_monochrome = (nch < 2 || mono) ? 1 : 0;
+    return B2R_OK;
+}

@@ -293,6 +293,27 @@ void
 launch_over_inplace(float* big, const float* blowup, long long npixels, int nch,
                     int alpha_channel, void* stream);
 
+// computePixelStats + isMonochrome in one pass (imagebufalgo_compare.cpp:81-215,
+// 539-600).  One partial per (block, channel), merged on the host.
+struct StatsPartial {
+    double sum, sum2;
+    float mn, mx;
+    unsigned long long finite, nan, inf;
+};
+struct StatsParams {
+    DevImage src;
+    int roi_x0, roi_x1, roi_y0, roi_y1;
+    int chbegin, chend, nchannels;
+    StatsPartial* partials;  // [nblocks * nchannels]
+    int want_mono;
+    float mono_threshold;
+    int* mono_flags;         // [nblocks]
+};
+int
+stats_grid_blocks(int rows);
+void
+launch_pixel_stats(const StatsParams& p, int nblocks, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

@@ -444,6 +444,47 @@ def fillholes_pushpull(src_arr, alpha_channel):
         else pyramid[0]
 
 
+def pixel_stats(arr):
+    """ImageBufAlgo::computePixelStats (imagebufalgo_compare.cpp:81-215) on an
+    HxWxC array: per channel dict of min, max, avg, stddev, nancount,
+    infcount, finitecount, sum, sum2.  Values are converted to float the way
+    the iterator does; sums run in double (numpy pairwise summation -- the
+    reference's own order depends on its thread bands)."""
+    h, w, c = arr.shape
+    f = np.zeros((h, w, c), np.float32)
+    resample(Img(f), Img(arr), False)
+    out = []
+    for ch in range(c):
+        v = f[..., ch].ravel()
+        nan = np.isnan(v)
+        inf = np.isinf(v)
+        fin = v[~(nan | inf)].astype(np.float64)
+        d = dict(nancount=int(nan.sum()), infcount=int(inf.sum()),
+                 finitecount=int(fin.size), sum=float(fin.sum()),
+                 sum2=float((fin * fin).sum()))
+        if fin.size == 0:
+            d.update(min=0.0, max=0.0, avg=0.0, stddev=0.0)
+        else:
+            davg = d["sum"] / fin.size
+            var = d["sum2"] / fin.size - davg * davg
+            d.update(min=float(np.float32(fin.min())), max=float(np.float32(fin.max())),
+                     avg=float(np.float32(davg)),
+                     stddev=float(np.float32(np.sqrt(var) if var > 0 else 0.0)))
+        out.append(d)
+    return out
+
+
+def is_monochrome(arr, threshold=0.0):
+    """ImageBufAlgo::isMonochrome (imagebufalgo_compare.cpp:539-600)."""
+    if arr.shape[2] < 2:
+        return True
+    if threshold == 0.0:
+        return bool((arr[..., 1:] == arr[..., :1]).all())
+    f = np.zeros(arr.shape, np.float32)
+    resample(Img(f), Img(arr), False)
+    return bool(not (np.abs(f[..., 1:] - f[..., :1]) > np.float32(threshold)).any())
+
+
 def quantize(arr_f32, dtype):
     """convert_type<float, D> on a whole array through the oracle's store."""
     dtype = np.dtype(dtype)

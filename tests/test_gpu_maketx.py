@@ -193,3 +193,68 @@ def test_fillholes_errors(oiio):
     rgb = oiio.ImageBuf(np.zeros((8, 8, 3), np.float32))
     assert oiio.ImageBufAlgo.fillholes_pushpull(rgb).geterror() == \
         "images must have alpha channels"
+
+
+# ------------------------------------------------------------- pixel stats ----
+@pytest.mark.parametrize("dtype,nch", [(np.float32, 4), (np.float32, 3), (np.float16, 4),
+                                       (np.uint8, 3), (np.uint16, 1), (np.float32, 6)])
+def test_pixel_stats(oiio, oracle, dtype, nch):
+    src = synth.image(333, 257, nch, dtype, seed=151, hdr=(dtype == np.float32))
+    if dtype in (np.float32, np.float16):
+        src[5, 7, 0] = np.nan
+        src[100, 200, nch - 1] = np.inf
+        src[101, 200, nch - 1] = -np.inf
+    ref = oracle.pixel_stats(src)
+    st = oiio.ImageBufAlgo.computePixelStats(oiio.ImageBuf(src))
+    assert len(st.min) == nch
+    for c in range(nch):
+        r = ref[c]
+        assert st.min[c] == r["min"] and st.max[c] == r["max"], c
+        assert (st.nancount[c], st.infcount[c], st.finitecount[c]) == \
+            (r["nancount"], r["infcount"], r["finitecount"]), c
+        assert abs(st.sum[c] - r["sum"]) <= 1e-11 * max(1.0, abs(r["sum"])), c
+        assert abs(st.sum2[c] - r["sum2"]) <= 1e-11 * max(1.0, abs(r["sum2"])), c
+        assert abs(st.avg[c] - r["avg"]) <= 1e-6 * max(1.0, abs(r["avg"])), c
+        assert abs(st.stddev[c] - r["stddev"]) <= 1e-5 * max(1.0, abs(r["stddev"])), c
+    assert st.monochrome == oracle.is_monochrome(src)
+
+
+def test_pixel_stats_reference_kat_monochrome_constant_device(oiio, oracle):
+    """The reference's own known answer (imagebufalgo_test.cpp:1101-1123), the
+    monochrome / constant-colour answers, a device-resident image, a ROI."""
+    import torch
+    IBA = oiio.ImageBufAlgo
+    img = np.zeros((2, 2, 3), np.float32)
+    img[:, 1, :] = 1.0
+    st = IBA.computePixelStats(oiio.ImageBuf(img))
+    for c in range(3):
+        assert (st.min[c], st.max[c], st.avg[c], st.stddev[c]) == (0.0, 1.0, 0.5, 0.5)
+        assert (st.nancount[c], st.infcount[c], st.finitecount[c]) == (0, 0, 4)
+    assert st.monochrome and IBA.isConstantColor(oiio.ImageBuf(img)) is None
+    const = np.full((40, 50, 4), 0.25, np.float32)
+    assert IBA.isConstantColor(oiio.ImageBuf(const)) == [0.25] * 4
+    grey = synth.image(64, 48, 1, np.uint8, seed=3).repeat(3, axis=2)
+    assert IBA.isMonochrome(oiio.ImageBuf(grey))
+    grey[47, 63, 2] ^= 1
+    assert not IBA.isMonochrome(oiio.ImageBuf(grey))
+    f = synth.image(64, 48, 3, np.float32, seed=4)
+    f[..., 1] = f[..., 0] + np.float32(0.001)
+    f[..., 2] = f[..., 0]
+    assert not IBA.isMonochrome(oiio.ImageBuf(f))
+    assert IBA.isMonochrome(oiio.ImageBuf(f), 0.01) == oracle.is_monochrome(f, 0.01) == True
+    big = synth.image(1024, 512, 4, np.float32, seed=5)
+    t = torch.from_numpy(big).cuda()
+    st = IBA.computePixelStats(oiio.ImageBuf(t), roi=oiio.ROI(10, 700, 20, 500, 0, 1, 1, 3))
+    ref = oracle.pixel_stats(big[20:500, 10:700, 1:3].copy())
+    for k, c in enumerate((1, 2)):
+        assert st.min[c] == ref[k]["min"] and st.finitecount[c] == ref[k]["finitecount"]
+        assert abs(st.sum[c] - ref[k]["sum"]) <= 1e-11 * abs(ref[k]["sum"])
+    assert st.finitecount[0] == 0 and st.min[0] == 0.0      # channel outside the ROI
+
+
+def test_make_texture_reports_statistics(oiio, oracle):
+    src = synth.image(64, 32, 3, np.float32, seed=6)
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"maketx:nomipmap": 1})
+    ref = oracle.pixel_stats(src)
+    assert T.ok and T.constant_color is None and T.monochrome is False
+    assert all(abs(a - r["avg"]) < 1e-6 for a, r in zip(T.average_color, ref))
