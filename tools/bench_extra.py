@@ -4,6 +4,7 @@ chain (BASELINE config 4) and the other BASELINE configs' kernels.
 usage: bench_extra.py mip [size] [filter] [hicomp]
        bench_extra.py warp         rotate / resize:from-to / fit exact, 4K RGBA f32 and u8
        bench_extra.py conv         convolve / unsharp_mask / MIP chain with --sharpen
+       bench_extra.py maketx       pixel statistics, fixNonFinite, fillholes_pushpull
        bench_extra.py range        rangecompress / rangeexpand / highlightcomp resize, 8K RGBA f32"""
 import json
 import os
@@ -140,6 +141,36 @@ def conv_ops():
                           "ms": best}))
 
 
+def maketx_ops():
+    """The whole-image maketx stages either side of the MIP chain, 8K RGBA f32
+    device resident: one read of the image each (stats), read + write (fixnan)."""
+    import torch
+    import openimageio_b200 as oiio
+    IBA = oiio.ImageBufAlgo
+    w, h = 7680, 4320
+    g = torch.Generator(device="cuda").manual_seed(5)
+    src = torch.rand((h, w, 4), dtype=torch.float32, device="cuda", generator=g)
+    src[100, 100, 2] = float("nan")
+    S = oiio.ImageBuf(src)
+    nbytes = src.numel() * 4
+    ms = _time(lambda: IBA.computePixelStats(S))
+    print(json.dumps({"workload": "computePixelStats+isMonochrome 8K RGBA f32 (incl. host merge)",
+                      "ms": ms, "algorithmic_GBs": nbytes / ms / 1e6}))
+    dst = torch.empty_like(src)
+    D = oiio.ImageBuf(dst)
+    for mode, name in ((oiio.NONFINITE_BOX3, "box3"), (oiio.NONFINITE_NONE, "count only")):
+        ms = _time(lambda: IBA.fixNonFinite(D, S, mode))
+        print(json.dumps({"workload": "fixNonFinite %s 8K RGBA f32" % name, "ms": ms,
+                          "algorithmic_GBs": 2 * nbytes / ms / 1e6}))
+    hole = torch.rand((2160, 3840, 4), dtype=torch.float32, device="cuda", generator=g)
+    hole[..., 3] = (hole[..., 3] > 0.3).float()
+    hole[..., :3] *= hole[..., 3:4]
+    H, O = oiio.ImageBuf(hole), oiio.ImageBuf(torch.empty_like(hole))
+    ms = _time(lambda: IBA.fillholes_pushpull(O, H), steps=5)
+    print(json.dumps({"workload": "fillholes_pushpull 4K RGBA f32 (12 levels down + up)",
+                      "ms": ms}))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "mip":
         mip(int(sys.argv[2]) if len(sys.argv) > 2 else 16384,
@@ -151,3 +182,5 @@ if __name__ == "__main__":
         warp_ops()
     elif sys.argv[1] == "conv":
         conv_ops()
+    elif sys.argv[1] == "maketx":
+        maketx_ops()
