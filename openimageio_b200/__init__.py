@@ -25,7 +25,8 @@ __all__ = ["ROI", "ImageSpec", "ImageBuf", "ImageBufAlgo", "Filter2D",
            "source_rows", "resize_banded", "shard_frames"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libb2r.so")
+# B2R_LIBPATH: load another build of the same library (A/B kernel experiments)
+_LIBPATH = os.environ.get("B2R_LIBPATH") or os.path.join(_HERE, "libb2r.so")
 
 UINT8, UINT16, HALF, FLOAT = 2, 4, 10, 11
 _NAME2BT = {"uint8": UINT8, "uint16": UINT16, "half": HALF, "float": FLOAT}
