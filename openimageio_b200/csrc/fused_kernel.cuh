@@ -380,7 +380,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
 //   ringw  max_band_rows x VKP x 4               ring weights            "
 //   lastr  max_band_dy x 4                       completion rows         "
 template<int ST, int NCH, int VK, int HT>
-__global__ void __launch_bounds__(FUSED_THREADS, 3)
+__global__ void __launch_bounds__(FUSED_THREADS, fused_min_ctas(SrcTraits<ST>::es, VK))
 resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -458,12 +458,13 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         constexpr int VKP  = (VK + 3) & ~3;
         // FIFO geometry: thread t owns bytes [t*4*es, (t+1)*4*es) of every row
         // slot (dense, so 8- and 4-byte accesses stay bank-conflict free)
+        constexpr int NFIFO = fused_fifo_rows(es, VK);  // rows in flight per thread
         constexpr int TB   = 4 * es;             // bytes per thread per row
         constexpr int SLOT = FUSED_THREADS * TB;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
         unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HPAIRS * 8;
-        float* ringw = reinterpret_cast<float*>(fifo + FUSED_FIFO * SLOT);
+        float* ringw = reinterpret_cast<float*>(fifo + NFIFO * SLOT);
         int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
 
         // stage this band's ring weights and completion rows
@@ -526,7 +527,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                 raw = make_uint4(lds_u32(fifo_s + slot_cur), 0u, 0u, 0u);
             }
             slot_free = slot_cur;
-            slot_cur  = (slot_cur + SLOT) & (FUSED_FIFO * SLOT - 1);
+            slot_cur  = (slot_cur + SLOT) & (NFIFO * SLOT - 1);
             return raw;
         };
         // one source row: scatter it into the VK open destination rows
@@ -571,7 +572,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         if (async_ok) {
             if (!vfetch) {
 #pragma unroll
-                for (int q = 0; q < FUSED_FIFO; ++q)
+                for (int q = 0; q < NFIFO; ++q)
                     if (es == 4)
                         *reinterpret_cast<uint4*>(fifo + tid * TB + q * SLOT)
                             = make_uint4(0u, 0u, 0u, 0u);
@@ -582,12 +583,12 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
                         *reinterpret_cast<unsigned*>(fifo + tid * TB + q * SLOT) = 0u;
             }
 #pragma unroll
-            for (int q = 0; q < FUSED_FIFO; ++q) {
+            for (int q = 0; q < NFIFO; ++q) {
                 slot_free = q * SLOT;
                 issue_next();
             }
             finish_hb();
-            cp_async_wait<FUSED_FIFO - 1>();  // tables and first row landed
+            cp_async_wait<NFIFO - 1>();  // tables and first row landed
             uint4 rawA = fifo_pop(), rawB = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();  // ringw / lastr visible
             // Software pipeline: the row being accumulated was popped one
@@ -596,7 +597,7 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
             // steps per trip so the two register sets swap roles for free.
             auto step = [&](const uint4& cur, uint4& nxt) {
                 issue_next();
-                cp_async_wait<FUSED_FIFO - 1>();
+                cp_async_wait<NFIFO - 1>();
                 nxt = fifo_pop();
                 accumulate(cur, wrow);
                 wrow += VKP / 4;

@@ -313,7 +313,8 @@ fused_smem_bytes(const FusedParams& p, int max_band_rows, int max_band_dy,
     if (p.vk > 0) {
         f += (size_t)max_band_rows * ((p.vk + 3) & ~3);
         f += (size_t)((max_band_dy + 3) & ~3);
-        f += (size_t)FUSED_FIFO * FUSED_THREADS * basetype_size(p.srctype);  // 4*es bytes per thread
+        f += (size_t)fused_fifo_rows(basetype_size(p.srctype), p.vk) * FUSED_THREADS
+             * basetype_size(p.srctype);  // 4*es bytes per thread
     }
     return f * sizeof(float);
 }

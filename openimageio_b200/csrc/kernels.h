@@ -118,13 +118,24 @@ fused_batch(int vk)
     return vk == 6 ? 12 : 8;
 }
 constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
-
-// Expand variant (upsizing in y: the V pass gathers): strips are up to
-// EXPAND_GROUPS groups of four dst columns wide, a group per H-pass thread.
-constexpr int EXPAND_GROUPS = 256;
-constexpr int EXPAND_BATCH  = 8;    // V-filtered rows between the passes
-constexpr int EXPAND_MAXVT  = 8;    // widest V window (rows held in registers)
-constexpr int EXPAND_FIFO   = 4;    // raw source rows in flight per thread
+#if defined(__CUDACC__)
+#    define B2R_HD __host__ __device__
+#else
+#    define B2R_HD
+#endif
+// Per (element size, ring size): rows in flight per thread and resident CTAs
+// the kernel is compiled for.  Measured on C2 (half, VK = 4, 100.0 us): 4 rows
+// with 4 CTAs/SM 104.0 us, 16 rows 105.1 us -- 8 rows / 3 CTAs stays.
+B2R_HD constexpr int
+fused_fifo_rows(int es, int vk)
+{
+    return (void)es, (void)vk, FUSED_FIFO;
+}
+B2R_HD constexpr int
+fused_min_ctas(int es, int vk)
+{
+    return (void)es, (void)vk, 3;
+}
 
 struct FusedParams {
     const unsigned char* src;  // data-window origin, pixels contiguous in x
