@@ -137,6 +137,13 @@ fused_min_ctas(int es, int vk)
     return (void)es, (void)vk, 3;
 }
 
+// Expand variant (upsizing in y: the V pass gathers): strips are up to
+// EXPAND_GROUPS groups of four dst columns wide, a group per H-pass thread.
+constexpr int EXPAND_GROUPS = 256;
+constexpr int EXPAND_BATCH  = 8;    // V-filtered rows between the passes
+constexpr int EXPAND_MAXVT  = 8;    // widest V window (rows held in registers)
+constexpr int EXPAND_FIFO   = 4;    // raw source rows in flight per thread
+
 struct FusedParams {
     const unsigned char* src;  // data-window origin, pixels contiguous in x
     long long src_ystride;
