@@ -366,6 +366,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms_max = float(t.item())
 
+    # the same from PAGEABLE host memory (what an ImageBuf normally owns): the
+    # library stages it through pinned bounce rings with a few host threads
+    page_ms = None
+    if world == 1:
+        Sp = oiio.ImageBuf(src_np)
+        Dp = oiio.ImageBuf(np.zeros((dh, dw, c), np.dtype(ddt)))
+        for _ in range(2):
+            IBA.resize(Dp, Sp, filtername=filt, device=local_rank)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            IBA.resize(Dp, Sp, filtername=filt, device=local_rank)
+        page_ms = (time.perf_counter() - t0) * 1e3 / 3
+
     # parity spot check of what was just timed (device result == host result)
     same = bool(torch.equal(dst_dev.cpu().view(torch.uint8),
                             dst_host.view(torch.uint8))) if rank == 0 else True
@@ -398,7 +411,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mpixel/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max, "steps": e2e_steps,
-                    "host_memory": "pinned"},
+                    "host_memory": "pinned",
+                    "pageable_value": (mpix_frame / (page_ms * 1e-3)
+                                       if page_ms else None),
+                    "pageable_ms_per_frame": page_ms},
             "gpu_launches": args.steps * nfr * (2 if src_is_fp else 1),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
