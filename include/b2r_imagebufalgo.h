@@ -624,5 +624,207 @@ fit(const ImageBuf& src, const KWArgs& options = {}, ROI roi = {}, int nthreads 
     return result;
 }
 
+
+// ---------------------------------------------------------------------------
+// The widened rows: st_warp, make_kernel / convolve /
+// unsharp_mask, fixNonFinite, computePixelStats / isMonochrome,
+// fillholes_pushpull -- same names and argument order as imagebufalgo.h.
+// ---------------------------------------------------------------------------
+namespace detail {
+inline bool
+report(ImageBuf& dst, int rc, const char* err)
+{
+    if (rc) {
+        dst.error(err);
+        return false;
+    }
+    return true;
+}
+inline b2r_roi
+c_roi(const ROI& r)
+{
+    return b2r_roi { r.xbegin, r.xend, r.ybegin, r.yend, r.chbegin, r.chend };
+}
+}  // namespace detail
+
+/// ImageBufAlgo::st_warp(dst, src, stbuf, filtername, filterwidth, chan_s,
+/// chan_t, flip_s, flip_t, roi, nthreads) -- imagebufalgo_xform.cpp:2010-2025.
+inline bool
+st_warp(ImageBuf& dst, const ImageBuf& src, const ImageBuf& stbuf,
+        const std::string& filtername = "", float filterwidth = 0.0f, int chan_s = 0,
+        int chan_t = 1, bool flip_s = false, bool flip_t = false, ROI roi = {},
+        int /*nthreads*/ = 0)
+{
+    if (!stbuf.initialized()) {
+        dst.error("ImageBufAlgo::st_warp : Uninitialized ST buffer");
+        return false;
+    }
+    if (!detail::prep(roi, dst, src))
+        return false;
+    roi.chend = std::min(roi.chend, std::min(dst.nchannels(), src.nchannels()));
+    b2r_image d = dst.c_image(), s = src.c_image(), t = stbuf.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    char err[512] = "";
+    int rc = b2r_st_warp(&d, &s, &t, filtername.c_str(), filterwidth, chan_s, chan_t, flip_s,
+                         flip_t, &r, nullptr, nullptr, err, sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
+/// ImageBufAlgo::make_kernel(name, width, height, depth, normalize) --
+/// imagebufalgo.cpp:864-957: 1-channel float image centred on the origin; an
+/// unknown name yields a box with the error set.
+inline ImageBuf
+make_kernel(const std::string& name, float width, float height, float /*depth*/ = 1.0f,
+            bool normalize = true)
+{
+    int kw = 0, kh = 0;
+    char err[512] = "";
+    b2r_make_kernel(name.c_str(), width, height, normalize, nullptr, &kw, &kh, err, sizeof(err));
+    ImageSpec spec(kw, kh, 1, TypeDesc::FLOAT);
+    spec.x = spec.full_x = -kw / 2;
+    spec.y = spec.full_y = -kh / 2;
+    ImageBuf K(spec);
+    int rc = b2r_make_kernel(name.c_str(), width, height, normalize, (float*)K.localpixels(),
+                             &kw, &kh, err, sizeof(err));
+    if (rc)
+        K.error(err);
+    return K;
+}
+
+/// ImageBufAlgo::convolve(dst, src, kernel, normalize, roi, nthreads) --
+/// imagebufalgo.cpp:817-838.
+inline bool
+convolve(ImageBuf& dst, const ImageBuf& src, const ImageBuf& kernel, bool normalize = true,
+         ROI roi = {}, int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    if (dst.nchannels() != src.nchannels()) {
+        dst.error("images must have the same number of channels");
+        return false;
+    }
+    roi.chend = std::min(roi.chend, dst.nchannels());
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    char err[512] = "";
+    int rc = b2r_convolve(&d, &s, (const float*)kernel.localpixels(), kernel.spec().width,
+                          kernel.spec().height, normalize, &r, nullptr, nullptr, err,
+                          sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
+/// ImageBufAlgo::unsharp_mask(dst, src, kernel, width, contrast, threshold,
+/// roi, nthreads) -- imagebufalgo.cpp:975-1031.
+inline bool
+unsharp_mask(ImageBuf& dst, const ImageBuf& src, const std::string& kernel = "gaussian",
+             float width = 3.0f, float contrast = 1.0f, float threshold = 0.0f, ROI roi = {},
+             int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    if (dst.nchannels() != src.nchannels()) {
+        dst.error("images must have the same number of channels");
+        return false;
+    }
+    roi.chend = std::min(roi.chend, dst.nchannels());
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    char err[512] = "";
+    int rc = b2r_unsharp_mask(&d, &s, kernel.c_str(), width, contrast, threshold, &r, nullptr,
+                              nullptr, err, sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
+/// ImageBufAlgo::NonFiniteFixMode and fixNonFinite(dst, src, mode,
+/// pixelsFixed, roi, nthreads) -- imagebufalgo_pixelmath.cpp:1562-1610.
+enum NonFiniteFixMode {
+    NONFINITE_NONE  = 0,
+    NONFINITE_BLACK = 1,
+    NONFINITE_BOX3  = 2,
+    NONFINITE_ERROR = 100,
+};
+inline bool
+fixNonFinite(ImageBuf& dst, const ImageBuf& src, NonFiniteFixMode mode = NONFINITE_BOX3,
+             int* pixelsFixed = nullptr, ROI roi = {}, int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    roi.chend = std::min(roi.chend, std::min(dst.nchannels(), src.nchannels()));
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    char err[512] = "";
+    int rc = b2r_fix_nonfinite(&d, &s, int(mode), pixelsFixed, &r, nullptr, nullptr, err,
+                               sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
+/// ImageBufAlgo::PixelStats / computePixelStats(src, roi, nthreads) --
+/// imagebufalgo_compare.cpp:187-208; isMonochrome -- :579-600.
+struct PixelStats {
+    std::vector<float> min, max, avg, stddev;
+    std::vector<long long> nancount, infcount, finitecount;
+    std::vector<double> sum, sum2;
+};
+inline PixelStats
+computePixelStats(const ImageBuf& src, ROI roi = {}, int /*nthreads*/ = 0,
+                  bool* monochrome = nullptr, float mono_threshold = 0.0f)
+{
+    PixelStats st;
+    if (!src.initialized())
+        return st;
+    const int n = src.nchannels();
+    std::vector<b2r_pixel_stats_t> recs((size_t)n);
+    b2r_image s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    if (roi.defined())
+        r.chend = std::min(r.chend, n);
+    int mono      = 1;
+    char err[512] = "";
+    if (b2r_pixel_stats(&s, roi.defined() ? &r : nullptr, recs.data(), n, &mono,
+                        mono_threshold, nullptr, err, sizeof(err))) {
+        src.error(err);
+        return st;
+    }
+    for (const auto& q : recs) {
+        st.min.push_back(q.min), st.max.push_back(q.max), st.avg.push_back(q.avg);
+        st.stddev.push_back(q.stddev);
+        st.nancount.push_back(q.nancount), st.infcount.push_back(q.infcount);
+        st.finitecount.push_back(q.finitecount);
+        st.sum.push_back(q.sum), st.sum2.push_back(q.sum2);
+    }
+    if (monochrome)
+        *monochrome = mono != 0;
+    return st;
+}
+inline bool
+isMonochrome(const ImageBuf& src, float threshold = 0.0f, ROI roi = {}, int nthreads = 0)
+{
+    bool mono = false;
+    computePixelStats(src, roi, nthreads, &mono, threshold);
+    return mono;
+}
+
+/// ImageBufAlgo::fillholes_pushpull(dst, src, roi, nthreads) --
+/// imagebufalgo.cpp:1600-1670.
+inline bool
+fillholes_pushpull(ImageBuf& dst, const ImageBuf& src, ROI roi = {}, int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    if (dst.nchannels() != src.nchannels()) {
+        dst.error("images must have the same number of channels");
+        return false;
+    }
+    if (src.spec().alpha_channel < 0 || dst.spec().alpha_channel < 0) {
+        dst.error("images must have alpha channels");
+        return false;
+    }
+    b2r_image d = dst.c_image(), s = src.c_image();
+    char err[512] = "";
+    int rc = b2r_fillholes_pushpull(&d, &s, src.spec().alpha_channel, nullptr, nullptr, err,
+                                    sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
 }  // namespace ImageBufAlgo
 }  // namespace b2r

@@ -4,7 +4,7 @@
 //   ImageBufAlgo::resize(dst, src, {{"filtername", f}}, roi);
 // usage: iba_cli errors
 //        iba_cli resize in.raw w h nch basetype dw dh filter out.raw
-//        iba_cli rotate | fitexact  (same arguments)
+//        iba_cli rotate | fitexact | sharpen  (same arguments)
 //        iba_cli hicomp in.raw w h nch basetype dw dh filter out.raw
 //            (oiiotool --resize:highlightcomp=1 spelled with three IBA calls)
 #include "b2r_imagebufalgo.h"
@@ -50,7 +50,9 @@ main(int argc, char** argv)
     const bool hicomp = argc >= 2 && std::string(argv[1]) == "hicomp";
     const bool rotate = argc >= 2 && std::string(argv[1]) == "rotate";
     const bool fitx   = argc >= 2 && std::string(argv[1]) == "fitexact";
-    if (argc != 11 || (std::string(argv[1]) != "resize" && !hicomp && !rotate && !fitx)) {
+    const bool sharp  = argc >= 2 && std::string(argv[1]) == "sharpen";
+    if (argc != 11
+        || (std::string(argv[1]) != "resize" && !hicomp && !rotate && !fitx && !sharp)) {
         fprintf(stderr, "usage: see source\n");
         return 2;
     }
@@ -73,6 +75,24 @@ main(int argc, char** argv)
     ImageBuf dst;
     if (rotate) {  // 30 degrees about the display-window centre, dst = src's window
         dst = ImageBufAlgo::rotate(src, 30.0f * float(M_PI / 180.0), argv[9]);
+        dw = w, dh = h;
+    } else if (sharp) {
+        // fixNonFinite -> unsharp_mask -> convolve with a 3x3 box, plus the
+        // statistics of the result on stderr: the widened C++ surface
+        ImageBuf fixed, sharpened;
+        int nfixed = 0;
+        if (!ImageBufAlgo::fixNonFinite(fixed, src, ImageBufAlgo::NONFINITE_BOX3, &nfixed)
+            || !ImageBufAlgo::unsharp_mask(sharpened, fixed, "gaussian", 3.0f, 0.7f, 0.0f)) {
+            fprintf(stderr, "%s%s\n", fixed.geterror().c_str(), sharpened.geterror().c_str());
+            return 7;
+        }
+        ImageBuf K = ImageBufAlgo::make_kernel(argv[9], 3.0f, 3.0f);
+        if (!ImageBufAlgo::convolve(dst, sharpened, K))
+            return 8;
+        bool mono = true;
+        ImageBufAlgo::PixelStats st = ImageBufAlgo::computePixelStats(dst, {}, 0, &mono);
+        fprintf(stderr, "fixed=%d avg0=%.9g finite0=%lld mono=%d\n", nfixed, st.avg[0],
+                st.finitecount[0], int(mono));
         dw = w, dh = h;
     } else if (fitx) {
         dst = ImageBufAlgo::fit(src, { { "exact", 1 }, { "filtername", argv[9] } },

@@ -91,3 +91,29 @@ def test_cpp_rotate_and_fit_exact_match_oracle(iba_cli, oracle, tmp_path):
     oracle.warp(oracle.Img(ref), oracle.Img(src), Mx, "lanczos3", 6.0, 6.0, wrap="black",
                 edgeclamp=True)
     assert np.abs(got - ref).max() <= 1e-5
+
+
+@pytest.mark.gpu
+def test_cpp_widened_surface(iba_cli, oracle, tmp_path):
+    """fixNonFinite -> unsharp_mask -> convolve -> computePixelStats written
+    against the C++ mirror, checked bit for bit against the oracle chain."""
+    src = synth.image(90, 70, 3, np.float32, seed=94)
+    src[10, 20, 1] = np.nan
+    src[40, 50, 2] = np.inf
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    src.tofile(fin)
+    p = subprocess.run([iba_cli, "sharpen", fin, "90", "70", "3", "11", "90", "70", "box",
+                        fout], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    got = np.fromfile(fout, np.float32).reshape(70, 90, 3)
+    a = np.zeros_like(src)
+    assert oracle.fix_nonfinite(oracle.Img(a), oracle.Img(src), "box3") == 2
+    b = np.zeros_like(src)
+    oracle.unsharp_mask(oracle.Img(b), oracle.Img(a), "gaussian", 3.0, 0.7, 0.0)
+    K, _ = oracle.make_kernel("box", 3, 3)
+    ref = np.zeros_like(src)
+    oracle.convolve(oracle.Img(ref), oracle.Img(b), K)
+    assert np.array_equal(got, ref)
+    st = oracle.pixel_stats(ref)
+    assert "fixed=2" in p.stderr and "finite0=%d" % st[0]["finitecount"] in p.stderr
+    assert "mono=0" in p.stderr
