@@ -2968,6 +2968,10 @@ struct StencilIO {
         return B2R_OK;
     }
 
+    // true when dst and src share device pixels even though the caller's host
+    // pointers differ (never: each host image gets its own staging buffer)
+    bool dst_alloc_is_src() const { return ddst == dsrc; }
+
     // a further input image (st_warp's ST buffer): whole data window up
     void* extra_alloc = nullptr;
     int stage_extra(const b2r_image& im, b2r_image* imd, void** dpix, b2r_report* report,
@@ -3149,6 +3153,34 @@ b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src, const char* kernel,
         io.release();
         return code;
     };
+    rc = upload_floats(K.v.data(), K.v.size(), io.stream, &dk, err, errlen);
+    if (rc)
+        return fail(rc);
+    b2r_roi croi  = io.roi;  // convolve runs over every channel (:1004-1019 pass roi as is)
+    const float s = kernel_scale(K.v.data(), K.w * K.h, true);
+    int launched  = 0;
+    if (!two_pass && !io.same_pixels && !io.dst_alloc_is_src()) {
+        // one 2-D pass and distinct images: blur and combine in ONE kernel,
+        // the blur image never exists (same arithmetic, same result)
+        ConvParams cp;
+        memset(&cp, 0, sizeof(cp));
+        cp.dst       = to_dev(io.dstd, io.ddst);
+        cp.src       = to_dev(S, io.dsrc);
+        cp.roi_x0    = io.roi.xbegin, cp.roi_x1 = io.roi.xend;
+        cp.roi_y0    = io.roi.ybegin, cp.roi_y1 = io.roi.yend;
+        cp.chbegin   = io.roi.chbegin;
+        cp.chend     = io.roi.chend;
+        cp.kernel    = dk;
+        cp.kw        = K.w;
+        cp.kh        = K.h;
+        cp.scale     = s;
+        cp.unsharp   = 1;
+        cp.contrast  = contrast;
+        cp.threshold = threshold;
+        launch_convolve(cp, io.stream);
+        cudaFreeAsync(dk, io.stream);
+        return io.end(*dst, report, 1, err, errlen);
+    }
     if (cudaMallocAsync(&blur, bsize, io.stream) != cudaSuccess
         || cudaMemsetAsync(blur, 0, bsize, io.stream) != cudaSuccess) {
         set_err(err, errlen, "CUDA error allocating the blur image");
@@ -3160,12 +3192,6 @@ b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src, const char* kernel,
     B.xstride   = (int64_t)S.nchannels * 4;
     B.ystride   = (int64_t)brow;
     B.memspace  = B2R_MEM_DEVICE;
-    rc          = upload_floats(K.v.data(), K.v.size(), io.stream, &dk, err, errlen);
-    if (rc)
-        return fail(rc);
-    b2r_roi croi  = io.roi;  // convolve runs over every channel (:1004-1019 pass roi as is)
-    const float s = kernel_scale(K.v.data(), K.w * K.h, true);
-    int launched  = 0;
     if (two_pass) {
         if (cudaMallocAsync(&first, bsize, io.stream) != cudaSuccess
             || cudaMemsetAsync(first, 0, bsize, io.stream) != cudaSuccess) {

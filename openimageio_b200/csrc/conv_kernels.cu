@@ -120,6 +120,29 @@ convolve_kernel(const ConvParams p)
                     }
                 }
             }
+            if (p.unsharp) {
+                // unsharp_impl fused behind the blur (:961-985): the blurred
+                // value is what convolve would have stored in the float
+                // `Blurry` image, so the result is the same to the bit
+                const bool in = x >= S.x && x < S.x + S.width && y >= S.y && y < S.y + S.height;
+                const unsigned char* cp = (const unsigned char*)S.pixels
+                                          + (long long)(y - S.y) * S.ystride
+                                          + (long long)(x - S.x) * S.xstride;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int ch = c0 + c;
+                    if (ch >= p.chbegin && ch < p.chend) {
+                        const float sv   = in ? load_elem(cp + ch * ses, S.basetype) : 0.0f;
+                        const float b    = in ? __fmul_rn(p.scale, sum[c]) : 0.0f;
+                        const float diff = __fsub_rn(sv, b);
+                        float v          = sv;
+                        if (fabsf(diff) > p.threshold)
+                            v = __fadd_rn(sv, __fmul_rn(p.contrast, diff));
+                        store_elem(dp + ch * des, p.dst.basetype, v);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int ch = c0 + c;

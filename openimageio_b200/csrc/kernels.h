@@ -277,6 +277,10 @@ struct ConvParams {
     const float* kernel;  // device, kh rows of kw; window origin (-kw/2, -kh/2)
     int kw, kh;
     float scale;          // 1 / sum(kernel) when normalising, else 1
+    // unsharp != 0: store src + contrast * (src - blur) where |src - blur| >
+    // threshold instead of the blur (unsharp_mask in one pass, no blur image)
+    int unsharp;
+    float contrast, threshold;
 };
 void
 launch_convolve(const ConvParams& p, void* stream);
