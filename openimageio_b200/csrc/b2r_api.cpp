@@ -930,10 +930,17 @@ parallel_copy_rows(unsigned char* d, size_t dpitch, const unsigned char* s, size
         return;
     }
     std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    for (int t = 1; t < nt; ++t)
-        th.emplace_back(work, t);
+    int started = 1;  // part 0 runs on this thread
+    try {
+        th.reserve(nt - 1);
+        for (; started < nt; ++started)
+            th.emplace_back(work, started);
+    } catch (...) {
+        // no more threads to be had: this thread does the parts not handed out
+    }
     work(0);
+    for (int t = started; t < nt; ++t)
+        work(t);
     for (auto& x : th)
         x.join();
 }
