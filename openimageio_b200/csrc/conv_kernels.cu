@@ -20,8 +20,126 @@ namespace {
 
 constexpr int CONV_BX = 32, CONV_BY = 8;
 
-// KW, KH > 0: compile-time kernel extent (taps fully unrolled, weights in
-// registers); 0: run-time extent.
+// One source pixel's (up to) four channels as float.
+template<bool VEC_F32>
+__device__ __forceinline__ void
+conv_load(const unsigned char* sp, const DevImage& S, int c0, int ses, float v[4])
+{
+    if (VEC_F32) {
+        const float4 q = __ldg((const float4*)sp);
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            v[c] = (c0 + c < S.nchannels) ? load_elem(sp + c * ses, S.basetype) : 0.0f;
+    }
+}
+
+// Store one output pixel's channel pass: the blur itself, or -- unsharp -- the
+// combine step fused behind it (unsharp_impl, :961-985: the blurred value is
+// what convolve would have stored in the float `Blurry` image, so the result
+// is the same to the bit).
+__device__ __forceinline__ void
+conv_store(const ConvParams& p, int x, int y, int c0, int ses, int des, const float (&sum)[4])
+{
+    unsigned char* dp = (unsigned char*)p.dst.pixels + (long long)(y - p.dst.y) * p.dst.ystride
+                        + (long long)(x - p.dst.x) * p.dst.xstride;
+    const DevImage& S = p.src;
+    if (p.unsharp) {
+        const bool in = x >= S.x && x < S.x + S.width && y >= S.y && y < S.y + S.height;
+        const unsigned char* cp = (const unsigned char*)S.pixels
+                                  + (long long)(y - S.y) * S.ystride
+                                  + (long long)(x - S.x) * S.xstride;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ch = c0 + c;
+            if (ch >= p.chbegin && ch < p.chend) {
+                const float sv   = in ? load_elem(cp + ch * ses, S.basetype) : 0.0f;
+                const float b    = in ? __fmul_rn(p.scale, sum[c]) : 0.0f;
+                const float diff = __fsub_rn(sv, b);
+                float v          = sv;
+                if (fabsf(diff) > p.threshold)
+                    v = __fadd_rn(sv, __fmul_rn(p.contrast, diff));
+                store_elem(dp + ch * des, p.dst.basetype, v);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int ch = c0 + c;
+        if (ch >= p.chbegin && ch < p.chend)
+            store_elem(dp + ch * des, p.dst.basetype, __fmul_rn(p.scale, sum[c]));
+    }
+}
+
+// One output pixel, any position: taps in the reference's order, WrapClamp.
+template<bool VEC_F32>
+__device__ __forceinline__ void
+conv_pixel_generic(const ConvParams& p, int x, int y, int c0, int kw, int kh, int ses,
+                   float (&sum)[4])
+{
+    const DevImage& S = p.src;
+    const int kx0 = -(kw / 2), ky0 = -(kh / 2);
+    const int fx0 = S.full_x, fx1 = S.full_x + S.full_width - 1;
+    const int fy0 = S.full_y, fy1 = S.full_y + S.full_height - 1;
+    const bool interior = x + kx0 >= S.x && x + kx0 + kw <= S.x + S.width && y + ky0 >= S.y
+                          && y + ky0 + kh <= S.y + S.height;
+    const float* k = p.kernel;
+    if (interior) {
+        const unsigned char* rowp = (const unsigned char*)S.pixels
+                                    + (long long)(y + ky0 - S.y) * S.ystride
+                                    + (long long)(x + kx0 - S.x) * S.xstride + c0 * ses;
+#pragma unroll 1
+        for (int j = 0; j < kh; ++j, rowp += S.ystride) {
+            const unsigned char* sp = rowp;
+#pragma unroll 1
+            for (int i = 0; i < kw; ++i, sp += S.xstride) {
+                const float w = __ldg(k++);
+                float v[4];
+                conv_load<VEC_F32>(sp, S, c0, ses, v);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int j = 0; j < kh; ++j) {
+        const int ty = y + ky0 + j;
+#pragma unroll 1
+        for (int i = 0; i < kw; ++i, ++k) {
+            const float w = __ldg(k);
+            int px = x + kx0 + i, py = ty;
+            bool ok = px >= S.x && px < S.x + S.width && py >= S.y && py < S.y + S.height;
+            if (!ok) {
+                px = min(max(px, fx0), fx1);
+                py = min(max(py, fy0), fy1);
+                ok = px >= S.x && px < S.x + S.width && py >= S.y && py < S.y + S.height;
+            }
+            float v[4] = { 0.f, 0.f, 0.f, 0.f };
+            if (ok)
+                conv_load<VEC_F32>((const unsigned char*)S.pixels
+                                       + (long long)(py - S.y) * S.ystride
+                                       + (long long)(px - S.x) * S.xstride + c0 * ses,
+                                   S, c0, ses, v);
+            // a black tap still adds k * 0 (sign of zero aside: no effect)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+        }
+    }
+}
+
+// KW, KH > 0: compile-time kernel extent -- taps fully unrolled, weights in
+// registers, and CONV_RPT vertically adjacent output pixels per thread so that
+// each source pixel of the (KH + RPT - 1) x KW window is loaded once and feeds
+// every output it belongs to (each output still receives its taps in the
+// reference's order: rows ascending, columns ascending).  0: run-time extent,
+// one output per thread.
+constexpr int CONV_RPT = 4;
+
 template<bool VEC_F32, int KW, int KH>
 __global__ void __launch_bounds__(CONV_BX* CONV_BY)
 convolve_kernel(const ConvParams p)
@@ -33,121 +151,67 @@ convolve_kernel(const ConvParams p)
     const DevImage& S = p.src;
     const int ses = S.basetype == BT_UINT8 ? 1 : (S.basetype == BT_FLOAT ? 4 : 2);
     const int des = p.dst.basetype == BT_UINT8 ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
-    const int kw = KW > 0 ? KW : p.kw, kh = KH > 0 ? KH : p.kh;
-    const int kx0 = -(kw / 2), ky0 = -(kh / 2);
-    const int fx0 = S.full_x, fx1 = S.full_x + S.full_width - 1;
-    const int fy0 = S.full_y, fy1 = S.full_y + S.full_height - 1;
-    float wreg[KW > 0 ? KW * KH : 1];
-    if (KW > 0) {
+    constexpr int RPT = KW > 0 ? CONV_RPT : 1;
+    if constexpr (KW > 0) {
+        float wreg[KW > 0 ? KW * KH : 1];
 #pragma unroll
-        for (int i = 0; i < KW * KH; ++i)
+        for (int i = 0; i < (KW > 0 ? KW * KH : 1); ++i)
             wreg[i] = __ldg(p.kernel + i);
-    }
-    const bool x_inside = x + kx0 >= S.x && x + kx0 + kw <= S.x + S.width;
-    for (int y = p.roi_y0 + blockIdx.y * CONV_BY + threadIdx.y; y < p.roi_y1;
-         y += gridDim.y * CONV_BY) {
-        unsigned char* dp = (unsigned char*)p.dst.pixels
-                            + (long long)(y - p.dst.y) * p.dst.ystride
-                            + (long long)(x - p.dst.x) * p.dst.xstride;
-        // the whole stencil inside the data window: no wrap tests
-        const bool interior = x_inside && y + ky0 >= S.y && y + ky0 + kh <= S.y + S.height;
-        for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
-            float sum[4] = { 0.f, 0.f, 0.f, 0.f };
-            if (interior) {
-                const unsigned char* rowp = (const unsigned char*)S.pixels
-                                            + (long long)(y + ky0 - S.y) * S.ystride
-                                            + (long long)(x + kx0 - S.x) * S.xstride
-                                            + c0 * ses;
-                const float* k = p.kernel;
-#pragma unroll(KH > 0 ? KH : 1)
-                for (int j = 0; j < kh; ++j, rowp += S.ystride) {
-                    const unsigned char* sp = rowp;
-#pragma unroll(KW > 0 ? KW : 1)
-                    for (int i = 0; i < kw; ++i, sp += S.xstride) {
-                        const float w = KW > 0 ? wreg[KW > 0 ? j * KW + i : 0] : __ldg(k++);
-                        float v[4] = { 0.f, 0.f, 0.f, 0.f };
-                        if (VEC_F32) {
-                            const float4 q = __ldg((const float4*)sp);
-                            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
-                        } else {
+        const int kx0 = -(KW / 2), ky0 = -(KH / 2);
+        const bool x_inside = x + kx0 >= S.x && x + kx0 + KW <= S.x + S.width;
+        for (int y0 = p.roi_y0 + (blockIdx.y * CONV_BY + threadIdx.y) * RPT; y0 < p.roi_y1;
+             y0 += gridDim.y * CONV_BY * RPT) {
+            const int nr = min(RPT, p.roi_y1 - y0);
+            const bool interior = x_inside && nr == RPT && y0 + ky0 >= S.y
+                                  && y0 + RPT - 1 + ky0 + KH <= S.y + S.height;
+            for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
+                if (interior) {
+                    float sum[RPT][4];
 #pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (c0 + c < S.nchannels)
-                                    v[c] = load_elem(sp + c * ses, S.basetype);
-                        }
+                    for (int r = 0; r < RPT; ++r)
+                        sum[r][0] = sum[r][1] = sum[r][2] = sum[r][3] = 0.0f;
+                    const unsigned char* rowp = (const unsigned char*)S.pixels
+                                                + (long long)(y0 + ky0 - S.y) * S.ystride
+                                                + (long long)(x + kx0 - S.x) * S.xstride
+                                                + c0 * ses;
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
-                    }
-                }
-            } else {
-                const float* k = p.kernel;
-#pragma unroll 1
-                for (int j = 0; j < kh; ++j) {
-                    const int ty = y + ky0 + j;
-#pragma unroll 1
-                    for (int i = 0; i < kw; ++i, ++k) {
-                        const float w = __ldg(k);
-                        int px = x + kx0 + i, py = ty;
-                        bool ok = px >= S.x && px < S.x + S.width && py >= S.y
-                                  && py < S.y + S.height;
-                        if (!ok) {
-                            px = min(max(px, fx0), fx1);
-                            py = min(max(py, fy0), fy1);
-                            ok = px >= S.x && px < S.x + S.width && py >= S.y
-                                 && py < S.y + S.height;
-                        }
-                        float v[4] = { 0.f, 0.f, 0.f, 0.f };
-                        if (ok) {
-                            const unsigned char* sp = (const unsigned char*)S.pixels
-                                                      + (long long)(py - S.y) * S.ystride
-                                                      + (long long)(px - S.x) * S.xstride
-                                                      + c0 * ses;
-                            if (VEC_F32) {
-                                const float4 q = __ldg((const float4*)sp);
-                                v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
-                            } else {
+                    for (int j = 0; j < (KW > 0 ? KH + RPT - 1 : 1); ++j, rowp += S.ystride) {
+                        const unsigned char* sp = rowp;
 #pragma unroll
-                                for (int c = 0; c < 4; ++c)
-                                    if (c0 + c < S.nchannels)
-                                        v[c] = load_elem(sp + c * ses, S.basetype);
+                        for (int i = 0; i < (KW > 0 ? KW : 1); ++i, sp += S.xstride) {
+                            float v[4];
+                            conv_load<VEC_F32>(sp, S, c0, ses, v);
+#pragma unroll
+                            for (int r = 0; r < RPT; ++r) {
+                                const int jj = j - r;  // this row's tap row for output r
+                                if (jj >= 0 && jj < KH) {
+                                    const float w = wreg[KW > 0 ? jj * KW + i : 0];
+#pragma unroll
+                                    for (int c = 0; c < 4; ++c)
+                                        sum[r][c] = __fadd_rn(sum[r][c], __fmul_rn(w, v[c]));
+                                }
                             }
                         }
-                        // a black tap still adds k * 0 (sign of zero aside: no effect)
+                    }
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                    for (int r = 0; r < RPT; ++r)
+                        conv_store(p, x, y0 + r, c0, ses, des, sum[r]);
+                } else {
+                    for (int r = 0; r < nr; ++r) {
+                        float sum[4] = { 0.f, 0.f, 0.f, 0.f };
+                        conv_pixel_generic<VEC_F32>(p, x, y0 + r, c0, KW, KH, ses, sum);
+                        conv_store(p, x, y0 + r, c0, ses, des, sum);
                     }
                 }
             }
-            if (p.unsharp) {
-                // unsharp_impl fused behind the blur (:961-985): the blurred
-                // value is what convolve would have stored in the float
-                // `Blurry` image, so the result is the same to the bit
-                const bool in = x >= S.x && x < S.x + S.width && y >= S.y && y < S.y + S.height;
-                const unsigned char* cp = (const unsigned char*)S.pixels
-                                          + (long long)(y - S.y) * S.ystride
-                                          + (long long)(x - S.x) * S.xstride;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int ch = c0 + c;
-                    if (ch >= p.chbegin && ch < p.chend) {
-                        const float sv   = in ? load_elem(cp + ch * ses, S.basetype) : 0.0f;
-                        const float b    = in ? __fmul_rn(p.scale, sum[c]) : 0.0f;
-                        const float diff = __fsub_rn(sv, b);
-                        float v          = sv;
-                        if (fabsf(diff) > p.threshold)
-                            v = __fadd_rn(sv, __fmul_rn(p.contrast, diff));
-                        store_elem(dp + ch * des, p.dst.basetype, v);
-                    }
-                }
-                continue;
-            }
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int ch = c0 + c;
-                if (ch >= p.chbegin && ch < p.chend)
-                    store_elem(dp + ch * des, p.dst.basetype, __fmul_rn(p.scale, sum[c]));
+        }
+    } else {
+        for (int y = p.roi_y0 + blockIdx.y * CONV_BY + threadIdx.y; y < p.roi_y1;
+             y += gridDim.y * CONV_BY) {
+            for (int c0 = p.chbegin & ~3; c0 < p.chend; c0 += 4) {
+                float sum[4] = { 0.f, 0.f, 0.f, 0.f };
+                conv_pixel_generic<VEC_F32>(p, x, y, c0, p.kw, p.kh, ses, sum);
+                conv_store(p, x, y, c0, ses, des, sum);
             }
         }
     }
@@ -195,18 +259,22 @@ launch_convolve(const ConvParams& p, void* stream)
     const int w = p.roi_x1 - p.roi_x0, h = p.roi_y1 - p.roi_y0;
     if (w <= 0 || h <= 0)
         return;
-    dim3 grid((w + CONV_BX - 1) / CONV_BX, std::min((h + CONV_BY - 1) / CONV_BY, 32768), 1);
     const bool vec = p.src.basetype == BT_FLOAT && p.src.nchannels == 4 && p.src.xstride == 16
                      && (uintptr_t)p.src.pixels % 16 == 0 && p.src.ystride % 16 == 0;
+    const bool k3 = p.kw == 3 && p.kh == 3, k5 = p.kw == 5 && p.kh == 5;
+    const bool unrolled = k3 || (vec && k5);
+    const int rows_per_cta = CONV_BY * (unrolled ? CONV_RPT : 1);
+    dim3 grid((w + CONV_BX - 1) / CONV_BX,
+              std::min((h + rows_per_cta - 1) / rows_per_cta, 32768), 1);
     cudaStream_t st = (cudaStream_t)stream;
     const dim3 block(CONV_BX, CONV_BY);
-    if (vec && p.kw == 3 && p.kh == 3)  // unsharp_mask's default, maketx --sharpen
+    if (vec && k3)  // unsharp_mask's default, maketx --sharpen
         launch_pdl(convolve_kernel<true, 3, 3>, grid, block, 0, st, p);
-    else if (vec && p.kw == 5 && p.kh == 5)
+    else if (vec && k5)
         launch_pdl(convolve_kernel<true, 5, 5>, grid, block, 0, st, p);
     else if (vec)
         launch_pdl(convolve_kernel<true, 0, 0>, grid, block, 0, st, p);
-    else if (p.kw == 3 && p.kh == 3)
+    else if (k3)
         launch_pdl(convolve_kernel<false, 3, 3>, grid, block, 0, st, p);
     else
         launch_pdl(convolve_kernel<false, 0, 0>, grid, block, 0, st, p);
