@@ -5,7 +5,7 @@
 // get_resize_filter (imagebufalgo_xform.cpp:830-860), the (dst,src) type-pair
 // rule of OIIO_DISPATCH_COMMON_TYPES2 (imagebufalgo_util.h:463-552) and the
 // call into resize_<D,S> (:595-826) -- here two CUDA kernels instead.
-#include "b2r.h"
+#include "api_internal.h"
 
 #include "axis_plan.h"
 #include "fused_plan.h"
@@ -30,150 +30,9 @@
 #include <vector>
 
 using namespace b2r;
-
-struct b2r_filter2d {
-    Filter2D* f;
-};
-struct b2r_filter1d {
-    Filter1D* f;
-};
+using namespace b2r::api;
 
 namespace {
-
-void
-set_err(char* err, size_t errlen, const char* fmt, ...)
-{
-    if (!err || !errlen)
-        return;
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(err, errlen, fmt, ap);
-    va_end(ap);
-}
-
-#define CUDA_TRY(call)                                                        \
-    do {                                                                      \
-        cudaError_t e_ = (call);                                              \
-        if (e_ != cudaSuccess) {                                              \
-            set_err(err, errlen, "CUDA error: %s (%s)", cudaGetErrorString(e_), \
-                    #call);                                                   \
-            return B2R_ERR_CUDA;                                              \
-        }                                                                     \
-    } while (0)
-
-bool
-valid_basetype(int bt)
-{
-    return bt == B2R_UINT8 || bt == B2R_UINT16 || bt == B2R_HALF
-           || bt == B2R_FLOAT;
-}
-
-// OIIO_DISPATCH_COMMON_TYPES2: the ten native (dst,src) pairs.
-bool
-legal_pair(int d, int s)
-{
-    if (d == B2R_FLOAT)
-        return valid_basetype(s);
-    return s == B2R_FLOAT || s == d;
-}
-
-int
-device_count_cached()
-{
-    static int n = -1;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int c = 0;
-        if (cudaGetDeviceCount(&c) != cudaSuccess)
-            c = 0;
-        cudaGetLastError();
-        n = c;
-    });
-    return n;
-}
-
-struct DeviceInfo {
-    int sms = 0;
-    bool pool_ready = false;
-};
-DeviceInfo&
-device_info(int dev)
-{
-    static DeviceInfo info[64];
-    static std::mutex m;
-    std::lock_guard<std::mutex> lock(m);
-    DeviceInfo& d = info[dev & 63];
-    if (!d.sms) {
-        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ull;  // keep freed blocks cached
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            d.pool_ready = true;
-        }
-    }
-    return d;
-}
-
-int
-memspace_of(const b2r_image* im, int* device)
-{
-    if (im->memspace == B2R_MEM_HOST)
-        return B2R_MEM_HOST;
-    if (im->memspace == B2R_MEM_DEVICE) {
-        *device = im->device;
-        return B2R_MEM_DEVICE;
-    }
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, im->pixels) == cudaSuccess
-        && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged)) {
-        *device = a.device;
-        return B2R_MEM_DEVICE;
-    }
-    cudaGetLastError();
-    return B2R_MEM_HOST;
-}
-
-DevImage
-to_dev(const b2r_image& im, void* pixels)
-{
-    DevImage d;
-    d.pixels      = pixels;
-    d.basetype    = im.basetype;
-    d.nchannels   = im.nchannels;
-    d.x           = im.x;
-    d.y           = im.y;
-    d.width       = im.width;
-    d.height      = im.height;
-    d.full_x      = im.full_x;
-    d.full_y      = im.full_y;
-    d.full_width  = im.full_width;
-    d.full_height = im.full_height;
-    d.xstride     = im.xstride;
-    d.ystride     = im.ystride;
-    return d;
-}
-
-int
-check_image(const b2r_image* im, bool is_src, char* err, size_t errlen)
-{
-    if (!im || !im->pixels || im->width <= 0 || im->height <= 0
-        || im->nchannels <= 0) {
-        set_err(err, errlen,
-                is_src ? "Uninitialized input image"
-                       : "Uninitialized destination image");
-        return B2R_ERR_INVALID;
-    }
-    if (!valid_basetype(im->basetype)) {
-        set_err(err, errlen, "unsupported pixel data type %d", im->basetype);
-        return B2R_ERR_TYPES;
-    }
-    if (im->full_width <= 0 || im->full_height <= 0) {
-        set_err(err, errlen, "image has an empty display window");
-        return B2R_ERR_INVALID;
-    }
-    return B2R_OK;
-}
 
 // ---------------------------------------------------------------------------
 // A device blob holding every table of one resize shape.  Cached (LRU) so a
@@ -448,21 +307,6 @@ next_flag(int dev, int* epoch)
     *epoch     = int((n & 0x3fffffffu) + 1);
     return r.base + (n & 255);
 }
-
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev)
-    {
-        cudaGetDevice(&prev);
-        if (prev != dev)
-            cudaSetDevice(dev);
-    }
-    ~DeviceGuard()
-    {
-        if (prev >= 0)
-            cudaSetDevice(prev);
-    }
-};
 
 int
 resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
@@ -2534,1263 +2378,5 @@ b2r_mip_level(const b2r_image* dst, const b2r_image* src, const char* filtername
         set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
         return B2R_ERR_CUDA;
     }
-    return B2R_OK;
-}
-
-// =========================================================================
-// warp / rotate / fit(exact) / --resize:from/to
-// (imagebufalgo_xform.cpp:263-591, 1012-1027, 1727-1760; oiiotool.cpp:4684-4720)
-// =========================================================================
-#include "xform_matrix.h"
-
-namespace {
-
-int
-warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
-          const Filter2D& filter, int wrap, int edgeclamp, const b2r_roi* roi_in,
-          const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
-{
-    if (report)
-        memset(report, 0, sizeof(*report));
-    int rc = check_image(src_in, true, err, errlen);
-    if (rc)
-        return rc;
-    rc = check_image(dst_in, false, err, errlen);
-    if (rc)
-        return rc;
-    if (!M9) {
-        set_err(err, errlen, "warp: no matrix");
-        return B2R_ERR_INVALID;
-    }
-    if (wrap < 0 || wrap > 4) {
-        set_err(err, errlen, "warp: unknown wrap mode %d", wrap);
-        return B2R_ERR_INVALID;
-    }
-    const b2r_image& dst = *dst_in;
-    const b2r_image& src = *src_in;
-    if (device_count_cached() <= 0) {
-        set_err(err, errlen,
-                "no CUDA device available: the B200 warp path has no CPU fallback");
-        return B2R_ERR_NO_DEVICE;
-    }
-    b2r_roi roi;
-    if (roi_in) {
-        roi         = *roi_in;
-        roi.xbegin  = std::max(roi.xbegin, dst.x);
-        roi.xend    = std::min(roi.xend, dst.x + dst.width);
-        roi.ybegin  = std::max(roi.ybegin, dst.y);
-        roi.yend    = std::min(roi.yend, dst.y + dst.height);
-        roi.chbegin = std::max(roi.chbegin, 0);
-        roi.chend   = std::min(roi.chend, dst.nchannels);
-    } else {
-        roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
-                        dst.nchannels };
-    }
-    roi.chend = std::min(roi.chend, src.nchannels);  // warp_impl, xform.cpp:395
-    if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin || roi.chend <= roi.chbegin)
-        return B2R_OK;
-    const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
-    const int ses = basetype_size(src.basetype);
-    const int des = basetype_size(dst.basetype);
-
-    int sdev = opt ? opt->device : 0, ddev = sdev;
-    const int smem = memspace_of(&src, &sdev);
-    const int dmem = memspace_of(&dst, &ddev);
-    int device     = opt ? opt->device : 0;
-    if (smem == B2R_MEM_DEVICE)
-        device = sdev;
-    else if (dmem == B2R_MEM_DEVICE)
-        device = ddev;
-    if (device < 0 || device >= device_count_cached()) {
-        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
-        return B2R_ERR_INVALID;
-    }
-    DeviceGuard guard(device);
-    device_info(device);
-    cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
-
-    // Host images: the whole source data window goes up (a warp may read any
-    // of it), the dst ROI comes back.
-    b2r_image srcd = src, dstd = dst;
-    void* dsrc = src.pixels;
-    void* ddst = dst.pixels;
-    void *src_alloc = nullptr, *dst_alloc = nullptr;
-    size_t dpitch = 0, drowbytes = 0;
-    if (smem == B2R_MEM_HOST) {
-        if (src.xstride != (int64_t)src.nchannels * ses) {
-            set_err(err, errlen, "host source pixels must be contiguous in x");
-            return B2R_ERR_UNSUPPORTED;
-        }
-        const size_t rowbytes = size_t(src.width) * src.xstride;
-        const size_t pitch    = (rowbytes + 15) & ~size_t(15);
-        CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * src.height, stream));
-        CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
-                                   src.height, cudaMemcpyHostToDevice, stream));
-        srcd.ystride = (int64_t)pitch;
-        dsrc         = src_alloc;
-        if (report)
-            report->h2d_bytes += (int64_t)rowbytes * src.height;
-    }
-    unsigned char* host_out = nullptr;
-    if (dmem == B2R_MEM_HOST) {
-        if (dst.xstride != (int64_t)dst.nchannels * des) {
-            set_err(err, errlen, "host destination pixels must be contiguous in x");
-            if (src_alloc)
-                cudaFreeAsync(src_alloc, stream);
-            return B2R_ERR_UNSUPPORTED;
-        }
-        drowbytes = size_t(roi_w) * dst.xstride;
-        dpitch    = (drowbytes + 15) & ~size_t(15);
-        CUDA_TRY(cudaMallocAsync(&dst_alloc, dpitch * roi_h, stream));
-        host_out = (unsigned char*)dst.pixels + (long long)(roi.ybegin - dst.y) * dst.ystride
-                   + (long long)(roi.xbegin - dst.x) * dst.xstride;
-        if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
-            // channels outside the range keep what dst holds
-            CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
-                                       roi_h, cudaMemcpyHostToDevice, stream));
-            if (report)
-                report->h2d_bytes += (int64_t)drowbytes * roi_h;
-        }
-        ddst         = dst_alloc;
-        dstd.x       = roi.xbegin;
-        dstd.y       = roi.ybegin;
-        dstd.width   = roi_w;
-        dstd.height  = roi_h;
-        dstd.ystride = (int64_t)dpitch;
-    }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    const bool timed = report != nullptr;
-    if (timed) {
-        cudaEventCreate(&ev0);
-        cudaEventCreate(&ev1);
-        cudaEventRecord(ev0, stream);
-    }
-    WarpParams wp;
-    memset(&wp, 0, sizeof(wp));
-    wp.dst     = to_dev(dstd, ddst);
-    wp.src     = to_dev(srcd, dsrc);
-    wp.roi_x0  = roi.xbegin;
-    wp.roi_x1  = roi.xend;
-    wp.roi_y0  = roi.ybegin;
-    wp.roi_y1  = roi.yend;
-    wp.chbegin = roi.chbegin;
-    wp.chend   = roi.chend;
-    Mat33(M9).inverse().store(wp.minv);  // warp_: Minv = M.inverse()
-    const Filter2D::DeviceDesc fd = filter.device_desc();
-    wp.filt_profile = fd.profile;
-    wp.filt_scale   = fd.scale;
-    wp.filt_param   = fd.param;
-    wp.filt_w       = fd.w;
-    wp.filt_h       = fd.h;
-    wp.wrap         = wrap;
-    wp.edgeclamp    = edgeclamp ? 1 : 0;
-    launch_warp(wp, stream);
-    if (timed)
-        cudaEventRecord(ev1, stream);
-    {
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
-            return B2R_ERR_CUDA;
-        }
-    }
-    if (dst_alloc) {
-        CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
-                                   roi_h, cudaMemcpyDeviceToHost, stream));
-        if (report)
-            report->d2h_bytes += (int64_t)drowbytes * roi_h;
-        CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
-    }
-    if (src_alloc)
-        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
-    if (dst_alloc || src_alloc || timed)
-        CUDA_TRY(cudaStreamSynchronize(stream));
-    if (timed) {
-        cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
-        report->kernels_launched = 1;
-        report->path_used        = B2R_PATH_EXACT;
-    }
-    return B2R_OK;
-}
-
-}  // namespace
-
-extern "C" int
-b2r_warp_filter(const b2r_image* dst, const b2r_image* src, const float* M,
-                const b2r_filter2d* filter, int wrap, int edgeclamp, const b2r_roi* roi,
-                const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
-{
-    if (!filter || !filter->f) {
-        // warp_impl: "If no filter was provided, punt and use lanczos3" (:403-408)
-        std::unique_ptr<Filter2D, void (*)(Filter2D*)> f(Filter2D::create("lanczos3", 6.0f,
-                                                                          6.0f),
-                                                         Filter2D::destroy);
-        return warp_impl(dst, src, M, *f, wrap, edgeclamp, roi, opt, report, err, errlen);
-    }
-    return warp_impl(dst, src, M, *filter->f, wrap, edgeclamp, roi, opt, report, err, errlen);
-}
-
-extern "C" int
-b2r_warp(const b2r_image* dst, const b2r_image* src, const float* M, const char* filtername,
-         float filterwidth, int wrap, int edgeclamp, const b2r_roi* roi,
-         const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
-{
-    // get_warp_filter, imagebufalgo_xform.cpp:329-349
-    std::string name = (filtername && filtername[0]) ? filtername : "lanczos3";
-    std::unique_ptr<Filter2D, void (*)(Filter2D*)> filter(nullptr, Filter2D::destroy);
-    for (int i = 0, e = Filter2D::num_filters(); i < e; ++i) {
-        const FilterDesc& fd = Filter2D::get_filterdesc(i);
-        if (name == fd.name) {
-            const float w = filterwidth > 0.0f ? filterwidth : fd.width;
-            filter.reset(Filter2D::create(name, w, w));
-            break;
-        }
-    }
-    if (!filter) {
-        set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
-        return B2R_ERR_FILTER;
-    }
-    return warp_impl(dst, src, M, *filter, wrap, edgeclamp, roi, opt, report, err, errlen);
-}
-
-extern "C" void
-b2r_m33_inverse(const float* M, float* out)
-{
-    Mat33(M).inverse().store(out);
-}
-
-extern "C" void
-b2r_rotate_matrix(float angle, float center_x, float center_y, float* out)
-{
-    rotation_about(angle, center_x, center_y).store(out);
-}
-
-extern "C" void
-b2r_fromto_matrix(float from_x, float from_y, float from_w, float from_h, float to_x,
-                  float to_y, float to_w, float to_h, float* out)
-{
-    fromto_matrix(from_x, from_y, from_w, from_h, to_x, to_y, to_w, to_h).store(out);
-}
-
-extern "C" void
-b2r_transform_roi(const float* M, const b2r_roi* roi, b2r_roi* out)
-{
-    int b[4];
-    transform_bounds(Mat33(M), roi->xbegin, roi->xend, roi->ybegin, roi->yend, b);
-    *out        = *roi;
-    out->xbegin = b[0], out->xend = b[1], out->ybegin = b[2], out->yend = b[3];
-}
-
-extern "C" void
-b2r_fit_exact(int src_full_width, int src_full_height, int fit_width, int fit_height,
-              const char* fillmode, float* M, int* resize_width, int* resize_height)
-{
-    // imagebufalgo_xform.cpp:962-997 (scale / offsets) and :1023
-    const float oldaspect = float(src_full_width) / src_full_height;
-    const float newaspect = float(fit_width) / fit_height;
-    int rw = fit_width, rh = fit_height;
-    float xoff = 0.0f, yoff = 0.0f, scale = 1.0f;
-    std::string mode = fillmode ? fillmode : "letterbox";
-    if (mode != "height" && mode != "width")
-        mode = "letterbox";
-    if (mode == "letterbox")
-        mode = (newaspect >= oldaspect) ? "height" : "width";
-    if (mode == "height") {
-        rw    = int(rh * oldaspect + 0.5f);
-        scale = float(fit_height) / float(src_full_height);
-        xoff  = float(fit_width - scale * src_full_width) / 2.0f;
-    } else {
-        rh    = int(rw / oldaspect + 0.5f);
-        scale = float(fit_width) / float(src_full_width);
-        yoff  = float(fit_height - scale * src_full_height) / 2.0f;
-    }
-    if (M) {
-        const float m[9] = { scale, 0.0f, 0.0f, 0.0f, scale, 0.0f, xoff, yoff, 1.0f };
-        memcpy(M, m, sizeof(m));
-    }
-    if (resize_width)
-        *resize_width = rw;
-    if (resize_height)
-        *resize_height = rh;
-}
-
-// =========================================================================
-// make_kernel / convolve / unsharp_mask  (imagebufalgo.cpp:772-1031)
-// =========================================================================
-#include "conv_kernel.h"
-
-namespace {
-
-// Host<->device staging shared by the stencil entry points: the whole source
-// data window goes up (a stencil may read any of it), the dst ROI comes back.
-struct StencilIO {
-    b2r_roi roi;
-    b2r_image srcd, dstd;
-    void *dsrc = nullptr, *ddst = nullptr;
-    void *src_alloc = nullptr, *dst_alloc = nullptr;
-    unsigned char* host_out = nullptr;
-    size_t dpitch = 0, drowbytes = 0;
-    int roi_w = 0, roi_h = 0, device = 0;
-    bool empty       = false;
-    bool same_pixels = false;  // dst and src are one image (in place)
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    std::unique_ptr<DeviceGuard> guard;
-
-    int begin(const b2r_image* dst_in, const b2r_image* src_in, const b2r_roi* roi_in,
-              const b2r_options* opt, b2r_report* report, const char* what, char* err,
-              size_t errlen, bool same_nchannels = true)
-    {
-        if (report)
-            memset(report, 0, sizeof(*report));
-        int rc = check_image(src_in, true, err, errlen);
-        if (rc)
-            return rc;
-        rc = check_image(dst_in, false, err, errlen);
-        if (rc)
-            return rc;
-        const b2r_image& dst = *dst_in;
-        const b2r_image& src = *src_in;
-        if (same_nchannels && dst.nchannels != src.nchannels) {
-            set_err(err, errlen, "images must have the same number of channels");
-            return B2R_ERR_INVALID;
-        }
-        if (device_count_cached() <= 0) {
-            set_err(err, errlen,
-                    "no CUDA device available: the B200 %s path has no CPU fallback", what);
-            return B2R_ERR_NO_DEVICE;
-        }
-        if (roi_in) {
-            roi         = *roi_in;
-            roi.xbegin  = std::max(roi.xbegin, dst.x);
-            roi.xend    = std::min(roi.xend, dst.x + dst.width);
-            roi.ybegin  = std::max(roi.ybegin, dst.y);
-            roi.yend    = std::min(roi.yend, dst.y + dst.height);
-            roi.chbegin = std::max(roi.chbegin, 0);
-            roi.chend   = std::min(roi.chend, dst.nchannels);
-        } else {
-            roi = b2r_roi { dst.x, dst.x + dst.width, dst.y, dst.y + dst.height, 0,
-                            dst.nchannels };
-        }
-        if (roi.xend <= roi.xbegin || roi.yend <= roi.ybegin || roi.chend <= roi.chbegin) {
-            empty = true;
-            return B2R_OK;
-        }
-        roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
-        const int ses = basetype_size(src.basetype);
-        const int des = basetype_size(dst.basetype);
-        int sdev = opt ? opt->device : 0, ddev = sdev;
-        const int smem = memspace_of(&src, &sdev);
-        const int dmem = memspace_of(&dst, &ddev);
-        device         = opt ? opt->device : 0;
-        if (smem == B2R_MEM_DEVICE)
-            device = sdev;
-        else if (dmem == B2R_MEM_DEVICE)
-            device = ddev;
-        if (device < 0 || device >= device_count_cached()) {
-            set_err(err, errlen, "invalid CUDA device ordinal %d", device);
-            return B2R_ERR_INVALID;
-        }
-        guard.reset(new DeviceGuard(device));
-        device_info(device);
-        stream      = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
-        same_pixels = dst.pixels == src.pixels;
-        srcd = src, dstd = dst;
-        dsrc = src.pixels, ddst = dst.pixels;
-        if (smem == B2R_MEM_HOST) {
-            if (src.xstride != (int64_t)src.nchannels * ses) {
-                set_err(err, errlen, "host source pixels must be contiguous in x");
-                return B2R_ERR_UNSUPPORTED;
-            }
-            const size_t rowbytes = size_t(src.width) * src.xstride;
-            const size_t pitch    = (rowbytes + 15) & ~size_t(15);
-            CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * src.height, stream));
-            CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
-                                       src.height, cudaMemcpyHostToDevice, stream));
-            srcd.ystride = (int64_t)pitch;
-            dsrc         = src_alloc;
-            if (report)
-                report->h2d_bytes += (int64_t)rowbytes * src.height;
-        }
-        if (dmem == B2R_MEM_HOST) {
-            if (dst.xstride != (int64_t)dst.nchannels * des) {
-                set_err(err, errlen, "host destination pixels must be contiguous in x");
-                return B2R_ERR_UNSUPPORTED;
-            }
-            drowbytes = size_t(roi_w) * dst.xstride;
-            dpitch    = (drowbytes + 15) & ~size_t(15);
-            CUDA_TRY(cudaMallocAsync(&dst_alloc, dpitch * roi_h, stream));
-            host_out = (unsigned char*)dst.pixels
-                       + (long long)(roi.ybegin - dst.y) * dst.ystride
-                       + (long long)(roi.xbegin - dst.x) * dst.xstride;
-            if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
-                CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
-                                           roi_h, cudaMemcpyHostToDevice, stream));
-                if (report)
-                    report->h2d_bytes += (int64_t)drowbytes * roi_h;
-            }
-            ddst         = dst_alloc;
-            dstd.x       = roi.xbegin;
-            dstd.y       = roi.ybegin;
-            dstd.width   = roi_w;
-            dstd.height  = roi_h;
-            dstd.ystride = (int64_t)dpitch;
-        }
-        if (report) {
-            cudaEventCreate(&ev0);
-            cudaEventCreate(&ev1);
-            cudaEventRecord(ev0, stream);
-        }
-        return B2R_OK;
-    }
-
-    int end(const b2r_image& dst, b2r_report* report, int launched, char* err, size_t errlen)
-    {
-        if (report)
-            cudaEventRecord(ev1, stream);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            set_err(err, errlen, "CUDA launch error: %s", cudaGetErrorString(e));
-            return B2R_ERR_CUDA;
-        }
-        if (dst_alloc) {
-            CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
-                                       roi_h, cudaMemcpyDeviceToHost, stream));
-            if (report)
-                report->d2h_bytes += (int64_t)drowbytes * roi_h;
-        }
-        release();
-        if (dst_alloc || src_alloc || extra_alloc || report)
-            CUDA_TRY(cudaStreamSynchronize(stream));
-        if (report) {
-            cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
-            cudaEventDestroy(ev0);
-            cudaEventDestroy(ev1);
-            ev0 = ev1                = nullptr;
-            report->kernels_launched = launched;
-            report->path_used        = B2R_PATH_EXACT;
-        }
-        return B2R_OK;
-    }
-
-    // true when dst and src share device pixels even though the caller's host
-    // pointers differ (never: each host image gets its own staging buffer)
-    bool dst_alloc_is_src() const { return ddst == dsrc; }
-
-    // a further input image (st_warp's ST buffer): whole data window up
-    void* extra_alloc = nullptr;
-    int stage_extra(const b2r_image& im, b2r_image* imd, void** dpix, b2r_report* report,
-                    char* err, size_t errlen)
-    {
-        *imd  = im;
-        *dpix = im.pixels;
-        int dev = device;
-        if (memspace_of(&im, &dev) != B2R_MEM_HOST)
-            return B2R_OK;
-        const int es = basetype_size(im.basetype);
-        if (im.xstride != (int64_t)im.nchannels * es) {
-            set_err(err, errlen, "host pixels must be contiguous in x");
-            return B2R_ERR_UNSUPPORTED;
-        }
-        const size_t rowbytes = size_t(im.width) * im.xstride;
-        const size_t pitch    = (rowbytes + 15) & ~size_t(15);
-        CUDA_TRY(cudaMallocAsync(&extra_alloc, pitch * im.height, stream));
-        CUDA_TRY(cudaMemcpy2DAsync(extra_alloc, pitch, im.pixels, im.ystride, rowbytes,
-                                   im.height, cudaMemcpyHostToDevice, stream));
-        imd->ystride = (int64_t)pitch;
-        *dpix        = extra_alloc;
-        if (report)
-            report->h2d_bytes += (int64_t)rowbytes * im.height;
-        return B2R_OK;
-    }
-
-    void release()
-    {
-        if (dst_alloc)
-            cudaFreeAsync(dst_alloc, stream);
-        if (src_alloc)
-            cudaFreeAsync(src_alloc, stream);
-        if (extra_alloc)
-            cudaFreeAsync(extra_alloc, stream);
-    }
-    ~StencilIO()
-    {
-        if (ev0)
-            cudaEventDestroy(ev0);
-        if (ev1)
-            cudaEventDestroy(ev1);
-    }
-};
-
-// upload a host float table; freed stream-ordered by the caller
-int
-upload_floats(const float* host, size_t n, cudaStream_t stream, float** out, char* err,
-              size_t errlen)
-{
-    CUDA_TRY(cudaMallocAsync((void**)out, n * sizeof(float), stream));
-    CUDA_TRY(cudaMemcpyAsync(*out, host, n * sizeof(float), cudaMemcpyHostToDevice, stream));
-    return B2R_OK;
-}
-
-float
-kernel_scale(const float* k, int n, bool normalize)
-{
-    if (!normalize)
-        return 1.0f;
-    float s = 0.0f;
-    for (int i = 0; i < n; ++i)
-        s += k[i];
-    return 1.0f / s;
-}
-
-void
-run_convolve(const b2r_image& dstd, void* ddst, const b2r_image& srcd, void* dsrc,
-             const b2r_roi& roi, const float* dkernel, int kw, int kh, float scale,
-             cudaStream_t stream)
-{
-    ConvParams cp;
-    memset(&cp, 0, sizeof(cp));
-    cp.dst     = to_dev(dstd, ddst);
-    cp.src     = to_dev(srcd, dsrc);
-    cp.roi_x0  = std::max(roi.xbegin, dstd.x);
-    cp.roi_x1  = std::min(roi.xend, dstd.x + dstd.width);
-    cp.roi_y0  = std::max(roi.ybegin, dstd.y);
-    cp.roi_y1  = std::min(roi.yend, dstd.y + dstd.height);
-    cp.chbegin = roi.chbegin;
-    cp.chend   = roi.chend;
-    cp.kernel  = dkernel;
-    cp.kw      = kw;
-    cp.kh      = kh;
-    cp.scale   = scale;
-    launch_convolve(cp, stream);
-}
-
-}  // namespace
-
-/* ImageBufAlgo::make_kernel (imagebufalgo.cpp:864-957), depth 1. */
-extern "C" int
-b2r_make_kernel(const char* name, float width, float height, int normalize, float* out,
-                int* kw, int* kh, char* err, size_t errlen)
-{
-    ConvKernel K = make_conv_kernel(name ? name : "", width, height, normalize != 0);
-    if (kw)
-        *kw = K.w;
-    if (kh)
-        *kh = K.h;
-    if (out)
-        memcpy(out, K.v.data(), K.v.size() * sizeof(float));
-    if (!K.known) {
-        set_err(err, errlen, "%s", K.error.c_str());
-        return B2R_ERR_FILTER;
-    }
-    return B2R_OK;
-}
-
-extern "C" int
-b2r_convolve(const b2r_image* dst, const b2r_image* src, const float* kernel, int kw, int kh,
-             int normalize, const b2r_roi* roi, const b2r_options* opt, b2r_report* report,
-             char* err, size_t errlen)
-{
-    if (!kernel || kw <= 0 || kh <= 0) {
-        set_err(err, errlen, "convolve: no kernel");
-        return B2R_ERR_INVALID;
-    }
-    StencilIO io;
-    int rc = io.begin(dst, src, roi, opt, report, "convolve", err, errlen);
-    if (rc || io.empty) {
-        io.release();
-        return rc;
-    }
-    if (io.same_pixels) {
-        io.release();
-        set_err(err, errlen, "convolve: dst and src must be different images");
-        return B2R_ERR_INVALID;
-    }
-    float* dk = nullptr;
-    rc        = upload_floats(kernel, (size_t)kw * kh, io.stream, &dk, err, errlen);
-    if (rc) {
-        io.release();
-        return rc;
-    }
-    run_convolve(io.dstd, io.ddst, io.srcd, io.dsrc, io.roi, dk, kw, kh,
-                 kernel_scale(kernel, kw * kh, normalize != 0), io.stream);
-    cudaFreeAsync(dk, io.stream);
-    return io.end(*dst, report, 1, err, errlen);
-}
-
-extern "C" int
-b2r_unsharp_mask(const b2r_image* dst, const b2r_image* src, const char* kernel, float width,
-                 float contrast, float threshold, const b2r_roi* roi, const b2r_options* opt,
-                 b2r_report* report, char* err, size_t errlen)
-{
-    const std::string kname = (kernel && kernel[0]) ? kernel : "gaussian";
-    if (kname == "median") {
-        set_err(err, errlen,
-                "unsharp_mask: the median kernel is not part of the B200 resampling path");
-        return B2R_ERR_UNSUPPORTED;
-    }
-    // the kernels first: an unknown name is an error before anything is staged
-    const bool two_pass = width > 3.0;
-    ConvKernel K = two_pass ? make_conv_kernel(kname, 1, width) : make_conv_kernel(kname, width, width);
-    if (!K.known) {
-        set_err(err, errlen, "%s", K.error.c_str());
-        return B2R_ERR_FILTER;
-    }
-    StencilIO io;
-    int rc = io.begin(dst, src, roi, opt, report, "unsharp_mask", err, errlen);
-    if (rc || io.empty) {
-        io.release();
-        return rc;
-    }
-    // Blurry (and fst_pass): float images with src's windows, zero filled (:988-992)
-    const b2r_image& S = io.srcd;
-    const size_t brow  = size_t(S.width) * S.nchannels * sizeof(float);
-    const size_t bsize = brow * S.height;
-    void *blur = nullptr, *first = nullptr;
-    float* dk  = nullptr;
-    auto fail  = [&](int code) {
-        if (blur)
-            cudaFreeAsync(blur, io.stream);
-        if (first)
-            cudaFreeAsync(first, io.stream);
-        if (dk)
-            cudaFreeAsync(dk, io.stream);
-        io.release();
-        return code;
-    };
-    rc = upload_floats(K.v.data(), K.v.size(), io.stream, &dk, err, errlen);
-    if (rc)
-        return fail(rc);
-    b2r_roi croi  = io.roi;  // convolve runs over every channel (:1004-1019 pass roi as is)
-    const float s = kernel_scale(K.v.data(), K.w * K.h, true);
-    int launched  = 0;
-    if (!two_pass && !io.same_pixels && !io.dst_alloc_is_src()) {
-        // one 2-D pass and distinct images: blur and combine in ONE kernel,
-        // the blur image never exists (same arithmetic, same result)
-        ConvParams cp;
-        memset(&cp, 0, sizeof(cp));
-        cp.dst       = to_dev(io.dstd, io.ddst);
-        cp.src       = to_dev(S, io.dsrc);
-        cp.roi_x0    = io.roi.xbegin, cp.roi_x1 = io.roi.xend;
-        cp.roi_y0    = io.roi.ybegin, cp.roi_y1 = io.roi.yend;
-        cp.chbegin   = io.roi.chbegin;
-        cp.chend     = io.roi.chend;
-        cp.kernel    = dk;
-        cp.kw        = K.w;
-        cp.kh        = K.h;
-        cp.scale     = s;
-        cp.unsharp   = 1;
-        cp.contrast  = contrast;
-        cp.threshold = threshold;
-        launch_convolve(cp, io.stream);
-        cudaFreeAsync(dk, io.stream);
-        return io.end(*dst, report, 1, err, errlen);
-    }
-    if (cudaMallocAsync(&blur, bsize, io.stream) != cudaSuccess
-        || cudaMemsetAsync(blur, 0, bsize, io.stream) != cudaSuccess) {
-        set_err(err, errlen, "CUDA error allocating the blur image");
-        return fail(B2R_ERR_CUDA);
-    }
-    b2r_image B = S;
-    B.pixels    = blur;
-    B.basetype  = B2R_FLOAT;
-    B.xstride   = (int64_t)S.nchannels * 4;
-    B.ystride   = (int64_t)brow;
-    B.memspace  = B2R_MEM_DEVICE;
-    if (two_pass) {
-        if (cudaMallocAsync(&first, bsize, io.stream) != cudaSuccess
-            || cudaMemsetAsync(first, 0, bsize, io.stream) != cudaSuccess) {
-            set_err(err, errlen, "CUDA error allocating the first-pass image");
-            return fail(B2R_ERR_CUDA);
-        }
-        b2r_image F = B;
-        F.pixels    = first;
-        run_convolve(F, first, S, io.dsrc, croi, dk, K.w, K.h, s, io.stream);
-        // Kt = transpose(K): same values, K.h wide and K.w tall
-        run_convolve(B, blur, F, first, croi, dk, K.h, K.w, s, io.stream);
-        launched += 2;
-    } else {
-        run_convolve(B, blur, S, io.dsrc, croi, dk, K.w, K.h, s, io.stream);
-        launched += 1;
-    }
-    UnsharpParams up;
-    memset(&up, 0, sizeof(up));
-    up.dst       = to_dev(io.dstd, io.ddst);
-    up.src       = to_dev(S, io.dsrc);
-    up.blur      = to_dev(B, blur);
-    up.roi_x0    = io.roi.xbegin;
-    up.roi_x1    = io.roi.xend;
-    up.roi_y0    = io.roi.ybegin;
-    up.roi_y1    = io.roi.yend;
-    up.chbegin   = io.roi.chbegin;
-    up.chend     = io.roi.chend;
-    up.contrast  = contrast;
-    up.threshold = threshold;
-    launch_unsharp_combine(up, io.stream);
-    ++launched;
-    cudaFreeAsync(blur, io.stream);
-    if (first)
-        cudaFreeAsync(first, io.stream);
-    cudaFreeAsync(dk, io.stream);
-    return io.end(*dst, report, launched, err, errlen);
-}
-
-
-// =========================================================================
-// st_warp (imagebufalgo_xform.cpp:1834-2058)
-// =========================================================================
-namespace {
-int
-st_warp_impl(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
-             const Filter2D& filter, int chan_s, int chan_t, int flip_s, int flip_t,
-             const b2r_roi* roi_in, const b2r_options* opt, b2r_report* report, char* err,
-             size_t errlen)
-{
-    // check_st_warp_args (:1929-1972)
-    if (!st || !st->pixels || st->width <= 0 || st->height <= 0 || st->nchannels <= 0) {
-        set_err(err, errlen, "ImageBufAlgo::st_warp : Uninitialized ST buffer");
-        return B2R_ERR_INVALID;
-    }
-    if (!valid_basetype(st->basetype)) {
-        set_err(err, errlen, "unsupported pixel data type %d", st->basetype);
-        return B2R_ERR_TYPES;
-    }
-    if (chan_s >= st->nchannels || chan_s < 0) {
-        set_err(err, errlen, "ImageBufAlgo::st_warp : Out-of-range S channel index: %d",
-                chan_s);
-        return B2R_ERR_INVALID;
-    }
-    if (chan_t >= st->nchannels || chan_t < 0) {
-        set_err(err, errlen, "ImageBufAlgo::st_warp : Out-of-range T channel index: %d",
-                chan_t);
-        return B2R_ERR_INVALID;
-    }
-    StencilIO io;
-    int rc = io.begin(dst, src, roi_in, opt, report, "st_warp", err, errlen, false);
-    if (rc || io.empty) {
-        io.release();
-        return rc;
-    }
-    io.roi.chend = std::min(io.roi.chend, src->nchannels);
-    // the warp is only defined where the ST image has pixels
-    b2r_roi r = io.roi;
-    r.xbegin  = std::max(r.xbegin, st->x), r.xend = std::min(r.xend, st->x + st->width);
-    r.ybegin  = std::max(r.ybegin, st->y), r.yend = std::min(r.yend, st->y + st->height);
-    if (r.xend <= r.xbegin || r.yend <= r.ybegin) {
-        io.release();
-        set_err(err, errlen,
-                "ImageBufAlgo::st_warp : Output ROI does not intersect ST buffer.");
-        return B2R_ERR_INVALID;
-    }
-    if (io.dst_alloc && (r.xbegin != io.roi.xbegin || r.xend != io.roi.xend
-                         || r.ybegin != io.roi.ybegin || r.yend != io.roi.yend
-                         || io.roi.chbegin != 0 || io.roi.chend != dst->nchannels)) {
-        // part of the staged dst ROI will not be written: bring its pixels over
-        cudaMemcpy2DAsync(io.dst_alloc, io.dpitch, io.host_out, dst->ystride, io.drowbytes,
-                          io.roi_h, cudaMemcpyHostToDevice, io.stream);
-    }
-    b2r_image std_;
-    void* dst_pix = nullptr;
-    rc = io.stage_extra(*st, &std_, &dst_pix, report, err, errlen);
-    if (rc) {
-        io.release();
-        return rc;
-    }
-    StWarpParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.dst     = to_dev(io.dstd, io.ddst);
-    sp.src     = to_dev(io.srcd, io.dsrc);
-    sp.st      = to_dev(std_, dst_pix);
-    sp.roi_x0  = r.xbegin;
-    sp.roi_x1  = r.xend;
-    sp.roi_y0  = r.ybegin;
-    sp.roi_y1  = r.yend;
-    sp.chbegin = io.roi.chbegin;
-    sp.chend   = io.roi.chend;
-    sp.chan_s  = chan_s;
-    sp.chan_t  = chan_t;
-    sp.flip_s  = flip_s ? 1 : 0;
-    sp.flip_t  = flip_t ? 1 : 0;
-    const float xscale = float(dst->full_width) / src->full_width;
-    const float yscale = float(dst->full_height) / src->full_height;
-    sp.filterrad_x     = (int)ceilf(filter.width() / 2.0f / xscale);
-    sp.filterrad_y     = (int)ceilf(filter.height() / 2.0f / yscale);
-    const Filter2D::DeviceDesc fd = filter.device_desc();
-    sp.filt_profile = fd.profile;
-    sp.filt_scale   = fd.scale;
-    sp.filt_param   = fd.param;
-    sp.filt_w       = fd.w;
-    sp.filt_h       = fd.h;
-    launch_st_warp(sp, io.stream);
-    return io.end(*dst, report, 1, err, errlen);
-}
-}  // namespace
-
-extern "C" int
-b2r_st_warp_filter(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
-                   const b2r_filter2d* filter, int chan_s, int chan_t, int flip_s,
-                   int flip_t, const b2r_roi* roi, const b2r_options* opt,
-                   b2r_report* report, char* err, size_t errlen)
-{
-    if (!filter || !filter->f) {  // :1994-1998
-        std::unique_ptr<Filter2D, void (*)(Filter2D*)> f(Filter2D::create("lanczos3", 6.0f,
-                                                                          6.0f),
-                                                         Filter2D::destroy);
-        return st_warp_impl(dst, src, st, *f, chan_s, chan_t, flip_s, flip_t, roi, opt, report,
-                            err, errlen);
-    }
-    return st_warp_impl(dst, src, st, *filter->f, chan_s, chan_t, flip_s, flip_t, roi, opt,
-                        report, err, errlen);
-}
-
-extern "C" int
-b2r_st_warp(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
-            const char* filtername, float filterwidth, int chan_s, int chan_t, int flip_s,
-            int flip_t, const b2r_roi* roi, const b2r_options* opt, b2r_report* report,
-            char* err, size_t errlen)
-{
-    std::string name = (filtername && filtername[0]) ? filtername : "lanczos3";
-    std::unique_ptr<Filter2D, void (*)(Filter2D*)> filter(nullptr, Filter2D::destroy);
-    for (int i = 0, e = Filter2D::num_filters(); i < e; ++i) {
-        const FilterDesc& fd = Filter2D::get_filterdesc(i);
-        if (name == fd.name) {
-            const float w = filterwidth > 0.0f ? filterwidth : fd.width;
-            filter.reset(Filter2D::create(name, w, w));
-            break;
-        }
-    }
-    if (!filter) {
-        set_err(err, errlen, "Filter \"%s\" not recognized", name.c_str());
-        return B2R_ERR_FILTER;
-    }
-    return st_warp_impl(dst, src, st, *filter, chan_s, chan_t, flip_s, flip_t, roi, opt,
-                        report, err, errlen);
-}
-
-
-// =========================================================================
-// fixNonFinite / check_nan  (imagebufalgo_pixelmath.cpp:1424-1610,
-// maketexture.cpp:340-360, 1666-1705)
-// =========================================================================
-extern "C" int
-b2r_fix_nonfinite(const b2r_image* dst, const b2r_image* src, int mode, int* pixels_fixed,
-                  const b2r_roi* roi, const b2r_options* opt, b2r_report* report, char* err,
-                  size_t errlen)
-{
-    if (pixels_fixed)
-        *pixels_fixed = 0;
-    if (mode != 0 && mode != 1 && mode != 2 && mode != 100) {
-        set_err(err, errlen, "fixNonFinite: unknown repair mode");
-        return B2R_ERR_INVALID;
-    }
-    StencilIO io;
-    int rc = io.begin(dst, src, roi, opt, report, "fixNonFinite", err, errlen);
-    if (rc || io.empty) {
-        io.release();
-        return rc;
-    }
-    if (dst->basetype != src->basetype) {
-        io.release();
-        set_err(err, errlen, "fixNonFinite: dst and src must have the same pixel type");
-        return B2R_ERR_TYPES;
-    }
-    const bool fp    = src->basetype == B2R_FLOAT || src->basetype == B2R_HALF;
-    const int es     = basetype_size(src->basetype);
-    const bool count_only = (mode == 0 || mode == 100);
-    int launched     = 0;
-    int* counter     = nullptr;
-    void* inplace_tmp = nullptr;
-    b2r_image S      = io.srcd;
-    void* spix       = io.dsrc;
-    // Integer types cannot hold NaN/Inf: fixNonFinite is just the copy
-    // (:1586-1587); the counting modes copy too.  (The repair kernel writes
-    // every channel of every ROI pixel itself.)
-    if ((!fp || count_only) && (io.dst_alloc || !io.same_pixels)) {
-        if (S.xstride != (int64_t)S.nchannels * es
-            || io.dstd.xstride != (int64_t)S.nchannels * es) {
-            io.release();
-            set_err(err, errlen, "fixNonFinite: pixels must be contiguous in x");
-            return B2R_ERR_UNSUPPORTED;
-        }
-        if (io.dst_alloc)
-            cudaMemset2DAsync(io.dst_alloc, io.dpitch, 0, io.drowbytes, io.roi_h, io.stream);
-        const int x0 = std::max(io.roi.xbegin, S.x), x1 = std::min(io.roi.xend, S.x + S.width);
-        const int y0 = std::max(io.roi.ybegin, S.y), y1 = std::min(io.roi.yend, S.y + S.height);
-        if (x1 > x0 && y1 > y0) {
-            unsigned char* dp = (unsigned char*)io.ddst
-                                + (long long)(y0 - io.dstd.y) * io.dstd.ystride
-                                + (long long)(x0 - io.dstd.x) * io.dstd.xstride;
-            const unsigned char* sp = (const unsigned char*)spix
-                                      + (long long)(y0 - S.y) * S.ystride
-                                      + (long long)(x0 - S.x) * S.xstride;
-            cudaMemcpy2DAsync(dp, io.dstd.ystride, sp, S.ystride, size_t(x1 - x0) * S.xstride,
-                              y1 - y0, cudaMemcpyDeviceToDevice, io.stream);
-        }
-    }
-    if (fp) {
-        if (cudaMallocAsync((void**)&counter, sizeof(int), io.stream) != cudaSuccess
-            || cudaMemsetAsync(counter, 0, sizeof(int), io.stream) != cudaSuccess) {
-            io.release();
-            set_err(err, errlen, "CUDA error allocating the counter");
-            return B2R_ERR_CUDA;
-        }
-        if (io.same_pixels && mode == 2 && !io.src_alloc) {
-            // box3 in place on the device: neighbours must be read unrepaired
-            const size_t rowb = size_t(S.width) * S.nchannels * es;
-            if (cudaMallocAsync(&inplace_tmp, rowb * S.height, io.stream) != cudaSuccess) {
-                cudaFreeAsync(counter, io.stream);
-                io.release();
-                set_err(err, errlen, "CUDA error allocating the in-place copy");
-                return B2R_ERR_CUDA;
-            }
-            cudaMemcpy2DAsync(inplace_tmp, rowb, spix, S.ystride, rowb, S.height,
-                              cudaMemcpyDeviceToDevice, io.stream);
-            S.ystride = (int64_t)rowb;
-            S.xstride = (int64_t)S.nchannels * es;
-            spix      = inplace_tmp;
-        }
-        NonFiniteParams np;
-        memset(&np, 0, sizeof(np));
-        np.dst     = to_dev(io.dstd, io.ddst);
-        np.src     = to_dev(S, spix);
-        np.roi_x0  = io.roi.xbegin;
-        np.roi_x1  = io.roi.xend;
-        np.roi_y0  = io.roi.ybegin;
-        np.roi_y1  = io.roi.yend;
-        np.chbegin = io.roi.chbegin;
-        np.chend   = io.roi.chend;
-        np.mode    = mode;
-        np.write   = count_only ? 0 : 1;
-        np.counter = counter;
-        launch_fix_nonfinite(np, io.stream);
-        launched = 1;
-    }
-    int host_count = 0;
-    if (counter) {
-        cudaMemcpyAsync(&host_count, counter, sizeof(int), cudaMemcpyDeviceToHost, io.stream);
-        cudaFreeAsync(counter, io.stream);
-    }
-    if (inplace_tmp)
-        cudaFreeAsync(inplace_tmp, io.stream);
-    rc = io.end(*dst, report, launched, err, errlen);
-    if (rc)
-        return rc;
-    if (counter) {
-        cudaError_t e = cudaStreamSynchronize(io.stream);  // the count is a return value
-        if (e != cudaSuccess) {
-            set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
-            return B2R_ERR_CUDA;
-        }
-    }
-    if (pixels_fixed)
-        *pixels_fixed = host_count;
-    if (mode == 100 && host_count) {
-        set_err(err, errlen, "Nonfinite pixel values found");
-        return B2R_ERR_INVALID;
-    }
-    return B2R_OK;
-}
-
-
-// =========================================================================
-// fillholes_pushpull (imagebufalgo.cpp:1600-1670): a float pyramid made with
-// the triangle-filter resize, pushed down (divide by alpha) and pulled back up
-// (over), entirely on the device.
-// =========================================================================
-extern "C" int
-b2r_fillholes_pushpull(const b2r_image* dst, const b2r_image* src, int alpha_channel,
-                       const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
-{
-    int rc = check_image(src, true, err, errlen);
-    if (rc)
-        return rc;
-    if (alpha_channel < 0 || alpha_channel >= src->nchannels) {
-        set_err(err, errlen, "images must have alpha channels");
-        return B2R_ERR_INVALID;
-    }
-    // the result is pasted back at the source's origin (:1659): the region
-    // written is src's data window (clipped to dst's)
-    b2r_roi roi { src->x, src->x + src->width, src->y, src->y + src->height, 0,
-                  src->nchannels };
-    StencilIO io;
-    rc = io.begin(dst, src, &roi, opt, report, "fillholes_pushpull", err, errlen);
-    if (rc || io.empty) {
-        io.release();
-        return rc;
-    }
-    const int nch = src->nchannels;
-    const int W = src->width, H = src->height;
-    struct Lv {
-        int w, h;
-        float* px;
-    };
-    std::vector<Lv> pyr;
-    float* blow = nullptr;
-    auto fail = [&](int code) {
-        for (auto& l : pyr)
-            if (l.px)
-                cudaFreeAsync(l.px, io.stream);
-        if (blow)
-            cudaFreeAsync(blow, io.stream);
-        io.release();
-        return code;
-    };
-    for (int w = W, h = H;;) {
-        Lv l { w, h, nullptr };
-        if (cudaMallocAsync((void**)&l.px, size_t(w) * h * nch * 4, io.stream) != cudaSuccess) {
-            set_err(err, errlen, "fillholes_pushpull: out of device memory");
-            return fail(B2R_ERR_CUDA);
-        }
-        pyr.push_back(l);
-        if (w <= 1 && h <= 1)
-            break;
-        w = std::max(1, w / 2);
-        h = std::max(1, h / 2);
-    }
-    auto describe = [&](const Lv& l) {
-        b2r_image im;
-        memset(&im, 0, sizeof(im));
-        im.pixels    = l.px;
-        im.basetype  = B2R_FLOAT;
-        im.nchannels = nch;
-        im.width = im.full_width = l.w;
-        im.height = im.full_height = l.h;
-        im.xstride  = (int64_t)nch * 4;
-        im.ystride  = (int64_t)l.w * nch * 4;
-        im.memspace = B2R_MEM_DEVICE;
-        im.device   = io.device;
-        return im;
-    };
-    b2r_options sub;
-    memset(&sub, 0, sizeof(sub));
-    sub.device      = io.device;
-    sub.cuda_stream = (void*)io.stream;
-    int launched    = 0;
-    {   // top = float copy of src shifted to the origin (paste, :1620-1634):
-        // a nearest resample between equal windows is the identity + conversion
-        b2r_image T = describe(pyr[0]);
-        b2r_image S = io.srcd;
-        S.pixels    = io.dsrc;
-        S.x = S.y = S.full_x = S.full_y = 0;
-        S.full_width  = S.width;
-        S.full_height = S.height;
-        S.memspace    = B2R_MEM_DEVICE;
-        S.device      = io.device;
-        rc = b2r_resample(&T, &S, 0, nullptr, &sub, nullptr, err, errlen);
-        if (rc)
-            return fail(rc);
-        ++launched;
-    }
-    for (size_t i = 1; i < pyr.size(); ++i) {
-        b2r_image D = describe(pyr[i]), S = describe(pyr[i - 1]);
-        rc = b2r_resize(&D, &S, "triangle", 0.0f, nullptr, &sub, nullptr, err, errlen);
-        if (rc)
-            return fail(rc);
-        launch_divide_by_alpha(pyr[i].px, (long long)pyr[i].w * pyr[i].h, nch, alpha_channel,
-                               io.stream);
-        launched += 3;
-    }
-    if (pyr.size() > 1) {
-        if (cudaMallocAsync((void**)&blow, size_t(W) * H * nch * 4, io.stream) != cudaSuccess) {
-            set_err(err, errlen, "fillholes_pushpull: out of device memory");
-            return fail(B2R_ERR_CUDA);
-        }
-        for (int i = (int)pyr.size() - 2; i >= 0; --i) {
-            Lv b { pyr[i].w, pyr[i].h, blow };
-            b2r_image D = describe(b), S = describe(pyr[i + 1]);
-            rc = b2r_resize(&D, &S, "triangle", 0.0f, nullptr, &sub, nullptr, err, errlen);
-            if (rc)
-                return fail(rc);
-            launch_over_inplace(pyr[i].px, blow, (long long)pyr[i].w * pyr[i].h, nch,
-                                alpha_channel, io.stream);
-            launched += 3;
-        }
-    }
-    {   // paste the finished top level back at src's origin, in dst's type
-        const b2r_image& D = io.dstd;
-        const int x0 = io.roi.xbegin, y0 = io.roi.ybegin;  // inside src's window
-        if (D.xstride != (int64_t)nch * basetype_size(D.basetype)) {
-            set_err(err, errlen, "destination pixels must be contiguous in x");
-            return fail(B2R_ERR_UNSUPPORTED);
-        }
-        unsigned char* dp = (unsigned char*)io.ddst + (long long)(y0 - D.y) * D.ystride
-                            + (long long)(x0 - D.x) * D.xstride;
-        const float* sp = pyr[0].px + ((size_t)(y0 - src->y) * W + (x0 - src->x)) * nch;
-        launch_convert_from_float(sp, (long long)W * nch * 4, dp, D.ystride, io.roi_w * nch,
-                                  io.roi_h, D.basetype, io.stream);
-        ++launched;
-    }
-    for (auto& l : pyr)
-        cudaFreeAsync(l.px, io.stream);
-    pyr.clear();
-    if (blow)
-        cudaFreeAsync(blow, io.stream);
-    blow = nullptr;
-    return io.end(*dst, report, launched, err, errlen);
-}
-
-
-// =========================================================================
-// computePixelStats / isMonochrome (imagebufalgo_compare.cpp:81-215, 539-600)
-// =========================================================================
-extern "C" int
-b2r_pixel_stats(const b2r_image* src, const b2r_roi* roi_in, b2r_pixel_stats_t* stats,
-                int nstats, int* is_monochrome, float mono_threshold, const b2r_options* opt,
-                char* err, size_t errlen)
-{
-    int rc = check_image(src, true, err, errlen);
-    if (rc)
-        return rc;
-    if (!stats || nstats < src->nchannels) {
-        set_err(err, errlen, "pixel_stats: need one stats record per channel (%d)",
-                src->nchannels);
-        return B2R_ERR_INVALID;
-    }
-    if (device_count_cached() <= 0) {
-        set_err(err, errlen,
-                "no CUDA device available: the B200 pixel statistics path has no CPU "
-                "fallback");
-        return B2R_ERR_NO_DEVICE;
-    }
-    const int nch = src->nchannels;
-    b2r_roi roi;
-    if (roi_in) {
-        roi        = *roi_in;
-        roi.chbegin = std::max(roi.chbegin, 0);
-        roi.chend  = std::min(roi.chend, nch);
-    } else {
-        roi = b2r_roi { src->x, src->x + src->width, src->y, src->y + src->height, 0, nch };
-    }
-    // PixelStats::reset
-    for (int c = 0; c < nch; ++c) {
-        memset(&stats[c], 0, sizeof(stats[c]));
-    }
-    if (is_monochrome)
-        *is_monochrome = 1;
-    // pixels of the ROI outside the data window read as black through the
-    // iterator; restrict to the window and account for them as zeros below
-    const int x0 = std::max(roi.xbegin, src->x), x1 = std::min(roi.xend, src->x + src->width);
-    const int y0 = std::max(roi.ybegin, src->y), y1 = std::min(roi.yend, src->y + src->height);
-    const long long roi_px = (long long)std::max(0, roi.xend - roi.xbegin)
-                             * std::max(0, roi.yend - roi.ybegin);
-    const long long in_px = (long long)std::max(0, x1 - x0) * std::max(0, y1 - y0);
-    std::vector<StatsPartial> total((size_t)nch);
-    for (auto& t : total) {
-        t.sum = t.sum2 = 0.0;
-        t.mn  = INFINITY;
-        t.mx  = -INFINITY;
-        t.finite = t.nan = t.inf = 0;
-    }
-    bool mono = true;
-    if (in_px > 0 && roi.chend > roi.chbegin) {
-        int dev = opt ? opt->device : 0;
-        const int mem = memspace_of(src, &dev);
-        if (dev < 0 || dev >= device_count_cached()) {
-            set_err(err, errlen, "invalid CUDA device ordinal %d", dev);
-            return B2R_ERR_INVALID;
-        }
-        DeviceGuard guard(dev);
-        device_info(dev);
-        cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
-        b2r_image S = *src;
-        void* spix  = src->pixels;
-        void* stage = nullptr;
-        const int es = basetype_size(src->basetype);
-        if (mem == B2R_MEM_HOST) {
-            if (src->xstride != (int64_t)nch * es) {
-                set_err(err, errlen, "host source pixels must be contiguous in x");
-                return B2R_ERR_UNSUPPORTED;
-            }
-            const size_t rowbytes = size_t(x1 - x0) * src->xstride;
-            const size_t pitch    = (rowbytes + 15) & ~size_t(15);
-            CUDA_TRY(cudaMallocAsync(&stage, pitch * (y1 - y0), stream));
-            const unsigned char* hp = (const unsigned char*)src->pixels
-                                      + (long long)(y0 - src->y) * src->ystride
-                                      + (long long)(x0 - src->x) * src->xstride;
-            CUDA_TRY(cudaMemcpy2DAsync(stage, pitch, hp, src->ystride, rowbytes, y1 - y0,
-                                       cudaMemcpyHostToDevice, stream));
-            S.x = x0, S.y = y0, S.width = x1 - x0, S.height = y1 - y0;
-            S.ystride = (int64_t)pitch;
-            spix      = stage;
-        }
-        const int nblocks = stats_grid_blocks(y1 - y0);
-        StatsPartial* dpart = nullptr;
-        int* dmono          = nullptr;
-        CUDA_TRY(cudaMallocAsync((void**)&dpart, sizeof(StatsPartial) * nblocks * nch, stream));
-        CUDA_TRY(cudaMallocAsync((void**)&dmono, sizeof(int) * nblocks, stream));
-        StatsParams sp;
-        memset(&sp, 0, sizeof(sp));
-        sp.src       = to_dev(S, spix);
-        sp.roi_x0    = x0, sp.roi_x1 = x1, sp.roi_y0 = y0, sp.roi_y1 = y1;
-        sp.chbegin   = roi.chbegin;
-        sp.chend     = roi.chend;
-        sp.nchannels = nch;
-        sp.partials  = dpart;
-        sp.want_mono = is_monochrome ? 1 : 0;
-        sp.mono_threshold = mono_threshold;
-        sp.mono_flags     = dmono;
-        launch_pixel_stats(sp, nblocks, stream);
-        std::vector<StatsPartial> hpart((size_t)nblocks * nch);
-        std::vector<int> hmono((size_t)nblocks, 1);
-        CUDA_TRY(cudaMemcpyAsync(hpart.data(), dpart, sizeof(StatsPartial) * hpart.size(),
-                                 cudaMemcpyDeviceToHost, stream));
-        if (is_monochrome)
-            CUDA_TRY(cudaMemcpyAsync(hmono.data(), dmono, sizeof(int) * nblocks,
-                                     cudaMemcpyDeviceToHost, stream));
-        cudaFreeAsync(dpart, stream);
-        cudaFreeAsync(dmono, stream);
-        if (stage)
-            cudaFreeAsync(stage, stream);
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        {
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) {
-                set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
-                return B2R_ERR_CUDA;
-            }
-        }
-        for (int b = 0; b < nblocks; ++b) {  // PixelStats::merge, in block order
-            for (int c = roi.chbegin; c < roi.chend; ++c) {
-                const StatsPartial& q = hpart[(size_t)b * nch + c];
-                StatsPartial& t       = total[c];
-                t.mn = std::min(t.mn, q.mn);
-                t.mx = std::max(t.mx, q.mx);
-                t.nan += q.nan, t.inf += q.inf, t.finite += q.finite;
-                t.sum += q.sum, t.sum2 += q.sum2;
-            }
-            mono = mono && hmono[b] != 0;
-        }
-    }
-    // black pixels of the ROI beyond the data window: value 0 in every channel
-    if (roi_px > in_px)
-        for (int c = roi.chbegin; c < roi.chend; ++c) {
-            total[c].finite += (unsigned long long)(roi_px - in_px);
-            total[c].mn = std::min(total[c].mn, 0.0f);
-            total[c].mx = std::max(total[c].mx, 0.0f);
-        }
-    for (int c = 0; c < nch; ++c) {  // finalize (:101-118)
-        const StatsPartial& t = total[c];
-        b2r_pixel_stats_t& o  = stats[c];
-        o.nancount    = (int64_t)t.nan;
-        o.infcount    = (int64_t)t.inf;
-        o.finitecount = (int64_t)t.finite;
-        o.sum         = t.sum;
-        o.sum2        = t.sum2;
-        if (t.finite == 0) {
-            o.min = o.max = o.avg = o.stddev = 0.0f;
-        } else {
-            const double count = double(t.finite);
-            const double davg  = t.sum / count;
-            const double var   = t.sum2 / count - davg * davg;
-            o.min    = t.mn;
-            o.max    = t.mx;
-            o.avg    = float(davg);
-            o.stddev = float(var > 0.0 ? sqrt(var) : 0.0);
-        }
-    }
-    if (is_monochrome)
-        *is_monochrome = (nch < 2 || mono) ? 1 : 0;
     return B2R_OK;
 }
