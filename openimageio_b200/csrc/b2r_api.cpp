@@ -141,6 +141,11 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
     hi = std::min(std::max(hi, hi_c), src.y + src.height - 1);
     if (hi < lo)
         lo = hi = src.y;  // nothing but black is visible: stage one row
+    // The kernels' row windows are rounded up (gather / expand read an even
+    // number of rows, shifted back inside the image at its bottom edge) and
+    // read those extra rows with zero weights: keep them inside what is staged.
+    lo = std::max(lo - 8, src.y);
+    hi = std::min(hi + 8, src.y + src.height - 1);
     *row0 = lo - src.y;
     *row1 = hi - src.y;
 }

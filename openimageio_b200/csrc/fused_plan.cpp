@@ -189,9 +189,23 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     P.interior_zero = gx.interior_zero || gy.interior_zero;
 
     const int W = gx.n, H = gy.n;
+    // An output whose footprint contributes nothing (all weights zero, or only
+    // black pixels) has no source index of its own: it borrows its
+    // predecessor's, and LEADING ones borrow the first real one -- never 0,
+    // which may lie outside the rows a host source had staged (only the span
+    // the taps can touch is uploaded) and would stretch the first strip.
+    int x_seed = -1, y_seed = -1;
+    for (int k = 0; k < W && x_seed < 0; ++k)
+        if (gx.count[k] > 0)
+            x_seed = gx.first[k];
+    for (int k = 0; k < H && y_seed < 0; ++k)
+        if (gy.count[k] > 0)
+            y_seed = gy.first[k];
+    if (x_seed < 0 || y_seed < 0)
+        return false;  // nothing contributes anywhere: the exact kernel writes the zeros
     std::vector<int32_t> cfirst(W);
     for (int k = 0; k < W; ++k) {
-        cfirst[k] = gx.count[k] > 0 ? gx.first[k] : (k > 0 ? cfirst[k - 1] : 0);
+        cfirst[k] = gx.count[k] > 0 ? gx.first[k] : (k > 0 ? cfirst[k - 1] : x_seed);
         if (k > 0 && cfirst[k] < cfirst[k - 1])
             return false;  // not monotone: leave it to the exact kernel
     }
@@ -202,7 +216,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
             first[k] = gy.first[k];
             last[k]  = gy.first[k] + gy.count[k] - 1;
         } else {
-            first[k] = last[k] = k > 0 ? last[k - 1] : 0;
+            first[k] = last[k] = k > 0 ? last[k - 1] : y_seed;
         }
         if (k > 0) {
             if (first[k] < first[k - 1])

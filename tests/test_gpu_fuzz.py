@@ -1,0 +1,159 @@
+"""Seeded differential fuzz of the resize path: random sizes (incl. 1-pixel
+axes and prime sizes), ratios from 8x down to 8x up (independently per axis),
+every filter, every native type pair, 1-5 channels, cropped /
+overscanned source windows, offset destination windows, partial ROIs, random
+filter widths -- CUDA path through the C ABI against the CPU oracle."""
+import numpy as np
+import pytest
+
+import synth
+from test_gpu_parity import run_both, check, _np_dtype
+
+pytestmark = pytest.mark.gpu
+
+FILTERS = ["", "box", "triangle", "gaussian", "sharp-gaussian", "catmull-rom",
+           "blackman-harris", "sinc", "lanczos3", "radial-lanczos3", "nuke-lanczos6",
+           "mitchell", "bspline", "disk", "cubic", "keys", "simon", "rifman"]
+TYPES = ["float", "half", "uint16", "uint8"]
+
+
+def _case(rng):
+    sw = int(rng.choice([1, 2, 3, 5, 17, 31, 64, 97, 128, 200, 257, 400]))
+    sh = int(rng.choice([1, 2, 3, 7, 16, 33, 64, 90, 131, 256, 300]))
+    rx = float(rng.choice([0.125, 0.25, 0.37, 0.5, 0.75, 1.0, 1.3, 2.0, 3.0, 4.0, 8.0]))
+    ry = float(rng.choice([0.125, 0.25, 0.4, 0.5, 0.8, 1.0, 1.5, 2.0, 2.5, 4.0, 8.0]))
+    dw = max(1, min(700, int(round(sw * rx))))
+    dh = max(1, min(700, int(round(sh * ry))))
+    nch = int(rng.choice([1, 2, 3, 4, 5]))
+    # the ten native (dst, src) pairs (the others are covered by
+    # test_non_native_type_pairs_go_through_float)
+    dt = str(rng.choice(TYPES))
+    st = str(rng.choice(TYPES)) if dt == "float" else str(rng.choice([dt, "float"]))
+    filt = str(rng.choice(FILTERS))
+    fw = float(rng.choice([0.0, 0.0, 0.0, 2.5, 5.0]))
+    src_win = dst_win = roi = None
+    if rng.rand() < 0.35:   # source data window != display window (crop or overscan)
+        ox, oy = int(rng.randint(-6, 7)), int(rng.randint(-6, 7))
+        src_win = (ox, oy, (0, 0, max(1, sw + int(rng.randint(-5, 6))),
+                            max(1, sh + int(rng.randint(-5, 6)))))
+    if rng.rand() < 0.35:   # destination data window inside / around its display window
+        ox, oy = int(rng.randint(-4, 5)), int(rng.randint(-4, 5))
+        dst_win = (ox, oy, (0, 0, max(1, dw + int(rng.randint(-3, 4))),
+                            max(1, dh + int(rng.randint(-3, 4)))))
+    if rng.rand() < 0.3:
+        dx, dy = (dst_win[0], dst_win[1]) if dst_win else (0, 0)
+        x0 = dx + int(rng.randint(0, max(1, dw // 2)))
+        y0 = dy + int(rng.randint(0, max(1, dh // 2)))
+        roi = (x0, min(dx + dw, x0 + 1 + int(rng.randint(0, dw))),
+               y0, min(dy + dh, y0 + 1 + int(rng.randint(0, dh))))
+    return dict(sw=sw, sh=sh, dw=dw, dh=dh, nch=nch, st=str(st), dt=str(dt), filt=filt,
+                fw=fw, src_win=src_win, dst_win=dst_win, roi=roi)
+
+
+@pytest.mark.parametrize("chunk", range(16))
+def test_resize_fuzz(oiio, oracle, chunk):
+    rng = np.random.RandomState(20261020 + chunk)
+    for k in range(60):
+        c = _case(rng)
+        src = synth.image(c["sw"], c["sh"], c["nch"], _np_dtype(c["st"]),
+                          seed=1000 * chunk + k)
+        pre = synth.image(c["dw"], c["dh"], c["nch"], _np_dtype(c["dt"]),
+                          seed=5000 + 1000 * chunk + k)
+        try:
+            g, o, _ = run_both(oiio, oracle, src, (c["dh"], c["dw"]), _np_dtype(c["dt"]),
+                               c["filt"], c["fw"], c["src_win"], c["dst_win"], c["roi"],
+                               prefill=pre)
+            check(g, o)
+        except AssertionError as e:
+            raise AssertionError("case %d/%d %r: %s" % (chunk, k, c, e))
+
+
+def test_regression_leading_rows_without_taps_host_source(oiio, oracle):
+    """Found by the fuzz: a fixed filter width under 4x upsizing leaves the
+    ROI's first dst rows with no contributing tap; the planner used to give
+    them source row 0, outside the rows staged for a host source."""
+    src = synth.image(257, 64, 2, np.float32, seed=1)
+    pre = synth.image(95, 256, 2, np.float16, seed=2)
+    g, o, rep = run_both(oiio, oracle, src, (256, 95), np.float16, "cubic", 2.5,
+                         None, None, (23, 24, 20, 220), prefill=pre)
+    check(g, o)
+
+
+# ---------------------------------------------------------------- resample ----
+@pytest.mark.parametrize("chunk", range(4))
+def test_resample_fuzz(oiio, oracle, chunk):
+    rng = np.random.RandomState(777 + chunk)
+    for k in range(40):
+        c = _case(rng)
+        src = synth.image(c["sw"], c["sh"], c["nch"], _np_dtype(c["st"]), seed=k)
+        interp = bool(rng.randint(0, 2))
+        ref = synth.image(c["dw"], c["dh"], c["nch"], _np_dtype(c["dt"]), seed=99 + k)
+        got = ref.copy()
+        sx, sy, sfull = c["src_win"] if c["src_win"] else (0, 0, None)
+        dx, dy, dfull = c["dst_win"] if c["dst_win"] else (0, 0, None)
+        oracle.resample(oracle.Img(ref, dx, dy, dfull), oracle.Img(src, sx, sy, sfull),
+                        interp, c["roi"])
+        S, D = oiio.ImageBuf(src), oiio.ImageBuf(got)
+        for B, (x, y, full), arr in ((S, (sx, sy, sfull), src), (D, (dx, dy, dfull), got)):
+            sp = B.spec()
+            sp.x, sp.y = x, y
+            (sp.full_x, sp.full_y, sp.full_width, sp.full_height) = \
+                full if full else (x, y, arr.shape[1], arr.shape[0])
+        r = c["roi"]
+        roi = oiio.ROI(r[0], r[1], r[2], r[3], 0, 1, 0, c["nch"]) if r else None
+        assert oiio.ImageBufAlgo.resample(D, S, interpolate=interp, roi=roi), D.geterror()
+        try:
+            check(got, ref, exact=(got.dtype == np.float32))
+        except AssertionError as e:
+            raise AssertionError("case %d/%d %r interp=%s: %s" % (chunk, k, c, interp, e))
+
+
+# -------------------------------------------------------------------- warp ----
+@pytest.mark.parametrize("chunk", range(4))
+def test_warp_fuzz(oiio, oracle, chunk):
+    """Random affine / projective matrices (rotation, anisotropic scale down to
+    1/6, shear, translation, mild perspective), every wrap mode, edgeclamp,
+    cropped source windows, ROIs, 1-5 channels, the positive filters (the
+    negative-lobe ones are ill-conditioned where a clipped footprint keeps
+    few taps, see test_st_warp_parity)."""
+    rng = np.random.RandomState(4242 + chunk)
+    for k in range(25):
+        sw, sh = int(rng.randint(8, 90)), int(rng.randint(8, 70))
+        dw, dh = int(rng.randint(4, 80)), int(rng.randint(4, 60))
+        nch = int(rng.choice([1, 2, 3, 4, 5]))
+        st = str(rng.choice(TYPES))
+        dt = str(rng.choice(TYPES))
+        filt = str(rng.choice(["box", "triangle", "gaussian", "bspline", "disk",
+                               "blackman-harris"]))
+        ang = rng.uniform(-3.14, 3.14)
+        sx_, sy_ = rng.uniform(0.17, 3.0), rng.uniform(0.17, 3.0)
+        shear = rng.uniform(-0.4, 0.4)
+        A = np.array([[np.cos(ang) * sx_, np.sin(ang) * sx_], [-np.sin(ang) * sy_ + shear,
+                                                               np.cos(ang) * sy_]])
+        persp = rng.uniform(-4e-4, 4e-4, 2) if rng.rand() < 0.4 else (0.0, 0.0)
+        M = np.array([[A[0, 0], A[0, 1], persp[0]], [A[1, 0], A[1, 1], persp[1]],
+                      [rng.uniform(-10, 30), rng.uniform(-10, 30), 1.0]], np.float32)
+        wrap = str(rng.choice(["default", "black", "clamp", "periodic", "mirror"]))
+        edgeclamp = bool(rng.rand() < 0.3)
+        src_win = None
+        if rng.rand() < 0.4:
+            src_win = (int(rng.randint(-5, 6)), int(rng.randint(-5, 6)),
+                       (0, 0, sw + int(rng.randint(-4, 8)), sh + int(rng.randint(-4, 8))))
+        roi = None
+        if rng.rand() < 0.3:
+            x0, y0 = int(rng.randint(0, dw)), int(rng.randint(0, dh))
+            roi = (x0, min(dw, x0 + 1 + int(rng.randint(0, dw))), y0,
+                   min(dh, y0 + 1 + int(rng.randint(0, dh))))
+        src = synth.image(sw, sh, nch, _np_dtype(st), seed=300 + k)
+        pre = synth.image(dw, dh, nch, _np_dtype(dt), seed=600 + k)
+        from test_gpu_warp import warp_both
+        try:
+            g, o = warp_both(oiio, oracle, src, (dh, dw), _np_dtype(dt), M, filt,
+                             wrap=wrap, edgeclamp=edgeclamp, src_win=src_win, roi=roi,
+                             prefill=pre)
+            check(g, o)
+        except AssertionError as e:
+            raise AssertionError("case %d/%d M=%r filt=%s wrap=%s ec=%s st=%s dt=%s nch=%d "
+                                 "src_win=%r roi=%r size=%r->%r: %s"
+                                 % (chunk, k, M.tolist(), filt, wrap, edgeclamp, st, dt, nch,
+                                    src_win, roi, (sw, sh), (dw, dh), e))
