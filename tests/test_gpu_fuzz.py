@@ -157,3 +157,101 @@ def test_warp_fuzz(oiio, oracle, chunk):
                                  "src_win=%r roi=%r size=%r->%r: %s"
                                  % (chunk, k, M.tolist(), filt, wrap, edgeclamp, st, dt, nch,
                                     src_win, roi, (sw, sh), (dw, dh), e))
+
+
+# ----------------------------------------------------- large shapes, banded ----
+@pytest.mark.parametrize("chunk", range(3))
+def test_resize_fuzz_large(oiio, oracle, chunk):
+    """Multi-strip / multi-band plans and the pipelined host path (>= 32 MB):
+    the whole image on the GPU, the oracle on a random band of rows."""
+    rng = np.random.RandomState(9000 + chunk)
+    for k in range(5):
+        sw, sh = int(rng.randint(900, 3300)), int(rng.randint(700, 2600))
+        rx = float(rng.choice([0.25, 0.4, 0.5, 0.77, 1.0, 1.6, 2.0]))
+        ry = float(rng.choice([0.25, 0.5, 0.5, 0.66, 1.0, 1.5, 2.0]))
+        dw, dh = max(8, int(sw * rx)), max(8, int(sh * ry))
+        if dw * dh > 12e6:
+            dw, dh = dw // 2, dh // 2
+        nch = int(rng.choice([1, 3, 4]))
+        dt = str(rng.choice(TYPES))
+        st = str(rng.choice(TYPES)) if dt == "float" else str(rng.choice([dt, "float"]))
+        filt = str(rng.choice(["", "lanczos3", "blackman-harris", "mitchell", "box",
+                               "gaussian", "catmull-rom"]))
+        src = synth.image(sw, sh, nch, _np_dtype(st), seed=40 + k)
+        got = np.zeros((dh, dw, nch), _np_dtype(dt))
+        D = oiio.ImageBuf(got)
+        assert oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(src), filtername=filt), D.geterror()
+        y0 = int(rng.randint(0, max(1, dh - 24)))
+        y1 = min(dh, y0 + 24)
+        ref = np.zeros_like(got)
+        oracle.resize(oracle.Img(ref), oracle.Img(src), filt, roi=(0, dw, y0, y1))
+        try:
+            check(got[y0:y1], ref[y0:y1])
+        except AssertionError as e:
+            raise AssertionError("case %d/%d %r: %s" % (chunk, k,
+                                 dict(sw=sw, sh=sh, dw=dw, dh=dh, nch=nch, st=st, dt=dt,
+                                      filt=filt, band=(y0, y1)), e))
+
+
+# --------------------------------------------------------------- MIP chain ----
+def test_mip_chain_fuzz(oiio, oracle):
+    """Odd, prime, 1-pixel-wide and non-square level-0 sizes; box (bit-exact:
+    both the 2x2 and the bilinear resize_block paths) and filtered chains."""
+    rng = np.random.RandomState(31337)
+    for k in range(24):
+        w = int(rng.choice([1, 2, 3, 5, 16, 33, 64, 100, 127, 255, 256]))
+        h = int(rng.choice([1, 2, 4, 7, 32, 50, 64, 99, 128, 200]))
+        if w == 1 and h == 1:
+            continue
+        nch = int(rng.choice([1, 2, 3, 4]))
+        filt = str(rng.choice(["box", "box", "lanczos3", "triangle", "blackman-harris"]))
+        lvl0 = synth.image(w, h, nch, np.float32, seed=70 + k)
+        ref = oracle.mip_chain(lvl0, filt)
+        chain = oiio.MipChain(lvl0, filt)
+        assert chain.nlevels == len(ref) + 1, (w, h, filt)
+        for i, r in enumerate(ref):
+            g = chain.download(i + 1)
+            assert g.shape == r.shape
+            if filt == "box":
+                assert np.array_equal(g, r), (w, h, nch, filt, i + 1)
+            else:
+                assert np.abs(g - r).max() <= 1e-5 * (i + 1), (w, h, nch, filt, i + 1)
+
+
+# ------------------------------------------------ convolve / fixNonFinite ----
+def test_convolve_unsharp_fuzz(oiio, oracle):
+    rng = np.random.RandomState(555)
+    IBA = oiio.ImageBufAlgo
+    for k in range(30):
+        w, h = int(rng.randint(1, 120)), int(rng.randint(1, 90))
+        nch = int(rng.choice([1, 2, 3, 4, 5, 7]))
+        st = str(rng.choice(TYPES))
+        src = synth.image(w, h, nch, _np_dtype(st), seed=800 + k)
+        name = str(rng.choice(["gaussian", "box", "triangle", "mitchell", "binomial", "disk"]))
+        kw = int(rng.choice([1, 3, 5, 7, 9]))
+        kh = int(rng.choice([1, 3, 5, 7]))
+        K, _ = oracle.make_kernel(name, kw, kh)
+        swin = None
+        if rng.rand() < 0.4:
+            swin = (int(rng.randint(-4, 5)), int(rng.randint(-4, 5)),
+                    (0, 0, w + int(rng.randint(0, 6)), h + int(rng.randint(0, 6))))
+        x, y, full = swin if swin else (0, 0, None)
+        ref = np.zeros_like(src)
+        got = np.zeros_like(src)
+        S, D = oiio.ImageBuf(src), oiio.ImageBuf(got)
+        for B in (S, D):
+            sp = B.spec()
+            sp.x, sp.y = x, y
+            (sp.full_x, sp.full_y, sp.full_width, sp.full_height) = \
+                full if full else (x, y, w, h)
+        if rng.rand() < 0.5:
+            oracle.convolve(oracle.Img(ref, x, y, full), oracle.Img(src, x, y, full), K)
+            assert IBA.convolve(D, S, IBA.make_kernel(name, kw, kh)), D.geterror()
+        else:
+            width = float(rng.choice([3.0, 3.0, 5.0]))
+            oracle.unsharp_mask(oracle.Img(ref, x, y, full), oracle.Img(src, x, y, full),
+                                name if name != "binomial" else "gaussian", width, 0.6, 0.01)
+            assert IBA.unsharp_mask(D, S, kernel=name if name != "binomial" else "gaussian",
+                                    width=width, contrast=0.6, threshold=0.01), D.geterror()
+        assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), \
+            (k, w, h, nch, st, name, kw, kh, swin)
