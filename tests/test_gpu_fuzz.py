@@ -255,3 +255,56 @@ def test_convolve_unsharp_fuzz(oiio, oracle):
                                     width=width, contrast=0.6, threshold=0.01), D.geterror()
         assert np.array_equal(got.view(np.uint8), ref.view(np.uint8)), \
             (k, w, h, nch, st, name, kw, kh, swin)
+
+
+# --------------------------------- device-resident, padded rows, misaligned ----
+@pytest.mark.parametrize("chunk", range(4))
+def test_resize_fuzz_device_strided(oiio, oracle, chunk):
+    """Device tensors that are views into larger allocations: padded row
+    strides, first pixel not 16-byte aligned (the vector-load / cp.async paths
+    must fall back), canary columns around the destination left untouched."""
+    import torch
+    rng = np.random.RandomState(6000 + chunk)
+    TT = {"float": torch.float32, "half": torch.float16, "uint8": torch.uint8,
+          "uint16": torch.uint16}
+
+    def up(a):
+        if a.dtype == np.uint16:
+            return torch.from_numpy(a.view(np.int16)).cuda().view(torch.uint16)
+        return torch.from_numpy(a).cuda()
+    for k in range(30):
+        c = _case(rng)
+        c["src_win"] = c["dst_win"] = None
+        src = synth.image(c["sw"], c["sh"], c["nch"], _np_dtype(c["st"]), seed=k)
+        pre = synth.image(c["dw"], c["dh"], c["nch"], _np_dtype(c["dt"]), seed=50 + k)
+        ref = pre.copy()
+        oracle.resize(oracle.Img(ref), oracle.Img(src), c["filt"], c["fw"], c["roi"])
+        padl, padr = int(rng.randint(0, 4)), int(rng.randint(0, 5))
+        sbig = torch.zeros((c["sh"], c["sw"] + padl + padr, c["nch"]), dtype=TT[c["st"]],
+                           device="cuda")
+        sview = sbig[:, padl:padl + c["sw"]]
+        sview.copy_(up(src))
+        dpl, dpr = int(rng.randint(0, 4)), int(rng.randint(0, 5))
+        dbig = torch.zeros((c["dh"], c["dw"] + dpl + dpr, c["nch"]), dtype=TT[c["dt"]],
+                           device="cuda")
+        if TT[c["dt"]] in (torch.uint8,):
+            dbig.fill_(77)
+        dview = dbig[:, dpl:dpl + c["dw"]]
+        dview.copy_(up(pre))
+        before = dbig.clone()
+        r = c["roi"]
+        roi = oiio.ROI(r[0], r[1], r[2], r[3], 0, 1, 0, c["nch"]) if r else None
+        D = oiio.ImageBuf(dview)
+        ok = oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(sview), filtername=c["filt"],
+                                      filterwidth=c["fw"], roi=roi)
+        assert ok, (c, D.geterror())
+        got = D.get_pixels()
+        try:
+            check(np.ascontiguousarray(got), ref)
+        except AssertionError as e:
+            raise AssertionError("case %d/%d %r pads=%r: %s"
+                                 % (chunk, k, c, (padl, padr, dpl, dpr), e))
+        # canaries: the padding columns are exactly as before
+        b8 = lambda t: t.contiguous().view(torch.uint8)
+        assert torch.equal(b8(dbig[:, :dpl]), b8(before[:, :dpl]))
+        assert torch.equal(b8(dbig[:, dpl + c["dw"]:]), b8(before[:, dpl + c["dw"]:]))
