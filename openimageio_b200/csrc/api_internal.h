@@ -6,6 +6,7 @@
 
 #include "b2r.h"
 
+#include "host_copy.h"
 #include "kernels.h"
 #include "recon_filter.h"
 
@@ -265,8 +266,8 @@ struct StencilIO {
             const size_t rowbytes = size_t(src.width) * src.xstride;
             const size_t pitch    = (rowbytes + 15) & ~size_t(15);
             CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * src.height, stream));
-            CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
-                                       src.height, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
+                                       src.height, stream));
             srcd.ystride = (int64_t)pitch;
             dsrc         = src_alloc;
             if (report)
@@ -284,8 +285,8 @@ struct StencilIO {
                        + (long long)(roi.ybegin - dst.y) * dst.ystride
                        + (long long)(roi.xbegin - dst.x) * dst.xstride;
             if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
-                CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
-                                           roi_h, cudaMemcpyHostToDevice, stream));
+                CUDA_TRY(copy_h2d_2d(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
+                                           roi_h, stream));
                 if (report)
                     report->h2d_bytes += (int64_t)drowbytes * roi_h;
             }
@@ -314,8 +315,8 @@ struct StencilIO {
             return B2R_ERR_CUDA;
         }
         if (dst_alloc) {
-            CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
-                                       roi_h, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(copy_d2h_2d(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
+                                       roi_h, stream));
             if (report)
                 report->d2h_bytes += (int64_t)drowbytes * roi_h;
         }
@@ -355,8 +356,8 @@ struct StencilIO {
         const size_t rowbytes = size_t(im.width) * im.xstride;
         const size_t pitch    = (rowbytes + 15) & ~size_t(15);
         CUDA_TRY(cudaMallocAsync(&extra_alloc, pitch * im.height, stream));
-        CUDA_TRY(cudaMemcpy2DAsync(extra_alloc, pitch, im.pixels, im.ystride, rowbytes,
-                                   im.height, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(copy_h2d_2d(extra_alloc, pitch, im.pixels, im.ystride, rowbytes,
+                                   im.height, stream));
         imd->ystride = (int64_t)pitch;
         *dpix        = extra_alloc;
         if (report)

@@ -6,6 +6,7 @@
 // rule of OIIO_DISPATCH_COMMON_TYPES2 (imagebufalgo_util.h:463-552) and the
 // call into resize_<D,S> (:595-826) -- here two CUDA kernels instead.
 #include "api_internal.h"
+#include "host_copy.h"
 
 #include "axis_plan.h"
 #include "fused_plan.h"
@@ -429,8 +430,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                 launch_convert_from_float((const float*)ftmp, (long long)frow, dtmp,
                                           (long long)drow, roi_w * dst.nchannels,
                                           roi_h, dst.basetype, stream);
-                CUDA_TRY(cudaMemcpy2DAsync(out, dst.ystride, dtmp, drow, drow, roi_h,
-                                           cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(copy_d2h_2d(out, dst.ystride, dtmp, drow, drow, roi_h, stream));
                 CUDA_TRY(cudaFreeAsync(dtmp, stream));
                 if (report)
                     report->d2h_bytes += (int64_t)drow * roi_h;
@@ -487,11 +487,10 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         src_bytes       = pitch * nrows;
         CUDA_TRY(cudaMallocAsync(&src_alloc, src_bytes, stream));
         src_staged = true;
-        CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch,
+        CUDA_TRY(copy_h2d_2d(src_alloc, pitch,
                                    (const unsigned char*)src.pixels
                                        + (long long)r0 * src.ystride,
-                                   src.ystride, rowbytes, nrows,
-                                   cudaMemcpyHostToDevice, stream));
+                                   src.ystride, rowbytes, nrows, stream));
         // virtual origin: row r of the data window lives at dsrc + r*pitch;
         // rows outside [r0, r0+nrows) are never addressed
         dsrc         = (unsigned char*)src_alloc - (long long)r0 * (long long)pitch;
@@ -665,8 +664,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         unsigned char* hp = (unsigned char*)dst.pixels
                             + (long long)(roi.ybegin - dst.y) * dst.ystride
                             + (long long)(roi.xbegin - dst.x) * dst.xstride;
-        CUDA_TRY(cudaMemcpy2DAsync(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h,
-                                   cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(copy_d2h_2d(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
     }
@@ -725,127 +723,6 @@ pipe_streams(int dev)
     return p;
 }
 
-// ---- pageable host memory ------------------------------------------------
-// An ImageBuf normally owns pageable memory.  cudaMemcpyAsync from / to it is
-// staged by the driver through one thread (~9 GB/s measured: 58 ms for the
-// 8K frame against 10.4 ms from pinned memory).  Instead, rows are copied by a
-// few host threads into / out of a small ring of pinned bounce buffers (kept
-// per device) and the DMA engine only ever sees pinned memory.
-bool
-host_is_pinned(const void* p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
-}
-
-int
-host_copy_threads()
-{
-    static const int n = [] {
-        if (const char* e = getenv("B2R_COPY_THREADS")) {
-            int v = atoi(e);
-            if (v > 0)
-                return std::min(v, 64);
-        }
-        unsigned hc = std::thread::hardware_concurrency();
-        return (int)std::max(1u, std::min(8u, hc / 2));
-    }();
-    return n;
-}
-
-// rows x rowbytes, split over host threads
-void
-parallel_copy_rows(unsigned char* d, size_t dpitch, const unsigned char* s, size_t spitch,
-                   size_t rowbytes, int nrows)
-{
-    const int nt = (size_t)nrows * rowbytes < (size_t(1) << 20)
-                       ? 1
-                       : std::min(host_copy_threads(), nrows);
-    auto work = [=](int t) {
-        const int a = (int)((long long)nrows * t / nt), b = (int)((long long)nrows * (t + 1) / nt);
-        if (dpitch == rowbytes && spitch == rowbytes) {
-            memcpy(d + (size_t)a * dpitch, s + (size_t)a * spitch, (size_t)(b - a) * rowbytes);
-            return;
-        }
-        for (int r = a; r < b; ++r)
-            memcpy(d + (size_t)r * dpitch, s + (size_t)r * spitch, rowbytes);
-    };
-    if (nt == 1) {
-        work(0);
-        return;
-    }
-    std::vector<std::thread> th;
-    int started = 1;  // part 0 runs on this thread
-    try {
-        th.reserve(nt - 1);
-        for (; started < nt; ++started)
-            th.emplace_back(work, started);
-    } catch (...) {
-        // no more threads to be had: this thread does the parts not handed out
-    }
-    work(0);
-    for (int t = started; t < nt; ++t)
-        work(t);
-    for (auto& x : th)
-        x.join();
-}
-
-constexpr int BOUNCE_SLOTS = 3;
-struct BounceRing {
-    void* buf[BOUNCE_SLOTS]      = { nullptr, nullptr, nullptr };
-    size_t cap                   = 0;
-    cudaEvent_t done[BOUNCE_SLOTS] = { nullptr, nullptr, nullptr };  // last DMA on the slot
-    bool busy[BOUNCE_SLOTS]      = { false, false, false };
-    // make every slot at least `bytes` large (idle ring only)
-    bool reserve(size_t bytes)
-    {
-        if (bytes <= cap)
-            return true;
-        for (int i = 0; i < BOUNCE_SLOTS; ++i) {
-            if (buf[i])
-                cudaFreeHost(buf[i]);
-            buf[i] = nullptr;
-            if (!done[i])
-                cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-        }
-        cap = 0;
-        for (int i = 0; i < BOUNCE_SLOTS; ++i)
-            if (cudaHostAlloc(&buf[i], bytes, cudaHostAllocDefault) != cudaSuccess) {
-                cudaGetLastError();
-                return false;
-            }
-        cap = bytes;
-        return true;
-    }
-    // the slot is free again once the DMA that used it has finished
-    void* acquire(int i)
-    {
-        if (busy[i]) {
-            cudaEventSynchronize(done[i]);
-            busy[i] = false;
-        }
-        return buf[i];
-    }
-    void release_after(int i, cudaStream_t st)
-    {
-        cudaEventRecord(done[i], st);
-        busy[i] = true;
-    }
-};
-struct Bounce {
-    BounceRing in, out;
-};
-Bounce&
-bounce_rings(int dev)
-{
-    static Bounce b[64];
-    return b[dev & 63];  // used under the device's pipe mutex
-}
-
 int
 resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
                       const Filter2D& filter, const b2r_roi& roi, int device,
@@ -865,7 +742,7 @@ resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
     static std::mutex pipe_mutex[64];
     std::lock_guard<std::mutex> lock(pipe_mutex[device & 63]);
     PipeStreams& ps = pipe_streams(device);
-    Bounce& bounce          = bounce_rings(device);
+    Bounce& bounce          = pipeline_bounce(device);
 
     // source rows each band touches (band + filter halo)
     std::vector<b2r_roi> bands(nbands);
@@ -1042,8 +919,8 @@ resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
     cudaStreamSynchronize(ps.in);
     cudaStreamSynchronize(ps.k);
     cudaError_t es = cudaStreamSynchronize(ps.out);
-    for (int q = 0; q < BOUNCE_SLOTS; ++q)
-        bounce.in.busy[q] = bounce.out.busy[q] = false;  // everything has completed
+    bounce.in.idle();  // everything has completed
+    bounce.out.idle();
     cudaFreeAsync(salloc, ps.k);
     cudaFreeAsync(dalloc, ps.k);
     cudaEventDestroy(ready);
@@ -1469,8 +1346,8 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
             const unsigned char* hp = (const unsigned char*)src.pixels
                                       + (long long)(y0 - src.y) * src.ystride
                                       + (long long)(x0 - src.x) * src.xstride;
-            CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, hp, src.ystride, rowbytes,
-                                       srcd.height, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(src_alloc, pitch, hp, src.ystride, rowbytes,
+                                       srcd.height, stream));
             srcd.ystride = (int64_t)pitch;
             if (report)
                 report->h2d_bytes += (int64_t)rowbytes * srcd.height;
@@ -1495,8 +1372,8 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
                    + (long long)(roi.xbegin - dst.x) * dst.xstride;
         if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
             // channels outside the range keep what dst holds
-            CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
-                                       roi_h, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
+                                       roi_h, stream));
             if (report)
                 report->h2d_bytes += (int64_t)drowbytes * roi_h;
         }
@@ -1526,8 +1403,8 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
         }
     }
     if (dst_alloc) {
-        CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
-                                   roi_h, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(copy_d2h_2d(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
+                                   roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
         CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
@@ -1665,9 +1542,8 @@ resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Fil
         unsigned char* hp = (unsigned char*)dst.pixels
                             + (long long)(roi.ybegin - dst.y) * dst.ystride
                             + (long long)(roi.xbegin - dst.x) * dst.xstride;
-        cudaError_t e = cudaMemcpy2DAsync(hp, dst.ystride, dpix, D.ystride,
-                                          size_t(roi_w) * dst.xstride, roi_h,
-                                          cudaMemcpyDeviceToHost, stream);
+        cudaError_t e = copy_d2h_2d(hp, dst.ystride, dpix, D.ystride,
+                                          size_t(roi_w) * dst.xstride, roi_h, stream);
         if (e != cudaSuccess) {
             set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
             rc = B2R_ERR_CUDA;
@@ -1807,8 +1683,7 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
                 launch_convert_from_float((const float*)ftmp, (long long)frow, dtmp,
                                           (long long)drow, roi_w * dst.nchannels,
                                           roi_h, dst.basetype, stream);
-                CUDA_TRY(cudaMemcpy2DAsync(out, dst.ystride, dtmp, drow, drow, roi_h,
-                                           cudaMemcpyDeviceToHost, stream));
+                CUDA_TRY(copy_d2h_2d(out, dst.ystride, dtmp, drow, drow, roi_h, stream));
                 CUDA_TRY(cudaFreeAsync(dtmp, stream));
             }
         }
@@ -1832,8 +1707,8 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
         size_t pitch    = (rowbytes + 15) & ~size_t(15);
         CUDA_TRY(cudaMallocAsync(&dsrc, pitch * src.height, stream));
         src_staged = true;
-        CUDA_TRY(cudaMemcpy2DAsync(dsrc, pitch, src.pixels, src.ystride, rowbytes,
-                                   src.height, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(copy_h2d_2d(dsrc, pitch, src.pixels, src.ystride, rowbytes,
+                                   src.height, stream));
         srcd.ystride = (int64_t)pitch;
         if (report)
             report->h2d_bytes += (int64_t)rowbytes * src.height;
@@ -1854,8 +1729,8 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
             unsigned char* hp = (unsigned char*)dst.pixels
                                 + (long long)(roi.ybegin - dst.y) * dst.ystride
                                 + (long long)(roi.xbegin - dst.x) * dst.xstride;
-            CUDA_TRY(cudaMemcpy2DAsync(ddst, dpitch, hp, dst.ystride, drowbytes,
-                                       roi_h, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(ddst, dpitch, hp, dst.ystride, drowbytes,
+                                       roi_h, stream));
         }
         dstd.x       = roi.xbegin;
         dstd.y       = roi.ybegin;
@@ -1898,8 +1773,7 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
         unsigned char* hp = (unsigned char*)dst.pixels
                             + (long long)(roi.ybegin - dst.y) * dst.ystride
                             + (long long)(roi.xbegin - dst.x) * dst.xstride;
-        CUDA_TRY(cudaMemcpy2DAsync(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h,
-                                   cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(copy_d2h_2d(hp, dst.ystride, ddst, dpitch, drowbytes, roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
     }
@@ -2044,9 +1918,13 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
         }
         l0.owned = true;
         chain->levels.push_back(l0);
-        cudaError_t e = cudaMemcpy2DAsync(l0.px, row0, level0->pixels,
-                                          level0->ystride, row0, level0->height,
-                                          cudaMemcpyDefault, stream);
+        // host level 0 (pageable or pinned) or a strided device image
+        cudaError_t e = (mem == B2R_MEM_HOST)
+                            ? copy_h2d_2d(l0.px, row0, level0->pixels, level0->ystride, row0,
+                                          level0->height, stream)
+                            : cudaMemcpy2DAsync(l0.px, row0, level0->pixels, level0->ystride,
+                                                row0, level0->height, cudaMemcpyDefault,
+                                                stream);
         if (e != cudaSuccess) {
             set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
             return fail(B2R_ERR_CUDA);
@@ -2262,8 +2140,14 @@ b2r_mipchain_download(const b2r_mipchain* chain, int level, const b2r_image* out
     }
     DeviceGuard guard(chain->device);
     size_t row = size_t(l.w) * chain->nch * 4;
-    CUDA_TRY(cudaMemcpy2D(out->pixels, out->ystride, l.px, row, row, l.h,
-                          cudaMemcpyDefault));
+    int odev = 0;
+    if (memspace_of(out, &odev) == B2R_MEM_HOST) {
+        CUDA_TRY(copy_d2h_2d(out->pixels, out->ystride, l.px, row, row, l.h, nullptr));
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+    } else {
+        CUDA_TRY(cudaMemcpy2D(out->pixels, out->ystride, l.px, row, row, l.h,
+                              cudaMemcpyDefault));
+    }
     return B2R_OK;
 }
 

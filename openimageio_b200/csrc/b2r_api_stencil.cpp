@@ -1,6 +1,7 @@
 // b2r_api_stencil.cpp -- part of the C ABI (include/b2r.h): make_kernel / convolve / unsharp_mask, fixNonFinite, fillholes_pushpull,
 // computePixelStats.
 #include "api_internal.h"
+#include "host_copy.h"
 
 #include "conv_kernel.h"
 #include "xform_matrix.h"
@@ -572,8 +573,7 @@ b2r_pixel_stats(const b2r_image* src, const b2r_roi* roi_in, b2r_pixel_stats_t* 
             const unsigned char* hp = (const unsigned char*)src->pixels
                                       + (long long)(y0 - src->y) * src->ystride
                                       + (long long)(x0 - src->x) * src->xstride;
-            CUDA_TRY(cudaMemcpy2DAsync(stage, pitch, hp, src->ystride, rowbytes, y1 - y0,
-                                       cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(stage, pitch, hp, src->ystride, rowbytes, y1 - y0, stream));
             S.x = x0, S.y = y0, S.width = x1 - x0, S.height = y1 - y0;
             S.ystride = (int64_t)pitch;
             spix      = stage;

@@ -1,5 +1,6 @@
 // b2r_api_warp.cpp -- part of the C ABI (include/b2r.h): warp / rotate / fit(exact) / --resize:from/to and st_warp.
 #include "api_internal.h"
+#include "host_copy.h"
 
 #include "conv_kernel.h"
 #include "xform_matrix.h"
@@ -97,8 +98,8 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
         const size_t rowbytes = size_t(src.width) * src.xstride;
         const size_t pitch    = (rowbytes + 15) & ~size_t(15);
         CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * src.height, stream));
-        CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
-                                   src.height, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(copy_h2d_2d(src_alloc, pitch, src.pixels, src.ystride, rowbytes,
+                                   src.height, stream));
         srcd.ystride = (int64_t)pitch;
         dsrc         = src_alloc;
         if (report)
@@ -119,8 +120,8 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
                    + (long long)(roi.xbegin - dst.x) * dst.xstride;
         if (roi.chbegin != 0 || roi.chend != dst.nchannels) {
             // channels outside the range keep what dst holds
-            CUDA_TRY(cudaMemcpy2DAsync(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
-                                       roi_h, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(copy_h2d_2d(dst_alloc, dpitch, host_out, dst.ystride, drowbytes,
+                                       roi_h, stream));
             if (report)
                 report->h2d_bytes += (int64_t)drowbytes * roi_h;
         }
@@ -168,8 +169,8 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
         }
     }
     if (dst_alloc) {
-        CUDA_TRY(cudaMemcpy2DAsync(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
-                                   roi_h, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(copy_d2h_2d(host_out, dst.ystride, dst_alloc, dpitch, drowbytes,
+                                   roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
         CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
@@ -340,8 +341,8 @@ st_warp_impl(const b2r_image* dst, const b2r_image* src, const b2r_image* st,
                          || r.ybegin != io.roi.ybegin || r.yend != io.roi.yend
                          || io.roi.chbegin != 0 || io.roi.chend != dst->nchannels)) {
         // part of the staged dst ROI will not be written: bring its pixels over
-        cudaMemcpy2DAsync(io.dst_alloc, io.dpitch, io.host_out, dst->ystride, io.drowbytes,
-                          io.roi_h, cudaMemcpyHostToDevice, io.stream);
+        copy_h2d_2d(io.dst_alloc, io.dpitch, io.host_out, dst->ystride, io.drowbytes,
+                          io.roi_h, io.stream);
     }
     b2r_image std_;
     void* dst_pix = nullptr;
