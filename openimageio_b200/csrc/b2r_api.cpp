@@ -288,30 +288,50 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     return B2R_OK;
 }
 
-// Ring of redo flags per device.  A call gets a slot and a fresh, non-zero
-// epoch: the fused kernel writes the epoch into the slot when it sees a
-// non-finite output, the gated exact kernel runs only if the slot holds that
-// epoch.  Stale values of earlier calls never match, so nothing is cleared and
-// no memset node is needed per call.
-int*
-next_flag(int dev, int* epoch)
+// Ring of redo slots per device.  A call gets a slot -- one flag plus a dirty
+// map -- and a fresh, non-zero epoch: the fused kernel writes the epoch into
+// the flag when it sees a non-finite output and into the map cell (128 columns
+// x 2^yshift rows of the ROI) that holds the pixel; the gated exact kernel
+// runs only if the flag holds that epoch and re-does only the cells that do.
+// Stale values of earlier calls never match, so nothing is cleared and no
+// memset node is needed per call.
+constexpr int REDO_SLOTS     = 256;
+constexpr int REDO_MAP_CELLS = 16384;  // ints per slot (64 KB)
+struct RedoSlot {
+    int* flag  = nullptr;
+    int* dirty = nullptr;
+    int epoch  = 0;
+};
+RedoSlot
+next_flag(int dev)
 {
     struct Ring {
-        int* base = nullptr;
+        int* flags = nullptr;
+        int* maps  = nullptr;
         unsigned next = 0;
     };
     static Ring rings[64];
     static std::mutex m;
     std::lock_guard<std::mutex> lock(m);
     Ring& r = rings[dev & 63];
-    if (!r.base) {
-        if (cudaMalloc((void**)&r.base, 256 * sizeof(int)) != cudaSuccess)
-            return nullptr;
-        cudaMemset(r.base, 0, 256 * sizeof(int));
+    RedoSlot s;
+    if (!r.flags) {
+        const size_t map_bytes = size_t(REDO_SLOTS) * REDO_MAP_CELLS * sizeof(int);
+        if (cudaMalloc((void**)&r.flags, REDO_SLOTS * sizeof(int)) != cudaSuccess)
+            return s;
+        if (cudaMalloc((void**)&r.maps, map_bytes) != cudaSuccess) {
+            cudaFree(r.flags);
+            r.flags = nullptr;
+            return s;
+        }
+        cudaMemset(r.flags, 0, REDO_SLOTS * sizeof(int));
+        cudaMemset(r.maps, 0, map_bytes);
     }
     unsigned n = r.next++;
-    *epoch     = int((n & 0x3fffffffu) + 1);
-    return r.base + (n & 255);
+    s.epoch    = int((n & 0x3fffffffu) + 1);
+    s.flag     = r.flags + (n % REDO_SLOTS);
+    s.dirty    = r.maps + size_t(n % REDO_SLOTS) * REDO_MAP_CELLS;
+    return s;
 }
 
 int
@@ -623,21 +643,34 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             // per-call flag from a per-device ring (plans are shared between
             // concurrent calls); the gated exact kernel leaves it cleared, so
             // no memset node is needed per call
-            flag = next_flag(device, &epoch);
+            RedoSlot slot = next_flag(device);
+            flag          = slot.flag;
+            epoch         = slot.epoch;
             if (!flag) {
                 set_err(err, errlen, "CUDA error: cannot allocate the redo flags");
                 return B2R_ERR_CUDA;
             }
             fp.nonfinite_flag  = flag;
             fp.nonfinite_epoch = epoch;
+            // dirty-map geometry: 128-column cells, as few rows per cell as
+            // the map has room for (16 at least)
+            fp.dirty        = slot.dirty;
+            fp.dirty_xcells = (roi_w + 127) / 128;
+            fp.dirty_yshift = 4;
+            while ((long long)fp.dirty_xcells * (((long long)roi_h >> fp.dirty_yshift) + 1)
+                   > REDO_MAP_CELLS)
+                ++fp.dirty_yshift;
         }
         launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,
                             plan->fp.max_nvec, stream);
         ++launched;
         used = B2R_PATH_FUSED;
         if (src_is_fp) {
-            ep.gate       = flag;  // runs only if a non-finite output was seen
-            ep.gate_value = epoch;
+            ep.gate         = flag;  // runs only if a non-finite output was seen
+            ep.gate_value   = epoch;
+            ep.dirty        = fp.dirty;  // ... and only over the cells that hold one
+            ep.dirty_xcells = fp.dirty_xcells;
+            ep.dirty_yshift = fp.dirty_yshift;
             launch_resize_exact(ep, stream);
             ++launched;
         }

@@ -213,7 +213,7 @@ store_group(unsigned char* dp, int align, int nvalid, const float (&o)[N])
 template<int NCH, int NR, int DT>
 __device__ __forceinline__ bool
 store_rows(const FusedParams& p, const GroupAcc<NCH> (&acc)[NR], unsigned char* dp,
-           int nrows, int ncols)
+           int nrows, int ncols, int x0, int y0)
 {
     constexpr int N = 4 * NCH;
     bool bad = false;
@@ -227,7 +227,14 @@ store_rows(const FusedParams& p, const GroupAcc<NCH> (&acc)[NR], unsigned char* 
 #pragma unroll
                 for (int i = 0; i < N; ++i)
                     t += o[i];  // Inf/NaN in any element survives the sum
-                bad |= !(fabsf(t) <= 3.402823466e+38f);
+                if (!(fabsf(t) <= 3.402823466e+38f)) {
+                    bad = true;
+                    // mark the cell(s) of the dirty map this group of four
+                    // columns touches: the gated exact kernel re-does only those
+                    int* row = p.dirty + ((y0 + k) >> p.dirty_yshift) * p.dirty_xcells;
+                    row[x0 >> DIRTY_CELL_SHIFT_X]                   = p.nonfinite_epoch;
+                    row[(x0 + ncols - 1) >> DIRTY_CELL_SHIFT_X] = p.nonfinite_epoch;
+                }
             }
             store_group<N, DT>(dp, p.dst_align, ncols * NCH, o);
         }
@@ -274,13 +281,13 @@ expand_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb, 
         // one type dispatch per NR rows
         const int nrows = nb - rb;
         if (dt == BT_UINT8)
-            bad |= store_rows<NCH, NR, BT_UINT8>(p, acc, dp, nrows, ncols);
+            bad |= store_rows<NCH, NR, BT_UINT8>(p, acc, dp, nrows, ncols, dx0, dyb + rb);
         else if (dt == BT_FLOAT)
-            bad |= store_rows<NCH, NR, BT_FLOAT>(p, acc, dp, nrows, ncols);
+            bad |= store_rows<NCH, NR, BT_FLOAT>(p, acc, dp, nrows, ncols, dx0, dyb + rb);
         else if (dt == BT_HALF)
-            bad |= store_rows<NCH, NR, BT_HALF>(p, acc, dp, nrows, ncols);
+            bad |= store_rows<NCH, NR, BT_HALF>(p, acc, dp, nrows, ncols, dx0, dyb + rb);
         else
-            bad |= store_rows<NCH, NR, BT_UINT16>(p, acc, dp, nrows, ncols);
+            bad |= store_rows<NCH, NR, BT_UINT16>(p, acc, dp, nrows, ncols, dx0, dyb + rb);
         dp += (long long)NR * p.dst_ystride;
     }
     if (bad)

@@ -362,7 +362,13 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
                 ob[c] = cb[c];
                 t += ca[c] + cb[c];  // Inf/NaN in any channel survives the sum
             }
-            bad |= !(fabsf(t) <= 3.402823466e+38f);
+            if (p.check_nonfinite && !(fabsf(t) <= 3.402823466e+38f)) {
+                bad = true;
+                // the gated exact kernel re-does only the marked cells
+                p.dirty[((dyb + hr + k * ROWG) >> p.dirty_yshift) * p.dirty_xcells
+                        + (dxA >> DIRTY_CELL_SHIFT_X)]
+                    = p.nonfinite_epoch;
+            }
             store_pixel<NCH>(p, dp, des, oa);
             if (has_b)
                 store_pixel<NCH>(p, dp + NCH * des, des, ob);

@@ -81,22 +81,10 @@ dev_nonsep_filter(int kind, float fw, float fh, float x, float y)
 
 constexpr int EXACT_CH = 4;  // channels per thread
 
-__global__ void __launch_bounds__(128)
-resize_exact_kernel(ExactParams p)
+// One destination pixel (kx, ky: ROI-relative), channels [c0, c0 + EXACT_CH).
+__device__ __forceinline__ void
+exact_pixel(const ExactParams& p, int kx, int ky, int c0)
 {
-    pdl_prologue();
-    if (p.gate && *p.gate != p.gate_value)
-        return;
-    const int roi_w   = p.roi_x1 - p.roi_x0;
-    const int roi_h   = p.roi_y1 - p.roi_y0;
-    const int xblocks = (roi_w + blockDim.x - 1) / blockDim.x;
-    const int c0      = blockIdx.z * EXACT_CH;
-    for (long long tile = blockIdx.x; tile < (long long)xblocks * roi_h;
-         tile += gridDim.x) {
-    const int kx = int(tile % xblocks) * blockDim.x + threadIdx.x;
-    const int ky = int(tile / xblocks);
-    if (kx >= roi_w)
-        continue;
     const int nc  = min(EXACT_CH, p.nch - c0);
     const int ses = (p.src.basetype == BT_UINT8) ? 1 : (p.src.basetype == BT_FLOAT ? 4 : 2);
     const int des = (p.dst.basetype == BT_UINT8) ? 1 : (p.dst.basetype == BT_FLOAT ? 4 : 2);
@@ -184,7 +172,44 @@ resize_exact_kernel(ExactParams p)
     for (int c = 0; c < EXACT_CH; ++c)
         if (c < nc)
             store_elem(dp + c * des, p.dst.basetype, zero_out ? 0.0f : pel[c]);
-    }  // tile loop
+}
+
+__global__ void __launch_bounds__(128)
+resize_exact_kernel(ExactParams p)
+{
+    pdl_prologue();
+    if (p.gate && *p.gate != p.gate_value)
+        return;
+    const int roi_w = p.roi_x1 - p.roi_x0;
+    const int roi_h = p.roi_y1 - p.roi_y0;
+    const int c0    = blockIdx.z * EXACT_CH;
+    if (p.gate && p.dirty) {
+        // redo pass: only the cells the fused kernel marked (a cell is 128
+        // columns x 2^yshift rows; blockDim.x == 128)
+        const int cell_h = 1 << p.dirty_yshift;
+        const int ycells = (roi_h + cell_h - 1) >> p.dirty_yshift;
+        for (int cell = blockIdx.x; cell < p.dirty_xcells * ycells; cell += gridDim.x) {
+            if (p.dirty[cell] != p.gate_value)
+                continue;
+            const int cy = cell / p.dirty_xcells, cx = cell - cy * p.dirty_xcells;
+            const int kx = (cx << DIRTY_CELL_SHIFT_X) + threadIdx.x;
+            if (kx >= roi_w)
+                continue;
+            // the rows of a cell are spread over gridDim.y CTAs
+            const int y1 = min(roi_h, (cy + 1) << p.dirty_yshift);
+            for (int ky = (cy << p.dirty_yshift) + blockIdx.y; ky < y1; ky += gridDim.y)
+                exact_pixel(p, kx, ky, c0);
+        }
+        return;
+    }
+    const int xblocks = (roi_w + blockDim.x - 1) / blockDim.x;
+    for (long long tile = blockIdx.x; tile < (long long)xblocks * roi_h;
+         tile += gridDim.x) {
+        const int kx = int(tile % xblocks) * blockDim.x + threadIdx.x;
+        const int ky = int(tile / xblocks);
+        if (kx < roi_w)
+            exact_pixel(p, kx, ky, c0);
+    }
 }
 
 void
@@ -199,9 +224,18 @@ launch_resize_exact(const ExactParams& p, void* stream)
     // gated off by *p.gate == 0 retires in a few microseconds
     // a gated launch (redo path) uses a small grid so that the usual case --
     // flag clear, every CTA exits at once -- costs as little as possible
-    const long long cap = p.gate ? 148 * 2 : 148 * 16;
+    // (the redo pass walks dirty-map cells: a few per CTA at most)
+    const long long cap = p.gate ? 148 * 4 : 148 * 16;
     dim3 grid((unsigned)std::min<long long>(tiles, cap), 1,
               (p.nch + EXACT_CH - 1) / EXACT_CH);
+    if (p.gate && p.dirty) {
+        // redo pass: x walks the dirty-map cells, y splits a cell's rows
+        const int cell_h = 1 << p.dirty_yshift;
+        const long long ncells
+            = (long long)p.dirty_xcells * ((roi_h + cell_h - 1) >> p.dirty_yshift);
+        grid.y = 16;
+        grid.x = (unsigned)std::max<long long>(1, std::min<long long>(ncells, cap / 16));
+    }
     launch_pdl(resize_exact_kernel, grid, block, 0, (cudaStream_t)stream, p);
 }
 

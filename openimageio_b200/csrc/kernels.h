@@ -87,6 +87,11 @@ struct ExactParams {
     // when not null: run only if *gate == gate_value (non-finite redo)
     const int* gate;
     int gate_value;
+    // gated runs re-do only the cells of the ROI the fused kernel marked:
+    // cell (cx, cy) = 128 columns x (1 << dirty_yshift) rows, marked when
+    // dirty[cy * dirty_xcells + cx] == gate_value
+    const int* dirty;
+    int dirty_xcells, dirty_yshift;
 };
 void
 launch_resize_exact(const ExactParams& p, void* stream);
@@ -144,6 +149,8 @@ constexpr int EXPAND_BATCH  = 8;    // V-filtered rows between the passes
 constexpr int EXPAND_MAXVT  = 8;    // widest V window (rows held in registers)
 constexpr int EXPAND_FIFO   = 4;    // raw source rows in flight per thread
 
+constexpr int DIRTY_CELL_SHIFT_X = 7;  // 128 dst columns per dirty-map cell
+
 struct FusedParams {
     const unsigned char* src;  // data-window origin, pixels contiguous in x
     long long src_ystride;
@@ -158,6 +165,10 @@ struct FusedParams {
     int check_nonfinite;         // float/half sources: flag non-finite outputs
     int* nonfinite_flag;
     int nonfinite_epoch;         // value written to the flag (unique per call)
+    // ... and to the cell of the dirty map that holds the offending pixel
+    // (128 columns x (1 << dirty_yshift) rows of the ROI per cell)
+    int* dirty;
+    int dirty_xcells, dirty_yshift;
 
     int nstrips, nbands;
     const Strip* strips;

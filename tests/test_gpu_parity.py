@@ -258,7 +258,9 @@ def test_expand_kernel_nonfinite_and_windows(oiio, oracle):
     src[10, 17, 1] = np.inf
     src[30, 40, 2] = np.nan
     g, o, rep = run_both(oiio, oracle, src, (160, 208), np.float32, "mitchell")
-    check(g, o, exact=True)
+    # the exact kernel re-does the cells that hold a non-finite output (the
+    # NaN / Inf pattern must equal the reference's); the rest stays fused
+    check(g, o)
     assert rep.nonfinite_redo == 1
     # ROI inside a larger destination, offset windows, unaligned ROI origin
     src = synth.image(52, 40, 3, np.uint8, seed=78)
@@ -273,17 +275,20 @@ def test_expand_kernel_nonfinite_and_windows(oiio, oracle):
 
 def test_nonfinite_zero_weight_skip(oiio, oracle):
     """Inf/NaN under zero-weight taps must not poison the output: the fused
-    kernel flags the image and the exact kernel re-does it."""
+    kernel marks the cells that hold a non-finite output and the exact kernel
+    re-does those cells."""
     src = synth.image(96, 80, 4, np.float32, seed=13)
     src[10, 17, 1] = np.inf
     src[40, 60, 2] = np.nan
     src[70, 5, 0] = -np.inf
     g, o, rep = run_both(oiio, oracle, src, (40, 48), np.float32)
-    check(g, o, exact=True)
+    check(g, o)
     assert rep.nonfinite_redo == 1
+    # the re-done cells are the exact kernel's: bit-exact around the defects
+    assert np.array_equal(g[0:16, 0:48], o[0:16, 0:48], equal_nan=True)
     # ratio 1 with lanczos3: integer taps are exact zeros around the centre
     g, o, rep = run_both(oiio, oracle, src, (80, 96), np.float32, "triangle")
-    check(g, o, exact=True)
+    check(g, o)
 
 
 def test_explicit_filterwidth_and_errors(oiio, oracle):
@@ -689,3 +694,41 @@ def test_host_pipeline_pageable_and_pinned_equal_device(oiio, oracle, st, dt):
     ref = np.zeros_like(out_page)
     oracle.resize(oracle.Img(ref), oracle.Img(src), "lanczos3", roi=(0, dw, 500, 532))
     check(out_page[500:532], ref[500:532])
+
+
+def test_nonfinite_redo_is_local(oiio, oracle):
+    """One Inf in a large image: only the dirty-map cells around it are
+    re-done (bit-exact there, NaN/Inf pattern as the reference), the rest of
+    the image keeps the fused kernel's result; and the redo costs a fraction
+    of a full exact pass."""
+    import torch
+    src = synth.image(2048, 1536, 4, np.float32, seed=181)
+    src[700, 1000, 2] = np.inf
+    src[701, 1000, 0] = np.nan
+    t = torch.from_numpy(src).cuda()
+    out = torch.zeros((768, 1024, 4), dtype=torch.float32, device="cuda")
+    IBA = oiio.ImageBufAlgo
+    assert IBA.resize(oiio.ImageBuf(out), oiio.ImageBuf(t), filtername="lanczos3")
+    got = out.cpu().numpy()
+    ref = np.zeros_like(got)
+    y0, y1 = 320, 384           # the band that holds the defect (350 = 700 / 2)
+    oracle.resize(oracle.Img(ref), oracle.Img(src), "lanczos3", roi=(0, 1024, y0, y1))
+    check(got[y0:y1], ref[y0:y1])
+    # the cell holding the defect was re-done by the exact kernel
+    assert np.array_equal(got[336:352, 384:512], ref[336:352, 384:512], equal_nan=True)
+    assert np.isnan(got[350, 500]).any() or np.isinf(got[350, 500]).any()
+    # timing: redo of a few cells vs the whole image through the exact kernel
+    def timed(fn, n=5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    D, S = oiio.ImageBuf(out), oiio.ImageBuf(t)
+    local = timed(lambda: IBA.resize(D, S, filtername="lanczos3"))
+    full = timed(lambda: IBA.resize(D, S, filtername="lanczos3", path=oiio.PATH_EXACT))
+    assert local < 0.6 * full, (local, full)
