@@ -464,6 +464,120 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         return rc;
     }
 
+    // More than four channels (multi-layer EXRs): the fused kernels handle up
+    // to four, and the single-pass exact kernel is ~170x slower on a large
+    // frame.  Split into groups of <= 4 channels on the device, run each group
+    // through the normal path, put the results back.  Separable filters only
+    // (the exact kernel keeps the non-separable ones), equal channel counts.
+    if (nch > 4 && src.nchannels == nch && filter.separable() && path != B2R_PATH_EXACT
+        && !(opt && opt->reserved[0]) && src.xstride == (int64_t)nch * ses
+        && dst.xstride == (int64_t)nch * des) {
+        void *s_all = nullptr, *d_all = nullptr, *ts = nullptr, *td = nullptr;
+        auto cleanup = [&]() {
+            for (void* p : { s_all, d_all, ts, td })
+                if (p)
+                    cudaFreeAsync(p, stream);
+        };
+        // the whole interleaved source on the device
+        const unsigned char* sbase = (const unsigned char*)src.pixels;
+        long long s_ys             = src.ystride;
+        if (smem == B2R_MEM_HOST) {
+            const size_t rowb = size_t(src.width) * src.xstride;
+            if (cudaMallocAsync(&s_all, rowb * src.height, stream) != cudaSuccess
+                || copy_h2d_2d(s_all, rowb, src.pixels, src.ystride, rowb, src.height, stream)
+                       != cudaSuccess) {
+                cleanup();
+                set_err(err, errlen, "CUDA error staging the source");
+                return B2R_ERR_CUDA;
+            }
+            sbase = (const unsigned char*)s_all;
+            s_ys  = (long long)rowb;
+            if (report)
+                report->h2d_bytes += (int64_t)rowb * src.height;
+        }
+        // the interleaved dst ROI on the device
+        unsigned char* dbase = (unsigned char*)dst.pixels
+                               + (long long)(roi.ybegin - dst.y) * dst.ystride
+                               + (long long)(roi.xbegin - dst.x) * dst.xstride;
+        long long d_ys = dst.ystride;
+        const size_t drowb = size_t(roi_w) * dst.xstride;
+        if (dmem == B2R_MEM_HOST) {
+            if (cudaMallocAsync(&d_all, drowb * roi_h, stream) != cudaSuccess) {
+                cleanup();
+                set_err(err, errlen, "CUDA error allocating the destination");
+                return B2R_ERR_CUDA;
+            }
+            dbase = (unsigned char*)d_all;
+            d_ys  = (long long)drowb;
+        }
+        if (cudaMallocAsync(&ts, size_t(src.width) * src.height * 4 * ses, stream) != cudaSuccess
+            || cudaMallocAsync(&td, size_t(roi_w) * roi_h * 4 * des, stream) != cudaSuccess) {
+            cleanup();
+            set_err(err, errlen, "CUDA error allocating the channel-group images");
+            return B2R_ERR_CUDA;
+        }
+        b2r_options sub;
+        memset(&sub, 0, sizeof(sub));
+        sub.device      = device;
+        sub.path        = path;
+        sub.cuda_stream = (void*)stream;
+        sub.reserved[1] = 1;
+        int launched    = 0;
+        b2r_report last;
+        memset(&last, 0, sizeof(last));
+        for (int c0 = 0; c0 < nch && rc == B2R_OK; c0 += 4) {
+            const int ns = std::min(4, nch - c0);
+            b2r_image TS = src, TD = dst;
+            TS.pixels    = ts;
+            TS.nchannels = ns;
+            TS.xstride   = (int64_t)ns * ses;
+            TS.ystride   = TS.xstride * src.width;
+            TS.memspace  = B2R_MEM_DEVICE;
+            TS.device    = device;
+            TD.pixels    = td;
+            TD.nchannels = ns;
+            TD.x         = roi.xbegin;
+            TD.y         = roi.ybegin;
+            TD.width     = roi_w;
+            TD.height    = roi_h;
+            TD.xstride   = (int64_t)ns * des;
+            TD.ystride   = TD.xstride * roi_w;
+            TD.memspace  = B2R_MEM_DEVICE;
+            TD.device    = device;
+            launch_pixel_bytes_copy(ts, TS.xstride, TS.ystride, sbase + (size_t)c0 * ses,
+                                    src.xstride, s_ys, src.width, src.height, ns * ses, stream);
+            b2r_roi r = roi;
+            r.chbegin = 0;
+            r.chend   = ns;
+            rc = resize_impl(&TD, &TS, filter, &r, &sub, &last, err, errlen);
+            launch_pixel_bytes_copy(dbase + (size_t)c0 * des, dst.xstride, d_ys, td, TD.xstride,
+                                    TD.ystride, roi_w, roi_h, ns * des, stream);
+            launched += 2 + last.kernels_launched;
+        }
+        if (rc == B2R_OK && dmem == B2R_MEM_HOST) {
+            unsigned char* hp = (unsigned char*)dst.pixels
+                                + (long long)(roi.ybegin - dst.y) * dst.ystride
+                                + (long long)(roi.xbegin - dst.x) * dst.xstride;
+            if (copy_d2h_2d(hp, dst.ystride, d_all, drowb, drowb, roi_h, stream) != cudaSuccess) {
+                set_err(err, errlen, "CUDA error copying the result back");
+                rc = B2R_ERR_CUDA;
+            }
+            if (report)
+                report->d2h_bytes += (int64_t)drowb * roi_h;
+        }
+        cleanup();
+        if (rc == B2R_OK && (smem == B2R_MEM_HOST || dmem == B2R_MEM_HOST))
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        if (report && rc == B2R_OK) {
+            const int64_t h2d = report->h2d_bytes, d2h = report->d2h_bytes;
+            *report                  = last;
+            report->h2d_bytes        = h2d;
+            report->d2h_bytes        = d2h;
+            report->kernels_launched = launched;
+        }
+        return rc;
+    }
+
     // Large host -> host resize: run it as a pipeline of row bands so the
     // upload of later source rows, the kernels and the download of finished
     // rows overlap (PCIe is full duplex; the copies dominate end to end).

@@ -347,6 +347,13 @@ stats_grid_blocks(int rows);
 void
 launch_pixel_stats(const StatsParams& p, int nblocks, void* stream);
 
+// copy `nbytes` bytes of every pixel (a channel group) between two images with
+// independent pixel / row strides
+void
+launch_pixel_bytes_copy(void* dst, long long dst_xstride, long long dst_ystride,
+                        const void* src, long long src_xstride, long long src_ystride,
+                        int width, int height, int nbytes, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

@@ -556,4 +556,47 @@ launch_clamp(float* pixels, long long n, int nch, int alpha, float lo, float hi,
         pixels, n, nch, alpha, lo, hi);
 }
 
+// ------------------------------------------------------------------------
+// Channel-group copy: `nbytes` bytes of every pixel from src to dst (each
+// with its own pixel / row strides).  Splits an N-channel image into <= 4
+// channel groups for the fused kernel and puts the results back.
+// ------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+pixel_bytes_copy_kernel(unsigned char* dst, long long dxs, long long dys,
+                        const unsigned char* src, long long sxs, long long sys, int w, int h,
+                        int nbytes)
+{
+    pdl_prologue();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w)
+        return;
+    for (int y = blockIdx.y; y < h; y += gridDim.y) {
+        unsigned char* d       = dst + y * dys + x * dxs;
+        const unsigned char* s = src + y * sys + x * sxs;
+        if (((nbytes | (uintptr_t)d | (uintptr_t)s) & 3) == 0) {
+            for (int i = 0; i < nbytes; i += 4)
+                *(unsigned*)(d + i) = __ldg((const unsigned*)(s + i));
+        } else if (((nbytes | (uintptr_t)d | (uintptr_t)s) & 1) == 0) {
+            for (int i = 0; i < nbytes; i += 2)
+                *(unsigned short*)(d + i) = __ldg((const unsigned short*)(s + i));
+        } else {
+            for (int i = 0; i < nbytes; ++i)
+                d[i] = __ldg(s + i);
+        }
+    }
+}
+}  // namespace
+
+void
+launch_pixel_bytes_copy(void* dst, long long dxs, long long dys, const void* src, long long sxs,
+                        long long sys, int w, int h, int nbytes, void* stream)
+{
+    if (w <= 0 || h <= 0 || nbytes <= 0)
+        return;
+    dim3 grid((w + 255) / 256, std::min(h, 32768), 1);
+    launch_pdl(pixel_bytes_copy_kernel, grid, dim3(256), 0, (cudaStream_t)stream,
+               (unsigned char*)dst, dxs, dys, (const unsigned char*)src, sxs, sys, w, h, nbytes);
+}
+
 }  // namespace b2r

@@ -732,3 +732,25 @@ def test_nonfinite_redo_is_local(oiio, oracle):
     local = timed(lambda: IBA.resize(D, S, filtername="lanczos3"))
     full = timed(lambda: IBA.resize(D, S, filtername="lanczos3", path=oiio.PATH_EXACT))
     assert local < 0.6 * full, (local, full)
+
+
+@pytest.mark.parametrize("nch", [5, 6, 9])
+@pytest.mark.parametrize("st,dt", [("float", "float"), ("uint8", "uint8"), ("half", "float")])
+def test_more_than_four_channels_split_into_groups(oiio, oracle, nch, st, dt):
+    """Multi-layer images: channel groups of <= 4 go through the fused kernel
+    (the report says so) and are put back; ROI and prefill respected; host and
+    device-resident."""
+    import torch
+    src = synth.image(130, 90, nch, _np_dtype(st), seed=191)
+    pre = synth.image(65, 45, nch, _np_dtype(dt), seed=192)
+    g, o, rep = run_both(oiio, oracle, src, (45, 65), _np_dtype(dt), "lanczos3",
+                         roi=(3, 60, 2, 40), prefill=pre)
+    check(g, o)
+    assert rep.path_used == oiio.PATH_FUSED
+    if dt != "uint16" and st != "uint16":
+        def up(a):
+            return torch.from_numpy(a).cuda()
+        D = oiio.ImageBuf(up(pre))
+        assert oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(up(src)), filtername="lanczos3",
+                                        roi=oiio.ROI(3, 60, 2, 40, 0, 1, 0, nch))
+        assert np.array_equal(D.get_pixels().view(np.uint8), g.view(np.uint8))
