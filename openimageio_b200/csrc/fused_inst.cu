@@ -21,6 +21,10 @@ pick_ht(int ht)
     case 14: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 14>;
     case 16: return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 16>;
     }
+    // wide H windows (strong minification): one run-time-tap-count variant per
+    // ring size, only where it can occur (downsizing: ring mode)
+    if (VK > 0 && ht > 16 && ht <= FUSED_MAX_HT && ht % 4 == 0)
+        return resize_fused_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 0>;
     return nullptr;
 }
 

@@ -333,8 +333,7 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
 #pragma unroll
     for (int k = 0; k < NR; ++k)
         aA[k] = aB[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < HT; ++j) {
+    auto tap = [&](int j) {
         const float2 w   = hws[j * FUSED_HPAIRS];
         const float2 wwA = make_float2(w.x, w.x), wwB = make_float2(w.y, w.y);
 #pragma unroll
@@ -345,6 +344,21 @@ fused_hpass(const FusedParams& p, const unsigned char* vrows, int nb, int dyb,
                 vrows + k * ROWG * FUSED_PITCH_B + hb[j & 3] + (j >> 2) * 16);
             fma4(aA[k], wwA, v);
             fma4(aB[k], wwB, v);
+        }
+    };
+    if constexpr (HT > 0) {
+#pragma unroll
+        for (int j = 0; j < HT; ++j)
+            tap(j);
+    } else {
+        // HT == 0: wide windows (strong minification), tap count at run time
+        // (a multiple of 4), four taps per trip
+#pragma unroll 1
+        for (int j = 0; j < p.ht; j += 4) {
+            tap(j);
+            tap(j + 1);
+            tap(j + 2);
+            tap(j + 3);
         }
     }
     unsigned char* dp = p.dst + (long long)(dyb + hr) * p.dst_ystride
@@ -414,8 +428,9 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         // ring mode: staged with cp.async (joins the group of the ring
         // weights below, completes with the first FIFO row) so the table
         // loads overlap the first source rows' latency
-        for (int j = hr; j < HT; j += FUSED_HROWG_MAX) {
-            const float2* g = reinterpret_cast<const float2*>(p.hw) + (size_t)gp * HT + j;
+        const int ht = HT > 0 ? HT : p.ht;  // HT == 0: run-time window (<= 64 taps)
+        for (int j = hr; j < ht; j += FUSED_HROWG_MAX) {
+            const float2* g = reinterpret_cast<const float2*>(p.hw) + (size_t)gp * ht + j;
             if (2 * hp >= strip.ndx)
                 hws_all[j * FUSED_HPAIRS + hp] = make_float2(0.f, 0.f);
             else if (VK > 0)
@@ -469,7 +484,8 @@ resize_fused_kernel(const FusedParams p, int max_band_rows, int max_band_dy)
         constexpr int SLOT = FUSED_THREADS * TB;  // bytes between FIFO rows
         // fixed-offset regions first, so their addresses are compile-time
         // offsets from the dynamic shared memory base
-        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B + HT * FUSED_HPAIRS * 8;
+        unsigned char* fifo = smem_raw + BATCH * FUSED_PITCH_B
+                              + (HT > 0 ? HT : p.ht) * FUSED_HPAIRS * 8;
         float* ringw = reinterpret_cast<float*>(fifo + NFIFO * SLOT);
         int* lastr   = reinterpret_cast<int*>(ringw + (size_t)max_band_rows * VKP);
 

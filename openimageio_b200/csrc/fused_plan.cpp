@@ -14,6 +14,10 @@ round_taps(int n)
     for (int t : { 4, 6, 8, 10, 14, 16 })
         if (n <= t)
             return t;
+    // wider windows (strong minification) run the variant whose tap count is
+    // a run-time multiple of four
+    if (n <= FUSED_MAX_HT)
+        return (n + 3) & ~3;
     return 0;
 }
 
