@@ -123,7 +123,7 @@ fused_batch(int vk)
     return vk == 6 ? 12 : 8;
 }
 constexpr int FUSED_FIFO    = 8;    // source rows in flight per thread (power of 2)
-constexpr int FUSED_MAX_HT  = 64;   // widest H window (taps) of the run-time-HT variant
+constexpr int FUSED_MAX_HT  = 128;  // widest H window (taps) of the run-time-HT variant
 #if defined(__CUDACC__)
 #    define B2R_HD __host__ __device__
 #else
