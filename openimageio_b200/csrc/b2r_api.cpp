@@ -468,9 +468,12 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     // to four, and the single-pass exact kernel is ~170x slower on a large
     // frame.  Split into groups of <= 4 channels on the device, run each group
     // through the normal path, put the results back.  Separable filters only
-    // (the exact kernel keeps the non-separable ones), equal channel counts.
-    if (nch > 4 && src.nchannels == nch && filter.separable() && path != B2R_PATH_EXACT
-        && !(opt && opt->reserved[0]) && src.xstride == (int64_t)nch * ses
+    // (the exact kernel keeps the non-separable ones).
+    // The same split serves a source with MORE channels than the destination
+    // (resize_ reads the first dst.nchannels of them): the group copy drops
+    // the extra ones.
+    if ((nch > 4 || src.nchannels > nch) && filter.separable() && path != B2R_PATH_EXACT
+        && !(opt && opt->reserved[0]) && src.xstride == (int64_t)src.nchannels * ses
         && dst.xstride == (int64_t)nch * des) {
         void *s_all = nullptr, *d_all = nullptr, *ts = nullptr, *td = nullptr;
         auto cleanup = [&]() {

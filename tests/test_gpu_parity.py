@@ -754,3 +754,16 @@ def test_more_than_four_channels_split_into_groups(oiio, oracle, nch, st, dt):
         assert oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(up(src)), filtername="lanczos3",
                                         roi=oiio.ROI(3, 60, 2, 40, 0, 1, 0, nch))
         assert np.array_equal(D.get_pixels().view(np.uint8), g.view(np.uint8))
+
+
+def test_source_with_more_channels_than_destination(oiio, oracle):
+    """resize_ reads the first dst.nchannels channels of a wider source; the
+    channel-group copy drops the rest and the fused kernel runs."""
+    src = synth.image(120, 80, 4, np.float32, seed=195)
+    ref = np.zeros((40, 60, 3), np.float32)
+    oracle.resize(oracle.Img(ref), oracle.Img(np.ascontiguousarray(src[..., :3])), "lanczos3")
+    got = np.zeros_like(ref)
+    D = oiio.ImageBuf(got)
+    assert oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(src), filtername="lanczos3"), D.geterror()
+    check(got, ref)
+    assert oiio.ImageBufAlgo.last_report.path_used == oiio.PATH_FUSED
