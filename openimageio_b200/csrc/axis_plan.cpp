@@ -60,12 +60,27 @@ build_axis_taps(const AxisGeom& g, const Filter2D& filter, bool is_y)
 }
 
 bool
-build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out)
+axis_overscan(const AxisGeom& g)
+{
+    return g.src_data_begin < g.src_full_origin
+           || g.src_data_end > g.src_full_origin + g.src_full_size;
+}
+
+bool
+build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
+                  bool other_axis_overscan)
 {
     const int full_lo = g.src_full_origin;
     const int full_hi = g.src_full_origin + g.src_full_size - 1;
-    if (g.src_data_begin < full_lo || g.src_data_end - 1 > full_hi)
-        return false;  // overscan: WrapClamp addressing is not separable
+    // Overscan (data window beyond the display window): a tap outside the
+    // data window is clamped in BOTH axes, which is not separable.  But where
+    // every contributing tap of every output lies inside the data window the
+    // reference just reads the pixels themselves: such ranges (the interior of
+    // the image) are accepted, anything else is left to the exact kernel.
+    // The same holds when only the OTHER axis is overscanned: a tap outside
+    // the data window on this axis drags the other coordinate to the display
+    // window too.
+    const bool overscan = other_axis_overscan || axis_overscan(g);
     const int n = taps.n();
     out->n      = n;
     out->first.assign(n, 0);
@@ -85,7 +100,9 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out)
             if (w[i] == 0.0f)
                 continue;
             int idx = taps.center[k] - taps.rad + i;
-            int c   = std::min(std::max(idx, full_lo), full_hi);
+            if (overscan && (idx < g.src_data_begin || idx >= g.src_data_end))
+                return false;
+            int c = overscan ? idx : std::min(std::max(idx, full_lo), full_hi);
             if (c < g.src_data_begin || c >= g.src_data_end)
                 continue;  // black pixel
             lo = std::min(lo, c);
@@ -99,7 +116,7 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out)
             if (w[i] == 0.0f)
                 continue;
             int idx = taps.center[k] - taps.rad + i;
-            int c   = std::min(std::max(idx, full_lo), full_hi);
+            int c   = overscan ? idx : std::min(std::max(idx, full_lo), full_hi);
             if (c < g.src_data_begin || c >= g.src_data_end)
                 continue;
             merged[c - lo] += w[i];

@@ -61,7 +61,13 @@ struct AxisGather {
 
 // Valid when the source data window lies inside its full window on this
 // axis (then WrapClamp addressing is separable); returns false otherwise.
+// With overscan on either axis (data window beyond the display window) only
+// ranges whose contributing taps ALL lie inside the data window are accepted
+// (pass the other axis' axis_overscan() as `other_axis_overscan`).
 bool
-build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out);
+axis_overscan(const AxisGeom& g);
+bool
+build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
+                  bool other_axis_overscan = false);
 
 }  // namespace b2r

@@ -214,7 +214,8 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
            o_vf = 0, o_vw = 0;
     if (filter.separable()) {
         AxisGather ax, ay;
-        bool ok = build_axis_gather(gx, tx, &ax) && build_axis_gather(gy, ty, &ay)
+        bool ok = build_axis_gather(gx, tx, &ax, axis_overscan(gy))
+                  && build_axis_gather(gy, ty, &ay, axis_overscan(gx))
                   && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
                                 &plan->fp)
                   && plan_supported(src.basetype, nch, plan->fp);
@@ -462,6 +463,75 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         if (rc == B2R_OK && (dmem == B2R_MEM_HOST || smem == B2R_MEM_HOST))
             CUDA_TRY(cudaStreamSynchronize(stream));
         return rc;
+    }
+
+    // Overscan (source data window beyond its display window): only outputs
+    // whose taps all lie inside the data window are separable (axis_plan.cpp).
+    // On the device, cut the ROI into that interior -- which the fused kernel
+    // takes -- and the thin frame around it, which stays with the exact kernel.
+    if (smem == B2R_MEM_DEVICE && dmem == B2R_MEM_DEVICE && filter.separable()
+        && path == B2R_PATH_AUTO && !(opt && (opt->reserved[0] || opt->reserved[2]))
+        && (src.x < src.full_x || src.y < src.full_y
+            || src.x + src.width > src.full_x + src.full_width
+            || src.y + src.height > src.full_y + src.full_height)) {
+        AxisGeom gx { roi.xbegin, roi.xend, dst.full_x, dst.full_width, src.full_x,
+                      src.full_width, src.x, src.x + src.width };
+        AxisGeom gy { roi.ybegin, roi.yend, dst.full_y, dst.full_height, src.full_y,
+                      src.full_height, src.y, src.y + src.height };
+        AxisTaps tx = build_axis_taps(gx, filter, false);
+        AxisTaps ty = build_axis_taps(gy, filter, true);
+        auto interior = [](const AxisTaps& t, int data_begin, int data_end, int* a, int* b) {
+            const int n = t.n();
+            int lo = 0, hi = n;
+            while (lo < n && t.center[lo] - t.rad < data_begin)
+                ++lo;
+            while (hi > lo && t.center[hi - 1] + t.rad > data_end - 1)
+                --hi;
+            for (int k = lo; k < hi; ++k)  // centres are monotone; be safe anyway
+                if (t.center[k] - t.rad < data_begin || t.center[k] + t.rad > data_end - 1)
+                    hi = k;
+            *a = lo, *b = hi;
+        };
+        int xa, xb, ya, yb;
+        interior(tx, src.x, src.x + src.width, &xa, &xb);
+        interior(ty, src.y, src.y + src.height, &ya, &yb);
+        if (xb - xa >= 64 && yb - ya >= 64) {
+            const int X0 = roi.xbegin + xa, X1 = roi.xbegin + xb;
+            const int Y0 = roi.ybegin + ya, Y1 = roi.ybegin + yb;
+            const b2r_roi parts[5] = {
+                { X0, X1, Y0, Y1, roi.chbegin, roi.chend },                  // interior
+                { roi.xbegin, roi.xend, roi.ybegin, Y0, roi.chbegin, roi.chend },  // top
+                { roi.xbegin, roi.xend, Y1, roi.yend, roi.chbegin, roi.chend },    // bottom
+                { roi.xbegin, X0, Y0, Y1, roi.chbegin, roi.chend },          // left
+                { X1, roi.xend, Y0, Y1, roi.chbegin, roi.chend },            // right
+            };
+            b2r_options sub;
+            memset(&sub, 0, sizeof(sub));
+            if (opt)
+                sub = *opt;
+            sub.device      = device;
+            sub.cuda_stream = (void*)stream;
+            sub.reserved[2] = 1;  // private: do not split again
+            b2r_report first, part;
+            memset(&first, 0, sizeof(first));
+            int launched = 0;
+            for (int i = 0; i < 5 && rc == B2R_OK; ++i) {
+                if (parts[i].xend <= parts[i].xbegin || parts[i].yend <= parts[i].ybegin)
+                    continue;
+                rc = resize_impl(dst_in, src_in, filter, &parts[i], &sub,
+                                 report ? &part : nullptr, err, errlen);
+                if (report) {
+                    launched += part.kernels_launched;
+                    if (i == 0)
+                        first = part;
+                }
+            }
+            if (report && rc == B2R_OK) {
+                *report                  = first;
+                report->kernels_launched = launched;
+            }
+            return rc;
+        }
     }
 
     // More than four channels (multi-layer EXRs): the fused kernels handle up

@@ -767,3 +767,42 @@ def test_source_with_more_channels_than_destination(oiio, oracle):
     assert oiio.ImageBufAlgo.resize(D, oiio.ImageBuf(src), filtername="lanczos3"), D.geterror()
     check(got, ref)
     assert oiio.ImageBufAlgo.last_report.path_used == oiio.PATH_FUSED
+
+
+@pytest.mark.parametrize("st", ["float", "uint8"])
+def test_overscan_interior_fused_frame_exact(oiio, oracle, st):
+    """A source whose data window extends beyond its display window: device
+    resident, the interior (all taps inside the data window) goes through the
+    fused kernel, the frame around it through the exact kernel; the whole
+    image must match the oracle, seams included."""
+    import torch
+    sw, sh = 700, 500
+    src = synth.image(sw, sh, 4, _np_dtype(st), seed=201)
+    swin = (-4, -3, (0, 0, sw - 8, sh - 6))              # 4 / 3 px of overscan all round
+    dw, dh = 326, 234
+    dwin = (0, 0, (0, 0, dw, dh))
+    ref = np.zeros((dh, dw, 4), _np_dtype(st))
+    oracle.resize(oracle.Img(ref, *dwin), oracle.Img(src, *swin), "lanczos3")
+    t = torch.from_numpy(src).cuda()
+    out = torch.zeros((dh, dw, 4), dtype=t.dtype, device="cuda")
+    S, D = oiio.ImageBuf(t), oiio.ImageBuf(out)
+    for B, (x, y, full) in ((S, swin), (D, dwin)):
+        sp = B.spec()
+        sp.x, sp.y = x, y
+        sp.full_x, sp.full_y, sp.full_width, sp.full_height = full
+    assert oiio.ImageBufAlgo.resize(D, S, filtername="lanczos3"), D.geterror()
+    got = out.cpu().numpy()
+    check(got, ref)
+    # the same through the exact kernel only: the interior differs from it in
+    # the last bits (fused), so the fused kernel did run there
+    out2 = torch.zeros_like(out)
+    D2 = oiio.ImageBuf(out2)
+    sp = D2.spec()
+    sp.full_x, sp.full_y, sp.full_width, sp.full_height = dwin[2]
+    assert oiio.ImageBufAlgo.resize(D2, S, filtername="lanczos3", path=oiio.PATH_EXACT)
+    g2 = out2.cpu().numpy()
+    check(g2, ref)
+    # the first row / column need taps beyond the data window: exact kernel
+    assert np.array_equal(got[:1], g2[:1]) and np.array_equal(got[:, :1], g2[:, :1])
+    if st == "float":
+        assert not np.array_equal(got[60:160, 80:240], g2[60:160, 80:240])
