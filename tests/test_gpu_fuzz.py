@@ -11,6 +11,10 @@ from test_gpu_parity import run_both, check, _np_dtype
 
 pytestmark = pytest.mark.gpu
 
+# B2R_FUZZ_SEED=<n> shifts every seed: fresh random cases for an extra sweep
+import os
+SEED = int(os.environ.get("B2R_FUZZ_SEED", "0")) * 100003
+
 FILTERS = ["", "box", "triangle", "gaussian", "sharp-gaussian", "catmull-rom",
            "blackman-harris", "sinc", "lanczos3", "radial-lanczos3", "nuke-lanczos6",
            "mitchell", "bspline", "disk", "cubic", "keys", "simon", "rifman"]
@@ -52,7 +56,7 @@ def _case(rng):
 
 @pytest.mark.parametrize("chunk", range(16))
 def test_resize_fuzz(oiio, oracle, chunk):
-    rng = np.random.RandomState(20261020 + chunk)
+    rng = np.random.RandomState(20261020 + chunk + SEED)
     for k in range(60):
         c = _case(rng)
         src = synth.image(c["sw"], c["sh"], c["nch"], _np_dtype(c["st"]),
@@ -82,7 +86,7 @@ def test_regression_leading_rows_without_taps_host_source(oiio, oracle):
 # ---------------------------------------------------------------- resample ----
 @pytest.mark.parametrize("chunk", range(4))
 def test_resample_fuzz(oiio, oracle, chunk):
-    rng = np.random.RandomState(777 + chunk)
+    rng = np.random.RandomState(777 + chunk + SEED)
     for k in range(40):
         c = _case(rng)
         src = synth.image(c["sw"], c["sh"], c["nch"], _np_dtype(c["st"]), seed=k)
@@ -116,7 +120,7 @@ def test_warp_fuzz(oiio, oracle, chunk):
     cropped source windows, ROIs, 1-5 channels, the positive filters (the
     negative-lobe ones are ill-conditioned where a clipped footprint keeps
     few taps, see test_st_warp_parity)."""
-    rng = np.random.RandomState(4242 + chunk)
+    rng = np.random.RandomState(4242 + chunk + SEED)
     for k in range(25):
         sw, sh = int(rng.randint(8, 90)), int(rng.randint(8, 70))
         dw, dh = int(rng.randint(4, 80)), int(rng.randint(4, 60))
@@ -164,7 +168,7 @@ def test_warp_fuzz(oiio, oracle, chunk):
 def test_resize_fuzz_large(oiio, oracle, chunk):
     """Multi-strip / multi-band plans and the pipelined host path (>= 32 MB):
     the whole image on the GPU, the oracle on a random band of rows."""
-    rng = np.random.RandomState(9000 + chunk)
+    rng = np.random.RandomState(9000 + chunk + SEED)
     for k in range(5):
         sw, sh = int(rng.randint(900, 3300)), int(rng.randint(700, 2600))
         rx = float(rng.choice([0.25, 0.4, 0.5, 0.77, 1.0, 1.6, 2.0]))
@@ -197,7 +201,7 @@ def test_resize_fuzz_large(oiio, oracle, chunk):
 def test_mip_chain_fuzz(oiio, oracle):
     """Odd, prime, 1-pixel-wide and non-square level-0 sizes; box (bit-exact:
     both the 2x2 and the bilinear resize_block paths) and filtered chains."""
-    rng = np.random.RandomState(31337)
+    rng = np.random.RandomState(31337 + SEED)
     for k in range(24):
         w = int(rng.choice([1, 2, 3, 5, 16, 33, 64, 100, 127, 255, 256]))
         h = int(rng.choice([1, 2, 4, 7, 32, 50, 64, 99, 128, 200]))
@@ -220,7 +224,7 @@ def test_mip_chain_fuzz(oiio, oracle):
 
 # ------------------------------------------------ convolve / fixNonFinite ----
 def test_convolve_unsharp_fuzz(oiio, oracle):
-    rng = np.random.RandomState(555)
+    rng = np.random.RandomState(555 + SEED)
     IBA = oiio.ImageBufAlgo
     for k in range(30):
         w, h = int(rng.randint(1, 120)), int(rng.randint(1, 90))
@@ -264,7 +268,7 @@ def test_resize_fuzz_device_strided(oiio, oracle, chunk):
     strides, first pixel not 16-byte aligned (the vector-load / cp.async paths
     must fall back), canary columns around the destination left untouched."""
     import torch
-    rng = np.random.RandomState(6000 + chunk)
+    rng = np.random.RandomState(6000 + chunk + SEED)
     TT = {"float": torch.float32, "half": torch.float16, "uint8": torch.uint8,
           "uint16": torch.uint16}
 
