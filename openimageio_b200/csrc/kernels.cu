@@ -59,7 +59,11 @@ dev_lanczos3(float x)
         return 0.0f;
     if (x < 0.0001f)
         return 1.0f;
-    float s1 = sinf(__fmul_rn(__fmul_rn(x, ainv), pi));
+    // double-precision sine rounded to float: the correctly rounded value, which
+    // is what glibc's sinf returns in all but rare cases.  radial-lanczos3
+    // weights are normalised by their sum, which nearly cancels for narrow fixed
+    // widths, so a last-bit difference in a weight can show up amplified.
+    float s1 = (float)sin((double)__fmul_rn(__fmul_rn(x, ainv), pi));
     float s3 = __fmul_rn(__fadd_rn(__fmul_rn(__fmul_rn(-4.0f, s1), s1), 3.0f), s1);
     float den = __fmul_rn(__fmul_rn(x, x), __fmul_rn(pi, pi));
     return __fmul_rn(__fmul_rn(__fdiv_rn(a, den), s1), s3);
