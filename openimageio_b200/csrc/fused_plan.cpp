@@ -327,7 +327,10 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     // ring weights live in shared memory: keep a band's source rows bounded
     // ring row = vk weights padded to float4 loads
     const int vkp           = (vk + 3) & ~3;
-    const int max_rows_smem = use_ring ? (24 * 1024 / (4 * std::max(4, vkp))) : INT_MAX;
+    // (wide H windows already spend shared memory on their weights: a smaller
+    // ring-weight budget there keeps two CTAs resident per SM)
+    const int ring_budget   = ((P.ht > 16 && P.ht <= 32) ? 10 : 24) * 1024;
+    const int max_rows_smem = use_ring ? (ring_budget / (4 * std::max(4, vkp))) : INT_MAX;
     for (;;) {
         bool ok = true;
         P.bands.clear();
