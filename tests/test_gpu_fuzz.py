@@ -50,6 +50,11 @@ def _case(rng):
         y0 = dy + int(rng.randint(0, max(1, dh // 2)))
         roi = (x0, min(dx + dw, x0 + 1 + int(rng.randint(0, dw))),
                y0, min(dy + dh, y0 + 1 + int(rng.randint(0, dh))))
+    # radial-lanczos3 with a narrow FIXED width normalises by a weight sum that
+    # can nearly cancel: the result then hangs on the last bit of sinf (device
+    # vs glibc) -- in the reference itself as much as here.  Keep its own width.
+    if filt == "radial-lanczos3":
+        fw = 0.0
     return dict(sw=sw, sh=sh, dw=dw, dh=dh, nch=nch, st=str(st), dt=str(dt), filt=filt,
                 fw=fw, src_win=src_win, dst_win=dst_win, roi=roi)
 
