@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the B200 resize path.
+"""bench.py -- benchmark of the B200 resize path, one JSON line.
 
 Metric (BASELINE.json): output Mpixel/s of an 8K (7680x4320) -> 4K (3840x2160)
-lanczos3 RGBA float resize.  One "step" = one resize of one frame per GPU.
+lanczos3 RGBA float resize (workload c0).  One "step" = one batch of
+independent frames per GPU through the hot path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c0|c1|c2|c3|c5]
   python bench.py --impl reference ...     # the CPU algorithm, host cores
 
-value : device-resident: src and dst live in HBM, CUDA events around the K
-        steps on the launching stream, max over ranks.
-e2e   : the same resize through the public API with HOST (pinned) buffers:
-        H2D of the source and D2H of the result inside the timed region.
-roofline : algorithmic bytes (every source pixel read once + every output
-        pixel written once) / mean step time, against MEASURED_PEAKS.json.
-cpu_baseline : the oracle (the reference's single-pass algorithm, row-band
-        threaded like parallel_image) on a bounded row band of the same job.
-Multi-GPU: frames are independent -> one frame per rank per step, no
+value      device-resident: src and dst live in HBM, CUDA events around the K
+           steps on the launching stream, max over ranks (burst clocks: the
+           timed region is tens of ms).
+sustained  the same measurement repeated after --sustain-ms (default 300) of
+           untimed load, when the B200 sits in its 1 kW power cap.
+e2e        the same resize through the public API with HOST (pinned) buffers:
+           H2D of the source and D2H of the result inside the timed region.
+roofline   algorithmic bytes (every source pixel read once + every output
+           pixel written once) / mean step time, against MEASURED_PEAKS.json.
+cpu_baseline  the oracle (the reference's single-pass algorithm, row-band
+           threaded like parallel_image) on a bounded row band of the same job.
+configs    the other BASELINE configs, each with its own value / roofline
+           fraction / e2e: c1, c2, c3, c4 (16K^2 MIP chain, box and lanczos3)
+           and the real c5 batch (256 frames, sharded over the ranks).
+banded     (N > 1) the 16K^2 MIP chain cut into row bands over the N GPUs of
+           the box from ONE process (b2r_mipchain_create_banded: peer access,
+           halo rows pushed over NVLink, per-band upload), next to the
+           one-GPU chain including its upload.
+Multi-GPU: frames are independent -> one batch per rank per step, no
 collective in the data path (weak scaling); NCCL only for the barrier and the
 max-over-ranks reduction of the timing.
 """
@@ -51,11 +62,30 @@ DESCR = {
 # frames in one step's batch, per GPU (each frame has its own buffers)
 FRAMES_PER_STEP = {"c0": 8, "c1": 8, "c2": 8, "c3": 8, "c5": 8}
 DT_SHORT = {"float32": "f32", "float16": "f16", "uint8": "u8", "uint16": "u16"}
+C5_BATCH = 256
+C4_SIZE = 16384
+
+
+def config_of(wl):
+    """The config dict BOTH arms print (the driver compares them)."""
+    return {"workload": DESCR[wl], "name": wl}
 
 
 def algorithmic_bytes(wl):
     sw, sh, c, sdt, dw, dh, ddt, _ = WORKLOADS[wl]
     return sw * sh * c * np.dtype(sdt).itemsize + dw * dh * c * np.dtype(ddt).itemsize
+
+
+def chain_bytes(size, nch=4):
+    """Algorithmic bytes of a MIP chain from a size x size float image:
+    every level read once as a source, every level >= 1 written once."""
+    rd = wr = 0
+    w = h = size
+    while w > 1 or h > 1:
+        rd += w * h * nch * 4
+        w, h = max(1, w // 2), max(1, h // 2)
+        wr += w * h * nch * 4
+    return rd + wr, wr // (nch * 4)
 
 
 def measured_traffic(wl):
@@ -113,29 +143,19 @@ class ClockSampler:
         while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
             time.sleep(0.005)
 
-    def stop(self, t0=None, t1=None):
+    def window(self, t0, t1):
         """Median SM clock over the samples taken in [t0, t1] (host
-        perf_counter times of the timed region); all samples if none fell
-        inside."""
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        perf_counter times); all samples so far if none fell inside."""
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
-        rows = self.rows
-        if t0 is not None:
-            inside = [r for r in rows if t0 <= r[-1] <= t1 + 0.004]
-            rows = inside or rows
-        for r in rows:
+        rows = list(self.rows)
+        inside = [r for r in rows if t0 <= r[-1] <= t1 + 0.004]
+        for r in inside or rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
@@ -143,8 +163,18 @@ class ClockSampler:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None,
+                "power_w": float(np.median(pw)) if pw else None,
                 "reasons": sorted(reasons), "samples": len(sm),
-                "samples_total": len(self.rows)}
+                "samples_total": len(rows)}
+
+    def stop(self):
+        if not self.proc:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
 
 
 def sample_rows(wl, cores):
@@ -214,10 +244,10 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": DT_SHORT[sdt], "data": "synthetic",
-        "config": {"workload": DESCR[wl], "name": wl,
-                   "note": "reference algorithm restated in oracle/ (the OIIO "
-                           "library itself cannot be built here: needs Imath, "
-                           "OpenEXR, libtiff, OpenColorIO)"},
+        "config": config_of(wl),
+        "details": {"note": "reference algorithm restated in oracle/ (the OIIO "
+                            "library itself cannot be built here: needs Imath, "
+                            "OpenEXR, libtiff, OpenColorIO)"},
         "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": cores,
                          "kind": "port", "sample": sample},
         "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0,
@@ -226,6 +256,271 @@ def run_reference(args):
     }
     print(json.dumps(line))
     return 0
+
+
+# --------------------------------------------------------------------------
+class Harness:
+    """Everything one rank needs to time resizes on its GPU."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        import openimageio_b200 as oiio
+        self.torch, self.dist, self.oiio = torch, dist, oiio
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.tdt = {"float32": torch.float32, "float16": torch.float16,
+                    "uint8": torch.uint8, "uint16": torch.uint16}
+        self.peak, self.peak_src = measured_peak()
+        self.launches = 0
+
+    def to_torch(self, a):
+        t = self.torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        return t.view(self.torch.uint16) if a.dtype == np.uint16 else t
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def time_steps(self, step, steps):
+        """K steps between two CUDA events on the launch stream, queued behind
+        a ~2 ms device spin so the region measures the device and not the
+        host's launch rate.  Returns (ms per step on this rank, t0, t1)."""
+        torch = self.torch
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        t0 = time.perf_counter()
+        torch.cuda._sleep(4_000_000)
+        ev0.record()
+        for _ in range(steps):
+            step()
+        ev1.record()
+        self.barrier()
+        return ev0.elapsed_time(ev1) / steps, t0, time.perf_counter()
+
+    def frames(self, wl, nfr, seed=20261019):
+        """nfr independent device-resident (src, dst) frames of workload wl,
+        plus one pinned host pair."""
+        import synth
+        torch = self.torch
+        sw, sh, c, sdt, dw, dh, ddt, _ = WORKLOADS[wl]
+        src_np = synth.image(sw, sh, c, np.dtype(sdt), seed=seed + self.rank)
+        src_host = self.to_torch(src_np).pin_memory()
+        dst_host = torch.empty((dh, dw, c), dtype=self.tdt[ddt]).pin_memory()
+        srcs, dsts = [], []
+        base = src_host.to(self.dev, non_blocking=True)
+        for f in range(nfr):
+            t = base
+            if f:  # a different picture per frame: roll the rows
+                t = torch.roll(base.view(torch.uint8), shifts=137 * f, dims=0).view(base.dtype)
+            srcs.append(t)
+            dsts.append(torch.zeros((dh, dw, c), dtype=self.tdt[ddt], device=self.dev))
+        torch.cuda.synchronize()
+        return src_np, src_host, dst_host, srcs, dsts
+
+    def resize_config(self, wl, steps, warmup, nfr, e2e_steps, sustain_ms=0.0,
+                      sampler=None, pageable=False, total_frames=None):
+        """Device-resident + end-to-end numbers of one resize workload."""
+        oiio, torch = self.oiio, self.torch
+        IBA = oiio.ImageBufAlgo
+        sw, sh, c, sdt, dw, dh, ddt, filt = WORKLOADS[wl]
+        src_np, src_host, dst_host, srcs, dsts = self.frames(wl, nfr)
+        S_devs = [oiio.ImageBuf(t) for t in srcs]
+        D_devs = [oiio.ImageBuf(t) for t in dsts]
+        S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
+
+        def step_dev():
+            for S, D in zip(S_devs, D_devs):
+                if not IBA.resize(D, S, filtername=filt):
+                    raise RuntimeError(D.geterror())
+
+        def step_host():
+            # the batch through the host-memory API: every frame's source goes
+            # up and every result comes down (the same pinned host frame stands
+            # in for the nfr frames; a host->device copy cannot be cached)
+            for _ in range(nfr):
+                if not IBA.resize(D_host, S_host, filtername=filt, device=self.local_rank):
+                    raise RuntimeError(D_host.geterror())
+
+        for _ in range(warmup):
+            step_dev()
+        ms, t0, t1 = self.time_steps(step_dev, steps)
+        ms = self.max_over_ranks(ms)
+        clocks = sampler.window(t0, t1) if sampler else None
+        out = {"ms_per_step": ms, "clocks": clocks}
+        if sustain_ms > 0:
+            t_ramp = time.perf_counter()
+            while (time.perf_counter() - t_ramp) * 1e3 < sustain_ms:
+                step_dev()
+                torch.cuda.synchronize()
+            ms_s, t0, t1 = self.time_steps(step_dev, steps)
+            out["sustained_ms_per_step"] = self.max_over_ranks(ms_s)
+            out["sustained_clocks"] = sampler.window(t0, t1) if sampler else None
+        self.launches += (warmup + steps) * nfr
+
+        # end to end (host buffers through the public API)
+        for _ in range(2):
+            step_host()
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        self.barrier()
+        e2e_ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+        rep = IBA.last_report
+        out["e2e_ms_per_step"] = e2e_ms
+        out["h2d"] = int(rep.h2d_bytes) * nfr
+        out["d2h"] = int(rep.d2h_bytes) * nfr
+        out["kernel_path"] = ("stream" if getattr(rep, "kernels_launched", 2) == 1
+                              and sdt in ("float32", "float16") else "fused")
+        if pageable and self.world == 1:
+            Sp = oiio.ImageBuf(src_np)
+            Dp = oiio.ImageBuf(np.zeros((dh, dw, c), np.dtype(ddt)))
+            for _ in range(2):
+                IBA.resize(Dp, Sp, filtername=filt, device=self.local_rank)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                IBA.resize(Dp, Sp, filtername=filt, device=self.local_rank)
+            out["pageable_ms"] = (time.perf_counter() - t0) * 1e3 / 3
+        # parity spot check of what was just timed (device result == host result)
+        out["same"] = bool(torch.equal(dsts[0].cpu().view(torch.uint8),
+                                       dst_host.view(torch.uint8)))
+        out["nfr"] = nfr
+        del S_devs, D_devs, srcs, dsts
+        torch.cuda.empty_cache()
+        return out
+
+    def summarise(self, wl, r, frames_total):
+        """value / roofline / e2e record of a resize workload from
+        resize_config's timings; frames_total = frames per step, all ranks."""
+        sw, sh, c, sdt, dw, dh, ddt, _ = WORKLOADS[wl]
+        mpix = dw * dh / 1e6
+        ab = algorithmic_bytes(wl)
+        per_gpu = frames_total / self.world
+        ach = ab * per_gpu / (r["ms_per_step"] * 1e-3) / 1e9
+        rec = {"workload": DESCR[wl],
+               "value": mpix * frames_total / (r["ms_per_step"] * 1e-3),
+               "unit": "Mpixel/s", "launch_us": r["ms_per_step"] * 1e3 / per_gpu,
+               "achieved_gbs": ach, "frac": ach / self.peak,
+               "e2e_value": mpix * frames_total / (r["e2e_ms_per_step"] * 1e-3),
+               "device_equals_host_result": r["same"]}
+        if "sustained_ms_per_step" in r:
+            a2 = ab * per_gpu / (r["sustained_ms_per_step"] * 1e-3) / 1e9
+            rec["sustained_value"] = mpix * frames_total / (r["sustained_ms_per_step"] * 1e-3)
+            rec["sustained_frac"] = a2 / self.peak
+        return rec
+
+    # ---- C5: the real 256-frame batch, sharded over the ranks -----------
+    def c5_batch(self, steps=3):
+        oiio, torch = self.oiio, self.torch
+        IBA = oiio.ImageBufAlgo
+        wl = "c5"
+        sw, sh, c, sdt, dw, dh, ddt, filt = WORKLOADS[wl]
+        mine = oiio.shard_frames(C5_BATCH, self.world, self.rank)
+        nf = len(mine)
+        _, src_host, dst_host, srcs, dsts = self.frames(wl, nf, seed=20261024)
+        S = [oiio.ImageBuf(t) for t in srcs]
+        D = [oiio.ImageBuf(t) for t in dsts]
+        S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
+
+        def step_dev():
+            for s, d in zip(S, D):
+                if not IBA.resize(d, s, filtername=filt):
+                    raise RuntimeError(d.geterror())
+
+        def step_host():
+            for _ in range(nf):
+                if not IBA.resize(D_host, S_host, filtername=filt, device=self.local_rank):
+                    raise RuntimeError(D_host.geterror())
+        step_dev()
+        ms, _, _ = self.time_steps(step_dev, steps)
+        ms = self.max_over_ranks(ms)
+        self.launches += (1 + steps) * nf
+        step_host()
+        self.barrier()
+        t0 = time.perf_counter()
+        step_host()
+        self.barrier()
+        e2e_ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3)
+        same = bool(torch.equal(dsts[0].cpu().view(torch.uint8), dst_host.view(torch.uint8)))
+        del S, D, srcs, dsts
+        torch.cuda.empty_cache()
+        mpix = dw * dh / 1e6 * C5_BATCH
+        ach = algorithmic_bytes(wl) * nf / (ms * 1e-3) / 1e9  # per GPU
+        return {"workload": "batch of %d 4K->1080p lanczos3 RGB uint16 frames, "
+                            "frames sharded over %d GPU(s)" % (C5_BATCH, self.world),
+                "frames": C5_BATCH, "frames_per_gpu": nf, "scaling": "strong",
+                "value": mpix / (ms * 1e-3), "unit": "Mpixel/s", "ms_per_batch": ms,
+                "launch_us": ms * 1e3 / nf, "achieved_gbs": ach, "frac": ach / self.peak,
+                "e2e_value": mpix / (e2e_ms * 1e-3), "e2e_ms_per_batch": e2e_ms,
+                "device_equals_host_result": same}
+
+    # ---- C4: 16K^2 RGBA float MIP chain on one GPU -----------------------
+    def c4_level0(self, size):
+        """A synthetic size x size RGBA float level 0 in HBM (counter hash of
+        the element index, computed on the device) and its pinned host copy."""
+        torch = self.torch
+        n = size * size * 4
+        t = torch.empty(n, dtype=torch.float32, device=self.dev)
+        chunk = 1 << 26
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            i = torch.arange(a, b, device=self.dev, dtype=torch.int64)
+            v = (i * 2654435761 + 20261023) & 0xFFFFFFFF
+            v = ((v ^ (v >> 15)) * 2246822519) & 0xFFFFFFFF
+            v = v ^ (v >> 13)
+            t[a:b] = v.to(torch.float32) * (1.0 / 4294967296.0)
+            del i, v
+        return t.view(size, size, 4)
+
+    def c4_chain(self, size, host_pinned, lvl0, filt, repeats=2):
+        oiio, torch = self.oiio, self.torch
+        ab, out_px = chain_bytes(size)
+        best = None
+        nlev = 0
+        for _ in range(repeats):
+            ch = oiio.MipChain(oiio.ImageBuf(lvl0), filtername=filt, device=self.local_rank)
+            nlev = ch.nlevels
+            best = ch.kernel_ms if best is None else min(best, ch.kernel_ms)
+            del ch
+        self.launches += repeats * (nlev - 1)
+        # end to end: pinned host level 0 up, chain, every level >= 1 back
+        t0 = time.perf_counter()
+        ch = oiio.MipChain(oiio.ImageBuf(host_pinned), filtername=filt, device=self.local_rank)
+        t_up = time.perf_counter()
+        total = 0
+        for lv in range(1, ch.nlevels):
+            total += ch.download(lv).nbytes
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        up_ms = (t_up - t0) * 1e3
+        del ch
+        torch.cuda.empty_cache()
+        ach = ab / (best * 1e-3) / 1e9
+        return {"workload": "maketx MIP chain of a %dx%d RGBA float32 texture, %s, "
+                            "%d levels, device-resident" % (size, size, filt, nlev),
+                "value": out_px / 1e6 / (best * 1e-3), "unit": "Mpixel/s (levels >= 1)",
+                "chain_ms": best, "achieved_gbs": ach, "frac": ach / self.peak,
+                "algorithmic_bytes": ab,
+                "e2e_value": out_px / 1e6 / (e2e_ms * 1e-3), "e2e_ms": e2e_ms,
+                "e2e_upload_and_chain_ms": up_ms,
+                "e2e_note": "level 0 (%.1f GB, pinned host) up, chain, levels >= 1 "
+                            "(%.1f GB) down to pageable host memory"
+                            % (size * size * 16 / 1e9, total / 1e9)}
 
 
 def main():
@@ -237,195 +532,136 @@ def main():
     ap.add_argument("--workload", default="c0", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true",
                     help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="headline workload only (skip c1..c5 / c4 / banded)")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--frames-per-step", type=int, default=0,
                     help="frames in one step's batch per GPU (0 = workload default)")
     ap.add_argument("--ramp-ms", type=float, default=0.0,
-                    help="extra untimed load after the warm-up steps (a long "
-                         "ramp drives the GPU into its 1 kW power cap: "
-                         "sustained rather than burst clocks)")
+                    help="extra untimed load BEFORE the headline measurement")
+    ap.add_argument("--sustain-ms", type=float, default=300.0,
+                    help="untimed load between the burst measurement and its "
+                         "sustained twin (drives the GPU into its 1 kW power "
+                         "cap); 0 = skip the twin")
+    ap.add_argument("--c4-size", type=int, default=C4_SIZE)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
     if args.impl == "reference":
         return run_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    import openimageio_b200 as oiio
-    import synth
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
+    H = Harness(args)
+    torch = H.torch
     wl = args.workload
     sw, sh, c, sdt, dw, dh, ddt, filt = WORKLOADS[wl]
-    tdt = {"float32": torch.float32, "float16": torch.float16,
-           "uint8": torch.uint8, "uint16": torch.uint16}
-
-    # One step = one batch of `nfr` independent frames per GPU, each with its
-    # own source and destination in HBM (nothing is shared or reused between
-    # the frames of a batch); every rank has its own frames.
     nfr = args.frames_per_step or FRAMES_PER_STEP[wl]
+    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
 
-    def to_torch(a):
-        t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
-        return t.view(torch.uint16) if a.dtype == np.uint16 else t
-
-    src_np = synth.image(sw, sh, c, np.dtype(sdt), seed=20261019 + rank)
-    src_host = to_torch(src_np).pin_memory()
-    dst_host = torch.empty((dh, dw, c), dtype=tdt[ddt]).pin_memory()
-    src_devs, dst_devs = [], []
-    for f in range(nfr):
-        t = src_host.to(dev, non_blocking=True)
-        if f:  # a different picture per frame: roll the rows
-            t = torch.roll(t.view(torch.uint8), shifts=137 * f, dims=0).view(t.dtype)
-        src_devs.append(t)
-        dst_devs.append(torch.zeros((dh, dw, c), dtype=tdt[ddt], device=dev))
-    torch.cuda.synchronize()
-
-    S_devs = [oiio.ImageBuf(t) for t in src_devs]
-    D_devs = [oiio.ImageBuf(t) for t in dst_devs]
-    S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
-    IBA = oiio.ImageBufAlgo
-    dst_dev = dst_devs[0]
-
-    def step_dev():
-        for S, D in zip(S_devs, D_devs):
-            if not IBA.resize(D, S, filtername=filt):
-                raise RuntimeError(D.geterror())
-
-    def step_host():
-        # the batch through the host-memory API: every frame's source goes up
-        # and every result comes down (the same pinned host frame stands in
-        # for the nfr frames; a host->device copy cannot be cached)
-        for _ in range(nfr):
-            if not IBA.resize(D_host, S_host, filtername=filt, device=local_rank):
-                raise RuntimeError(D_host.geterror())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----------------------------------------
-    for _ in range(args.warmup):
-        step_dev()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
+    sampler = ClockSampler(H.local_rank) if H.rank == 0 else None
+    if sampler:
         sampler.start()
         sampler.wait_first()
-    # Optional extra untimed load (--ramp-ms).  The clock sampler runs from
-    # here to the end of the timed region ("under load").
-    t_ramp = time.perf_counter()
-    while (time.perf_counter() - t_ramp) * 1e3 < args.ramp_ms:
-        step_dev()
-        torch.cuda.synchronize()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    # a ~2 ms device-side spin in front of the first event: the K launches
-    # queue up behind it, so the timed region measures the device, not the
-    # host's launch rate (which matters when K is small)
-    t_host0 = time.perf_counter()
-    torch.cuda._sleep(4_000_000)
-    ev0.record()
-    for _ in range(args.steps):
-        step_dev()
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    clocks = sampler.stop(t_host0, time.perf_counter()) if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    if args.ramp_ms > 0:
+        x = torch.empty(1 << 28, dtype=torch.float32, device=H.dev)
+        t_ramp = time.perf_counter()
+        while (time.perf_counter() - t_ramp) * 1e3 < args.ramp_ms:
+            x.add_(1.0)
+            torch.cuda.synchronize()
+        del x
+    r = H.resize_config(wl, args.steps, args.warmup, nfr, e2e_steps,
+                        sustain_ms=args.sustain_ms, sampler=sampler, pageable=True)
+    head = H.summarise(wl, r, nfr * H.world)
 
-    # ---- end-to-end timing (host buffers through the public API) --------
-    e2e_steps = args.e2e_steps or max(3, min(args.steps, 10))
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    rep = IBA.last_report
-    h2d, d2h = int(rep.h2d_bytes) * nfr, int(rep.d2h_bytes) * nfr
-    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t.item())
+    configs, banded = {}, None
+    if not args.no_configs:
+        for w2 in ("c1", "c2", "c3"):
+            if w2 == wl or H.world > 1:
+                continue  # single-GPU shapes: measured at N = 1
+            rr = H.resize_config(w2, 10, 3, FRAMES_PER_STEP[w2], 3)
+            configs[w2] = H.summarise(w2, rr, FRAMES_PER_STEP[w2])
+        configs["c5"] = H.c5_batch()
+        if H.rank == 0 and H.world == 1:
+            try:
+                size = args.c4_size
+                lvl0 = H.c4_level0(size)
+                host = torch.empty((size, size, 4), dtype=torch.float32).pin_memory()
+                host.copy_(lvl0)
+                torch.cuda.synchronize()
+                for f in ("box", "lanczos3"):
+                    configs["c4_" + f] = H.c4_chain(size, host, lvl0, f)
+                del lvl0, host
+                torch.cuda.empty_cache()
+            except Exception as e:  # a side config must not sink the headline
+                configs["c4_error"] = str(e)
+        if H.world > 1:
+            H.barrier()
+            if H.rank == 0:
+                try:
+                    import banded_bench
+                    banded = banded_bench.run(H, args.c4_size)
+                except Exception as e:
+                    banded = {"error": str(e)}
+            H.barrier()
+    if sampler:
+        sampler.stop()
 
-    # the same from PAGEABLE host memory (what an ImageBuf normally owns): the
-    # library stages it through pinned bounce rings with a few host threads
-    page_ms = None
-    if world == 1:
-        Sp = oiio.ImageBuf(src_np)
-        Dp = oiio.ImageBuf(np.zeros((dh, dw, c), np.dtype(ddt)))
-        for _ in range(2):
-            IBA.resize(Dp, Sp, filtername=filt, device=local_rank)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            IBA.resize(Dp, Sp, filtername=filt, device=local_rank)
-        page_ms = (time.perf_counter() - t0) * 1e3 / 3
-
-    # parity spot check of what was just timed (device result == host result)
-    same = bool(torch.equal(dst_dev.cpu().view(torch.uint8),
-                            dst_host.view(torch.uint8))) if rank == 0 else True
-
-    if rank == 0:
+    if H.rank == 0:
         mpix_frame = dw * dh / 1e6
-        value = mpix_frame * nfr * world / (ms_max * 1e-3)
-        e2e_value = mpix_frame * nfr * world / (e2e_ms_max * 1e-3)
         abytes = algorithmic_bytes(wl)
-        peak, which = measured_peak()
-        achieved = abytes * nfr / (ms_max * 1e-3) / 1e9  # per launch = per frame
-        src_is_fp = sdt in ("float32", "float16")
+        src_mb = sw * sh * c * np.dtype(sdt).itemsize / 1e6
         line = {
-            "metric": "output Mpixel/s", "value": value, "unit": "Mpixel/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": DT_SHORT[sdt], "data": "synthetic",
-            "config": {"workload": DESCR[wl], "name": wl,
-                       "frames_per_step": nfr * world,
-                       "frames_per_step_per_gpu": nfr,
-                       "l2": "source frame (%.0f MB) larger than L2; no flush"
-                             % (sw * sh * c * np.dtype(sdt).itemsize / 1e6)
-                       if sw * sh * c * np.dtype(sdt).itemsize > 126e6 else
-                       "working set fits L2; steps run back to back",
-                       "parallelism": "frame-per-gpu x%d" % world,
-                       "timing": "CUDA events on the launch stream; launches "
-                                 "queued behind a 2 ms device spin; %.0f ms "
-                                 "untimed clock ramp after the W warm-ups"
-                                 % args.ramp_ms},
-            "e2e": {"value": e2e_value, "unit": "Mpixel/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max, "steps": e2e_steps,
+            "metric": "output Mpixel/s", "value": head["value"], "unit": "Mpixel/s",
+            "n_gpus": H.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DT_SHORT[sdt],
+            "data": "synthetic",
+            "config": config_of(wl),
+            "details": {
+                "frames_per_step": nfr * H.world, "frames_per_step_per_gpu": nfr,
+                "l2": ("source frame (%.0f MB) larger than L2; no flush" % src_mb)
+                      if src_mb > 126 else
+                      ("%d independent frames per step, %.0f MB of sources per "
+                       "step (> L2), run back to back" % (nfr, src_mb * nfr)),
+                "parallelism": "frame-per-gpu x%d" % H.world,
+                "timing": "CUDA events on the launch stream; launches queued "
+                          "behind a 2 ms device spin; burst = right after the W "
+                          "warm-ups, sustained = after %.0f ms of untimed load"
+                          % args.sustain_ms},
+            "e2e": {"value": head["e2e_value"], "unit": "Mpixel/s",
+                    "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "ms_per_step": r["e2e_ms_per_step"], "steps": e2e_steps,
                     "host_memory": "pinned",
-                    "pageable_value": (mpix_frame / (page_ms * 1e-3)
-                                       if page_ms else None),
-                    "pageable_ms_per_frame": page_ms},
-            "gpu_launches": args.steps * nfr * (2 if src_is_fp else 1),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(wl), "peak_source": which,
-                         "algorithmic_bytes": abytes,
-                         "launch_us": ms_max * 1e3 / nfr,
-                         "kernel": "resize_fused_kernel"},
-            "clocks": clocks,
-            "device_equals_host_result": same,
+                    "pageable_value": (mpix_frame / (r["pageable_ms"] * 1e-3)
+                                       if r.get("pageable_ms") else None),
+                    "pageable_ms_per_frame": r.get("pageable_ms")},
+            "gpu_launches": H.launches,
+            "roofline": {"bound": "hbm", "achieved": head["achieved_gbs"],
+                         "peak": H.peak, "unit": "GB/s", "frac": head["frac"],
+                         "traffic": measured_traffic(wl),
+                         "traffic_source": "static: dram__bytes_read+write of the "
+                                           "committed ncu capture (profiles/traffic.json), "
+                                           "not measured in this run",
+                         "peak_source": H.peak_src, "algorithmic_bytes": abytes,
+                         "launch_us": head["launch_us"],
+                         "frac_of_nominal_8tbs": head["achieved_gbs"] / 8000.0,
+                         "kernel": "resize_stream_kernel (TMA, warp-specialised)"},
+            "clocks": r["clocks"],
+            "device_equals_host_result": r["same"],
         }
-        if not args.no_cpu and world == 1:
+        if "sustained_value" in head:
+            s_ms = r["sustained_ms_per_step"]
+            line["sustained"] = {
+                "value": head["sustained_value"], "unit": "Mpixel/s",
+                "ms_per_step": s_ms, "launch_us": s_ms * 1e3 / nfr,
+                "frac": head["sustained_frac"],
+                "frac_of_nominal_8tbs": head["sustained_frac"] * H.peak / 8000.0,
+                "after_ms_of_load": args.sustain_ms,
+                "clocks": r.get("sustained_clocks")}
+        if configs:
+            line["configs"] = configs
+        if banded is not None:
+            line["banded"] = banded
+        if not args.no_cpu and H.world == 1:
             try:
                 mp, cores, sample = cpu_sample(wl)
                 line["cpu_baseline"] = {"value": mp, "unit": "Mpixel/s",
@@ -436,8 +672,8 @@ def main():
                                         "cores": 0, "kind": "port",
                                         "sample": "failed: %s" % e}
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if H.world > 1:
+        H.dist.destroy_process_group()
     return 0
 
 

@@ -87,9 +87,11 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
     out->count.assign(n, 0);
     out->woff.assign(n, 0);
     out->w.clear();
+    out->mixed.clear();
     out->maxcount      = 0;
     out->interior_zero = false;
     std::vector<float> merged;
+    std::vector<uint8_t> signs;
     for (int k = 0; k < n; ++k) {
         out->woff[k] = int(out->w.size());
         if (taps.wsum[k] == 0.0f)
@@ -112,6 +114,7 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
             continue;
         int cnt = hi - lo + 1;
         merged.assign(cnt, 0.0f);
+        signs.assign(cnt, 0);
         for (int i = 0; i < taps.ntaps; ++i) {
             if (w[i] == 0.0f)
                 continue;
@@ -120,6 +123,7 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
             if (c < g.src_data_begin || c >= g.src_data_end)
                 continue;
             merged[c - lo] += w[i];
+            signs[c - lo] |= (w[i] > 0.0f) ? 1 : 2;
         }
         for (int i = 0; i < cnt; ++i)
             if (merged[i] == 0.0f)
@@ -127,6 +131,8 @@ build_axis_gather(const AxisGeom& g, const AxisTaps& taps, AxisGather* out,
         out->first[k] = lo - g.src_data_begin;
         out->count[k] = cnt;
         out->w.insert(out->w.end(), merged.begin(), merged.end());
+        for (int i = 0; i < cnt; ++i)
+            out->mixed.push_back(signs[i] == 3 ? 1 : 0);
         out->maxcount = std::max(out->maxcount, cnt);
     }
     return true;

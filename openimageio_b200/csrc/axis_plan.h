@@ -56,6 +56,9 @@ struct AxisGather {
     std::vector<int32_t> count;  // run length (0 = output is zero)  [n]
     std::vector<int32_t> woff;   // offset of the run's weights in w [n]
     std::vector<float> w;
+    // parallel to w: 1 when the weight is the sum of clamped taps of BOTH signs
+    // (an Inf under it is NaN in the reference: w1*Inf + w2*Inf)
+    std::vector<uint8_t> mixed;
     bool interior_zero = false;  // some run contains a zero weight
 };
 

@@ -78,6 +78,8 @@ struct DevicePlan {
     const int* hfirst = nullptr;
     const float* hw = nullptr;
     const float* vring = nullptr;
+    const float* vstream = nullptr;
+    const int* hmix = nullptr;
     const int* vlast = nullptr;
     const int* vfirst = nullptr;
     const float* vw = nullptr;
@@ -95,7 +97,8 @@ struct DevicePlan {
 
 std::mutex g_plan_mutex;
 std::list<std::shared_ptr<DevicePlan>> g_plans;  // most recent first
-const size_t kMaxPlans = 32;
+// above the band count of the pipelined host path (<= 64 bands, one plan each)
+const size_t kMaxPlans = 192;
 
 struct BlobBuilder {
     std::vector<unsigned char> host;
@@ -211,13 +214,13 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
            o_yf = bb.add(ty.frac);
 
     size_t o_strips = 0, o_bands = 0, o_hf = 0, o_hw = 0, o_vr = 0, o_vl = 0,
-           o_vf = 0, o_vw = 0;
+           o_vf = 0, o_vw = 0, o_vs = 0, o_hm = 0;
     if (filter.separable()) {
         AxisGather ax, ay;
         bool ok = build_axis_gather(gx, tx, &ax, axis_overscan(gy))
                   && build_axis_gather(gy, ty, &ay, axis_overscan(gx))
                   && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
-                                &plan->fp)
+                                &plan->fp, 16 / basetype_size(src.basetype))
                   && plan_supported(src.basetype, nch, plan->fp);
         if (ok) {
             // the band count was sized for an assumed number of resident CTAs
@@ -236,7 +239,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             int sms   = cta_slots / 3;
             if (per > 0 && per != 3)
                 ok = plan_fused(ax, ay, nch, src.width, src.height, sms * per,
-                                &plan->fp)
+                                &plan->fp, 16 / basetype_size(src.basetype))
                      && plan_supported(src.basetype, nch, plan->fp);
         }
         if (ok) {
@@ -246,6 +249,8 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             o_hf        = bb.add(plan->fp.hfirst);
             o_hw        = bb.add(plan->fp.hw);
             o_vr        = bb.add(plan->fp.vring);
+            o_vs        = bb.add(plan->fp.vstream);
+            o_hm        = bb.add(plan->fp.hmix);
             o_vl        = bb.add(plan->fp.vlast);
             o_vf        = bb.add(plan->fp.vfirst);
             o_vw        = bb.add(plan->fp.vw);
@@ -254,12 +259,17 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             plan->fp.hw.shrink_to_fit();
             plan->fp.vring.clear();
             plan->fp.vring.shrink_to_fit();
+            plan->fp.vstream.clear();
+            plan->fp.vstream.shrink_to_fit();
         }
     }
     CUDA_TRY(cudaMalloc(&plan->blob, std::max<size_t>(bb.host.size(), 256)));
     CUDA_TRY(cudaMemcpyAsync(plan->blob, bb.host.data(), bb.host.size(),
                              cudaMemcpyHostToDevice, stream));
-    // the host blob is pageable: the copy has been staged when the call returns
+    // The plan is about to be published in the cache, where a call on ANOTHER
+    // stream can pick it up: the tables must have landed by then (a pageable
+    // async copy only guarantees that the data has been staged).  Once per shape.
+    CUDA_TRY(cudaStreamSynchronize(stream));
     unsigned char* base = (unsigned char*)plan->blob;
     plan->xcenter = (const int*)(base + o_xc);
     plan->xw      = (const float*)(base + o_xw);
@@ -275,6 +285,8 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
         plan->hfirst = (const int*)(base + o_hf);
         plan->hw     = (const float*)(base + o_hw);
         plan->vring  = (const float*)(base + o_vr);
+        plan->vstream = (const float*)(base + o_vs);
+        plan->hmix    = (const int*)(base + o_hm);
         plan->vlast  = (const int*)(base + o_vl);
         plan->vfirst = (const int*)(base + o_vf);
         plan->vw     = (const float*)(base + o_vw);
@@ -333,6 +345,17 @@ next_flag(int dev)
     s.flag     = r.flags + (n % REDO_SLOTS);
     s.dirty    = r.maps + size_t(n % REDO_SLOTS) * REDO_MAP_CELLS;
     return s;
+}
+
+// B2R_STREAM=0 keeps ring-mode shapes on resize_fused_kernel (A/B runs)
+bool
+stream_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("B2R_STREAM");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 int
@@ -813,6 +836,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         fp.ht              = plan->fp.ht;
         fp.vk              = plan->fp.vk;
         fp.vring           = plan->vring;
+        fp.vstream         = plan->vstream;
+        fp.hmix            = plan->hmix;
         fp.vlast           = plan->vlast;
         fp.vt              = plan->fp.vt;
         fp.vfirst          = plan->vfirst;
@@ -848,11 +873,32 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                    > REDO_MAP_CELLS)
                 ++fp.dirty_yshift;
         }
-        launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,
-                            plan->fp.max_nvec, stream);
+        // Ring-mode shapes whose source rows are 16-byte aligned take the
+        // persistent TMA kernel (stream_kernel.cuh); it resolves zero weights
+        // under non-finite pixels itself, so no gated exact kernel follows.
+        bool streamed = false;
+        if (!fp.expand && fp.vk > 0 && stream_enabled()
+            && stream_supported(src.basetype, nch, fp.vk, fp.ht, 1)) {
+            const int trow0 = src_staged ? plan->src_row0 : 0;
+            const int trows = src_staged ? plan->src_row1 - plan->src_row0 + 1 : src.height;
+            const unsigned char* tbase
+                = (const unsigned char*)dsrc + (long long)trow0 * srcd.ystride;
+            fp.tma_row0        = trow0;
+            fp.check_nonfinite = 0;
+            streamed = launch_resize_stream(fp, 1, tbase, trows, di.sms, stream) == 0;
+            if (!streamed)
+                fp.check_nonfinite = src_is_fp ? 1 : 0;
+        }
+        if (!streamed)
+            launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,
+                                plan->fp.max_nvec, stream);
         ++launched;
         used = B2R_PATH_FUSED;
-        if (src_is_fp) {
+        if (src_is_fp && streamed) {
+            flag  = nullptr;
+            epoch = 0;
+        }
+        if (src_is_fp && !streamed) {
             ep.gate         = flag;  // runs only if a non-finite output was seen
             ep.gate_value   = epoch;
             ep.dirty        = fp.dirty;  // ... and only over the cells that hold one
@@ -889,7 +935,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
     }
     int redo = 0;
-    if (report && used == B2R_PATH_FUSED && src_is_fp
+    if (report && used == B2R_PATH_FUSED && src_is_fp && flag
         && (dst_staged || src_staged))
         CUDA_TRY(cudaMemcpyAsync(&redo, flag, sizeof(int),
                                  cudaMemcpyDeviceToHost, stream));

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstring>
 
 namespace b2r {
 
@@ -184,8 +185,11 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
 
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan)
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align)
 {
+    // strips start on a 16-byte boundary of the source row (e0_align elements):
+    // the TMA boxes of the stream kernel need it, the other kernels need 4
+    e0_align = std::max(4, e0_align) & ~3;
     if (nch < 1 || nch > 4 || gx.n <= 0 || gy.n <= 0)
         return false;
     FusedPlan& P = *plan;
@@ -278,16 +282,25 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         return false;
     P.hfirst.resize(npairs);
     P.hw.assign(size_t(npairs) * P.ht * 2, 0.0f);
+    // per pair: bit j (column A) / 16 + j (column B) set when window tap j
+    // merges clamped taps of both signs (windows of <= 16 taps only)
+    P.hmix.assign(npairs, 0);
     for (int pr = 0; pr < npairs; ++pr) {
         int a = 2 * pr, bcol = a + 1;
         P.hfirst[pr] = cfirst[a];
         float* w     = &P.hw[size_t(pr) * P.ht * 2];
-        for (int i = 0; i < gx.count[a]; ++i)
+        for (int i = 0; i < gx.count[a]; ++i) {
             w[2 * i] = gx.w[gx.woff[a] + i];
+            if (i < 16 && gx.mixed[gx.woff[a] + i])
+                P.hmix[pr] |= 1 << i;
+        }
         if (bcol < W) {
             int s = cfirst[bcol] - cfirst[a];
-            for (int i = 0; i < gx.count[bcol]; ++i)
+            for (int i = 0; i < gx.count[bcol]; ++i) {
                 w[2 * (s + i) + 1] = gx.w[gx.woff[bcol] + i];
+                if (s + i < 16 && gx.mixed[gx.woff[bcol] + i])
+                    P.hmix[pr] |= 1 << (16 + s + i);
+            }
         }
     }
 
@@ -298,7 +311,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     for (int dx0 = 0; dx0 < W;) {
         Strip s;
         s.dx0  = dx0;
-        s.e0   = (cfirst[dx0] * nch) & ~3;
+        s.e0   = (cfirst[dx0] * nch) / e0_align * e0_align;
         s.ndx  = 0;
         s.nvec = 0;
         const int px0 = s.e0 / nch;
@@ -372,7 +385,9 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         size_t total = 0;
         for (const Band& b : P.bands)
             total += size_t(b.nrows);
-        P.vring.assign(total * vkp, 0.0f);
+        // (+ STREAM_ROWS rows: the stream kernel fetches whole stages of ring
+        // weights and may run past the last band's rows)
+        P.vring.assign((total + STREAM_ROWS) * vkp, 0.0f);
         for (const Band& b : P.bands) {
             for (int k = b.dy0; k < b.dy0 + b.ndy; ++k) {
                 int slot = (k - b.dy0) % vk;
@@ -381,6 +396,35 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
                     P.vring[(size_t(b.woff) + (r - b.r0)) * vkp + slot]
                         = gy.w[gy.woff[k] + j];
                 }
+            }
+        }
+        // The stream kernel's view of the same weights: per source row, slot i
+        // is the weight of the i-th OLDEST open destination row (the kernel
+        // rotates its accumulators when a row completes instead of indexing
+        // them), and the last float of the row holds, as an integer, how many
+        // destination rows complete with this source row.
+        const int vsw = stream_wrow(vk);
+        P.vstream.assign((total + STREAM_ROWS) * vsw, 0.0f);
+        for (const Band& b : P.bands) {
+            int oldest = b.dy0;  // first dst row of the band not yet complete
+            for (int r = b.r0; r < b.r0 + b.nrows; ++r) {
+                float* row = &P.vstream[(size_t(b.woff) + (r - b.r0)) * vsw];
+                while (oldest < b.dy0 + b.ndy && last[oldest] < r)
+                    ++oldest;
+                int done = 0, mix = 0;
+                for (int k = oldest; k < std::min(oldest + vk, b.dy0 + b.ndy); ++k) {
+                    if (gy.count[k] > 0 && r >= gy.first[k] && r < gy.first[k] + gy.count[k]) {
+                        row[k - oldest] = gy.w[gy.woff[k] + (r - gy.first[k])];
+                        if (gy.mixed[gy.woff[k] + (r - gy.first[k])])
+                            mix |= 1 << (k - oldest);
+                    }
+                }
+                for (int k = oldest; k < b.dy0 + b.ndy && last[k] == r; ++k)
+                    ++done;
+                // low byte: rows completing here; bits 8..: slots whose weight
+                // merges clamped taps of both signs
+                int32_t di = done | (mix << 8);
+                memcpy(&row[vsw - 1], &di, sizeof(di));
             }
         }
     } else if (!build_v_gather(gy, first, vt, src_h, P)) {

@@ -18,9 +18,11 @@ struct FusedPlan {
     int ht = 0;
     std::vector<int32_t> hfirst;
     std::vector<float> hw;
+    std::vector<int32_t> hmix;  // stream kernel: mixed-sign merged taps per pair
     // V pass
     int vk = 0;  // ring size, 0 = gather
     std::vector<float> vring;
+    std::vector<float> vstream;  // stream kernel: rotated ring weights + completion counts
     std::vector<int32_t> vlast;
     int vt = 0;
     std::vector<int32_t> vfirst;
@@ -37,6 +39,6 @@ struct FusedPlan {
 // what the fused kernel instantiates (then the exact kernel runs).
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan);
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align = 4);
 
 }  // namespace b2r

@@ -204,9 +204,14 @@ copy_d2h_2d(void* hdst, size_t dpitch, const void* dsrc, size_t spitch, size_t r
             for (size_t r = 0; r < nrows && e == cudaSuccess; r += chunk) {
                 const size_t n = std::min(chunk, nrows - r);
                 drain(slot);
-                e = cudaMemcpy2DAsync(R.ring.buf[slot], rowbytes,
-                                      (const unsigned char*)dsrc + r * spitch, spitch, rowbytes, n,
-                                      cudaMemcpyDeviceToHost, st);
+                // the ring is shared with copy_h2d_2d, which returns with its
+                // slots still in flight (possibly on another stream): wait for
+                // whoever used this slot last before the DMA overwrites it
+                unsigned char* pb = (unsigned char*)R.ring.acquire(slot);
+                e = cudaMemcpy2DAsync(pb, rowbytes, (const unsigned char*)dsrc + r * spitch,
+                                      spitch, rowbytes, n, cudaMemcpyDeviceToHost, st);
+                if (e != cudaSuccess)
+                    break;
                 R.ring.release_after(slot, st);
                 pending[slot].host = (unsigned char*)hdst + r * dpitch;
                 pending[slot].rows = n;

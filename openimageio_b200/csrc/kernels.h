@@ -7,6 +7,10 @@
 #    include <cuda_runtime.h>
 #endif
 
+#if defined(__CUDACC__)
+struct CUtensorMap_st;  // <cuda.h>
+#endif
+
 namespace b2r {
 
 // Programmatic dependent launch (PDL): every resize kernel is launched with
@@ -143,6 +147,54 @@ fused_min_ctas(int es, int vk)
     return (void)es, (void)vk, 3;
 }
 
+// Stream variant (stream_kernel.cuh): persistent, warp-specialised -- one TMA
+// producer warp, STREAM_VTHREADS V-pass threads, STREAM_HTHREADS H-pass
+// threads per CTA, one CTA per SM.
+constexpr int STREAM_ROWS     = 4;    // source rows per TMA stage
+constexpr int STREAM_VTHREADS = 256;
+constexpr int STREAM_HTHREADS = 256;
+// warpgroup 0 holds the producer warp (its other three warps give their
+// registers away with setmaxnreg and exit), warpgroups 1-2 the V threads, 3-4
+// the H threads
+constexpr int STREAM_PTHREADS = 128;
+constexpr int STREAM_THREADS  = STREAM_PTHREADS + STREAM_VTHREADS + STREAM_HTHREADS;
+constexpr int STREAM_SMEM_MAX = 227 * 1024;
+// V-filtered rows per hand-over batch (w2: elements per V thread / 4)
+B2R_HD constexpr int
+stream_batch(int vk, int w2)
+{
+    return (void)vk, w2 == 1 ? 12 : 6;
+}
+B2R_HD constexpr int
+stream_pitch_bytes(int w2)
+{
+    return 4 * (STREAM_VTHREADS * w2 / 4 + 2) * 16;
+}
+// floats per source row of the stream kernel's ring table: vk weights (oldest
+// open destination row first) + the completion count, padded to float4 loads
+B2R_HD constexpr int
+stream_wrow(int vk)
+{
+    return (vk + 1 + 3) & ~3;
+}
+B2R_HD constexpr int
+stream_stage_bytes(int es, int vk, int w2)
+{
+    return (STREAM_VTHREADS * 4 * w2 * es * STREAM_ROWS + STREAM_ROWS * stream_wrow(vk) * 4 + 127)
+           & ~127;
+}
+// stages of the TMA ring: what fits beside the two V-row buffers, at most 8
+B2R_HD constexpr int
+stream_stages(int es, int vk, int w2)
+{
+    return (STREAM_SMEM_MAX - 2 * stream_batch(vk, w2) * stream_pitch_bytes(w2) - 1024)
+                       / stream_stage_bytes(es, vk, w2)
+                   >= 8
+               ? 8
+               : (STREAM_SMEM_MAX - 2 * stream_batch(vk, w2) * stream_pitch_bytes(w2) - 1024)
+                     / stream_stage_bytes(es, vk, w2);
+}
+
 // Expand variant (upsizing in y: the V pass gathers): strips are up to
 // EXPAND_GROUPS groups of four dst columns wide, a group per H-pass thread.
 constexpr int EXPAND_GROUPS = 256;
@@ -187,10 +239,14 @@ struct FusedParams {
     int vk;
     const float* vring;  // [(woff + r - r0) * vk + slot]
     const int* vlast;    // [roi_h] source row after which dst row completes
+    const float* vstream;  // stream kernel: [(woff + r - r0) * stream_wrow(vk) + i]
+    const int* hmix;       // stream kernel: [ceil(roi_w/2)] mixed-sign merged H taps
     // V pass, gather mode (vk == 0)
     int vt;
     const int* vfirst;   // [roi_h]
     const float* vw;     // [roi_h * vt]
+    // stream kernel: data-window row that is row 0 of the TMA tensor map
+    int tma_row0;
 };
 // Returns false when no instantiation matches (srctype, nch, vk, ht).
 bool
@@ -198,6 +254,19 @@ fused_supported(int srctype, int nch, int vk, int ht);
 bool
 expand_supported(int srctype, int nch, int vt, int ht);
 typedef void (*FusedKernel)(const FusedParams, int, int);
+// stream kernel (TMA): ring-mode shapes with a compile-time H window whose
+// source rows are 16-byte aligned.  `w2`: 1 or 2 (4 or 8 elements per V thread).
+#if defined(__CUDACC__)
+typedef void (*StreamKernel)(const ::CUtensorMap_st, const FusedParams);
+#endif
+bool
+stream_supported(int srctype, int nch, int vk, int ht, int w2);
+// tma_base: address of element 0 of data-window row p.tma_row0; tma_rows: rows
+// that exist from there on.  Returns 0, or a negative value when the tensor
+// map could not be made (the caller falls back to the fused kernel).
+int
+launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma_rows,
+                     int sms, void* stream);
 typedef void (*ExpandKernel)(const FusedParams, int);
 // resident CTAs per SM for this shape (occupancy query), 0 on error
 int

@@ -1,0 +1,55 @@
+// stream_inst.cu -- instantiations of resize_stream_kernel for one (source
+// type, channel count); compiled 16 times with -DB2R_INST_ST=<0..3>
+// -DB2R_INST_NCH=<1..4> so the build parallelises (see Makefile).
+#include "stream_kernel.cuh"
+
+#ifndef B2R_INST_ST
+#    error "compile with -DB2R_INST_ST=<0..3> -DB2R_INST_NCH=<1..4>"
+#endif
+
+namespace b2r {
+
+template<int VK, int W2>
+static StreamKernel
+pick_ht(int ht, int* smem)
+{
+    *smem = StreamSmem<B2R_INST_ST, VK, W2>::TOTAL;
+    switch (ht) {
+    case 6: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 6, W2>;
+    case 10: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 10, W2>;
+    case 14: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 14, W2>;
+    case 16: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 16, W2>;
+    }
+    return nullptr;
+}
+
+template<int W2>
+static StreamKernel
+pick_vk(int vk, int ht, int* smem)
+{
+    switch (vk) {
+    case 2: return pick_ht<2, W2>(ht, smem);
+    case 4: return pick_ht<4, W2>(ht, smem);
+    case 6: return pick_ht<6, W2>(ht, smem);
+    case 8: return pick_ht<8, W2>(ht, smem);
+    }
+    return nullptr;
+}
+
+#define B2R_CAT3(a, b, c) a##b##_##c
+#define B2R_NAME(st, nch) B2R_CAT3(stream_lookup_, st, nch)
+
+StreamKernel
+B2R_NAME(B2R_INST_ST, B2R_INST_NCH)(int vk, int ht, int w2, int* smem)
+{
+    if (w2 == 1)
+        return pick_vk<1>(vk, ht, smem);
+#if B2R_INST_ST != 3
+    // 8 elements per V thread: 1- and 2-byte sources only
+    if (w2 == 2)
+        return pick_vk<2>(vk, ht, smem);
+#endif
+    return nullptr;
+}
+
+}  // namespace b2r

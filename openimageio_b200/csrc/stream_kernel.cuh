@@ -1,0 +1,580 @@
+// stream_kernel.cuh -- the hot path for downsizing (ring-mode) shapes:
+// a persistent, warp-specialised version of the fused two-pass resize.
+//
+// One CTA per SM walks a static list of work items (column strip x row band
+// of the dst ROI, the same decomposition as resize_fused_kernel).  Three
+// roles run concurrently inside the CTA:
+//
+//   producer  warp 0, one elected lane (its warpgroup gives its registers
+//             to the H warps with setmaxnreg).  Streams the band's source rows
+//             HBM -> shared memory with TMA: per stage STREAM_ROWS rows of the
+//             strip as 2-D tensor-map boxes (cp.async.bulk.tensor.2d, 256
+//             elements x STREAM_ROWS rows each) plus the ring weights of those
+//             rows (cp.async.bulk), all completing on the stage's `full`
+//             mbarrier.  A stage is re-armed when the V warps have arrived on
+//             its `empty` mbarrier.  The producer runs ahead across item
+//             boundaries, so the pipe never drains between items.
+//   V warps   8 warps; thread t owns 4*W2 consecutive source elements of the
+//             strip.  Every source row is read from shared memory ONCE and
+//             scattered into the VK destination rows open at that moment
+//             (register accumulators, ring weights from the stage).  A
+//             completed destination row is parked in one of two V-row
+//             buffers for the H warps.
+//   H warps   8 warps; thread = two adjacent dst columns x NR rows of the
+//             batch, H weights held in registers for the whole item; the
+//             quantise + store epilogue of resize_fused_kernel.
+//
+// V and H overlap: while the H warps filter batch n the V warps fill batch
+// n+1 (named barriers 1..4 hand the two buffers back and forth).
+//
+// Zero weights / non-finite pixels.  The reference never multiplies a zero
+// weight (imagebufalgo_xform.cpp:749-759).  Here a V thread tests every
+// float / half source group it loads; a group with an Inf/NaN takes a
+// predicated accumulate that skips zero ring weights (warp-divergent, rare).
+// The H pass screens its outputs; a thread with a non-finite one re-filters
+// its rows from the parked V rows with the zero taps skipped.  So the result
+// has the reference's finite / Inf / NaN pattern without a second kernel.
+#pragma once
+
+#include "fused_kernel.cuh"
+
+#include <cuda.h>  // CUtensorMap
+
+namespace b2r {
+
+// ---- mbarrier / TMA wrappers (PTX) ---------------------------------------
+__device__ __forceinline__ void
+mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void
+mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void
+mbar_arrive(unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void
+mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "B2R_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra B2R_DONE;\n"
+                 "bra B2R_WAIT;\n"
+                 "B2R_DONE:\n"
+                 "}" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void
+tma_load_2d(unsigned smem_dst, const CUtensorMap* map, int c0, int c1, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void
+bulk_load_1d(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void
+named_bar_sync(int id, int count)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void
+named_bar_arrive(int id, int count)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// ---- geometry ---------------------------------------------------------------
+// W2 = 1: a V thread owns 4 elements (the strip geometry of the fused kernel);
+// W2 = 2: 8 elements -- strips twice as wide, half as many rows per batch.
+template<int W2> struct StreamGeom {
+    static constexpr int EPT     = 4 * W2;                    // elements per V thread
+    static constexpr int VPIX    = STREAM_VTHREADS * W2;      // pixels a V row holds
+    static constexpr int HCOLS   = FUSED_HCOLS * W2;          // dst columns per strip
+    static constexpr int HPAIRS  = HCOLS / 2;
+    static constexpr int ROWG    = STREAM_HTHREADS / HPAIRS;  // H row groups (4 / 2)
+    static constexpr int PLANE   = VPIX / 4 + 2;              // slots per plane
+    static constexpr int PITCH_B = 4 * PLANE * 16;            // bytes per V row
+};
+template<int W2>
+__device__ __forceinline__ int
+stream_planar_byte(int q)
+{
+    return ((q >> 2) + (q & 3) * StreamGeom<W2>::PLANE) * 16;
+}
+
+// Where a V thread parks its EPT filtered elements.  NCH == 4: EPT/4 planar
+// float4 pixels; otherwise one scalar offset per element (padded pixels).
+template<int NCH, int W2> struct StreamPark {
+    static constexpr int EPT = 4 * W2;
+    int off[NCH == 4 ? W2 : EPT];
+    __device__ __forceinline__ void init(int e0, int v)
+    {
+        if (NCH == 4) {
+#pragma unroll
+            for (int k = 0; k < W2; ++k)
+                off[k] = stream_planar_byte<W2>(W2 * v + k);
+        } else {
+            const int px0 = e0 / NCH;
+#pragma unroll
+            for (int k = 0; k < (NCH == 4 ? W2 : EPT); ++k) {
+                int E  = e0 + EPT * v + k;
+                int px = E / NCH;
+                off[k] = stream_planar_byte<W2>(px - px0) + (E - NCH * px) * 4;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(unsigned row, const float4 (&a)[W2]) const
+    {
+        if (NCH == 4) {
+#pragma unroll
+            for (int k = 0; k < W2; ++k)
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[k]),
+                             "f"(a[k].x), "f"(a[k].y), "f"(a[k].z), "f"(a[k].w)
+                             : "memory");
+        } else {
+#pragma unroll
+            for (int k = 0; k < W2; ++k) {
+                constexpr int S = NCH == 4 ? 0 : 1;  // keeps the indices in range for NCH == 4
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k)]), "f"(a[k].x)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 1)]),
+                             "f"(a[k].y)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 2)]),
+                             "f"(a[k].z)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 3)]),
+                             "f"(a[k].w)
+                             : "memory");
+            }
+        }
+    }
+};
+
+// ---- H pass over one batch ---------------------------------------------------
+// Same arithmetic as fused_hpass (two adjacent dst columns per thread from one
+// window of HT parked pixels); the weights stay in registers for the whole
+// item and the thread's NR rows are filtered one after the other (HT
+// independent loads and four FFMA2 chains per row are enough to keep the
+// pipes fed; interleaving rows would not fit the register budget).
+// FP: screen the outputs and re-filter with the zero taps skipped.
+template<int NCH, int HT, int W2, int NR, bool FP>
+__device__ __forceinline__ void
+stream_hpass(const FusedParams& p, unsigned vrows, int nb, int dyb, int dxA, bool has_b,
+             const int (&hb)[4], const float2 (&hw)[HT], int hmix, int hr)
+{
+    using G = StreamGeom<W2>;
+    const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
+    unsigned char* dp = p.dst + (long long)(dyb + hr) * p.dst_ystride
+                        + (long long)dxA * (NCH * des);
+#pragma unroll 1
+    for (int k = 0; k < NR; ++k) {
+        if (hr + k * G::ROWG >= nb)
+            break;
+        auto ldv = [&](int j) -> float4 {
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(vrows + hb[j & 3] + (j >> 2) * 16));
+            return v;
+        };
+        float4 aA = make_float4(0.f, 0.f, 0.f, 0.f), aB = aA;
+#pragma unroll
+        for (int j = 0; j < HT; ++j) {
+            const float4 v = ldv(j);
+            fma4(aA, hw[j].x, v);
+            fma4(aB, hw[j].y, v);
+        }
+        if (FP) {
+            const float t = ((aA.x + aA.y) + (aA.z + aA.w)) + ((aB.x + aB.y) + (aB.z + aB.w));
+            if (!(fabsf(t) <= 3.402823466e+38f)) {
+                // an Inf/NaN reached this window: filter again the way the
+                // reference does, never touching a zero weight
+                aA = aB = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < HT; ++j) {
+                    const float4 v = ldv(j);
+                    if (hw[j].x != 0.0f)
+                        fma4(aA, hw[j].x, v);
+                    if (hw[j].y != 0.0f)
+                        fma4(aB, hw[j].y, v);
+                    // a weight that stands for clamped taps of both signs:
+                    // w1*Inf + w2*Inf is NaN in the reference
+                    if ((hmix >> j) & 1)
+                        fma4(aA, 0.0f, v);
+                    if ((hmix >> (16 + j)) & 1)
+                        fma4(aB, 0.0f, v);
+                }
+            }
+        }
+        const float ca[4] = { aA.x, aA.y, aA.z, aA.w };
+        const float cb[4] = { aB.x, aB.y, aB.z, aB.w };
+        float oa[NCH], ob[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            oa[c] = ca[c];
+            ob[c] = cb[c];
+        }
+        store_pixel<NCH>(p, dp, des, oa);
+        if (has_b)
+            store_pixel<NCH>(p, dp + NCH * des, des, ob);
+        dp += (long long)G::ROWG * p.dst_ystride;
+        vrows += G::ROWG * G::PITCH_B;
+    }
+}
+
+// Raw 16-byte group -> W2 float4 values.
+template<int ST, int W2>
+__device__ __forceinline__ void
+stream_convert(const uint4& r, float4 (&v)[W2])
+{
+    if (W2 == 1) {
+        v[0] = convert_raw4<ST>(r);
+    } else {
+        // 8 elements: float never gets here (es == 4 -> W2 == 1)
+        if (SrcTraits<ST>::es == 2) {
+            v[0]      = convert_raw4<ST>(make_uint4(r.x, r.y, 0u, 0u));
+            v[W2 - 1] = convert_raw4<ST>(make_uint4(r.z, r.w, 0u, 0u));
+        } else {
+            v[0]      = convert_raw4<ST>(make_uint4(r.x, 0u, 0u, 0u));
+            v[W2 - 1] = convert_raw4<ST>(make_uint4(r.y, 0u, 0u, 0u));
+        }
+    }
+}
+
+// Shared memory carve-up (bytes), all regions 128-byte aligned:
+//   stages  NST x STAGE_B   STAGE_B = NBOX boxes of (ROWS x 256 elements) + ROWS ring-weight rows
+//   vbuf    2 x BATCH x PITCH_B
+//   bars    2 x NST mbarriers
+template<int ST, int VK, int W2> struct StreamSmem {
+    using G = StreamGeom<W2>;
+    static constexpr int es       = SrcTraits<ST>::es;
+    static constexpr int ROWS     = STREAM_ROWS;
+    static constexpr int BOXW     = 256;  // elements per box row (the TMA limit)
+    static constexpr int NBOX     = STREAM_VTHREADS * G::EPT / BOXW;
+    static constexpr int BOX_ROWB = BOXW * es;
+    static constexpr int BOX_B    = ROWS * BOX_ROWB;
+    static constexpr int WROW     = stream_wrow(VK);  // floats per ring-table row
+    static constexpr int WROWB    = WROW * 4;
+    static constexpr int DATA_B   = NBOX * BOX_B;
+    static constexpr int STAGE_B  = (DATA_B + ROWS * WROWB + 127) & ~127;
+    static constexpr int BATCH    = stream_batch(VK, W2);
+    static constexpr int NR       = BATCH / G::ROWG;
+    static constexpr int VBUF_B   = BATCH * G::PITCH_B;
+    static constexpr int NST      = stream_stages(es, VK, W2);
+    static constexpr int BARS_OFF = NST * STAGE_B + 2 * VBUF_B;
+    static constexpr int TOTAL    = BARS_OFF + 2 * NST * 8 + 64;
+};
+
+template<int ST, int NCH, int VK, int HT, int W2>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p)
+{
+    using G = StreamGeom<W2>;
+    using S = StreamSmem<ST, VK, W2>;
+    constexpr int es   = S::es;
+    constexpr int ROWS = S::ROWS;
+    constexpr int NST  = S::NST;
+    constexpr int WROW = S::WROW;
+    constexpr int BATCH = S::BATCH;
+    constexpr int NR    = S::NR;
+    constexpr bool FP   = (ST == ST_FLOAT || ST == ST_HALF);
+    static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
+
+    extern __shared__ __align__(1024) unsigned char stream_smem[];
+    pdl_prologue();
+    const unsigned smem0  = smem_u32(stream_smem);
+    const unsigned vbuf0  = smem0 + NST * S::STAGE_B;
+    const unsigned bars   = smem0 + S::BARS_OFF;  // full[NST], empty[NST]
+    const int warp        = threadIdx.x >> 5;
+    const int lane        = threadIdx.x & 31;
+    const int nitems      = p.nstrips * p.nbands;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (NST + s), STREAM_VTHREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (NCH < 4) {
+        // padded V rows: the unused lanes are never written, they must read as zero
+        for (int i = threadIdx.x; i < 2 * S::VBUF_B / 16; i += STREAM_THREADS)
+            reinterpret_cast<uint4*>(stream_smem + NST * S::STAGE_B)[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+
+    // batches this CTA will hand over in total (both consumer roles count them
+    // the same way; the last two hand-backs are not awaited by anybody)
+    if (warp < STREAM_PTHREADS / 32) {
+        // ================= producer ========================================
+        // (one lane of warp 0; the warpgroup hands its registers to the H warps)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (warp == 0 && lane == 0) {
+            int stage = 0;
+            unsigned phase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const Strip strip = p.strips[item % p.nstrips];
+                const Band band   = p.bands[item / p.nstrips];
+                const int nst     = (band.nrows + ROWS - 1) / ROWS;
+                const int nbox    = min(S::NBOX, (strip.nvec * G::EPT + S::BOXW - 1) / S::BOXW);
+                const unsigned tx = nbox * S::BOX_B + ROWS * S::WROWB;
+                const float* gw   = p.vstream + (size_t)band.woff * WROW;
+                int row           = band.r0 - p.tma_row0;
+                for (int i = 0; i < nst; ++i) {
+                    const unsigned full  = bars + 8 * stage;
+                    const unsigned empty = bars + 8 * (NST + stage);
+                    mbar_wait(empty, phase ^ 1);
+                    mbar_expect_tx(full, tx);
+                    const unsigned sb = smem0 + stage * S::STAGE_B;
+                    for (int b = 0; b < nbox; ++b)
+                        tma_load_2d(sb + b * S::BOX_B, &tmap, strip.e0 + b * S::BOXW, row, full);
+                    bulk_load_1d(sb + S::DATA_B, gw, ROWS * S::WROWB, full);
+                    gw += ROWS * WROW;
+                    row += ROWS;
+                    if (++stage == NST) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp < (STREAM_PTHREADS + STREAM_VTHREADS) / 32) {
+        // ================= V warps =========================================
+        const int tid = threadIdx.x - STREAM_PTHREADS;
+        int stage = 0;
+        unsigned phase = 0;
+        int nbatch = 0;  // batches handed over so far (whole kernel)
+        // this thread's 4*W2*es bytes inside a stage
+        const int toff = ((tid * G::EPT) / S::BOXW) * S::BOX_B + ((tid * G::EPT) % S::BOXW) * es;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const Strip strip = p.strips[item % p.nstrips];
+            const Band band   = p.bands[item / p.nstrips];
+            const bool vactive = tid < strip.nvec;
+            StreamPark<NCH, W2> park;
+            park.init(strip.e0, tid);
+            // acc[0] is the oldest open destination row (the ring table is
+            // laid out the same way).  When a row completes it is parked and
+            // the others move up one place -- not with register moves: the
+            // NEXT source row's FFMA2s read acc[k+1] and write acc[k]
+            // (`shift`), so the rotation costs nothing.
+            float4 acc[VK][W2];
+#pragma unroll
+            for (int k = 0; k < VK; ++k)
+#pragma unroll
+                for (int h = 0; h < W2; ++h)
+                    acc[k][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            bool shift = false;  // acc[0] was parked after the previous source row
+            int ndone  = 0;      // destination rows of the band completed so far
+            int nb     = 0;      // rows parked in the open batch
+            unsigned prow = vbuf0 + (nbatch & 1) * S::VBUF_B;  // where the next row is parked
+            // park acc[0] as the next destination row of the batch
+            auto park_oldest = [&]() {
+                if (nb == 0 && nbatch >= 2)  // the H warps are done with this buffer
+                    named_bar_sync(3 + (nbatch & 1), STREAM_VTHREADS + STREAM_HTHREADS);
+                if (vactive)
+                    park.store(prow, acc[0]);
+                prow += G::PITCH_B;
+                ++nb;
+                ++ndone;
+                if (nb == BATCH || ndone == band.ndy) {
+                    named_bar_arrive(1 + (nbatch & 1), STREAM_VTHREADS + STREAM_HTHREADS);
+                    ++nbatch;
+                    nb   = 0;
+                    prow = vbuf0 + (nbatch & 1) * S::VBUF_B;
+                }
+            };
+            // explicit rotation (only when a second row completes with the
+            // same source row: edges, ratios near 1)
+            auto rotate = [&]() {
+#pragma unroll
+                for (int k = 0; k + 1 < VK; ++k)
+#pragma unroll
+                    for (int h = 0; h < W2; ++h)
+                        acc[k][h] = acc[k + 1][h];
+#pragma unroll
+                for (int h = 0; h < W2; ++h)
+                    acc[VK - 1][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            for (int rbase = 0; rbase < band.nrows; rbase += ROWS) {
+                const unsigned char* sb = stream_smem + stage * S::STAGE_B;
+                mbar_wait(bars + 8 * stage, phase);
+                // the stage's rows of this thread and their ring-table rows
+                uint4 raw[ROWS];
+                float4 wv[ROWS][WROW / 4];
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    const unsigned char* a = sb + toff + j * S::BOX_ROWB;
+                    if (G::EPT * es == 16)
+                        raw[j] = *reinterpret_cast<const uint4*>(a);
+                    else if (G::EPT * es == 8) {
+                        uint2 u = *reinterpret_cast<const uint2*>(a);
+                        raw[j]  = make_uint4(u.x, u.y, 0u, 0u);
+                    } else
+                        raw[j] = make_uint4(*reinterpret_cast<const unsigned*>(a), 0u, 0u, 0u);
+#pragma unroll
+                    for (int k = 0; k < WROW / 4; ++k)
+                        wv[j][k] = *reinterpret_cast<const float4*>(sb + S::DATA_B + j * S::WROWB
+                                                                    + k * 16);
+                }
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    if (rbase + j < band.nrows) {
+                        float w[WROW];
+#pragma unroll
+                        for (int k = 0; k < WROW / 4; ++k) {
+                            w[4 * k]     = wv[j][k].x;
+                            w[4 * k + 1] = wv[j][k].y;
+                            w[4 * k + 2] = wv[j][k].z;
+                            w[4 * k + 3] = wv[j][k].w;
+                        }
+                        // low byte: rows completing with this source row; bits
+                        // 8..: slots whose weight merges clamped taps of both signs
+                        const int info = __float_as_int(w[WROW - 1]);
+                        float4 v[W2];
+                        stream_convert<ST, W2>(raw[j], v);
+                        bool bad = false;
+                        if (FP) {
+                            float q = 0.0f;
+#pragma unroll
+                            for (int h = 0; h < W2; ++h)
+                                q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                            bad = !(fabsf(q) <= 3.402823466e+38f);
+                        }
+                        if (FP && bad) {
+                            // Inf/NaN in this group: never let it meet a zero
+                            // weight; a weight that stands for clamped taps of
+                            // both signs turns it into NaN (w1*Inf + w2*Inf)
+                            if (shift)
+                                rotate();
+#pragma unroll
+                            for (int k = 0; k < VK; ++k) {
+                                if (w[k] != 0.0f) {
+#pragma unroll
+                                    for (int h = 0; h < W2; ++h)
+                                        fma4(acc[k][h], w[k], v[h]);
+                                }
+                                if ((info >> (8 + k)) & 1) {
+#pragma unroll
+                                    for (int h = 0; h < W2; ++h)
+                                        fma4(acc[k][h], 0.0f, v[h]);
+                                }
+                            }
+                        } else if (shift) {
+#pragma unroll
+                            for (int k = 0; k < VK; ++k)
+#pragma unroll
+                                for (int h = 0; h < W2; ++h) {
+                                    // acc[k] = w[k] * v + acc[k + 1]
+                                    const float4 c = (k + 1 < VK) ? acc[k + 1][h]
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                                    const float2 ww = make_float2(w[k], w[k]);
+                                    float2 lo = __ffma2_rn(ww, make_float2(v[h].x, v[h].y),
+                                                           make_float2(c.x, c.y));
+                                    float2 hi = __ffma2_rn(ww, make_float2(v[h].z, v[h].w),
+                                                           make_float2(c.z, c.w));
+                                    acc[k][h] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                                }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < VK; ++k)
+#pragma unroll
+                                for (int h = 0; h < W2; ++h)
+                                    fma4(acc[k][h], w[k], v[h]);
+                        }
+                        if (FP)
+                            __syncwarp();
+                        // destination rows that complete with this source row
+                        int ne = info & 0xff;
+                        shift  = ne > 0;
+                        if (ne > 0) {
+                            park_oldest();
+#pragma unroll 1
+                            while (--ne > 0) {
+                                rotate();
+                                park_oldest();
+                            }
+                        }
+                    }
+                }
+                // stage consumed: hand it back to the producer
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(bars + 8 * (NST + stage));
+                if (++stage == NST) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================= H warps =========================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+        const int tid = threadIdx.x - STREAM_PTHREADS - STREAM_VTHREADS;
+        const int hp  = tid % G::HPAIRS;
+        const int hr  = tid / G::HPAIRS;
+        int nbatch    = 0;
+        // total batches of this CTA: the last two hand-backs have no taker
+        int total = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x)
+            total += (p.bands[item / p.nstrips].ndy + BATCH - 1) / BATCH;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const Strip strip = p.strips[item % p.nstrips];
+            const Band band   = p.bands[item / p.nstrips];
+            const bool pair_active = 2 * hp < strip.ndx;
+            const bool has_b       = 2 * hp + 1 < strip.ndx;
+            const int dxA          = strip.dx0 + 2 * hp;
+            const int gp           = (strip.dx0 >> 1) + hp;  // pair index in the ROI
+            float2 hw[HT];
+            int hb[4] = { 0, 0, 0, 0 };
+            int hmix  = 0;
+            if (pair_active) {
+                if (FP)
+                    hmix = __ldg(p.hmix + gp);
+                const float2* g = reinterpret_cast<const float2*>(p.hw) + (size_t)gp * HT;
+#pragma unroll
+                for (int j = 0; j < HT; ++j)
+                    hw[j] = __ldg(g + j);
+                const int q = __ldg(p.hfirst + gp) - strip.e0 / NCH;  // window start in the strip
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    hb[k] = stream_planar_byte<W2>(q + k) + hr * G::PITCH_B;
+            } else {
+#pragma unroll
+                for (int j = 0; j < HT; ++j)
+                    hw[j] = make_float2(0.f, 0.f);
+            }
+            const int dy_end = band.dy0 + band.ndy;
+            for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
+                const int nb = min(BATCH, dy_end - dyb);
+                const int b  = nbatch & 1;
+                named_bar_sync(1 + b, STREAM_VTHREADS + STREAM_HTHREADS);
+                if (pair_active)
+                    stream_hpass<NCH, HT, W2, NR, FP>(p, vbuf0 + b * S::VBUF_B, nb, dyb, dxA,
+                                                      has_b, hb, hw, hmix, hr);
+                ++nbatch;
+                if (nbatch + 2 <= total)
+                    named_bar_arrive(3 + b, STREAM_VTHREADS + STREAM_HTHREADS);
+            }
+        }
+    }
+}
+
+}  // namespace b2r
