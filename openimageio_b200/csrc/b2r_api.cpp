@@ -154,6 +154,17 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
     *row1 = hi - src.y;
 }
 
+// B2R_STREAM=0 keeps ring-mode shapes on resize_fused_kernel (A/B runs)
+bool
+stream_enabled()
+{
+    static const bool on = [] {
+        const char* e = getenv("B2R_STREAM");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static bool
 plan_supported(int basetype, int nch, const FusedPlan& fp)
 {
@@ -165,7 +176,7 @@ int
 get_plan(int device, const b2r_image& dst, const b2r_image& src,
          const b2r_roi& roi, const Filter2D& filter, int nch, int cta_slots,
          cudaStream_t stream, std::shared_ptr<DevicePlan>* out, char* err,
-         size_t errlen)
+         size_t errlen, bool tma_ok = false)
 {
     PlanKey key;
     key.device = device;
@@ -178,7 +189,9 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     key.fh    = filter.height();
     key.fname = std::string(filter.name());
     key.nch   = nch;
-    key.st    = src.basetype;
+    // source rows TMA can fetch (16-byte aligned base and pitch) get the stream
+    // kernel's strip geometry: part of the key
+    key.st    = src.basetype | (tma_ok ? 0x100 : 0);
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
@@ -217,12 +230,26 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
            o_vf = 0, o_vw = 0, o_vs = 0, o_hm = 0;
     if (filter.separable()) {
         AxisGather ax, ay;
+        const int e0a = 16 / basetype_size(src.basetype);
+        const int sms = cta_slots / 3;
         bool ok = build_axis_gather(gx, tx, &ax, axis_overscan(gy))
-                  && build_axis_gather(gy, ty, &ay, axis_overscan(gx))
-                  && plan_fused(ax, ay, nch, src.width, src.height, cta_slots,
-                                &plan->fp, 16 / basetype_size(src.basetype))
-                  && plan_supported(src.basetype, nch, plan->fp);
-        if (ok) {
+                  && build_axis_gather(gy, ty, &ay, axis_overscan(gx));
+        // first choice: the persistent TMA kernel with 512 V threads (wide
+        // strips, two work items per SM); it needs a ring-mode shape with a
+        // compile-time H window and enough work to fill the SMs that way
+        bool stream_plan = false;
+        if (ok && tma_ok && stream_enabled()) {
+            stream_plan = plan_fused(ax, ay, nch, src.width, src.height, sms * 2, &plan->fp,
+                                     e0a, 2)
+                          && plan->fp.w2 == 2 && !plan->fp.expand && plan->fp.vk > 0
+                          && stream_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht, 2)
+                          && (int)(plan->fp.strips.size() * plan->fp.bands.size()) >= sms;
+        }
+        ok = ok
+             && (stream_plan
+                 || (plan_fused(ax, ay, nch, src.width, src.height, cta_slots, &plan->fp, e0a)
+                     && plan_supported(src.basetype, nch, plan->fp)));
+        if (ok && !stream_plan) {
             // the band count was sized for an assumed number of resident CTAs
             // per SM; ask the runtime what this shape really gets and re-plan
             // when it differs (one wave, no ragged tail)
@@ -236,10 +263,9 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             q.expand  = plan->fp.expand ? 1 : 0;
             int per   = fused_ctas_per_sm(q, plan->fp.max_band_rows,
                                           plan->fp.max_band_dy, plan->fp.max_nvec);
-            int sms   = cta_slots / 3;
             if (per > 0 && per != 3)
                 ok = plan_fused(ax, ay, nch, src.width, src.height, sms * per,
-                                &plan->fp, 16 / basetype_size(src.basetype))
+                                &plan->fp, e0a)
                      && plan_supported(src.basetype, nch, plan->fp);
         }
         if (ok) {
@@ -345,17 +371,6 @@ next_flag(int dev)
     s.flag     = r.flags + (n % REDO_SLOTS);
     s.dirty    = r.maps + size_t(n % REDO_SLOTS) * REDO_MAP_CELLS;
     return s;
-}
-
-// B2R_STREAM=0 keeps ring-mode shapes on resize_fused_kernel (A/B runs)
-bool
-stream_enabled()
-{
-    static const bool on = [] {
-        const char* e = getenv("B2R_STREAM");
-        return !(e && e[0] == '0');
-    }();
-    return on;
 }
 
 int
@@ -687,9 +702,14 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         return resize_host_pipelined(dst, src, filter, roi, device, path, report,
                                      err, errlen);
 
+    // TMA needs 16-byte aligned source rows: host sources are staged with such
+    // a pitch, device sources are used where they lie
+    const bool tma_ok = src.xstride == (int64_t)src.nchannels * ses
+                        && (smem == B2R_MEM_HOST
+                            || (((uintptr_t)src.pixels & 15) == 0 && (src.ystride & 15) == 0));
     std::shared_ptr<DevicePlan> plan;
     rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 3, stream, &plan,
-                  err, errlen);
+                  err, errlen, tma_ok);
     if (rc)
         return rc;
     if (opt && opt->reserved[0] == 1)
@@ -877,17 +897,26 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         // persistent TMA kernel (stream_kernel.cuh); it resolves zero weights
         // under non-finite pixels itself, so no gated exact kernel follows.
         bool streamed = false;
-        if (!fp.expand && fp.vk > 0 && stream_enabled()
-            && stream_supported(src.basetype, nch, fp.vk, fp.ht, 1)) {
+        const int w2 = plan->fp.w2;
+        if (!fp.expand && fp.vk > 0 && tma_ok && stream_enabled()
+            && stream_supported(src.basetype, nch, fp.vk, fp.ht, w2)) {
             const int trow0 = src_staged ? plan->src_row0 : 0;
             const int trows = src_staged ? plan->src_row1 - plan->src_row0 + 1 : src.height;
             const unsigned char* tbase
                 = (const unsigned char*)dsrc + (long long)trow0 * srcd.ystride;
             fp.tma_row0        = trow0;
             fp.check_nonfinite = 0;
-            streamed = launch_resize_stream(fp, 1, tbase, trows, di.sms, stream) == 0;
+            streamed = launch_resize_stream(fp, w2, tbase, trows, di.sms, stream) == 0;
             if (!streamed)
                 fp.check_nonfinite = src_is_fp ? 1 : 0;
+        }
+        if (!streamed && w2 != 1) {
+            set_err(err, errlen, "resize: the stream kernel could not be launched");
+            if (src_staged)
+                cudaFreeAsync(src_alloc, stream);
+            if (dst_staged)
+                cudaFreeAsync(ddst, stream);
+            return B2R_ERR_CUDA;
         }
         if (!streamed)
             launch_resize_fused(fp, plan->fp.max_band_rows, plan->fp.max_band_dy,

@@ -185,7 +185,7 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
 
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan, int e0_align)
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align, int w2)
 {
     // strips start on a 16-byte boundary of the source row (e0_align elements):
     // the TMA boxes of the stream kernel need it, the other kernels need 4
@@ -308,6 +308,10 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     // V rows are parked as float4 pixels (1-3 channel rows padded): a row
     // holds FUSED_THREADS pixels, and a strip stages <= FUSED_THREADS
     // four-element groups.  Strips hold an even number of columns (pairs).
+    // (stream kernel, w2 = 2: strips twice as wide -- 512 V threads)
+    if (!(use_ring && P.ht <= 16) || w2 < 1 || w2 > 2)
+        w2 = 1;
+    P.w2 = w2;
     for (int dx0 = 0; dx0 < W;) {
         Strip s;
         s.dx0  = dx0;
@@ -315,12 +319,12 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         s.ndx  = 0;
         s.nvec = 0;
         const int px0 = s.e0 / nch;
-        while (dx0 + s.ndx < W && s.ndx < FUSED_HCOLS) {
+        while (dx0 + s.ndx < W && s.ndx < FUSED_HCOLS * w2) {
             // take columns two at a time: the pair's window end bounds both
             int pr   = (dx0 + s.ndx) / 2;
             int pend = P.hfirst[pr] + P.ht;          // one past the last px read
             int nvec = (pend * nch - s.e0 + 3) / 4;
-            if (nvec > FUSED_THREADS || pend - px0 > FUSED_THREADS)
+            if (nvec > FUSED_THREADS * w2 || pend - px0 > FUSED_THREADS * w2)
                 break;
             s.nvec = nvec;
             s.ndx += std::min(2, W - (dx0 + s.ndx));
@@ -335,7 +339,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     // ---------------- row bands -------------------------------------------
     const int nstrips = int(P.strips.size());
     int nbands        = std::max(1, cta_slots / std::max(1, nstrips));
-    const int min_rows = 8;
+    const int min_rows = w2 == 2 ? 32 : 8;
     nbands             = std::min(nbands, std::max(1, H / min_rows));
     // ring weights live in shared memory: keep a band's source rows bounded
     // ring row = vk weights padded to float4 loads
@@ -343,7 +347,9 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     // (wide H windows already spend shared memory on their weights: a smaller
     // ring-weight budget there keeps two CTAs resident per SM)
     const int ring_budget   = ((P.ht > 16 && P.ht <= 32) ? 10 : 24) * 1024;
-    const int max_rows_smem = use_ring ? (ring_budget / (4 * std::max(4, vkp))) : INT_MAX;
+    // (the stream kernel streams its ring table through the TMA stages: no bound)
+    const int max_rows_smem = (use_ring && w2 == 1) ? (ring_budget / (4 * std::max(4, vkp)))
+                                                    : INT_MAX;
     for (;;) {
         bool ok = true;
         P.bands.clear();
@@ -385,9 +391,9 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         size_t total = 0;
         for (const Band& b : P.bands)
             total += size_t(b.nrows);
-        // (+ STREAM_ROWS rows: the stream kernel fetches whole stages of ring
+        // (+ STREAM_MAXROWS rows: the stream kernel fetches whole stages of ring
         // weights and may run past the last band's rows)
-        P.vring.assign((total + STREAM_ROWS) * vkp, 0.0f);
+        P.vring.assign((total + STREAM_MAXROWS) * vkp, 0.0f);
         for (const Band& b : P.bands) {
             for (int k = b.dy0; k < b.dy0 + b.ndy; ++k) {
                 int slot = (k - b.dy0) % vk;
@@ -404,7 +410,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         // them), and the last float of the row holds, as an integer, how many
         // destination rows complete with this source row.
         const int vsw = stream_wrow(vk);
-        P.vstream.assign((total + STREAM_ROWS) * vsw, 0.0f);
+        P.vstream.assign((total + STREAM_MAXROWS) * vsw, 0.0f);
         for (const Band& b : P.bands) {
             int oldest = b.dy0;  // first dst row of the band not yet complete
             for (int r = b.r0; r < b.r0 + b.nrows; ++r) {

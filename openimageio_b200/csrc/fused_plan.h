@@ -12,6 +12,7 @@ struct FusedPlan {
     std::vector<Strip> strips;
     std::vector<Band> bands;
     bool expand = false;  // tables are for resize_expand_kernel
+    int w2 = 1;           // 2: strips sized for the stream kernel's 512 V threads
     int ngroups = 0;      // expand: groups of four dst columns in the ROI
     bool vrow_linear = false;  // expand: V-row layout (see expand_kernel.cuh)
     // H pass
@@ -39,6 +40,6 @@ struct FusedPlan {
 // what the fused kernel instantiates (then the exact kernel runs).
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan, int e0_align = 4);
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align = 4, int w2 = 1);
 
 }  // namespace b2r

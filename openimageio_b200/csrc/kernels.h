@@ -148,18 +148,22 @@ fused_min_ctas(int es, int vk)
 }
 
 // Stream variant (stream_kernel.cuh): persistent, warp-specialised -- one TMA
-// producer warp, STREAM_VTHREADS V-pass threads, STREAM_HTHREADS H-pass
+// producer warp, w2 * STREAM_VTHREADS V-pass threads, STREAM_HTHREADS H-pass
 // threads per CTA, one CTA per SM.
-constexpr int STREAM_ROWS     = 4;    // source rows per TMA stage
-constexpr int STREAM_VTHREADS = 256;
+constexpr int STREAM_VTHREADS = 256;  // V threads per unit of strip width (w2)
 constexpr int STREAM_HTHREADS = 256;
 // warpgroup 0 holds the producer warp (its other three warps give their
-// registers away with setmaxnreg and exit), warpgroups 1-2 the V threads, 3-4
-// the H threads
+// registers away with setmaxnreg and exit), then the V warps, then the H warps
 constexpr int STREAM_PTHREADS = 128;
-constexpr int STREAM_THREADS  = STREAM_PTHREADS + STREAM_VTHREADS + STREAM_HTHREADS;
 constexpr int STREAM_SMEM_MAX = 227 * 1024;
-// V-filtered rows per hand-over batch (w2: elements per V thread / 4)
+constexpr int STREAM_MAXROWS  = 4;  // rows per stage, at most (table padding)
+// source rows per TMA stage (w2 = 1: 4 rows of 256 chunks; w2 = 2: 2 rows of 512)
+B2R_HD constexpr int
+stream_rows(int w2)
+{
+    return w2 == 1 ? 4 : 2;
+}
+// V-filtered rows per hand-over batch
 B2R_HD constexpr int
 stream_batch(int vk, int w2)
 {
@@ -180,7 +184,8 @@ stream_wrow(int vk)
 B2R_HD constexpr int
 stream_stage_bytes(int es, int vk, int w2)
 {
-    return (STREAM_VTHREADS * 4 * w2 * es * STREAM_ROWS + STREAM_ROWS * stream_wrow(vk) * 4 + 127)
+    return (STREAM_VTHREADS * w2 * 4 * es * stream_rows(w2)
+            + stream_rows(w2) * stream_wrow(vk) * 4 + 127)
            & ~127;
 }
 // stages of the TMA ring: what fits beside the two V-row buffers, at most 8

@@ -44,11 +44,8 @@ B2R_NAME(B2R_INST_ST, B2R_INST_NCH)(int vk, int ht, int w2, int* smem)
 {
     if (w2 == 1)
         return pick_vk<1>(vk, ht, smem);
-#if B2R_INST_ST != 3
-    // 8 elements per V thread: 1- and 2-byte sources only
     if (w2 == 2)
         return pick_vk<2>(vk, ht, smem);
-#endif
     return nullptr;
 }
 

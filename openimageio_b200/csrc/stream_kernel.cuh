@@ -14,8 +14,8 @@
 //             mbarrier.  A stage is re-armed when the V warps have arrived on
 //             its `empty` mbarrier.  The producer runs ahead across item
 //             boundaries, so the pipe never drains between items.
-//   V warps   8 warps; thread t owns 4*W2 consecutive source elements of the
-//             strip.  Every source row is read from shared memory ONCE and
+//   V warps   8 (W2 = 1) or 16 (W2 = 2) warps; thread t owns 4 consecutive
+//             source elements of the strip.  Every source row is read from shared memory ONCE and
 //             scattered into the VK destination rows open at that moment
 //             (register accumulators, ring weights from the stage).  A
 //             completed destination row is parked in one of two V-row
@@ -101,16 +101,22 @@ named_bar_arrive(int id, int count)
 }
 
 // ---- geometry ---------------------------------------------------------------
-// W2 = 1: a V thread owns 4 elements (the strip geometry of the fused kernel);
-// W2 = 2: 8 elements -- strips twice as wide, half as many rows per batch.
+// W2 = 1: 256 V threads, the strip geometry of the fused kernel (<= 128 dst
+// columns, <= 256 source pixels); W2 = 2: 512 V threads, strips twice as wide,
+// half as many rows per hand-over batch.  A V thread always owns 4 elements.
 template<int W2> struct StreamGeom {
-    static constexpr int EPT     = 4 * W2;                    // elements per V thread
-    static constexpr int VPIX    = STREAM_VTHREADS * W2;      // pixels a V row holds
+    static constexpr int NVT     = STREAM_VTHREADS * W2;      // V threads
+    static constexpr int VPIX    = NVT;                       // pixels a V row holds
     static constexpr int HCOLS   = FUSED_HCOLS * W2;          // dst columns per strip
     static constexpr int HPAIRS  = HCOLS / 2;
     static constexpr int ROWG    = STREAM_HTHREADS / HPAIRS;  // H row groups (4 / 2)
     static constexpr int PLANE   = VPIX / 4 + 2;              // slots per plane
     static constexpr int PITCH_B = 4 * PLANE * 16;            // bytes per V row
+    static constexpr int THREADS = STREAM_PTHREADS + NVT + STREAM_HTHREADS;
+    static constexpr int ROWS    = stream_rows(W2);           // source rows per stage
+    // registers after setmaxnreg (the kernel is compiled for 65536 / THREADS)
+    static constexpr int VREGS   = W2 == 1 ? 96 : 64;
+    static constexpr int HREGS   = W2 == 1 ? 120 : 112;
 };
 template<int W2>
 __device__ __forceinline__ int
@@ -119,51 +125,36 @@ stream_planar_byte(int q)
     return ((q >> 2) + (q & 3) * StreamGeom<W2>::PLANE) * 16;
 }
 
-// Where a V thread parks its EPT filtered elements.  NCH == 4: EPT/4 planar
-// float4 pixels; otherwise one scalar offset per element (padded pixels).
+// Where a V thread parks its 4 filtered elements.  NCH == 4: one planar
+// float4 pixel; otherwise one scalar offset per element (padded pixels).
 template<int NCH, int W2> struct StreamPark {
-    static constexpr int EPT = 4 * W2;
-    int off[NCH == 4 ? W2 : EPT];
+    int off[NCH == 4 ? 1 : 4];
     __device__ __forceinline__ void init(int e0, int v)
     {
         if (NCH == 4) {
-#pragma unroll
-            for (int k = 0; k < W2; ++k)
-                off[k] = stream_planar_byte<W2>(W2 * v + k);
+            off[0] = stream_planar_byte<W2>(v);
         } else {
             const int px0 = e0 / NCH;
 #pragma unroll
-            for (int k = 0; k < (NCH == 4 ? W2 : EPT); ++k) {
-                int E  = e0 + EPT * v + k;
+            for (int k = 0; k < (NCH == 4 ? 1 : 4); ++k) {
+                int E  = e0 + 4 * v + k;
                 int px = E / NCH;
                 off[k] = stream_planar_byte<W2>(px - px0) + (E - NCH * px) * 4;
             }
         }
     }
-    __device__ __forceinline__ void store(unsigned row, const float4 (&a)[W2]) const
+    __device__ __forceinline__ void store(unsigned row, const float4& a) const
     {
         if (NCH == 4) {
-#pragma unroll
-            for (int k = 0; k < W2; ++k)
-                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[k]),
-                             "f"(a[k].x), "f"(a[k].y), "f"(a[k].z), "f"(a[k].w)
-                             : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[0]), "f"(a.x),
+                         "f"(a.y), "f"(a.z), "f"(a.w)
+                         : "memory");
         } else {
-#pragma unroll
-            for (int k = 0; k < W2; ++k) {
-                constexpr int S = NCH == 4 ? 0 : 1;  // keeps the indices in range for NCH == 4
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k)]), "f"(a[k].x)
-                             : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 1)]),
-                             "f"(a[k].y)
-                             : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 2)]),
-                             "f"(a[k].z)
-                             : "memory");
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * k + 3)]),
-                             "f"(a[k].w)
-                             : "memory");
-            }
+            constexpr int S = NCH == 4 ? 0 : 1;  // keeps the indices in range for NCH == 4
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[0]), "f"(a.x) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 1]), "f"(a.y) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 2]), "f"(a.z) : "memory");
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 3]), "f"(a.w) : "memory");
         }
     }
 };
@@ -240,61 +231,45 @@ stream_hpass(const FusedParams& p, unsigned vrows, int nb, int dyb, int dxA, boo
     }
 }
 
-// Raw 16-byte group -> W2 float4 values.
-template<int ST, int W2>
-__device__ __forceinline__ void
-stream_convert(const uint4& r, float4 (&v)[W2])
-{
-    if (W2 == 1) {
-        v[0] = convert_raw4<ST>(r);
-    } else {
-        // 8 elements: float never gets here (es == 4 -> W2 == 1)
-        if (SrcTraits<ST>::es == 2) {
-            v[0]      = convert_raw4<ST>(make_uint4(r.x, r.y, 0u, 0u));
-            v[W2 - 1] = convert_raw4<ST>(make_uint4(r.z, r.w, 0u, 0u));
-        } else {
-            v[0]      = convert_raw4<ST>(make_uint4(r.x, 0u, 0u, 0u));
-            v[W2 - 1] = convert_raw4<ST>(make_uint4(r.y, 0u, 0u, 0u));
-        }
-    }
-}
-
 // Shared memory carve-up (bytes), all regions 128-byte aligned:
-//   stages  NST x STAGE_B   STAGE_B = NBOX boxes of (ROWS x 256 elements) + ROWS ring-weight rows
+//   stages  NST x STAGE_B   STAGE_B = NBOX boxes of (ROWS x 256 elements) + ROWS ring-table rows
 //   vbuf    2 x BATCH x PITCH_B
 //   bars    2 x NST mbarriers
 template<int ST, int VK, int W2> struct StreamSmem {
     using G = StreamGeom<W2>;
     static constexpr int es       = SrcTraits<ST>::es;
-    static constexpr int ROWS     = STREAM_ROWS;
+    static constexpr int ROWS     = G::ROWS;
     static constexpr int BOXW     = 256;  // elements per box row (the TMA limit)
-    static constexpr int NBOX     = STREAM_VTHREADS * G::EPT / BOXW;
+    static constexpr int NBOX     = G::NVT * 4 / BOXW;
     static constexpr int BOX_ROWB = BOXW * es;
     static constexpr int BOX_B    = ROWS * BOX_ROWB;
     static constexpr int WROW     = stream_wrow(VK);  // floats per ring-table row
     static constexpr int WROWB    = WROW * 4;
     static constexpr int DATA_B   = NBOX * BOX_B;
-    static constexpr int STAGE_B  = (DATA_B + ROWS * WROWB + 127) & ~127;
+    static constexpr int STAGE_B  = stream_stage_bytes(es, VK, W2);
     static constexpr int BATCH    = stream_batch(VK, W2);
     static constexpr int NR       = BATCH / G::ROWG;
     static constexpr int VBUF_B   = BATCH * G::PITCH_B;
     static constexpr int NST      = stream_stages(es, VK, W2);
     static constexpr int BARS_OFF = NST * STAGE_B + 2 * VBUF_B;
     static constexpr int TOTAL    = BARS_OFF + 2 * NST * 8 + 64;
+    static_assert(DATA_B + ROWS * WROWB <= STAGE_B, "stage layout");
+    static_assert(NST >= 2, "at least two stages");
 };
 
 template<int ST, int NCH, int VK, int HT, int W2>
-__global__ void __launch_bounds__(STREAM_THREADS, 1)
+__global__ void __launch_bounds__(StreamGeom<W2>::THREADS, 1)
 resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p)
 {
     using G = StreamGeom<W2>;
     using S = StreamSmem<ST, VK, W2>;
-    constexpr int es   = S::es;
-    constexpr int ROWS = S::ROWS;
-    constexpr int NST  = S::NST;
-    constexpr int WROW = S::WROW;
+    constexpr int es    = S::es;
+    constexpr int ROWS  = S::ROWS;
+    constexpr int NST   = S::NST;
+    constexpr int WROW  = S::WROW;
     constexpr int BATCH = S::BATCH;
     constexpr int NR    = S::NR;
+    constexpr int NSYNC = G::NVT + STREAM_HTHREADS;  // threads on the V <-> H barriers
     constexpr bool FP   = (ST == ST_FLOAT || ST == ST_HALF);
     static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
 
@@ -310,19 +285,17 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (NST + s), STREAM_VTHREADS / 32);
+            mbar_init(bars + 8 * (NST + s), G::NVT / 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (NCH < 4) {
         // padded V rows: the unused lanes are never written, they must read as zero
-        for (int i = threadIdx.x; i < 2 * S::VBUF_B / 16; i += STREAM_THREADS)
+        for (int i = threadIdx.x; i < 2 * S::VBUF_B / 16; i += G::THREADS)
             reinterpret_cast<uint4*>(stream_smem + NST * S::STAGE_B)[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
 
-    // batches this CTA will hand over in total (both consumer roles count them
-    // the same way; the last two hand-backs are not awaited by anybody)
     if (warp < STREAM_PTHREADS / 32) {
         // ================= producer ========================================
         // (one lane of warp 0; the warpgroup hands its registers to the H warps)
@@ -334,7 +307,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 const Strip strip = p.strips[item % p.nstrips];
                 const Band band   = p.bands[item / p.nstrips];
                 const int nst     = (band.nrows + ROWS - 1) / ROWS;
-                const int nbox    = min(S::NBOX, (strip.nvec * G::EPT + S::BOXW - 1) / S::BOXW);
+                const int nbox    = min(S::NBOX, (strip.nvec * 4 + S::BOXW - 1) / S::BOXW);
                 const unsigned tx = nbox * S::BOX_B + ROWS * S::WROWB;
                 const float* gw   = p.vstream + (size_t)band.woff * WROW;
                 int row           = band.r0 - p.tma_row0;
@@ -356,14 +329,16 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 }
             }
         }
-    } else if (warp < (STREAM_PTHREADS + STREAM_VTHREADS) / 32) {
+    } else if (warp < (STREAM_PTHREADS + G::NVT) / 32) {
         // ================= V warps =========================================
+        if (G::VREGS < 65536 / G::THREADS / 8 * 8)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::VREGS));
         const int tid = threadIdx.x - STREAM_PTHREADS;
         int stage = 0;
         unsigned phase = 0;
         int nbatch = 0;  // batches handed over so far (whole kernel)
-        // this thread's 4*W2*es bytes inside a stage
-        const int toff = ((tid * G::EPT) / S::BOXW) * S::BOX_B + ((tid * G::EPT) % S::BOXW) * es;
+        // this thread's 4*es bytes inside a stage
+        const int toff = ((tid * 4) / S::BOXW) * S::BOX_B + ((tid * 4) % S::BOXW) * es;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const Strip strip = p.strips[item % p.nstrips];
             const Band band   = p.bands[item / p.nstrips];
@@ -375,12 +350,10 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             // the others move up one place -- not with register moves: the
             // NEXT source row's FFMA2s read acc[k+1] and write acc[k]
             // (`shift`), so the rotation costs nothing.
-            float4 acc[VK][W2];
+            float4 acc[VK];
 #pragma unroll
             for (int k = 0; k < VK; ++k)
-#pragma unroll
-                for (int h = 0; h < W2; ++h)
-                    acc[k][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             bool shift = false;  // acc[0] was parked after the previous source row
             int ndone  = 0;      // destination rows of the band completed so far
             int nb     = 0;      // rows parked in the open batch
@@ -388,14 +361,14 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             // park acc[0] as the next destination row of the batch
             auto park_oldest = [&]() {
                 if (nb == 0 && nbatch >= 2)  // the H warps are done with this buffer
-                    named_bar_sync(3 + (nbatch & 1), STREAM_VTHREADS + STREAM_HTHREADS);
+                    named_bar_sync(3 + (nbatch & 1), NSYNC);
                 if (vactive)
                     park.store(prow, acc[0]);
                 prow += G::PITCH_B;
                 ++nb;
                 ++ndone;
                 if (nb == BATCH || ndone == band.ndy) {
-                    named_bar_arrive(1 + (nbatch & 1), STREAM_VTHREADS + STREAM_HTHREADS);
+                    named_bar_arrive(1 + (nbatch & 1), NSYNC);
                     ++nbatch;
                     nb   = 0;
                     prow = vbuf0 + (nbatch & 1) * S::VBUF_B;
@@ -406,58 +379,46 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             auto rotate = [&]() {
 #pragma unroll
                 for (int k = 0; k + 1 < VK; ++k)
-#pragma unroll
-                    for (int h = 0; h < W2; ++h)
-                        acc[k][h] = acc[k + 1][h];
-#pragma unroll
-                for (int h = 0; h < W2; ++h)
-                    acc[VK - 1][h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc[k] = acc[k + 1];
+                acc[VK - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             };
             for (int rbase = 0; rbase < band.nrows; rbase += ROWS) {
                 const unsigned char* sb = stream_smem + stage * S::STAGE_B;
                 mbar_wait(bars + 8 * stage, phase);
-                // the stage's rows of this thread and their ring-table rows
+                // the stage's rows of this thread
                 uint4 raw[ROWS];
-                float4 wv[ROWS][WROW / 4];
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
                     const unsigned char* a = sb + toff + j * S::BOX_ROWB;
-                    if (G::EPT * es == 16)
+                    if (es == 4)
                         raw[j] = *reinterpret_cast<const uint4*>(a);
-                    else if (G::EPT * es == 8) {
+                    else if (es == 2) {
                         uint2 u = *reinterpret_cast<const uint2*>(a);
                         raw[j]  = make_uint4(u.x, u.y, 0u, 0u);
                     } else
                         raw[j] = make_uint4(*reinterpret_cast<const unsigned*>(a), 0u, 0u, 0u);
-#pragma unroll
-                    for (int k = 0; k < WROW / 4; ++k)
-                        wv[j][k] = *reinterpret_cast<const float4*>(sb + S::DATA_B + j * S::WROWB
-                                                                    + k * 16);
                 }
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
                     if (rbase + j < band.nrows) {
+                        // the row of the ring table (broadcast loads)
                         float w[WROW];
 #pragma unroll
                         for (int k = 0; k < WROW / 4; ++k) {
-                            w[4 * k]     = wv[j][k].x;
-                            w[4 * k + 1] = wv[j][k].y;
-                            w[4 * k + 2] = wv[j][k].z;
-                            w[4 * k + 3] = wv[j][k].w;
+                            const float4 t = *reinterpret_cast<const float4*>(
+                                sb + S::DATA_B + j * S::WROWB + k * 16);
+                            w[4 * k]     = t.x;
+                            w[4 * k + 1] = t.y;
+                            w[4 * k + 2] = t.z;
+                            w[4 * k + 3] = t.w;
                         }
                         // low byte: rows completing with this source row; bits
                         // 8..: slots whose weight merges clamped taps of both signs
                         const int info = __float_as_int(w[WROW - 1]);
-                        float4 v[W2];
-                        stream_convert<ST, W2>(raw[j], v);
-                        bool bad = false;
-                        if (FP) {
-                            float q = 0.0f;
-#pragma unroll
-                            for (int h = 0; h < W2; ++h)
-                                q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
-                            bad = !(fabsf(q) <= 3.402823466e+38f);
-                        }
+                        const float4 v = convert_raw4<ST>(raw[j]);
+                        bool bad       = false;
+                        if (FP)
+                            bad = !(fabsf((v.x + v.y) + (v.z + v.w)) <= 3.402823466e+38f);
                         if (FP && bad) {
                             // Inf/NaN in this group: never let it meet a zero
                             // weight; a weight that stands for clamped taps of
@@ -466,38 +427,28 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                                 rotate();
 #pragma unroll
                             for (int k = 0; k < VK; ++k) {
-                                if (w[k] != 0.0f) {
-#pragma unroll
-                                    for (int h = 0; h < W2; ++h)
-                                        fma4(acc[k][h], w[k], v[h]);
-                                }
-                                if ((info >> (8 + k)) & 1) {
-#pragma unroll
-                                    for (int h = 0; h < W2; ++h)
-                                        fma4(acc[k][h], 0.0f, v[h]);
-                                }
+                                if (w[k] != 0.0f)
+                                    fma4(acc[k], w[k], v);
+                                if ((info >> (8 + k)) & 1)
+                                    fma4(acc[k], 0.0f, v);
                             }
                         } else if (shift) {
 #pragma unroll
-                            for (int k = 0; k < VK; ++k)
-#pragma unroll
-                                for (int h = 0; h < W2; ++h) {
-                                    // acc[k] = w[k] * v + acc[k + 1]
-                                    const float4 c = (k + 1 < VK) ? acc[k + 1][h]
-                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-                                    const float2 ww = make_float2(w[k], w[k]);
-                                    float2 lo = __ffma2_rn(ww, make_float2(v[h].x, v[h].y),
-                                                           make_float2(c.x, c.y));
-                                    float2 hi = __ffma2_rn(ww, make_float2(v[h].z, v[h].w),
-                                                           make_float2(c.z, c.w));
-                                    acc[k][h] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                                }
+                            for (int k = 0; k < VK; ++k) {
+                                // acc[k] = w[k] * v + acc[k + 1]
+                                const float4 c = (k + 1 < VK) ? acc[k + 1]
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float2 ww = make_float2(w[k], w[k]);
+                                float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
+                                                       make_float2(c.x, c.y));
+                                float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
+                                                       make_float2(c.z, c.w));
+                                acc[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                            }
                         } else {
 #pragma unroll
                             for (int k = 0; k < VK; ++k)
-#pragma unroll
-                                for (int h = 0; h < W2; ++h)
-                                    fma4(acc[k][h], w[k], v[h]);
+                                fma4(acc[k], w[k], v);
                         }
                         if (FP)
                             __syncwarp();
@@ -526,8 +477,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         }
     } else {
         // ================= H warps =========================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
-        const int tid = threadIdx.x - STREAM_PTHREADS - STREAM_VTHREADS;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::HREGS));
+        const int tid = threadIdx.x - STREAM_PTHREADS - G::NVT;
         const int hp  = tid % G::HPAIRS;
         const int hr  = tid / G::HPAIRS;
         int nbatch    = 0;
@@ -565,13 +516,13 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             for (int dyb = band.dy0; dyb < dy_end; dyb += BATCH) {
                 const int nb = min(BATCH, dy_end - dyb);
                 const int b  = nbatch & 1;
-                named_bar_sync(1 + b, STREAM_VTHREADS + STREAM_HTHREADS);
+                named_bar_sync(1 + b, NSYNC);
                 if (pair_active)
                     stream_hpass<NCH, HT, W2, NR, FP>(p, vbuf0 + b * S::VBUF_B, nb, dyb, dxA,
                                                       has_b, hb, hw, hmix, hr);
                 ++nbatch;
                 if (nbatch + 2 <= total)
-                    named_bar_arrive(3 + b, STREAM_VTHREADS + STREAM_HTHREADS);
+                    named_bar_arrive(3 + b, NSYNC);
             }
         }
     }

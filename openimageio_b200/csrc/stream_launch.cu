@@ -85,7 +85,7 @@ launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma
     alignas(64) CUtensorMap map;
     const cuuint64_t dims[2]    = { (cuuint64_t)p.src_w * p.nch, (cuuint64_t)tma_rows };
     const cuuint64_t strides[1] = { (cuuint64_t)p.src_ystride };
-    const cuuint32_t box[2]     = { 256u, (cuuint32_t)STREAM_ROWS };
+    const cuuint32_t box[2]     = { 256u, (cuuint32_t)stream_rows(w2) };
     const cuuint32_t estr[2]    = { 1u, 1u };
     const CUtensorMapDataType dt = es == 4   ? CU_TENSOR_MAP_DATA_TYPE_UINT32
                                    : es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
@@ -102,7 +102,8 @@ launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma
     }
     const int items = p.nstrips * p.nbands;
     dim3 grid((unsigned)std::min(items, std::max(1, sms)), 1, 1);
-    launch_pdl(k, grid, dim3(STREAM_THREADS), (size_t)smem, (cudaStream_t)stream, map, p);
+    const int threads = STREAM_PTHREADS + STREAM_VTHREADS * w2 + STREAM_HTHREADS;
+    launch_pdl(k, grid, dim3(threads), (size_t)smem, (cudaStream_t)stream, map, p);
     return 0;
 }
 

@@ -4,7 +4,7 @@ timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > $O/r2_parit
 tail -3 $O/r2_parity.log
 for wl in c0 c1 c5; do
   for s in 1; do
-    B2R_STREAM=$s timeout 300 python bench.py --workload $wl --steps 25 --no-cpu --e2e-steps 3 > $O/r2_ab_${wl}_s${s}.json 2> $O/r2_ab_${wl}_s${s}.err
+    B2R_STREAM=$s timeout 300 python bench.py --workload $wl --steps 25 --no-cpu --e2e-steps 3 --no-configs --sustain-ms 0 > $O/r2_ab_${wl}_s${s}.json 2> $O/r2_ab_${wl}_s${s}.err
     python - <<PY
 import json
 try:
@@ -15,4 +15,4 @@ except Exception as e:
 PY
   done
 done
-bash tools/r2_prof.sh d c0
+bash tools/r2_prof.sh e c0
