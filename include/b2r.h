@@ -415,6 +415,46 @@ B2R_API int b2r_mipchain_download(const b2r_mipchain* chain, int level,
 B2R_API float b2r_mipchain_kernel_ms(const b2r_mipchain* chain);
 B2R_API void b2r_mipchain_destroy(b2r_mipchain* chain);
 
+/* ---- the same chain cut into row bands over several GPUs ---------------- */
+/* One process, `ndevices` GPUs of one box (replaces the level loop
+ * of write_mipmap, maketexture.cpp:823-986, for textures whose level 0 is too
+ * large or too slow to push through one PCIe link).  Level k is split into
+ * ndevices row bands; band g lives on devices[g] together with the halo rows
+ * level k+1's band g reads.  Level 0 is uploaded band by band straight from
+ * the HOST image `level0` (every device pulls its rows over its own PCIe
+ * link).  After each level a device pushes the rows its neighbours need into
+ * their memory with peer copies over NVLink and the neighbour's next level
+ * waits for them on the device (no NCCL, no host synchronisation per level).
+ * Levels whose bands would be shorter than 64 rows are gathered on devices[0]
+ * and finished there.  Every level equals the single-device chain bit for bit.
+ * mip->sharpen and highlight compensation are not supported here.
+ * devices == NULL: devices 0 .. ndevices-1. */
+typedef struct b2r_mipchain_banded b2r_mipchain_banded;
+B2R_API int b2r_mipchain_create_banded(b2r_mipchain_banded** chain,
+                                       const b2r_image* level0,
+                                       const b2r_mip_options* mip,
+                                       const int* devices, int ndevices,
+                                       char* err, size_t errlen);
+B2R_API int b2r_mipchain_banded_nlevels(const b2r_mipchain_banded* chain);
+B2R_API int b2r_mipchain_banded_level(const b2r_mipchain_banded* chain, int level,
+                                      int* width, int* height);
+/* Band `band` of a level: the device that owns it, its rows [row_begin,
+ * row_end) and the device address of row_begin (NULL when the device sits
+ * the level out). */
+B2R_API int b2r_mipchain_banded_band(const b2r_mipchain_banded* chain, int level,
+                                     int band, int* device, int* row_begin,
+                                     int* row_end, void** device_pixels);
+/* Copy a finished level into the host image `out` (float32, same channels);
+ * every device sends its own rows.  Synchronous. */
+B2R_API int b2r_mipchain_banded_download(const b2r_mipchain_banded* chain, int level,
+                                         const b2r_image* out, char* err,
+                                         size_t errlen);
+/* what: 0 host wall clock of the create call (upload + tables + level loop),
+ * 1 level-0 upload and 2 level loop incl. the pushes (device events, max over
+ * the devices), 3 bytes pushed between devices.  ms (bytes for 3). */
+B2R_API float b2r_mipchain_banded_ms(const b2r_mipchain_banded* chain, int what);
+B2R_API void b2r_mipchain_banded_destroy(b2r_mipchain_banded* chain);
+
 /* One level step of the chain on arbitrary windows: rows `roi` of level k+1
  * (dst: data window = the rows held, display window = the whole level) from
  * level k (src: data window = the rows available, display window = the whole

@@ -226,6 +226,20 @@ def lib():
     L.b2r_mipchain_kernel_ms.restype = C.c_float
     L.b2r_mipchain_kernel_ms.argtypes = [C.c_void_p]
     L.b2r_mipchain_destroy.argtypes = [C.c_void_p]
+    L.b2r_mipchain_create_banded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
+                                             C.POINTER(_MipOptions), C.POINTER(C.c_int),
+                                             C.c_int, C.c_char_p, C.c_size_t]
+    L.b2r_mipchain_banded_nlevels.argtypes = [C.c_void_p]
+    L.b2r_mipchain_banded_level.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                            C.POINTER(C.c_int)]
+    L.b2r_mipchain_banded_band.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.b2r_mipchain_banded_download.argtypes = [C.c_void_p, C.c_int, C.POINTER(_Image),
+                                               C.c_char_p, C.c_size_t]
+    L.b2r_mipchain_banded_ms.restype = C.c_float
+    L.b2r_mipchain_banded_ms.argtypes = [C.c_void_p, C.c_int]
+    L.b2r_mipchain_banded_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -1461,6 +1475,75 @@ class MipChain:
         im = ib._c()
         err = C.create_string_buffer(512)
         rc = lib().b2r_mipchain_download(self._h, level, C.byref(im), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        return out
+
+
+class MipChainBanded:
+    """The MIP chain cut into row bands over several GPUs of one box, driven
+    from this process (b2r_mipchain_create_banded: per-band upload of level 0
+    from the host image, halo rows pushed between devices over NVLink, tail of
+    the chain gathered on the first device).  Levels equal MipChain's bit for
+    bit.  `devices`: CUDA ordinals, one band per entry."""
+
+    def __init__(self, level0, devices, filtername="box", clamp_half=False):
+        if not isinstance(level0, ImageBuf):
+            level0 = ImageBuf(level0)
+        L = lib()
+        h = C.c_void_p()
+        im = level0._c()
+        mo = _MipOptions()
+        mo.filtername = filtername.encode()
+        mo.clamp_half = 1 if clamp_half else 0
+        mo.alpha_channel = level0.spec_.alpha_channel
+        devs = (C.c_int * len(devices))(*devices)
+        err = C.create_string_buffer(512)
+        rc = L.b2r_mipchain_create_banded(C.byref(h), C.byref(im), C.byref(mo),
+                                          devs, len(devices), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        self._h = h
+        self.nchannels = level0.nchannels
+        self.devices = list(devices)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2r_mipchain_banded_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def nlevels(self):
+        return lib().b2r_mipchain_banded_nlevels(self._h)
+
+    def ms(self, what="total"):
+        """'total': host wall clock of the construction; 'upload' / 'chain':
+        device events, max over the devices; 'halo_bytes'."""
+        k = {"total": 0, "upload": 1, "chain": 2, "halo_bytes": 3}[what]
+        return lib().b2r_mipchain_banded_ms(self._h, k)
+
+    def level_size(self, level):
+        w, h = C.c_int(), C.c_int()
+        lib().b2r_mipchain_banded_level(self._h, level, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def band(self, level, band):
+        d, y0, y1, p = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+        lib().b2r_mipchain_banded_band(self._h, level, band, C.byref(d), C.byref(y0),
+                                       C.byref(y1), C.byref(p))
+        return d.value, y0.value, y1.value, p.value
+
+    def download(self, level, out=None):
+        w, h = self.level_size(level)
+        if out is None:
+            out = np.empty((h, w, self.nchannels), np.float32)
+        ib = ImageBuf(out)
+        im = ib._c()
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_mipchain_banded_download(self._h, level, C.byref(im), err, 512)
         if rc:
             raise B2RError(err.value.decode())
         return out

@@ -176,6 +176,7 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
         bd.r0    = P.vfirst[bd.dy0];
         bd.nrows = P.vfirst[e - 1] + vt - bd.r0;
         bd.woff  = 0;
+        bd.soff  = 0;
         P.max_band_dy   = std::max(P.max_band_dy, bd.ndy);
         P.max_band_rows = std::max(P.max_band_rows, bd.nrows);
         P.bands.push_back(bd);
@@ -366,6 +367,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
             bd.r0    = first[bd.dy0];
             bd.nrows = last[e - 1] - bd.r0 + 1;
             bd.woff  = woff;
+            bd.soff  = 0;
             P.max_band_dy = std::max(P.max_band_dy, bd.ndy);
             if (use_ring) {
                 if (bd.nrows > max_rows_smem) {
@@ -391,9 +393,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         size_t total = 0;
         for (const Band& b : P.bands)
             total += size_t(b.nrows);
-        // (+ STREAM_MAXROWS rows: the stream kernel fetches whole stages of ring
-        // weights and may run past the last band's rows)
-        P.vring.assign((total + STREAM_MAXROWS) * vkp, 0.0f);
+        P.vring.assign(total * vkp, 0.0f);
         for (const Band& b : P.bands) {
             for (int k = b.dy0; k < b.dy0 + b.ndy; ++k) {
                 int slot = (k - b.dy0) % vk;
@@ -410,11 +410,17 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
         // them), and the last float of the row holds, as an integer, how many
         // destination rows complete with this source row.
         const int vsw = stream_wrow(vk);
-        P.vstream.assign((total + STREAM_MAXROWS) * vsw, 0.0f);
+        const int batch = stream_batch(vk, P.w2);
+        size_t stotal = 0;
+        for (Band& b : P.bands) {
+            b.soff = int(stotal);
+            stotal += size_t((b.nrows + STREAM_ROWPAD - 1) / STREAM_ROWPAD) * STREAM_ROWPAD;
+        }
+        P.vstream.assign(stotal * vsw, 0.0f);
         for (const Band& b : P.bands) {
             int oldest = b.dy0;  // first dst row of the band not yet complete
             for (int r = b.r0; r < b.r0 + b.nrows; ++r) {
-                float* row = &P.vstream[(size_t(b.woff) + (r - b.r0)) * vsw];
+                float* row = &P.vstream[(size_t(b.soff) + (r - b.r0)) * vsw];
                 while (oldest < b.dy0 + b.ndy && last[oldest] < r)
                     ++oldest;
                 int done = 0, mix = 0;
@@ -427,9 +433,18 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
                 }
                 for (int k = oldest; k < b.dy0 + b.ndy && last[k] == r; ++k)
                     ++done;
-                // low byte: rows completing here; bits 8..: slots whose weight
-                // merges clamped taps of both signs
+                // bits 0-7: rows completing here; 8-15: slots whose weight merges
+                // clamped taps of both signs; 16 / 17: the completing row opens /
+                // closes a hand-over batch of the band (only read when one row
+                // completes; the kernel counts for itself otherwise)
+                const int n = oldest - b.dy0;  // index in the band of the first completing row
                 int32_t di = done | (mix << 8);
+                if (done == 1) {
+                    if (n % batch == 0)
+                        di |= 1 << 16;
+                    if (n % batch == batch - 1 || n == b.ndy - 1)
+                        di |= 1 << 17;
+                }
                 memcpy(&row[vsw - 1], &di, sizeof(di));
             }
         }

@@ -115,6 +115,8 @@ struct Band {
     int r0;     // first source row consumed (relative to src data origin)
     int nrows;  // source rows consumed (ring mode)
     int woff;   // ring mode: row offset of this band's weights in vring
+    int soff;   // ring mode: row offset of this band in vstream (bands padded to
+                // whole stages there)
 };
 
 constexpr int FUSED_THREADS = 256;
@@ -156,12 +158,14 @@ constexpr int STREAM_HTHREADS = 256;
 // registers away with setmaxnreg and exit), then the V warps, then the H warps
 constexpr int STREAM_PTHREADS = 128;
 constexpr int STREAM_SMEM_MAX = 227 * 1024;
-constexpr int STREAM_MAXROWS  = 4;  // rows per stage, at most (table padding)
-// source rows per TMA stage (w2 = 1: 4 rows of 256 chunks; w2 = 2: 2 rows of 512)
+// a band's rows in the stream kernel's ring table are padded to a multiple of
+// this (whole stages for either geometry)
+constexpr int STREAM_ROWPAD = 12;
+// source rows per TMA stage (w2 = 1: 4 rows of 256 chunks; w2 = 2: 3 rows of 512)
 B2R_HD constexpr int
 stream_rows(int w2)
 {
-    return w2 == 1 ? 4 : 2;
+    return w2 == 1 ? 4 : 3;
 }
 // V-filtered rows per hand-over batch
 B2R_HD constexpr int

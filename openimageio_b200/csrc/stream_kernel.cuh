@@ -89,6 +89,19 @@ bulk_load_1d(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned bar)
                  "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// one lane of a converged warp (the TMA issue slot)
+__device__ __forceinline__ bool
+elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n"
+                 ".reg .pred P;\n"
+                 "elect.sync _|P, 0xffffffff;\n"
+                 "selp.u32 %0, 1, 0, P;\n"
+                 "}"
+                 : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void
 named_bar_sync(int id, int count)
 {
@@ -296,11 +309,14 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     }
     __syncthreads();
 
-    if (warp < STREAM_PTHREADS / 32) {
+    if (warp >= (G::NVT + STREAM_HTHREADS) / 32) {
         // ================= producer ========================================
-        // (one lane of warp 0; the warpgroup hands its registers to the H warps)
+        // The LAST warpgroup: the issue arbiter favours high warp ids, and the
+        // ring must never wait for its refill requests.  One warp runs the
+        // loop (converged; an elected lane issues the copies); the warpgroup
+        // hands its registers to the H warps.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        if (warp == 0 && lane == 0) {
+        if (warp == (G::NVT + STREAM_HTHREADS) / 32) {
             int stage = 0;
             unsigned phase = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -309,17 +325,23 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 const int nst     = (band.nrows + ROWS - 1) / ROWS;
                 const int nbox    = min(S::NBOX, (strip.nvec * 4 + S::BOXW - 1) / S::BOXW);
                 const unsigned tx = nbox * S::BOX_B + ROWS * S::WROWB;
-                const float* gw   = p.vstream + (size_t)band.woff * WROW;
+                const float* gw   = p.vstream + (size_t)band.soff * WROW;
                 int row           = band.r0 - p.tma_row0;
                 for (int i = 0; i < nst; ++i) {
                     const unsigned full  = bars + 8 * stage;
                     const unsigned empty = bars + 8 * (NST + stage);
                     mbar_wait(empty, phase ^ 1);
-                    mbar_expect_tx(full, tx);
-                    const unsigned sb = smem0 + stage * S::STAGE_B;
-                    for (int b = 0; b < nbox; ++b)
-                        tma_load_2d(sb + b * S::BOX_B, &tmap, strip.e0 + b * S::BOXW, row, full);
-                    bulk_load_1d(sb + S::DATA_B, gw, ROWS * S::WROWB, full);
+                    if (elect_one()) {
+                        mbar_expect_tx(full, tx);
+                        const unsigned sb = smem0 + stage * S::STAGE_B;
+#pragma unroll
+                        for (int b = 0; b < S::NBOX; ++b)
+                            if (b < nbox)
+                                tma_load_2d(sb + b * S::BOX_B, &tmap, strip.e0 + b * S::BOXW, row,
+                                            full);
+                        bulk_load_1d(sb + S::DATA_B, gw, ROWS * S::WROWB, full);
+                    }
+                    __syncwarp();
                     gw += ROWS * WROW;
                     row += ROWS;
                     if (++stage == NST) {
@@ -329,11 +351,11 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 }
             }
         }
-    } else if (warp < (STREAM_PTHREADS + G::NVT) / 32) {
+    } else if (warp < G::NVT / 32) {
         // ================= V warps =========================================
         if (G::VREGS < 65536 / G::THREADS / 8 * 8)
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::VREGS));
-        const int tid = threadIdx.x - STREAM_PTHREADS;
+        const int tid = threadIdx.x;
         int stage = 0;
         unsigned phase = 0;
         int nbatch = 0;  // batches handed over so far (whole kernel)
@@ -356,21 +378,19 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             bool shift = false;  // acc[0] was parked after the previous source row
             int ndone  = 0;      // destination rows of the band completed so far
-            int nb     = 0;      // rows parked in the open batch
             unsigned prow = vbuf0 + (nbatch & 1) * S::VBUF_B;  // where the next row is parked
-            // park acc[0] as the next destination row of the batch
-            auto park_oldest = [&]() {
-                if (nb == 0 && nbatch >= 2)  // the H warps are done with this buffer
+            // park acc[0] as the next destination row; `first` / `last`: the
+            // row opens / closes a hand-over batch
+            auto park_oldest = [&](bool first, bool last) {
+                if (first && nbatch >= 2)  // the H warps are done with this buffer
                     named_bar_sync(3 + (nbatch & 1), NSYNC);
                 if (vactive)
                     park.store(prow, acc[0]);
                 prow += G::PITCH_B;
-                ++nb;
                 ++ndone;
-                if (nb == BATCH || ndone == band.ndy) {
+                if (last) {
                     named_bar_arrive(1 + (nbatch & 1), NSYNC);
                     ++nbatch;
-                    nb   = 0;
                     prow = vbuf0 + (nbatch & 1) * S::VBUF_B;
                 }
             };
@@ -382,6 +402,10 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     acc[k] = acc[k + 1];
                 acc[VK - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             };
+            // The band's rows in the ring table are padded to whole stages with
+            // all-zero rows, so every stage is processed in full: a padded row
+            // multiplies whatever the TMA fetched by zero (and a non-finite
+            // value takes the predicated path, which skips zero weights).
             for (int rbase = 0; rbase < band.nrows; rbase += ROWS) {
                 const unsigned char* sb = stream_smem + stage * S::STAGE_B;
                 mbar_wait(bars + 8 * stage, phase);
@@ -400,68 +424,71 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 }
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
-                    if (rbase + j < band.nrows) {
-                        // the row of the ring table (broadcast loads)
-                        float w[WROW];
+                    // the row of the ring table (broadcast loads)
+                    float w[WROW];
 #pragma unroll
-                        for (int k = 0; k < WROW / 4; ++k) {
-                            const float4 t = *reinterpret_cast<const float4*>(
-                                sb + S::DATA_B + j * S::WROWB + k * 16);
-                            w[4 * k]     = t.x;
-                            w[4 * k + 1] = t.y;
-                            w[4 * k + 2] = t.z;
-                            w[4 * k + 3] = t.w;
-                        }
-                        // low byte: rows completing with this source row; bits
-                        // 8..: slots whose weight merges clamped taps of both signs
-                        const int info = __float_as_int(w[WROW - 1]);
-                        const float4 v = convert_raw4<ST>(raw[j]);
-                        bool bad       = false;
-                        if (FP)
-                            bad = !(fabsf((v.x + v.y) + (v.z + v.w)) <= 3.402823466e+38f);
-                        if (FP && bad) {
-                            // Inf/NaN in this group: never let it meet a zero
-                            // weight; a weight that stands for clamped taps of
-                            // both signs turns it into NaN (w1*Inf + w2*Inf)
-                            if (shift)
-                                rotate();
+                    for (int k = 0; k < WROW / 4; ++k) {
+                        const float4 t = *reinterpret_cast<const float4*>(
+                            sb + S::DATA_B + j * S::WROWB + k * 16);
+                        w[4 * k]     = t.x;
+                        w[4 * k + 1] = t.y;
+                        w[4 * k + 2] = t.z;
+                        w[4 * k + 3] = t.w;
+                    }
+                    // bits 0-7: rows completing with this source row; 8-15:
+                    // slots whose weight merges clamped taps of both signs;
+                    // 16 / 17: the (single) completing row opens / closes a batch
+                    const int info = __float_as_int(w[WROW - 1]);
+                    const float4 v = convert_raw4<ST>(raw[j]);
+                    bool bad       = false;
+                    if (FP)
+                        bad = !(fabsf((v.x + v.y) + (v.z + v.w)) <= 3.402823466e+38f);
+                    if (FP && bad) {
+                        // Inf/NaN in this group: never let it meet a zero
+                        // weight; a weight that stands for clamped taps of
+                        // both signs turns it into NaN (w1*Inf + w2*Inf)
+                        if (shift)
+                            rotate();
 #pragma unroll
-                            for (int k = 0; k < VK; ++k) {
-                                if (w[k] != 0.0f)
-                                    fma4(acc[k], w[k], v);
-                                if ((info >> (8 + k)) & 1)
-                                    fma4(acc[k], 0.0f, v);
-                            }
-                        } else if (shift) {
-#pragma unroll
-                            for (int k = 0; k < VK; ++k) {
-                                // acc[k] = w[k] * v + acc[k + 1]
-                                const float4 c = (k + 1 < VK) ? acc[k + 1]
-                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-                                const float2 ww = make_float2(w[k], w[k]);
-                                float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
-                                                       make_float2(c.x, c.y));
-                                float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
-                                                       make_float2(c.z, c.w));
-                                acc[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                            }
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < VK; ++k)
+                        for (int k = 0; k < VK; ++k) {
+                            if (w[k] != 0.0f)
                                 fma4(acc[k], w[k], v);
+                            if ((info >> (8 + k)) & 1)
+                                fma4(acc[k], 0.0f, v);
                         }
-                        if (FP)
-                            __syncwarp();
-                        // destination rows that complete with this source row
-                        int ne = info & 0xff;
-                        shift  = ne > 0;
-                        if (ne > 0) {
-                            park_oldest();
+                    } else if (shift) {
+#pragma unroll
+                        for (int k = 0; k < VK; ++k) {
+                            // acc[k] = w[k] * v + acc[k + 1]
+                            const float4 c = (k + 1 < VK) ? acc[k + 1]
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float2 ww = make_float2(w[k], w[k]);
+                            float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
+                                                   make_float2(c.x, c.y));
+                            float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
+                                                   make_float2(c.z, c.w));
+                            acc[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < VK; ++k)
+                            fma4(acc[k], w[k], v);
+                    }
+                    if (FP)
+                        __syncwarp();
+                    // destination rows that complete with this source row
+                    int ne = info & 0xff;
+                    shift  = ne > 0;
+                    if (ne == 1) {
+                        park_oldest((info >> 16) & 1, (info >> 17) & 1);
+                    } else if (ne > 1) {
 #pragma unroll 1
-                            while (--ne > 0) {
-                                rotate();
-                                park_oldest();
-                            }
+                        for (;;) {
+                            park_oldest(ndone % BATCH == 0,
+                                        ndone % BATCH == BATCH - 1 || ndone == band.ndy - 1);
+                            if (--ne == 0)
+                                break;
+                            rotate();
                         }
                     }
                 }
@@ -478,7 +505,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     } else {
         // ================= H warps =========================================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::HREGS));
-        const int tid = threadIdx.x - STREAM_PTHREADS - G::NVT;
+        const int tid = threadIdx.x - G::NVT;
         const int hp  = tid % G::HPAIRS;
         const int hr  = tid / G::HPAIRS;
         int nbatch    = 0;

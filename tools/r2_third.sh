@@ -1,6 +1,6 @@
 #!/bin/bash
 O=gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > $O/r2_parity.log 2>&1; echo "parity rc=$?"
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_maketx.py -x -q -m gpu > $O/r2_parity.log 2>&1; echo "parity rc=$?"
 tail -3 $O/r2_parity.log
 for wl in c0 c1 c5; do
   for s in 1; do
@@ -15,4 +15,4 @@ except Exception as e:
 PY
   done
 done
-bash tools/r2_prof.sh e c0
+bash tools/r2_prof.sh f c0
