@@ -345,9 +345,10 @@ class Harness:
         S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
 
         def step_dev():
-            for S, D in zip(S_devs, D_devs):
-                if not IBA.resize(D, S, filtername=filt):
-                    raise RuntimeError(D.geterror())
+            # one step = the batch of nfr frames through ONE call (frames of one
+            # shape run as a single persistent launch, b2r_resize_batch)
+            if not IBA.resize_batch(D_devs, S_devs, filtername=filt):
+                raise RuntimeError(D_devs[0].geterror())
 
         def step_host():
             # the batch through the host-memory API: every frame's source goes
@@ -371,7 +372,7 @@ class Harness:
             ms_s, t0, t1 = self.time_steps(step_dev, steps)
             out["sustained_ms_per_step"] = self.max_over_ranks(ms_s)
             out["sustained_clocks"] = sampler.window(t0, t1) if sampler else None
-        self.launches += (warmup + steps) * nfr
+        self.launches += (warmup + steps)  # one launch per batch of nfr frames
 
         # end to end (host buffers through the public API)
         for _ in range(2):
@@ -439,9 +440,8 @@ class Harness:
         S_host, D_host = oiio.ImageBuf(src_host), oiio.ImageBuf(dst_host)
 
         def step_dev():
-            for s, d in zip(S, D):
-                if not IBA.resize(d, s, filtername=filt):
-                    raise RuntimeError(d.geterror())
+            if not IBA.resize_batch(D, S, filtername=filt):
+                raise RuntimeError(D[0].geterror())
 
         def step_host():
             for _ in range(nf):
@@ -450,7 +450,7 @@ class Harness:
         step_dev()
         ms, _, _ = self.time_steps(step_dev, steps)
         ms = self.max_over_ranks(ms)
-        self.launches += (1 + steps) * nf
+        self.launches += (1 + steps)
         step_host()
         self.barrier()
         t0 = time.perf_counter()

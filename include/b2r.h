@@ -167,6 +167,20 @@ B2R_API int b2r_resize_filter(const b2r_image* dst, const b2r_image* src,
                               const b2r_options* opt, b2r_report* report,
                               char* err, size_t errlen);
 
+/* A batch of `nframes` independent frames (dst[i] <- src[i]) with one filter.
+ * The reference resizes a frame sequence with one ImageBufAlgo::resize call per
+ * frame (oiiotool --frames, imagebufalgo_xform.cpp:864-918); here frames of ONE
+ * shape (equal windows, types, strides) that live on one device run as a
+ * single persistent launch over (frame, strip, band) work items, which removes
+ * the per-frame launch gap, ramp-up and tail -- what bounds small frames.
+ * Frames that do not qualify (host memory, differing geometry, shapes of the
+ * other kernels) are resized one after the other, with the same results.
+ * report (optional) describes the batch launch or the last frame. */
+B2R_API int b2r_resize_batch(const b2r_image* dst, const b2r_image* src, int nframes,
+                             const char* filtername, float filterwidth,
+                             const b2r_roi* roi, const b2r_options* opt,
+                             b2r_report* report, char* err, size_t errlen);
+
 /* ---- rangecompress / rangeexpand ---------------------------------------
  * Replaces rangecompress_<R,A> / rangeexpand_<R,A>
  * (src/libOpenImageIO/imagebufalgo_pixelmath.cpp:560-735): the log-curve

@@ -143,6 +143,10 @@ def lib():
     L.b2r_resize.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_char_p,
                              C.c_float, C.POINTER(_Roi), C.POINTER(_Options),
                              C.POINTER(Report), C.c_char_p, C.c_size_t]
+    L.b2r_resize_batch.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_int,
+                                   C.c_char_p, C.c_float, C.POINTER(_Roi),
+                                   C.POINTER(_Options), C.POINTER(Report), C.c_char_p,
+                                   C.c_size_t]
     L.b2r_resize_filter.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
                                     C.c_void_p, C.POINTER(_Roi),
                                     C.POINTER(_Options), C.POINTER(Report),
@@ -616,6 +620,41 @@ class _IBA:
         if not ok and not result.has_error:
             result.errorfmt("ImageBufAlgo::resize() error")
         return result
+
+    def resize_batch(self, dsts, srcs, filtername="", filterwidth=0.0, roi=None,
+                     device=0, report=False):
+        """Resize srcs[i] into dsts[i] (lists of ImageBuf of ONE shape).  Frames
+        that live on one device run as a single persistent launch
+        (b2r_resize_batch); anything else falls back to frame-by-frame."""
+        if len(dsts) != len(srcs):
+            raise ValueError("resize_batch: %d destinations for %d sources"
+                             % (len(dsts), len(srcs)))
+        if not dsts:
+            return True
+        n = len(dsts)
+        r0 = _ibaprep(roi, dsts[0], srcs[0])
+        if r0 is None:
+            return False
+        for d, s_ in zip(dsts[1:], srcs[1:]):
+            if _ibaprep(roi, d, s_) is None:
+                return False
+        L = lib()
+        D = (_Image * n)(*[d._c() for d in dsts])
+        S = (_Image * n)(*[s_._c() for s_ in srcs])
+        r = _Roi(r0.xbegin, r0.xend, r0.ybegin, r0.yend, r0.chbegin, r0.chend)
+        stream = _current_stream(dsts[0]) or _current_stream(srcs[0])
+        o = _options(device, PATH_AUTO, stream, False, srcs[0].spec_.alpha_channel,
+                     srcs[0].spec_.z_channel)
+        rep = Report()
+        err = C.create_string_buffer(512)
+        rc = L.b2r_resize_batch(D, S, n, (filtername or "").encode(), float(filterwidth),
+                                C.byref(r), C.byref(o), C.byref(rep) if report else None,
+                                err, 512)
+        self.last_report = rep if report else None
+        if rc:
+            dsts[0].errorfmt(err.value.decode())
+            return False
+        return True
 
     def _resize(self, dst, src, filtername, filterwidth, roi, filterptr, path,
                 device, highlightcomp=False):

@@ -154,22 +154,18 @@ source_row_span(const b2r_image& src, const Filter2D& filter, const AxisTaps& tx
     *row1 = hi - src.y;
 }
 
-// B2R_STREAM=0 keeps ring-mode shapes on resize_fused_kernel (A/B runs)
-bool
-stream_enabled()
-{
-    static const bool on = [] {
-        const char* e = getenv("B2R_STREAM");
-        return !(e && e[0] == '0');
-    }();
-    return on;
-}
-
+// Is there a kernel for this plan?  Ring-mode plans with a compile-time H
+// window belong to the stream kernel (their source rows are TMA-fetchable:
+// contiguous pixels, re-pitched if need be), everything else to the expand /
+// fused kernels.
 static bool
-plan_supported(int basetype, int nch, const FusedPlan& fp)
+plan_supported(int basetype, int nch, const FusedPlan& fp, bool tma_ok)
 {
-    return fp.expand ? expand_supported(basetype, nch, fp.vt, fp.ht)
-                     : fused_supported(basetype, nch, fp.vk, fp.ht);
+    if (fp.expand)
+        return expand_supported(basetype, nch, fp.vt, fp.ht);
+    if (fp.vk > 0 && fp.ht > 0 && fp.ht <= 16)
+        return tma_ok && stream_supported(basetype, nch, fp.vk, fp.ht, fp.w2);
+    return fused_supported(basetype, nch, fp.vk, fp.ht);
 }
 
 int
@@ -238,7 +234,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
         // strips, two work items per SM); it needs a ring-mode shape with a
         // compile-time H window and enough work to fill the SMs that way
         bool stream_plan = false;
-        if (ok && tma_ok && stream_enabled()) {
+        if (ok && tma_ok) {
             stream_plan = plan_fused(ax, ay, nch, src.width, src.height, sms * 2, &plan->fp,
                                      e0a, 2)
                           && plan->fp.w2 == 2 && !plan->fp.expand && plan->fp.vk > 0
@@ -248,7 +244,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
         ok = ok
              && (stream_plan
                  || (plan_fused(ax, ay, nch, src.width, src.height, cta_slots, &plan->fp, e0a)
-                     && plan_supported(src.basetype, nch, plan->fp)));
+                     && plan_supported(src.basetype, nch, plan->fp, tma_ok)));
         if (ok && !stream_plan) {
             // the band count was sized for an assumed number of resident CTAs
             // per SM; ask the runtime what this shape really gets and re-plan
@@ -266,7 +262,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             if (per > 0 && per != 3)
                 ok = plan_fused(ax, ay, nch, src.width, src.height, sms * per,
                                 &plan->fp, e0a)
-                     && plan_supported(src.basetype, nch, plan->fp);
+                     && plan_supported(src.basetype, nch, plan->fp, tma_ok);
         }
         if (ok) {
             plan->fused = true;
@@ -377,6 +373,17 @@ int
 resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
                       const Filter2D& filter, const b2r_roi& roi, int device,
                       int path, b2r_report* report, char* err, size_t errlen);
+
+// b2r_resize_batch: the first frame goes through resize_impl with this set; at
+// the point where the stream kernel would be launched the parameters are
+// handed over instead (the batch entry launches once for all frames).
+struct BatchCapture {
+    bool want = false, got = false;
+    FusedParams fp;
+    int w2 = 1, sms = 0;
+    std::shared_ptr<DevicePlan> plan;  // keeps the tables alive
+};
+thread_local BatchCapture* g_capture = nullptr;
 
 // options.reserved[] is private to the library:
 //   [0] == 1  build + upload the tables only, no launch (MIP chain pass 1)
@@ -703,10 +710,13 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                                      err, errlen);
 
     // TMA needs 16-byte aligned source rows: host sources are staged with such
-    // a pitch, device sources are used where they lie
-    const bool tma_ok = src.xstride == (int64_t)src.nchannels * ses
-                        && (smem == B2R_MEM_HOST
-                            || (((uintptr_t)src.pixels & 15) == 0 && (src.ystride & 15) == 0));
+    // a pitch; a device source that is not aligned (a packed 7679-pixel RGB
+    // image, a sub-view) is re-pitched into a temporary first when its shape
+    // belongs to the stream kernel (one copy pass at HBM speed instead of the
+    // 2-3x slower unaligned paths)
+    const bool src_contig  = src.xstride == (int64_t)src.nchannels * ses;
+    const bool src_aligned = ((uintptr_t)src.pixels & 15) == 0 && (src.ystride & 15) == 0;
+    const bool tma_ok      = src_contig;
     std::shared_ptr<DevicePlan> plan;
     rc = get_plan(device, dst, src, roi, filter, nch, di.sms * 3, stream, &plan,
                   err, errlen, tma_ok);
@@ -721,7 +731,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     b2r_image srcd   = src;
     b2r_image dstd   = dst;
     size_t src_bytes = 0, dst_bytes = 0;
-    bool src_staged = false, dst_staged = false;
+    bool src_staged = false, dst_staged = false, src_repitched = false;
     void* src_alloc = nullptr;
     if (smem == B2R_MEM_HOST) {
         if (src.xstride != (int64_t)src.nchannels * ses) {
@@ -748,11 +758,28 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         if (report)
             report->h2d_bytes += (int64_t)rowbytes * nrows;
     }
+    const bool stream_shape = plan->fused && !plan->fp.expand && plan->fp.vk > 0
+                              && plan->fp.ht > 0 && plan->fp.ht <= 16;
+    if (smem == B2R_MEM_DEVICE && stream_shape && !src_aligned && src_contig
+        && path != B2R_PATH_EXACT) {
+        const int r0 = plan->src_row0, nrows = plan->src_row1 - plan->src_row0 + 1;
+        size_t rowbytes = size_t(src.width) * src.xstride;
+        size_t pitch    = (rowbytes + 15) & ~size_t(15);
+        CUDA_TRY(cudaMallocAsync(&src_alloc, pitch * nrows, stream));
+        src_repitched = true;
+        CUDA_TRY(cudaMemcpy2DAsync(src_alloc, pitch,
+                                   (const unsigned char*)src.pixels
+                                       + (long long)r0 * src.ystride,
+                                   src.ystride, rowbytes, nrows, cudaMemcpyDeviceToDevice,
+                                   stream));
+        dsrc         = (unsigned char*)src_alloc - (long long)r0 * (long long)pitch;
+        srcd.ystride = (int64_t)pitch;
+    }
     size_t dpitch = 0, drowbytes = 0;
     if (dmem == B2R_MEM_HOST) {
         if (dst.xstride != (int64_t)dst.nchannels * des) {
             set_err(err, errlen, "host destination pixels must be contiguous in x");
-            if (src_staged)
+            if (src_alloc)
                 cudaFreeAsync(src_alloc, stream);
             return B2R_ERR_UNSUPPORTED;
         }
@@ -817,7 +844,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     int epoch    = 0;
     if (path == B2R_PATH_FUSED && !fused_ok) {
         set_err(err, errlen, "resize: shape is not eligible for the fused kernel");
-        if (src_staged)
+        if (src_alloc)
             cudaFreeAsync(src_alloc, stream);
         if (dst_staged)
             cudaFreeAsync(ddst, stream);
@@ -898,21 +925,32 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         // under non-finite pixels itself, so no gated exact kernel follows.
         bool streamed = false;
         const int w2 = plan->fp.w2;
-        if (!fp.expand && fp.vk > 0 && tma_ok && stream_enabled()
+        if (!fp.expand && fp.vk > 0 && tma_ok
             && stream_supported(src.basetype, nch, fp.vk, fp.ht, w2)) {
-            const int trow0 = src_staged ? plan->src_row0 : 0;
-            const int trows = src_staged ? plan->src_row1 - plan->src_row0 + 1 : src.height;
+            const bool temp = src_staged || src_repitched;
+            const int trow0 = temp ? plan->src_row0 : 0;
+            const int trows = temp ? plan->src_row1 - plan->src_row0 + 1 : src.height;
             const unsigned char* tbase
                 = (const unsigned char*)dsrc + (long long)trow0 * srcd.ystride;
             fp.tma_row0        = trow0;
             fp.check_nonfinite = 0;
+            if (g_capture && g_capture->want && !temp && !dst_staged
+                && !(opt && (opt->reserved[1] || opt->reserved[2]))) {
+                // batch entry: hand the launch parameters over, launch nothing
+                g_capture->fp   = fp;
+                g_capture->w2   = w2;
+                g_capture->sms  = di.sms;
+                g_capture->plan = plan;
+                g_capture->got  = true;
+                return B2R_OK;
+            }
             streamed = launch_resize_stream(fp, w2, tbase, trows, di.sms, stream) == 0;
             if (!streamed)
                 fp.check_nonfinite = src_is_fp ? 1 : 0;
         }
         if (!streamed && w2 != 1) {
             set_err(err, errlen, "resize: the stream kernel could not be launched");
-            if (src_staged)
+            if (src_alloc)
                 cudaFreeAsync(src_alloc, stream);
             if (dst_staged)
                 cudaFreeAsync(ddst, stream);
@@ -968,7 +1006,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         && (dst_staged || src_staged))
         CUDA_TRY(cudaMemcpyAsync(&redo, flag, sizeof(int),
                                  cudaMemcpyDeviceToHost, stream));
-    if (src_staged)
+    if (src_alloc)
         CUDA_TRY(cudaFreeAsync(src_alloc, stream));
     if (dst_staged)
         CUDA_TRY(cudaFreeAsync(ddst, stream));
@@ -1428,6 +1466,161 @@ b2r_resize(const b2r_image* dst, const b2r_image* src, const char* filtername,
         return B2R_ERR_FILTER;
     }
     return resize_entry(dst, src, *filter, roi, opt, report, err, errlen);
+}
+
+// A batch of frames of ONE shape: a single persistent launch of the stream
+// kernel walks (frame, strip, band) work items -- no launch gaps, no ramp-up
+// and tail per frame, which is what bounds small frames (a 4K -> 1080p uint16
+// frame is 11 us of HBM time).  Frames that do not qualify (host memory,
+// shapes of other kernels, differing geometry) run one by one.
+int
+b2r_resize_batch(const b2r_image* dst, const b2r_image* src, int nframes,
+                 const char* filtername, float filterwidth, const b2r_roi* roi,
+                 const b2r_options* opt, b2r_report* report, char* err, size_t errlen)
+{
+    if (report)
+        memset(report, 0, sizeof(*report));
+    if (nframes < 0 || (nframes > 0 && (!dst || !src))) {
+        set_err(err, errlen, "resize_batch: bad frame arrays");
+        return B2R_ERR_INVALID;
+    }
+    if (nframes == 0)
+        return B2R_OK;
+    auto same_shape = [](const b2r_image& a, const b2r_image& b) {
+        return a.basetype == b.basetype && a.nchannels == b.nchannels && a.x == b.x && a.y == b.y
+               && a.width == b.width && a.height == b.height && a.full_x == b.full_x
+               && a.full_y == b.full_y && a.full_width == b.full_width
+               && a.full_height == b.full_height && a.xstride == b.xstride
+               && a.ystride == b.ystride;
+    };
+    bool one_launch = nframes > 1 && !(opt && opt->highlightcomp)
+                      && (!opt || opt->path == B2R_PATH_AUTO || opt->path == B2R_PATH_FUSED);
+    int dev0 = opt ? opt->device : 0;
+    for (int i = 0; i < nframes && one_launch; ++i) {
+        if (!dst[i].pixels || !src[i].pixels || !same_shape(dst[i], dst[0])
+            || !same_shape(src[i], src[0]))
+            one_launch = false;
+        int ds = dev0, dd = dev0;
+        if (one_launch
+            && (memspace_of(&src[i], &ds) != B2R_MEM_DEVICE
+                || memspace_of(&dst[i], &dd) != B2R_MEM_DEVICE || ds != dd
+                || (i > 0 && ds != dev0)))
+            one_launch = false;
+        if (i == 0)
+            dev0 = ds;
+        // TMA: 16-byte aligned rows (frame 0 could be re-pitched, a batch is not)
+        if (one_launch
+            && ((((uintptr_t)src[i].pixels) & 15) != 0 || (src[i].ystride & 15) != 0))
+            one_launch = false;
+    }
+    if (one_launch) {
+        BatchCapture cap;
+        cap.want  = true;
+        g_capture = &cap;
+        int rc    = b2r_resize(&dst[0], &src[0], filtername, filterwidth, roi, opt, nullptr, err,
+                               errlen);
+        g_capture = nullptr;
+        if (rc)
+            return rc;
+        if (cap.got) {
+            DeviceGuard guard(dev0);
+            cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
+            FusedParams fp      = cap.fp;
+            const long long doff = (const unsigned char*)fp.dst
+                                   - (const unsigned char*)dst[0].pixels;
+            // per frame: the tensor map over its source rows, its ROI origin
+            const size_t map_bytes = size_t(nframes) * 128;
+            std::vector<unsigned char> host(map_bytes + 64 + size_t(nframes) * sizeof(void*));
+            unsigned char* maps_h
+                = (unsigned char*)(((uintptr_t)host.data() + 63) & ~uintptr_t(63));
+            std::vector<unsigned char*> dsts(nframes);
+            for (int i = 0; i < nframes; ++i) {
+                FusedParams q = fp;
+                q.src         = (const unsigned char*)src[i].pixels;
+                if (stream_encode_map(maps_h + size_t(i) * 128, q, cap.w2, src[i].pixels,
+                                      src[i].height)
+                    != 0) {
+                    set_err(err, errlen, "resize_batch: cannot encode the tensor map of frame %d",
+                            i);
+                    return B2R_ERR_CUDA;
+                }
+                dsts[i] = (unsigned char*)dst[i].pixels + doff;
+            }
+            void* scratch = nullptr;
+            CUDA_TRY(cudaMallocAsync(&scratch, map_bytes + size_t(nframes) * sizeof(void*),
+                                     stream));
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            CUDA_TRY(cudaMemcpyAsync(scratch, maps_h, map_bytes, cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaMemcpyAsync((unsigned char*)scratch + map_bytes, dsts.data(),
+                                     size_t(nframes) * sizeof(void*), cudaMemcpyHostToDevice,
+                                     stream));
+            if (report) {
+                cudaEventCreate(&ev0);
+                cudaEventCreate(&ev1);
+                cudaEventRecord(ev0, stream);
+            }
+            fp.nframes    = nframes;
+            fp.batch_maps = scratch;
+            fp.batch_dst  = (unsigned char* const*)((unsigned char*)scratch + map_bytes);
+            int lrc = launch_resize_stream_batch(fp, cap.w2, cap.sms, stream);
+            cudaError_t e = cudaGetLastError();
+            if (report)
+                cudaEventRecord(ev1, stream);
+            cudaFreeAsync(scratch, stream);
+            if (lrc != 0 || e != cudaSuccess) {
+                set_err(err, errlen, "resize_batch: launch failed (%s)",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "no kernel");
+                return B2R_ERR_CUDA;
+            }
+            if (report) {
+                CUDA_TRY(cudaStreamSynchronize(stream));
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ev0, ev1);
+                cudaEventDestroy(ev0);
+                cudaEventDestroy(ev1);
+                report->path_used        = B2R_PATH_FUSED;
+                report->kernels_launched = 1;
+                report->kernel_ms        = ms;
+                report->fused_vmode      = fp.vk;
+                report->fused_htaps      = fp.ht;
+            }
+            return B2R_OK;
+        }
+        // frame 0 took another kernel (and is done): the rest one by one
+        int launched = 0;
+        for (int i = 1; i < nframes; ++i) {
+            b2r_report r;
+            rc = b2r_resize(&dst[i], &src[i], filtername, filterwidth, roi, opt,
+                            report ? &r : nullptr, err, errlen);
+            if (rc)
+                return rc;
+            if (report) {
+                launched += r.kernels_launched;
+                *report = r;
+            }
+        }
+        if (report)
+            report->kernels_launched = launched;
+        return B2R_OK;
+    }
+    int launched = 0;
+    for (int i = 0; i < nframes; ++i) {
+        b2r_report r;
+        int rc = b2r_resize(&dst[i], &src[i], filtername, filterwidth, roi, opt,
+                            report ? &r : nullptr, err, errlen);
+        if (rc)
+            return rc;
+        if (report) {
+            launched += r.kernels_launched;
+            const int64_t h2d = report->h2d_bytes + r.h2d_bytes, d2h = report->d2h_bytes + r.d2h_bytes;
+            *report            = r;
+            report->h2d_bytes  = h2d;
+            report->d2h_bytes  = d2h;
+        }
+    }
+    if (report)
+        report->kernels_launched = launched;
+    return B2R_OK;
 }
 
 int

@@ -25,9 +25,24 @@ round_taps(int n)
 static int
 round_ring(int k)
 {
-    for (int t : { 2, 4, 6, 8 })
+    // (a ring of 2 runs as a ring of 4 with two idle slots)
+    for (int t : { 4, 6, 8 })
         if (k <= t)
             return t;
+    return 0;
+}
+
+// H windows of the ring-mode (downsizing) kernels: the stream kernel is
+// instantiated for 8 / 10 / 14 / 16 taps; wider windows (strong minification)
+// run the fused kernel's variant whose tap count is a run-time multiple of four
+static int
+round_taps_ring(int n)
+{
+    for (int t : { 8, 10, 14, 16 })
+        if (n <= t)
+            return t;
+    if (n <= FUSED_MAX_HT)
+        return (n + 3) & ~3;
     return 0;
 }
 
@@ -278,7 +293,7 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
             span = std::max(span, cfirst[bcol] - cfirst[a] + std::max(1, gx.count[bcol]));
         window = std::max(window, span);
     }
-    P.ht = round_taps(window);
+    P.ht = use_ring ? round_taps_ring(window) : round_taps(window);
     if (!P.ht)
         return false;
     P.hfirst.resize(npairs);

@@ -256,6 +256,12 @@ struct FusedParams {
     const float* vw;     // [roi_h * vt]
     // stream kernel: data-window row that is row 0 of the TMA tensor map
     int tma_row0;
+    // stream kernel, a batch of frames of one shape in one launch (nframes > 1):
+    // per frame a tensor map (device array of CUtensorMap, 64-byte aligned) and
+    // the address of the ROI's first pixel
+    int nframes;
+    const void* batch_maps;
+    unsigned char* const* batch_dst;
 };
 // Returns false when no instantiation matches (srctype, nch, vk, ht).
 bool
@@ -276,6 +282,14 @@ stream_supported(int srctype, int nch, int vk, int ht, int w2);
 int
 launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma_rows,
                      int sms, void* stream);
+// Fill `map` (128 bytes, 64-byte aligned) with the tensor map the stream kernel
+// reads source rows through.  0 on success.
+int
+stream_encode_map(void* map, const FusedParams& p, int w2, const void* tma_base,
+                  int tma_rows);
+// nframes > 1: p.batch_maps / p.batch_dst are device arrays (one entry per frame)
+int
+launch_resize_stream_batch(const FusedParams& p, int w2, int sms, void* stream);
 typedef void (*ExpandKernel)(const FusedParams, int);
 // resident CTAs per SM for this shape (occupancy query), 0 on error
 int

@@ -15,7 +15,7 @@ pick_ht(int ht, int* smem)
 {
     *smem = StreamSmem<B2R_INST_ST, VK, W2>::TOTAL;
     switch (ht) {
-    case 6: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 6, W2>;
+    case 8: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 8, W2>;
     case 10: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 10, W2>;
     case 14: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 14, W2>;
     case 16: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 16, W2>;
@@ -28,7 +28,6 @@ static StreamKernel
 pick_vk(int vk, int ht, int* smem)
 {
     switch (vk) {
-    case 2: return pick_ht<2, W2>(ht, smem);
     case 4: return pick_ht<4, W2>(ht, smem);
     case 6: return pick_ht<6, W2>(ht, smem);
     case 8: return pick_ht<8, W2>(ht, smem);

@@ -181,12 +181,12 @@ template<int NCH, int W2> struct StreamPark {
 // FP: screen the outputs and re-filter with the zero taps skipped.
 template<int NCH, int HT, int W2, int NR, bool FP>
 __device__ __forceinline__ void
-stream_hpass(const FusedParams& p, unsigned vrows, int nb, int dyb, int dxA, bool has_b,
-             const int (&hb)[4], const float2 (&hw)[HT], int hmix, int hr)
+stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb, int dyb,
+             int dxA, bool has_b, const int (&hb)[4], const float2 (&hw)[HT], int hmix, int hr)
 {
     using G = StreamGeom<W2>;
     const int des = (p.dsttype == BT_UINT8) ? 1 : (p.dsttype == BT_FLOAT ? 4 : 2);
-    unsigned char* dp = p.dst + (long long)(dyb + hr) * p.dst_ystride
+    unsigned char* dp = dbase + (long long)(dyb + hr) * p.dst_ystride
                         + (long long)dxA * (NCH * des);
 #pragma unroll 1
     for (int k = 0; k < NR; ++k) {
@@ -293,7 +293,10 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     const unsigned bars   = smem0 + S::BARS_OFF;  // full[NST], empty[NST]
     const int warp        = threadIdx.x >> 5;
     const int lane        = threadIdx.x & 31;
-    const int nitems      = p.nstrips * p.nbands;
+    // work items: (frame, strip, band), frame-major -- a batch of frames of one
+    // shape runs as ONE persistent launch (p.nframes > 1)
+    const int per_frame   = p.nstrips * p.nbands;
+    const int nitems      = per_frame * (p.nframes > 1 ? p.nframes : 1);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -320,8 +323,13 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             int stage = 0;
             unsigned phase = 0;
             for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-                const Strip strip = p.strips[item % p.nstrips];
-                const Band band   = p.bands[item / p.nstrips];
+                const int frame   = item / per_frame;
+                const int fitem   = item - frame * per_frame;
+                const Strip strip = p.strips[fitem % p.nstrips];
+                const Band band   = p.bands[fitem / p.nstrips];
+                const CUtensorMap* map
+                    = p.batch_maps ? reinterpret_cast<const CUtensorMap*>(p.batch_maps) + frame
+                                   : &tmap;
                 const int nst     = (band.nrows + ROWS - 1) / ROWS;
                 const int nbox    = min(S::NBOX, (strip.nvec * 4 + S::BOXW - 1) / S::BOXW);
                 const unsigned tx = nbox * S::BOX_B + ROWS * S::WROWB;
@@ -337,7 +345,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
 #pragma unroll
                         for (int b = 0; b < S::NBOX; ++b)
                             if (b < nbox)
-                                tma_load_2d(sb + b * S::BOX_B, &tmap, strip.e0 + b * S::BOXW, row,
+                                tma_load_2d(sb + b * S::BOX_B, map, strip.e0 + b * S::BOXW, row,
                                             full);
                         bulk_load_1d(sb + S::DATA_B, gw, ROWS * S::WROWB, full);
                     }
@@ -362,8 +370,9 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         // this thread's 4*es bytes inside a stage
         const int toff = ((tid * 4) / S::BOXW) * S::BOX_B + ((tid * 4) % S::BOXW) * es;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const Strip strip = p.strips[item % p.nstrips];
-            const Band band   = p.bands[item / p.nstrips];
+            const int fitem   = item % per_frame;
+            const Strip strip = p.strips[fitem % p.nstrips];
+            const Band band   = p.bands[fitem / p.nstrips];
             const bool vactive = tid < strip.nvec;
             StreamPark<NCH, W2> park;
             park.init(strip.e0, tid);
@@ -512,10 +521,13 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         // total batches of this CTA: the last two hand-backs have no taker
         int total = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x)
-            total += (p.bands[item / p.nstrips].ndy + BATCH - 1) / BATCH;
+            total += (p.bands[(item % per_frame) / p.nstrips].ndy + BATCH - 1) / BATCH;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-            const Strip strip = p.strips[item % p.nstrips];
-            const Band band   = p.bands[item / p.nstrips];
+            const int frame   = item / per_frame;
+            const int fitem   = item - frame * per_frame;
+            const Strip strip = p.strips[fitem % p.nstrips];
+            const Band band   = p.bands[fitem / p.nstrips];
+            unsigned char* dbase = p.batch_dst ? p.batch_dst[frame] : p.dst;
             const bool pair_active = 2 * hp < strip.ndx;
             const bool has_b       = 2 * hp + 1 < strip.ndx;
             const int dxA          = strip.dx0 + 2 * hp;
@@ -545,8 +557,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 const int b  = nbatch & 1;
                 named_bar_sync(1 + b, NSYNC);
                 if (pair_active)
-                    stream_hpass<NCH, HT, W2, NR, FP>(p, vbuf0 + b * S::VBUF_B, nb, dyb, dxA,
-                                                      has_b, hb, hw, hmix, hr);
+                    stream_hpass<NCH, HT, W2, NR, FP>(p, dbase, vbuf0 + b * S::VBUF_B, nb, dyb,
+                                                      dxA, has_b, hb, hw, hmix, hr);
                 ++nbatch;
                 if (nbatch + 2 <= total)
                     named_bar_arrive(3 + b, NSYNC);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 
 namespace b2r {
@@ -71,18 +72,15 @@ encode_tiled_fn()
 }
 
 int
-launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma_rows,
-                     int sms, void* stream)
+stream_encode_map(void* mapv, const FusedParams& p, int w2, const void* tma_base,
+                  int tma_rows)
 {
-    int smem = 0;
-    StreamKernel k = pick_stream(p.srctype, p.nch, p.vk, p.ht, w2, &smem);
     EncodeTiledFn enc = encode_tiled_fn();
-    if (!k || !enc || p.nstrips <= 0 || p.nbands <= 0 || tma_rows <= 0)
+    if (!enc || tma_rows <= 0)
         return -1;
     const int es = basetype_size(p.srctype);
     if (((uintptr_t)tma_base & 15) || (p.src_ystride & 15) || p.src_ystride <= 0)
         return -2;
-    alignas(64) CUtensorMap map;
     const cuuint64_t dims[2]    = { (cuuint64_t)p.src_w * p.nch, (cuuint64_t)tma_rows };
     const cuuint64_t strides[1] = { (cuuint64_t)p.src_ystride };
     const cuuint32_t box[2]     = { 256u, (cuuint32_t)stream_rows(w2) };
@@ -90,21 +88,52 @@ launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma
     const CUtensorMapDataType dt = es == 4   ? CU_TENSOR_MAP_DATA_TYPE_UINT32
                                    : es == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
                                              : CU_TENSOR_MAP_DATA_TYPE_UINT8;
-    if (enc(&map, dt, 2, const_cast<void*>(tma_base), dims, strides, box, estr,
+    if (enc((CUtensorMap*)mapv, dt, 2, const_cast<void*>(tma_base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
         != CUDA_SUCCESS)
         return -3;
+    return 0;
+}
+
+static int
+launch_with_map(const FusedParams& p, int w2, const CUtensorMap& map, int sms, void* stream)
+{
+    int smem = 0;
+    StreamKernel k = pick_stream(p.srctype, p.nch, p.vk, p.ht, w2, &smem);
+    if (!k || p.nstrips <= 0 || p.nbands <= 0)
+        return -1;
     if (cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
         != cudaSuccess) {
         cudaGetLastError();
         return -4;
     }
-    const int items = p.nstrips * p.nbands;
-    dim3 grid((unsigned)std::min(items, std::max(1, sms)), 1, 1);
+    const long long items = (long long)p.nstrips * p.nbands * (p.nframes > 1 ? p.nframes : 1);
+    dim3 grid((unsigned)std::min<long long>(items, std::max(1, sms)), 1, 1);
     const int threads = STREAM_PTHREADS + STREAM_VTHREADS * w2 + STREAM_HTHREADS;
     launch_pdl(k, grid, dim3(threads), (size_t)smem, (cudaStream_t)stream, map, p);
     return 0;
+}
+
+int
+launch_resize_stream(const FusedParams& p, int w2, const void* tma_base, int tma_rows,
+                     int sms, void* stream)
+{
+    alignas(64) CUtensorMap map;
+    int rc = stream_encode_map(&map, p, w2, tma_base, tma_rows);
+    if (rc)
+        return rc;
+    return launch_with_map(p, w2, map, sms, stream);
+}
+
+int
+launch_resize_stream_batch(const FusedParams& p, int w2, int sms, void* stream)
+{
+    if (p.nframes < 1 || !p.batch_maps || !p.batch_dst)
+        return -1;
+    alignas(64) CUtensorMap unused;
+    memset(&unused, 0, sizeof(unused));
+    return launch_with_map(p, w2, unused, sms, stream);
 }
 
 }  // namespace b2r

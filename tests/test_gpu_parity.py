@@ -832,3 +832,40 @@ def test_overscan_interior_fused_frame_exact(oiio, oracle, st):
     assert np.array_equal(got[:1], g2[:1]) and np.array_equal(got[:, :1], g2[:, :1])
     if st == "float":
         assert not np.array_equal(got[60:160, 80:240], g2[60:160, 80:240])
+
+
+# ---- b2r_resize_batch: many frames of one shape in one launch -------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("st,dt,nch,filt,sshape,dshape", [
+    ("uint16", "uint16", 3, "lanczos3", (432, 768), (216, 384)),
+    ("float", "float", 4, "lanczos3", (600, 1100), (300, 550)),
+    ("half", "half", 4, "blackman-harris", (400, 640), (200, 320)),
+    ("float", "float", 3, "mitchell", (300, 500), (170, 260)),
+    ("uint8", "uint8", 3, "mitchell", (90, 160), (360, 640)),      # expand kernel: frame by frame
+])
+def test_resize_batch_equals_single_frames(oiio, st, dt, nch, filt, sshape, dshape):
+    """Frames of one shape through ONE persistent launch give exactly what
+    one call per frame gives (and the shapes the stream kernel does not take
+    fall back to frame-by-frame)."""
+    import torch
+    IBA = oiio.ImageBufAlgo
+    nfr = 5
+
+    def T(a):
+        t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
+        return (t.view(torch.uint16) if a.dtype == np.uint16 else t).cuda()
+    srcs = [T(synth.image(sshape[1], sshape[0], nch, _np_dtype(st), seed=300 + i))
+            for i in range(nfr)]
+    tdt = {"uint8": torch.uint8, "uint16": torch.uint16, "half": torch.float16,
+           "float": torch.float32}[dt]
+    one = [torch.zeros((dshape[0], dshape[1], nch), dtype=tdt, device="cuda") for _ in range(nfr)]
+    many = [torch.zeros_like(t) for t in one]
+    for s_, d in zip(srcs, one):
+        assert IBA.resize(oiio.ImageBuf(d), oiio.ImageBuf(s_), filtername=filt)
+    assert IBA.resize_batch([oiio.ImageBuf(d) for d in many], [oiio.ImageBuf(s_) for s_ in srcs],
+                            filtername=filt, report=True)
+    torch.cuda.synchronize()
+    for a, b in zip(one, many):
+        assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
+    if st != "uint8":
+        assert IBA.last_report.kernels_launched == 1  # one launch for the five frames
