@@ -897,6 +897,9 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             const uintptr_t a = (uintptr_t)fp.dst | (uintptr_t)dstd.ystride;
             fp.dst_align = (a % 16 == 0 && (4 * nch * des) % 16 == 0) ? 16
                            : (a % 4 == 0 ? 4 : 0);
+            fp.dst_pow2  = 16;
+            while (fp.dst_pow2 > 1 && (a & uintptr_t(fp.dst_pow2 - 1)))
+                fp.dst_pow2 >>= 1;
         }
         if (src_is_fp) {
             // per-call flag from a per-device ring (plans are shared between

@@ -49,6 +49,29 @@ store_elem(unsigned char* p, int bt, float v)
     }
 }
 
+// convert_type<float,uint>(v) (fmath.h:753-764, 1009-1031) for v*mx computed
+// with a separate multiply: s = v*mx; s += 0.5 (s >= 0) ; clamp ; truncate.
+// For s < 0 the reference adds -0.5 and clamps to 0: s + 0.5 is below 0.5
+// there and truncates (or saturates) to 0 as well, so one FADD serves both
+// signs.  A float -> u8/u16 cvt clamps to the destination range by itself (and
+// sends NaN to 0), which is the reference's clamp: no min/max instructions.
+__device__ __forceinline__ unsigned
+quant_u8(float v)
+{
+    float s = __fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+    unsigned u;
+    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(u) : "f"(s));
+    return u;
+}
+__device__ __forceinline__ unsigned
+quant_u16(float v)
+{
+    float s = __fadd_rn(__fmul_rn(v, 65535.0f), 0.5f);
+    unsigned u;
+    asm("cvt.rzi.u16.f32 %0, %1;" : "=r"(u) : "f"(s));
+    return u;
+}
+
 __device__ __forceinline__ bool
 nonfinite(float v)
 {

@@ -295,13 +295,12 @@ store_pixel(const FusedParams& p, unsigned char* dp, int des, const float (&a)[N
             *reinterpret_cast<uint2*>(dp) = u;
         } else if (p.dsttype == BT_UINT16) {
             uint2 u;
-            u.x = quant_int(a[0], 65535.0f) | (quant_int(a[1], 65535.0f) << 16);
-            u.y = quant_int(a[2], 65535.0f) | (quant_int(a[NCH - 1], 65535.0f) << 16);
+            u.x = quant_u16(a[0]) | (quant_u16(a[1]) << 16);
+            u.y = quant_u16(a[2]) | (quant_u16(a[NCH - 1]) << 16);
             *reinterpret_cast<uint2*>(dp) = u;
         } else {
-            unsigned int u = quant_int(a[0], 255.0f) | (quant_int(a[1], 255.0f) << 8)
-                             | (quant_int(a[2], 255.0f) << 16)
-                             | (quant_int(a[NCH - 1], 255.0f) << 24);
+            unsigned int u = quant_u8(a[0]) | (quant_u8(a[1]) << 8) | (quant_u8(a[2]) << 16)
+                             | (quant_u8(a[NCH - 1]) << 24);
             *reinterpret_cast<unsigned int*>(dp) = u;
         }
     } else {

@@ -223,6 +223,8 @@ struct FusedParams {
     int src_vec_ok, dst_vec_ok;  // 4-element vector loads / stores allowed
     int expand;                  // 1: resize_expand_kernel tables (groups of 4 columns)
     int dst_align;               // expand: 16 / 4 / 0 = alignment dst rows guarantee
+    int dst_pow2;                // stream: largest power of two (<= 16) dividing the ROI
+                                 // origin's address and the dst row pitch
     int vrow_linear;             // expand: V rows laid out linearly, not in planes
     int check_nonfinite;         // float/half sources: flag non-finite outputs
     int* nonfinite_flag;

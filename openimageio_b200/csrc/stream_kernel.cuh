@@ -117,9 +117,12 @@ named_bar_arrive(int id, int count)
 // W2 = 1: 256 V threads, the strip geometry of the fused kernel (<= 128 dst
 // columns, <= 256 source pixels); W2 = 2: 512 V threads, strips twice as wide,
 // half as many rows per hand-over batch.  A V thread always owns 4 elements.
-template<int W2> struct StreamGeom {
-    static constexpr int NVT     = STREAM_VTHREADS * W2;      // V threads
-    static constexpr int VPIX    = NVT;                       // pixels a V row holds
+// E2: four-element groups per V thread -- 2 for the 1- and 2-byte source types
+// of the wide geometry (16 / 8 bytes per thread per row: half the per-element
+// control and load overhead), 1 otherwise.
+template<int W2, int E2 = 1> struct StreamGeom {
+    static constexpr int NVT     = STREAM_VTHREADS * W2 / E2;  // V threads
+    static constexpr int VPIX    = STREAM_VTHREADS * W2;      // pixels a V row holds
     static constexpr int HCOLS   = FUSED_HCOLS * W2;          // dst columns per strip
     static constexpr int HPAIRS  = HCOLS / 2;
     static constexpr int ROWG    = STREAM_HTHREADS / HPAIRS;  // H row groups (4 / 2)
@@ -128,8 +131,8 @@ template<int W2> struct StreamGeom {
     static constexpr int THREADS = STREAM_PTHREADS + NVT + STREAM_HTHREADS;
     static constexpr int ROWS    = stream_rows(W2);           // source rows per stage
     // registers after setmaxnreg (the kernel is compiled for 65536 / THREADS)
-    static constexpr int VREGS   = W2 == 1 ? 96 : 64;
-    static constexpr int HREGS   = W2 == 1 ? 120 : 112;
+    static constexpr int VREGS   = NVT == 256 ? 96 : 64;
+    static constexpr int HREGS   = NVT == 256 ? 120 : 112;
 };
 template<int W2>
 __device__ __forceinline__ int
@@ -138,39 +141,149 @@ stream_planar_byte(int q)
     return ((q >> 2) + (q & 3) * StreamGeom<W2>::PLANE) * 16;
 }
 
-// Where a V thread parks its 4 filtered elements.  NCH == 4: one planar
-// float4 pixel; otherwise one scalar offset per element (padded pixels).
-template<int NCH, int W2> struct StreamPark {
-    int off[NCH == 4 ? 1 : 4];
+// Where a V thread parks its 4 * E2 filtered elements.  NCH == 4: E2 planar
+// float4 pixels; otherwise one scalar offset per element (padded pixels).
+template<int NCH, int W2, int E2> struct StreamPark {
+    static constexpr int NOFF = NCH == 4 ? E2 : 4 * E2;
+    int off[NOFF];
     __device__ __forceinline__ void init(int e0, int v)
     {
         if (NCH == 4) {
-            off[0] = stream_planar_byte<W2>(v);
+#pragma unroll
+            for (int k = 0; k < E2; ++k)
+                off[k] = stream_planar_byte<W2>(E2 * v + k);
         } else {
             const int px0 = e0 / NCH;
 #pragma unroll
-            for (int k = 0; k < (NCH == 4 ? 1 : 4); ++k) {
-                int E  = e0 + 4 * v + k;
+            for (int k = 0; k < NOFF; ++k) {
+                int E  = e0 + 4 * E2 * v + k;
                 int px = E / NCH;
                 off[k] = stream_planar_byte<W2>(px - px0) + (E - NCH * px) * 4;
             }
         }
     }
-    __device__ __forceinline__ void store(unsigned row, const float4& a) const
+    __device__ __forceinline__ void store(unsigned row, const float4 (&a)[E2]) const
     {
-        if (NCH == 4) {
-            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[0]), "f"(a.x),
-                         "f"(a.y), "f"(a.z), "f"(a.w)
-                         : "memory");
-        } else {
-            constexpr int S = NCH == 4 ? 0 : 1;  // keeps the indices in range for NCH == 4
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[0]), "f"(a.x) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 1]), "f"(a.y) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 2]), "f"(a.z) : "memory");
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * 3]), "f"(a.w) : "memory");
+#pragma unroll
+        for (int h = 0; h < E2; ++h) {
+            if (NCH == 4) {
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(row + off[h]),
+                             "f"(a[h].x), "f"(a[h].y), "f"(a[h].z), "f"(a[h].w)
+                             : "memory");
+            } else {
+                constexpr int S = NCH == 4 ? 0 : 1;  // keeps the indices in range for NCH == 4
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * h)]), "f"(a[h].x)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * h + 1)]),
+                             "f"(a[h].y)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * h + 2)]),
+                             "f"(a[h].z)
+                             : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(row + off[S * (4 * h + 3)]),
+                             "f"(a[h].w)
+                             : "memory");
+            }
         }
     }
 };
+
+// Raw group of 4 * E2 elements -> E2 float4 values.
+template<int ST, int E2>
+__device__ __forceinline__ void
+stream_convert(const uint4& r, float4 (&v)[E2])
+{
+    if (E2 == 1) {
+        v[0] = convert_raw4<ST>(r);
+    } else if (SrcTraits<ST>::es == 2) {
+        v[0]      = convert_raw4<ST>(make_uint4(r.x, r.y, 0u, 0u));
+        v[E2 - 1] = convert_raw4<ST>(make_uint4(r.z, r.w, 0u, 0u));
+    } else {
+        v[0]      = convert_raw4<ST>(make_uint4(r.x, 0u, 0u, 0u));
+        v[E2 - 1] = convert_raw4<ST>(make_uint4(r.y, 0u, 0u, 0u));
+    }
+}
+
+// ---- H-pass epilogue: quantise and store two adjacent pixels ---------------
+// convert_type<float,D> (fmath.h:753-764, 1009-1031) per channel, then the
+// pair's 2 * NCH elements leave as the widest words their alignment allows
+// (RGB: three words of two elements; `palign` = power of two dividing the ROI
+// origin and the row pitch).
+__device__ __forceinline__ unsigned
+pack_half2(float a, float b)
+{
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<unsigned*>(&h);
+}
+template<int NCH>
+__device__ __forceinline__ void
+stream_store_pair(const FusedParams& p, unsigned char* dp, int des, const float4& A,
+                  const float4& B, bool has_b)
+{
+    const float a[4] = { A.x, A.y, A.z, A.w };
+    const float b[4] = { B.x, B.y, B.z, B.w };
+    if (NCH == 4 || !has_b || p.dst_pow2 < 2 * des * (NCH == 3 ? 1 : NCH)) {
+        float oa[NCH], ob[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            oa[c] = a[c];
+            ob[c] = b[c];
+        }
+        store_pixel<NCH>(p, dp, des, oa);
+        if (has_b)
+            store_pixel<NCH>(p, dp + NCH * des, des, ob);
+        return;
+    }
+    // the pair's elements in memory order
+    float e[2 * NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        e[c]       = a[c];
+        e[NCH + c] = b[c];
+    }
+    if (p.dsttype == BT_FLOAT) {
+        if (NCH == 2)
+            *reinterpret_cast<float4*>(dp) = make_float4(e[0], e[1], e[2 % (2 * NCH)],
+                                                         e[3 % (2 * NCH)]);
+        else
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                reinterpret_cast<float2*>(dp)[k] = make_float2(e[2 * k], e[2 * k + 1]);
+    } else if (p.dsttype == BT_HALF) {
+        unsigned wds[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+            wds[k] = pack_half2(e[2 * k], e[2 * k + 1]);
+        if (NCH == 2)
+            *reinterpret_cast<uint2*>(dp) = make_uint2(wds[0], wds[1 % NCH]);
+        else
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                reinterpret_cast<unsigned*>(dp)[k] = wds[k];
+    } else if (p.dsttype == BT_UINT16) {
+        unsigned wds[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+            wds[k] = quant_u16(e[2 * k]) | (quant_u16(e[2 * k + 1]) << 16);
+        if (NCH == 2)
+            *reinterpret_cast<uint2*>(dp) = make_uint2(wds[0], wds[1 % NCH]);
+        else
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                reinterpret_cast<unsigned*>(dp)[k] = wds[k];
+    } else {
+        unsigned short wds[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+            wds[k] = (unsigned short)(quant_u8(e[2 * k]) | (quant_u8(e[2 * k + 1]) << 8));
+        if (NCH == 2)
+            *reinterpret_cast<unsigned*>(dp) = unsigned(wds[0]) | (unsigned(wds[1 % NCH]) << 16);
+        else
+#pragma unroll
+            for (int k = 0; k < NCH; ++k)
+                reinterpret_cast<unsigned short*>(dp)[k] = wds[k];
+    }
+}
 
 // ---- H pass over one batch ---------------------------------------------------
 // Same arithmetic as fused_hpass (two adjacent dst columns per thread from one
@@ -228,17 +341,7 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
                 }
             }
         }
-        const float ca[4] = { aA.x, aA.y, aA.z, aA.w };
-        const float cb[4] = { aB.x, aB.y, aB.z, aB.w };
-        float oa[NCH], ob[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            oa[c] = ca[c];
-            ob[c] = cb[c];
-        }
-        store_pixel<NCH>(p, dp, des, oa);
-        if (has_b)
-            store_pixel<NCH>(p, dp + NCH * des, des, ob);
+        stream_store_pair<NCH>(p, dp, des, aA, aB, has_b);
         dp += (long long)G::ROWG * p.dst_ystride;
         vrows += G::ROWG * G::PITCH_B;
     }
@@ -248,12 +351,16 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
 //   stages  NST x STAGE_B   STAGE_B = NBOX boxes of (ROWS x 256 elements) + ROWS ring-table rows
 //   vbuf    2 x BATCH x PITCH_B
 //   bars    2 x NST mbarriers
+template<int ST> struct StreamE2 {
+    template<int W2> static constexpr int of() { return (W2 == 2 && SrcTraits<ST>::es < 4) ? 2 : 1; }
+};
 template<int ST, int VK, int W2> struct StreamSmem {
-    using G = StreamGeom<W2>;
+    static constexpr int E2       = StreamE2<ST>::template of<W2>();
+    using G = StreamGeom<W2, E2>;
     static constexpr int es       = SrcTraits<ST>::es;
     static constexpr int ROWS     = G::ROWS;
     static constexpr int BOXW     = 256;  // elements per box row (the TMA limit)
-    static constexpr int NBOX     = G::NVT * 4 / BOXW;
+    static constexpr int NBOX     = G::NVT * 4 * E2 / BOXW;
     static constexpr int BOX_ROWB = BOXW * es;
     static constexpr int BOX_B    = ROWS * BOX_ROWB;
     static constexpr int WROW     = stream_wrow(VK);  // floats per ring-table row
@@ -271,11 +378,12 @@ template<int ST, int VK, int W2> struct StreamSmem {
 };
 
 template<int ST, int NCH, int VK, int HT, int W2>
-__global__ void __launch_bounds__(StreamGeom<W2>::THREADS, 1)
+__global__ void __launch_bounds__(StreamSmem<ST, VK, W2>::G::THREADS, 1)
 resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p)
 {
-    using G = StreamGeom<W2>;
     using S = StreamSmem<ST, VK, W2>;
+    using G = typename S::G;
+    constexpr int E2    = S::E2;
     constexpr int es    = S::es;
     constexpr int ROWS  = S::ROWS;
     constexpr int NST   = S::NST;
@@ -367,24 +475,27 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         int stage = 0;
         unsigned phase = 0;
         int nbatch = 0;  // batches handed over so far (whole kernel)
-        // this thread's 4*es bytes inside a stage
-        const int toff = ((tid * 4) / S::BOXW) * S::BOX_B + ((tid * 4) % S::BOXW) * es;
+        // this thread's 4*E2*es bytes inside a stage
+        constexpr int EPT = 4 * E2;
+        const int toff = ((tid * EPT) / S::BOXW) * S::BOX_B + ((tid * EPT) % S::BOXW) * es;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
             const int fitem   = item % per_frame;
             const Strip strip = p.strips[fitem % p.nstrips];
             const Band band   = p.bands[fitem / p.nstrips];
-            const bool vactive = tid < strip.nvec;
-            StreamPark<NCH, W2> park;
+            const bool vactive = tid * E2 < strip.nvec;
+            StreamPark<NCH, W2, E2> park;
             park.init(strip.e0, tid);
             // acc[0] is the oldest open destination row (the ring table is
             // laid out the same way).  When a row completes it is parked and
             // the others move up one place -- not with register moves: the
             // NEXT source row's FFMA2s read acc[k+1] and write acc[k]
             // (`shift`), so the rotation costs nothing.
-            float4 acc[VK];
+            float4 acc[VK][E2];
 #pragma unroll
             for (int k = 0; k < VK; ++k)
-                acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int h = 0; h < E2; ++h)
+                    acc[k][h] = make_float4(0.f, 0.f, 0.f, 0.f);
             bool shift = false;  // acc[0] was parked after the previous source row
             int ndone  = 0;      // destination rows of the band completed so far
             unsigned prow = vbuf0 + (nbatch & 1) * S::VBUF_B;  // where the next row is parked
@@ -408,8 +519,12 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             auto rotate = [&]() {
 #pragma unroll
                 for (int k = 0; k + 1 < VK; ++k)
-                    acc[k] = acc[k + 1];
-                acc[VK - 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int h = 0; h < E2; ++h)
+                        acc[k][h] = acc[k + 1][h];
+#pragma unroll
+                for (int h = 0; h < E2; ++h)
+                    acc[VK - 1][h] = make_float4(0.f, 0.f, 0.f, 0.f);
             };
             // The band's rows in the ring table are padded to whole stages with
             // all-zero rows, so every stage is processed in full: a padded row
@@ -423,9 +538,9 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
                     const unsigned char* a = sb + toff + j * S::BOX_ROWB;
-                    if (es == 4)
+                    if (EPT * es == 16)
                         raw[j] = *reinterpret_cast<const uint4*>(a);
-                    else if (es == 2) {
+                    else if (EPT * es == 8) {
                         uint2 u = *reinterpret_cast<const uint2*>(a);
                         raw[j]  = make_uint4(u.x, u.y, 0u, 0u);
                     } else
@@ -448,10 +563,16 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     // slots whose weight merges clamped taps of both signs;
                     // 16 / 17: the (single) completing row opens / closes a batch
                     const int info = __float_as_int(w[WROW - 1]);
-                    const float4 v = convert_raw4<ST>(raw[j]);
-                    bool bad       = false;
-                    if (FP)
-                        bad = !(fabsf((v.x + v.y) + (v.z + v.w)) <= 3.402823466e+38f);
+                    float4 v[E2];
+                    stream_convert<ST, E2>(raw[j], v);
+                    bool bad = false;
+                    if (FP) {
+                        float q = 0.0f;
+#pragma unroll
+                        for (int h = 0; h < E2; ++h)
+                            q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                        bad = !(fabsf(q) <= 3.402823466e+38f);
+                    }
                     if (FP && bad) {
                         // Inf/NaN in this group: never let it meet a zero
                         // weight; a weight that stands for clamped taps of
@@ -460,28 +581,36 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                             rotate();
 #pragma unroll
                         for (int k = 0; k < VK; ++k) {
-                            if (w[k] != 0.0f)
-                                fma4(acc[k], w[k], v);
-                            if ((info >> (8 + k)) & 1)
-                                fma4(acc[k], 0.0f, v);
+#pragma unroll
+                            for (int h = 0; h < E2; ++h) {
+                                if (w[k] != 0.0f)
+                                    fma4(acc[k][h], w[k], v[h]);
+                                if ((info >> (8 + k)) & 1)
+                                    fma4(acc[k][h], 0.0f, v[h]);
+                            }
                         }
                     } else if (shift) {
 #pragma unroll
                         for (int k = 0; k < VK; ++k) {
-                            // acc[k] = w[k] * v + acc[k + 1]
-                            const float4 c = (k + 1 < VK) ? acc[k + 1]
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                            const float2 ww = make_float2(w[k], w[k]);
-                            float2 lo = __ffma2_rn(ww, make_float2(v.x, v.y),
-                                                   make_float2(c.x, c.y));
-                            float2 hi = __ffma2_rn(ww, make_float2(v.z, v.w),
-                                                   make_float2(c.z, c.w));
-                            acc[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+#pragma unroll
+                            for (int h = 0; h < E2; ++h) {
+                                // acc[k] = w[k] * v + acc[k + 1]
+                                const float4 c = (k + 1 < VK) ? acc[k + 1][h]
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                                const float2 ww = make_float2(w[k], w[k]);
+                                float2 lo = __ffma2_rn(ww, make_float2(v[h].x, v[h].y),
+                                                       make_float2(c.x, c.y));
+                                float2 hi = __ffma2_rn(ww, make_float2(v[h].z, v[h].w),
+                                                       make_float2(c.z, c.w));
+                                acc[k][h] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                            }
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < VK; ++k)
-                            fma4(acc[k], w[k], v);
+#pragma unroll
+                            for (int h = 0; h < E2; ++h)
+                                fma4(acc[k][h], w[k], v[h]);
                     }
                     if (FP)
                         __syncwarp();
