@@ -429,6 +429,53 @@ B2R_API int b2r_mipchain_download(const b2r_mipchain* chain, int level,
 B2R_API float b2r_mipchain_kernel_ms(const b2r_mipchain* chain);
 B2R_API void b2r_mipchain_destroy(b2r_mipchain* chain);
 
+/* ---- pixel hash (maketx oiio:SHA-1) --------------------------------------- */
+/* ImageBufAlgo::computePixelHashSHA1 (imagebufalgo_compare.cpp:856-892): SHA-1
+ * over the ROI's scanlines in the image's own pixel format, in `blocksize`-row
+ * blocks (0 or >= height: one stream) whose hex digests are hashed together,
+ * with `extrainfo` appended last.  maketx calls it on the top level with
+ * blocksize 256 and "<filter> [sharpen_A=..] [highlightcomp=1 ] .." as extra
+ * info (maketexture.cpp:1909-1934).  Runs on `nthreads` HOST threads (0 = all),
+ * one block per task; device images are downloaded first.  digest41 receives
+ * 40 upper-case hex digits and a terminating NUL. */
+B2R_API int b2r_pixel_hash_sha1(const b2r_image* src, const char* extrainfo,
+                                const b2r_roi* roi, int blocksize, int nthreads,
+                                char* digest41, char* err, size_t errlen);
+
+/* ---- tiled, compressed level output ------------------------ */
+/* What write_mipmap does with every finished level -- out->open(AppendMIPLevel),
+ * small->write(out), maketexture.cpp:957-974 -- up to the compressed tiles the
+ * file plugin stores: each level of `chain` (from first_level on) is re-laid
+ * into tile_width x tile_height tiles on the device (float32, or converted to
+ * half: maketx -d half), downloaded through pinned staging slots on a copy
+ * stream, and deflated tile by tile (zlib; maketx's default "zip" compression,
+ * maketexture.cpp:1605) by `nthreads` host threads while the next chunk is in
+ * flight.  Edge tiles are zero-padded to full size.  The container format
+ * (TIFF / OpenEXR headers and offset tables) stays with the file plugins. */
+typedef struct b2r_tile_options {
+    int32_t tile_width, tile_height; /* 0 -> 64 (maketexture.cpp:1100-1106) */
+    int32_t out_basetype;            /* B2R_FLOAT (0 -> float) or B2R_HALF */
+    int32_t compression;             /* 0 store, 1 zlib deflate */
+    int32_t zlevel;                  /* 1..9, 0 -> 1 */
+    int32_t nthreads;                /* 0 -> hardware concurrency */
+    int32_t first_level;             /* skip levels below this one */
+    int32_t reserved[3];
+} b2r_tile_options;
+typedef struct b2r_tileset b2r_tileset;
+B2R_API int b2r_mipchain_encode_tiles(const b2r_mipchain* chain,
+                                      const b2r_tile_options* opt, b2r_tileset** out,
+                                      char* err, size_t errlen);
+B2R_API int b2r_tileset_nlevels(const b2r_tileset* ts);
+B2R_API int b2r_tileset_level(const b2r_tileset* ts, int level, int* width, int* height,
+                              int* ntiles_x, int* ntiles_y);
+/* One stored tile (compressed bytes, or raw when compression == 0). */
+B2R_API int b2r_tileset_tile(const b2r_tileset* ts, int level, int tx, int ty,
+                             const void** data, size_t* bytes);
+/* what: 0 wall ms of the encode call, 1 device ms (relayout + downloads),
+ * 2 host ms inside the deflate phases, 3 raw bytes, 4 stored bytes. */
+B2R_API double b2r_tileset_stat(const b2r_tileset* ts, int what);
+B2R_API void b2r_tileset_destroy(b2r_tileset* ts);
+
 /* ---- the same chain cut into row bands over several GPUs ---------------- */
 /* One process, `ndevices` GPUs of one box (replaces the level loop
  * of write_mipmap, maketexture.cpp:823-986, for textures whose level 0 is too

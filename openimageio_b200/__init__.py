@@ -72,6 +72,13 @@ class _MipOptions(C.Structure):
                 ("reserved", C.c_int32 * 4)]
 
 
+class _TileOptions(C.Structure):
+    _fields_ = [("tile_width", C.c_int32), ("tile_height", C.c_int32),
+                ("out_basetype", C.c_int32), ("compression", C.c_int32),
+                ("zlevel", C.c_int32), ("nthreads", C.c_int32),
+                ("first_level", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
 class _PixelStatsC(C.Structure):
     _fields_ = [("min", C.c_float), ("max", C.c_float), ("avg", C.c_float),
                 ("stddev", C.c_float), ("nancount", C.c_int64),
@@ -230,6 +237,17 @@ def lib():
     L.b2r_mipchain_kernel_ms.restype = C.c_float
     L.b2r_mipchain_kernel_ms.argtypes = [C.c_void_p]
     L.b2r_mipchain_destroy.argtypes = [C.c_void_p]
+    L.b2r_pixel_hash_sha1.argtypes = [C.POINTER(_Image), C.c_char_p, C.POINTER(_Roi),
+                                      C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]
+    L.b2r_mipchain_encode_tiles.argtypes = [C.c_void_p, C.POINTER(_TileOptions),
+                                            C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.b2r_tileset_nlevels.argtypes = [C.c_void_p]
+    L.b2r_tileset_level.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int)] * 4
+    L.b2r_tileset_tile.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.b2r_tileset_stat.restype = C.c_double
+    L.b2r_tileset_stat.argtypes = [C.c_void_p, C.c_int]
+    L.b2r_tileset_destroy.argtypes = [C.c_void_p]
     L.b2r_mipchain_create_banded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
                                              C.POINTER(_MipOptions), C.POINTER(C.c_int),
                                              C.c_int, C.c_char_p, C.c_size_t]
@@ -1005,6 +1023,25 @@ class _IBA:
         return None
 
     # ---- fillholes_pushpull ----------------------------------------------
+    def computePixelHashSHA1(self, src, extrainfo="", roi=None, blocksize=0, nthreads=0):
+        """ImageBufAlgo::computePixelHashSHA1 (imagebufalgo_compare.cpp:856-892):
+        upper-case hex SHA-1 of the pixels (+ extrainfo), in `blocksize`-row
+        blocks when blocksize > 0.  Host threads; needs no GPU for host images."""
+        if not isinstance(src, ImageBuf):
+            src = ImageBuf(src)
+        im = src._c()
+        r = None
+        if roi is not None and roi.defined:
+            r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend)
+        out = C.create_string_buffer(41)
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_pixel_hash_sha1(C.byref(im), (extrainfo or "").encode(),
+                                       C.byref(r) if r is not None else None,
+                                       int(blocksize), int(nthreads), out, err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        return out.value.decode()
+
     def fillholes_pushpull(self, *args, roi=None, nthreads=0, device=0):
         """ImageBufAlgo::fillholes_pushpull(dst, src, roi, nthreads)
         (imagebufalgo.cpp:1600-1682)."""
@@ -1517,6 +1554,69 @@ class MipChain:
         if rc:
             raise B2RError(err.value.decode())
         return out
+
+
+class TileSet:
+    """Compressed tiles of every level of a MipChain (b2r_mipchain_encode_tiles:
+    the level output stage of write_mipmap, maketexture.cpp:957-974, up to the
+    compressed tiles a file plugin stores)."""
+
+    def __init__(self, chain, tile=64, half=False, compression=True, zlevel=1,
+                 nthreads=0, first_level=0):
+        o = _TileOptions()
+        o.tile_width = o.tile_height = int(tile)
+        o.out_basetype = 10 if half else 11
+        o.compression = 1 if compression else 0
+        o.zlevel = int(zlevel)
+        o.nthreads = int(nthreads)
+        o.first_level = int(first_level)
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_mipchain_encode_tiles(chain._h, C.byref(o), C.byref(h), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        self._h = h
+        self.tile = int(tile)
+        self.half = bool(half)
+        self.compressed = bool(compression)
+        self.nchannels = chain.nchannels
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().b2r_tileset_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def nlevels(self):
+        return lib().b2r_tileset_nlevels(self._h)
+
+    def level_info(self, level):
+        v = [C.c_int() for _ in range(4)]
+        lib().b2r_tileset_level(self._h, level, *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)  # width, height, ntiles_x, ntiles_y
+
+    def tile_bytes(self, level, tx, ty):
+        p, n = C.c_void_p(), C.c_size_t()
+        if lib().b2r_tileset_tile(self._h, level, tx, ty, C.byref(p), C.byref(n)):
+            raise B2RError("no such tile")
+        return C.string_at(p.value, n.value)
+
+    def tile_pixels(self, level, tx, ty):
+        """The tile decoded back into a tile x tile x nchannels array."""
+        import zlib
+        b = self.tile_bytes(level, tx, ty)
+        if self.compressed:
+            b = zlib.decompress(b)
+        dt = np.float16 if self.half else np.float32
+        return np.frombuffer(b, dt).reshape(self.tile, self.tile, self.nchannels)
+
+    def stat(self, what):
+        k = {"total_ms": 0, "device_ms": 1, "deflate_ms": 2, "raw_bytes": 3,
+             "stored_bytes": 4}[what]
+        return lib().b2r_tileset_stat(self._h, k)
 
 
 class MipChainBanded:

@@ -18,6 +18,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 struct b2r_filter2d {
     b2r::Filter2D* f;
@@ -26,6 +27,20 @@ struct b2r_filter1d {
     b2r::Filter1D* f;
 };
 
+
+// device-resident MIP chain (b2r_mipchain_create*, b2r_api.cpp)
+struct b2r_mipchain {
+    int device = 0;
+    int nch    = 0;
+    struct Level {
+        int w, h;
+        void* px;
+        bool owned;
+    };
+    std::vector<Level> levels;
+    float kernel_ms = 0.0f;
+    int launches    = 0;
+};
 
 namespace b2r {
 namespace api {

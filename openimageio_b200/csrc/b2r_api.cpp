@@ -2289,18 +2289,6 @@ b2r_resample(const b2r_image* dst_in, const b2r_image* src_in, int interpolate,
 // =========================================================================
 // device-resident MIP chain (write_mipmap level loop, maketexture.cpp:823-986)
 // =========================================================================
-struct b2r_mipchain {
-    int device = 0;
-    int nch    = 0;
-    struct Level {
-        int w, h;
-        void* px;
-        bool owned;
-    };
-    std::vector<Level> levels;
-    float kernel_ms = 0.0f;
-    int launches    = 0;
-};
 
 extern "C" int
 b2r_mipchain_create(b2r_mipchain** out, const b2r_image* level0,

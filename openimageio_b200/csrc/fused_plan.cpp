@@ -462,6 +462,25 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
                 }
                 memcpy(&row[vsw - 1], &di, sizeof(di));
             }
+            // stage descriptors (slot vk of a stage's first row; stages are
+            // `rows` source rows from the band's start): bit j = exactly one
+            // destination row completes with row j of the stage, 0x100 = some
+            // row completes several (the kernel then decodes row by row)
+            const int rows    = stream_rows(P.w2);
+            const int padded  = (b.nrows + STREAM_ROWPAD - 1) / STREAM_ROWPAD * STREAM_ROWPAD;
+            for (int r0s = 0; r0s < padded; r0s += rows) {
+                int32_t desc = 0;
+                for (int j = 0; j < rows; ++j) {
+                    int32_t di;
+                    memcpy(&di, &P.vstream[(size_t(b.soff) + r0s + j) * vsw + vsw - 1], sizeof(di));
+                    const int ne = di & 0xff;
+                    if (ne == 1)
+                        desc |= 1 << j;
+                    else if (ne > 1)
+                        desc |= 0x100;
+                }
+                memcpy(&P.vstream[(size_t(b.soff) + r0s) * vsw + vk], &desc, sizeof(desc));
+            }
         }
     } else if (!build_v_gather(gy, first, vt, src_h, P)) {
         return false;

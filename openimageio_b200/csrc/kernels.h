@@ -449,6 +449,11 @@ launch_pixel_bytes_copy(void* dst, long long dst_xstride, long long dst_ystride,
                         const void* src, long long src_xstride, long long src_ystride,
                         int width, int height, int nbytes, void* stream);
 
+// tile rows [ty0, ty1) of a contiguous float level -> tiles (tile_kernel.cu)
+void
+launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int tile_h,
+                     int ty0, int ty1, int out_half, void* out, void* stream);
+
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)
 void

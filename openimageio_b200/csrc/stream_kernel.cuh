@@ -40,6 +40,8 @@
 
 #include <cuda.h>  // CUtensorMap
 
+#include <type_traits>
+
 namespace b2r {
 
 // ---- mbarrier / TMA wrappers (PTX) ---------------------------------------
@@ -352,7 +354,11 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
 //   vbuf    2 x BATCH x PITCH_B
 //   bars    2 x NST mbarriers
 template<int ST> struct StreamE2 {
-    template<int W2> static constexpr int of() { return (W2 == 2 && SrcTraits<ST>::es < 4) ? 2 : 1; }
+    // Measured (C2 half RGBA, C5 uint16 RGB): two groups per thread with half
+    // as many V warps is 5-6 % SLOWER than one group per thread -- the V pass is
+    // bound by latency per row, not by its instruction count -- so every type
+    // runs one group per thread; the E2 = 2 code stays for the record.
+    template<int W2> static constexpr int of() { return 1; }
 };
 template<int ST, int VK, int W2> struct StreamSmem {
     static constexpr int E2       = StreamE2<ST>::template of<W2>();
@@ -546,10 +552,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     } else
                         raw[j] = make_uint4(*reinterpret_cast<const unsigned*>(a), 0u, 0u, 0u);
                 }
-#pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
-                    // the row of the ring table (broadcast loads)
-                    float w[WROW];
+                // ring-table row j of the stage (broadcast loads)
+                auto load_w = [&](int j, float (&w)[WROW]) {
 #pragma unroll
                     for (int k = 0; k < WROW / 4; ++k) {
                         const float4 t = *reinterpret_cast<const float4*>(
@@ -559,42 +563,15 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                         w[4 * k + 2] = t.z;
                         w[4 * k + 3] = t.w;
                     }
-                    // bits 0-7: rows completing with this source row; 8-15:
-                    // slots whose weight merges clamped taps of both signs;
-                    // 16 / 17: the (single) completing row opens / closes a batch
-                    const int info = __float_as_int(w[WROW - 1]);
-                    float4 v[E2];
-                    stream_convert<ST, E2>(raw[j], v);
-                    bool bad = false;
-                    if (FP) {
-                        float q = 0.0f;
-#pragma unroll
-                        for (int h = 0; h < E2; ++h)
-                            q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
-                        bad = !(fabsf(q) <= 3.402823466e+38f);
-                    }
-                    if (FP && bad) {
-                        // Inf/NaN in this group: never let it meet a zero
-                        // weight; a weight that stands for clamped taps of
-                        // both signs turns it into NaN (w1*Inf + w2*Inf)
-                        if (shift)
-                            rotate();
+                };
+                // acc[k] (+)= w[k] * v, reading acc[k + 1] when the oldest row
+                // was parked after the previous source row
+                auto fma_row = [&](const float (&w)[WROW], const float4 (&v)[E2], bool shifted) {
+                    if (shifted) {
 #pragma unroll
                         for (int k = 0; k < VK; ++k) {
 #pragma unroll
                             for (int h = 0; h < E2; ++h) {
-                                if (w[k] != 0.0f)
-                                    fma4(acc[k][h], w[k], v[h]);
-                                if ((info >> (8 + k)) & 1)
-                                    fma4(acc[k][h], 0.0f, v[h]);
-                            }
-                        }
-                    } else if (shift) {
-#pragma unroll
-                        for (int k = 0; k < VK; ++k) {
-#pragma unroll
-                            for (int h = 0; h < E2; ++h) {
-                                // acc[k] = w[k] * v + acc[k + 1]
                                 const float4 c = (k + 1 < VK) ? acc[k + 1][h]
                                                               : make_float4(0.f, 0.f, 0.f, 0.f);
                                 const float2 ww = make_float2(w[k], w[k]);
@@ -612,6 +589,116 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                             for (int h = 0; h < E2; ++h)
                                 fma4(acc[k][h], w[k], v[h]);
                     }
+                };
+                // Inf/NaN in this thread's group: never let it meet a zero
+                // weight; a weight that stands for clamped taps of both signs
+                // turns it into NaN (w1*Inf + w2*Inf).  Rare, divergent.
+                auto slow_row = [&](const float (&w)[WROW], const float4 (&v)[E2], int info,
+                                    bool shifted) {
+                    if (shifted)
+                        rotate();
+#pragma unroll
+                    for (int k = 0; k < VK; ++k) {
+#pragma unroll
+                        for (int h = 0; h < E2; ++h) {
+                            if (w[k] != 0.0f)
+                                fma4(acc[k][h], w[k], v[h]);
+                            if ((info >> (8 + k)) & 1)
+                                fma4(acc[k][h], 0.0f, v[h]);
+                        }
+                    }
+                };
+                // Stage descriptor (slot VK of the stage's first table row): bits
+                // 0..ROWS-1 = exactly one destination row completes with row j;
+                // 0x100 = irregular stage (several rows complete at once).
+                // Regular stages of the wide geometry run straight-line code
+                // specialised on (shift at entry, completion mask): no per-row
+                // flag decoding, no shift / completion branches.  (Screening
+                // the whole stage for Inf/NaN up front instead of row by row
+                // was measured: it delays the first FMA of every stage and
+                // costs C0 9 %.)
+                int sdesc = 0x100;
+                if (W2 == 2)
+                    sdesc = __float_as_int(
+                        *reinterpret_cast<const float*>(sb + S::DATA_B + VK * 4));
+                const bool slow = (sdesc & 0x100) != 0;
+                if (!slow) {
+                    auto fast = [&](auto code) {
+                        constexpr int C = decltype(code)::value;
+#pragma unroll
+                        for (int j = 0; j < ROWS; ++j) {
+                            // shift state is static: at entry from C, then from the mask
+                            constexpr int dummy = 0;
+                            (void)dummy;
+                            const bool shifted = j == 0 ? ((C >> ROWS) & 1) != 0
+                                                        : ((C >> (j - 1)) & 1) != 0;
+                            float w[WROW];
+                            load_w(j, w);
+                            const int info = __float_as_int(w[WROW - 1]);
+                            float4 v[E2];
+                            stream_convert<ST, E2>(raw[j], v);
+                            bool bad = false;
+                            if (FP) {
+                                float q = 0.0f;
+#pragma unroll
+                                for (int h = 0; h < E2; ++h)
+                                    q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                                bad = !(fabsf(q) <= 3.402823466e+38f);
+                            }
+                            if (FP && bad)
+                                slow_row(w, v, info, shifted);
+                            else
+                                fma_row(w, v, shifted);
+                            if (FP)
+                                __syncwarp();
+                            if ((C >> j) & 1)
+                                park_oldest((info >> 16) & 1, (info >> 17) & 1);
+                        }
+                        shift = ((C >> (ROWS - 1)) & 1) != 0;
+                    };
+                    const int code = (sdesc & ((1 << ROWS) - 1)) | (shift ? (1 << ROWS) : 0);
+                    static_assert(ROWS <= 3 || W2 == 1, "16 specialisations cover three rows");
+                    switch (code) {
+                    case 0: fast(std::integral_constant<int, 0>{}); break;
+                    case 1: fast(std::integral_constant<int, 1>{}); break;
+                    case 2: fast(std::integral_constant<int, 2>{}); break;
+                    case 3: fast(std::integral_constant<int, 3>{}); break;
+                    case 4: fast(std::integral_constant<int, 4>{}); break;
+                    case 5: fast(std::integral_constant<int, 5>{}); break;
+                    case 6: fast(std::integral_constant<int, 6>{}); break;
+                    case 7: fast(std::integral_constant<int, 7>{}); break;
+                    case 8: fast(std::integral_constant<int, 8>{}); break;
+                    case 9: fast(std::integral_constant<int, 9>{}); break;
+                    case 10: fast(std::integral_constant<int, 10>{}); break;
+                    case 11: fast(std::integral_constant<int, 11>{}); break;
+                    case 12: fast(std::integral_constant<int, 12>{}); break;
+                    case 13: fast(std::integral_constant<int, 13>{}); break;
+                    case 14: fast(std::integral_constant<int, 14>{}); break;
+                    default: fast(std::integral_constant<int, 15>{}); break;
+                    }
+                } else {
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    float w[WROW];
+                    load_w(j, w);
+                    // bits 0-7: rows completing with this source row; 8-15:
+                    // slots whose weight merges clamped taps of both signs;
+                    // 16 / 17: the (single) completing row opens / closes a batch
+                    const int info = __float_as_int(w[WROW - 1]);
+                    float4 v[E2];
+                    stream_convert<ST, E2>(raw[j], v);
+                    bool bad = false;
+                    if (FP) {
+                        float q = 0.0f;
+#pragma unroll
+                        for (int h = 0; h < E2; ++h)
+                            q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                        bad = !(fabsf(q) <= 3.402823466e+38f);
+                    }
+                    if (FP && bad)
+                        slow_row(w, v, info, shift);
+                    else
+                        fma_row(w, v, shift);
                     if (FP)
                         __syncwarp();
                     // destination rows that complete with this source row
@@ -629,6 +716,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                             rotate();
                         }
                     }
+                }
                 }
                 // stage consumed: hand it back to the producer
                 __syncwarp();

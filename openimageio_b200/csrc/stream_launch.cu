@@ -110,8 +110,8 @@ launch_with_map(const FusedParams& p, int w2, const CUtensorMap& map, int sms, v
     }
     const long long items = (long long)p.nstrips * p.nbands * (p.nframes > 1 ? p.nframes : 1);
     dim3 grid((unsigned)std::min<long long>(items, std::max(1, sms)), 1, 1);
-    // 1- and 2-byte sources of the wide geometry: two groups per V thread
-    const int e2      = (w2 == 2 && basetype_size(p.srctype) < 4) ? 2 : 1;
+    // four-element groups per V thread
+    const int e2      = 1;  // see StreamE2 in stream_kernel.cuh
     const int threads = STREAM_PTHREADS + STREAM_VTHREADS * w2 / e2 + STREAM_HTHREADS;
     launch_pdl(k, grid, dim3(threads), (size_t)smem, (cudaStream_t)stream, map, p);
     return 0;

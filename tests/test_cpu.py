@@ -436,3 +436,59 @@ def test_oracle_fillholes_golden(oracle):
     G = np.load(os.path.join(GOLD, "fillholes_ref.npz"))
     out = oracle.fillholes_pushpull(G["hole"], 3)
     assert np.array_equal(out, G["tahoe_filled"])
+
+
+def _oiio_hash(a, extra="", blocksize=0):
+    """computePixelHashSHA1 restated with hashlib (the oracle for the product's
+    own SHA-1): imagebufalgo_compare.cpp:817-892."""
+    import hashlib
+    h = a.shape[0]
+    if blocksize <= 0 or blocksize >= h:
+        s = hashlib.sha1(np.ascontiguousarray(a).tobytes())
+        s.update(extra.encode())
+        return s.hexdigest().upper()
+    s = hashlib.sha1()
+    for y in range(0, h, blocksize):
+        s.update(hashlib.sha1(np.ascontiguousarray(a[y:y + blocksize]).tobytes())
+                 .hexdigest().upper().encode())
+    s.update(extra.encode())
+    return s.hexdigest().upper()
+
+
+def test_pixel_hash_sha1_reference_goldens(oiio):
+    """The two SHA-1 values the reference's own test suite holds for
+    testsuite/common/grid.tif (testsuite/maketx/ref/out.txt:4, 20): the plain
+    pixel hash of the uint8 image (`SHA-1:` of oiiotool --info) and maketx's
+    oiio:SHA-1 -- 256-row blocks of the float32 top level with the filter name
+    "box " appended (maketexture.cpp:1909-1934).  Host images: no GPU needed."""
+    X = np.load(os.path.join(GOLD, "xform_ref.npz"))
+    grid = X["grid"]
+    assert grid.shape == (1000, 1000, 4) and grid.dtype == np.uint8
+    IBA = oiio.ImageBufAlgo
+    assert IBA.computePixelHashSHA1(grid) == "97D6548FF9E9BFD21424B773B1D84FACDF0C1797"
+    top = grid.astype(np.float32) * np.float32(1.0 / 255.0)   # convert_type<uint8,float>
+    assert (IBA.computePixelHashSHA1(top, "box ", blocksize=256)
+            == "9B24D4CC05313A43973AC384718D81D19183B691")
+    # and the hashlib restatement agrees with both
+    assert _oiio_hash(grid) == "97D6548FF9E9BFD21424B773B1D84FACDF0C1797"
+    assert _oiio_hash(top, "box ", 256) == "9B24D4CC05313A43973AC384718D81D19183B691"
+
+
+@pytest.mark.parametrize("shape,dt,blocksize", [((37, 53, 3), np.float32, 0),
+                                                ((700, 129, 4), np.uint16, 256),
+                                                ((256, 64, 1), np.uint8, 256),
+                                                ((513, 64, 2), np.float16, 256),
+                                                ((1, 1, 1), np.uint8, 0),
+                                                ((1000, 31, 3), np.float32, 7)])
+def test_pixel_hash_sha1_matches_hashlib(oiio, shape, dt, blocksize):
+    a = synth.image(shape[1], shape[0], shape[2], dt, seed=4242)
+    for extra in ("", "lanczos3 sharpen_A=0.5 highlightcomp=1 "):
+        for nt in (1, 5):
+            got = oiio.ImageBufAlgo.computePixelHashSHA1(a, extra, blocksize=blocksize,
+                                                         nthreads=nt)
+            assert got == _oiio_hash(a, extra, blocksize)
+    # a region of interest hashes only its columns / rows
+    if shape[0] > 20 and shape[1] > 20:
+        roi = oiio.ROI(3, shape[1] - 5, 2, shape[0] - 7, 0, 1, 0, shape[2])
+        got = oiio.ImageBufAlgo.computePixelHashSHA1(a, "x", roi=roi, blocksize=blocksize)
+        assert got == _oiio_hash(a[2:shape[0] - 7, 3:shape[1] - 5], "x", blocksize)

@@ -281,3 +281,29 @@ def test_banded_chain_equals_single_device_chain(oiio, filt, shape, nbands):
         assert np.array_equal(a, b), "level %d differs (max %g)" % (lv, np.abs(a - b).max())
     if nbands > 1 and h // nbands >= 128:
         assert many.ms("halo_bytes") > 0
+
+
+# ---- tiled, deflated level output (b2r_mipchain_encode_tiles) --------------
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("shape,tile", [((300, 500), 64), ((1024, 1024), 64), ((97, 130), 32)])
+def test_encode_tiles_roundtrip(oiio, shape, tile, half):
+    """Every level, re-laid into tiles on the device, downloaded and deflated
+    on the host, inflates back to exactly the level's pixels (float) or their
+    half conversion; edge tiles are zero padded."""
+    h, w = shape
+    src = synth.image(w, h, 3, np.float32, seed=900 + tile)
+    ch = oiio.MipChain(src, filtername="lanczos3")
+    ts = oiio.TileSet(ch, tile=tile, half=half, zlevel=1, nthreads=4)
+    assert ts.nlevels == ch.nlevels
+    for lv in range(ch.nlevels):
+        px = ch.download(lv)
+        lw, lh, ntx, nty = ts.level_info(lv)
+        assert (lh, lw) == px.shape[:2]
+        assert ntx == -(-lw // tile) and nty == -(-lh // tile)
+        ref = np.zeros((nty * tile, ntx * tile, 3), np.float16 if half else np.float32)
+        ref[:lh, :lw] = px.astype(np.float16) if half else px
+        for ty in range(nty):
+            for tx in range(ntx):
+                t = ts.tile_pixels(lv, tx, ty)
+                assert np.array_equal(t, ref[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile])
+    assert ts.stat("stored_bytes") > 0 and ts.stat("raw_bytes") >= ts.stat("stored_bytes") * 0.5
