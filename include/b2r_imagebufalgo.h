@@ -20,7 +20,10 @@
 #include "b2r.h"
 
 #include <algorithm>
+#include <cctype>
 #include <climits>
+#include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <initializer_list>
 #include <string>
@@ -824,6 +827,346 @@ fillholes_pushpull(ImageBuf& dst, const ImageBuf& src, ROI roi = {}, int /*nthre
     int rc = b2r_fillholes_pushpull(&d, &s, src.spec().alpha_channel, nullptr, nullptr, err,
                                     sizeof(err));
     return detail::report(dst, rc, err);
+}
+
+/// ImageBufAlgo::computePixelHashSHA1(src, extrainfo, roi, blocksize, nthreads)
+/// -- imagebufalgo_compare.cpp:856-892 (upper-case hex; blocks of `blocksize`
+/// rows hashed separately, their digests hashed together, extrainfo last).
+inline std::string
+computePixelHashSHA1(const ImageBuf& src, const std::string& extrainfo = "", ROI roi = {},
+                     int blocksize = 0, int nthreads = 0)
+{
+    if (!src.initialized())
+        return std::string();
+    b2r_image s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    char digest[41] = "", err[512] = "";
+    if (b2r_pixel_hash_sha1(&s, extrainfo.c_str(), roi.defined() ? &r : nullptr, blocksize,
+                            nthreads, digest, err, sizeof(err))) {
+        src.error(err);
+        return std::string();
+    }
+    return std::string(digest);
+}
+
+/// A sequence of frames of one shape through one call (b2r_resize_batch: a
+/// single persistent launch when the frames live on one device).  The
+/// reference has no such entry: it is one ImageBufAlgo::resize per frame.
+inline bool
+resize_batch(std::vector<ImageBuf>& dst, const std::vector<ImageBuf>& src,
+             const KWArgs& options = {}, ROI roi = {}, int /*nthreads*/ = 0)
+{
+    if (dst.size() != src.size() || dst.empty())
+        return dst.size() == src.size();
+    std::vector<b2r_image> D, S;
+    ROI r0 = roi;
+    for (size_t i = 0; i < dst.size(); ++i) {
+        ROI r = roi;
+        if (!detail::prep(r, dst[i], src[i]))
+            return false;
+        if (i == 0)
+            r0 = r;
+        D.push_back(dst[i].c_image());
+        S.push_back(src[i].c_image());
+    }
+    b2r_roi r = detail::c_roi(r0);
+    char err[512] = "";
+    int rc = b2r_resize_batch(D.data(), S.data(), (int)D.size(),
+                              options.get_string("filtername").c_str(),
+                              options.get_float("filterwidth"), &r, nullptr, nullptr, err,
+                              sizeof(err));
+    return detail::report(dst[0], rc, err);
+}
+
+}  // namespace ImageBufAlgo
+
+/// The compute step of `oiiotool --resize[:from=..][:to=..][:filter=..]
+/// [:highlightcomp=1][:edgeclamp=1] WxH` (OpResize, src/oiiotool/oiiotool.cpp:
+/// 4581-4735): a separable resize of the display window to width x height
+/// (the data window scales with it, :4622-4642), or -- when from / to differ
+/// from the full windows -- a warp by the from -> to matrix (:4652-4656,
+/// 4684-4720).  from / to: {x, y, w, h}; pass nullptr for the full windows.
+inline ImageBuf
+oiiotool_resize(const ImageBuf& src, int width, int height, const std::string& filtername = "",
+                const float* from = nullptr, const float* to = nullptr,
+                bool highlightcomp = false, bool edgeclamp = false)
+{
+    ImageBuf dst;
+    if (!src.initialized()) {
+        dst.error("Uninitialized input image");
+        return dst;
+    }
+    const ImageSpec& A = src.spec();
+    ImageSpec ns       = A;
+    ns.full_width      = width;
+    ns.full_height     = height;
+    ns.x = ns.full_x, ns.y = ns.full_y, ns.width = width, ns.height = height;
+    const float f0[4] = { float(A.full_x), float(A.full_y), float(A.full_width),
+                          float(A.full_height) };
+    const float t0[4] = { float(ns.full_x), float(ns.full_y), float(width), float(height) };
+    const float* f = from ? from : f0;
+    const float* t = to ? to : t0;
+    bool do_warp   = false;
+    for (int i = 0; i < 4; ++i)
+        do_warp = do_warp || f[i] != f0[i] || t[i] != t0[i];
+    if (!do_warp) {
+        const float wr = float(width) / float(A.full_width);
+        const float hr = float(height) / float(A.full_height);
+        ns.x      = ns.full_x + int(std::floor(float(A.x - A.full_x) * wr));
+        ns.y      = ns.full_y + int(std::floor(float(A.y - A.full_y) * hr));
+        ns.width  = int(std::ceil(float(A.width) * wr));
+        ns.height = int(std::ceil(float(A.height) * hr));
+    }
+    dst.reset(ns);
+    if (!do_warp) {
+        b2r_image d = dst.c_image(), s = src.c_image();
+        b2r_roi r   = ImageBufAlgo::detail::c_roi(dst.roi());
+        b2r_options o;
+        std::memset(&o, 0, sizeof(o));
+        o.highlightcomp  = highlightcomp ? 1 : 0;
+        o.alpha_channel1 = A.alpha_channel + 1;
+        o.z_channel1     = A.z_channel + 1;
+        char err[512]    = "";
+        int rc = b2r_resize(&d, &s, filtername.c_str(), 0.0f, &r, &o, nullptr, err, sizeof(err));
+        ImageBufAlgo::detail::report(dst, rc, err);
+        return dst;
+    }
+    float M[9];
+    b2r_fromto_matrix(f[0], f[1], f[2], f[3], t[0], t[1], t[2], t[3], M);
+    ImageBuf tmp;
+    const ImageBuf* s = &src;
+    if (highlightcomp) {
+        if (!ImageBufAlgo::rangecompress(tmp, src)) {
+            dst.error(tmp.geterror());
+            return dst;
+        }
+        s = &tmp;
+    }
+    bool ok = ImageBufAlgo::warp(dst, *s, M,
+                                 { { "filtername", filtername },
+                                   { "edgeclamp", int(edgeclamp) } });
+    if (ok && highlightcomp)
+        ImageBufAlgo::rangeexpand(dst, dst);
+    return dst;
+}
+
+/// What make_texture computes for a plain texture: the MIP levels (float32 host
+/// images, levels[0] = the top level after fixnan / power-of-two resize) and
+/// the metadata maketx derives from the pixels.
+struct Texture {
+    std::vector<ImageBuf> levels;
+    std::string format = "float";      // the pixel type the file would be written as
+    int pixels_fixed   = 0;            // --fixnan
+    std::vector<float> average_color;  // "oiio:AverageColor"
+    std::vector<float> constant_color; // "oiio:ConstantColor" when min == max
+    bool monochrome = false;
+    std::string sha1;                  // "oiio:SHA-1" (maketx:hash)
+    std::string error;
+    bool ok() const { return error.empty(); }
+};
+
+namespace ImageBufAlgo {
+
+enum MakeTextureMode { MakeTxTexture = 0 };
+
+/// ImageBufAlgo::make_texture(mode, input, outputfilename, configspec) for
+/// MakeTxTexture -- make_texture_impl, src/libOpenImageIO/maketexture.cpp:
+/// 1011-2040 -- returning the levels instead of writing a file.  config keys
+/// (the maketx attributes that select pixel work): "maketx:filtername" ("box";
+/// "post-" / "unsharp-<f>" prefixes, :759-768), "maketx:highlightcomp",
+/// "maketx:sharpen", "maketx:fixnan" ("none" | "black" | "box3"),
+/// "maketx:checknan", "maketx:resize" (round up to a power of two),
+/// "maketx:nomipmap", "maketx:hash" (default 1), "format" (output type: levels
+/// written as half are clamped to +-HALF_MAX, :709-714, 943-945).
+inline Texture
+make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config = {})
+{
+    Texture T;
+    if (mode != MakeTxTexture) {
+        T.error = "make_texture: only MakeTxTexture is on the B200 resampling path";
+        return T;
+    }
+    if (!input.initialized()) {
+        T.error = "make_texture: uninitialized input image";
+        return T;
+    }
+    const ImageSpec& sspec = input.spec();
+    const int bt           = sspec.format.basetype;
+    const bool isfp        = bt == TypeDesc::HALF || bt == TypeDesc::FLOAT;
+    // --fixnan / --checknan (:1666-1705)
+    std::string fixnan = config.get_string("maketx:fixnan", "none");
+    if (fixnan.empty())
+        fixnan = "none";
+    if (fixnan != "none" && fixnan != "black" && fixnan != "box3") {
+        T.error = "Unknown fixnan mode \"" + fixnan + "\"";
+        return T;
+    }
+    ImageBuf fixed;
+    const ImageBuf* src = &input;
+    if (fixnan != "none" && isfp) {
+        if (!fixNonFinite(fixed, input, fixnan == "black" ? NONFINITE_BLACK : NONFINITE_BOX3,
+                          &T.pixels_fixed)) {
+            T.error = "Error fixing nans/infs.";
+            return T;
+        }
+        src = &fixed;
+    }
+    if (config.get_int("maketx:checknan") && isfp) {
+        ImageBuf probe;
+        int bad = 0;
+        fixNonFinite(probe, *src, NONFINITE_NONE, &bad);
+        if (bad) {
+            T.error = "maketx ERROR: Nan/Inf at " + std::to_string(bad) + " pixels";
+            return T;
+        }
+    }
+    // pixel statistics (:1396-1430): average colour, constant colour, monochrome
+    {
+        PixelStats st = computePixelStats(*src, {}, 0, &T.monochrome);
+        if (st.min.empty()) {
+            T.error = src->geterror();
+            return T;
+        }
+        T.average_color = st.avg;
+        if (st.min == st.max)
+            T.constant_color = st.min;
+    }
+    std::string filtername = config.get_string("maketx:filtername", "box");
+    if (filtername.empty())
+        filtername = "box";
+    auto lower_starts = [](const std::string& s, const char* p) {
+        size_t n = std::strlen(p);
+        if (s.size() < n)
+            return false;
+        for (size_t i = 0; i < n; ++i)
+            if (std::tolower((unsigned char)s[i]) != p[i])
+                return false;
+        return true;
+    };
+    // the float top level, origin at 0 (maketx:forcefloat; :1791-1877)
+    int dw = sspec.width, dh = sspec.height;
+    if (config.get_int("maketx:resize")) {
+        auto ceil2 = [](int x) {
+            int p = 1;
+            while (p < x)
+                p <<= 1;
+            return p;
+        };
+        dw = ceil2(dw), dh = ceil2(dh);
+    }
+    ImageSpec s0 = sspec;
+    s0.x = s0.y = s0.full_x = s0.full_y = 0;
+    s0.full_width = s0.width, s0.full_height = s0.height;
+    ImageBuf src0(s0, const_cast<void*>(src->localpixels()), src->c_image().memspace,
+                  src->c_image().device);
+    ImageSpec fspec = s0;
+    fspec.format    = TypeDesc::FLOAT;
+    ImageBuf srcf;
+    if (bt != TypeDesc::FLOAT) {
+        srcf.reset(fspec);
+        if (!resample(srcf, src0, false)) {  // copy_pixels == nearest resample at 1:1
+            T.error = srcf.geterror();
+            return T;
+        }
+    }
+    const ImageBuf& F = (bt != TypeDesc::FLOAT) ? srcf : src0;
+    ImageBuf top;
+    if (dw == s0.width && dh == s0.height) {
+        top.copy(F);
+        if (!top.initialized()) {  // device-resident input: bring it down through a 1:1 resample
+            top.reset(fspec);
+            if (!resample(top, F, false)) {
+                T.error = top.geterror();
+                return T;
+            }
+        }
+    } else {
+        ImageSpec ts = fspec;
+        ts.width = ts.full_width = dw;
+        ts.height = ts.full_height = dh;
+        top.reset(ts);
+        std::string rf = lower_starts(filtername, "unsharp-") ? "lanczos3" : filtername;
+        char err[512]  = "";
+        b2r_image d = top.c_image(), s = F.c_image();
+        int rc;
+        if (rf == "box" || rf == "triangle")  // resize_block (:141-334, 1858-1864)
+            rc = b2r_mip_level(&d, &s, "box", nullptr, nullptr, err, sizeof(err));
+        else
+            rc = b2r_resize(&d, &s, rf.c_str(), 0.0f, nullptr, nullptr, nullptr, err,
+                            sizeof(err));
+        if (rc) {
+            T.error = err;
+            return T;
+        }
+    }
+    const char* names[12] = { "", "", "uint8", "", "uint16", "", "", "", "", "", "half", "float" };
+    T.format = config.get_string("format", names[bt]);
+    const bool clamp_half = T.format == "half";
+    float sharpen         = config.get_float("maketx:sharpen");
+    bool sharpen_first    = true;
+    std::string sharpenfilt = "gaussian", fn = filtername;
+    if (lower_starts(fn, "post-")) {
+        sharpen_first = false;
+        fn            = fn.substr(5);
+    }
+    if (lower_starts(fn, "unsharp-")) {
+        sharpenfilt = fn.substr(8);
+        fn          = "lanczos3";
+    }
+    // oiio:SHA-1 of the top level (:1909-1934): host threads, 256-row blocks
+    if (config.get_int("maketx:hash", 1)) {
+        std::string extra = filtername + " ";
+        if (sharpen != 0.0f) {
+            char b[64];
+            std::snprintf(b, sizeof(b), "sharpen_A=%g ", sharpen);
+            extra += b;
+        }
+        if (config.get_int("maketx:highlightcomp"))
+            extra += "highlightcomp=1 ";
+        if (config.get_int("maketx:keepaspect"))
+            extra += "keepaspect=1 ";
+        T.sha1 = computePixelHashSHA1(top, extra, {}, 256, 0);
+    }
+    T.levels.push_back(std::move(top));
+    if (config.get_int("maketx:nomipmap"))
+        return T;
+    b2r_mip_options mo;
+    std::memset(&mo, 0, sizeof(mo));
+    mo.filtername    = fn.c_str();
+    mo.clamp_half    = clamp_half ? 1 : 0;
+    mo.alpha_channel = sspec.alpha_channel;
+    mo.sharpen       = sharpen;
+    mo.sharpen_first = sharpen_first ? 1 : 0;
+    mo.sharpenfilt   = sharpenfilt.c_str();
+    b2r_options o;
+    std::memset(&o, 0, sizeof(o));
+    o.highlightcomp  = config.get_int("maketx:highlightcomp") ? 1 : 0;
+    o.alpha_channel1 = sspec.alpha_channel + 1;
+    o.z_channel1     = sspec.z_channel + 1;
+    b2r_mipchain* chain = nullptr;
+    char err[512]       = "";
+    b2r_image l0        = T.levels[0].c_image();
+    if (b2r_mipchain_create_ex(&chain, &l0, &mo, &o, err, sizeof(err))) {
+        T.error = err;
+        return T;
+    }
+    const int n = b2r_mipchain_nlevels(chain);
+    for (int lv = 1; lv < n; ++lv) {
+        int w = 0, h = 0;
+        b2r_mipchain_level(chain, lv, &w, &h, nullptr);
+        ImageSpec ls = T.levels[0].spec();
+        ls.width = ls.full_width = w;
+        ls.height = ls.full_height = h;
+        ImageBuf L(ls);
+        b2r_image li = L.c_image();
+        if (b2r_mipchain_download(chain, lv, &li, err, sizeof(err))) {
+            T.error = err;
+            break;
+        }
+        T.levels.push_back(std::move(L));
+    }
+    b2r_mipchain_destroy(chain);
+    return T;
 }
 
 }  // namespace ImageBufAlgo

@@ -398,6 +398,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     constexpr int NR    = S::NR;
     constexpr int NSYNC = G::NVT + STREAM_HTHREADS;  // threads on the V <-> H barriers
     constexpr bool FP   = (ST == ST_FLOAT || ST == ST_HALF);
+    // stage-specialised V pass (see the V warps below)
+    constexpr bool SPEC = W2 == 2 && (!FP || VK <= 4);
     static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
 
     extern __shared__ __align__(1024) unsigned char stream_smem[];
@@ -613,16 +615,33 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 // 0x100 = irregular stage (several rows complete at once).
                 // Regular stages of the wide geometry run straight-line code
                 // specialised on (shift at entry, completion mask): no per-row
-                // flag decoding, no shift / completion branches.  (Screening
-                // the whole stage for Inf/NaN up front instead of row by row
-                // was measured: it delays the first FMA of every stage and
-                // costs C0 9 %.)
+                // flag decoding, no shift / completion branches; float / half
+                // stages are screened for Inf/NaN as a whole first.  Measured:
+                // it pays for integer sources and for rings of <= 4 rows (C2
+                // 96.7 -> 85.8 us, C5 36.0 -> 32.2 us); float / half rings of
+                // 6-8 rows lose (C0 115.7 -> 126 us, the screening delays the
+                // first FMA of a stage) and keep the row-by-row path (SPEC).
                 int sdesc = 0x100;
-                if (W2 == 2)
+                if (SPEC)
                     sdesc = __float_as_int(
                         *reinterpret_cast<const float*>(sb + S::DATA_B + VK * 4));
-                const bool slow = (sdesc & 0x100) != 0;
-                if (!slow) {
+                bool slow = (sdesc & 0x100) != 0;
+                if (FP && SPEC) {
+                    // any Inf/NaN in this warp's rows of the stage -> the per-row
+                    // path with its zero-weight handling; otherwise the stage is
+                    // straight-line code with no per-row branches at all
+                    float q = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < ROWS; ++j) {
+                        float4 v[E2];
+                        stream_convert<ST, E2>(raw[j], v);
+#pragma unroll
+                        for (int h = 0; h < E2; ++h)
+                            q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                    }
+                    slow = slow || __any_sync(0xffffffffu, !(fabsf(q) <= 3.402823466e+38f));
+                }
+                if (SPEC && !slow) {
                     auto fast = [&](auto code) {
                         constexpr int C = decltype(code)::value;
 #pragma unroll
@@ -634,25 +653,13 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                                                         : ((C >> (j - 1)) & 1) != 0;
                             float w[WROW];
                             load_w(j, w);
-                            const int info = __float_as_int(w[WROW - 1]);
                             float4 v[E2];
                             stream_convert<ST, E2>(raw[j], v);
-                            bool bad = false;
-                            if (FP) {
-                                float q = 0.0f;
-#pragma unroll
-                                for (int h = 0; h < E2; ++h)
-                                    q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
-                                bad = !(fabsf(q) <= 3.402823466e+38f);
-                            }
-                            if (FP && bad)
-                                slow_row(w, v, info, shifted);
-                            else
-                                fma_row(w, v, shifted);
-                            if (FP)
-                                __syncwarp();
-                            if ((C >> j) & 1)
+                            fma_row(w, v, shifted);
+                            if ((C >> j) & 1) {
+                                const int info = __float_as_int(w[WROW - 1]);
                                 park_oldest((info >> 16) & 1, (info >> 17) & 1);
+                            }
                         }
                         shift = ((C >> (ROWS - 1)) & 1) != 0;
                     };

@@ -42,11 +42,70 @@ run_errors()
     return 0;
 }
 
+// iba_cli maketx in.raw w h nch basetype filter hicomp(0|1) out.raw
+//   ImageBufAlgo::make_texture: every level appended to out.raw (float32),
+//   "levels=N sha1=... avg0=..." on stdout
+static int
+run_maketx(char** argv)
+{
+    int w = atoi(argv[3]), h = atoi(argv[4]), c = atoi(argv[5]), bt = atoi(argv[6]);
+    ImageSpec sspec(w, h, c, TypeDesc(bt));
+    std::vector<unsigned char> px(size_t(w) * h * c * sspec.format.size());
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(px.data(), 1, px.size(), f) != px.size())
+        return 3;
+    fclose(f);
+    ImageBuf src(sspec, px.data(), B2R_MEM_HOST);
+    Texture T = ImageBufAlgo::make_texture(ImageBufAlgo::MakeTxTexture, src,
+                                           { { "maketx:filtername", argv[7] },
+                                             { "maketx:highlightcomp", atoi(argv[8]) } });
+    if (!T.ok()) {
+        fprintf(stderr, "%s\n", T.error.c_str());
+        return 4;
+    }
+    f = fopen(argv[9], "wb");
+    for (auto& L : T.levels)
+        fwrite(L.localpixels(), 4, size_t(L.spec().width) * L.spec().height * c, f);
+    fclose(f);
+    printf("levels=%d sha1=%s avg0=%.9g\n", int(T.levels.size()), T.sha1.c_str(),
+           T.average_color[0]);
+    return 0;
+}
+
+// iba_cli otresize in.raw w h nch basetype dw dh filter hicomp out.raw
+//   oiiotool --resize[:highlightcomp=1] WxH
+static int
+run_otresize(char** argv)
+{
+    int w = atoi(argv[3]), h = atoi(argv[4]), c = atoi(argv[5]), bt = atoi(argv[6]);
+    int dw = atoi(argv[7]), dh = atoi(argv[8]);
+    ImageSpec sspec(w, h, c, TypeDesc(bt));
+    std::vector<unsigned char> px(size_t(w) * h * c * sspec.format.size());
+    FILE* f = fopen(argv[2], "rb");
+    if (!f || fread(px.data(), 1, px.size(), f) != px.size())
+        return 3;
+    fclose(f);
+    ImageBuf src(sspec, px.data(), B2R_MEM_HOST);
+    ImageBuf dst = oiiotool_resize(src, dw, dh, argv[9], nullptr, nullptr, atoi(argv[10]) != 0);
+    if (dst.has_error()) {
+        fprintf(stderr, "%s\n", dst.geterror().c_str());
+        return 4;
+    }
+    f = fopen(argv[11], "wb");
+    fwrite(dst.localpixels(), sspec.format.size(), size_t(dw) * dh * c, f);
+    fclose(f);
+    return 0;
+}
+
 int
 main(int argc, char** argv)
 {
     if (argc >= 2 && std::string(argv[1]) == "errors")
         return run_errors();
+    if (argc == 10 && std::string(argv[1]) == "maketx")
+        return run_maketx(argv);
+    if (argc == 12 && std::string(argv[1]) == "otresize")
+        return run_otresize(argv);
     const bool hicomp = argc >= 2 && std::string(argv[1]) == "hicomp";
     const bool rotate = argc >= 2 && std::string(argv[1]) == "rotate";
     const bool fitx   = argc >= 2 && std::string(argv[1]) == "fitexact";

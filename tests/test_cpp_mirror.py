@@ -117,3 +117,49 @@ def test_cpp_widened_surface(iba_cli, oracle, tmp_path):
     st = oracle.pixel_stats(ref)
     assert "fixed=2" in p.stderr and "finite0=%d" % st[0]["finitecount"] in p.stderr
     assert "mono=0" in p.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("filt,hicomp", [("box", 0), ("lanczos3", 0), ("lanczos3", 1)])
+def test_cpp_make_texture(iba_cli, oracle, tmp_path, filt, hicomp):
+    """ImageBufAlgo::make_texture of the C++ mirror: the levels against the
+    oracle's write_mipmap loop, oiio:SHA-1 against a hashlib restatement of
+    computePixelHashSHA1 (256-row blocks + "<filter> [highlightcomp=1 ]")."""
+    import hashlib
+    src = synth.image(300, 520, 4, np.float32, seed=93)
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    src.tofile(fin)
+    out = subprocess.check_output([iba_cli, "maketx", fin, "300", "520", "4", "11", filt,
+                                   str(hicomp), fout], text=True)
+    kv = dict(t.split("=") for t in out.split())
+    levels = [src] + oracle.mip_chain(src, filt, highlightcomp=bool(hicomp), alpha_channel=3)
+    assert int(kv["levels"]) == len(levels)
+    got = np.fromfile(fout, np.float32)
+    off = 0
+    for lv, ref in enumerate(levels):
+        n = ref.size
+        g = got[off:off + n].reshape(ref.shape)
+        off += n
+        if filt == "box" or lv == 0:
+            assert np.array_equal(g, ref), lv
+        else:
+            assert np.abs(g - ref).max() <= (5e-5 if hicomp else 1e-5) * max(1, lv), lv
+    s = hashlib.sha1()
+    for y in range(0, 520, 256):
+        s.update(hashlib.sha1(src[y:y + 256].tobytes()).hexdigest().upper().encode())
+    s.update((filt + " " + ("highlightcomp=1 " if hicomp else "")).encode())
+    assert kv["sha1"] == s.hexdigest().upper()
+    assert abs(float(kv["avg0"]) - float(src[..., 0].astype(np.float64).mean())) < 1e-6
+
+
+@pytest.mark.gpu
+def test_cpp_oiiotool_resize(iba_cli, oracle, tmp_path):
+    src = synth.image(180, 120, 3, np.float32, seed=94)
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    src.tofile(fin)
+    subprocess.check_call([iba_cli, "otresize", fin, "180", "120", "3", "11", "90", "60",
+                           "lanczos3", "0", fout])
+    got = np.fromfile(fout, np.float32).reshape(60, 90, 3)
+    ref = np.zeros_like(got)
+    oracle.resize(oracle.Img(ref), oracle.Img(src), "lanczos3")
+    assert np.abs(got - ref).max() <= 1e-5
