@@ -95,6 +95,10 @@ struct DevicePlan {
     }
 };
 
+// frames of the batch being planned (b2r_resize_batch): a small frame alone
+// cannot fill the SMs with wide strips, a batch of them can
+thread_local int g_batch_frames = 1;
+
 std::mutex g_plan_mutex;
 std::list<std::shared_ptr<DevicePlan>> g_plans;  // most recent first
 // above the band count of the pipelined host path (<= 64 bands, one plan each)
@@ -187,7 +191,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     key.nch   = nch;
     // source rows TMA can fetch (16-byte aligned base and pitch) get the stream
     // kernel's strip geometry: part of the key
-    key.st    = src.basetype | (tma_ok ? 0x100 : 0);
+    key.st    = src.basetype | (tma_ok ? 0x100 : 0) | (g_batch_frames > 1 ? 0x200 : 0);
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
@@ -239,7 +243,9 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
                                      e0a, 2)
                           && plan->fp.w2 == 2 && !plan->fp.expand && plan->fp.vk > 0
                           && stream_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht, 2)
-                          && (int)(plan->fp.strips.size() * plan->fp.bands.size()) >= sms;
+                          && (long long)plan->fp.strips.size() * (long long)plan->fp.bands.size()
+                                     * g_batch_frames
+                                 >= sms;
         }
         ok = ok
              && (stream_plan
@@ -385,9 +391,16 @@ struct BatchCapture {
 };
 thread_local BatchCapture* g_capture = nullptr;
 
+// private return code of resize_impl: "highlight compensation was requested
+// fused (options.reserved[3]) but this call does not end in the stream kernel
+// with float pixels on both sides" -- nothing has been launched
+constexpr int HC_NOT_FUSED = 1000;
+
 // options.reserved[] is private to the library:
 //   [0] == 1  build + upload the tables only, no launch (MIP chain pass 1)
 //   [1] == 1  sub-call of the pipelined host path: never time, never sync
+//   [3] == 1  fuse highlight compensation into the stream kernel or return
+//             HC_NOT_FUSED before anything is launched
 int
 resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             const Filter2D& filter, const b2r_roi* roi_in,
@@ -451,6 +464,12 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
     const int path      = opt ? opt->path : B2R_PATH_AUTO;
 
+    const bool want_hc = opt && opt->reserved[3] == 1;
+    if (want_hc
+        && !(src.basetype == B2R_FLOAT && dst.basetype == B2R_FLOAT && smem == B2R_MEM_DEVICE
+             && dmem == B2R_MEM_DEVICE && nch <= 4 && src.nchannels == nch && filter.separable()
+             && path != B2R_PATH_EXACT))
+        return HC_NOT_FUSED;
     // (dst,src) pairs outside OIIO_DISPATCH_COMMON_TYPES2's ten native ones
     // are computed through a float temporary and converted back
     // (imagebufalgo_util.h:463-478, 540-546) -- here on the device: float
@@ -516,6 +535,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     // takes -- and the thin frame around it, which stays with the exact kernel.
     if (smem == B2R_MEM_DEVICE && dmem == B2R_MEM_DEVICE && filter.separable()
         && path == B2R_PATH_AUTO && !(opt && (opt->reserved[0] || opt->reserved[2]))
+        && !want_hc
         && (src.x < src.full_x || src.y < src.full_y
             || src.x + src.width > src.full_x + src.full_width
             || src.y + src.height > src.full_y + src.full_height)) {
@@ -724,6 +744,10 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         return rc;
     if (opt && opt->reserved[0] == 1)
         return B2R_OK;  // private: build + upload the tables only (MIP chain)
+    if (want_hc
+        && !(plan->fused && !plan->fp.expand && plan->fp.vk > 0 && plan->fp.ht > 0
+             && plan->fp.ht <= 16 && src_contig && dst.xstride == (int64_t)nch * des))
+        return HC_NOT_FUSED;
 
     // ---- stage host images ------------------------------------------------
     void* dsrc       = src.pixels;
@@ -937,6 +961,14 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                 = (const unsigned char*)dsrc + (long long)trow0 * srcd.ystride;
             fp.tma_row0        = trow0;
             fp.check_nonfinite = 0;
+            if (want_hc) {
+                fp.hicomp  = 1;
+                fp.hc_skip = 0;
+                if (opt->alpha_channel1 > 0)
+                    fp.hc_skip |= 1 << (opt->alpha_channel1 - 1);
+                if (opt->z_channel1 > 0)
+                    fp.hc_skip |= 1 << (opt->z_channel1 - 1);
+            }
             if (g_capture && g_capture->want && !temp && !dst_staged
                 && !(opt && (opt->reserved[1] || opt->reserved[2]))) {
                 // batch entry: hand the launch parameters over, launch nothing
@@ -1518,11 +1550,13 @@ b2r_resize_batch(const b2r_image* dst, const b2r_image* src, int nframes,
     }
     if (one_launch) {
         BatchCapture cap;
-        cap.want  = true;
-        g_capture = &cap;
-        int rc    = b2r_resize(&dst[0], &src[0], filtername, filterwidth, roi, opt, nullptr, err,
-                               errlen);
-        g_capture = nullptr;
+        cap.want       = true;
+        g_capture      = &cap;
+        g_batch_frames = nframes;
+        int rc = b2r_resize(&dst[0], &src[0], filtername, filterwidth, roi, opt, nullptr, err,
+                            errlen);
+        g_capture      = nullptr;
+        g_batch_frames = 1;
         if (rc)
             return rc;
         if (cap.got) {
@@ -1976,6 +2010,19 @@ resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Fil
     b2r_options sub = *opt;
     sub.highlightcomp = 0;
     sub.device        = device;
+    if (opt->reserved[0] == 1)  // tables only (MIP chain pass 1)
+        return resize_impl(dst_in, src_in, filter, roi_in, &sub, report, err, errlen);
+
+    // float -> float on the device: compress on load, expand on store, inside
+    // the stream kernel (one pass over HBM instead of three)
+    {
+        b2r_options fused = sub;
+        fused.reserved[3] = 1;
+        rc = resize_impl(dst_in, src_in, filter, roi_in, &fused, report, err, errlen);
+        if (rc != HC_NOT_FUSED)
+            return rc;
+        rc = B2R_OK;
+    }
 
     // compressed copy of the source, same type and windows, on the device
     b2r_image T = src;
@@ -2440,8 +2487,9 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
     const bool box_path = fname == "box" && !(sharpen > 0.0f);
     const bool hicomp   = opt && opt->highlightcomp && !box_path
                         && chain->levels.size() > 1;
-    const bool scratch_needed = hicomp || (sharpen > 0.0f && sharpen_first && !box_path
-                                           && chain->levels.size() > 1);
+    const bool scratch_needed = (hicomp && sharpen > 0.0f)
+                                || (sharpen > 0.0f && sharpen_first && !box_path
+                                    && chain->levels.size() > 1);
     const int hc_z    = opt ? opt->z_channel1 - 1 : -1;
     void* hc_tmp      = nullptr;
     if (scratch_needed
@@ -2502,6 +2550,29 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
                 chain->launches += 1;
             } else {
                 b2r_image R = S;  // what the resize reads
+                if (hicomp && !(sharpen > 0.0f)) {
+                    // rangecompress -> resize -> rangeexpand in ONE kernel when
+                    // the level's shape belongs to the stream kernel (else the
+                    // three passes, inside b2r_resize), then the clamp (:936-938)
+                    b2r_options hc = sub;
+                    hc.highlightcomp  = 1;
+                    hc.alpha_channel1 = alpha_channel + 1;
+                    hc.z_channel1     = hc_z + 1;
+                    rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &hc, nullptr, err,
+                                    errlen);
+                    if (rc) {
+                        if (ev0)
+                            cudaEventDestroy(ev0);
+                        if (ev1)
+                            cudaEventDestroy(ev1);
+                        return fail(rc);
+                    }
+                    if (pass == 1) {
+                        launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,
+                                     alpha_channel, 0.0f, 3.402823466e+38f, stream);
+                        chain->launches += 2;
+                    }
+                } else {
                 if (hicomp) {
                     // rangecompress(*img) (:907-909); the level itself stays
                     // intact for the caller, the compressed copy is scratch
@@ -2553,6 +2624,7 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
                     launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,
                                  alpha_channel, 0.0f, 3.402823466e+38f, stream);
                     chain->launches += 2;
+                }
                 }
             }
             if (pass == 1 && clamp_half) {

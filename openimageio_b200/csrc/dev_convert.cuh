@@ -72,6 +72,34 @@ quant_u16(float v)
     return u;
 }
 
+// rangecompress / rangeexpand of one value (imagebufalgo_pixelmath.cpp:560-735)
+__device__ __forceinline__ float
+dev_rangecompress(float x)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absx = fabsf(x);
+    if (absx <= x1)
+        return x;
+    float t = __fadd_rn(__fmul_rn(c, absx), 1.0f);
+    return copysignf(__fadd_rn(a, __fmul_rn(b, logf(fabsf(t)))), x);
+}
+
+__device__ __forceinline__ float
+dev_rangeexpand(float y)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    float absy = fabsf(y);
+    if (absy <= x1)
+        return y;
+    float xi = expf(__fdiv_rn(__fsub_rn(absy, a), b));
+    float x  = __fdiv_rn(__fsub_rn(xi, 1.0f), c);
+    if (x < x1)
+        x = __fdiv_rn(__fsub_rn(-xi, 1.0f), c);
+    return copysignf(x, y);
+}
+
 __device__ __forceinline__ bool
 nonfinite(float v)
 {

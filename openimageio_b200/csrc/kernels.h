@@ -258,6 +258,13 @@ struct FusedParams {
     const float* vw;     // [roi_h * vt]
     // stream kernel: data-window row that is row 0 of the TMA tensor map
     int tma_row0;
+    // stream kernel, float -> float: highlight compensation fused in --
+    // rangecompress on the source values as the V pass loads them, rangeexpand
+    // on the results as the H pass stores them (oiiotool.cpp:4644-4663,
+    // maketexture.cpp:907-935); bit c of hc_skip = channel c is left alone
+    // (alpha, z)
+    int hicomp;
+    int hc_skip;
     // stream kernel, a batch of frames of one shape in one launch (nframes > 1):
     // per frame a tensor map (device array of CUtensorMap, 64-byte aligned) and
     // the address of the ROI's first pixel

@@ -5,6 +5,7 @@
 // intrinsics: the reference computes them unfused, and a fused multiply-add
 // moves results across integer / rounding boundaries
 // (imagebufalgo_xform.cpp:1337-1341 warns about exactly that).
+#include "dev_convert.cuh"
 #include "kernels.h"
 
 #include <cuda_fp16.h>
@@ -393,33 +394,6 @@ launch_box_downsample(const BoxParams& p, void* stream)
 // highlight-compensation point ops oiiotool and maketx wrap around a resize.
 // ------------------------------------------------------------------------
 namespace {
-
-__device__ __forceinline__ float
-dev_rangecompress(float x)
-{
-    const float x1 = 0.18f, a = -0.54576885700225830078f;
-    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
-    float absx = fabsf(x);
-    if (absx <= x1)
-        return x;
-    float t = __fadd_rn(__fmul_rn(c, absx), 1.0f);
-    return copysignf(__fadd_rn(a, __fmul_rn(b, logf(fabsf(t)))), x);
-}
-
-__device__ __forceinline__ float
-dev_rangeexpand(float y)
-{
-    const float x1 = 0.18f, a = -0.54576885700225830078f;
-    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
-    float absy = fabsf(y);
-    if (absy <= x1)
-        return y;
-    float xi = expf(__fdiv_rn(__fsub_rn(absy, a), b));
-    float x  = __fdiv_rn(__fsub_rn(xi, 1.0f), c);
-    if (x < x1)
-        x = __fdiv_rn(__fsub_rn(-xi, 1.0f), c);
-    return copysignf(x, y);
-}
 
 template<bool EXPAND>
 __device__ __forceinline__ float

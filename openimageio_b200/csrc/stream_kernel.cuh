@@ -343,6 +343,17 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
                 }
             }
         }
+        if (FP && p.hicomp) {
+            // rangeexpand the results (not alpha / z)
+            float* fa[4] = { &aA.x, &aA.y, &aA.z, &aA.w };
+            float* fb[4] = { &aB.x, &aB.y, &aB.z, &aB.w };
+#pragma unroll
+            for (int c = 0; c < NCH; ++c)
+                if (!((p.hc_skip >> c) & 1)) {
+                    *fa[c] = dev_rangeexpand(*fa[c]);
+                    *fb[c] = dev_rangeexpand(*fb[c]);
+                }
+        }
         stream_store_pair<NCH>(p, dp, des, aA, aB, has_b);
         dp += (long long)G::ROWG * p.dst_ystride;
         vrows += G::ROWG * G::PITCH_B;
@@ -493,6 +504,34 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             const bool vactive = tid * E2 < strip.nvec;
             StreamPark<NCH, W2, E2> park;
             park.init(strip.e0, tid);
+            // fused highlight compensation (float sources): which of this
+            // thread's elements are range-compressed on load
+            unsigned hcmask = 0;
+            if (ST == ST_FLOAT && p.hicomp) {
+#pragma unroll
+                for (int k = 0; k < 4 * E2; ++k) {
+                    const int ch = (strip.e0 + 4 * E2 * tid + k) % NCH;
+                    if (!((p.hc_skip >> ch) & 1))
+                        hcmask |= 1u << k;
+                }
+            }
+            // raw group -> float values (+ rangecompress)
+            auto load_values = [&](const uint4& r, float4 (&v)[E2]) {
+                stream_convert<ST, E2>(r, v);
+                if (ST == ST_FLOAT && hcmask) {
+#pragma unroll
+                    for (int h = 0; h < E2; ++h) {
+                        if (hcmask & (1u << (4 * h)))
+                            v[h].x = dev_rangecompress(v[h].x);
+                        if (hcmask & (2u << (4 * h)))
+                            v[h].y = dev_rangecompress(v[h].y);
+                        if (hcmask & (4u << (4 * h)))
+                            v[h].z = dev_rangecompress(v[h].z);
+                        if (hcmask & (8u << (4 * h)))
+                            v[h].w = dev_rangecompress(v[h].w);
+                    }
+                }
+            };
             // acc[0] is the oldest open destination row (the ring table is
             // laid out the same way).  When a row completes it is parked and
             // the others move up one place -- not with register moves: the
@@ -654,7 +693,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                             float w[WROW];
                             load_w(j, w);
                             float4 v[E2];
-                            stream_convert<ST, E2>(raw[j], v);
+                            load_values(raw[j], v);
                             fma_row(w, v, shifted);
                             if ((C >> j) & 1) {
                                 const int info = __float_as_int(w[WROW - 1]);
@@ -693,7 +732,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     // 16 / 17: the (single) completing row opens / closes a batch
                     const int info = __float_as_int(w[WROW - 1]);
                     float4 v[E2];
-                    stream_convert<ST, E2>(raw[j], v);
+                    load_values(raw[j], v);
                     bool bad = false;
                     if (FP) {
                         float q = 0.0f;

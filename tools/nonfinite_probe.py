@@ -17,4 +17,8 @@ src[1000,2000,1]=float("inf")
 one=t()
 src[::97,::89,2]=float("nan")
 many=t()
-print(json.dumps({"clean_ms":clean,"one_inf_ms":one,"scattered_nan_ms":many}))
+# dense: 1 % of all values NaN / +-Inf (nearly every output pixel is non-finite in the reference too)
+m=torch.rand((h,w,4),device="cuda",generator=g)<0.01
+src[m]=float("nan")
+dense=t()
+print(json.dumps({"clean_ms":clean,"one_inf_ms":one,"scattered_nan_ms":many,"dense_1pct_nan_ms":dense}))
