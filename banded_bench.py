@@ -3,7 +3,7 @@ BASELINE config 4 cut into row bands over the N GPUs of the box from ONE
 process (b2r_mipchain_create_banded), next to the one-GPU chain -- both
 INCLUDING the upload of level 0 from pinned host memory, because that is what
 banding buys: N PCIe links instead of one.  Rank 0 runs it while the other
-ranks wait at a barrier."""
+ranks wait at a host-side (gloo) barrier, their GPUs idle."""
 import time
 
 import numpy as np

@@ -210,6 +210,51 @@ def cpu_sample(wl, nthreads=0, rows=None, repeat=5):
                          "%d threads, %.2f s" % (rows, dh, wl, cores, best))
 
 
+def cpu_c4_sample(size=4096, filt="lanczos3"):
+    """The CPU side of the same maketx stage on a bounded sample: the oracle's
+    write_mipmap level loop on a size x size RGBA float image, then every
+    level cut into 64x64 half tiles and deflated (zlib level 1) on all host
+    threads.  Mpixel/s over all levels, so it compares with tiles.mpixel_s."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+    import oracle_py
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(20261023)
+    lvl0 = rng.random((size, size, 4), dtype=np.float32)
+    t0 = time.perf_counter()
+    levels = [lvl0] + oracle_py.mip_chain(lvl0, filt)
+    t_chain = time.perf_counter() - t0
+
+    def encode(level):
+        h, w, c = level.shape
+        H2, W2 = -(-h // 64) * 64, -(-w // 64) * 64
+        pad = np.zeros((H2, W2, c), np.float16)
+        pad[:h, :w] = level
+        t = pad.reshape(H2 // 64, 64, W2 // 64, 64, c).transpose(0, 2, 1, 3, 4)
+        t = np.ascontiguousarray(t).reshape(-1, 64 * 64 * c)
+        return sum(len(zlib.compress(row.tobytes(), 1)) for row in t)
+
+    def encode_rows(job):
+        level, a, b = job
+        return encode(level[a:b])
+    jobs = []
+    for lv in levels:
+        for a in range(0, lv.shape[0], 256):
+            jobs.append((lv, a, min(lv.shape[0], a + 256)))
+    t1 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        stored = sum(ex.map(encode_rows, jobs))
+    t_enc = time.perf_counter() - t1
+    npx = sum(l.shape[0] * l.shape[1] for l in levels)
+    total = t_chain + t_enc
+    return {"value": npx / 1e6 / total, "unit": "Mpixel/s (all levels)", "cores": cores,
+            "kind": "port", "chain_ms": t_chain * 1e3, "encode_ms": t_enc * 1e3,
+            "stored_mb": stored / 1e6,
+            "sample": "%dx%d RGBA float %s chain (oracle port, threaded) + 64x64 half tiles, "
+                      "zlib level 1 on %d threads; level 0 already in host memory"
+                      % (size, size, filt, cores)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -274,8 +319,12 @@ class Harness:
             raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.cpu_group = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
+            # host-side barrier (gloo): ranks that wait while rank 0 drives all
+            # GPUs from one process must not park a spinning NCCL kernel on them
+            self.cpu_group = dist.new_group(backend="gloo")
         self.tdt = {"float32": torch.float32, "float16": torch.float16,
                     "uint8": torch.uint8, "uint16": torch.uint16}
         self.peak, self.peak_src = measured_peak()
@@ -289,6 +338,11 @@ class Harness:
         if self.world > 1:
             self.dist.barrier()
         self.torch.cuda.synchronize()
+
+    def cpu_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.cpu_group is not None:
+            self.dist.barrier(group=self.cpu_group)
 
     def max_over_ranks(self, x):
         t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
@@ -334,7 +388,7 @@ class Harness:
         return src_np, src_host, dst_host, srcs, dsts
 
     def resize_config(self, wl, steps, warmup, nfr, e2e_steps, sustain_ms=0.0,
-                      sampler=None, pageable=False, total_frames=None):
+                      sampler=None, pageable=False, total_frames=None, pcie=False):
         """Device-resident + end-to-end numbers of one resize workload."""
         oiio, torch = self.oiio, self.torch
         IBA = oiio.ImageBufAlgo
@@ -385,6 +439,21 @@ class Harness:
         e2e_ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
         rep = IBA.last_report
         out["e2e_ms_per_step"] = e2e_ms
+        if pcie:
+            # what this host can feed the GPU(s): plain pinned -> device copies of
+            # the same source frame, all ranks at once, no kernels
+            flat = src_host.view(torch.uint8).reshape(-1)
+            dflat = torch.empty_like(flat, device=self.dev)
+            for _ in range(2):
+                dflat.copy_(flat, non_blocking=True)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                dflat.copy_(flat, non_blocking=True)
+            self.barrier()
+            cp_ms = self.max_over_ranks((time.perf_counter() - t0) * 1e3 / 5)
+            out["h2d_ceiling_gbs"] = flat.numel() / (cp_ms * 1e-3) / 1e9
+            del dflat
         out["h2d"] = int(rep.h2d_bytes) * nfr
         out["d2h"] = int(rep.d2h_bytes) * nfr
         out["kernel_path"] = ("stream" if getattr(rep, "kernels_launched", 2) == 1
@@ -488,7 +557,7 @@ class Harness:
             del i, v
         return t.view(size, size, 4)
 
-    def c4_chain(self, size, host_pinned, lvl0, filt, repeats=2):
+    def c4_chain(self, size, host_pinned, lvl0, filt, repeats=2, with_tiles=False):
         oiio, torch = self.oiio, self.torch
         ab, out_px = chain_bytes(size)
         best = None
@@ -510,8 +579,28 @@ class Harness:
         up_ms = (t_up - t0) * 1e3
         del ch
         torch.cuda.empty_cache()
+        # maketx's output stage (maketexture.cpp:957-974): level 0 up, chain,
+        # EVERY level re-laid into 64x64 tiles (float -> half, maketx -d half) on
+        # the device, brought down on a copy stream and deflated by host threads
+        tiles = None
+        if with_tiles:
+            t0 = time.perf_counter()
+            ch = oiio.MipChain(oiio.ImageBuf(host_pinned), filtername=filt, device=self.local_rank)
+            ts = oiio.TileSet(ch, tile=64, half=True, zlevel=1, nthreads=0)
+            t_ms = (time.perf_counter() - t0) * 1e3
+            npx = sum(ts.level_info(l)[0] * ts.level_info(l)[1] for l in range(ts.nlevels))
+            tiles = {"what": "pinned level 0 up, chain, all %d levels -> 64x64 half tiles, "
+                             "zlib level 1 on host threads; wall clock" % ts.nlevels,
+                     "e2e_ms": t_ms, "mpixel_s_all_levels": npx / 1e6 / (t_ms * 1e-3),
+                     "encode_ms": ts.stat("total_ms"), "device_ms": ts.stat("device_ms"),
+                     "deflate_busy_ms": ts.stat("deflate_ms"),
+                     "raw_mb": ts.stat("raw_bytes") / 1e6, "stored_mb": ts.stat("stored_bytes") / 1e6,
+                     "host_threads": os.cpu_count()}
+            del ts, ch
+            torch.cuda.empty_cache()
         ach = ab / (best * 1e-3) / 1e9
-        return {"workload": "maketx MIP chain of a %dx%d RGBA float32 texture, %s, "
+        return {"tiles": tiles,
+                "workload": "maketx MIP chain of a %dx%d RGBA float32 texture, %s, "
                             "%d levels, device-resident" % (size, size, filt, nlev),
                 "value": out_px / 1e6 / (best * 1e-3), "unit": "Mpixel/s (levels >= 1)",
                 "chain_ms": best, "achieved_gbs": ach, "frac": ach / self.peak,
@@ -569,7 +658,8 @@ def main():
             torch.cuda.synchronize()
         del x
     r = H.resize_config(wl, args.steps, args.warmup, nfr, e2e_steps,
-                        sustain_ms=args.sustain_ms, sampler=sampler, pageable=True)
+                        sustain_ms=args.sustain_ms, sampler=sampler, pageable=True,
+                        pcie=True)
     head = H.summarise(wl, r, nfr * H.world)
 
     configs, banded = {}, None
@@ -588,19 +678,24 @@ def main():
                 host.copy_(lvl0)
                 torch.cuda.synchronize()
                 for f in ("box", "lanczos3"):
-                    configs["c4_" + f] = H.c4_chain(size, host, lvl0, f)
+                    configs["c4_" + f] = H.c4_chain(size, host, lvl0, f,
+                                                    with_tiles=(f == "lanczos3"))
+                if not args.no_cpu:
+                    configs["c4_lanczos3"]["cpu_baseline"] = cpu_c4_sample()
                 del lvl0, host
                 torch.cuda.empty_cache()
             except Exception as e:  # a side config must not sink the headline
                 configs["c4_error"] = str(e)
         if H.world > 1:
             H.barrier()
+            H.cpu_barrier()
             if H.rank == 0:
                 try:
                     import banded_bench
                     banded = banded_bench.run(H, args.c4_size)
                 except Exception as e:
                     banded = {"error": str(e)}
+            H.cpu_barrier()
             H.barrier()
     if sampler:
         sampler.stop()
@@ -631,6 +726,13 @@ def main():
                     "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "ms_per_step": r["e2e_ms_per_step"], "steps": e2e_steps,
                     "host_memory": "pinned",
+                    # per-GPU upload rate of the e2e step against a plain
+                    # cudaMemcpyAsync loop of the same frame run by all ranks at
+                    # once (the host's ceiling at this N)
+                    "h2d_gbs_per_gpu": r["h2d"] / (r["e2e_ms_per_step"] * 1e-3) / 1e9,
+                    "h2d_ceiling_gbs_per_gpu": r.get("h2d_ceiling_gbs"),
+                    "pcie_frac": (r["h2d"] / (r["e2e_ms_per_step"] * 1e-3) / 1e9
+                                  / r["h2d_ceiling_gbs"]) if r.get("h2d_ceiling_gbs") else None,
                     "pageable_value": (mpix_frame / (r["pageable_ms"] * 1e-3)
                                        if r.get("pageable_ms") else None),
                     "pageable_ms_per_frame": r.get("pageable_ms")},

@@ -191,7 +191,8 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     key.nch   = nch;
     // source rows TMA can fetch (16-byte aligned base and pitch) get the stream
     // kernel's strip geometry: part of the key
-    key.st    = src.basetype | (tma_ok ? 0x100 : 0) | (g_batch_frames > 1 ? 0x200 : 0);
+    // (the band count of a batch plan depends on the number of frames)
+    key.st    = src.basetype | (tma_ok ? 0x100 : 0) | (std::min(g_batch_frames, 0xffff) << 10);
     {
         std::lock_guard<std::mutex> lock(g_plan_mutex);
         for (auto it = g_plans.begin(); it != g_plans.end(); ++it) {
@@ -240,7 +241,7 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
         bool stream_plan = false;
         if (ok && tma_ok) {
             stream_plan = plan_fused(ax, ay, nch, src.width, src.height, sms * 2, &plan->fp,
-                                     e0a, 2)
+                                     e0a, 2, sms, g_batch_frames)
                           && plan->fp.w2 == 2 && !plan->fp.expand && plan->fp.vk > 0
                           && stream_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht, 2)
                           && (long long)plan->fp.strips.size() * (long long)plan->fp.bands.size()
@@ -746,7 +747,9 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         return B2R_OK;  // private: build + upload the tables only (MIP chain)
     if (want_hc
         && !(plan->fused && !plan->fp.expand && plan->fp.vk > 0 && plan->fp.ht > 0
-             && plan->fp.ht <= 16 && src_contig && dst.xstride == (int64_t)nch * des))
+             && plan->fp.ht <= 16 && src_contig && dst.xstride == (int64_t)nch * des
+             && tma_ok
+             && stream_supported(src.basetype, nch, plan->fp.vk, plan->fp.ht, plan->fp.w2, 1)))
         return HC_NOT_FUSED;
 
     // ---- stage host images ------------------------------------------------
@@ -953,7 +956,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         bool streamed = false;
         const int w2 = plan->fp.w2;
         if (!fp.expand && fp.vk > 0 && tma_ok
-            && stream_supported(src.basetype, nch, fp.vk, fp.ht, w2)) {
+            && stream_supported(src.basetype, nch, fp.vk, fp.ht, w2, want_hc ? 1 : 0)) {
             const bool temp = src_staged || src_repitched;
             const int trow0 = temp ? plan->src_row0 : 0;
             const int trows = temp ? plan->src_row1 - plan->src_row0 + 1 : src.height;

@@ -59,17 +59,36 @@ convert_raw4(uint4 r)
         float2 fa = __half22float2(a), fb = __half22float2(b);
         return make_float4(fa.x, fa.y, fb.x, fb.y);
     } else if (ST == ST_U16) {
-        const float s = 1.0f / 65535.0f;
-        return make_float4(__fmul_rn(small_uint_to_float(r.x & 0xffffu), s),
-                           __fmul_rn(small_uint_to_float(r.x >> 16), s),
-                           __fmul_rn(small_uint_to_float(r.y & 0xffffu), s),
-                           __fmul_rn(small_uint_to_float(r.y >> 16), s));
+        // convert_type<uint16,float> is float(u) * (1/65535) (fmath.h:1009-1031).
+        // PRMT builds the float 2^23 + u (0x4B00'0000 | u), then ONE packed FMA
+        // per element pair computes (2^23 + u) * s - 2^23 * s: the product
+        // 2^23 * s is exact, so the FMA rounds exactly u * s -- the same bits as
+        // the multiply, without the subtraction and the shifts / masks.
+        const float s    = 1.0f / 65535.0f;
+        const float2 ss  = make_float2(s, s);
+        const float2 off = make_float2(-8388608.0f * s, -8388608.0f * s);
+        const float2 lo  = __ffma2_rn(
+            make_float2(__uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7410)),
+                        __uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7432))),
+            ss, off);
+        const float2 hi = __ffma2_rn(
+            make_float2(__uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7410)),
+                        __uint_as_float(__byte_perm(r.y, 0x4B000000u, 0x7432))),
+            ss, off);
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
     } else {
-        const float s = 1.0f / 255.0f;
-        return make_float4(__fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4440)), s),
-                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4441)), s),
-                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4442)), s),
-                           __fmul_rn(small_uint_to_float(__byte_perm(r.x, 0, 0x4443)), s));
+        const float s    = 1.0f / 255.0f;
+        const float2 ss  = make_float2(s, s);
+        const float2 off = make_float2(-8388608.0f * s, -8388608.0f * s);
+        const float2 lo  = __ffma2_rn(
+            make_float2(__uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7440)),
+                        __uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7441))),
+            ss, off);
+        const float2 hi = __ffma2_rn(
+            make_float2(__uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7442)),
+                        __uint_as_float(__byte_perm(r.x, 0x4B000000u, 0x7443))),
+            ss, off);
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
     }
 }
 

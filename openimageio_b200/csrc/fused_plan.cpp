@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cstring>
 
 namespace b2r {
@@ -201,7 +202,8 @@ plan_expand(const AxisGather& gx, const AxisGather& gy,
 
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan, int e0_align, int w2)
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align, int w2, int stream_sms,
+           int nframes)
 {
     // strips start on a 16-byte boundary of the source row (e0_align elements):
     // the TMA boxes of the stream kernel need it, the other kernels need 4
@@ -357,6 +359,36 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
     int nbands        = std::max(1, cta_slots / std::max(1, nstrips));
     const int min_rows = w2 == 2 ? 32 : 8;
     nbands             = std::min(nbands, std::max(1, H / min_rows));
+    // (B2R_BANDSEARCH=0: the fixed two-items-per-SM split, for A/B measurements)
+    static const bool band_search = [] {
+        const char* e = getenv("B2R_BANDSEARCH");
+        return !(e && e[0] == '0');
+    }();
+    if (band_search && stream_sms > 0 && use_ring && w2 == 2) {
+        // Persistent kernel: CTA c runs items c, c + sms, ... of the
+        // (frame, band, strip) list, so the schedule takes ceil(items / sms)
+        // rounds of one band each.  A band costs its source rows -- its share
+        // of the rows plus the filter's reach into the neighbouring bands,
+        // which is read again -- plus a fixed start-up (tables, pipe fill).
+        // More bands fill the last round better, fewer re-read less: pick
+        // the cheapest count.
+        const int halo  = std::max(0, vt - int(rows_total / std::max(1, H)));
+        const int setup = 12;
+        const int nbmax = std::max(1, std::min(H / min_rows, 4 * stream_sms));
+        // (at least one item per CTA when the shape allows it)
+        const long long per_band = (long long)nstrips * std::max(1, nframes);
+        const int nbmin = int(std::min<long long>(nbmax, (stream_sms + per_band - 1) / per_band));
+        long long best  = -1;
+        for (int nb = nbmin; nb <= nbmax; ++nb) {
+            const long long items  = (long long)nstrips * nb * std::max(1, nframes);
+            const long long rounds = (items + stream_sms - 1) / stream_sms;
+            const long long cost   = rounds * ((rows_total + nb - 1) / nb + halo + setup);
+            if (best < 0 || cost < best) {
+                best   = cost;
+                nbands = nb;
+            }
+        }
+    }
     // ring weights live in shared memory: keep a band's source rows bounded
     // ring row = vk weights padded to float4 loads
     const int vkp           = (vk + 3) & ~3;

@@ -38,8 +38,12 @@ struct FusedPlan {
 // many CTAs the device keeps resident (SMs x CTAs per SM); the band count is
 // chosen so the grid fills one wave.  Returns false when the shape is outside
 // what the fused kernel instantiates (then the exact kernel runs).
+// stream_sms > 0 (persistent stream kernel, one CTA per SM walking a static
+// item list): the band count is searched for the shortest schedule of
+// nstrips x nbands x nframes items over stream_sms CTAs instead.
 bool
 plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
-           int src_h, int cta_slots, FusedPlan* plan, int e0_align = 4, int w2 = 1);
+           int src_h, int cta_slots, FusedPlan* plan, int e0_align = 4, int w2 = 1,
+           int stream_sms = 0, int nframes = 1);
 
 }  // namespace b2r

@@ -284,7 +284,7 @@ typedef void (*FusedKernel)(const FusedParams, int, int);
 typedef void (*StreamKernel)(const ::CUtensorMap_st, const FusedParams);
 #endif
 bool
-stream_supported(int srctype, int nch, int vk, int ht, int w2);
+stream_supported(int srctype, int nch, int vk, int ht, int w2, int hicomp = 0);
 // tma_base: address of element 0 of data-window row p.tma_row0; tma_rows: rows
 // that exist from there on.  Returns 0, or a negative value when the tensor
 // map could not be made (the caller falls back to the fused kernel).

@@ -39,6 +39,7 @@
 #include "fused_kernel.cuh"
 
 #include <cuda.h>  // CUtensorMap
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -294,7 +295,7 @@ stream_store_pair(const FusedParams& p, unsigned char* dp, int des, const float4
 // independent loads and four FFMA2 chains per row are enough to keep the
 // pipes fed; interleaving rows would not fit the register budget).
 // FP: screen the outputs and re-filter with the zero taps skipped.
-template<int NCH, int HT, int W2, int NR, bool FP>
+template<int NCH, int HT, int W2, int NR, bool FP, bool HC>
 __device__ __forceinline__ void
 stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb, int dyb,
              int dxA, bool has_b, const int (&hb)[4], const float2 (&hw)[HT], int hmix, int hr)
@@ -343,7 +344,7 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
                 }
             }
         }
-        if (FP && p.hicomp) {
+        if (HC) {
             // rangeexpand the results (not alpha / z)
             float* fa[4] = { &aA.x, &aA.y, &aA.z, &aA.w };
             float* fb[4] = { &aB.x, &aB.y, &aB.z, &aB.w };
@@ -394,7 +395,10 @@ template<int ST, int VK, int W2> struct StreamSmem {
     static_assert(NST >= 2, "at least two stages");
 };
 
-template<int ST, int NCH, int VK, int HT, int W2>
+// HC: highlight compensation fused in (float sources only) -- a template
+// parameter because the V loop has no register to spare for a run-time flag
+// (the run-time version cost the plain C0 frame 115 -> 136 us).
+template<int ST, int NCH, int VK, int HT, int W2, bool HC = false>
 __global__ void __launch_bounds__(StreamSmem<ST, VK, W2>::G::THREADS, 1)
 resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p)
 {
@@ -411,6 +415,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     constexpr bool FP   = (ST == ST_FLOAT || ST == ST_HALF);
     // stage-specialised V pass (see the V warps below)
     constexpr bool SPEC = W2 == 2 && (!FP || VK <= 4);
+    static_assert(!HC || ST == ST_FLOAT, "highlight compensation is fused for float sources");
     static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
 
     extern __shared__ __align__(1024) unsigned char stream_smem[];
@@ -502,12 +507,17 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             const Strip strip = p.strips[fitem % p.nstrips];
             const Band band   = p.bands[fitem / p.nstrips];
             const bool vactive = tid * E2 < strip.nvec;
+            // (Measured: letting V warps that have no elements in the strip --
+            // RGB strips fill 3/4 of the V threads -- skip the arithmetic and only
+            // follow the barrier protocol is SLOWER, in line or out of line: the
+            // second path costs the hot loop registers (16 bytes of spills per
+            // stage); C0 111 -> 145 us, C5 26.9 -> 31.0 us.)
             StreamPark<NCH, W2, E2> park;
             park.init(strip.e0, tid);
             // fused highlight compensation (float sources): which of this
             // thread's elements are range-compressed on load
             unsigned hcmask = 0;
-            if (ST == ST_FLOAT && p.hicomp) {
+            if (HC) {
 #pragma unroll
                 for (int k = 0; k < 4 * E2; ++k) {
                     const int ch = (strip.e0 + 4 * E2 * tid + k) % NCH;
@@ -518,7 +528,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             // raw group -> float values (+ rangecompress)
             auto load_values = [&](const uint4& r, float4 (&v)[E2]) {
                 stream_convert<ST, E2>(r, v);
-                if (ST == ST_FLOAT && hcmask) {
+                if (HC && hcmask) {
 #pragma unroll
                     for (int h = 0; h < E2; ++h) {
                         if (hcmask & (1u << (4 * h)))
@@ -669,16 +679,32 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     // any Inf/NaN in this warp's rows of the stage -> the per-row
                     // path with its zero-weight handling; otherwise the stage is
                     // straight-line code with no per-row branches at all
-                    float q = 0.0f;
+                    if (ST == ST_HALF && E2 == 1) {
+                        // on the raw words: x * 0 is NaN exactly for Inf / NaN, so
+                        // one packed half FMA per word leaves q at +0 unless the
+                        // stage holds a non-finite value
+                        __half2 q = __floats2half2_rn(0.f, 0.f);
+                        const __half2 z = q;
 #pragma unroll
-                    for (int j = 0; j < ROWS; ++j) {
-                        float4 v[E2];
-                        stream_convert<ST, E2>(raw[j], v);
+                        for (int j = 0; j < ROWS; ++j) {
+                            q = __hfma2(*reinterpret_cast<const __half2*>(&raw[j].x), z, q);
+                            q = __hfma2(*reinterpret_cast<const __half2*>(&raw[j].y), z, q);
+                        }
+                        const unsigned qb = *reinterpret_cast<const unsigned*>(&q);
+                        slow = slow || __any_sync(0xffffffffu, (qb & 0x7fff7fffu) != 0u);
+                    } else {
+                        float q = 0.0f;
 #pragma unroll
-                        for (int h = 0; h < E2; ++h)
-                            q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                        for (int j = 0; j < ROWS; ++j) {
+                            float4 v[E2];
+                            stream_convert<ST, E2>(raw[j], v);
+#pragma unroll
+                            for (int h = 0; h < E2; ++h)
+                                q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
+                        }
+                        slow = slow
+                               || __any_sync(0xffffffffu, !(fabsf(q) <= 3.402823466e+38f));
                     }
-                    slow = slow || __any_sync(0xffffffffu, !(fabsf(q) <= 3.402823466e+38f));
                 }
                 if (SPEC && !slow) {
                     auto fast = [&](auto code) {
@@ -820,7 +846,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 const int b  = nbatch & 1;
                 named_bar_sync(1 + b, NSYNC);
                 if (pair_active)
-                    stream_hpass<NCH, HT, W2, NR, FP>(p, dbase, vbuf0 + b * S::VBUF_B, nb, dyb,
+                    stream_hpass<NCH, HT, W2, NR, FP, HC>(p, dbase, vbuf0 + b * S::VBUF_B, nb, dyb,
                                                       dxA, has_b, hb, hw, hmix, hr);
                 ++nbatch;
                 if (nbatch + 2 <= total)

@@ -10,7 +10,7 @@
 
 namespace b2r {
 
-#define B2R_DECL_LOOKUP(ST, NCH) StreamKernel stream_lookup_##ST##_##NCH(int, int, int, int*);
+#define B2R_DECL_LOOKUP(ST, NCH) StreamKernel stream_lookup_##ST##_##NCH(int, int, int, int, int*);
 #define B2R_DECL_ST(ST) \
     B2R_DECL_LOOKUP(ST, 1) B2R_DECL_LOOKUP(ST, 2) B2R_DECL_LOOKUP(ST, 3) B2R_DECL_LOOKUP(ST, 4)
 B2R_DECL_ST(0) B2R_DECL_ST(1) B2R_DECL_ST(2) B2R_DECL_ST(3)
@@ -28,23 +28,23 @@ st_index(int basetype)
 }
 
 static StreamKernel
-pick_stream(int srctype, int nch, int vk, int ht, int w2, int* smem)
+pick_stream(int srctype, int nch, int vk, int ht, int w2, int hc, int* smem)
 {
-    typedef StreamKernel (*Lookup)(int, int, int, int*);
+    typedef StreamKernel (*Lookup)(int, int, int, int, int*);
 #define B2R_ROW(ST) \
     { stream_lookup_##ST##_1, stream_lookup_##ST##_2, stream_lookup_##ST##_3, stream_lookup_##ST##_4 }
     static const Lookup table[4][4] = { B2R_ROW(0), B2R_ROW(1), B2R_ROW(2), B2R_ROW(3) };
     int st = st_index(srctype);
     if (st < 0 || nch < 1 || nch > 4)
         return nullptr;
-    return table[st][nch - 1](vk, ht, w2, smem);
+    return table[st][nch - 1](vk, ht, w2, hc, smem);
 }
 
 bool
-stream_supported(int srctype, int nch, int vk, int ht, int w2)
+stream_supported(int srctype, int nch, int vk, int ht, int w2, int hicomp)
 {
     int smem = 0;
-    return pick_stream(srctype, nch, vk, ht, w2, &smem) != nullptr;
+    return pick_stream(srctype, nch, vk, ht, w2, hicomp, &smem) != nullptr;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the
@@ -100,7 +100,7 @@ static int
 launch_with_map(const FusedParams& p, int w2, const CUtensorMap& map, int sms, void* stream)
 {
     int smem = 0;
-    StreamKernel k = pick_stream(p.srctype, p.nch, p.vk, p.ht, w2, &smem);
+    StreamKernel k = pick_stream(p.srctype, p.nch, p.vk, p.ht, w2, p.hicomp, &smem);
     if (!k || p.nstrips <= 0 || p.nbands <= 0)
         return -1;
     if (cudaFuncSetAttribute((const void*)k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
