@@ -594,6 +594,7 @@ class Harness:
                      "e2e_ms": t_ms, "mpixel_s_all_levels": npx / 1e6 / (t_ms * 1e-3),
                      "encode_ms": ts.stat("total_ms"), "device_ms": ts.stat("device_ms"),
                      "deflate_busy_ms": ts.stat("deflate_ms"),
+                     "setup_ms": ts.stat("setup_ms"), "download_wait_ms": ts.stat("wait_ms"),
                      "raw_mb": ts.stat("raw_bytes") / 1e6, "stored_mb": ts.stat("stored_bytes") / 1e6,
                      "host_threads": os.cpu_count()}
             del ts, ch

@@ -472,7 +472,8 @@ B2R_API int b2r_tileset_level(const b2r_tileset* ts, int level, int* width, int*
 B2R_API int b2r_tileset_tile(const b2r_tileset* ts, int level, int tx, int ty,
                              const void** data, size_t* bytes);
 /* what: 0 wall ms of the encode call, 1 device ms (relayout + downloads),
- * 2 host ms inside the deflate phases, 3 raw bytes, 4 stored bytes. */
+ * 2 host ms inside the deflate phases, 3 raw bytes, 4 stored bytes,
+ * 5 ms spent setting up the staging slots, 6 host ms blocked on downloads. */
 B2R_API double b2r_tileset_stat(const b2r_tileset* ts, int what);
 B2R_API void b2r_tileset_destroy(b2r_tileset* ts);
 

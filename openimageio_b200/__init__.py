@@ -1615,7 +1615,7 @@ class TileSet:
 
     def stat(self, what):
         k = {"total_ms": 0, "device_ms": 1, "deflate_ms": 2, "raw_bytes": 3,
-             "stored_bytes": 4}[what]
+             "stored_bytes": 4, "setup_ms": 5, "wait_ms": 6}[what]
         return lib().b2r_tileset_stat(self._h, k)
 
 

@@ -18,6 +18,7 @@
 #include <zlib.h>
 
 #include <atomic>
+#include <mutex>
 #include <chrono>
 #include <thread>
 
@@ -32,8 +33,52 @@ struct b2r_tileset {
     int nch = 0, tile_w = 0, tile_h = 0, out_basetype = 0, compression = 0;
     std::vector<Level> levels;
     long long raw_bytes = 0, stored_bytes = 0;
-    float total_ms = 0, device_ms = 0, deflate_busy_ms = 0;
+    float total_ms = 0, device_ms = 0, deflate_busy_ms = 0, setup_ms = 0, wait_ms = 0;
 };
+
+namespace {
+
+// The three device + three pinned host staging slots, kept per device between
+// calls (grow-only): pinning and unpinning 3 x 64 MB cost 90-300 ms per call,
+// a third of an 8K^2 chain's whole output stage.  One encode at a time per
+// device holds them.
+constexpr int NSLOT = 3;
+struct SlotCache {
+    std::mutex mu;
+    void* d[NSLOT] = { nullptr, nullptr, nullptr };
+    void* h[NSLOT] = { nullptr, nullptr, nullptr };
+    size_t bytes   = 0;
+    bool reserve(size_t need)
+    {
+        if (need <= bytes)
+            return true;
+        for (int i = 0; i < NSLOT; ++i) {
+            if (d[i])
+                cudaFree(d[i]);
+            if (h[i])
+                cudaFreeHost(h[i]);
+            d[i] = h[i] = nullptr;
+        }
+        bytes = 0;
+        for (int i = 0; i < NSLOT; ++i) {
+            if (cudaMalloc(&d[i], need) != cudaSuccess
+                || cudaHostAlloc(&h[i], need, cudaHostAllocDefault) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+        }
+        bytes = need;
+        return true;
+    }
+};
+SlotCache&
+slot_cache(int device)
+{
+    static SlotCache caches[64];
+    return caches[device & 63];
+}
+
+}  // namespace
 
 extern "C" int
 b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
@@ -96,21 +141,17 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
     for (const Chunk& c : chunks)
         slot_bytes = std::max(slot_bytes,
                               size_t(c.ty1 - c.ty0) * ts->levels[c.level].ntx * tile_bytes);
-    constexpr int NSLOT = 3;
-    void* dslot[NSLOT] = { nullptr, nullptr, nullptr };
-    void* hslot[NSLOT] = { nullptr, nullptr, nullptr };
+    SlotCache& cache = slot_cache(chain->device);
+    std::lock_guard<std::mutex> cache_lock(cache.mu);
+    void** dslot = cache.d;
+    void** hslot = cache.h;
     cudaEvent_t landed[NSLOT] = { nullptr, nullptr, nullptr };
     cudaStream_t sk = nullptr, sc = nullptr;
     cudaEvent_t relaid = nullptr, ev0 = nullptr, ev1 = nullptr;
     auto cleanup = [&]() {
-        for (int i = 0; i < NSLOT; ++i) {
-            if (dslot[i])
-                cudaFree(dslot[i]);
-            if (hslot[i])
-                cudaFreeHost(hslot[i]);
+        for (int i = 0; i < NSLOT; ++i)
             if (landed[i])
                 cudaEventDestroy(landed[i]);
-        }
         if (relaid)
             cudaEventDestroy(relaid);
         if (ev0)
@@ -122,24 +163,21 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
         if (sc)
             cudaStreamDestroy(sc);
     };
-    if (slot_bytes) {
-        for (int i = 0; i < NSLOT; ++i) {
-            if (cudaMalloc(&dslot[i], slot_bytes) != cudaSuccess
-                || cudaHostAlloc(&hslot[i], slot_bytes, cudaHostAllocDefault) != cudaSuccess
-                || cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming) != cudaSuccess) {
-                cudaGetLastError();
-                cleanup();
-                set_err(err, errlen, "encode_tiles: out of memory for the staging slots");
-                return B2R_ERR_CUDA;
-            }
-        }
+    if (slot_bytes && !cache.reserve(slot_bytes)) {
+        set_err(err, errlen, "encode_tiles: out of memory for the staging slots");
+        return B2R_ERR_CUDA;
     }
+    for (int i = 0; i < NSLOT; ++i)
+        cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&sk, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&relaid, cudaEventDisableTiming);
     cudaEventCreate(&ev0);
     cudaEventCreate(&ev1);
     cudaEventRecord(ev0, sk);
+    ts->setup_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now()
+                                                            - t_begin)
+                       .count();
 
     // device side of chunk i: relayout on `sk`, download on `sc`
     auto issue = [&](int i) {
@@ -161,14 +199,18 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
     for (int i = 0; i < std::min(nchunks, NSLOT - 1); ++i)
         issue(i);
     std::atomic<int> failed(0);
-    double busy_ms = 0;
+    double busy_ms = 0, wait_ms = 0;
     for (int i = 0; i < nchunks; ++i) {
         const Chunk& c = chunks[i];
         auto& TL       = ts->levels[c.level];
         const int s    = i % NSLOT;
         if (i + NSLOT - 1 < nchunks)
             issue(i + NSLOT - 1);  // its slot was deflated in the previous iteration
-        if (cudaEventSynchronize(landed[s]) != cudaSuccess) {
+        auto tw = std::chrono::steady_clock::now();
+        const cudaError_t landed_rc = cudaEventSynchronize(landed[s]);
+        wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw)
+                       .count();
+        if (landed_rc != cudaSuccess) {
             cleanup();
             set_err(err, errlen, "encode_tiles: CUDA error: %s",
                     cudaGetErrorString(cudaGetLastError()));
@@ -229,6 +271,7 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
             ts->stored_bytes += (long long)t.size();
         }
     ts->deflate_busy_ms = (float)busy_ms;
+    ts->wait_ms         = (float)wait_ms;
     ts->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now()
                                                             - t_begin)
                        .count();
@@ -288,6 +331,8 @@ b2r_tileset_stat(const b2r_tileset* ts, int what)
     case 2: return ts->deflate_busy_ms;  // host time spent in the deflate phases
     case 3: return (double)ts->raw_bytes;
     case 4: return (double)ts->stored_bytes;
+    case 5: return ts->setup_ms;  // staging slots, streams
+    case 6: return ts->wait_ms;   // host time blocked on the downloads
     }
     return 0.0;
 }
