@@ -47,6 +47,8 @@ def run(H, size, filters=("box", "lanczos3"), devices=None, check=True):
             rec["banded_upload_ms"] = many.ms("upload")
             rec["banded_chain_ms"] = many.ms("chain")
             rec["halo_mb"] = many.ms("halo_bytes") / 1e6
+            rec["banded_host_ms"] = {"setup": many.ms("setup"), "upload_and_tables": many.ms("phase_a"),
+                                     "level_loop": many.ms("phase_b")}
             if _ == 0:
                 del many
         rec["speedup"] = rec["one_gpu_ms"] / rec["banded_ms"]

@@ -513,7 +513,9 @@ B2R_API int b2r_mipchain_banded_download(const b2r_mipchain_banded* chain, int l
                                          size_t errlen);
 /* what: 0 host wall clock of the create call (upload + tables + level loop),
  * 1 level-0 upload and 2 level loop incl. the pushes (device events, max over
- * the devices), 3 bytes pushed between devices.  ms (bytes for 3). */
+ * the devices), 3 bytes pushed between devices; host wall clock of the call's
+ * parts: 4 setup (peer access, band buffers), 5 upload threads + tables,
+ * 6 level loop issue + final synchronise.  ms (bytes for 3). */
 B2R_API float b2r_mipchain_banded_ms(const b2r_mipchain_banded* chain, int what);
 B2R_API void b2r_mipchain_banded_destroy(b2r_mipchain_banded* chain);
 

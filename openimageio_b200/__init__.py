@@ -1661,7 +1661,8 @@ class MipChainBanded:
     def ms(self, what="total"):
         """'total': host wall clock of the construction; 'upload' / 'chain':
         device events, max over the devices; 'halo_bytes'."""
-        k = {"total": 0, "upload": 1, "chain": 2, "halo_bytes": 3}[what]
+        k = {"total": 0, "upload": 1, "chain": 2, "halo_bytes": 3, "setup": 4,
+             "phase_a": 5, "phase_b": 6}[what]
         return lib().b2r_mipchain_banded_ms(self._h, k)
 
     def level_size(self, level):

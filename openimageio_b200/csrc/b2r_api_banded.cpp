@@ -21,6 +21,8 @@
 #include "api_internal.h"
 
 #include <chrono>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,11 +45,58 @@ struct b2r_mipchain_banded {
     std::vector<cudaStream_t> streams;
     std::vector<Level> levels;
     float upload_ms = 0, chain_ms = 0, total_ms = 0;
+    float setup_ms = 0, phase_a_ms = 0, phase_b_ms = 0;  // host wall clock of the three parts
     long long halo_bytes = 0;
     int launches = 0;
 };
 
 namespace {
+
+// Band buffers are multi-gigabyte cudaMalloc blocks that every peer maps: 10-60
+// ms per chain when allocated fresh, against ~40 ms for the whole banded chain
+// at two GPUs.  Blocks of destroyed chains are kept per device (exact-size
+// reuse, bounded) so a run of same-sized textures -- what maketx jobs are --
+// allocates once.
+struct BandBlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> blocks[64];
+    size_t held[64] = {};
+    static constexpr size_t kMaxHeld = size_t(12) << 30;  // per device
+    void* take(int dev, size_t bytes)
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto& m = blocks[dev & 63];
+        auto it = m.find(bytes);
+        if (it == m.end())
+            return nullptr;
+        void* p = it->second;
+        m.erase(it);
+        held[dev & 63] -= bytes;
+        return p;
+    }
+    // caller has made `dev` current
+    void give(int dev, void* p, size_t bytes)
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            if (held[dev & 63] + bytes <= kMaxHeld) {
+                blocks[dev & 63].emplace(bytes, p);
+                held[dev & 63] += bytes;
+                return;
+            }
+        }
+        cudaFree(p);
+    }
+};
+BandBlockCache g_band_blocks;
+
+size_t
+band_bytes(const b2r_mipchain_banded& c, int level, int g)
+{
+    const auto& L = c.levels[level];
+    const auto& B = L.bands[g];
+    return size_t(B.a1 - B.a0) * L.w * c.nch * 4;
+}
 
 b2r_image
 level_image(const b2r_mipchain_banded& c, int level, int g)
@@ -197,6 +246,8 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
             for (int g = 0; g < G; ++g)
                 if (c->levels[k].bands[g].px) {
                     cudaSetDevice(c->devices[g]);
+                    // error path: work may still be in flight on the block, so
+                    // it is freed (which waits), not handed to the cache
                     cudaFree(c->levels[k].bands[g].px);
                 }
         for (int g = 0; g < G; ++g)
@@ -272,7 +323,8 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
             if (B.a1 <= B.a0)
                 continue;
             cudaSetDevice(c->devices[g]);
-            if (cudaMalloc(&B.px, size_t(B.a1 - B.a0) * L.w * nch * 4) != cudaSuccess) {
+            B.px = g_band_blocks.take(c->devices[g], band_bytes(*c, k, g));
+            if (!B.px && cudaMalloc(&B.px, band_bytes(*c, k, g)) != cudaSuccess) {
                 cudaGetLastError();
                 set_err(err, errlen, "mipchain_banded: out of device memory (level %d, device %d)",
                         k, c->devices[g]);
@@ -303,6 +355,8 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
         }
     };
 
+    auto t_setup = std::chrono::steady_clock::now();
+    c->setup_ms  = std::chrono::duration<float, std::milli>(t_setup - t_begin).count();
     // ---- phase A (one host thread per device): upload the device's rows of
     // level 0 and build + upload the tables of all its levels -----------------
     std::vector<int> trc(G, B2R_OK);
@@ -368,6 +422,8 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
             return destroy(trc[g]);
         }
 
+    auto t_a      = std::chrono::steady_clock::now();
+    c->phase_a_ms = std::chrono::duration<float, std::milli>(t_a - t_setup).count();
     // ---- phase B: the level loop, issued level by level ---------------------
     // level 0's rows came from the host, so nothing is pushed for it; from
     // level 1 on, the owner of a row pushes it to every device that holds it
@@ -445,6 +501,7 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
     }
     auto t_end  = std::chrono::steady_clock::now();
     c->total_ms = std::chrono::duration<float, std::milli>(t_end - t_begin).count();
+    c->phase_b_ms = std::chrono::duration<float, std::milli>(t_end - t_a).count();
     for (int g = 0; g < G; ++g) {
         cudaSetDevice(c->devices[g]);
         float up = 0, ch = 0;
@@ -556,6 +613,9 @@ b2r_mipchain_banded_ms(const b2r_mipchain_banded* c, int what)
     case 1: return c->upload_ms;  // level-0 upload, device events, max over devices
     case 2: return c->chain_ms;   // level loop incl. pushes, device events, max over devices
     case 3: return float(c->halo_bytes);
+    case 4: return c->setup_ms;    // host: peer access, streams, band buffers, events
+    case 5: return c->phase_a_ms;  // host: per-device upload threads + tables
+    case 6: return c->phase_b_ms;  // host: level loop issue + final synchronise
     }
     return 0.0f;
 }
@@ -567,12 +627,16 @@ b2r_mipchain_banded_destroy(b2r_mipchain_banded* c)
         return;
     int prev = 0;
     cudaGetDevice(&prev);
-    for (auto& L : c->levels)
+    for (size_t k = 0; k < c->levels.size(); ++k) {
+        auto& L = c->levels[k];
         for (size_t g = 0; g < L.bands.size(); ++g)
             if (L.bands[g].px) {
                 cudaSetDevice(c->devices[g]);
-                cudaFree(L.bands[g].px);
+                // the chain's work is complete (create synchronised its streams;
+                // downloads are synchronous), the block can go back for reuse
+                g_band_blocks.give(c->devices[g], L.bands[g].px, band_bytes(*c, (int)k, (int)g));
             }
+    }
     for (size_t g = 0; g < c->streams.size(); ++g)
         if (c->streams[g]) {
             cudaSetDevice(c->devices[g]);
