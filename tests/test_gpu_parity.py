@@ -884,26 +884,34 @@ def test_overscan_interior_fused_frame_exact(oiio, oracle, st):
 
 # ---- b2r_resize_batch: many frames of one shape in one launch -------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("st,dt,nch,filt,sshape,dshape", [
-    ("uint16", "uint16", 3, "lanczos3", (432, 768), (216, 384)),
-    ("float", "float", 4, "lanczos3", (600, 1100), (300, 550)),
-    ("half", "half", 4, "blackman-harris", (400, 640), (200, 320)),
-    ("float", "float", 3, "mitchell", (300, 500), (170, 260)),
-    ("uint8", "uint8", 3, "mitchell", (90, 160), (360, 640)),      # expand kernel: frame by frame
+@pytest.mark.parametrize("st,dt,nch,filt,sshape,dshape,nfr", [
+    ("uint16", "uint16", 3, "lanczos3", (432, 768), (216, 384), 5),
+    ("float", "float", 4, "lanczos3", (600, 1100), (300, 550), 5),
+    ("half", "half", 4, "blackman-harris", (400, 640), (200, 320), 5),
+    ("float", "float", 3, "mitchell", (300, 500), (170, 260), 5),
+    ("uint8", "uint8", 3, "mitchell", (90, 160), (360, 640), 5),      # expand kernel: frame by frame
+    # enough frames that the schedule search gives every frame ONE band (no halo rows)
+    ("uint16", "uint16", 3, "lanczos3", (432, 768), (216, 384), 80),
+    ("uint8", "uint8", 4, "lanczos3", (432, 768), (216, 384), 150),
+    ("half", "float", 4, "lanczos3", (432, 1100), (216, 550), 37),
 ])
-def test_resize_batch_equals_single_frames(oiio, st, dt, nch, filt, sshape, dshape):
+def test_resize_batch_equals_single_frames(oiio, st, dt, nch, filt, sshape, dshape, nfr):
     """Frames of one shape through ONE persistent launch give exactly what
     one call per frame gives (and the shapes the stream kernel does not take
-    fall back to frame-by-frame)."""
+    fall back to frame-by-frame).  The band count of the batch plan differs
+    from the single-frame plan's (fused_plan.cpp searches it per batch size):
+    the results must not."""
     import torch
     IBA = oiio.ImageBufAlgo
-    nfr = 5
 
     def T(a):
         t = torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a)
         return (t.view(torch.uint16) if a.dtype == np.uint16 else t).cuda()
-    srcs = [T(synth.image(sshape[1], sshape[0], nch, _np_dtype(st), seed=300 + i))
-            for i in range(nfr)]
+    base = [T(synth.image(sshape[1], sshape[0], nch, _np_dtype(st), seed=300 + i))
+            for i in range(min(nfr, 5))]
+    def rolled(t, k):  # a different picture per frame (uint16 rolls as bytes)
+        return torch.roll(t.view(torch.uint8), k, 0).contiguous().view(t.dtype)
+    srcs = [base[i] if i < len(base) else rolled(base[i % len(base)], 7 * i) for i in range(nfr)]
     tdt = {"uint8": torch.uint8, "uint16": torch.uint16, "half": torch.float16,
            "float": torch.float32}[dt]
     one = [torch.zeros((dshape[0], dshape[1], nch), dtype=tdt, device="cuda") for _ in range(nfr)]
@@ -916,4 +924,4 @@ def test_resize_batch_equals_single_frames(oiio, st, dt, nch, filt, sshape, dsha
     for a, b in zip(one, many):
         assert torch.equal(a.view(torch.uint8), b.view(torch.uint8))
     if st != "uint8":
-        assert IBA.last_report.kernels_launched == 1  # one launch for the five frames
+        assert IBA.last_report.kernels_launched == 1  # one launch for all the frames
