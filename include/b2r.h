@@ -388,6 +388,10 @@ B2R_API int b2r_source_rows(const b2r_image* dst, const b2r_image* src,
  * (maketx:forcefloat), windows zeroed per level (:848-879).
  * filtername "box" takes the resize_block path (:881-887 -> :141-334), any
  * other name the resize path with setup_filter's width rule (:38-66).
+ * Pass level 0 with its REAL windows: like write_mipmap the chain sets its
+ * display window to its data window (:876-877) and keeps its origin for the
+ * first resize; a level 0 that is offset, cropped or overscanned
+ * (orig_was_overscan, :700-703) takes the resize path even for "box" (:881).
  * clamp_half != 0 clamps each level to +-HALF_MAX and, like
  * ImageBufAlgo::clamp(..., clampalpha01=true), the alpha channel
  * (alpha_channel >= 0) to [0,1] (:943-945). */
@@ -489,7 +493,8 @@ B2R_API void b2r_tileset_destroy(b2r_tileset* ts);
  * waits for them on the device (no NCCL, no host synchronisation per level).
  * Levels whose bands would be shorter than 64 rows are gathered on devices[0]
  * and finished there.  Every level equals the single-device chain bit for bit.
- * mip->sharpen and highlight compensation are not supported here.
+ * mip->sharpen, highlight compensation and a level 0 with a non-zero origin
+ * or display window != data window are not supported here.
  * devices == NULL: devices 0 .. ndevices-1. */
 typedef struct b2r_mipchain_banded b2r_mipchain_banded;
 B2R_API int b2r_mipchain_create_banded(b2r_mipchain_banded** chain,

@@ -2487,7 +2487,14 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
     sub.cuda_stream = (void*)stream;
     // maketx --hicomp: only the filtered branch is wrapped (:889-935)
     // sharpening takes the filtered branch even for "box" (:880-881)
-    const bool box_path = fname == "box" && !(sharpen > 0.0f);
+    // ... and so does an image that came in offset, cropped or overscanned
+    // (orig_was_overscan, :700-703, :881): its levels go through resize() with
+    // the "box" Filter2D, level 0 keeping its origin with display == data
+    // (img->set_full, :876-877)
+    const bool orig_was_overscan
+        = level0->x || level0->y || level0->full_x || level0->full_y
+          || level0->full_width != level0->width || level0->full_height != level0->height;
+    const bool box_path = fname == "box" && !(sharpen > 0.0f) && !orig_was_overscan;
     const bool hicomp   = opt && opt->highlightcomp && !box_path
                         && chain->levels.size() > 1;
     const bool scratch_needed = (hicomp && sharpen > 0.0f)
@@ -2535,6 +2542,12 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
             S.memspace = B2R_MEM_DEVICE;
             S.device   = device;
             b2r_image D = S;
+            if (li == 1) {
+                // level 0 keeps its pixel origin; its display window is set
+                // to its data window (:876-877).  Levels >= 1 sit at the origin.
+                S.x = S.full_x = level0->x;
+                S.y = S.full_y = level0->y;
+            }
             D.pixels    = lv.px;
             D.width = D.full_width = sw;
             D.height = D.full_height = sh;

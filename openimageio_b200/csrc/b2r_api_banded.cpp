@@ -202,6 +202,14 @@ b2r_mipchain_create_banded(b2r_mipchain_banded** out, const b2r_image* level0,
         }
         c->devices.push_back(d);
     }
+    if (level0->x || level0->y || level0->full_x || level0->full_y
+        || level0->full_width != level0->width || level0->full_height != level0->height) {
+        // orig_was_overscan (maketexture.cpp:700-703): level 0 keeps its origin
+        // through the first resize; the bands here are crops of zero-origin levels
+        set_err(err, errlen, "mipchain_banded: level 0 must have a zero origin and "
+                             "display window == data window");
+        return B2R_ERR_UNSUPPORTED;
+    }
     const int G   = ndevices;
     const int nch = level0->nchannels;
     c->nch        = nch;

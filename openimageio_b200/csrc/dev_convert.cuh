@@ -72,27 +72,33 @@ quant_u16(float v)
     return u;
 }
 
-// The same quantiser for two values with the multiply and the add contracted
-// into one packed FMA (expand kernel: the quantiser was a third of its
-// instructions).  One rounding instead of two; see the call site.
+// The same quantiser for two values WITHOUT the float -> int conversion unit
+// (expand kernel: an 8K uint8 frame is 100 M cvt instructions, and the XU pipe
+// they run on was the kernel's bottleneck -- sm__inst_executed_pipe_xu at its
+// peak while issue slots and HBM idled).  v is clamped to [0, 1] by add.sat
+// (NaN -> 0, like the cvt), then ONE packed FMA computes v * mx + 2^23: the
+// sum lies in [2^23, 2^24), where a float's ulp is 1, so the FMA's rounding IS
+// the rounding to an integer and the low mantissa bits are the result.  It
+// rounds v * mx to nearest, ties to even, where the reference truncates
+// v * mx + 0.5 (ties up): v * mx is an exact tie only for v = 0.5 with mx odd
+// (127.5 -> 128, 32767.5 -> 32768: the even neighbour is the upper one), so
+// the two agree wherever the reference's own two roundings (multiply, then
+// add) do not move the value across an integer -- inside the +-1 LSB this
+// kernel is held to; the exact kernel keeps the reference's sequence.
+__device__ __forceinline__ float
+sat01(float v)
+{
+    float r;
+    asm("add.sat.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+    return r;
+}
+// returns the two floats 2^23 + round(v * mx); their low 8 / 16 bits are the
+// quantised values
 __device__ __forceinline__ float2
-quant2_fma(float a, float b, float mx)
+quant2_magic(float a, float b, float mx)
 {
-    return __ffma2_rn(make_float2(a, b), make_float2(mx, mx), make_float2(0.5f, 0.5f));
-}
-__device__ __forceinline__ unsigned
-cvt_u8(float s)
-{
-    unsigned u;
-    asm("cvt.rzi.u8.f32 %0, %1;" : "=r"(u) : "f"(s));
-    return u;
-}
-__device__ __forceinline__ unsigned
-cvt_u16(float s)
-{
-    unsigned u;
-    asm("cvt.rzi.u16.f32 %0, %1;" : "=r"(u) : "f"(s));
-    return u;
+    return __ffma2_rn(make_float2(sat01(a), sat01(b)), make_float2(mx, mx),
+                      make_float2(8388608.0f, 8388608.0f));
 }
 
 // rangecompress / rangeexpand of one value (imagebufalgo_pixelmath.cpp:560-735)

@@ -139,17 +139,14 @@ store_group(unsigned char* dp, int align, int nvalid, const float (&o)[N])
                     reinterpret_cast<float*>(dp)[i] = o[i];
             }
         } else if (DT == BT_UINT8) {
-            // v * 255 + 0.5 as ONE packed FMA per element pair (a single
-            // rounding where the reference's two can differ by an ulp just
-            // below an integer: inside the +-1 LSB this kernel is held to --
-            // the exact kernel keeps the two roundings), then the saturating cvt
+            // clamp + one packed FMA per pair, no cvt (dev_convert.cuh: quant2_magic)
             unsigned w[N / 4];
 #pragma unroll
             for (int i = 0; i < N / 4; ++i) {
-                const float2 a = quant2_fma(o[4 * i], o[4 * i + 1], 255.0f);
-                const float2 b = quant2_fma(o[4 * i + 2], o[4 * i + 3], 255.0f);
-                unsigned lo = __byte_perm(cvt_u8(a.x), cvt_u8(a.y), 0x0040);
-                unsigned hi = __byte_perm(cvt_u8(b.x), cvt_u8(b.y), 0x0040);
+                const float2 a = quant2_magic(o[4 * i], o[4 * i + 1], 255.0f);
+                const float2 b = quant2_magic(o[4 * i + 2], o[4 * i + 3], 255.0f);
+                unsigned lo = __byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x0040);
+                unsigned hi = __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x0040);
                 w[i]        = __byte_perm(lo, hi, 0x5410);
             }
             if constexpr (N == 16) {
@@ -169,8 +166,8 @@ store_group(unsigned char* dp, int align, int nvalid, const float (&o)[N])
                     __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
                     w[i]      = *reinterpret_cast<unsigned*>(&h);
                 } else {
-                    const float2 a = quant2_fma(o[2 * i], o[2 * i + 1], 65535.0f);
-                    w[i] = __byte_perm(cvt_u16(a.x), cvt_u16(a.y), 0x5410);
+                    const float2 a = quant2_magic(o[2 * i], o[2 * i + 1], 65535.0f);
+                    w[i] = __byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x5410);
                 }
             }
             if (N % 8 == 0 && align == 16) {

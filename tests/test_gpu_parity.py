@@ -882,6 +882,40 @@ def test_overscan_interior_fused_frame_exact(oiio, oracle, st):
         assert not np.array_equal(got[60:160, 80:240], g2[60:160, 80:240])
 
 
+# ---- MIP chain of a level 0 that is offset / cropped (orig_was_overscan) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("filt", ["box", "lanczos3"])
+@pytest.mark.parametrize("origin,full", [((37, 11), None), ((0, 0), (0, 0, 200, 150)),
+                                         ((-6, -4), (0, 0, 180, 120))])
+def test_mip_chain_offset_level0(oiio, oracle, filt, origin, full):
+    """write_mipmap sends an image whose windows are not plain (non-zero origin,
+    crop, overscan: orig_was_overscan, maketexture.cpp:700-703) through
+    resize() with the named filter even for "box" (:881), level 0 keeping its
+    origin with display == data (:876-877); levels >= 1 sit at the origin."""
+    w, h = 192, 128
+    lvl0 = synth.image(w, h, 4, np.float32, seed=77)
+    spec = oiio.ImageSpec(w, h, 4, "float")
+    spec.x, spec.y = origin
+    if full is not None:
+        spec.full_x, spec.full_y, spec.full_width, spec.full_height = full
+    else:
+        spec.full_x, spec.full_y, spec.full_width, spec.full_height = origin[0], origin[1], w, h
+    chain = oiio.MipChain(oiio.ImageBuf(lvl0, spec), filt)
+    # the oracle's loop, composed by hand with the reference's windows
+    big = oracle.Img(lvl0, x=origin[0], y=origin[1], full=(origin[0], origin[1], w, h))
+    lv = 1
+    while big.arr.shape[1] > 1 or big.arr.shape[0] > 1:
+        bh, bw, _ = big.arr.shape
+        small = np.empty((max(1, bh // 2), max(1, bw // 2), 4), np.float32)
+        oracle.resize(oracle.Img(small), big, filt)
+        got = chain.download(lv)
+        assert got.shape == small.shape
+        assert np.max(np.abs(got - small)) <= 1e-5 * lv, (lv, np.max(np.abs(got - small)))
+        big = oracle.Img(small)
+        lv += 1
+    assert lv == chain.nlevels
+
+
 # ---- b2r_resize_batch: many frames of one shape in one launch -------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("st,dt,nch,filt,sshape,dshape,nfr", [

@@ -3,7 +3,7 @@
 O=gpurun_out
 for wl in ${WLS:-c0 c2 c5 c1}; do
   for lib in base new; do
-    for bs in 0 1; do
+    for bs in ${BSS:-0 1}; do
       L=openimageio_b200/libb2r.so; [ $lib = base ] && L=openimageio_b200/libb2r_base.so
       B2R_LIBPATH=$PWD/$L B2R_BANDSEARCH=$bs timeout 300 python bench.py --workload $wl --steps 25 --no-cpu --e2e-steps 3 --no-configs --sustain-ms 0 ${EXTRA} > $O/r2_ab_${wl}_${lib}_$bs.json 2> $O/r2_ab_${wl}_${lib}_$bs.err
       python - <<PY
