@@ -129,6 +129,50 @@ dev_rangeexpand(float y)
     return copysignf(x, y);
 }
 
+// The same two curves for the FUSED highlight compensation of the stream kernel,
+// on the special-function unit: lg2.approx / ex2.approx (relative error 2^-22
+// each) and the two IEEE divisions as multiplications by reciprocals.  There
+// the curves run inside an issue-bound kernel -- libm's logf / expf and the
+// divisions cost ~25 / ~30 instructions per value against ~7 / ~8 here, the
+// difference between 0.32 ms and 0.16 ms for an 8K frame.  Error budget: the
+// argument of the log is >= 1 + c * 0.18 = 52, so lg2's relative error is
+// 2.4e-7 * 8 = 2e-6 in log2 units = 2.4e-7 in the compressed value; through
+// rangeexpand's exponent ((y - a) / b * log2 e) that is 1.9e-6, i.e. 1.3e-6
+// RELATIVE in the expanded value, plus ex2's own 2.4e-7 and the argument
+// rounding: ~2e-6 relative end to end (measured: tools/hicomp_probe.py), inside
+// north_star's 1e-5.  The stand-alone rangecompress / rangeexpand ops keep the
+// libm forms above.
+__device__ __forceinline__ float
+dev_rangecompress_fast(float x)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    const float absx = fabsf(x);
+    if (absx <= x1)
+        return x;
+    float l2;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(fmaf(c, absx, 1.0f)));
+    return copysignf(fmaf(b * 0.693147180559945309f, l2, a), x);
+}
+
+__device__ __forceinline__ float
+dev_rangeexpand_fast(float y)
+{
+    const float x1 = 0.18f, a = -0.54576885700225830078f;
+    const float b = 0.18351669609546661377f, c = 284.3577880859375f;
+    const float absy = fabsf(y);
+    if (absy <= x1)
+        return y;
+    const float k = 1.44269504088896340736f / b;  // log2(e) / b
+    float xi;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(xi) : "f"(fmaf(absy, k, -a * k)));
+    const float rc = 1.0f / c;
+    float x = fmaf(xi, rc, -rc);
+    if (x < x1)  // the reference's second branch (imagebufalgo_pixelmath.cpp:596-601)
+        x = fmaf(-xi, rc, -rc);
+    return copysignf(x, y);
+}
+
 __device__ __forceinline__ bool
 nonfinite(float v)
 {

@@ -351,8 +351,8 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
                 if (!((p.hc_skip >> c) & 1)) {
-                    *fa[c] = dev_rangeexpand(*fa[c]);
-                    *fb[c] = dev_rangeexpand(*fb[c]);
+                    *fa[c] = dev_rangeexpand_fast(*fa[c]);
+                    *fb[c] = dev_rangeexpand_fast(*fb[c]);
                 }
         }
         stream_store_pair<NCH>(p, dp, des, aA, aB, has_b);
@@ -532,13 +532,13 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
 #pragma unroll
                     for (int h = 0; h < E2; ++h) {
                         if (hcmask & (1u << (4 * h)))
-                            v[h].x = dev_rangecompress(v[h].x);
+                            v[h].x = dev_rangecompress_fast(v[h].x);
                         if (hcmask & (2u << (4 * h)))
-                            v[h].y = dev_rangecompress(v[h].y);
+                            v[h].y = dev_rangecompress_fast(v[h].y);
                         if (hcmask & (4u << (4 * h)))
-                            v[h].z = dev_rangecompress(v[h].z);
+                            v[h].z = dev_rangecompress_fast(v[h].z);
                         if (hcmask & (8u << (4 * h)))
-                            v[h].w = dev_rangecompress(v[h].w);
+                            v[h].w = dev_rangecompress_fast(v[h].w);
                     }
                 }
             };
