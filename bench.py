@@ -426,6 +426,27 @@ class Harness:
             ms_s, t0, t1 = self.time_steps(step_dev, steps)
             out["sustained_ms_per_step"] = self.max_over_ranks(ms_s)
             out["sustained_clocks"] = sampler.window(t0, t1) if sampler else None
+            # the same power state's copy roofline: MEASURED_PEAKS.json's recipe
+            # (b.copy_(a), read + write bytes) timed right behind the load
+            try:
+                n = 1 << 29
+                a = torch.empty(n, dtype=torch.bfloat16, device=self.dev)
+                b = torch.empty_like(a)
+                t_ramp = time.perf_counter()
+                while (time.perf_counter() - t_ramp) * 1e3 < sustain_ms:
+                    b.copy_(a)
+                    torch.cuda.synchronize()
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(10):
+                    b.copy_(a)
+                e1.record()
+                torch.cuda.synchronize()
+                out["sustained_copy_gbs"] = 2 * n * 2 * 10 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+                del a, b
+            except Exception:
+                out["sustained_copy_gbs"] = None
         self.launches += (warmup + steps)  # one launch per batch of nfr frames
 
         # end to end (host buffers through the public API)
@@ -759,6 +780,11 @@ def main():
                 "frac": head["sustained_frac"],
                 "frac_of_nominal_8tbs": head["sustained_frac"] * H.peak / 8000.0,
                 "after_ms_of_load": args.sustain_ms,
+                # a plain device copy timed in the same power state (after the same
+                # load): the sustained twin of MEASURED_PEAKS.json's burst figure
+                "copy_gbs_same_state": r.get("sustained_copy_gbs"),
+                "frac_of_copy_same_state": (head["sustained_frac"] * H.peak / r["sustained_copy_gbs"]
+                                            if r.get("sustained_copy_gbs") else None),
                 "clocks": r.get("sustained_clocks")}
         if configs:
             line["configs"] = configs

@@ -414,7 +414,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     constexpr int NSYNC = G::NVT + STREAM_HTHREADS;  // threads on the V <-> H barriers
     constexpr bool FP   = (ST == ST_FLOAT || ST == ST_HALF);
     // stage-specialised V pass (see the V warps below)
-    constexpr bool SPEC = W2 == 2 && (!FP || VK <= 4);
+    constexpr bool JIT  = W2 == 2 && FP && VK == 6;
+    constexpr bool SPEC = W2 == 2 && (!FP || VK <= 6);
     static_assert(!HC || ST == ST_FLOAT, "highlight compensation is fused for float sources");
     static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
 
@@ -590,19 +591,28 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             for (int rbase = 0; rbase < band.nrows; rbase += ROWS) {
                 const unsigned char* sb = stream_smem + stage * S::STAGE_B;
                 mbar_wait(bars + 8 * stage, phase);
-                // the stage's rows of this thread
-                uint4 raw[ROWS];
-#pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
+                // The stage's rows of this thread.  JIT (float / half rings of 6-8
+                // rows, where the accumulators leave no room): a row is loaded
+                // where it is used -- the specialised stage code is straight-line,
+                // so ptxas hoists the loads as far as the registers allow; the
+                // other instantiations fetch the whole stage up front.
+                auto load_raw_at = [&](int j) -> uint4 {
                     const unsigned char* a = sb + toff + j * S::BOX_ROWB;
                     if (EPT * es == 16)
-                        raw[j] = *reinterpret_cast<const uint4*>(a);
+                        return *reinterpret_cast<const uint4*>(a);
                     else if (EPT * es == 8) {
                         uint2 u = *reinterpret_cast<const uint2*>(a);
-                        raw[j]  = make_uint4(u.x, u.y, 0u, 0u);
+                        return make_uint4(u.x, u.y, 0u, 0u);
                     } else
-                        raw[j] = make_uint4(*reinterpret_cast<const unsigned*>(a), 0u, 0u, 0u);
+                        return make_uint4(*reinterpret_cast<const unsigned*>(a), 0u, 0u, 0u);
+                };
+                uint4 raw[JIT ? 1 : ROWS];
+                if (!JIT) {
+#pragma unroll
+                    for (int j = 0; j < ROWS; ++j)
+                        raw[JIT ? 0 : j] = load_raw_at(j);
                 }
+                auto load_raw = [&](int j) -> uint4 { return JIT ? load_raw_at(j) : raw[JIT ? 0 : j]; };
                 // ring-table row j of the stage (broadcast loads)
                 auto load_w = [&](int j, float (&w)[WROW]) {
 #pragma unroll
@@ -666,10 +676,12 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                 // specialised on (shift at entry, completion mask): no per-row
                 // flag decoding, no shift / completion branches; float / half
                 // stages are screened for Inf/NaN as a whole first.  Measured:
-                // it pays for integer sources and for rings of <= 4 rows (C2
-                // 96.7 -> 85.8 us, C5 36.0 -> 32.2 us); float / half rings of
-                // 6-8 rows lose (C0 115.7 -> 126 us, the screening delays the
-                // first FMA of a stage) and keep the row-by-row path (SPEC).
+                // C2 96.7 -> 85.8 us, C5 36.0 -> 32.2 us.  Float / half rings of
+                // 6 rows only fit the specialised code in 64 registers when the
+                // stage's rows are loaded where they are used (JIT) -- with the
+                // rows held across the stage ptxas spills and C0 loses 10 us;
+                // with JIT it gains 0.6 %.  Rings of 8 rows spill either way and
+                // keep the row-by-row path.
                 int sdesc = 0x100;
                 if (SPEC)
                     sdesc = __float_as_int(
@@ -687,8 +699,9 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                         const __half2 z = q;
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
-                            q = __hfma2(*reinterpret_cast<const __half2*>(&raw[j].x), z, q);
-                            q = __hfma2(*reinterpret_cast<const __half2*>(&raw[j].y), z, q);
+                            const uint4 rr = load_raw(j);
+                            q = __hfma2(*reinterpret_cast<const __half2*>(&rr.x), z, q);
+                            q = __hfma2(*reinterpret_cast<const __half2*>(&rr.y), z, q);
                         }
                         const unsigned qb = *reinterpret_cast<const unsigned*>(&q);
                         slow = slow || __any_sync(0xffffffffu, (qb & 0x7fff7fffu) != 0u);
@@ -697,7 +710,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
                             float4 v[E2];
-                            stream_convert<ST, E2>(raw[j], v);
+                            stream_convert<ST, E2>(load_raw(j), v);
 #pragma unroll
                             for (int h = 0; h < E2; ++h)
                                 q += (v[h].x + v[h].y) + (v[h].z + v[h].w);
@@ -719,7 +732,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                             float w[WROW];
                             load_w(j, w);
                             float4 v[E2];
-                            load_values(raw[j], v);
+                            load_values(load_raw(j), v);
                             fma_row(w, v, shifted);
                             if ((C >> j) & 1) {
                                 const int info = __float_as_int(w[WROW - 1]);
@@ -758,7 +771,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
                     // 16 / 17: the (single) completing row opens / closes a batch
                     const int info = __float_as_int(w[WROW - 1]);
                     float4 v[E2];
-                    load_values(raw[j], v);
+                    load_values(load_raw(j), v);
                     bool bad = false;
                     if (FP) {
                         float q = 0.0f;

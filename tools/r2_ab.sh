@@ -10,7 +10,8 @@ for wl in ${WLS:-c0 c2 c5 c1}; do
 import json
 try:
     d=json.loads(open("$O/r2_ab_${wl}_${lib}_$bs.json").read().strip().splitlines()[-1])
-    print("$wl lib=$lib search=$bs", "us/frame %.1f" % d["roofline"]["launch_us"], "frac %.3f" % d["roofline"]["frac"], "same", d["device_equals_host_result"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
+    s=d.get("sustained") or {}
+    print("$wl lib=$lib search=$bs", "us/frame %.1f" % d["roofline"]["launch_us"], "frac %.3f" % d["roofline"]["frac"], "sustained %s %s" % (s.get("launch_us"), (s.get("clocks") or {}).get("sm_mhz")), "same", d["device_equals_host_result"], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 except Exception as e:
     print("$wl $lib $bs failed", e)
 PY
