@@ -616,6 +616,7 @@ class _IBA:
     ImageBuf (py_imagebufalgo.cpp:1470-1560)."""
 
     last_report = None
+    force_report = False
 
     # ---- resize -----------------------------------------------------------
     def resize(self, *args, filtername="", filterwidth=0.0, roi=None,
@@ -688,7 +689,9 @@ class _IBA:
                      src.spec_.alpha_channel, src.spec_.z_channel)
         rep = Report()
         err = C.create_string_buffer(512)
-        want_report = not (dst.on_device and src.on_device)
+        # device-resident calls skip the report (it costs two events and a
+        # synchronise) unless force_report is set (tests, probes)
+        want_report = self.force_report or not (dst.on_device and src.on_device)
         if filterptr is not None:
             rc = L.b2r_resize_filter(C.byref(d), C.byref(s), filterptr._h,
                                      C.byref(r), C.byref(o),

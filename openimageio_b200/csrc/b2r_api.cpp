@@ -608,9 +608,15 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     // The same split serves a source with MORE channels than the destination
     // (resize_ reads the first dst.nchannels of them): the group copy drops
     // the extra ones.
-    if ((nch > 4 || src.nchannels > nch) && filter.separable() && path != B2R_PATH_EXACT
-        && !(opt && opt->reserved[0]) && src.xstride == (int64_t)src.nchannels * ses
-        && dst.xstride == (int64_t)nch * des) {
+    // ... and images whose pixels are not contiguous in x (a channel sub-view
+    // of a wider buffer): the group copy packs them, so they no longer fall to
+    // the exact kernel (a host DESTINATION with gaps between its pixels is
+    // left out: its rows are staged whole, and the gaps must survive).
+    const bool src_gaps = src.xstride != (int64_t)src.nchannels * ses;
+    const bool dst_gaps = dst.xstride != (int64_t)nch * des;
+    if ((nch > 4 || src.nchannels > nch || src_gaps || dst_gaps) && filter.separable()
+        && path != B2R_PATH_EXACT && !(opt && opt->reserved[0])
+        && !(dst_gaps && dmem == B2R_MEM_HOST) && !(src_gaps && smem == B2R_MEM_HOST)) {
         void *s_all = nullptr, *d_all = nullptr, *ts = nullptr, *td = nullptr;
         auto cleanup = [&]() {
             for (void* p : { s_all, d_all, ts, td })

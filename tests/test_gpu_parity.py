@@ -843,6 +843,36 @@ def test_source_with_more_channels_than_destination(oiio, oracle):
     assert oiio.ImageBufAlgo.last_report.path_used == oiio.PATH_FUSED
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("st", ["float", "uint8", "half"])
+def test_device_views_with_gaps_between_pixels(oiio, oracle, st):
+    """Device images whose pixels are not contiguous in x (channel sub-views of
+    wider buffers, on either side) are packed by the channel-group copy and run
+    the fused path instead of the single-pass exact kernel; the bytes between
+    the destination's pixels are left alone."""
+    import torch
+    tdt = {"float": torch.float32, "uint8": torch.uint8, "half": torch.float16}[st]
+    wide = synth.image(300, 200, 8, _np_dtype(st), seed=410)       # 8 channels, use 1..4
+    src_view = torch.from_numpy(wide).cuda()[..., 1:5]
+    assert not src_view.is_contiguous()
+    canvas = torch.full((100, 150, 6), 7, dtype=tdt, device="cuda")  # 6 channels, write 2..5
+    dst_view = canvas[..., 2:6]
+    D, S = oiio.ImageBuf(dst_view), oiio.ImageBuf(src_view)
+    oiio.ImageBufAlgo.force_report = True
+    try:
+        assert oiio.ImageBufAlgo.resize(D, S, filtername="lanczos3"), D.geterror()
+    finally:
+        oiio.ImageBufAlgo.force_report = False
+    torch.cuda.synchronize()
+    rep = oiio.ImageBufAlgo.last_report
+    assert rep.path_used == oiio.PATH_FUSED and rep.kernels_launched >= 3  # pack, resize, unpack
+    ref = np.zeros((100, 150, 4), _np_dtype(st))
+    oracle.resize(oracle.Img(ref), oracle.Img(np.ascontiguousarray(wide[..., 1:5])), "lanczos3")
+    got = canvas.cpu().numpy()
+    check(np.ascontiguousarray(got[..., 2:6]), ref)
+    assert np.all(got[..., :2] == 7)     # the gap channels are untouched
+
+
 @pytest.mark.parametrize("st", ["float", "uint8"])
 def test_overscan_interior_fused_frame_exact(oiio, oracle, st):
     """A source whose data window extends beyond its display window: device
