@@ -197,6 +197,28 @@ struct DeviceGuard {
 };
 
 
+// Runs at every exit of an entry point: staging blocks that are still set go
+// back to the pool (stream-ordered), events that are still set are destroyed.
+// The normal path frees / destroys them itself and clears the variables.
+struct ScopeCleanup {
+    cudaStream_t stream;
+    void** blocks[3];
+    cudaEvent_t* events[2];
+    ~ScopeCleanup()
+    {
+        for (void** b : blocks)
+            if (b && *b) {
+                cudaFreeAsync(*b, stream);
+                *b = nullptr;
+            }
+        for (cudaEvent_t* e : events)
+            if (e && *e) {
+                cudaEventDestroy(*e);
+                *e = nullptr;
+            }
+    }
+};
+
 // Host<->device staging shared by the stencil entry points: the whole source
 // data window goes up (a stencil may read any of it), the dst ROI comes back.
 struct StencilIO {
@@ -335,8 +357,9 @@ struct StencilIO {
             if (report)
                 report->d2h_bytes += (int64_t)drowbytes * roi_h;
         }
+        const bool staged = dst_alloc || src_alloc || extra_alloc;
         release();
-        if (dst_alloc || src_alloc || extra_alloc || report)
+        if (staged || report)
             CUDA_TRY(cudaStreamSynchronize(stream));
         if (report) {
             cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
@@ -388,9 +411,13 @@ struct StencilIO {
             cudaFreeAsync(src_alloc, stream);
         if (extra_alloc)
             cudaFreeAsync(extra_alloc, stream);
+        dst_alloc = src_alloc = extra_alloc = nullptr;
     }
+    // every early return (CUDA_TRY, argument errors after begin) ends here: the
+    // staging buffers go back to the pool stream-ordered, the events are destroyed
     ~StencilIO()
     {
+        release();
         if (ev0)
             cudaEventDestroy(ev0);
         if (ev1)

@@ -766,6 +766,29 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     size_t src_bytes = 0, dst_bytes = 0;
     bool src_staged = false, dst_staged = false, src_repitched = false;
     void* src_alloc = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // every early return below (CUDA_TRY and the explicit error paths) runs
+    // this: staging buffers back to the pool, stream-ordered; events destroyed.
+    // The normal exit frees them itself and clears the pointers first.
+    struct StagingGuard {
+        void*& src_alloc;
+        void*& ddst;
+        bool& dst_staged;
+        cudaEvent_t& ev0;
+        cudaEvent_t& ev1;
+        cudaStream_t stream;
+        ~StagingGuard()
+        {
+            if (src_alloc)
+                cudaFreeAsync(src_alloc, stream);
+            if (dst_staged && ddst)
+                cudaFreeAsync(ddst, stream);
+            if (ev0)
+                cudaEventDestroy(ev0);
+            if (ev1)
+                cudaEventDestroy(ev1);
+        }
+    } staging_guard { src_alloc, ddst, dst_staged, ev0, ev1, stream };
     if (smem == B2R_MEM_HOST) {
         if (src.xstride != (int64_t)src.nchannels * ses) {
             set_err(err, errlen, "host source pixels must be contiguous in x");
@@ -812,8 +835,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     if (dmem == B2R_MEM_HOST) {
         if (dst.xstride != (int64_t)dst.nchannels * des) {
             set_err(err, errlen, "host destination pixels must be contiguous in x");
-            if (src_alloc)
-                cudaFreeAsync(src_alloc, stream);
             return B2R_ERR_UNSUPPORTED;
         }
         // stage only the ROI rectangle
@@ -829,7 +850,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         dstd.ystride = (int64_t)dpitch;
     }
 
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool timed = report != nullptr && !(opt && opt->reserved[1]);
     if (timed) {
         cudaEventCreate(&ev0);
@@ -877,10 +897,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     int epoch    = 0;
     if (path == B2R_PATH_FUSED && !fused_ok) {
         set_err(err, errlen, "resize: shape is not eligible for the fused kernel");
-        if (src_alloc)
-            cudaFreeAsync(src_alloc, stream);
-        if (dst_staged)
-            cudaFreeAsync(ddst, stream);
         return B2R_ERR_UNSUPPORTED;
     }
     const bool src_is_fp = src.basetype == B2R_FLOAT || src.basetype == B2R_HALF;
@@ -994,10 +1010,6 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         }
         if (!streamed && w2 != 1) {
             set_err(err, errlen, "resize: the stream kernel could not be launched");
-            if (src_alloc)
-                cudaFreeAsync(src_alloc, stream);
-            if (dst_staged)
-                cudaFreeAsync(ddst, stream);
             return B2R_ERR_CUDA;
         }
         if (!streamed)
@@ -1050,10 +1062,16 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
         && (dst_staged || src_staged))
         CUDA_TRY(cudaMemcpyAsync(&redo, flag, sizeof(int),
                                  cudaMemcpyDeviceToHost, stream));
-    if (src_alloc)
-        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
-    if (dst_staged)
-        CUDA_TRY(cudaFreeAsync(ddst, stream));
+    if (src_alloc) {
+        void* p   = src_alloc;
+        src_alloc = nullptr;
+        CUDA_TRY(cudaFreeAsync(p, stream));
+    }
+    if (dst_staged) {
+        void* p = ddst;
+        ddst    = nullptr;
+        CUDA_TRY(cudaFreeAsync(p, stream));
+    }
     if (dst_staged || src_staged || timed)
         CUDA_TRY(cudaStreamSynchronize(stream));
     if (report) {
@@ -1068,11 +1086,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             report->kernel_ms = ms;
         }
     }
-    if (ev0)
-        cudaEventDestroy(ev0);
-    if (ev1)
-        cudaEventDestroy(ev1);
-    return B2R_OK;
+    return B2R_OK;  // staging_guard destroys the events
 }
 
 // ---------------------------------------------------------------------------
@@ -1863,6 +1877,8 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
     void* dsrc = src.pixels;
     void* ddst = dst.pixels;
     void *src_alloc = nullptr, *dst_alloc = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ScopeCleanup cleanup { stream, { &src_alloc, &dst_alloc, nullptr }, { &ev0, &ev1 } };
     size_t dpitch = 0, drowbytes = 0;
     if (smem == B2R_MEM_HOST) {
         if (src.xstride != (int64_t)src.nchannels * ses) {
@@ -1895,8 +1911,6 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
     if (dmem == B2R_MEM_HOST) {
         if (dst.xstride != (int64_t)dst.nchannels * des) {
             set_err(err, errlen, "host destination pixels must be contiguous in x");
-            if (src_alloc)
-                cudaFreeAsync(src_alloc, stream);
             return B2R_ERR_UNSUPPORTED;
         }
         drowbytes = size_t(roi_w) * dst.xstride;
@@ -1918,7 +1932,6 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
         dstd.height  = roi_h;
         dstd.ystride = (int64_t)dpitch;
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool timed = report != nullptr;
     if (timed) {
         cudaEventCreate(&ev0);
@@ -1941,16 +1954,18 @@ range_impl(bool expand, const b2r_image* dst_in, const b2r_image* src_in, int us
                                    roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
-        CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
     }
-    if (src_alloc)
-        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
-    if (dst_alloc || src_alloc || timed)
+    const bool staged = dst_alloc || src_alloc;
+    for (void** b : { &dst_alloc, &src_alloc })
+        if (*b) {
+            void* q = *b;
+            *b      = nullptr;
+            CUDA_TRY(cudaFreeAsync(q, stream));
+        }
+    if (staged || timed)
         CUDA_TRY(cudaStreamSynchronize(stream));
     if (timed) {
         cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
         report->kernels_launched = 1;
     }
     return B2R_OK;

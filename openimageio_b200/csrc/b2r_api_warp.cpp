@@ -89,6 +89,8 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
     void* dsrc = src.pixels;
     void* ddst = dst.pixels;
     void *src_alloc = nullptr, *dst_alloc = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ScopeCleanup cleanup { stream, { &src_alloc, &dst_alloc, nullptr }, { &ev0, &ev1 } };
     size_t dpitch = 0, drowbytes = 0;
     if (smem == B2R_MEM_HOST) {
         if (src.xstride != (int64_t)src.nchannels * ses) {
@@ -109,8 +111,6 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
     if (dmem == B2R_MEM_HOST) {
         if (dst.xstride != (int64_t)dst.nchannels * des) {
             set_err(err, errlen, "host destination pixels must be contiguous in x");
-            if (src_alloc)
-                cudaFreeAsync(src_alloc, stream);
             return B2R_ERR_UNSUPPORTED;
         }
         drowbytes = size_t(roi_w) * dst.xstride;
@@ -132,7 +132,6 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
         dstd.height  = roi_h;
         dstd.ystride = (int64_t)dpitch;
     }
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     const bool timed = report != nullptr;
     if (timed) {
         cudaEventCreate(&ev0);
@@ -173,16 +172,18 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
                                    roi_h, stream));
         if (report)
             report->d2h_bytes += (int64_t)drowbytes * roi_h;
-        CUDA_TRY(cudaFreeAsync(dst_alloc, stream));
     }
-    if (src_alloc)
-        CUDA_TRY(cudaFreeAsync(src_alloc, stream));
-    if (dst_alloc || src_alloc || timed)
+    const bool staged = dst_alloc || src_alloc;
+    for (void** b : { &dst_alloc, &src_alloc })
+        if (*b) {
+            void* q = *b;
+            *b      = nullptr;
+            CUDA_TRY(cudaFreeAsync(q, stream));
+        }
+    if (staged || timed)
         CUDA_TRY(cudaStreamSynchronize(stream));
     if (timed) {
         cudaEventElapsedTime(&report->kernel_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
         report->kernels_launched = 1;
         report->path_used        = B2R_PATH_EXACT;
     }
