@@ -98,7 +98,14 @@ typedef struct b2r_options {
      * (ImageSpec::alpha_channel / z_channel), 0 = none. */
     int32_t highlightcomp;
     int32_t alpha_channel1, z_channel1;
-    int32_t reserved2;
+    /* Tolerance mode for the warp family (b2r_warp*, b2r_fit_exact's warp):
+     * 0 (default) accumulates `sum += w * pixel` as the reference's compiled
+     * code does, multiply and add rounded separately, so the footprint AND the
+     * sums follow its rounding; 1 lets the kernel use packed fused
+     * multiply-adds (a quarter of the floating-point instructions of an
+     * issue-bound kernel): results stay within 1e-5 relative / 1 LSB of the
+     * reference, the footprint arithmetic is unchanged. */
+    int32_t contract_fma;
 } b2r_options;
 
 /* Filled on request: what ran, for tests and benchmarks. */

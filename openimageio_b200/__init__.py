@@ -62,7 +62,7 @@ class _Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("path", C.c_int32),
                 ("cuda_stream", C.c_void_p), ("reserved", C.c_int32 * 4),
                 ("highlightcomp", C.c_int32), ("alpha_channel1", C.c_int32),
-                ("z_channel1", C.c_int32), ("reserved2", C.c_int32)]
+                ("z_channel1", C.c_int32), ("contract_fma", C.c_int32)]
 
 
 class _MipOptions(C.Structure):
@@ -592,8 +592,9 @@ def _ibaprep(roi, dst, src):
 
 
 def _options(device=0, path=PATH_AUTO, stream=None, highlightcomp=False,
-             alpha_channel=-1, z_channel=-1):
+             alpha_channel=-1, z_channel=-1, contract_fma=False):
     o = _Options()
+    o.contract_fma = 1 if contract_fma else 0
     o.device = device
     o.path = path
     o.cuda_stream = stream
@@ -617,6 +618,10 @@ class _IBA:
 
     last_report = None
     force_report = False
+    # b2r_options::contract_fma for the warp family (warp / rotate / fit exact /
+    # resize from-to): packed FMAs in the accumulation, results within 1e-5 /
+    # 1 LSB of the reference instead of its exact rounding sequence
+    contract_fma = False
 
     # ---- resize -----------------------------------------------------------
     def resize(self, *args, filtername="", filterwidth=0.0, roi=None,
@@ -1197,10 +1202,10 @@ class _IBA:
         r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin,
                  roi.chend)
         stream = _current_stream(dst) or _current_stream(src)
-        o = _options(device, PATH_AUTO, stream)
+        o = _options(device, PATH_AUTO, stream, contract_fma=self.contract_fma)
         err = C.create_string_buffer(512)
         rep = Report()
-        want_report = not (dst.on_device and src.on_device)
+        want_report = self.force_report or not (dst.on_device and src.on_device)
         if filterptr is not None:
             rc = L.b2r_warp_filter(C.byref(d), C.byref(s), m9, filterptr._h,
                                    int(wrap), 1 if edgeclamp else 0, C.byref(r),

@@ -157,6 +157,7 @@ warp_impl(const b2r_image* dst_in, const b2r_image* src_in, const float* M9,
     wp.filt_h       = fd.h;
     wp.wrap         = wrap;
     wp.edgeclamp    = edgeclamp ? 1 : 0;
+    wp.contract_fma = (opt && opt->contract_fma) ? 1 : 0;
     launch_warp(wp, stream);
     if (timed)
         cudaEventRecord(ev1, stream);

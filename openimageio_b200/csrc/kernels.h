@@ -364,6 +364,7 @@ struct WarpParams {
     float filt_param, filt_w, filt_h;
     int wrap;       // 0 default, 1 black, 2 clamp, 3 periodic, 4 mirror
     int edgeclamp;
+    int contract_fma;  // accumulate with packed FMAs (tolerance mode)
 };
 void
 launch_warp(const WarpParams& p, void* stream);

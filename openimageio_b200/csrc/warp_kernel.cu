@@ -144,7 +144,29 @@ load_px(const unsigned char* p, int n, float v[4])
         v[c] = (c < n) ? to_float<BT>(__ldg(q + c)) : 0.0f;
 }
 
-template<int BT, bool VEC>
+// sum += w * v over the four channels.  FMA = false: multiply, then add, each
+// rounded -- the reference's sequence (warp_ accumulates through filtered_sample's
+// `sum += w * pixel` compiled without contraction).  FMA = true (b2r_options::
+// contract_fma, "tolerance mode"): two packed fused multiply-adds -- a quarter
+// of the floating-point instructions of a kernel that is issue-bound on them;
+// results move by an ulp of the accumulator, inside north_star's 1e-5 / 1 LSB.
+template<bool FMA>
+__device__ __forceinline__ void
+accum4(float (&sum)[4], float w, const float (&v)[4])
+{
+    if (FMA) {
+        const float2 ww = make_float2(w, w);
+        const float2 lo = __ffma2_rn(ww, make_float2(v[0], v[1]), make_float2(sum[0], sum[1]));
+        const float2 hi = __ffma2_rn(ww, make_float2(v[2], v[3]), make_float2(sum[2], sum[3]));
+        sum[0] = lo.x, sum[1] = lo.y, sum[2] = hi.x, sum[3] = hi.y;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+    }
+}
+
+template<int BT, bool VEC, bool FMA>
 __global__ void __launch_bounds__(WARP_BX* WARP_BY)
 warp_kernel(const WarpParams p)
 {
@@ -239,9 +261,7 @@ warp_kernel(const WarpParams p)
                         const float w = __fmul_rn(wxc[i], wy);
                         float v[4];
                         load_px<BT, VEC>(sp, ncs, v);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                        accum4<FMA>(sum, w, v);
                         total_w = __fadd_rn(total_w, w);
                     }
                 }
@@ -293,9 +313,7 @@ warp_kernel(const WarpParams p)
                                                       + c0 * ses;
                             float v[4];
                             load_px<BT, VEC>(sp, ncs, v);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                sum[c] = __fadd_rn(sum[c], __fmul_rn(w, v[c]));
+                            accum4<FMA>(sum, w, v);
                         }
                         total_w = __fadd_rn(total_w, w);
                     }
@@ -427,10 +445,15 @@ template<int BT>
 void
 launch_bt(const WarpParams& p, bool vec, dim3 grid, cudaStream_t st)
 {
-    if (vec)
-        launch_pdl(warp_kernel<BT, true>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+    if (p.contract_fma) {
+        if (vec)
+            launch_pdl(warp_kernel<BT, true, true>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+        else
+            launch_pdl(warp_kernel<BT, false, true>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+    } else if (vec)
+        launch_pdl(warp_kernel<BT, true, false>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
     else
-        launch_pdl(warp_kernel<BT, false>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
+        launch_pdl(warp_kernel<BT, false, false>, grid, dim3(WARP_BX, WARP_BY), 0, st, p);
 }
 
 }  // namespace

@@ -298,3 +298,36 @@ def test_st_warp_errors(oiio):
     far.spec().x = 100
     assert IBA.st_warp(src, far).geterror() == \
         "ImageBufAlgo::st_warp : Output ROI does not intersect ST buffer."
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("st", ["float", "uint8", "half", "uint16"])
+def test_warp_tolerance_mode(oiio, oracle, st):
+    """b2r_options::contract_fma: the accumulation uses packed fused multiply-adds;
+    the footprint arithmetic is unchanged, so the result stays within north_star's
+    tolerance of the oracle (1e-5 of the value range for float, half an ulp more
+    for half, 1 LSB for integers) -- and it is not the default."""
+    dt = {"float": np.float32, "uint8": np.uint8, "half": np.float16, "uint16": np.uint16}[st]
+    src = synth.image(240, 160, 4, dt, seed=501)
+    M = oracle.rotate_matrix(0.4, 120.0, 80.0)
+    ref = np.zeros((160, 240, 4), dt)
+    oracle.warp(oracle.Img(ref), oracle.Img(src), M, "lanczos3", wrap="black")
+    exact = np.zeros_like(ref)
+    assert oiio.ImageBufAlgo.warp(oiio.ImageBuf(exact), oiio.ImageBuf(src), M,
+                                  filtername="lanczos3", wrap="black")
+    fast = np.zeros_like(ref)
+    oiio.ImageBufAlgo.contract_fma = True
+    try:
+        assert oiio.ImageBufAlgo.warp(oiio.ImageBuf(fast), oiio.ImageBuf(src), M,
+                                      filtername="lanczos3", wrap="black")
+    finally:
+        oiio.ImageBufAlgo.contract_fma = False
+    if st in ("uint8", "uint16"):
+        assert np.abs(fast.astype(int) - ref.astype(int)).max() <= 1
+        assert (fast != ref).mean() < 1e-2
+    else:
+        tol = 1e-5 if st == "float" else 2.0 ** -10
+        assert np.abs(fast.astype(np.float64) - ref.astype(np.float64)).max() <= tol
+    # a different rounding sequence really ran (float: some last bits differ)
+    if st == "float":
+        assert not np.array_equal(fast, exact)

@@ -96,8 +96,12 @@ def warp_ops():
         M = oiio.rotate_matrix(30.0 * math.pi / 180.0, w / 2, h / 2)
         for filt in ("lanczos3", "mitchell", "triangle"):
             ms = _time(lambda: IBA.warp(D, S, M, filtername=filt, wrap="black"))
+            IBA.contract_fma = True   # tolerance mode: packed FMAs in the accumulation
+            ms_fma = _time(lambda: IBA.warp(D, S, M, filtername=filt, wrap="black"))
+            IBA.contract_fma = False
             print(json.dumps({"workload": "rotate 30deg 4K RGBA %s %s" % (dt, filt),
-                              "ms": ms, "out_Mpix_s": w * h / ms / 1e3}))
+                              "ms": ms, "out_Mpix_s": w * h / ms / 1e3,
+                              "ms_contract_fma": ms_fma}))
         # 2x minification through the warp path (oiiotool --resize:from=...)
         small = torch.empty((h // 2, w // 2, 4), dtype=dt, device="cuda")
         R = oiio.ImageBuf(small)
