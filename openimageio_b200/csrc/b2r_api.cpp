@@ -1122,6 +1122,9 @@ resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
     const int roi_w = roi.xend - roi.xbegin, roi_h = roi.yend - roi.ybegin;
     const bool src_pageable = !host_is_pinned(src.pixels);
     const bool dst_pageable = !host_is_pinned(dst.pixels);
+    // (measured on C0: 16, 24, 32 and 48 bands all take 10.4-10.5 ms per frame --
+    // the exposed head and tail are not what separates the call from the plain
+    // copy ceiling, the concurrent download on the same link is)
     int nbands = std::max(2, std::min(16, roi_h / 128));
     if (src_pageable || dst_pageable) {
         // keep a bounce slot around 32 MB (3 pinned slots per direction)
