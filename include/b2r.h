@@ -427,6 +427,22 @@ B2R_API int b2r_mipchain_create_ex(b2r_mipchain** chain, const b2r_image* level0
                                    const b2r_mip_options* mip,
                                    const b2r_options* opt, char* err,
                                    size_t errlen);
+/* The same chain for a HOST level 0 whose levels are wanted in HOST memory, as
+ * ONE pipeline -- write_mipmap end to end (maketexture.cpp:823-986) without the
+ * file: level 0 goes up in row bands; as soon as the rows a band of level 1
+ * reads have landed, the band is computed and comes down on another stream
+ * while the next rows are still going up (PCIe is full duplex; level 1 is
+ * three quarters of what comes back); levels >= 2 follow from the device.
+ * out_levels[k-1] receives level k (float32, the level's size, contiguous in
+ * x; entries with NULL pixels are skipped), nout entries.  The chain stays
+ * resident (b2r_mipchain_level / _encode_tiles / _destroy as usual).  A level 0
+ * the pipeline does not cover (device resident, offset windows, sharpening,
+ * highlight compensation, fewer than 256 rows) takes b2r_mipchain_create_ex
+ * followed by the downloads: same results. */
+B2R_API int b2r_mipchain_create_streamed(b2r_mipchain** chain, const b2r_image* level0,
+                                         const b2r_mip_options* mip, const b2r_options* opt,
+                                         const b2r_image* out_levels, int nout, char* err,
+                                         size_t errlen);
 B2R_API int b2r_mipchain_nlevels(const b2r_mipchain* chain);
 /* Dimensions and device pointer of a level (level 0 = the input). */
 B2R_API int b2r_mipchain_level(const b2r_mipchain* chain, int level,

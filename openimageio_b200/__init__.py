@@ -1534,6 +1534,45 @@ class MipChain:
         except Exception:
             pass
 
+    @classmethod
+    def streamed(cls, level0, filtername="box", clamp_half=False, device=0, outputs=None):
+        """b2r_mipchain_create_streamed: a HOST level 0 up in row bands, level 1
+        computed and downloaded band by band while the upload is still running,
+        levels >= 2 from the device.  Returns (chain, [level 1, level 2, ...]) with
+        the levels as float32 numpy arrays (`outputs` supplies them; else they
+        are allocated here)."""
+        if not isinstance(level0, ImageBuf):
+            level0 = ImageBuf(level0)
+        L = lib()
+        sizes = []
+        w, h = level0.spec_.width, level0.spec_.height
+        while w > 1 or h > 1:
+            w, h = (w // 2 if w > 1 else w), (h // 2 if h > 1 else h)
+            sizes.append((h, w))
+        c = level0.nchannels
+        if outputs is None:
+            outputs = [np.empty((hh, ww, c), np.float32) for hh, ww in sizes]
+        bufs = [ImageBuf(a) for a in outputs]
+        arr = (type(level0._c()) * len(bufs))(*[b._c() for b in bufs])
+        self = cls.__new__(cls)
+        hnd = C.c_void_p()
+        im = level0._c()
+        o = _options(device, PATH_AUTO, None)
+        mo = _MipOptions()
+        mo.filtername = filtername.encode()
+        mo.clamp_half = 1 if clamp_half else 0
+        mo.alpha_channel = level0.spec_.alpha_channel
+        mo.sharpenfilt = b"gaussian"
+        err = C.create_string_buffer(512)
+        rc = L.b2r_mipchain_create_streamed(C.byref(hnd), C.byref(im), C.byref(mo), C.byref(o),
+                                            arr, len(bufs), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        self._h = hnd
+        self._keep = level0
+        self.nchannels = c
+        return self, outputs
+
     @property
     def nlevels(self):
         return lib().b2r_mipchain_nlevels(self._h)

@@ -25,6 +25,7 @@
 #include <cstring>
 #include <list>
 #include <memory>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -374,6 +375,14 @@ next_flag(int dev)
     s.flag     = r.flags + (n % REDO_SLOTS);
     s.dirty    = r.maps + size_t(n % REDO_SLOTS) * REDO_MAP_CELLS;
     return s;
+}
+
+// one mutex per device: the three streams are shared by all callers
+std::mutex&
+pipe_mutex(int dev)
+{
+    static std::mutex m[64];
+    return m[dev & 63];
 }
 
 int
@@ -1133,8 +1142,7 @@ resize_host_pipelined(const b2r_image& dst, const b2r_image& src,
         nbands                = std::max(nbands, std::min(want, std::max(2, roi_h / 32)));
     }
     // one mutex per device: the three streams are shared by all callers
-    static std::mutex pipe_mutex[64];
-    std::lock_guard<std::mutex> lock(pipe_mutex[device & 63]);
+    std::lock_guard<std::mutex> lock(pipe_mutex(device));
     PipeStreams& ps = pipe_streams(device);
     Bounce& bounce          = pipeline_bounce(device);
 
@@ -2689,6 +2697,287 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
     cudaEventDestroy(ev1);
     *out = chain.release();
     return B2R_OK;
+}
+
+// =========================================================================
+// The chain for a HOST level 0 with its levels delivered to HOST memory, as one
+// pipeline (write_mipmap end to end, maketexture.cpp:823-986, without the
+// file): level 0 goes up in row bands on one stream; as soon as the rows a band
+// of level 1 reads have landed, that band is computed on a second stream and
+// comes down on a third while the next rows are still going up (PCIe is full
+// duplex, and level 1 is three quarters of everything that comes back);
+// levels >= 2 follow from the device-resident level 1.  A host thread of its
+// own issues the downloads, so a pageable destination (whose copies block
+// while they drain the pinned bounce slots) never holds up the uploads.
+// =========================================================================
+extern "C" int
+b2r_mipchain_create_streamed(b2r_mipchain** out, const b2r_image* level0,
+                             const b2r_mip_options* mo, const b2r_options* opt,
+                             const b2r_image* out_levels, int nout, char* err, size_t errlen)
+{
+    if (!out || !mo || !level0) {
+        set_err(err, errlen, "mipchain: null argument");
+        return B2R_ERR_INVALID;
+    }
+    *out = nullptr;
+    int rc = check_image(level0, true, err, errlen);
+    if (rc)
+        return rc;
+    int dev0 = opt ? opt->device : 0;
+    const bool plain = level0->basetype == B2R_FLOAT && memspace_of(level0, &dev0) == B2R_MEM_HOST
+                       && !(mo->sharpen > 0.0f) && !(opt && opt->highlightcomp) && !level0->x
+                       && !level0->y && !level0->full_x && !level0->full_y
+                       && level0->full_width == level0->width
+                       && level0->full_height == level0->height
+                       && level0->xstride == (int64_t)level0->nchannels * 4
+                       && level0->width >= 2 && level0->height >= 256;
+    auto download_all = [&](b2r_mipchain* c) -> int {
+        for (int k = 1; k < (int)c->levels.size() && k - 1 < nout; ++k) {
+            if (!out_levels || !out_levels[k - 1].pixels)
+                continue;
+            int r = b2r_mipchain_download(c, k, &out_levels[k - 1], err, errlen);
+            if (r)
+                return r;
+        }
+        return B2R_OK;
+    };
+    if (!plain) {
+        // everything the pipeline does not cover: the chain, then the downloads
+        rc = b2r_mipchain_create_ex(out, level0, mo, opt, err, errlen);
+        if (rc)
+            return rc;
+        rc = download_all(*out);
+        if (rc) {
+            b2r_mipchain_destroy(*out);
+            *out = nullptr;
+        }
+        return rc;
+    }
+    std::string fname = (mo->filtername && mo->filtername[0]) ? mo->filtername : "box";
+    if (fname != "box") {
+        bool known = false;
+        for (int i = 0, e = Filter2D::num_filters(); i < e; ++i)
+            known |= (fname == Filter2D::get_filterdesc(i).name);
+        if (!known) {
+            set_err(err, errlen, "Could not make filter \"%s\"", fname.c_str());
+            return B2R_ERR_FILTER;
+        }
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen, "no CUDA device available: the B200 MIP path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    const int device = opt ? opt->device : 0;
+    if (device < 0 || device >= device_count_cached()) {
+        set_err(err, errlen, "invalid CUDA device ordinal %d", device);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(device);
+    device_info(device);
+    const int nch = level0->nchannels;
+    std::unique_ptr<b2r_mipchain> chain(new b2r_mipchain);
+    chain->device = device;
+    chain->nch    = nch;
+    auto fail = [&](int code) {
+        for (auto& l : chain->levels)
+            if (l.owned && l.px)
+                cudaFree(l.px);
+        chain->levels.clear();
+        return code;
+    };
+    for (int w = level0->width, h = level0->height;;) {
+        b2r_mipchain::Level lv { w, h, nullptr, true };
+        if (cudaMalloc(&lv.px, size_t(w) * h * nch * 4) != cudaSuccess) {
+            cudaGetLastError();
+            set_err(err, errlen, "mipchain: out of device memory");
+            return fail(B2R_ERR_CUDA);
+        }
+        chain->levels.push_back(lv);
+        if (w <= 1 && h <= 1)
+            break;
+        w = w > 1 ? w / 2 : w;
+        h = h > 1 ? h / 2 : h;
+    }
+    const int nlev = (int)chain->levels.size();
+    for (int k = 1; k < nlev && k - 1 < nout; ++k) {
+        const b2r_image* o = out_levels ? &out_levels[k - 1] : nullptr;
+        if (!o || !o->pixels)
+            continue;
+        const auto& l = chain->levels[k];
+        int odev = 0;
+        if (o->basetype != B2R_FLOAT || o->nchannels != nch || o->width != l.w || o->height != l.h
+            || o->xstride != (int64_t)nch * 4 || memspace_of(o, &odev) != B2R_MEM_HOST) {
+            set_err(err, errlen, "mipchain: output image does not match level %d", k);
+            return fail(B2R_ERR_INVALID);
+        }
+    }
+    auto image_of = [&](int k) {
+        const auto& l = chain->levels[k];
+        b2r_image im;
+        memset(&im, 0, sizeof(im));
+        im.pixels    = l.px;
+        im.basetype  = B2R_FLOAT;
+        im.nchannels = nch;
+        im.width = im.full_width = l.w;
+        im.height = im.full_height = l.h;
+        im.xstride  = (int64_t)nch * 4;
+        im.ystride  = (int64_t)l.w * nch * 4;
+        im.memspace = B2R_MEM_DEVICE;
+        im.device   = device;
+        return im;
+    };
+
+    std::lock_guard<std::mutex> lock(pipe_mutex(device));
+    PipeStreams& ps = pipe_streams(device);
+    const auto& L0  = chain->levels[0];
+    const auto& L1  = chain->levels[1];
+    const int nb    = std::max(2, std::min(16, L1.h / 128));
+    std::vector<cudaEvent_t> ev_up(nb, nullptr), ev_k(nlev + nb, nullptr);
+    auto free_events = [&]() {
+        for (auto e : ev_up)
+            if (e)
+                cudaEventDestroy(e);
+        for (auto e : ev_k)
+            if (e)
+                cudaEventDestroy(e);
+    };
+    for (auto& e : ev_up)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    for (auto& e : ev_k)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+
+    // the download thread: task i = rows [y0, y1) of level k, ready after ev
+    struct Task {
+        int level, y0, y1;
+        cudaEvent_t ready;
+    };
+    std::vector<Task> tasks;
+    std::mutex tm;
+    std::condition_variable tcv;
+    bool closed    = false;
+    int dl_rc      = B2R_OK;
+    std::string dl_err;
+    std::thread downloader([&]() {
+        cudaSetDevice(device);
+        size_t next = 0;
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(tm);
+                tcv.wait(lk, [&] { return next < tasks.size() || closed; });
+                if (next >= tasks.size())
+                    return;
+                t = tasks[next++];
+            }
+            const b2r_image* o = (out_levels && t.level - 1 < nout) ? &out_levels[t.level - 1]
+                                                                    : nullptr;
+            if (!o || !o->pixels || dl_rc)
+                continue;
+            const auto& l   = chain->levels[t.level];
+            const size_t rb = size_t(l.w) * nch * 4;
+            cudaStreamWaitEvent(ps.out, t.ready, 0);
+            cudaError_t e = copy_d2h_2d((unsigned char*)o->pixels + (long long)t.y0 * o->ystride,
+                                        o->ystride, (const unsigned char*)l.px + size_t(t.y0) * rb,
+                                        rb, rb, size_t(t.y1 - t.y0), ps.out);
+            if (e != cudaSuccess) {
+                dl_rc  = B2R_ERR_CUDA;
+                dl_err = std::string("CUDA error: ") + cudaGetErrorString(e);
+            }
+        }
+    });
+    auto post = [&](int level, int y0, int y1, cudaEvent_t ready) {
+        {
+            std::lock_guard<std::mutex> lk(tm);
+            tasks.push_back({ level, y0, y1, ready });
+        }
+        tcv.notify_one();
+    };
+    auto finish = [&](int code) {
+        {
+            std::lock_guard<std::mutex> lk(tm);
+            closed = true;
+        }
+        tcv.notify_one();
+        downloader.join();
+        cudaStreamSynchronize(ps.in);
+        cudaStreamSynchronize(ps.k);
+        cudaStreamSynchronize(ps.out);
+        free_events();
+        return code;
+    };
+
+    b2r_options sub;
+    memset(&sub, 0, sizeof(sub));
+    sub.device      = device;
+    sub.path        = opt ? opt->path : B2R_PATH_AUTO;
+    sub.cuda_stream = (void*)ps.k;
+    const size_t row0 = size_t(L0.w) * nch * 4;
+    b2r_image S0 = image_of(0), D1 = image_of(1);
+    int uploaded = 0;  // rows of level 0 on their way so far
+    for (int b = 0; b < nb; ++b) {
+        const int y0 = int((long long)L1.h * b / nb), y1 = int((long long)L1.h * (b + 1) / nb);
+        int r0 = 0, r1 = 0;
+        if (fname == "box") {
+            const bool two_pass = (2 * L1.w == L0.w) && !(L0.w % 2 || L0.h % 2);
+            r1 = two_pass ? 2 * y1
+                          : std::min(L0.h, int(((long long)y1 * L0.h + L1.h - 1) / L1.h) + 2);
+        } else {
+            b2r_roi rr { 0, L1.w, y0, y1, 0, nch };
+            rc = b2r_source_rows(&D1, &S0, fname.c_str(), 0.0f, &rr, &r0, &r1, err, errlen);
+            if (rc)
+                return fail(finish(rc));
+        }
+        if (b == nb - 1)
+            r1 = L0.h;
+        r1 = std::min(L0.h, std::max(r1, uploaded));
+        if (r1 > uploaded) {
+            cudaError_t e = copy_h2d_2d(
+                (unsigned char*)L0.px + size_t(uploaded) * row0, row0,
+                (const unsigned char*)level0->pixels + (long long)uploaded * level0->ystride,
+                level0->ystride, row0, size_t(r1 - uploaded), ps.in);
+            if (e != cudaSuccess) {
+                set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(e));
+                return fail(finish(B2R_ERR_CUDA));
+            }
+            uploaded = r1;
+        }
+        cudaEventRecord(ev_up[b], ps.in);
+        cudaStreamWaitEvent(ps.k, ev_up[b], 0);
+        b2r_roi roi { 0, L1.w, y0, y1, 0, nch };
+        rc = b2r_mip_level(&D1, &S0, fname.c_str(), &roi, &sub, err, errlen);
+        if (rc)
+            return fail(finish(rc));
+        if (mo->clamp_half)
+            launch_clamp((float*)L1.px + size_t(y0) * L1.w * nch, (long long)(y1 - y0) * L1.w * nch,
+                         nch, mo->alpha_channel, -65504.0f, 65504.0f, ps.k);
+        chain->launches += 1;
+        cudaEventRecord(ev_k[b], ps.k);
+        post(1, y0, y1, ev_k[b]);
+    }
+    for (int k = 2; k < nlev; ++k) {
+        b2r_image S = image_of(k - 1), D = image_of(k);
+        rc = b2r_mip_level(&D, &S, fname.c_str(), nullptr, &sub, err, errlen);
+        if (rc)
+            return fail(finish(rc));
+        if (mo->clamp_half)
+            launch_clamp((float*)D.pixels, (long long)D.width * D.height * nch, nch,
+                         mo->alpha_channel, -65504.0f, 65504.0f, ps.k);
+        chain->launches += 1;
+        cudaEventRecord(ev_k[nb + k], ps.k);
+        post(k, 0, D.height, ev_k[nb + k]);
+    }
+    rc = finish(B2R_OK);
+    cudaError_t ce = cudaGetLastError();
+    if (dl_rc) {
+        set_err(err, errlen, "%s", dl_err.c_str());
+        return fail(dl_rc);
+    }
+    if (ce != cudaSuccess) {
+        set_err(err, errlen, "CUDA error: %s", cudaGetErrorString(ce));
+        return fail(B2R_ERR_CUDA);
+    }
+    *out = chain.release();
+    return rc;
 }
 
 extern "C" int

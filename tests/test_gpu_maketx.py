@@ -307,3 +307,40 @@ def test_encode_tiles_roundtrip(oiio, shape, tile, half):
                 t = ts.tile_pixels(lv, tx, ty)
                 assert np.array_equal(t, ref[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile])
     assert ts.stat("stored_bytes") > 0 and ts.stat("raw_bytes") >= ts.stat("stored_bytes") * 0.5
+
+
+# ---- the chain as one pipeline: upload | level 1 bands | downloads ----------
+@pytest.mark.gpu
+@pytest.mark.parametrize("filt", ["box", "lanczos3"])
+@pytest.mark.parametrize("shape", [(1024, 1536), (700, 1031)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_streamed_chain_equals_chain(oiio, filt, shape, pinned):
+    """b2r_mipchain_create_streamed delivers every level to host memory while the
+    upload of level 0 is still running; each level must be bit-identical to the
+    plain chain's (same kernels on the same rows), for even sizes (box: 2x2
+    average) and odd ones (box: bilinear at NDC centres)."""
+    import torch
+    h, w = shape
+    lvl0 = synth.image(w, h, 4, np.float32, seed=610)
+    host = torch.from_numpy(lvl0).pin_memory() if pinned else lvl0
+    ref = oiio.MipChain(lvl0, filt)
+    chain, levels = oiio.MipChain.streamed(oiio.ImageBuf(host), filt)
+    assert chain.nlevels == ref.nlevels == len(levels) + 1
+    for k, got in enumerate(levels, start=1):
+        want = ref.download(k)
+        assert got.shape == want.shape
+        assert np.array_equal(got, want), "level %d differs (max %g)" % (
+            k, float(np.abs(got - want).max()))
+    # the chain stays resident: its device levels are the same pixels
+    assert np.array_equal(chain.download(2), levels[1])
+
+
+@pytest.mark.gpu
+def test_streamed_chain_falls_back(oiio):
+    """What the pipeline does not cover (here: a level 0 under 256 rows) takes the
+    plain chain followed by the downloads -- same results."""
+    lvl0 = synth.image(300, 120, 3, np.float32, seed=611)
+    ref = oiio.MipChain(lvl0, "lanczos3")
+    chain, levels = oiio.MipChain.streamed(lvl0, "lanczos3")
+    for k, got in enumerate(levels, start=1):
+        assert np.array_equal(got, ref.download(k))
