@@ -380,6 +380,16 @@ B2R_API int b2r_pixel_stats(const b2r_image* src, const b2r_roi* roi,
  * source -- no collective, outputs are disjoint.  Host arithmetic only. */
 /* Band `band` of `nbands`: rows [ybegin + H*band/nbands, ybegin + H*(band+1)/nbands). */
 B2R_API int b2r_band_split(const b2r_roi* roi, int nbands, int band, b2r_roi* out);
+/* One large HOST -> HOST resize over the `ndevices` GPUs of a box from this one
+ * call (the driver of the split above, for hosts that are not Python): band g
+ * of the dst ROI runs as b2r_resize on devices[g] (NULL: 0 .. ndevices-1),
+ * issued from one host thread per device; every band stages its own source
+ * rows (+ halo) and brings its own rows back over its own PCIe link.  Returns
+ * the first band's error, if any.  roi == NULL: dst's data window. */
+B2R_API int b2r_resize_banded(const b2r_image* dst, const b2r_image* src,
+                              const char* filtername, float filterwidth,
+                              const b2r_roi* roi, const int* devices, int ndevices,
+                              const b2r_options* opt, char* err, size_t errlen);
 /* Source rows [row_begin, row_end), relative to src's data-window origin,
  * that resizing into `roi` of dst reads (what b2r_resize stages for a host
  * source).  Only the images' windows are read, not their pixels. */

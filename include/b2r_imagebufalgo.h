@@ -878,6 +878,27 @@ resize_batch(std::vector<ImageBuf>& dst, const std::vector<ImageBuf>& src,
     return detail::report(dst[0], rc, err);
 }
 
+/// ImageBufAlgo::resize of one large HOST image over several GPUs of the box
+/// (b2r_resize_banded: dst rows in full-width bands like parallel_image,
+/// imagebufalgo_util.h:37-80, one band per device, each staging its own source
+/// rows + halo).  devices empty: all of them.
+inline bool
+resize_banded(ImageBuf& dst, const ImageBuf& src, const std::vector<int>& devices,
+              const KWArgs& options = {}, ROI roi = {}, int /*nthreads*/ = 0)
+{
+    if (!detail::prep(roi, dst, src))
+        return false;
+    b2r_image d = dst.c_image(), s = src.c_image();
+    b2r_roi r   = detail::c_roi(roi);
+    const int n = devices.empty() ? b2r_device_count() : (int)devices.size();
+    char err[512] = "";
+    int rc = b2r_resize_banded(&d, &s, options.get_string("filtername").c_str(),
+                               options.get_float("filterwidth"), &r,
+                               devices.empty() ? nullptr : devices.data(), n, nullptr, err,
+                               sizeof(err));
+    return detail::report(dst, rc, err);
+}
+
 }  // namespace ImageBufAlgo
 
 /// The compute step of `oiiotool --resize[:from=..][:to=..][:filter=..]

@@ -1444,10 +1444,9 @@ def source_rows(dst, src, filtername="", filterwidth=0.0, roi=None):
 
 def resize_banded(dst, src, devices, filtername="", filterwidth=0.0, roi=None):
     """ImageBufAlgo.resize of one large HOST image over several GPUs of a
-    box: dst rows are split into len(devices) bands, one synchronous
+    box (b2r_resize_banded): dst rows are split into len(devices) bands, one
     b2r_resize per band on its own device, issued from one host thread each
-    (ctypes releases the GIL).  Returns True / False like resize()."""
-    import threading
+    inside the library.  Returns True / False like resize()."""
     roi = _ibaprep(roi, dst, src)
     if roi is None:
         return False
@@ -1455,32 +1454,17 @@ def resize_banded(dst, src, devices, filtername="", filterwidth=0.0, roi=None):
         dst.errorfmt("resize_banded shards host images; device-resident "
                      "images are already on one GPU")
         return False
-    n = len(devices)
-    errs = [None] * n
-
-    def work(i):
-        band = band_split(roi, n, i)
-        if band.yend <= band.ybegin:
-            return
-        d, s = dst._c(), src._c()
-        r = _Roi(band.xbegin, band.xend, band.ybegin, band.yend, band.chbegin,
-                 band.chend)
-        o = _options(devices[i], PATH_AUTO, None)
-        err = C.create_string_buffer(512)
-        rc = lib().b2r_resize(C.byref(d), C.byref(s), (filtername or "").encode(),
-                              float(filterwidth), C.byref(r), C.byref(o), None,
-                              err, 512)
-        if rc:
-            errs[i] = err.value.decode()
-
-    threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    bad = [e for e in errs if e]
-    if bad:
-        dst.errorfmt(bad[0])
+    d, s = dst._c(), src._c()
+    r = _Roi(roi.xbegin, roi.xend, roi.ybegin, roi.yend, roi.chbegin, roi.chend)
+    devs = (C.c_int * len(devices))(*[int(x) for x in devices])
+    o = _options(0, PATH_AUTO, None)
+    err = C.create_string_buffer(512)
+    # the C ABI drives the bands: one host thread per device inside b2r_resize_banded
+    rc = lib().b2r_resize_banded(C.byref(d), C.byref(s), (filtername or "").encode(),
+                                 float(filterwidth), C.byref(r), devs, len(devices),
+                                 C.byref(o), err, 512)
+    if rc:
+        dst.errorfmt(err.value.decode())
         return False
     return True
 

@@ -1707,6 +1707,71 @@ b2r_band_split(const b2r_roi* roi, int nbands, int band, b2r_roi* out)
 }
 
 int
+b2r_resize_banded(const b2r_image* dst, const b2r_image* src, const char* filtername,
+                  float filterwidth, const b2r_roi* roi_in, const int* devices, int ndevices,
+                  const b2r_options* opt, char* err, size_t errlen)
+{
+    if (!dst || !src || ndevices < 1 || ndevices > 64) {
+        set_err(err, errlen, "resize_banded: bad arguments");
+        return B2R_ERR_INVALID;
+    }
+    int d0 = 0, d1 = 0;
+    if (memspace_of(dst, &d0) != B2R_MEM_HOST || memspace_of(src, &d1) != B2R_MEM_HOST) {
+        set_err(err, errlen, "resize_banded shards host images; device-resident images are "
+                             "already on one GPU");
+        return B2R_ERR_UNSUPPORTED;
+    }
+    const int ndev_all = device_count_cached();
+    if (ndev_all <= 0) {
+        set_err(err, errlen, "no CUDA device available: the B200 resize path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    b2r_roi roi = roi_in ? *roi_in
+                         : b2r_roi { dst->x, dst->x + dst->width, dst->y, dst->y + dst->height, 0,
+                                     dst->nchannels };
+    std::vector<int> rcs(ndevices, B2R_OK);
+    std::vector<std::string> errs(ndevices);
+    auto work = [&](int g) {
+        b2r_roi band;
+        if (b2r_band_split(&roi, ndevices, g, &band) || band.yend <= band.ybegin)
+            return;
+        b2r_options o;
+        memset(&o, 0, sizeof(o));
+        if (opt)
+            o = *opt;
+        o.device      = devices ? devices[g] : g;
+        o.cuda_stream = nullptr;
+        if (o.device < 0 || o.device >= ndev_all) {
+            rcs[g]  = B2R_ERR_INVALID;
+            errs[g] = "invalid CUDA device ordinal " + std::to_string(o.device);
+            return;
+        }
+        char e[512] = "";
+        rcs[g] = b2r_resize(dst, src, filtername, filterwidth, &band, &o, nullptr, e, sizeof(e));
+        if (rcs[g])
+            errs[g] = e;
+    };
+    std::vector<std::thread> th;
+    int started = 1;
+    try {
+        for (; started < ndevices; ++started)
+            th.emplace_back(work, started);
+    } catch (...) {
+    }
+    work(0);
+    for (int g = started; g < ndevices; ++g)
+        work(g);  // threads that could not be had
+    for (auto& t : th)
+        t.join();
+    for (int g = 0; g < ndevices; ++g)
+        if (rcs[g]) {
+            set_err(err, errlen, "%s", errs[g].c_str());
+            return rcs[g];
+        }
+    return B2R_OK;
+}
+
+int
 b2r_source_rows(const b2r_image* dst, const b2r_image* src, const char* filtername,
                 float filterwidth, const b2r_roi* roi_in, int* row_begin,
                 int* row_end, char* err, size_t errlen)
