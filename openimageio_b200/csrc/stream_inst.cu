@@ -13,7 +13,7 @@ template<int VK, int W2, bool HC>
 static StreamKernel
 pick_ht(int ht, int* smem)
 {
-    *smem = StreamSmem<B2R_INST_ST, VK, W2>::TOTAL;
+    *smem = StreamSmem<B2R_INST_ST, VK, W2, B2R_INST_NCH>::TOTAL;
     switch (ht) {
     case 8: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 8, W2, HC>;
     case 10: return resize_stream_kernel<B2R_INST_ST, B2R_INST_NCH, VK, 10, W2, HC>;

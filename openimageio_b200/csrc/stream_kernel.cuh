@@ -123,8 +123,12 @@ named_bar_arrive(int id, int count)
 // E2: four-element groups per V thread -- 2 for the 1- and 2-byte source types
 // of the wide geometry (16 / 8 bytes per thread per row: half the per-element
 // control and load overhead), 1 otherwise.
-template<int W2, int E2 = 1> struct StreamGeom {
-    static constexpr int NVT     = STREAM_VTHREADS * W2 / E2;  // V threads
+// NCH == 3 in the wide geometry: a V row holds 512 pixels, i.e. 1536 of the
+// 2048 elements 512 V threads would cover -- the CTA runs 384 V threads (12
+// warps) instead, so no warp spends its issue slots on padding
+// (stream_vthreads() in kernels.h, shared with the planner and the launcher).
+template<int W2, int E2 = 1, int NCH = 4> struct StreamGeom {
+    static constexpr int NVT     = stream_vthreads(NCH, W2) / E2;  // V threads
     static constexpr int VPIX    = STREAM_VTHREADS * W2;      // pixels a V row holds
     static constexpr int HCOLS   = FUSED_HCOLS * W2;          // dst columns per strip
     static constexpr int HPAIRS  = HCOLS / 2;
@@ -134,7 +138,9 @@ template<int W2, int E2 = 1> struct StreamGeom {
     static constexpr int THREADS = STREAM_PTHREADS + NVT + STREAM_HTHREADS;
     static constexpr int ROWS    = stream_rows(W2);           // source rows per stage
     // registers after setmaxnreg (the kernel is compiled for 65536 / THREADS)
-    static constexpr int VREGS   = NVT == 256 ? 96 : 64;
+    // (384 V threads: 128 x 24 + 384 x 72 + 256 x 112 = 59392 of the 61440 the
+    // launch holds at 80 per thread)
+    static constexpr int VREGS   = NVT == 256 ? 96 : (NVT == 384 ? 72 : 64);
     static constexpr int HREGS   = NVT == 256 ? 120 : 112;
 };
 template<int W2>
@@ -372,9 +378,9 @@ template<int ST> struct StreamE2 {
     // runs one group per thread; the E2 = 2 code stays for the record.
     template<int W2> static constexpr int of() { return 1; }
 };
-template<int ST, int VK, int W2> struct StreamSmem {
+template<int ST, int VK, int W2, int NCH = 4> struct StreamSmem {
     static constexpr int E2       = StreamE2<ST>::template of<W2>();
-    using G = StreamGeom<W2, E2>;
+    using G = StreamGeom<W2, E2, NCH>;
     static constexpr int es       = SrcTraits<ST>::es;
     static constexpr int ROWS     = G::ROWS;
     static constexpr int BOXW     = 256;  // elements per box row (the TMA limit)
@@ -399,10 +405,10 @@ template<int ST, int VK, int W2> struct StreamSmem {
 // parameter because the V loop has no register to spare for a run-time flag
 // (the run-time version cost the plain C0 frame 115 -> 136 us).
 template<int ST, int NCH, int VK, int HT, int W2, bool HC = false>
-__global__ void __launch_bounds__(StreamSmem<ST, VK, W2>::G::THREADS, 1)
+__global__ void __launch_bounds__(StreamSmem<ST, VK, W2, NCH>::G::THREADS, 1)
 resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams p)
 {
-    using S = StreamSmem<ST, VK, W2>;
+    using S = StreamSmem<ST, VK, W2, NCH>;
     using G = typename S::G;
     constexpr int E2    = S::E2;
     constexpr int es    = S::es;

@@ -112,7 +112,7 @@ launch_with_map(const FusedParams& p, int w2, const CUtensorMap& map, int sms, v
     dim3 grid((unsigned)std::min<long long>(items, std::max(1, sms)), 1, 1);
     // four-element groups per V thread
     const int e2      = 1;  // see StreamE2 in stream_kernel.cuh
-    const int threads = STREAM_PTHREADS + STREAM_VTHREADS * w2 / e2 + STREAM_HTHREADS;
+    const int threads = STREAM_PTHREADS + stream_vthreads(p.nch, w2) / e2 + STREAM_HTHREADS;
     launch_pdl(k, grid, dim3(threads), (size_t)smem, (cudaStream_t)stream, map, p);
     return 0;
 }
