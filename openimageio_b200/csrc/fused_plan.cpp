@@ -342,8 +342,9 @@ plan_fused(const AxisGather& gx, const AxisGather& gy, int nch, int src_w,
             int pr   = (dx0 + s.ndx) / 2;
             int pend = P.hfirst[pr] + P.ht;          // one past the last px read
             int nvec = (pend * nch - s.e0 + 3) / 4;
-            // (the stream kernel runs 384 V threads on wide RGB strips)
-            const int vcap = w2 == 2 ? stream_vthreads(nch, w2) : FUSED_THREADS * w2;
+            // (the stream kernel runs only the V warpgroups a strip of nch
+            // channels can fill)
+            const int vcap = std::min(FUSED_THREADS * w2, stream_vthreads(nch, w2));
             if (nvec > vcap || pend - px0 > FUSED_THREADS * w2)
                 break;
             s.nvec = nvec;

@@ -154,12 +154,15 @@ fused_min_ctas(int es, int vk)
 // threads per CTA, one CTA per SM.
 constexpr int STREAM_VTHREADS = 256;  // V threads per unit of strip width (w2)
 constexpr int STREAM_HTHREADS = 256;
-// V threads of a stream-kernel CTA: 256 per unit of strip width -- except RGB in
-// the wide geometry, whose 512-pixel V rows are 1536 elements = 384 threads
+// V threads of a stream-kernel CTA.  A V row holds 256 * w2 pixels, i.e.
+// 64 * w2 * nch four-element groups: with fewer than four channels a CTA of
+// 256 * w2 V threads would run the rest of its warps on padding.  Whole
+// warpgroups only (setmaxnreg is executed per warpgroup, and the H warps that
+// follow must start on a warpgroup boundary).
 B2R_HD constexpr int
 stream_vthreads(int nch, int w2)
 {
-    return (nch == 3 && w2 == 2) ? 384 : STREAM_VTHREADS * w2;
+    return (64 * w2 * (nch < 1 ? 1 : (nch > 4 ? 4 : nch)) + 127) / 128 * 128;
 }
 // warpgroup 0 holds the producer warp (its other three warps give their
 // registers away with setmaxnreg and exit), then the V warps, then the H warps

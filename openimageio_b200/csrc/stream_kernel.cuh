@@ -123,9 +123,9 @@ named_bar_arrive(int id, int count)
 // E2: four-element groups per V thread -- 2 for the 1- and 2-byte source types
 // of the wide geometry (16 / 8 bytes per thread per row: half the per-element
 // control and load overhead), 1 otherwise.
-// NCH == 3 in the wide geometry: a V row holds 512 pixels, i.e. 1536 of the
-// 2048 elements 512 V threads would cover -- the CTA runs 384 V threads (12
-// warps) instead, so no warp spends its issue slots on padding
+// NCH < 4: a V row holds 256 * W2 pixels, i.e. fewer elements than 256 * W2 V
+// threads would cover (RGB, wide: 1536 of 2048) -- the CTA runs only the V
+// warpgroups that have elements, so no warp spends its issue slots on padding
 // (stream_vthreads() in kernels.h, shared with the planner and the launcher).
 template<int W2, int E2 = 1, int NCH = 4> struct StreamGeom {
     static constexpr int NVT     = stream_vthreads(NCH, W2) / E2;  // V threads
@@ -138,10 +138,14 @@ template<int W2, int E2 = 1, int NCH = 4> struct StreamGeom {
     static constexpr int THREADS = STREAM_PTHREADS + NVT + STREAM_HTHREADS;
     static constexpr int ROWS    = stream_rows(W2);           // source rows per stage
     // registers after setmaxnreg (the kernel is compiled for 65536 / THREADS)
-    // (384 V threads: 128 x 24 + 384 x 72 + 256 x 112 = 59392 of the 61440 the
-    // launch holds at 80 per thread)
-    static constexpr int VREGS   = NVT == 256 ? 96 : (NVT == 384 ? 72 : 64);
-    static constexpr int HREGS   = NVT == 256 ? 120 : 112;
+    // LREGS: what a thread holds at launch (__launch_bounds__(THREADS, 1)).
+    //   NVT 512: 72 at launch -> P 24, V 64, H 112   (128 x 24 + 512 x 64 + 256 x 112 = 64512)
+    //   NVT 384: 80           -> P 24, V 72, H 112   (59392 of 61440)
+    //   NVT 256: 96           -> P 24, V 96, H 120   (58368 of 61440)
+    //   NVT 128: 128          -> P 24, V 96, H stays at 128
+    static constexpr int LREGS   = (65536 / THREADS) / 8 * 8;
+    static constexpr int VREGS   = NVT >= 512 ? 64 : (NVT == 384 ? 72 : 96);
+    static constexpr int HREGS   = NVT >= 384 ? 112 : 120;
 };
 template<int W2>
 __device__ __forceinline__ int
@@ -500,7 +504,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         }
     } else if (warp < G::NVT / 32) {
         // ================= V warps =========================================
-        if (G::VREGS < 65536 / G::THREADS / 8 * 8)
+        if (G::VREGS < G::LREGS)
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::VREGS));
         const int tid = threadIdx.x;
         int stage = 0;
@@ -821,7 +825,8 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
         }
     } else {
         // ================= H warps =========================================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::HREGS));
+        if (G::HREGS > G::LREGS)
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::HREGS));
         const int tid = threadIdx.x - G::NVT;
         const int hp  = tid % G::HPAIRS;
         const int hr  = tid / G::HPAIRS;
