@@ -140,12 +140,13 @@ template<int W2, int E2 = 1, int NCH = 4> struct StreamGeom {
     // registers after setmaxnreg (the kernel is compiled for 65536 / THREADS)
     // LREGS: what a thread holds at launch (__launch_bounds__(THREADS, 1)).
     //   NVT 512: 72 at launch -> P 24, V 64, H 112   (128 x 24 + 512 x 64 + 256 x 112 = 64512)
-    //   NVT 384: 80           -> P 24, V 72, H 112   (59392 of 61440)
+    //   NVT 384: 80           -> P 24, V 72, H 120   (61440 of 61440; at 112 the
+    //                                                 16-tap H windows spill)
     //   NVT 256: 96           -> P 24, V 96, H 120   (58368 of 61440)
     //   NVT 128: 128          -> P 24, V 96, H stays at 128
     static constexpr int LREGS   = (65536 / THREADS) / 8 * 8;
     static constexpr int VREGS   = NVT >= 512 ? 64 : (NVT == 384 ? 72 : 96);
-    static constexpr int HREGS   = NVT >= 384 ? 112 : 120;
+    static constexpr int HREGS   = NVT >= 512 ? 112 : 120;
 };
 template<int W2>
 __device__ __forceinline__ int
