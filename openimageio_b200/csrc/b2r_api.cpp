@@ -476,7 +476,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
 
     const bool want_hc = opt && opt->reserved[3] == 1;
     if (want_hc
-        && !(src.basetype == B2R_FLOAT && dst.basetype == B2R_FLOAT && smem == B2R_MEM_DEVICE
+        && !((src.basetype == B2R_FLOAT || src.basetype == B2R_HALF)
+             && (dst.basetype == B2R_FLOAT || dst.basetype == B2R_HALF) && smem == B2R_MEM_DEVICE
              && dmem == B2R_MEM_DEVICE && nch <= 4 && src.nchannels == nch && filter.separable()
              && path != B2R_PATH_EXACT))
         return HC_NOT_FUSED;
@@ -2113,8 +2114,8 @@ resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Fil
     if (opt->reserved[0] == 1)  // tables only (MIP chain pass 1)
         return resize_impl(dst_in, src_in, filter, roi_in, &sub, report, err, errlen);
 
-    // float -> float on the device: compress on load, expand on store, inside
-    // the stream kernel (one pass over HBM instead of three)
+    // float / half images on the device: compress on load, expand on store,
+    // inside the stream kernel (one pass over HBM instead of three)
     {
         b2r_options fused = sub;
         fused.reserved[3] = 1;

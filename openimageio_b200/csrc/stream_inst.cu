@@ -41,9 +41,9 @@ pick_vk(int vk, int ht, int* smem)
 StreamKernel
 B2R_NAME(B2R_INST_ST, B2R_INST_NCH)(int vk, int ht, int w2, int hc, int* smem)
 {
-    // highlight compensation fused in: float sources, wide geometry only
-    // (anything else runs the three passes)
-#if B2R_INST_ST == 3
+    // highlight compensation fused in: float / half sources, wide geometry
+    // only (anything else runs the three passes)
+#if B2R_INST_ST == 3 || B2R_INST_ST == 2
     if (hc)
         return w2 == 2 ? pick_vk<2, true>(vk, ht, smem) : nullptr;
 #else

@@ -359,11 +359,19 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
             // rangeexpand the results (not alpha / z)
             float* fa[4] = { &aA.x, &aA.y, &aA.z, &aA.w };
             float* fb[4] = { &aB.x, &aB.y, &aB.z, &aB.w };
+            // (a half destination holds the resize's result as a half before
+            // rangeexpand reads it back in place, oiiotool.cpp:4661-4662)
+            const bool hdst = p.dsttype == BT_HALF;
+            auto exp1 = [hdst](float y) -> float {
+                if (hdst)
+                    y = __half2float(__float2half_rn(y));
+                return dev_rangeexpand_fast(y);
+            };
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
                 if (!((p.hc_skip >> c) & 1)) {
-                    *fa[c] = dev_rangeexpand_fast(*fa[c]);
-                    *fb[c] = dev_rangeexpand_fast(*fb[c]);
+                    *fa[c] = exp1(*fa[c]);
+                    *fb[c] = exp1(*fb[c]);
                 }
         }
         stream_store_pair<NCH>(p, dp, des, aA, aB, has_b);
@@ -406,7 +414,7 @@ template<int ST, int VK, int W2, int NCH = 4> struct StreamSmem {
     static_assert(NST >= 2, "at least two stages");
 };
 
-// HC: highlight compensation fused in (float sources only) -- a template
+// HC: highlight compensation fused in (float / half sources) -- a template
 // parameter because the V loop has no register to spare for a run-time flag
 // (the run-time version cost the plain C0 frame 115 -> 136 us).
 template<int ST, int NCH, int VK, int HT, int W2, bool HC = false>
@@ -427,7 +435,7 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
     // stage-specialised V pass (see the V warps below)
     constexpr bool JIT  = W2 == 2 && FP && VK == 6;
     constexpr bool SPEC = W2 == 2 && (!FP || VK <= 6);
-    static_assert(!HC || ST == ST_FLOAT, "highlight compensation is fused for float sources");
+    static_assert(!HC || FP, "highlight compensation is fused for float / half sources");
     static_assert(BATCH % G::ROWG == 0, "batch rows must split evenly over the H row groups");
 
     extern __shared__ __align__(1024) unsigned char stream_smem[];
@@ -541,16 +549,23 @@ resize_stream_kernel(const __grid_constant__ CUtensorMap tmap, const FusedParams
             auto load_values = [&](const uint4& r, float4 (&v)[E2]) {
                 stream_convert<ST, E2>(r, v);
                 if (HC && hcmask) {
+                    // a half source is compressed into a half temporary by the
+                    // three passes (tmpimg has the source's type,
+                    // oiiotool.cpp:4646-4649): round the way that store does
+                    auto cmp = [](float x) -> float {
+                        const float y = dev_rangecompress_fast(x);
+                        return ST == ST_HALF ? __half2float(__float2half_rn(y)) : y;
+                    };
 #pragma unroll
                     for (int h = 0; h < E2; ++h) {
                         if (hcmask & (1u << (4 * h)))
-                            v[h].x = dev_rangecompress_fast(v[h].x);
+                            v[h].x = cmp(v[h].x);
                         if (hcmask & (2u << (4 * h)))
-                            v[h].y = dev_rangecompress_fast(v[h].y);
+                            v[h].y = cmp(v[h].y);
                         if (hcmask & (4u << (4 * h)))
-                            v[h].z = dev_rangecompress_fast(v[h].z);
+                            v[h].z = cmp(v[h].z);
                         if (hcmask & (8u << (4 * h)))
-                            v[h].w = dev_rangecompress_fast(v[h].w);
+                            v[h].w = cmp(v[h].w);
                     }
                 }
             };

@@ -701,6 +701,41 @@ def test_resize_highlightcomp(oiio, oracle, dt, st, nch):
             assert np.abs(p.astype(np.float64) - g.astype(np.float64)).max() > 1e-3
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("st,dt", [("float", "float"), ("half", "half"), ("half", "float"),
+                                   ("float", "half")])
+def test_resize_highlightcomp_fused(oiio, oracle, st, dt):
+    """Device-resident float / half images of a shape the wide stream kernel takes:
+    highlight compensation runs INSIDE the resize kernel (one launch) -- compress as
+    the V pass loads, expand as the H pass stores, with the roundings the three
+    passes make through their half temporaries -- and matches the oracle's
+    compress -> resize -> expand."""
+    import torch
+    w, h = 3072, 2304  # 6 strips x 36 bands: enough items for the wide geometry
+    src = (synth.image(w, h, 4, np.float32, seed=131) ** 4 * np.float32(20)).astype(_np_dtype(st))
+    tmp = src.copy()
+    oracle.rangecompress(oracle.Img(tmp), oracle.Img(src), alpha_channel=3)
+    ref = np.zeros((h // 2, w // 2, 4), _np_dtype(dt))
+    oracle.resize(oracle.Img(ref), oracle.Img(tmp), "lanczos3")
+    oracle.rangeexpand(oracle.Img(ref), oracle.Img(ref), alpha_channel=3)
+    tdt = {"float": torch.float32, "half": torch.float16}
+    S = oiio.ImageBuf(torch.from_numpy(src).cuda())
+    dst = torch.zeros((h // 2, w // 2, 4), dtype=tdt[dt], device="cuda")
+    D = oiio.ImageBuf(dst)
+    S.spec().alpha_channel = D.spec().alpha_channel = 3
+    oiio.ImageBufAlgo.force_report = True
+    try:
+        assert oiio.ImageBufAlgo.resize(D, S, filtername="lanczos3", highlightcomp=True), D.geterror()
+    finally:
+        oiio.ImageBufAlgo.force_report = False
+    assert oiio.ImageBufAlgo.last_report.kernels_launched == 1  # fused, not three passes
+    got = dst.cpu().numpy()
+    scale = max(1.0, float(np.abs(ref.astype(np.float64)).max()))
+    tol = 5e-5 if dt == "float" and st == "float" else 2.0 ** -9
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()
+    assert err <= tol * scale, (err, scale)
+
+
 def test_mip_chain_highlightcomp(oiio, oracle):
     lvl0 = (synth.image(96, 64, 4, np.float32, seed=111) ** 4 * np.float32(30)).astype(np.float32)
     ref = oracle.mip_chain(lvl0, "lanczos3", highlightcomp=True, alpha_channel=3)
