@@ -474,7 +474,7 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
     cudaStream_t stream = opt ? (cudaStream_t)opt->cuda_stream : nullptr;
     const int path      = opt ? opt->path : B2R_PATH_AUTO;
 
-    const bool want_hc = opt && opt->reserved[3] == 1;
+    const bool want_hc = opt && opt->reserved[3] >= 1;  // 2: + maketx's clamp
     if (want_hc
         && !((src.basetype == B2R_FLOAT || src.basetype == B2R_HALF)
              && (dst.basetype == B2R_FLOAT || dst.basetype == B2R_HALF) && smem == B2R_MEM_DEVICE
@@ -1003,6 +1003,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
                     fp.hc_skip |= 1 << (opt->alpha_channel1 - 1);
                 if (opt->z_channel1 > 0)
                     fp.hc_skip |= 1 << (opt->z_channel1 - 1);
+                fp.hc_clamp = opt->reserved[3] == 2 ? 1 : 0;
+                fp.hc_alpha = opt->alpha_channel1 - 1;
             }
             if (g_capture && g_capture->want && !temp && !dst_staged
                 && !(opt && (opt->reserved[1] || opt->reserved[2]))) {
@@ -2118,7 +2120,10 @@ resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Fil
     // inside the stream kernel (one pass over HBM instead of three)
     {
         b2r_options fused = sub;
-        fused.reserved[3] = 1;
+        // highlightcomp == 2 (private to the MIP chain): the level is clamped
+        // afterwards (maketexture.cpp:936-938) -- in the kernel's store when the
+        // call is fused, by clamp_kernel after the three passes otherwise
+        fused.reserved[3] = opt->highlightcomp == 2 ? 2 : 1;
         rc = resize_impl(dst_in, src_in, filter, roi_in, &fused, report, err, errlen);
         if (rc != HC_NOT_FUSED)
             return rc;
@@ -2177,6 +2182,12 @@ resize_highlightcomp(const b2r_image* dst_in, const b2r_image* src_in, const Fil
     }
     if (rc == B2R_OK)
         range_on_device(true, D, D.pixels, D, D.pixels, roi, false, alpha, z, stream);
+    if (rc == B2R_OK && opt->highlightcomp == 2 && !dpix && D.basetype == B2R_FLOAT
+        && D.xstride == (int64_t)D.nchannels * 4
+        && D.ystride == (int64_t)D.width * D.nchannels * 4 && roi_w == D.width
+        && roi_h == D.height)
+        launch_clamp((float*)D.pixels, (long long)D.width * D.height * D.nchannels,
+                     D.nchannels, alpha, 0.0f, 3.402823466e+38f, stream);
     if (rc == B2R_OK && dpix) {
         unsigned char* hp = (unsigned char*)dst.pixels
                             + (long long)(roi.ybegin - dst.y) * dst.ystride
@@ -2669,7 +2680,7 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
                     // the level's shape belongs to the stream kernel (else the
                     // three passes, inside b2r_resize), then the clamp (:936-938)
                     b2r_options hc = sub;
-                    hc.highlightcomp  = 1;
+                    hc.highlightcomp  = 2;  // + the clamp, wherever the call ends up
                     hc.alpha_channel1 = alpha_channel + 1;
                     hc.z_channel1     = hc_z + 1;
                     rc = b2r_resize(&D, &S, fname.c_str(), 0.0f, nullptr, &hc, nullptr, err,
@@ -2681,11 +2692,8 @@ b2r_mipchain_create_ex(b2r_mipchain** out, const b2r_image* level0,
                             cudaEventDestroy(ev1);
                         return fail(rc);
                     }
-                    if (pass == 1) {
-                        launch_clamp((float*)lv.px, (long long)sw * sh * nch, nch,
-                                     alpha_channel, 0.0f, 3.402823466e+38f, stream);
-                        chain->launches += 2;
-                    }
+                    if (pass == 1)
+                        chain->launches += 1;
                 } else {
                 if (hicomp) {
                     // rangecompress(*img) (:907-909); the level itself stays

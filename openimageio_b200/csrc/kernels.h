@@ -275,6 +275,10 @@ struct FusedParams {
     // (alpha, z)
     int hicomp;
     int hc_skip;
+    // ... followed by maketx's clamp (maketexture.cpp:936-938): every channel
+    // to [0, FLT_MAX] (NaN -> 0), channel hc_alpha (>= 0) to [0, 1]
+    int hc_clamp;
+    int hc_alpha;
     // stream kernel, a batch of frames of one shape in one launch (nframes > 1):
     // per frame a tensor map (device array of CUtensorMap, 64-byte aligned) and
     // the address of the ROI's first pixel

@@ -373,6 +373,24 @@ stream_hpass(const FusedParams& p, unsigned char* dbase, unsigned vrows, int nb,
                     *fa[c] = exp1(*fa[c]);
                     *fb[c] = exp1(*fb[c]);
                 }
+            if (p.hc_clamp) {
+                // ImageBufAlgo::clamp(small, small, 0, FLT_MAX, clampalpha01 = true)
+                // as clamp_kernel does it (NaN -> 0)
+                auto cl = [](float r, bool alpha) -> float {
+                    if (!(0.0f <= r))
+                        r = 0.0f;
+                    if (r > 3.402823466e+38f)
+                        r = 3.402823466e+38f;
+                    if (alpha && r > 1.0f)
+                        r = 1.0f;
+                    return r;
+                };
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    *fa[c] = cl(*fa[c], c == p.hc_alpha);
+                    *fb[c] = cl(*fb[c], c == p.hc_alpha);
+                }
+            }
         }
         stream_store_pair<NCH>(p, dp, des, aA, aB, has_b);
         dp += (long long)G::ROWG * p.dst_ystride;
