@@ -123,6 +123,12 @@ typedef struct b2r_report {
 
 /* ---- library ---------------------------------------------------------- */
 B2R_API const char* b2r_version(void);
+/* The library keeps device / pinned memory between calls so that a run of
+ * same-sized jobs allocates once: the band buffers of destroyed banded chains
+ * (up to 12 GB per device), the tile encoder's staging slots, the weight-table
+ * plans.  This call gives all of it back to the driver (no call may be in
+ * flight).  Host weight tables are rebuilt on the next call of each shape. */
+B2R_API void b2r_trim_caches(void);
 /* Number of usable CUDA devices (0 = none; compute calls will fail). */
 B2R_API int b2r_device_count(void);
 

@@ -1476,6 +1476,15 @@ def resize_banded(dst, src, devices, filtername="", filterwidth=0.0, roi=None):
     return True
 
 
+def trim_caches():
+    """b2r_trim_caches: give the library's cached device / pinned memory (band
+    buffers of destroyed banded chains, tile staging slots, weight-table plans)
+    back to the driver."""
+    L = lib()
+    L.b2r_trim_caches.restype = None
+    L.b2r_trim_caches()
+
+
 def shard_frames(nframes, world_size, rank):
     """Frames of a batch are independent: round-robin over ranks (one
     process per GPU), no exchange."""

@@ -197,6 +197,12 @@ struct DeviceGuard {
 };
 
 
+// caches behind b2r_trim_caches (b2r_api_banded.cpp, b2r_api_tiles.cpp)
+void
+trim_band_blocks();
+void
+trim_tile_slots();
+
 // Runs at every exit of an entry point: staging blocks that are still set go
 // back to the pool (stream-ordered), events that are still set are destroyed.
 // The normal path frees / destroys them itself and clears the variables.

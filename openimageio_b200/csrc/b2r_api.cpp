@@ -1356,6 +1356,17 @@ b2r_version(void)
     return "b2r 0.1 (sm_100a)";
 }
 
+void
+b2r_trim_caches(void)
+{
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plans.clear();  // ~DevicePlan frees the table blobs
+    }
+    trim_band_blocks();
+    trim_tile_slots();
+}
+
 int
 b2r_device_count(void)
 {

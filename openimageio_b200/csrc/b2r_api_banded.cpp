@@ -90,6 +90,33 @@ struct BandBlockCache {
 };
 BandBlockCache g_band_blocks;
 
+}  // namespace
+
+namespace b2r {
+namespace api {
+// b2r_trim_caches: every cached band block goes back to the driver
+void
+trim_band_blocks()
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::lock_guard<std::mutex> lock(g_band_blocks.mu);
+    for (int d = 0; d < 64; ++d) {
+        if (g_band_blocks.blocks[d].empty())
+            continue;
+        cudaSetDevice(d);
+        for (auto& kv : g_band_blocks.blocks[d])
+            cudaFree(kv.second);
+        g_band_blocks.blocks[d].clear();
+        g_band_blocks.held[d] = 0;
+    }
+    cudaSetDevice(prev);
+}
+}  // namespace api
+}  // namespace b2r
+
+namespace {
+
 size_t
 band_bytes(const b2r_mipchain_banded& c, int level, int g)
 {

@@ -80,6 +80,34 @@ slot_cache(int device)
 
 }  // namespace
 
+namespace b2r {
+namespace api {
+// b2r_trim_caches: the tile encoder's staging slots (device + pinned host)
+void
+trim_tile_slots()
+{
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < 64; ++d) {
+        SlotCache& c = slot_cache(d);
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (!c.bytes)
+            continue;
+        cudaSetDevice(d);
+        for (int i = 0; i < NSLOT; ++i) {
+            if (c.d[i])
+                cudaFree(c.d[i]);
+            if (c.h[i])
+                cudaFreeHost(c.h[i]);
+            c.d[i] = c.h[i] = nullptr;
+        }
+        c.bytes = 0;
+    }
+    cudaSetDevice(prev);
+}
+}  // namespace api
+}  // namespace b2r
+
 extern "C" int
 b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
                           b2r_tileset** out, char* err, size_t errlen)

@@ -344,3 +344,23 @@ def test_streamed_chain_falls_back(oiio):
     chain, levels = oiio.MipChain.streamed(lvl0, "lanczos3")
     for k, got in enumerate(levels, start=1):
         assert np.array_equal(got, ref.download(k))
+
+
+@pytest.mark.gpu
+def test_trim_caches(oiio):
+    """b2r_trim_caches returns the band buffers a destroyed banded chain left in
+    the per-device cache (and the plans, the tile slots); the library keeps working."""
+    import torch
+    lvl0 = synth.image(2048, 1024, 4, np.float32, seed=620)
+    ch = oiio.MipChainBanded(oiio.ImageBuf(lvl0), [0, 0], filtername="box")
+    want = ch.download(3)
+    del ch
+    torch.cuda.synchronize()
+    free_cached, _ = torch.cuda.mem_get_info()
+    oiio.trim_caches()
+    free_trimmed, _ = torch.cuda.mem_get_info()
+    assert free_trimmed >= free_cached + 2048 * 1024 * 16  # at least level 0's bands came back
+    ch = oiio.MipChainBanded(oiio.ImageBuf(lvl0), [0, 0], filtername="box")
+    assert np.array_equal(ch.download(3), want)
+    out = np.zeros((512, 1024, 4), np.float32)
+    assert oiio.ImageBufAlgo.resize(oiio.ImageBuf(out), oiio.ImageBuf(lvl0), filtername="lanczos3")
