@@ -154,13 +154,14 @@ def lib():
                                    C.c_char_p, C.c_float, C.POINTER(_Roi),
                                    C.POINTER(_Options), C.POINTER(Report), C.c_char_p,
                                    C.c_size_t]
-    L.b2r_resize_banded.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_char_p,
-                                    C.c_float, C.POINTER(_Roi), C.POINTER(C.c_int), C.c_int,
-                                    C.POINTER(_Options), C.c_char_p, C.c_size_t]
-    L.b2r_mipchain_create_streamed.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
-                                               C.POINTER(_MipOptions), C.POINTER(_Options),
-                                               C.POINTER(_Image), C.c_int, C.c_char_p,
-                                               C.c_size_t]
+    if hasattr(L, "b2r_resize_banded"):  # (absent from libraries older than round 2)
+        L.b2r_resize_banded.argtypes = [C.POINTER(_Image), C.POINTER(_Image), C.c_char_p,
+                                        C.c_float, C.POINTER(_Roi), C.POINTER(C.c_int), C.c_int,
+                                        C.POINTER(_Options), C.c_char_p, C.c_size_t]
+        L.b2r_mipchain_create_streamed.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
+                                                   C.POINTER(_MipOptions), C.POINTER(_Options),
+                                                   C.POINTER(_Image), C.c_int, C.c_char_p,
+                                                   C.c_size_t]
     L.b2r_resize_filter.argtypes = [C.POINTER(_Image), C.POINTER(_Image),
                                     C.c_void_p, C.POINTER(_Roi),
                                     C.POINTER(_Options), C.POINTER(Report),

@@ -59,6 +59,25 @@ def _case(rng):
                 fw=fw, src_win=src_win, dst_win=dst_win, roi=roi)
 
 
+def _int_lsb_tol(oiio, oracle, c, src):
+    """LSB tolerance of an integer destination.  1, except under a FIXED filter
+    width: the reference normalises each axis by its weight sum, and a narrow
+    fixed width can make that sum nearly cancel (rifman 2.5 at 1.3x: outputs of
+    +-1600 from data in [0, 1]) -- in the reference itself.  A float result's
+    rounding error then scales with the magnitude of the normalised weights,
+    and an integer output that happens to land inside the clamp range shows it
+    in LSBs.  The float-destination oracle of the same case measures that
+    magnitude (the float comparison already scales with it)."""
+    if c["fw"] <= 0.0 or c["dt"] not in ("uint8", "uint16"):
+        return 1
+    _, of, _ = run_both(oiio, oracle, src, (c["dh"], c["dw"]), np.float32, c["filt"], c["fw"],
+                        c["src_win"], c["dst_win"], c["roi"])
+    fin = np.isfinite(of)
+    amp = max(1.0, float(np.abs(of[fin]).max())) if fin.any() else 1.0
+    maxv = 255.0 if c["dt"] == "uint8" else 65535.0
+    return max(1, int(np.ceil(amp * maxv * 2.0 ** -21)))
+
+
 @pytest.mark.parametrize("chunk", range(16))
 def test_resize_fuzz(oiio, oracle, chunk):
     rng = np.random.RandomState(20261020 + chunk + SEED)
@@ -72,7 +91,7 @@ def test_resize_fuzz(oiio, oracle, chunk):
             g, o, _ = run_both(oiio, oracle, src, (c["dh"], c["dw"]), _np_dtype(c["dt"]),
                                c["filt"], c["fw"], c["src_win"], c["dst_win"], c["roi"],
                                prefill=pre)
-            check(g, o)
+            check(g, o, lsb_tol=_int_lsb_tol(oiio, oracle, c, src))
         except AssertionError as e:
             raise AssertionError("case %d/%d %r: %s" % (chunk, k, c, e))
 
@@ -315,7 +334,7 @@ def test_resize_fuzz_device_strided(oiio, oracle, chunk):
         assert ok, (c, D.geterror())
         got = D.get_pixels()
         try:
-            check(np.ascontiguousarray(got), ref)
+            check(np.ascontiguousarray(got), ref, lsb_tol=_int_lsb_tol(oiio, oracle, c, src))
         except AssertionError as e:
             raise AssertionError("case %d/%d %r pads=%r: %s"
                                  % (chunk, k, c, (padl, padr, dpl, dpr), e))
