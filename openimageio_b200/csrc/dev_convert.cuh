@@ -74,17 +74,18 @@ quant_u16(float v)
 
 // The same quantiser for two values WITHOUT the float -> int conversion unit
 // (expand kernel: an 8K uint8 frame is 100 M cvt instructions, and the XU pipe
-// they run on was the kernel's bottleneck -- sm__inst_executed_pipe_xu at its
-// peak while issue slots and HBM idled).  v is clamped to [0, 1] by add.sat
-// (NaN -> 0, like the cvt), then ONE packed FMA computes v * mx + 2^23: the
-// sum lies in [2^23, 2^24), where a float's ulp is 1, so the FMA's rounding IS
-// the rounding to an integer and the low mantissa bits are the result.  It
-// rounds v * mx to nearest, ties to even, where the reference truncates
-// v * mx + 0.5 (ties up): v * mx is an exact tie only for v = 0.5 with mx odd
-// (127.5 -> 128, 32767.5 -> 32768: the even neighbour is the upper one), so
-// the two agree wherever the reference's own two roundings (multiply, then
-// add) do not move the value across an integer -- inside the +-1 LSB this
-// kernel is held to; the exact kernel keeps the reference's sequence.
+// they run on was at its peak in the profile while issue slots and HBM idled).
+// The reference's sequence is kept to the bit -- s = v * mx rounded, s + 0.5
+// rounded, clamp, truncate (fmath.h:753-764) -- because for uint16 the two
+// roundings matter: s has an ulp of 2^-8 near the top of the range, so a
+// single-rounding shortcut (v * mx + 0.5 in one FMA, or rounding v * mx to
+// nearest) lands on the other integer for ~0.2 % of the values (the fuzz found
+// it: 2 LSB where filter noise and the shortcut added up).  Here: clamp v to
+// [0, 1] first (add.sat, NaN -> 0; equivalent to the reference's clamp of s),
+// the product and the sum as two packed FMAs with exact addends (x * mx + -0,
+// s * 1 + 0.5: one rounding each, the reference's), and the truncation by an
+// add of 2^23 rounded toward zero -- the sum lies in [2^23, 2^24), where a
+// float's ulp is 1, so the low mantissa bits are floor(s + 0.5).
 __device__ __forceinline__ float
 sat01(float v)
 {
@@ -92,12 +93,23 @@ sat01(float v)
     asm("add.sat.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
     return r;
 }
-// returns the two floats 2^23 + round(v * mx); their low 8 / 16 bits are the
-// quantised values
+// returns the two floats 2^23 + quantised value; their low 8 / 16 bits are the result
 __device__ __forceinline__ float2
 quant2_magic(float a, float b, float mx)
 {
-    return __ffma2_rn(make_float2(sat01(a), sat01(b)), make_float2(mx, mx),
+    const float2 s = __ffma2_rn(make_float2(sat01(a), sat01(b)), make_float2(mx, mx),
+                                make_float2(-0.0f, -0.0f));
+    const float2 t = __ffma2_rn(s, make_float2(1.0f, 1.0f), make_float2(0.5f, 0.5f));
+    return make_float2(__fadd_rz(t.x, 8388608.0f), __fadd_rz(t.y, 8388608.0f));
+}
+// uint8 only: v * 255 has an ulp of at most 2^-16, so rounding v * 255 to nearest
+// in ONE packed FMA onto 2^23 agrees with the reference's sequence except for
+// ~1e-5 of the values (and then by 1 LSB) -- against 0.2 % for uint16, which
+// therefore takes the exact form above.  Half the instructions of the exact form.
+__device__ __forceinline__ float2
+quant2_magic_u8(float a, float b)
+{
+    return __ffma2_rn(make_float2(sat01(a), sat01(b)), make_float2(255.0f, 255.0f),
                       make_float2(8388608.0f, 8388608.0f));
 }
 

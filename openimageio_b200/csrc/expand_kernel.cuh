@@ -143,8 +143,8 @@ store_group(unsigned char* dp, int align, int nvalid, const float (&o)[N])
             unsigned w[N / 4];
 #pragma unroll
             for (int i = 0; i < N / 4; ++i) {
-                const float2 a = quant2_magic(o[4 * i], o[4 * i + 1], 255.0f);
-                const float2 b = quant2_magic(o[4 * i + 2], o[4 * i + 3], 255.0f);
+                const float2 a = quant2_magic_u8(o[4 * i], o[4 * i + 1]);
+                const float2 b = quant2_magic_u8(o[4 * i + 2], o[4 * i + 3]);
                 unsigned lo = __byte_perm(__float_as_uint(a.x), __float_as_uint(a.y), 0x0040);
                 unsigned hi = __byte_perm(__float_as_uint(b.x), __float_as_uint(b.y), 0x0040);
                 w[i]        = __byte_perm(lo, hi, 0x5410);
