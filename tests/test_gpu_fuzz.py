@@ -373,3 +373,42 @@ def test_resize_fuzz_device_strided(oiio, oracle, chunk):
         b8 = lambda t: t.contiguous().view(torch.uint8)
         assert torch.equal(b8(dbig[:, :dpl]), b8(before[:, :dpl]))
         assert torch.equal(b8(dbig[:, dpl + c["dw"]:]), b8(before[:, dpl + c["dw"]:]))
+
+
+# ----------------------------------------------- batches of frames, one launch ----
+@pytest.mark.parametrize("chunk", range(2))
+def test_resize_batch_fuzz(oiio, chunk):
+    """b2r_resize_batch against one call per frame (which the tests above pin to
+    the oracle): random downsizing shapes, types, channel counts and frame counts,
+    so the batch plan's band count (searched per batch size) and the per-channel V
+    geometry vary; the bytes must not."""
+    import torch
+    rng = np.random.RandomState(9100 + chunk + SEED)
+    TT = {"float": torch.float32, "half": torch.float16, "uint8": torch.uint8,
+          "uint16": torch.uint16}
+    IBA = oiio.ImageBufAlgo
+    for k in range(8):
+        st = str(rng.choice(["float", "half", "uint16", "uint8"]))
+        dt = st if rng.rand() < 0.7 else "float"
+        nch = int(rng.choice([1, 2, 3, 4]))
+        sw, sh = int(rng.choice([640, 1000, 1921, 2560])), int(rng.choice([360, 777, 1080]))
+        rx, ry = float(rng.choice([0.5, 0.4, 0.66])), float(rng.choice([0.5, 0.4, 0.66]))
+        dw, dh = max(2, int(sw * rx)), max(2, int(sh * ry))
+        filt = str(rng.choice(["lanczos3", "mitchell", "blackman-harris", "triangle"]))
+        nfr = int(rng.choice([2, 3, 7, 19, 64]))
+        base = synth.image(sw, sh, nch, _np_dtype(st), seed=40 + k)
+        t0 = torch.from_numpy(base.view(np.int16) if st == "uint16" else base).cuda()
+        t0 = t0.view(torch.uint16) if st == "uint16" else t0
+        srcs = [t0 if i == 0 else
+                torch.roll(t0.view(torch.uint8), 5 * i + 1, 0).contiguous().view(t0.dtype)
+                for i in range(nfr)]
+        one = [torch.zeros((dh, dw, nch), dtype=TT[dt], device="cuda") for _ in range(nfr)]
+        many = [torch.zeros_like(t) for t in one]
+        for s_, d in zip(srcs, one):
+            assert IBA.resize(oiio.ImageBuf(d), oiio.ImageBuf(s_), filtername=filt)
+        assert IBA.resize_batch([oiio.ImageBuf(d) for d in many],
+                                [oiio.ImageBuf(s_) for s_ in srcs], filtername=filt)
+        torch.cuda.synchronize()
+        for i, (a, b) in enumerate(zip(one, many)):
+            assert torch.equal(a.view(torch.uint8), b.view(torch.uint8)), \
+                (chunk, k, i, st, dt, nch, (sw, sh), (dw, dh), filt, nfr)
