@@ -41,11 +41,12 @@ pick_vk(int vk, int ht, int* smem)
 StreamKernel
 B2R_NAME(B2R_INST_ST, B2R_INST_NCH)(int vk, int ht, int w2, int hc, int* smem)
 {
-    // highlight compensation fused in: float / half sources, wide geometry
-    // only (anything else runs the three passes)
+    // highlight compensation fused in: float / half sources (integer types
+    // run the three passes)
 #if B2R_INST_ST == 3 || B2R_INST_ST == 2
     if (hc)
-        return w2 == 2 ? pick_vk<2, true>(vk, ht, smem) : nullptr;
+        return w2 == 2 ? pick_vk<2, true>(vk, ht, smem)
+                       : (w2 == 1 ? pick_vk<1, true>(vk, ht, smem) : nullptr);
 #else
     if (hc)
         return nullptr;
