@@ -71,6 +71,15 @@ struct DevicePlan {
     const float* yw = nullptr;
     const float* ywsum = nullptr;
     const float* yfrac = nullptr;
+    // wide (two plain passes over the gather tables; any window width)
+    bool wide = false;
+    int wide_x0 = 0, wide_w = 0;  // source columns the H pass reads
+    const int *gyfirst = nullptr, *gycount = nullptr, *gywoff = nullptr;
+    const float* gyw = nullptr;
+    const unsigned char* gymixed = nullptr;
+    const int *gxfirst = nullptr, *gxcount = nullptr, *gxwoff = nullptr;
+    const float* gxw = nullptr;
+    const unsigned char* gxmixed = nullptr;
     // fused
     bool fused = false;
     FusedPlan fp;  // host copies of strips/bands kept for sizes only
@@ -230,12 +239,14 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
 
     size_t o_strips = 0, o_bands = 0, o_hf = 0, o_hw = 0, o_vr = 0, o_vl = 0,
            o_vf = 0, o_vw = 0, o_vs = 0, o_hm = 0;
+    size_t o_gy[5] = { 0, 0, 0, 0, 0 }, o_gx[5] = { 0, 0, 0, 0, 0 };
     if (filter.separable()) {
         AxisGather ax, ay;
         const int e0a = 16 / basetype_size(src.basetype);
         const int sms = cta_slots / 3;
         bool ok = build_axis_gather(gx, tx, &ax, axis_overscan(gy))
                   && build_axis_gather(gy, ty, &ay, axis_overscan(gx));
+        const bool gather_ok = ok;
         // first choice: the persistent TMA kernel with 512 V threads (wide
         // strips, two work items per SM); it needs a ring-mode shape with a
         // compile-time H window and enough work to fill the SMs that way
@@ -291,6 +302,29 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
             plan->fp.vring.shrink_to_fit();
             plan->fp.vstream.clear();
             plan->fp.vstream.shrink_to_fit();
+        } else if (gather_ok && (ax.maxcount > 16 || ay.maxcount > 16)) {
+            // a shape no fused instantiation covers because a window is too wide
+            // (thumbnail-scale minification): two plain passes over the gather
+            // tables instead of the O(taps^2) exact kernel
+            int lo = INT_MAX, hi = 0;
+            for (int k = 0; k < ax.n; ++k)
+                if (ax.count[k] > 0) {
+                    lo = std::min(lo, ax.first[k]);
+                    hi = std::max(hi, ax.first[k] + ax.count[k]);
+                }
+            if (hi > lo) {
+                plan->wide    = true;
+                plan->wide_x0 = lo;
+                plan->wide_w  = hi - lo;
+                // a column without taps reads nothing; keep its offset in range
+                for (int k = 0; k < ax.n; ++k)
+                    if (ax.count[k] <= 0)
+                        ax.first[k] = lo;
+                o_gy[0] = bb.add(ay.first), o_gy[1] = bb.add(ay.count), o_gy[2] = bb.add(ay.woff);
+                o_gy[3] = bb.add(ay.w), o_gy[4] = bb.add(ay.mixed);
+                o_gx[0] = bb.add(ax.first), o_gx[1] = bb.add(ax.count), o_gx[2] = bb.add(ax.woff);
+                o_gx[3] = bb.add(ax.w), o_gx[4] = bb.add(ax.mixed);
+            }
         }
     }
     CUDA_TRY(cudaMalloc(&plan->blob, std::max<size_t>(bb.host.size(), 256)));
@@ -305,6 +339,18 @@ get_plan(int device, const b2r_image& dst, const b2r_image& src,
     plan->xw      = (const float*)(base + o_xw);
     plan->xwsum   = (const float*)(base + o_xs);
     plan->xfrac   = (const float*)(base + o_xf);
+    if (plan->wide) {
+        plan->gyfirst = (const int*)(base + o_gy[0]);
+        plan->gycount = (const int*)(base + o_gy[1]);
+        plan->gywoff  = (const int*)(base + o_gy[2]);
+        plan->gyw     = (const float*)(base + o_gy[3]);
+        plan->gymixed = base + o_gy[4];
+        plan->gxfirst = (const int*)(base + o_gx[0]);
+        plan->gxcount = (const int*)(base + o_gx[1]);
+        plan->gxwoff  = (const int*)(base + o_gx[2]);
+        plan->gxw     = (const float*)(base + o_gx[3]);
+        plan->gxmixed = base + o_gx[4];
+    }
     plan->ycenter = (const int*)(base + o_yc);
     plan->yw      = (const float*)(base + o_yw);
     plan->ywsum   = (const float*)(base + o_ys);
@@ -1046,6 +1092,39 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             report->fused_vmode = fp.expand ? -fp.vt : fp.vk;
             report->fused_htaps = fp.ht;
         }
+    } else if (plan->wide && path == B2R_PATH_AUTO && filter.separable()
+               && src.nchannels >= nch) {
+        // windows no fused instantiation holds: V pass into a float
+        // intermediate, H pass from it (wide_kernel.cu)
+        WideParams wp;
+        memset(&wp, 0, sizeof(wp));
+        wp.src         = (const unsigned char*)dsrc;
+        wp.src_ystride = srcd.ystride;
+        wp.src_xstride = srcd.xstride;
+        wp.srctype     = src.basetype;
+        wp.src_es      = ses;
+        wp.dst         = (unsigned char*)ddst + (long long)(roi.ybegin - dstd.y) * dstd.ystride
+                 + (long long)(roi.xbegin - dstd.x) * dstd.xstride;
+        wp.dst_ystride = dstd.ystride;
+        wp.dst_xstride = dstd.xstride;
+        wp.dsttype     = dst.basetype;
+        wp.dst_es      = des;
+        wp.nch         = nch;
+        wp.roi_w       = roi_w;
+        wp.roi_h       = roi_h;
+        wp.x0          = plan->wide_x0;
+        wp.tmp_w       = plan->wide_w;
+        wp.yfirst = plan->gyfirst, wp.ycount = plan->gycount, wp.ywoff = plan->gywoff;
+        wp.yw = plan->gyw, wp.ymixed = plan->gymixed;
+        wp.xfirst = plan->gxfirst, wp.xcount = plan->gxcount, wp.xwoff = plan->gxwoff;
+        wp.xw = plan->gxw, wp.xmixed = plan->gxmixed;
+        void* tmp = nullptr;
+        CUDA_TRY(cudaMallocAsync(&tmp, (size_t)roi_h * wp.tmp_w * nch * sizeof(float), stream));
+        wp.tmp = (float*)tmp;
+        launch_resize_wide(wp, stream);
+        cudaFreeAsync(tmp, stream);
+        launched += 2;
+        used = B2R_PATH_FUSED;  // two-pass arithmetic, the fused kernels' tolerance
     } else {
         launch_resize_exact(ep, stream);
         ++launched;

@@ -68,6 +68,30 @@ struct DevImage {
     long long xstride, ystride;  // bytes
 };
 
+// ----------------------------------------------------------------- wide ----
+// Two plain passes over the gather tables for windows of any width
+// (wide_kernel.cu).  Table indices are relative to the ROI's first row /
+// column; source indices to the data window.
+struct WideParams {
+    const unsigned char* src;  // data-window row 0, column 0 (may be virtual for staged rows)
+    long long src_ystride, src_xstride;
+    int srctype, src_es;
+    unsigned char* dst;        // first pixel of the ROI
+    long long dst_ystride, dst_xstride;
+    int dsttype, dst_es;
+    int nch, roi_w, roi_h;
+    float* tmp;                // [roi_h][tmp_w][nch]
+    int x0, tmp_w;             // source columns [x0, x0 + tmp_w) the H pass reads
+    const int *yfirst, *ycount, *ywoff;
+    const float* yw;
+    const unsigned char* ymixed;
+    const int *xfirst, *xcount, *xwoff;
+    const float* xw;
+    const unsigned char* xmixed;
+};
+void
+launch_resize_wide(const WideParams& p, void* stream);
+
 // ---------------------------------------------------------------- exact ----
 // Single-pass kernel in the reference's own tap order (bit-exact path).
 struct ExactParams {

@@ -981,6 +981,93 @@ def test_mip_chain_offset_level0(oiio, oracle, filt, origin, full):
     assert lv == chain.nlevels
 
 
+# ---- thumbnail-scale minification: windows wider than any fused instantiation ----
+def _separable_truth(oiio, src, dst_shape, filt):
+    """resize_ (imagebufalgo_xform.cpp:595-826) for plain windows, evaluated in
+    float64: the reference's per-axis taps (float32 positions and weights, as it
+    computes them), normalised per axis, applied as Wy @ src @ Wx^T in double."""
+    import math
+    dh, dw = dst_shape
+    sh, sw, _ = src.shape
+    native = {"lanczos3": 6.0, "triangle": 2.0, "mitchell": 4.0, "blackman-harris": 3.0}[filt]
+    F = oiio.Filter2D.create(filt, native * max(1.0, dw / sw), native * max(1.0, dh / sh))
+
+    def axis(n_dst, n_src, f1, width):
+        ratio = np.float32(n_dst) / np.float32(n_src)
+        rad = int(math.ceil((width / 2.0) / float(ratio)))
+        W = np.zeros((n_dst, n_src), np.float64)
+        for d in range(n_dst):
+            s = np.float32(d + 0.5) * (np.float32(1.0) / np.float32(n_dst))
+            sf = np.float32(s * np.float32(n_src))
+            si = int(math.floor(sf))
+            frac = np.float32(sf - np.float32(si))
+            w = np.array([f1(float(ratio * np.float32(i - rad - (frac - np.float32(0.5)))))
+                          for i in range(2 * rad + 1)], np.float32)
+            tot = np.float32(w.sum(dtype=np.float32))
+            if tot != 0:
+                w = w / tot
+            for i, wi in enumerate(w):
+                W[d, min(max(si - rad + i, 0), n_src - 1)] += float(wi)
+        return W
+    Wy = axis(dh, sh, F.yfilt, native * max(1.0, dh / sh))
+    Wx = axis(dw, sw, F.xfilt, native * max(1.0, dw / sw))
+    return np.einsum("yr,rxc,dx->ydc", Wy, src.astype(np.float64), Wx)
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("st,dt,nch", [("float", "float", 4), ("uint8", "uint8", 3),
+                                       ("half", "half", 4), ("uint16", "uint16", 1),
+                                       ("float", "uint8", 3), ("float", "float", 5)])
+@pytest.mark.parametrize("filt", ["lanczos3", "triangle", "mitchell"])
+def test_thumbnail_minification_wide_windows(oiio, oracle, st, dt, nch, filt):
+    """1200 x 900 -> 23 x 17 (52:1; lanczos3: 313 taps per axis): no fused kernel
+    holds such a window; the two-pass wide kernels (wide_kernel.cu) run instead
+    of the O(taps^2) exact kernel and match the oracle like the fused ones do.
+    Host and device-resident, with a partial ROI and prefilled destination."""
+    src = synth.image(1200, 900, nch, _np_dtype(st), seed=700)
+    pre = synth.image(23, 17, nch, _np_dtype(dt), seed=701)
+    g, o, rep = run_both(oiio, oracle, src, (17, 23), _np_dtype(dt), filt)
+    if dt == "float":
+        # At this scale the reference adds ~98 000 float products per pixel one
+        # after the other: its own rounding noise (~ sqrt(taps) * 2^-24) is above
+        # 1e-5, so "within 1e-5 of the reference" is not defined by the arithmetic
+        # any more.  Pin both to the float64 evaluation of the same taps instead:
+        # the two-pass result must be at least as close to it as the reference's,
+        # and within the reference's noise of the reference.
+        truth = _separable_truth(oiio, src, (17, 23), filt)
+        e_ref = np.abs(o.astype(np.float64) - truth).max()
+        e_gpu = np.abs(g.astype(np.float64) - truth).max()
+        assert e_gpu <= max(e_ref, 2e-6), (e_gpu, e_ref)
+        assert np.abs(g.astype(np.float64) - o.astype(np.float64)).max() <= 2 * max(e_ref, 5e-6)
+    else:
+        check(g, o)
+    assert rep.path_used == oiio.PATH_FUSED
+    if nch <= 4:  # (five channels: two channel groups, each through the wide kernels)
+        assert rep.kernels_launched == 2
+    g, o, rep = run_both(oiio, oracle, src, (17, 23), _np_dtype(dt), filt, roi=(3, 20, 2, 15),
+                         prefill=pre)
+    if dt == "float":
+        assert np.abs(g.astype(np.float64) - o.astype(np.float64)).max() <= 5e-5
+    else:
+        check(g, o)
+    assert np.array_equal(g[:2], pre[:2]) and np.array_equal(g[:, :3], pre[:, :3])
+
+
+@pytest.mark.gpu
+def test_thumbnail_cropped_source_and_one_axis(oiio, oracle):
+    """A cropped source window (black beyond the data window, clamped taps merged)
+    and minification along one axis only."""
+    src = synth.image(1000, 64, 4, np.float32, seed=702)
+    g, o, rep = run_both(oiio, oracle, src, (64, 20), np.float32, "lanczos3",
+                         src_win=(7, 0, (0, 0, 1020, 64)))
+    check(g, o)
+    assert rep.kernels_launched == 2
+    src = synth.image(64, 1000, 3, np.uint16, seed=703)
+    g, o, rep = run_both(oiio, oracle, src, (20, 64), np.uint16, "blackman-harris")
+    check(g, o)
+
+
 # ---- b2r_resize_batch: many frames of one shape in one launch -------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("st,dt,nch,filt,sshape,dshape,nfr", [
