@@ -1093,7 +1093,8 @@ resize_impl(const b2r_image* dst_in, const b2r_image* src_in,
             report->fused_htaps = fp.ht;
         }
     } else if (plan->wide && path == B2R_PATH_AUTO && filter.separable()
-               && src.nchannels >= nch) {
+               && src.nchannels >= nch && roi_h <= 65535
+               && (size_t)roi_h * plan->wide_w * nch * sizeof(float) <= (size_t(8) << 30)) {
         // windows no fused instantiation holds: V pass into a float
         // intermediate, H pass from it (wide_kernel.cu)
         WideParams wp;
