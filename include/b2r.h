@@ -502,7 +502,12 @@ typedef struct b2r_tile_options {
     int32_t zlevel;                  /* 1..9, 0 -> 1 */
     int32_t nthreads;                /* 0 -> hardware concurrency */
     int32_t first_level;             /* skip levels below this one */
-    int32_t reserved[3];
+    int32_t predictor;               /* 0 / 1 none; 3 = TIFF's floating-point predictor
+                                        (PREDICTOR_FLOATINGPOINT, what the reference's
+                                        TIFF writer sets for float / half data under zip,
+                                        src/tiff.imageio/tiffoutput.cpp:683-690), applied
+                                        per tile row by the re-layout kernel */
+    int32_t reserved[2];
 } b2r_tile_options;
 typedef struct b2r_tileset b2r_tileset;
 B2R_API int b2r_mipchain_encode_tiles(const b2r_mipchain* chain,
@@ -519,6 +524,29 @@ B2R_API int b2r_tileset_tile(const b2r_tileset* ts, int level, int tx, int ty,
  * 5 ms spent setting up the staging slots, 6 host ms blocked on downloads. */
 B2R_API double b2r_tileset_stat(const b2r_tileset* ts, int what);
 B2R_API void b2r_tileset_destroy(b2r_tileset* ts);
+
+/* The container step the reference leaves to its TIFF plugin
+ * (out->open(..., AppendMIPLevel) + small->write(out), maketexture.cpp:957-974;
+ * src/tiff.imageio/tiffoutput.cpp): the tiles of `ts` written as a tiled TIFF
+ * texture, one directory per MIP level in level order (the layout OpenImageIO's
+ * TIFF reader presents as MIP levels when PIXAR_TEXTUREFORMAT is set,
+ * tiffinput.cpp:88,1435), contiguous planar config, IEEE float samples (32 or
+ * 16 bits), Compression = 8 (Adobe deflate: each stored tile is already the
+ * zlib stream TIFF wants) or 1, Predictor = 3 when the tiles were encoded with
+ * it, Software / ImageDescription / PIXAR_TEXTUREFORMAT ("Plain Texture") /
+ * PIXAR_WRAPMODES.  Classic TIFF below 4 GB, BigTIFF above (or when
+ * `bigtiff` != 0).  Tile sizes must be multiples of 16 and every level of the
+ * chain must have been encoded (first_level == 0).  Host code only: no
+ * device work, no copy of the tile bytes other than the file write. */
+typedef struct b2r_tiff_options {
+    const char* image_description; /* NULL: none (maketx stores the SHA-1 and stats here) */
+    const char* software;          /* NULL: "openimageio_b200" */
+    const char* wrapmodes;         /* NULL: "black,black" (maketx's default wrap) */
+    int32_t bigtiff;               /* 0 auto, 1 force BigTIFF */
+    int32_t reserved[3];
+} b2r_tiff_options;
+B2R_API int b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path,
+                                   const b2r_tiff_options* opt, char* err, size_t errlen);
 
 /* ---- the same chain cut into row bands over several GPUs ---------------- */
 /* One process, `ndevices` GPUs of one box (replaces the level loop

@@ -999,8 +999,14 @@ enum MakeTextureMode { MakeTxTexture = 0 };
 /// "maketx:checknan", "maketx:resize" (round up to a power of two),
 /// "maketx:nomipmap", "maketx:hash" (default 1), "format" (output type: levels
 /// written as half are clamped to +-HALF_MAX, :709-714, 943-945).
+/// With `outputfilename` the levels are also written as the tiled TIFF texture
+/// maketx produces (:957-974 + the TIFF plugin): 64x64 tiles ("tile_width"),
+/// deflate, floating-point predictor, one directory per MIP level,
+/// ImageDescription = "oiio:SHA-1=... oiio:ConstantColor=... oiio:AverageColor=..."
+/// (:1936-1975); the file's sample type is "format" (float or half).
 inline Texture
-make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config = {})
+make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config = {},
+             const std::string& outputfilename = "")
 {
     Texture T;
     if (mode != MakeTxTexture) {
@@ -1185,6 +1191,50 @@ make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config =
             break;
         }
         T.levels.push_back(std::move(L));
+    }
+    if (T.error.empty() && !outputfilename.empty()) {
+        if (T.format != "float" && T.format != "half") {
+            T.error = "make_texture: \"" + T.format
+                      + "\" output is not on the B200 path (tiles are float or half); "
+                        "use format=float or half";
+        } else {
+            auto join = [](const std::vector<float>& v) {
+                std::string r;
+                char b[40];
+                for (size_t i = 0; i < v.size(); ++i) {
+                    std::snprintf(b, sizeof(b), "%s%.9g", i ? "," : "", v[i]);
+                    r += b;
+                }
+                return r;
+            };
+            std::string desc;
+            if (!T.sha1.empty())
+                desc += "oiio:SHA-1=" + T.sha1;
+            if (!T.constant_color.empty())
+                desc += std::string(desc.empty() ? "" : " ")
+                        + "oiio:ConstantColor=" + join(T.constant_color);
+            if (!T.average_color.empty())
+                desc += std::string(desc.empty() ? "" : " ")
+                        + "oiio:AverageColor=" + join(T.average_color);
+            b2r_tile_options to;
+            std::memset(&to, 0, sizeof(to));
+            to.tile_width = to.tile_height = config.get_int("tile_width", 64);
+            to.out_basetype = T.format == "half" ? B2R_HALF : B2R_FLOAT;
+            to.compression  = 1;
+            to.zlevel       = config.get_int("tiff:zipquality", 1);
+            to.predictor    = 3;
+            b2r_tileset* ts = nullptr;
+            const std::string wrap = config.get_string("wrapmodes", "black,black");
+            b2r_tiff_options fo;
+            std::memset(&fo, 0, sizeof(fo));
+            fo.image_description = desc.empty() ? nullptr : desc.c_str();
+            fo.wrapmodes         = wrap.c_str();
+            if (b2r_mipchain_encode_tiles(chain, &to, &ts, err, sizeof(err))
+                || b2r_tileset_write_tiff(ts, outputfilename.c_str(), &fo, err, sizeof(err)))
+                T.error = err;
+            if (ts)
+                b2r_tileset_destroy(ts);
+        }
     }
     b2r_mipchain_destroy(chain);
     return T;

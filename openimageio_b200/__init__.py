@@ -76,7 +76,14 @@ class _TileOptions(C.Structure):
     _fields_ = [("tile_width", C.c_int32), ("tile_height", C.c_int32),
                 ("out_basetype", C.c_int32), ("compression", C.c_int32),
                 ("zlevel", C.c_int32), ("nthreads", C.c_int32),
-                ("first_level", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("first_level", C.c_int32), ("predictor", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+class _TiffOptions(C.Structure):
+    _fields_ = [("image_description", C.c_char_p), ("software", C.c_char_p),
+                ("wrapmodes", C.c_char_p), ("bigtiff", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class _PixelStatsC(C.Structure):
@@ -256,6 +263,8 @@ def lib():
     L.b2r_tileset_stat.restype = C.c_double
     L.b2r_tileset_stat.argtypes = [C.c_void_p, C.c_int]
     L.b2r_tileset_destroy.argtypes = [C.c_void_p]
+    L.b2r_tileset_write_tiff.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_TiffOptions),
+                                         C.c_char_p, C.c_size_t]
     L.b2r_mipchain_create_banded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
                                              C.POINTER(_MipOptions), C.POINTER(C.c_int),
                                              C.c_int, C.c_char_p, C.c_size_t]
@@ -1610,8 +1619,9 @@ class TileSet:
     compressed tiles a file plugin stores)."""
 
     def __init__(self, chain, tile=64, half=False, compression=True, zlevel=1,
-                 nthreads=0, first_level=0):
+                 nthreads=0, first_level=0, predictor=0):
         o = _TileOptions()
+        o.predictor = int(predictor)
         o.tile_width = o.tile_height = int(tile)
         o.out_basetype = 10 if half else 11
         o.compression = 1 if compression else 0
@@ -1627,6 +1637,7 @@ class TileSet:
         self.tile = int(tile)
         self.half = bool(half)
         self.compressed = bool(compression)
+        self.predictor = 3 if int(predictor) == 3 else 0
         self.nchannels = chain.nchannels
 
     def __del__(self):
@@ -1659,7 +1670,32 @@ class TileSet:
         if self.compressed:
             b = zlib.decompress(b)
         dt = np.float16 if self.half else np.float32
+        if self.predictor == 3:
+            # undo TIFF's floating-point predictor row by row (libtiff fpAcc)
+            bps = 2 if self.half else 4
+            wc = self.tile * self.nchannels
+            rows = np.frombuffer(b, np.uint8).reshape(self.tile, wc * bps).copy()
+            for k in range(self.nchannels, wc * bps):
+                rows[:, k] += rows[:, k - self.nchannels]
+            planes = rows.reshape(self.tile, bps, wc)[:, ::-1, :]
+            b = np.ascontiguousarray(planes.transpose(0, 2, 1)).tobytes()
         return np.frombuffer(b, dt).reshape(self.tile, self.tile, self.nchannels)
+
+    def write_tiff(self, path, image_description=None, software=None, wrapmodes=None,
+                   bigtiff=False):
+        """The tile set as a tiled TIFF texture, one directory per MIP level
+        (b2r_tileset_write_tiff; what `out->open(AppendMIPLevel)` +
+        `small->write(out)` leave to the TIFF plugin, maketexture.cpp:957-974)."""
+        o = _TiffOptions()
+        o.image_description = image_description.encode() if image_description else None
+        o.software = software.encode() if software else None
+        o.wrapmodes = wrapmodes.encode() if wrapmodes else None
+        o.bigtiff = 1 if bigtiff else 0
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_tileset_write_tiff(self._h, str(path).encode(), C.byref(o), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        return True
 
     def stat(self, what):
         k = {"total_ms": 0, "device_ms": 1, "deflate_ms": 2, "raw_bytes": 3,
@@ -1769,9 +1805,52 @@ def _ceil2(x):
     return p
 
 
-def make_texture(mode, src, config=None, device=0):
+def _write_texture_file(T, outputfilename, cfg):
+    """The tail of make_texture_impl (maketexture.cpp:1884-1990 metadata,
+    :957-974 level output): every level as 64x64 (config "tile_width") tiles,
+    deflated, floating-point predictor, into a tiled TIFF whose
+    ImageDescription carries oiio:SHA-1 / ConstantColor / AverageColor the way
+    the reference crams them in for formats without arbitrary metadata."""
+    if T.format not in ("float", "half"):
+        T.error = ("make_texture: \"%s\" output is not on the B200 path (tiles are "
+                   "float or half); use format=float or half" % T.format)
+        return T
+    desc = []
+    top = T.levels[0]
+    if int(cfg.get("maketx:hash", 1)) and not top.on_device:
+        # addlHashData (:1909-1926): the options that change the MIP levels
+        extra = (cfg.get("maketx:filtername", "box") or "box") + " "
+        if float(cfg.get("maketx:sharpen", 0.0) or 0.0):
+            extra += "sharpen_A=%g " % float(cfg["maketx:sharpen"])
+        if cfg.get("maketx:highlightcomp"):
+            extra += "highlightcomp=1 "
+        if cfg.get("maketx:keepaspect"):
+            extra += "keepaspect=1 "
+        T.sha1 = ImageBufAlgo.computePixelHashSHA1(top, extra, blocksize=256)
+        desc.append("oiio:SHA-1=" + T.sha1)
+    join = lambda v: ",".join(str(np.float32(x)) for x in v)
+    if T.constant_color is not None:
+        desc.append("oiio:ConstantColor=" + join(T.constant_color))
+    if T.average_color is not None and int(cfg.get("maketx:compute_average", 1)):
+        desc.append("oiio:AverageColor=" + join(T.average_color))
+    try:
+        ts = TileSet(T.chain, tile=int(cfg.get("tile_width", 64) or 64),
+                     half=T.format == "half", zlevel=int(cfg.get("tiff:zipquality", 1) or 1),
+                     predictor=3)
+        ts.write_tiff(outputfilename, image_description=" ".join(desc) or None,
+                      wrapmodes=cfg.get("wrapmodes", None))
+    except B2RError as e:
+        T.error = str(e)
+        return T
+    T.tiles = ts
+    T.filename = str(outputfilename)
+    return T
+
+
+def make_texture(mode, src, config=None, device=0, outputfilename=None):
     """ImageBufAlgo::make_texture(mode, input, outputfilename, configspec) for
-    mode MakeTxTexture, returning a `Texture` instead of writing a file.
+    mode MakeTxTexture, returning a `Texture`; with `outputfilename` the
+    levels are also written as a tiled TIFF texture (_write_texture_file).
     config: dict of the maketx attributes that select pixel work --
     "maketx:filtername" ("box"; "post-" / "unsharp-<f>" prefixes as in
     maketexture.cpp:759-768), "maketx:highlightcomp", "maketx:sharpen",
@@ -1883,6 +1962,9 @@ def make_texture(mode, src, config=None, device=0):
     clamp_half = out_format == "half"
     T.levels = [top]
     if cfg.get("maketx:nomipmap"):
+        if outputfilename:
+            T.error = ("make_texture: file output of a texture without MIP levels "
+                       "(maketx:nomipmap) is not on the B200 path")
         return T
     sharpen = float(cfg.get("maketx:sharpen", 0.0) or 0.0)
     sharpen_first, sharpenfilt = True, "gaussian"
@@ -1902,6 +1984,8 @@ def make_texture(mode, src, config=None, device=0):
     for lvl in range(1, chain.nlevels):
         T.levels.append(ImageBuf(chain.download(lvl)))
     T.chain = chain
+    if outputfilename:
+        return _write_texture_file(T, outputfilename, cfg)
     return T
 
 

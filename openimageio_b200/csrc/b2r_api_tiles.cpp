@@ -10,13 +10,21 @@
 //   device : relayout(chunk c+2) | D2H(chunk c+1)      (stream-ordered, 3 slots)
 //   host   :                                deflate(chunk c)   (nthreads workers)
 //
-// The result is an in-memory tile set (per level: a grid of compressed tiles);
-// the container formats themselves (TIFF / OpenEXR headers, offsets tables)
-// stay with the reference's file plugins.
+// The result is an in-memory tile set (per level: a grid of compressed tiles).
+// b2r_tileset_write_tiff puts the TIFF container around it (one directory per
+// MIP level, the layout of a maketx .tx file: src/tiff.imageio/tiffoutput.cpp);
+// with predictor = 3 the re-layout kernel has already applied the floating-point
+// predictor the reference's TIFF writer uses (tiffoutput.cpp:683-690).  OpenEXR
+// containers stay with the reference's plugin.
 #include "api_internal.h"
 
 #include <zlib.h>
 
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
 #include <atomic>
 #include <mutex>
 #include <chrono>
@@ -30,7 +38,8 @@ struct b2r_tileset {
         int w = 0, h = 0, ntx = 0, nty = 0;
         std::vector<std::vector<unsigned char>> tiles;  // nty * ntx, raster order
     };
-    int nch = 0, tile_w = 0, tile_h = 0, out_basetype = 0, compression = 0;
+    int nch = 0, tile_w = 0, tile_h = 0, out_basetype = 0, compression = 0, predictor = 0;
+    int first_level = 0;
     std::vector<Level> levels;
     long long raw_bytes = 0, stored_bytes = 0;
     float total_ms = 0, device_ms = 0, deflate_busy_ms = 0, setup_ms = 0, wait_ms = 0;
@@ -123,9 +132,18 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
     const int comp   = to ? to->compression : 1;
     const int zlevel = (to && to->zlevel > 0) ? std::min(9, (int)to->zlevel) : 1;
     const int first  = (to && to->first_level > 0) ? to->first_level : 0;
+    const int pred   = (to && to->predictor == 3) ? 3 : 0;
     if (obt != B2R_FLOAT && obt != B2R_HALF) {
         set_err(err, errlen, "encode_tiles: tiles are float32 or half");
         return B2R_ERR_TYPES;
+    }
+    if (to && to->predictor != 0 && to->predictor != 1 && to->predictor != 3) {
+        set_err(err, errlen, "encode_tiles: predictor must be 0, 1 (none) or 3 (floating point)");
+        return B2R_ERR_INVALID;
+    }
+    if (pred && (size_t(tile_w) * chain->nch * (obt == B2R_HALF ? 2 : 4)) % 4 != 0) {
+        set_err(err, errlen, "encode_tiles: predictor needs tile rows of whole 32-bit words");
+        return B2R_ERR_INVALID;
     }
     int nthreads = (to && to->nthreads > 0) ? to->nthreads
                                             : (int)std::thread::hardware_concurrency();
@@ -142,6 +160,8 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
     ts->tile_h       = tile_h;
     ts->out_basetype = obt;
     ts->compression  = comp;
+    ts->predictor    = pred;
+    ts->first_level  = first;
 
     // chunks of whole tile rows, at most ~64 MB of tiles each
     struct Chunk {
@@ -213,8 +233,12 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
         const auto& CL = chain->levels[c.level];
         const auto& TL = ts->levels[c.level];
         const int s    = i % NSLOT;
-        launch_tile_relayout((const float*)CL.px, CL.w, CL.h, nch, tile_w, tile_h, c.ty0, c.ty1,
-                             obt == B2R_HALF, dslot[s], sk);
+        if (pred)
+            launch_tile_relayout_fp_predictor((const float*)CL.px, CL.w, CL.h, nch, tile_w,
+                                              tile_h, c.ty0, c.ty1, obt == B2R_HALF, dslot[s], sk);
+        else
+            launch_tile_relayout((const float*)CL.px, CL.w, CL.h, nch, tile_w, tile_h, c.ty0,
+                                 c.ty1, obt == B2R_HALF, dslot[s], sk);
         cudaEventRecord(relaid, sk);
         cudaStreamWaitEvent(sc, relaid, 0);
         cudaMemcpyAsync(hslot[s], dslot[s], size_t(c.ty1 - c.ty0) * TL.ntx * tile_bytes,
@@ -369,4 +393,247 @@ extern "C" void
 b2r_tileset_destroy(b2r_tileset* ts)
 {
     delete ts;
+}
+
+
+// ---------------------------------------------------------------------------
+// TIFF container around the stored tiles
+// ---------------------------------------------------------------------------
+namespace {
+
+struct TiffTag {
+    uint16_t tag, type;  // type: 2 ASCII, 3 SHORT, 4 LONG, 16 LONG8
+    uint64_t count;
+    std::vector<unsigned char> data;
+};
+
+template<typename T>
+void
+put(std::vector<unsigned char>& v, T x)
+{
+    // the file is little-endian ("II"), like every host this library runs on
+    const unsigned char* p = reinterpret_cast<const unsigned char*>(&x);
+    v.insert(v.end(), p, p + sizeof(T));
+}
+
+TiffTag
+tag_shorts(uint16_t tag, const std::vector<uint16_t>& vals)
+{
+    TiffTag t { tag, 3, vals.size(), {} };
+    for (uint16_t x : vals)
+        put(t.data, x);
+    return t;
+}
+
+TiffTag
+tag_long(uint16_t tag, uint32_t v)
+{
+    TiffTag t { tag, 4, 1, {} };
+    put(t.data, v);
+    return t;
+}
+
+TiffTag
+tag_ascii(uint16_t tag, const std::string& s)
+{
+    TiffTag t { tag, 2, s.size() + 1, {} };
+    t.data.assign(s.begin(), s.end());
+    t.data.push_back(0);
+    return t;
+}
+
+TiffTag
+tag_offsets(uint16_t tag, const std::vector<uint64_t>& vals, bool big)
+{
+    TiffTag t { tag, uint16_t(big ? 16 : 4), vals.size(), {} };
+    for (uint64_t x : vals) {
+        if (big)
+            put(t.data, x);
+        else
+            put(t.data, uint32_t(x));
+    }
+    return t;
+}
+
+struct File {
+    FILE* f      = nullptr;
+    uint64_t pos = 0;
+    bool ok      = true;
+    ~File()
+    {
+        if (f)
+            fclose(f);
+    }
+    void write(const void* p, size_t n)
+    {
+        if (n && fwrite(p, 1, n, f) != n)
+            ok = false;
+        pos += n;
+    }
+    void align2()
+    {
+        if (pos & 1) {
+            const char z = 0;
+            write(&z, 1);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int
+b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_options* opt,
+                       char* err, size_t errlen)
+{
+    if (!ts || !path) {
+        set_err(err, errlen, "write_tiff: null argument");
+        return B2R_ERR_INVALID;
+    }
+    if (ts->levels.empty() || ts->first_level != 0) {
+        set_err(err, errlen, "write_tiff: the tile set must hold every level of the chain");
+        return B2R_ERR_INVALID;
+    }
+    if (ts->tile_w % 16 || ts->tile_h % 16) {
+        set_err(err, errlen, "write_tiff: TIFF tile sizes are multiples of 16 (%d x %d)",
+                ts->tile_w, ts->tile_h);
+        return B2R_ERR_INVALID;
+    }
+    const int nch = ts->nch;
+    const int bps = ts->out_basetype == B2R_HALF ? 16 : 32;
+    // classic TIFF holds 32-bit offsets; leave room for the directories
+    uint64_t payload = 0, ntiles = 0;
+    for (const auto& L : ts->levels)
+        for (const auto& t : L.tiles) {
+            payload += t.size() + 1;
+            ++ntiles;
+        }
+    const bool big = (opt && opt->bigtiff)
+                     || payload + ntiles * 16 + ts->levels.size() * 4096 + 65536 > 0xfff00000ull;
+    const std::string software = (opt && opt->software) ? opt->software : "openimageio_b200";
+    const std::string wrap     = (opt && opt->wrapmodes) ? opt->wrapmodes : "black,black";
+
+    File out;
+    out.f = fopen(path, "wb");
+    if (!out.f) {
+        set_err(err, errlen, "write_tiff: could not open \"%s\"", path);
+        return B2R_ERR_INVALID;
+    }
+    std::vector<unsigned char> hdr;
+    hdr.push_back('I');
+    hdr.push_back('I');
+    if (big) {
+        put(hdr, uint16_t(43));
+        put(hdr, uint16_t(8));
+        put(hdr, uint16_t(0));
+        put(hdr, uint64_t(0));
+    } else {
+        put(hdr, uint16_t(42));
+        put(hdr, uint32_t(0));
+    }
+    out.write(hdr.data(), hdr.size());
+    uint64_t link_pos = big ? 8 : 4;  // where the offset of the next directory goes
+    const size_t inline_bytes = big ? 8 : 4;
+
+    for (const auto& L : ts->levels) {
+        std::vector<uint64_t> offs, cnts;
+        offs.reserve(L.tiles.size());
+        cnts.reserve(L.tiles.size());
+        for (const auto& t : L.tiles) {
+            out.align2();
+            offs.push_back(out.pos);
+            cnts.push_back(t.size());
+            out.write(t.data(), t.size());
+        }
+        std::vector<TiffTag> tags;
+        tags.push_back(tag_long(256, (uint32_t)L.w));
+        tags.push_back(tag_long(257, (uint32_t)L.h));
+        tags.push_back(tag_shorts(258, std::vector<uint16_t>(nch, (uint16_t)bps)));
+        tags.push_back(tag_shorts(259, { uint16_t(ts->compression ? 8 : 1) }));
+        tags.push_back(tag_shorts(262, { uint16_t(nch >= 3 ? 2 : 1) }));
+        if (opt && opt->image_description)
+            tags.push_back(tag_ascii(270, opt->image_description));
+        tags.push_back(tag_shorts(277, { (uint16_t)nch }));
+        tags.push_back(tag_shorts(284, { 1 }));
+        tags.push_back(tag_ascii(305, software));
+        if (ts->predictor == 3)
+            tags.push_back(tag_shorts(317, { 3 }));
+        tags.push_back(tag_long(322, (uint32_t)ts->tile_w));
+        tags.push_back(tag_long(323, (uint32_t)ts->tile_h));
+        tags.push_back(tag_offsets(324, offs, big));
+        tags.push_back(tag_offsets(325, cnts, big));
+        // channels beyond the colour ones: alpha (associated, the reference's
+        // default: tiffoutput.cpp ExtraSamples) then unspecified
+        const int ncolor = nch >= 3 ? 3 : 1;
+        if (nch > ncolor) {
+            std::vector<uint16_t> extra(nch - ncolor, 0);
+            extra[0] = 1;
+            tags.push_back(tag_shorts(338, extra));
+        }
+        tags.push_back(tag_shorts(339, std::vector<uint16_t>(nch, 3)));
+        tags.push_back(tag_ascii(33302, "Plain Texture"));
+        tags.push_back(tag_ascii(33303, wrap));
+        std::sort(tags.begin(), tags.end(),
+                  [](const TiffTag& a, const TiffTag& b) { return a.tag < b.tag; });
+        std::vector<uint64_t> placed(tags.size(), 0);
+        for (size_t i = 0; i < tags.size(); ++i)
+            if (tags[i].data.size() > inline_bytes) {
+                out.align2();
+                placed[i] = out.pos;
+                out.write(tags[i].data.data(), tags[i].data.size());
+            }
+        out.align2();
+        const uint64_t ifd = out.pos;
+        std::vector<unsigned char> dir;
+        if (big)
+            put(dir, uint64_t(tags.size()));
+        else
+            put(dir, uint16_t(tags.size()));
+        for (size_t i = 0; i < tags.size(); ++i) {
+            put(dir, tags[i].tag);
+            put(dir, tags[i].type);
+            if (big)
+                put(dir, uint64_t(tags[i].count));
+            else
+                put(dir, uint32_t(tags[i].count));
+            if (tags[i].data.size() <= inline_bytes) {
+                std::vector<unsigned char> v = tags[i].data;
+                v.resize(inline_bytes, 0);
+                dir.insert(dir.end(), v.begin(), v.end());
+            } else if (big) {
+                put(dir, uint64_t(placed[i]));
+            } else {
+                put(dir, uint32_t(placed[i]));
+            }
+        }
+        const uint64_t next_link = ifd + dir.size();
+        if (big)
+            put(dir, uint64_t(0));
+        else
+            put(dir, uint32_t(0));
+        out.write(dir.data(), dir.size());
+        // link the previous directory (or the header) to this one
+        if (fseeko(out.f, (off_t)link_pos, SEEK_SET) != 0)
+            out.ok = false;
+        if (big) {
+            const uint64_t v = ifd;
+            if (fwrite(&v, 1, 8, out.f) != 8)
+                out.ok = false;
+        } else {
+            const uint32_t v = (uint32_t)ifd;
+            if (fwrite(&v, 1, 4, out.f) != 4)
+                out.ok = false;
+        }
+        if (fseeko(out.f, 0, SEEK_END) != 0)
+            out.ok = false;
+        link_pos = next_link;
+        if (!big && out.pos > 0xffffffffull)
+            out.ok = false;
+    }
+    if (fflush(out.f) != 0)
+        out.ok = false;
+    if (!out.ok) {
+        set_err(err, errlen, "write_tiff: write to \"%s\" failed", path);
+        return B2R_ERR_INVALID;
+    }
+    return B2R_OK;
 }

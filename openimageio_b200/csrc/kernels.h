@@ -499,6 +499,12 @@ launch_pixel_bytes_copy(void* dst, long long dst_xstride, long long dst_ystride,
 void
 launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int tile_h,
                      int ty0, int ty1, int out_half, void* out, void* stream);
+// the same with TIFF's floating-point predictor applied per tile row
+// (tile_w * nch * element size must be a multiple of 4)
+void
+launch_tile_relayout_fp_predictor(const float* level, int w, int h, int nch, int tile_w,
+                                  int tile_h, int ty0, int ty1, int out_half, void* out,
+                                  void* stream);
 
 // float -> dst type over a rectangle of `row_elems` x `height` elements
 // (the copy-back step for (dst,src) pairs computed through a float temporary)

@@ -45,7 +45,83 @@ tile_relayout_kernel(const float* __restrict__ src, int w, int h, int nch, int t
     }
 }
 
+// The same tiles with TIFF's floating-point predictor applied to every tile row
+// (PREDICTOR_FLOATINGPOINT, what the reference's TIFF writer sets for float /
+// half data under zip: tiffoutput.cpp:683-690; libtiff's fpDiff): the row's
+// samples are split into byte planes, most significant byte first, and every
+// byte of the re-ordered row has the byte `nch` positions before it subtracted.
+// One thread = four consecutive bytes of a predicted tile row (one 32-bit store);
+// a byte's two samples come from the level through L1.
+template<bool HALF>
+__device__ __forceinline__ unsigned
+tile_sample_byte(const float* __restrict__ src, int w, int h, int nch, int y, int x0,
+                 int count, int plane)
+{
+    const int x = x0 + count / nch;
+    float v     = 0.0f;
+    if (y < h && x < w)
+        v = __ldg(src + ((long long)y * w + x) * nch + (count % nch));
+    if (HALF)
+        return ((unsigned)__half_as_ushort(__float2half_rn(v)) >> (8 * (1 - plane))) & 0xffu;
+    return (__float_as_uint(v) >> (8 * (3 - plane))) & 0xffu;
+}
+
+template<bool HALF>
+__global__ void __launch_bounds__(256)
+tile_relayout_fp_predictor_kernel(const float* __restrict__ src, int w, int h, int nch,
+                                  int tile_w, int tile_h, int ntx, int ty0, long long total_words,
+                                  unsigned* __restrict__ out)
+{
+    pdl_prologue();
+    const int bps       = HALF ? 2 : 4;
+    const int wc        = tile_w * nch;  // samples of a tile row
+    const int row_words = wc * bps / 4;  // tile_w is a multiple of 16
+    const long long tile_words = (long long)row_words * tile_h;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_words;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / tile_words;
+        const int e       = int(i - t * tile_words);
+        const int yy      = e / row_words;
+        const int b0      = (e - yy * row_words) * 4;  // first byte of the predicted row
+        const int y       = (ty0 + int(t / ntx)) * tile_h + yy;
+        const int x0      = int(t % ntx) * tile_w;
+        unsigned word     = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int b = b0 + k;
+            unsigned v  = tile_sample_byte<HALF>(src, w, h, nch, y, x0, b % wc, b / wc);
+            if (b >= nch) {
+                const int a = b - nch;
+                v -= tile_sample_byte<HALF>(src, w, h, nch, y, x0, a % wc, a / wc);
+            }
+            word |= (v & 0xffu) << (8 * k);
+        }
+        out[i] = word;
+    }
+}
+
 }  // namespace
+
+void
+launch_tile_relayout_fp_predictor(const float* level, int w, int h, int nch, int tile_w,
+                                  int tile_h, int ty0, int ty1, int out_half, void* out,
+                                  void* stream)
+{
+    const int ntx         = (w + tile_w - 1) / tile_w;
+    const long long total = (long long)(ty1 - ty0) * ntx * tile_w * tile_h * nch
+                            * (out_half ? 2 : 4) / 4;
+    if (total <= 0)
+        return;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    if (out_half)
+        launch_pdl(tile_relayout_fp_predictor_kernel<true>, dim3(blocks), dim3(256), 0,
+                   (cudaStream_t)stream, level, w, h, nch, tile_w, tile_h, ntx, ty0, total,
+                   (unsigned*)out);
+    else
+        launch_pdl(tile_relayout_fp_predictor_kernel<false>, dim3(blocks), dim3(256), 0,
+                   (cudaStream_t)stream, level, w, h, nch, tile_w, tile_h, ntx, ty0, total,
+                   (unsigned*)out);
+}
 
 void
 launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int tile_h,

@@ -42,7 +42,7 @@ run_errors()
     return 0;
 }
 
-// iba_cli maketx in.raw w h nch basetype filter hicomp(0|1) out.raw
+// iba_cli maketx in.raw w h nch basetype filter hicomp(0|1) out.raw [out.tif]
 //   ImageBufAlgo::make_texture: every level appended to out.raw (float32),
 //   "levels=N sha1=... avg0=..." on stdout
 static int
@@ -58,7 +58,8 @@ run_maketx(char** argv)
     ImageBuf src(sspec, px.data(), B2R_MEM_HOST);
     Texture T = ImageBufAlgo::make_texture(ImageBufAlgo::MakeTxTexture, src,
                                            { { "maketx:filtername", argv[7] },
-                                             { "maketx:highlightcomp", atoi(argv[8]) } });
+                                             { "maketx:highlightcomp", atoi(argv[8]) } },
+                                           argv[10] ? argv[10] : "");
     if (!T.ok()) {
         fprintf(stderr, "%s\n", T.error.c_str());
         return 4;
@@ -102,7 +103,7 @@ main(int argc, char** argv)
 {
     if (argc >= 2 && std::string(argv[1]) == "errors")
         return run_errors();
-    if (argc == 10 && std::string(argv[1]) == "maketx")
+    if ((argc == 10 || argc == 11) && std::string(argv[1]) == "maketx")
         return run_maketx(argv);
     if (argc == 12 && std::string(argv[1]) == "otresize")
         return run_otresize(argv);

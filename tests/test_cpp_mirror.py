@@ -153,6 +153,35 @@ def test_cpp_make_texture(iba_cli, oracle, tmp_path, filt, hicomp):
 
 
 @pytest.mark.gpu
+def test_cpp_make_texture_writes_tiff(iba_cli, tmp_path):
+    """make_texture(..., outputfilename) of the C++ mirror: the file's
+    directories are the levels it returned (float, Predictor 3, 64x64 deflate
+    tiles), the ImageDescription carries the SHA-1 it reports."""
+    import tiff_mini
+    src = synth.image(200, 330, 3, np.float32, seed=95)
+    fin, fout, ftif = (str(tmp_path / n) for n in ("in.raw", "out.raw", "out.tif"))
+    src.tofile(fin)
+    out = subprocess.check_output([iba_cli, "maketx", fin, "200", "330", "3", "11", "lanczos3",
+                                   "0", fout, ftif], text=True)
+    kv = dict(t.split("=") for t in out.split())
+    dirs = tiff_mini.read(ftif)
+    assert len(dirs) == int(kv["levels"])
+    got = np.fromfile(fout, np.float32)
+    off = 0
+    for d in dirs:
+        n = d["pixels"].size
+        assert np.array_equal(d["pixels"].ravel(), got[off:off + n])
+        off += n
+        assert d["tags"][317] == [3] and d["tags"][322] == [64] and d["tags"][259] == [8]
+    assert off == got.size
+    assert ("oiio:SHA-1=" + kv["sha1"]) in dirs[0]["tags"][270]
+    assert "oiio:AverageColor=" in dirs[0]["tags"][270]
+    theirs = tiff_mini.read_libtiff(ftif, 3)
+    if theirs is not None:
+        assert all(np.array_equal(a, d["pixels"]) for a, d in zip(theirs, dirs))
+
+
+@pytest.mark.gpu
 def test_cpp_oiiotool_resize(iba_cli, oracle, tmp_path):
     src = synth.image(180, 120, 3, np.float32, seed=94)
     fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")

@@ -492,3 +492,37 @@ def test_pixel_hash_sha1_matches_hashlib(oiio, shape, dt, blocksize):
         roi = oiio.ROI(3, shape[1] - 5, 2, shape[0] - 7, 0, 1, 0, shape[2])
         got = oiio.ImageBufAlgo.computePixelHashSHA1(a, "x", roi=roi, blocksize=blocksize)
         assert got == _oiio_hash(a[2:shape[0] - 7, 3:shape[1] - 5], "x", blocksize)
+
+
+# ---- the TIFF checker of the tile-output tests, pinned against libtiff ------
+@pytest.mark.parametrize("big", [False, True])
+@pytest.mark.parametrize("predictor", [0, 3])
+@pytest.mark.parametrize("nch", [1, 3, 4])
+def test_tiff_mini_against_libtiff(tmp_path, nch, predictor, big):
+    """tests/tiff_mini.py (the numpy TIFF reader / writer the GPU tests use to
+    check b2r_tileset_write_tiff) against libtiff itself, through OpenCV / PIL:
+    a file it writes -- tiled, deflate, Predictor 3 as libtiff's fpDiff defines
+    it, classic and BigTIFF, one directory per level -- decodes to the same
+    pixels in both readers."""
+    import tiff_mini
+    rng = np.random.default_rng(40 + nch)
+    levels = [rng.standard_normal((h, w, nch)).astype(np.float32)
+              for h, w in ((150, 200), (75, 100), (1, 1))]
+    path = tmp_path / "m.tif"
+    tiff_mini.write(path, levels, tile=64, predictor=predictor, big=big)
+    mine = tiff_mini.read(path)
+    assert len(mine) == 3
+    for a, b in zip(levels, mine):
+        assert np.array_equal(a, b["pixels"]) and b["padding_is_zero"]
+        assert b["big"] == big
+    theirs = tiff_mini.read_libtiff(path, nch)
+    if theirs is None:
+        pytest.skip("neither OpenCV nor PIL here")
+    assert len(theirs) == 3
+    for a, b in zip(levels, theirs):
+        assert np.array_equal(a, b)
+    # half samples: only the numpy reader decodes them
+    halves = [a.astype(np.float16) for a in levels]
+    tiff_mini.write(path, halves, tile=32, predictor=predictor, big=big)
+    for a, b in zip(halves, tiff_mini.read(path)):
+        assert np.array_equal(a, b["pixels"])

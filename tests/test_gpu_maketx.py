@@ -260,6 +260,43 @@ def test_make_texture_reports_statistics(oiio, oracle):
     assert all(abs(a - r["avg"]) < 1e-6 for a, r in zip(T.average_color, ref))
 
 
+@pytest.mark.parametrize("fmt", ["float", "half"])
+def test_make_texture_writes_a_tiff_texture(oiio, tmp_path, fmt):
+    """make_texture with an output file name: the levels it returns are the
+    levels in the file (tiled TIFF, one directory per level, Predictor 3), and the
+    ImageDescription carries the SHA-1 of the top level and the average colour
+    (maketexture.cpp:1928-1975)."""
+    import hashlib
+    import tiff_mini
+    src = synth.image(300, 200, 4, np.float32, seed=77)
+    path = tmp_path / "out.tx.tif"
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src),
+                          {"maketx:filtername": "lanczos3", "format": fmt},
+                          outputfilename=path)
+    assert T.ok, T.error
+    dirs = tiff_mini.read(path)
+    assert len(dirs) == len(T.levels)
+    for lv, d in enumerate(dirs):
+        want = np.asarray(T.levels[lv].pixels)
+        if fmt == "half":
+            want = want.astype(np.float16)
+        assert np.array_equal(d["pixels"], want), lv
+        assert d["tags"][317] == [3] and d["tags"][322] == [64]
+    desc = dirs[0]["tags"][270]
+    assert "oiio:SHA-1=" + oiio.ImageBufAlgo.computePixelHashSHA1(
+        T.levels[0], "lanczos3 ", blocksize=256) in desc
+    assert "oiio:AverageColor=" in desc
+    avg = [float(x) for x in desc.split("oiio:AverageColor=")[1].split()[0].split(",")]
+    assert np.allclose(avg, src.reshape(-1, 4).mean(0), atol=1e-5)
+    if fmt == "float":
+        theirs = tiff_mini.read_libtiff(path, 4)
+        if theirs is not None:
+            assert all(np.array_equal(a, np.asarray(l.pixels)) for a, l in zip(theirs, T.levels))
+    bad = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"format": "uint8"},
+                            outputfilename=path)
+    assert not bad.ok and "float or half" in bad.error
+
+
 # ---- the chain cut into row bands (b2r_mipchain_create_banded) ------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("filt", ["box", "lanczos3", "triangle"])
@@ -307,6 +344,84 @@ def test_encode_tiles_roundtrip(oiio, shape, tile, half):
                 t = ts.tile_pixels(lv, tx, ty)
                 assert np.array_equal(t, ref[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile])
     assert ts.stat("stored_bytes") > 0 and ts.stat("raw_bytes") >= ts.stat("stored_bytes") * 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("nch,shape,tile", [(3, (300, 500), 64), (4, (257, 130), 64),
+                                            (1, (200, 333), 32), (2, (97, 130), 16)])
+def test_encode_tiles_fp_predictor(oiio, nch, shape, tile, half):
+    """predictor = 3: the re-layout kernel applies TIFF's floating-point
+    predictor per tile row (tiffoutput.cpp:683-690; libtiff fpDiff).  The stored
+    bytes equal the numpy restatement of fpDiff applied to the plain tiles, byte
+    for byte, and decode back to the level."""
+    import zlib
+    import tiff_mini
+    h, w = shape
+    src = synth.image(w, h, nch, np.float32, seed=930 + tile + nch)
+    ch = oiio.MipChain(src, filtername="lanczos3")
+    plain = oiio.TileSet(ch, tile=tile, half=half, zlevel=1, nthreads=4)
+    pred = oiio.TileSet(ch, tile=tile, half=half, zlevel=1, nthreads=4, predictor=3)
+    bps = 2 if half else 4
+    for lv in range(ch.nlevels):
+        _, _, ntx, nty = plain.level_info(lv)
+        for ty in range(nty):
+            for tx in range(ntx):
+                raw = np.frombuffer(zlib.decompress(plain.tile_bytes(lv, tx, ty)), np.uint8)
+                want = np.concatenate([tiff_mini.fp_predict_row(r, bps, nch)
+                                       for r in raw.reshape(tile, -1)])
+                got = np.frombuffer(zlib.decompress(pred.tile_bytes(lv, tx, ty)), np.uint8)
+                assert np.array_equal(got, want), (lv, tx, ty)
+                assert np.array_equal(pred.tile_pixels(lv, tx, ty).view(np.uint8),
+                                      plain.tile_pixels(lv, tx, ty).view(np.uint8))
+    with pytest.raises(oiio.B2RError, match="predictor"):
+        oiio.TileSet(ch, tile=tile, predictor=2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("half,predictor,big", [(False, 3, False), (False, 0, True),
+                                                (True, 3, False), (True, 0, False)])
+@pytest.mark.parametrize("nch,shape", [(4, (300, 500)), (3, (512, 512)), (1, (97, 130))])
+def test_write_tiff_texture(oiio, tmp_path, nch, shape, half, predictor, big):
+    """maketx's output file (maketexture.cpp:957-974 + the TIFF plugin): chain ->
+    tiles -> a tiled TIFF with one directory per MIP level.  libtiff (OpenCV /
+    PIL) reads every float level back bit for bit; half files go through the
+    numpy reader that test_cpu pins against libtiff."""
+    import tiff_mini
+    h, w = shape
+    src = synth.image(w, h, nch, np.float32, seed=960 + nch)
+    ch = oiio.MipChain(src, filtername="lanczos3")
+    ts = oiio.TileSet(ch, tile=64, half=half, zlevel=1, nthreads=4, predictor=predictor)
+    path = tmp_path / "tex.tif"
+    assert ts.write_tiff(path, image_description="SHA-1=0123", bigtiff=big)
+    dirs = tiff_mini.read(path)
+    assert len(dirs) == ch.nlevels
+    for lv, d in enumerate(dirs):
+        px = ch.download(lv)
+        want = px.astype(np.float16) if half else px
+        assert d["pixels"].shape == want.shape
+        assert np.array_equal(d["pixels"], want), "level %d" % lv
+        assert d["padding_is_zero"] and d["big"] == big
+        t = d["tags"]
+        assert t[322] == [64] and t[323] == [64] and t[259] == [8]
+        assert t.get(317, [1]) == [predictor or 1]
+        assert t[270] == "SHA-1=0123" and t[305] == "openimageio_b200"
+        assert t[33302] == "Plain Texture" and t[33303] == "black,black"
+        assert t[262] == [2 if nch >= 3 else 1]
+        assert (338 in t) == (nch in (2, 4))
+    if not half:
+        theirs = tiff_mini.read_libtiff(path, nch)
+        if theirs is not None:
+            assert len(theirs) == ch.nlevels
+            for lv, im in enumerate(theirs):
+                assert np.array_equal(im, ch.download(lv)), "libtiff level %d" % lv
+    # a tile set that skips levels, or tiles TIFF cannot hold, is refused
+    with pytest.raises(oiio.B2RError, match="every level"):
+        oiio.TileSet(ch, tile=64, first_level=1).write_tiff(path)
+    with pytest.raises(oiio.B2RError, match="multiples of 16"):
+        oiio.TileSet(ch, tile=40).write_tiff(path)
+    with pytest.raises(oiio.B2RError, match="could not open"):
+        ts.write_tiff(tmp_path / "no_such_dir" / "x.tif")
 
 
 # ---- the chain as one pipeline: upload | level 1 bands | downloads ----------
