@@ -525,6 +525,17 @@ B2R_API int b2r_tileset_tile(const b2r_tileset* ts, int level, int tx, int ty,
 B2R_API double b2r_tileset_stat(const b2r_tileset* ts, int what);
 B2R_API void b2r_tileset_destroy(b2r_tileset* ts);
 
+/* The device stage of b2r_mipchain_encode_tiles on its own, for hosts that
+ * keep the tiles on the device (their own compressor, their own download): one
+ * device-resident, contiguous float32 image re-laid into tiles -- raster order,
+ * tile_height x tile_width x nchannels each, float32 or half (opt->out_basetype),
+ * edge tiles zero padded, opt->predictor as above -- in the caller's device
+ * buffer of at least ntiles_x * ntiles_y * tile bytes.  Asynchronous on
+ * `stream` (a cudaStream_t, NULL = the default stream). */
+B2R_API int b2r_tile_relayout(const b2r_image* src, void* dst_device, size_t dst_bytes,
+                              const b2r_tile_options* opt, void* stream, char* err,
+                              size_t errlen);
+
 /* The container step the reference leaves to its TIFF plugin
  * (out->open(..., AppendMIPLevel) + small->write(out), maketexture.cpp:957-974;
  * src/tiff.imageio/tiffoutput.cpp): the tiles of `ts` written as a tiled TIFF

@@ -263,6 +263,9 @@ def lib():
     L.b2r_tileset_stat.restype = C.c_double
     L.b2r_tileset_stat.argtypes = [C.c_void_p, C.c_int]
     L.b2r_tileset_destroy.argtypes = [C.c_void_p]
+    L.b2r_tile_relayout.argtypes = [C.POINTER(_Image), C.c_void_p, C.c_size_t,
+                                    C.POINTER(_TileOptions), C.c_void_p, C.c_char_p,
+                                    C.c_size_t]
     L.b2r_tileset_write_tiff.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_TiffOptions),
                                          C.c_char_p, C.c_size_t]
     L.b2r_mipchain_create_banded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
@@ -1701,6 +1704,32 @@ class TileSet:
         k = {"total_ms": 0, "device_ms": 1, "deflate_ms": 2, "raw_bytes": 3,
              "stored_bytes": 4, "setup_ms": 5, "wait_ms": 6}[what]
         return lib().b2r_tileset_stat(self._h, k)
+
+
+def tile_relayout(src, tile=64, half=False, predictor=0):
+    """b2r_tile_relayout: a contiguous float32 CUDA tensor (h, w, c) re-laid into
+    `tile` x `tile` tiles on the device -> uint8 CUDA tensor of shape
+    (ntiles_y, ntiles_x, tile bytes); asynchronous on the current torch stream."""
+    import torch
+    img = src if isinstance(src, ImageBuf) else ImageBuf(src)
+    if not img.on_device:
+        raise B2RError("tile_relayout: the source is a contiguous float32 device image")
+    h, w, c = img.spec_.height, img.spec_.width, img.spec_.nchannels
+    ntx, nty = -(-w // tile), -(-h // tile)
+    tb = tile * tile * c * (2 if half else 4)
+    out = torch.empty((nty, ntx, tb), dtype=torch.uint8, device=img.pixels.device)
+    o = _TileOptions()
+    o.tile_width = o.tile_height = int(tile)
+    o.out_basetype = 10 if half else 11
+    o.predictor = int(predictor)
+    im = img._c()
+    err = C.create_string_buffer(512)
+    rc = lib().b2r_tile_relayout(C.byref(im), C.c_void_p(out.data_ptr()),
+                                 C.c_size_t(out.numel()), C.byref(o),
+                                 _current_stream(img), err, 512)
+    if rc:
+        raise B2RError(err.value.decode())
+    return out
 
 
 class MipChainBanded:

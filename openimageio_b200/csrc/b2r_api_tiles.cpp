@@ -141,8 +141,8 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
         set_err(err, errlen, "encode_tiles: predictor must be 0, 1 (none) or 3 (floating point)");
         return B2R_ERR_INVALID;
     }
-    if (pred && (size_t(tile_w) * chain->nch * (obt == B2R_HALF ? 2 : 4)) % 4 != 0) {
-        set_err(err, errlen, "encode_tiles: predictor needs tile rows of whole 32-bit words");
+    if (pred && (size_t(tile_w) * chain->nch) % 4 != 0) {
+        set_err(err, errlen, "encode_tiles: predictor needs tile rows of a multiple of 4 samples");
         return B2R_ERR_INVALID;
     }
     int nthreads = (to && to->nthreads > 0) ? to->nthreads
@@ -395,6 +395,59 @@ b2r_tileset_destroy(b2r_tileset* ts)
     delete ts;
 }
 
+
+extern "C" int
+b2r_tile_relayout(const b2r_image* src, void* dst, size_t dst_bytes, const b2r_tile_options* to,
+                  void* stream, char* err, size_t errlen)
+{
+    if (!src || !src->pixels || !dst) {
+        set_err(err, errlen, "tile_relayout: null argument");
+        return B2R_ERR_INVALID;
+    }
+    if (device_count_cached() <= 0) {
+        set_err(err, errlen,
+                "no CUDA device available: the B200 tile output path has no CPU fallback");
+        return B2R_ERR_NO_DEVICE;
+    }
+    const int nch    = src->nchannels;
+    const int tile_w = (to && to->tile_width > 0) ? to->tile_width : 64;
+    const int tile_h = (to && to->tile_height > 0) ? to->tile_height : 64;
+    const int obt    = (to && to->out_basetype) ? to->out_basetype : B2R_FLOAT;
+    const int pred   = (to && to->predictor == 3) ? 3 : 0;
+    if (src->memspace != B2R_MEM_DEVICE || src->basetype != B2R_FLOAT || nch < 1
+        || src->xstride != (int64_t)nch * 4 || src->ystride != (int64_t)src->width * nch * 4) {
+        set_err(err, errlen, "tile_relayout: the source is a contiguous float32 device image");
+        return B2R_ERR_INVALID;
+    }
+    if (obt != B2R_FLOAT && obt != B2R_HALF) {
+        set_err(err, errlen, "tile_relayout: tiles are float32 or half");
+        return B2R_ERR_TYPES;
+    }
+    if (pred && (size_t(tile_w) * nch) % 4 != 0) {
+        set_err(err, errlen, "tile_relayout: predictor needs tile rows of a multiple of 4 samples");
+        return B2R_ERR_INVALID;
+    }
+    const int ntx = (src->width + tile_w - 1) / tile_w, nty = (src->height + tile_h - 1) / tile_h;
+    const size_t need = size_t(ntx) * nty * tile_w * tile_h * nch * (obt == B2R_HALF ? 2 : 4);
+    if (dst_bytes < need) {
+        set_err(err, errlen, "tile_relayout: destination holds %zu bytes, the tiles need %zu",
+                dst_bytes, need);
+        return B2R_ERR_INVALID;
+    }
+    DeviceGuard guard(src->device);
+    if (pred)
+        launch_tile_relayout_fp_predictor((const float*)src->pixels, src->width, src->height, nch,
+                                          tile_w, tile_h, 0, nty, obt == B2R_HALF, dst, stream);
+    else
+        launch_tile_relayout((const float*)src->pixels, src->width, src->height, nch, tile_w,
+                             tile_h, 0, nty, obt == B2R_HALF, dst, stream);
+    const cudaError_t rc = cudaGetLastError();
+    if (rc != cudaSuccess) {
+        set_err(err, errlen, "tile_relayout: CUDA error: %s", cudaGetErrorString(rc));
+        return B2R_ERR_CUDA;
+    }
+    return B2R_OK;
+}
 
 // ---------------------------------------------------------------------------
 // TIFF container around the stored tiles

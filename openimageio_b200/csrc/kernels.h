@@ -500,7 +500,7 @@ void
 launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int tile_h,
                      int ty0, int ty1, int out_half, void* out, void* stream);
 // the same with TIFF's floating-point predictor applied per tile row
-// (tile_w * nch * element size must be a multiple of 4)
+// (tile_w * nch must be a multiple of 4)
 void
 launch_tile_relayout_fp_predictor(const float* level, int w, int h, int nch, int tile_w,
                                   int tile_h, int ty0, int ty1, int out_half, void* out,

@@ -15,8 +15,89 @@ namespace b2r {
 
 namespace {
 
-// one thread = one element of the tiled output (coalesced stores; the loads
-// are tile_w * nch contiguous floats per tile row)
+// One thread = four consecutive samples of a tile row (tile_w * nch is a
+// multiple of 4 in the vector kernels; other tile shapes take the scalar one).
+struct TileQuad {
+    const float* row;  // first sample of source row y (valid when inside)
+    bool inside;       // y < h
+    int x0;            // first source column of the tile
+    int count;         // first of the four samples within the tile row
+    long long out_row; // index of the tile row's first sample in the tiled output
+};
+
+__device__ __forceinline__ TileQuad
+tile_quad(long long i, const float* __restrict__ src, int w, int h, int nch, int tile_w,
+          int tile_h, int ntx, int ty0)
+{
+    const int row_quads   = tile_w * nch / 4;
+    const int tile_quads  = row_quads * tile_h;
+    const long long t     = i / tile_quads;
+    const int e           = int(i - t * tile_quads);
+    const int yy          = e / row_quads;
+    const int y           = (ty0 + int(t / ntx)) * tile_h + yy;
+    TileQuad q;
+    q.x0      = int(t % ntx) * tile_w;
+    q.count   = (e - yy * row_quads) * 4;
+    q.inside  = y < h;
+    q.row     = src + (long long)y * w * nch;
+    q.out_row = (t * tile_h + yy) * (long long)(tile_w * nch);
+    return q;
+}
+
+// samples count .. count+3 of the tile row (zero outside the level)
+__device__ __forceinline__ float4
+tile_load4(const TileQuad& q, int w, int nch, int count)
+{
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (!q.inside)
+        return v;
+    const long long first = (long long)q.x0 * nch + count;  // sample index within the source row
+    const long long valid = (long long)w * nch;
+    const float* p        = q.row + first;
+    if (first + 3 < valid && (reinterpret_cast<unsigned long long>(p) & 15ull) == 0)
+        return __ldg(reinterpret_cast<const float4*>(p));
+    if (first < valid)
+        v.x = __ldg(p);
+    if (first + 1 < valid)
+        v.y = __ldg(p + 1);
+    if (first + 2 < valid)
+        v.z = __ldg(p + 2);
+    if (first + 3 < valid)
+        v.w = __ldg(p + 3);
+    return v;
+}
+
+template<bool HALF>
+__device__ __forceinline__ unsigned
+tile_bits(float v)
+{
+    return HALF ? (unsigned)__half_as_ushort(__float2half_rn(v)) : __float_as_uint(v);
+}
+
+template<bool HALF>
+__global__ void __launch_bounds__(256)
+tile_relayout_vec_kernel(const float* __restrict__ src, int w, int h, int nch, int tile_w,
+                         int tile_h, int ntx, int ty0, long long total_quads,
+                         void* __restrict__ out)
+{
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads;
+         i += (long long)gridDim.x * blockDim.x) {
+        const TileQuad q = tile_quad(i, src, w, h, nch, tile_w, tile_h, ntx, ty0);
+        const float4 v   = tile_load4(q, w, nch, q.count);
+        if (HALF) {
+            uint2 o;
+            o.x = tile_bits<true>(v.x) | (tile_bits<true>(v.y) << 16);
+            o.y = tile_bits<true>(v.z) | (tile_bits<true>(v.w) << 16);
+            reinterpret_cast<uint2*>(out)[i] = o;
+        } else {
+            reinterpret_cast<float4*>(out)[i] = v;
+        }
+    }
+}
+
+// scalar form for tile rows that are not a multiple of four samples:
+// one thread = one element of the tiled output
 template<bool HALF>
 __global__ void __launch_bounds__(256)
 tile_relayout_kernel(const float* __restrict__ src, int w, int h, int nch, int tile_w, int tile_h,
@@ -49,54 +130,65 @@ tile_relayout_kernel(const float* __restrict__ src, int w, int h, int nch, int t
 // (PREDICTOR_FLOATINGPOINT, what the reference's TIFF writer sets for float /
 // half data under zip: tiffoutput.cpp:683-690; libtiff's fpDiff): the row's
 // samples are split into byte planes, most significant byte first, and every
-// byte of the re-ordered row has the byte `nch` positions before it subtracted.
-// One thread = four consecutive bytes of a predicted tile row (one 32-bit store);
-// a byte's two samples come from the level through L1.
-template<bool HALF>
-__device__ __forceinline__ unsigned
-tile_sample_byte(const float* __restrict__ src, int w, int h, int nch, int y, int x0,
-                 int count, int plane)
-{
-    const int x = x0 + count / nch;
-    float v     = 0.0f;
-    if (y < h && x < w)
-        v = __ldg(src + ((long long)y * w + x) * nch + (count % nch));
-    if (HALF)
-        return ((unsigned)__half_as_ushort(__float2half_rn(v)) >> (8 * (1 - plane))) & 0xffu;
-    return (__float_as_uint(v) >> (8 * (3 - plane))) & 0xffu;
-}
-
+// byte of the re-ordered row has the byte `nch` positions before it subtracted
+// -- the same byte of the same channel of the previous pixel, or, for the
+// first pixel of the row, the next more significant byte of the row's LAST
+// pixel (the end of the previous plane).  A thread's four samples give four
+// consecutive bytes in each plane: one 32-bit store per plane, coalesced
+// across the warp; loads are the four samples (128-bit when aligned) and their
+// four predecessors.
 template<bool HALF>
 __global__ void __launch_bounds__(256)
 tile_relayout_fp_predictor_kernel(const float* __restrict__ src, int w, int h, int nch,
-                                  int tile_w, int tile_h, int ntx, int ty0, long long total_words,
+                                  int tile_w, int tile_h, int ntx, int ty0, long long total_quads,
                                   unsigned* __restrict__ out)
 {
     pdl_prologue();
-    const int bps       = HALF ? 2 : 4;
-    const int wc        = tile_w * nch;  // samples of a tile row
-    const int row_words = wc * bps / 4;  // tile_w is a multiple of 16
-    const long long tile_words = (long long)row_words * tile_h;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_words;
+    constexpr int BPS   = HALF ? 2 : 4;
+    const int wc        = tile_w * nch;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads;
          i += (long long)gridDim.x * blockDim.x) {
-        const long long t = i / tile_words;
-        const int e       = int(i - t * tile_words);
-        const int yy      = e / row_words;
-        const int b0      = (e - yy * row_words) * 4;  // first byte of the predicted row
-        const int y       = (ty0 + int(t / ntx)) * tile_h + yy;
-        const int x0      = int(t % ntx) * tile_w;
-        unsigned word     = 0;
+        const TileQuad q = tile_quad(i, src, w, h, nch, tile_w, tile_h, ntx, ty0);
+        const float4 v   = tile_load4(q, w, nch, q.count);
+        const unsigned cur[4] = { tile_bits<HALF>(v.x), tile_bits<HALF>(v.y), tile_bits<HALF>(v.z),
+                                  tile_bits<HALF>(v.w) };
+        unsigned prev[4];      // the sample `nch` positions earlier ...
+        bool wrapped[4];       // ... or the row's last pixel when there is none
+        if (q.count >= nch) {
+            const float4 u = tile_load4(q, w, nch, q.count - nch);
+            prev[0] = tile_bits<HALF>(u.x), prev[1] = tile_bits<HALF>(u.y);
+            prev[2] = tile_bits<HALF>(u.z), prev[3] = tile_bits<HALF>(u.w);
+            wrapped[0] = wrapped[1] = wrapped[2] = wrapped[3] = false;
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int b = b0 + k;
-            unsigned v  = tile_sample_byte<HALF>(src, w, h, nch, y, x0, b % wc, b / wc);
-            if (b >= nch) {
-                const int a = b - nch;
-                v -= tile_sample_byte<HALF>(src, w, h, nch, y, x0, a % wc, a / wc);
+            for (int k = 0; k < 4; ++k) {
+                const int a = q.count + k - nch;
+                wrapped[k]  = a < 0;
+                const int s = a < 0 ? a + wc : a;  // sample index within the tile row
+                const long long first = (long long)q.x0 * nch + s;
+                float f = 0.0f;
+                if (q.inside && first < (long long)w * nch)
+                    f = __ldg(q.row + first);
+                prev[k] = tile_bits<HALF>(f);
             }
-            word |= (v & 0xffu) << (8 * k);
         }
-        out[i] = word;
+        // byte planes of this row in the output, in 32-bit words
+        unsigned* orow = out + q.out_row * BPS / 4 + q.count / 4;
+#pragma unroll
+        for (int plane = 0; plane < BPS; ++plane) {
+            const int shift = 8 * (BPS - 1 - plane);
+            unsigned word   = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                unsigned b = cur[k] >> shift;
+                if (!wrapped[k])
+                    b -= prev[k] >> shift;
+                else if (plane > 0)
+                    b -= prev[k] >> (shift + 8);
+                word |= (b & 0xffu) << (8 * k);
+            }
+            orow[plane * (wc / 4)] = word;
+        }
     }
 }
 
@@ -108,8 +200,7 @@ launch_tile_relayout_fp_predictor(const float* level, int w, int h, int nch, int
                                   void* stream)
 {
     const int ntx         = (w + tile_w - 1) / tile_w;
-    const long long total = (long long)(ty1 - ty0) * ntx * tile_w * tile_h * nch
-                            * (out_half ? 2 : 4) / 4;
+    const long long total = (long long)(ty1 - ty0) * ntx * tile_w * tile_h * nch / 4;
     if (total <= 0)
         return;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
@@ -131,6 +222,17 @@ launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int 
     const long long total = (long long)(ty1 - ty0) * ntx * tile_w * tile_h * nch;
     if (total <= 0)
         return;
+    if ((tile_w * nch) % 4 == 0 && (reinterpret_cast<unsigned long long>(out) & 15ull) == 0) {
+        const long long quads = total / 4;
+        const int blocks = (int)std::min<long long>((quads + 255) / 256, 148LL * 32);
+        if (out_half)
+            launch_pdl(tile_relayout_vec_kernel<true>, dim3(blocks), dim3(256), 0,
+                       (cudaStream_t)stream, level, w, h, nch, tile_w, tile_h, ntx, ty0, quads, out);
+        else
+            launch_pdl(tile_relayout_vec_kernel<false>, dim3(blocks), dim3(256), 0,
+                       (cudaStream_t)stream, level, w, h, nch, tile_w, tile_h, ntx, ty0, quads, out);
+        return;
+    }
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
     if (out_half)
         launch_pdl(tile_relayout_kernel<true>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream,

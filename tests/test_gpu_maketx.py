@@ -379,6 +379,31 @@ def test_encode_tiles_fp_predictor(oiio, nch, shape, tile, half):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("predictor", [0, 3])
+def test_tile_relayout_on_device(oiio, half, predictor):
+    """b2r_tile_relayout (device in, device out) produces the bytes the tile
+    set stores before deflate, for every tile, ragged edges included."""
+    import torch
+    import zlib
+    src = synth.image(333, 210, 4, np.float32, seed=990)
+    dev = torch.from_numpy(src).cuda()
+    tiles = oiio.tile_relayout(dev, tile=64, half=half, predictor=predictor).cpu().numpy()
+    ch = oiio.MipChain(src, filtername="box")
+    ts = oiio.TileSet(ch, tile=64, half=half, predictor=predictor)
+    _, _, ntx, nty = ts.level_info(0)
+    assert tiles.shape[:2] == (nty, ntx)
+    for ty in range(nty):
+        for tx in range(ntx):
+            want = np.frombuffer(zlib.decompress(ts.tile_bytes(0, tx, ty)), np.uint8)
+            assert np.array_equal(tiles[ty, tx], want), (tx, ty)
+    with pytest.raises(oiio.B2RError, match="contiguous float32 device image"):
+        oiio.tile_relayout(dev[:, ::2], tile=64)
+    with pytest.raises(oiio.B2RError, match="multiple of 4 samples"):
+        oiio.tile_relayout(dev[:, :, :3].contiguous(), tile=2, predictor=3)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("half,predictor,big", [(False, 3, False), (False, 0, True),
                                                 (True, 3, False), (True, 0, False)])
 @pytest.mark.parametrize("nch,shape", [(4, (300, 500)), (3, (512, 512)), (1, (97, 130))])
