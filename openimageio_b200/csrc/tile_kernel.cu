@@ -31,12 +31,28 @@ tile_quad(long long i, const float* __restrict__ src, int w, int h, int nch, int
 {
     const int row_quads   = tile_w * nch / 4;
     const int tile_quads  = row_quads * tile_h;
-    const long long t     = i / tile_quads;
-    const int e           = int(i - t * tile_quads);
-    const int yy          = e / row_quads;
-    const int y           = (ty0 + int(t / ntx)) * tile_h + yy;
+    // 64-bit divisions are emulated (~100 instructions each, most of this
+    // kernel before): every index of a launch below 2^32 quads -- a 64 MB chunk
+    // of the encode pipeline, or a whole 32K^2 RGBA level -- divides in 32 bits
+    long long t;
+    int e, trow, tcol;
+    if ((unsigned long long)i >> 32) {
+        t    = i / tile_quads;
+        e    = int(i - t * tile_quads);
+        trow = int(t / ntx);
+        tcol = int(t - (long long)trow * ntx);
+    } else {
+        const unsigned iu = (unsigned)i;
+        const unsigned tu = iu / (unsigned)tile_quads;
+        e                 = int(iu - tu * (unsigned)tile_quads);
+        trow              = int(tu / (unsigned)ntx);
+        tcol              = int(tu - (unsigned)trow * (unsigned)ntx);
+        t                 = tu;
+    }
+    const int yy = e / row_quads;
+    const int y  = (ty0 + trow) * tile_h + yy;
     TileQuad q;
-    q.x0      = int(t % ntx) * tile_w;
+    q.x0      = tcol * tile_w;
     q.count   = (e - yy * row_quads) * 4;
     q.inside  = y < h;
     q.row     = src + (long long)y * w * nch;
