@@ -493,8 +493,9 @@ B2R_API int b2r_pixel_hash_sha1(const b2r_image* src, const char* extrainfo,
  * half: maketx -d half), downloaded through pinned staging slots on a copy
  * stream, and deflated tile by tile (zlib; maketx's default "zip" compression,
  * maketexture.cpp:1605) by `nthreads` host threads while the next chunk is in
- * flight.  Edge tiles are zero-padded to full size.  The container format
- * (TIFF / OpenEXR headers and offset tables) stays with the file plugins. */
+ * flight.  Edge tiles are zero-padded to full size.  b2r_tileset_write_tiff
+ * (below) writes the TIFF container around the tile set; OpenEXR headers and
+ * offset tables stay with the reference's plugin. */
 typedef struct b2r_tile_options {
     int32_t tile_width, tile_height; /* 0 -> 64 (maketexture.cpp:1100-1106) */
     int32_t out_basetype;            /* B2R_FLOAT (0 -> float) or B2R_HALF */

@@ -551,6 +551,10 @@ b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_o
                 ts->tile_w, ts->tile_h);
         return B2R_ERR_INVALID;
     }
+    if (ts->predictor == 3 && !ts->compression) {
+        set_err(err, errlen, "write_tiff: TIFF's predictor goes with compressed tiles only");
+        return B2R_ERR_INVALID;
+    }
     const int nch = ts->nch;
     const int bps = ts->out_basetype == B2R_HALF ? 16 : 32;
     // classic TIFF holds 32-bit offsets; leave room for the directories

@@ -447,6 +447,13 @@ def test_write_tiff_texture(oiio, tmp_path, nch, shape, half, predictor, big):
         oiio.TileSet(ch, tile=40).write_tiff(path)
     with pytest.raises(oiio.B2RError, match="could not open"):
         ts.write_tiff(tmp_path / "no_such_dir" / "x.tif")
+    with pytest.raises(oiio.B2RError, match="compressed tiles only"):
+        oiio.TileSet(ch, tile=64, compression=False, predictor=3).write_tiff(path)
+    # stored (uncompressed) tiles: Compression = 1
+    oiio.TileSet(ch, tile=64, half=half, compression=False).write_tiff(path)
+    raw = tiff_mini.read(path)
+    assert raw[0]["tags"][259] == [1]
+    assert all(np.array_equal(a["pixels"], b["pixels"]) for a, b in zip(raw, dirs))
 
 
 # ---- the chain as one pipeline: upload | level 1 bands | downloads ----------
