@@ -498,16 +498,20 @@ B2R_API int b2r_pixel_hash_sha1(const b2r_image* src, const char* extrainfo,
  * offset tables stay with the reference's plugin. */
 typedef struct b2r_tile_options {
     int32_t tile_width, tile_height; /* 0 -> 64 (maketexture.cpp:1100-1106) */
-    int32_t out_basetype;            /* B2R_FLOAT (0 -> float) or B2R_HALF */
+    int32_t out_basetype;            /* B2R_FLOAT (0 -> float), B2R_HALF, or B2R_UINT16 /
+                                        B2R_UINT8: the level through convert_type<float,D>
+                                        (fmath.h:753-764), what maketx writes for an
+                                        integer texture */
     int32_t compression;             /* 0 store, 1 zlib deflate */
     int32_t zlevel;                  /* 1..9, 0 -> 1 */
     int32_t nthreads;                /* 0 -> hardware concurrency */
     int32_t first_level;             /* skip levels below this one */
     int32_t predictor;               /* 0 / 1 none; 3 = TIFF's floating-point predictor
-                                        (PREDICTOR_FLOATINGPOINT, what the reference's
-                                        TIFF writer sets for float / half data under zip,
-                                        src/tiff.imageio/tiffoutput.cpp:683-690), applied
-                                        per tile row by the re-layout kernel */
+                                        (float / half tiles), 2 = the horizontal one
+                                        (uint8 / uint16 tiles) -- what the reference's
+                                        TIFF writer sets under zip,
+                                        src/tiff.imageio/tiffoutput.cpp:683-698 --
+                                        applied per tile row by the re-layout kernel */
     int32_t reserved[2];
 } b2r_tile_options;
 typedef struct b2r_tileset b2r_tileset;
@@ -543,9 +547,9 @@ B2R_API int b2r_tile_relayout(const b2r_image* src, void* dst_device, size_t dst
  * texture, one directory per MIP level in level order (the layout OpenImageIO's
  * TIFF reader presents as MIP levels when PIXAR_TEXTUREFORMAT is set,
  * tiffinput.cpp:88,1435), contiguous planar config, IEEE float samples (32 or
- * 16 bits), Compression = 8 (Adobe deflate: each stored tile is already the
- * zlib stream TIFF wants) or 1, Predictor = 3 when the tiles were encoded with
- * it, Software / ImageDescription / PIXAR_TEXTUREFORMAT ("Plain Texture") /
+ * 16 bits) or unsigned integers (16 or 8 bits), Compression = 8 (Adobe deflate: each stored tile is already the
+ * zlib stream TIFF wants) or 1, Predictor = 3 / 2 when the tiles were encoded
+ * with it, Software / ImageDescription / PIXAR_TEXTUREFORMAT ("Plain Texture") /
  * PIXAR_WRAPMODES.  Classic TIFF below 4 GB, BigTIFF above (or when
  * `bigtiff` != 0).  Tile sizes must be multiples of 16 and every level of the
  * chain must have been encoded (first_level == 0).  Host code only: no

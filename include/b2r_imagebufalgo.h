@@ -1003,7 +1003,9 @@ enum MakeTextureMode { MakeTxTexture = 0 };
 /// maketx produces (:957-974 + the TIFF plugin): 64x64 tiles ("tile_width"),
 /// deflate, floating-point predictor, one directory per MIP level,
 /// ImageDescription = "oiio:SHA-1=... oiio:ConstantColor=... oiio:AverageColor=..."
-/// (:1936-1975); the file's sample type is "format" (float or half).
+/// (:1936-1975); the file's sample type is "format" (float, half, uint16 or
+/// uint8: integer files take the levels through convert_type<float,D> and the
+/// horizontal predictor).
 inline Texture
 make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config = {},
              const std::string& outputfilename = "")
@@ -1193,10 +1195,11 @@ make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config =
         T.levels.push_back(std::move(L));
     }
     if (T.error.empty() && !outputfilename.empty()) {
-        if (T.format != "float" && T.format != "half") {
+        const bool isint = T.format == "uint8" || T.format == "uint16";
+        if (T.format != "float" && T.format != "half" && !isint) {
             T.error = "make_texture: \"" + T.format
-                      + "\" output is not on the B200 path (tiles are float or half); "
-                        "use format=float or half";
+                      + "\" output is not on the B200 path (tiles are float, half, uint16 "
+                        "or uint8)";
         } else {
             auto join = [](const std::vector<float>& v) {
                 std::string r;
@@ -1219,10 +1222,13 @@ make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config =
             b2r_tile_options to;
             std::memset(&to, 0, sizeof(to));
             to.tile_width = to.tile_height = config.get_int("tile_width", 64);
-            to.out_basetype = T.format == "half" ? B2R_HALF : B2R_FLOAT;
+            to.out_basetype = T.format == "half"     ? B2R_HALF
+                              : T.format == "uint8"  ? B2R_UINT8
+                              : T.format == "uint16" ? B2R_UINT16
+                                                     : B2R_FLOAT;
             to.compression  = 1;
             to.zlevel       = config.get_int("tiff:zipquality", 1);
-            to.predictor    = 3;
+            to.predictor    = isint ? 2 : 3;  // tiffoutput.cpp:683-698
             b2r_tileset* ts = nullptr;
             const std::string wrap = config.get_string("wrapmodes", "black,black");
             b2r_tiff_options fo;

@@ -80,6 +80,10 @@ class _TileOptions(C.Structure):
                 ("reserved", C.c_int32 * 2)]
 
 
+_TILE_TYPES = {"float": (11, np.float32), "half": (10, np.float16),
+               "uint16": (4, np.uint16), "uint8": (2, np.uint8)}
+
+
 class _TiffOptions(C.Structure):
     _fields_ = [("image_description", C.c_char_p), ("software", C.c_char_p),
                 ("wrapmodes", C.c_char_p), ("bigtiff", C.c_int32),
@@ -1622,11 +1626,16 @@ class TileSet:
     compressed tiles a file plugin stores)."""
 
     def __init__(self, chain, tile=64, half=False, compression=True, zlevel=1,
-                 nthreads=0, first_level=0, predictor=0):
+                 nthreads=0, first_level=0, predictor=0, out_type=None):
+        """out_type: "float" (default), "half" (same as half=True), "uint16" or
+        "uint8" (the levels through convert_type<float,D>).  predictor: 0, 3
+        (TIFF floating point; float / half) or 2 (TIFF horizontal; integers)."""
+        out_type = out_type or ("half" if half else "float")
+        half = out_type == "half"
         o = _TileOptions()
         o.predictor = int(predictor)
         o.tile_width = o.tile_height = int(tile)
-        o.out_basetype = 10 if half else 11
+        o.out_basetype = _TILE_TYPES[out_type][0]
         o.compression = 1 if compression else 0
         o.zlevel = int(zlevel)
         o.nthreads = int(nthreads)
@@ -1640,7 +1649,8 @@ class TileSet:
         self.tile = int(tile)
         self.half = bool(half)
         self.compressed = bool(compression)
-        self.predictor = 3 if int(predictor) == 3 else 0
+        self.predictor = int(predictor) if int(predictor) in (2, 3) else 0
+        self.out_type = out_type
         self.nchannels = chain.nchannels
 
     def __del__(self):
@@ -1672,7 +1682,11 @@ class TileSet:
         b = self.tile_bytes(level, tx, ty)
         if self.compressed:
             b = zlib.decompress(b)
-        dt = np.float16 if self.half else np.float32
+        dt = _TILE_TYPES[self.out_type][1]
+        if self.predictor == 2:
+            # undo TIFF's horizontal predictor (libtiff horAcc8 / horAcc16)
+            px = np.frombuffer(b, dt).reshape(self.tile, self.tile, self.nchannels)
+            return np.cumsum(px, axis=1, dtype=dt)
         if self.predictor == 3:
             # undo TIFF's floating-point predictor row by row (libtiff fpAcc)
             bps = 2 if self.half else 4
@@ -1706,7 +1720,7 @@ class TileSet:
         return lib().b2r_tileset_stat(self._h, k)
 
 
-def tile_relayout(src, tile=64, half=False, predictor=0):
+def tile_relayout(src, tile=64, half=False, predictor=0, out_type=None):
     """b2r_tile_relayout: a contiguous float32 CUDA tensor (h, w, c) re-laid into
     `tile` x `tile` tiles on the device -> uint8 CUDA tensor of shape
     (ntiles_y, ntiles_x, tile bytes); asynchronous on the current torch stream."""
@@ -1716,11 +1730,12 @@ def tile_relayout(src, tile=64, half=False, predictor=0):
         raise B2RError("tile_relayout: the source is a contiguous float32 device image")
     h, w, c = img.spec_.height, img.spec_.width, img.spec_.nchannels
     ntx, nty = -(-w // tile), -(-h // tile)
-    tb = tile * tile * c * (2 if half else 4)
+    out_type = out_type or ("half" if half else "float")
+    tb = tile * tile * c * np.dtype(_TILE_TYPES[out_type][1]).itemsize
     out = torch.empty((nty, ntx, tb), dtype=torch.uint8, device=img.pixels.device)
     o = _TileOptions()
     o.tile_width = o.tile_height = int(tile)
-    o.out_basetype = 10 if half else 11
+    o.out_basetype = _TILE_TYPES[out_type][0]
     o.predictor = int(predictor)
     im = img._c()
     err = C.create_string_buffer(512)
@@ -1840,9 +1855,9 @@ def _write_texture_file(T, outputfilename, cfg):
     deflated, floating-point predictor, into a tiled TIFF whose
     ImageDescription carries oiio:SHA-1 / ConstantColor / AverageColor the way
     the reference crams them in for formats without arbitrary metadata."""
-    if T.format not in ("float", "half"):
+    if T.format not in _TILE_TYPES:
         T.error = ("make_texture: \"%s\" output is not on the B200 path (tiles are "
-                   "float or half); use format=float or half" % T.format)
+                   "float, half, uint16 or uint8)" % T.format)
         return T
     desc = []
     top = T.levels[0]
@@ -1864,8 +1879,8 @@ def _write_texture_file(T, outputfilename, cfg):
         desc.append("oiio:AverageColor=" + join(T.average_color))
     try:
         ts = TileSet(T.chain, tile=int(cfg.get("tile_width", 64) or 64),
-                     half=T.format == "half", zlevel=int(cfg.get("tiff:zipquality", 1) or 1),
-                     predictor=3)
+                     out_type=T.format, zlevel=int(cfg.get("tiff:zipquality", 1) or 1),
+                     predictor=3 if T.format in ("float", "half") else 2)
         ts.write_tiff(outputfilename, image_description=" ".join(desc) or None,
                       wrapmodes=cfg.get("wrapmodes", None))
     except B2RError as e:

@@ -47,6 +47,60 @@ struct b2r_tileset {
 
 namespace {
 
+int
+tile_elem_size(int obt)
+{
+    return obt == B2R_UINT8 ? 1 : (obt == B2R_FLOAT ? 4 : 2);
+}
+
+// out_basetype / predictor / tile-row rules shared by encode_tiles and tile_relayout:
+// predictor 3 (floating point) goes with float / half tiles, 2 (horizontal) with
+// uint8 / uint16 ones -- the pairing the reference's TIFF writer uses
+// (tiffoutput.cpp:683-698)
+int
+check_tile_format(const char* who, int obt, int predictor, int tile_w, int nch, int* pred,
+                  char* err, size_t errlen)
+{
+    const bool isint = obt == B2R_UINT8 || obt == B2R_UINT16;
+    if (!isint && obt != B2R_FLOAT && obt != B2R_HALF) {
+        set_err(err, errlen, "%s: tiles are float32, half, uint16 or uint8", who);
+        return B2R_ERR_TYPES;
+    }
+    if (predictor != 0 && predictor != 1 && predictor != 2 && predictor != 3) {
+        set_err(err, errlen,
+                "%s: predictor must be 0, 1 (none), 2 (horizontal) or 3 (floating point)", who);
+        return B2R_ERR_INVALID;
+    }
+    if ((predictor == 2 && !isint) || (predictor == 3 && isint)) {
+        set_err(err, errlen,
+                "%s: predictor 2 goes with uint8 / uint16 tiles, predictor 3 with float / half",
+                who);
+        return B2R_ERR_INVALID;
+    }
+    *pred = predictor >= 2 ? predictor : 0;
+    if ((*pred || isint) && (size_t(tile_w) * nch) % 4 != 0) {
+        set_err(err, errlen,
+                "%s: predictor and integer tiles need tile rows of a multiple of 4 samples", who);
+        return B2R_ERR_INVALID;
+    }
+    return B2R_OK;
+}
+
+void
+launch_tiles(const float* px, int w, int h, int nch, int tile_w, int tile_h, int ty0, int ty1,
+             int obt, int pred, void* out, void* stream)
+{
+    if (obt == B2R_UINT8 || obt == B2R_UINT16)
+        launch_tile_relayout_int(px, w, h, nch, tile_w, tile_h, ty0, ty1, obt == B2R_UINT16,
+                                 pred == 2, out, stream);
+    else if (pred == 3)
+        launch_tile_relayout_fp_predictor(px, w, h, nch, tile_w, tile_h, ty0, ty1,
+                                          obt == B2R_HALF, out, stream);
+    else
+        launch_tile_relayout(px, w, h, nch, tile_w, tile_h, ty0, ty1, obt == B2R_HALF, out,
+                             stream);
+}
+
 // The three device + three pinned host staging slots, kept per device between
 // calls (grow-only): pinning and unpinning 3 x 64 MB cost 90-300 ms per call,
 // a third of an 8K^2 chain's whole output stage.  One encode at a time per
@@ -132,24 +186,18 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
     const int comp   = to ? to->compression : 1;
     const int zlevel = (to && to->zlevel > 0) ? std::min(9, (int)to->zlevel) : 1;
     const int first  = (to && to->first_level > 0) ? to->first_level : 0;
-    const int pred   = (to && to->predictor == 3) ? 3 : 0;
-    if (obt != B2R_FLOAT && obt != B2R_HALF) {
-        set_err(err, errlen, "encode_tiles: tiles are float32 or half");
-        return B2R_ERR_TYPES;
-    }
-    if (to && to->predictor != 0 && to->predictor != 1 && to->predictor != 3) {
-        set_err(err, errlen, "encode_tiles: predictor must be 0, 1 (none) or 3 (floating point)");
-        return B2R_ERR_INVALID;
-    }
-    if (pred && (size_t(tile_w) * chain->nch) % 4 != 0) {
-        set_err(err, errlen, "encode_tiles: predictor needs tile rows of a multiple of 4 samples");
-        return B2R_ERR_INVALID;
+    int pred = 0;
+    {
+        const int rc = check_tile_format("encode_tiles", obt, to ? to->predictor : 0, tile_w,
+                                         chain->nch, &pred, err, errlen);
+        if (rc)
+            return rc;
     }
     int nthreads = (to && to->nthreads > 0) ? to->nthreads
                                             : (int)std::thread::hardware_concurrency();
     nthreads     = std::max(1, std::min(nthreads, 256));
     const int nch = chain->nch;
-    const int oes = obt == B2R_HALF ? 2 : 4;
+    const int oes = tile_elem_size(obt);
     const size_t tile_bytes = size_t(tile_w) * tile_h * nch * oes;
 
     auto t_begin = std::chrono::steady_clock::now();
@@ -233,12 +281,8 @@ b2r_mipchain_encode_tiles(const b2r_mipchain* chain, const b2r_tile_options* to,
         const auto& CL = chain->levels[c.level];
         const auto& TL = ts->levels[c.level];
         const int s    = i % NSLOT;
-        if (pred)
-            launch_tile_relayout_fp_predictor((const float*)CL.px, CL.w, CL.h, nch, tile_w,
-                                              tile_h, c.ty0, c.ty1, obt == B2R_HALF, dslot[s], sk);
-        else
-            launch_tile_relayout((const float*)CL.px, CL.w, CL.h, nch, tile_w, tile_h, c.ty0,
-                                 c.ty1, obt == B2R_HALF, dslot[s], sk);
+        launch_tiles((const float*)CL.px, CL.w, CL.h, nch, tile_w, tile_h, c.ty0, c.ty1, obt, pred,
+                     dslot[s], sk);
         cudaEventRecord(relaid, sk);
         cudaStreamWaitEvent(sc, relaid, 0);
         cudaMemcpyAsync(hslot[s], dslot[s], size_t(c.ty1 - c.ty0) * TL.ntx * tile_bytes,
@@ -413,34 +457,28 @@ b2r_tile_relayout(const b2r_image* src, void* dst, size_t dst_bytes, const b2r_t
     const int tile_w = (to && to->tile_width > 0) ? to->tile_width : 64;
     const int tile_h = (to && to->tile_height > 0) ? to->tile_height : 64;
     const int obt    = (to && to->out_basetype) ? to->out_basetype : B2R_FLOAT;
-    const int pred   = (to && to->predictor == 3) ? 3 : 0;
+    int pred         = 0;
     if (src->memspace != B2R_MEM_DEVICE || src->basetype != B2R_FLOAT || nch < 1
         || src->xstride != (int64_t)nch * 4 || src->ystride != (int64_t)src->width * nch * 4) {
         set_err(err, errlen, "tile_relayout: the source is a contiguous float32 device image");
         return B2R_ERR_INVALID;
     }
-    if (obt != B2R_FLOAT && obt != B2R_HALF) {
-        set_err(err, errlen, "tile_relayout: tiles are float32 or half");
-        return B2R_ERR_TYPES;
-    }
-    if (pred && (size_t(tile_w) * nch) % 4 != 0) {
-        set_err(err, errlen, "tile_relayout: predictor needs tile rows of a multiple of 4 samples");
-        return B2R_ERR_INVALID;
+    {
+        const int rc = check_tile_format("tile_relayout", obt, to ? to->predictor : 0, tile_w, nch,
+                                         &pred, err, errlen);
+        if (rc)
+            return rc;
     }
     const int ntx = (src->width + tile_w - 1) / tile_w, nty = (src->height + tile_h - 1) / tile_h;
-    const size_t need = size_t(ntx) * nty * tile_w * tile_h * nch * (obt == B2R_HALF ? 2 : 4);
+    const size_t need = size_t(ntx) * nty * tile_w * tile_h * nch * tile_elem_size(obt);
     if (dst_bytes < need) {
         set_err(err, errlen, "tile_relayout: destination holds %zu bytes, the tiles need %zu",
                 dst_bytes, need);
         return B2R_ERR_INVALID;
     }
     DeviceGuard guard(src->device);
-    if (pred)
-        launch_tile_relayout_fp_predictor((const float*)src->pixels, src->width, src->height, nch,
-                                          tile_w, tile_h, 0, nty, obt == B2R_HALF, dst, stream);
-    else
-        launch_tile_relayout((const float*)src->pixels, src->width, src->height, nch, tile_w,
-                             tile_h, 0, nty, obt == B2R_HALF, dst, stream);
+    launch_tiles((const float*)src->pixels, src->width, src->height, nch, tile_w, tile_h, 0, nty,
+                 obt, pred, dst, stream);
     const cudaError_t rc = cudaGetLastError();
     if (rc != cudaSuccess) {
         set_err(err, errlen, "tile_relayout: CUDA error: %s", cudaGetErrorString(rc));
@@ -551,12 +589,13 @@ b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_o
                 ts->tile_w, ts->tile_h);
         return B2R_ERR_INVALID;
     }
-    if (ts->predictor == 3 && !ts->compression) {
+    if (ts->predictor >= 2 && !ts->compression) {
         set_err(err, errlen, "write_tiff: TIFF's predictor goes with compressed tiles only");
         return B2R_ERR_INVALID;
     }
     const int nch = ts->nch;
-    const int bps = ts->out_basetype == B2R_HALF ? 16 : 32;
+    const int bps     = 8 * tile_elem_size(ts->out_basetype);
+    const bool isfloat = ts->out_basetype == B2R_HALF || ts->out_basetype == B2R_FLOAT;
     // classic TIFF holds 32-bit offsets; leave room for the directories
     uint64_t payload = 0, ntiles = 0;
     for (const auto& L : ts->levels)
@@ -612,8 +651,8 @@ b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_o
         tags.push_back(tag_shorts(277, { (uint16_t)nch }));
         tags.push_back(tag_shorts(284, { 1 }));
         tags.push_back(tag_ascii(305, software));
-        if (ts->predictor == 3)
-            tags.push_back(tag_shorts(317, { 3 }));
+        if (ts->predictor >= 2)
+            tags.push_back(tag_shorts(317, { (uint16_t)ts->predictor }));
         tags.push_back(tag_long(322, (uint32_t)ts->tile_w));
         tags.push_back(tag_long(323, (uint32_t)ts->tile_h));
         tags.push_back(tag_offsets(324, offs, big));
@@ -626,7 +665,7 @@ b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_o
             extra[0] = 1;
             tags.push_back(tag_shorts(338, extra));
         }
-        tags.push_back(tag_shorts(339, std::vector<uint16_t>(nch, 3)));
+        tags.push_back(tag_shorts(339, std::vector<uint16_t>(nch, uint16_t(isfloat ? 3 : 1))));
         tags.push_back(tag_ascii(33302, "Plain Texture"));
         tags.push_back(tag_ascii(33303, wrap));
         std::sort(tags.begin(), tags.end(),

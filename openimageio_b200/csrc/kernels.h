@@ -499,6 +499,11 @@ launch_pixel_bytes_copy(void* dst, long long dst_xstride, long long dst_ystride,
 void
 launch_tile_relayout(const float* level, int w, int h, int nch, int tile_w, int tile_h,
                      int ty0, int ty1, int out_half, void* out, void* stream);
+// uint8 / uint16 tiles (convert_type<float,D> of the level), optionally with TIFF's
+// horizontal predictor per tile row; tile_w * nch must be a multiple of 4
+void
+launch_tile_relayout_int(const float* level, int w, int h, int nch, int tile_w, int tile_h,
+                         int ty0, int ty1, int out_u16, int hdiff, void* out, void* stream);
 // the same with TIFF's floating-point predictor applied per tile row
 // (tile_w * nch must be a multiple of 4)
 void

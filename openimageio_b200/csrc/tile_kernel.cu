@@ -208,7 +208,83 @@ tile_relayout_fp_predictor_kernel(const float* __restrict__ src, int w, int h, i
     }
 }
 
+// Integer tiles (maketx of a uint8 / uint16 texture writes its float levels
+// through convert_type<float,D>, fmath.h:753-764 -- quant_u8 / quant_u16 here,
+// bit for bit), optionally with TIFF's horizontal predictor (PREDICTOR_HORIZONTAL,
+// what the reference's TIFF writer sets for 8- and 16-bit data under zip:
+// tiffoutput.cpp:691-694; libtiff horDiff8 / horDiff16): every sample of a tile
+// row minus the sample `nch` positions before it, modulo the sample width.
+template<bool U16, bool HDIFF>
+__global__ void __launch_bounds__(256)
+tile_relayout_int_kernel(const float* __restrict__ src, int w, int h, int nch, int tile_w,
+                         int tile_h, int ntx, int ty0, long long total_quads,
+                         void* __restrict__ out)
+{
+    pdl_prologue();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_quads;
+         i += (long long)gridDim.x * blockDim.x) {
+        const TileQuad q = tile_quad(i, src, w, h, nch, tile_w, tile_h, ntx, ty0);
+        const float4 v   = tile_load4(q, w, nch, q.count);
+        unsigned s[4];
+        s[0] = U16 ? quant_u16(v.x) : quant_u8(v.x);
+        s[1] = U16 ? quant_u16(v.y) : quant_u8(v.y);
+        s[2] = U16 ? quant_u16(v.z) : quant_u8(v.z);
+        s[3] = U16 ? quant_u16(v.w) : quant_u8(v.w);
+        if (HDIFF) {
+            unsigned p[4] = { 0u, 0u, 0u, 0u };
+            if (q.count >= nch) {
+                const float4 u = tile_load4(q, w, nch, q.count - nch);
+                p[0] = U16 ? quant_u16(u.x) : quant_u8(u.x);
+                p[1] = U16 ? quant_u16(u.y) : quant_u8(u.y);
+                p[2] = U16 ? quant_u16(u.z) : quant_u8(u.z);
+                p[3] = U16 ? quant_u16(u.w) : quant_u8(u.w);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int a = q.count + k - nch;  // < 0: first pixel of the row, kept as is
+                    if (a >= 0) {
+                        const long long first = (long long)q.x0 * nch + a;
+                        float f = 0.0f;
+                        if (q.inside && first < (long long)w * nch)
+                            f = __ldg(q.row + first);
+                        p[k] = U16 ? quant_u16(f) : quant_u8(f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                s[k] = (s[k] - p[k]) & (U16 ? 0xffffu : 0xffu);
+        }
+        if (U16) {
+            uint2 o;
+            o.x = s[0] | (s[1] << 16);
+            o.y = s[2] | (s[3] << 16);
+            reinterpret_cast<uint2*>(out)[i] = o;
+        } else {
+            reinterpret_cast<unsigned*>(out)[i] = s[0] | (s[1] << 8) | (s[2] << 16) | (s[3] << 24);
+        }
+    }
+}
+
 }  // namespace
+
+void
+launch_tile_relayout_int(const float* level, int w, int h, int nch, int tile_w, int tile_h,
+                         int ty0, int ty1, int out_u16, int hdiff, void* out, void* stream)
+{
+    const int ntx         = (w + tile_w - 1) / tile_w;
+    const long long total = (long long)(ty1 - ty0) * ntx * tile_w * tile_h * nch / 4;
+    if (total <= 0)
+        return;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    void (*k)(const float*, int, int, int, int, int, int, int, long long, void*)
+        = out_u16 ? (hdiff ? tile_relayout_int_kernel<true, true>
+                           : tile_relayout_int_kernel<true, false>)
+                  : (hdiff ? tile_relayout_int_kernel<false, true>
+                           : tile_relayout_int_kernel<false, false>);
+    launch_pdl(k, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, level, w, h, nch, tile_w,
+               tile_h, ntx, ty0, total, out);
+}
 
 void
 launch_tile_relayout_fp_predictor(const float* level, int w, int h, int nch, int tile_w,

@@ -153,6 +153,34 @@ def test_cpp_make_texture(iba_cli, oracle, tmp_path, filt, hicomp):
 
 
 @pytest.mark.gpu
+def test_cpp_make_texture_writes_uint8_tiff(iba_cli, tmp_path):
+    """The same for a uint8 picture: the file holds convert_type<float,uint8>
+    of the float levels (fmath.h:753-764), Predictor 2, SampleFormat uint."""
+    import tiff_mini
+    src = synth.image(200, 330, 3, np.uint8, seed=96)
+    fin, fout, ftif = (str(tmp_path / n) for n in ("in.raw", "out.raw", "out.tif"))
+    src.tofile(fin)
+    out = subprocess.check_output([iba_cli, "maketx", fin, "200", "330", "3", "2", "lanczos3",
+                                   "0", fout, ftif], text=True)
+    kv = dict(t.split("=") for t in out.split())
+    dirs = tiff_mini.read(ftif)
+    assert len(dirs) == int(kv["levels"])
+    got = np.fromfile(fout, np.float32)
+    off = 0
+    for lv, d in enumerate(dirs):
+        n = d["pixels"].size
+        s = got[off:off + n] * np.float32(255) + np.float32(0.5)
+        want = np.clip(s, np.float32(0), np.float32(255)).astype(np.uint8)
+        assert d["pixels"].dtype == np.uint8 and np.array_equal(d["pixels"].ravel(), want), lv
+        off += n
+        assert d["tags"][317] == [2] and d["tags"][339] == [1, 1, 1] and d["tags"][258] == [8] * 3
+    assert np.array_equal(dirs[0]["pixels"], src)
+    theirs = tiff_mini.read_libtiff(ftif, 3)
+    if theirs is not None:
+        assert all(np.array_equal(a, d["pixels"]) for a, d in zip(theirs, dirs))
+
+
+@pytest.mark.gpu
 def test_cpp_make_texture_writes_tiff(iba_cli, tmp_path):
     """make_texture(..., outputfilename) of the C++ mirror: the file's
     directories are the levels it returned (float, Predictor 3, 64x64 deflate

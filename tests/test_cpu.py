@@ -526,3 +526,24 @@ def test_tiff_mini_against_libtiff(tmp_path, nch, predictor, big):
     tiff_mini.write(path, halves, tile=32, predictor=predictor, big=big)
     for a, b in zip(halves, tiff_mini.read(path)):
         assert np.array_equal(a, b["pixels"])
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16])
+@pytest.mark.parametrize("predictor", [0, 2])
+def test_tiff_mini_integers_against_libtiff(tmp_path, dt, predictor):
+    """The integer side of tests/tiff_mini.py (uint8 / uint16 samples, TIFF's
+    horizontal predictor as libtiff's horDiff8 / horDiff16 define it) against
+    libtiff through OpenCV."""
+    import tiff_mini
+    rng = np.random.default_rng(50)
+    for nch in (1, 3, 4):
+        levels = [rng.integers(0, np.iinfo(dt).max + 1, (h, w, nch)).astype(dt)
+                  for h, w in ((150, 200), (75, 100), (1, 1))]
+        path = tmp_path / "i.tif"
+        tiff_mini.write(path, levels, tile=64, predictor=predictor, big=(nch == 3))
+        for a, b in zip(levels, tiff_mini.read(path)):
+            assert np.array_equal(a, b["pixels"]) and b["padding_is_zero"]
+        theirs = tiff_mini.read_libtiff(path, nch)
+        if theirs is None:
+            pytest.skip("no OpenCV here")
+        assert len(theirs) == 3 and all(np.array_equal(a, b) for a, b in zip(levels, theirs))

@@ -292,9 +292,90 @@ def test_make_texture_writes_a_tiff_texture(oiio, tmp_path, fmt):
         theirs = tiff_mini.read_libtiff(path, 4)
         if theirs is not None:
             assert all(np.array_equal(a, np.asarray(l.pixels)) for a, l in zip(theirs, T.levels))
-    bad = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"format": "uint8"},
+    bad = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"format": "double"},
                             outputfilename=path)
-    assert not bad.ok and "float or half" in bad.error
+    assert not bad.ok and "tiles are float, half, uint16 or uint8" in bad.error
+
+
+def _convert_type_from_float(px, dt):
+    """convert_type<float,D> (fmath.h:753-764, 1009-1031) in numpy float32 steps:
+    v * max, + 0.5, clamp, truncate."""
+    mx = np.float32(np.iinfo(dt).max)
+    s = px.astype(np.float32) * mx
+    s = s + np.float32(0.5)
+    return np.clip(s, np.float32(0), mx).astype(dt)
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16])
+def test_make_texture_writes_an_integer_tiff_texture(oiio, tmp_path, dt):
+    """maketx of a uint8 / uint16 picture: float levels, written through
+    convert_type<float,D> as 64x64 deflate tiles with the horizontal predictor
+    (tiffoutput.cpp:691-694).  libtiff reads every level back equal to the
+    quantised levels make_texture returned."""
+    import tiff_mini
+    src = synth.image(260, 190, 3, dt, seed=78)
+    path = tmp_path / "out8.tif"
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src),
+                          {"maketx:filtername": "lanczos3"}, outputfilename=path)
+    assert T.ok, T.error
+    assert T.format == np.dtype(dt).name
+    dirs = tiff_mini.read(path)
+    assert len(dirs) == len(T.levels)
+    want = [_convert_type_from_float(np.asarray(l.pixels), dt) for l in T.levels]
+    assert np.array_equal(want[0], src)     # level 0 survives the float round trip
+    for lv, d in enumerate(dirs):
+        assert d["pixels"].dtype == dt and np.array_equal(d["pixels"], want[lv]), lv
+        assert d["tags"][317] == [2] and d["tags"][339] == [1, 1, 1]
+        assert d["tags"][258] == [8 * np.dtype(dt).itemsize] * 3
+    theirs = tiff_mini.read_libtiff(path, 3)
+    if theirs is not None:
+        assert len(theirs) == len(want)
+        assert all(np.array_equal(a, b) for a, b in zip(theirs, want))
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.uint16])
+@pytest.mark.parametrize("predictor", [0, 2])
+@pytest.mark.parametrize("nch,shape,tile", [(4, (300, 500), 64), (3, (130, 97), 32), (1, (70, 200), 16)])
+def test_encode_tiles_integer(oiio, tmp_path, nch, shape, tile, predictor, dt):
+    """uint8 / uint16 tiles: every tile decodes to convert_type<float,D> of the
+    level (values outside [0, 1] included: lanczos3 overshoots), zero padded; the
+    device-to-device entry gives the same bytes; the TIFF goes through libtiff."""
+    import zlib
+    import torch
+    import tiff_mini
+    h, w = shape
+    src = synth.image(w, h, nch, np.float32, seed=970 + nch) * 1.4 - 0.2
+    ch = oiio.MipChain(src, filtername="lanczos3")
+    name = np.dtype(dt).name
+    ts = oiio.TileSet(ch, tile=tile, out_type=name, predictor=predictor, nthreads=4)
+    for lv in range(ch.nlevels):
+        q = _convert_type_from_float(ch.download(lv), dt)
+        lw, lh, ntx, nty = ts.level_info(lv)
+        ref = np.zeros((nty * tile, ntx * tile, nch), dt)
+        ref[:lh, :lw] = q
+        for ty in range(nty):
+            for tx in range(ntx):
+                assert np.array_equal(ts.tile_pixels(lv, tx, ty),
+                                      ref[ty * tile:(ty + 1) * tile, tx * tile:(tx + 1) * tile]), \
+                    (lv, tx, ty)
+    dev = oiio.tile_relayout(torch.from_numpy(src).cuda(), tile=tile, out_type=name,
+                             predictor=predictor).cpu().numpy()
+    _, _, ntx, nty = ts.level_info(0)
+    for ty in range(nty):
+        for tx in range(ntx):
+            assert np.array_equal(dev[ty, tx], np.frombuffer(
+                zlib.decompress(ts.tile_bytes(0, tx, ty)), np.uint8))
+    path = tmp_path / "i.tif"
+    ts.write_tiff(path)
+    dirs = tiff_mini.read(path)
+    for lv, d in enumerate(dirs):
+        assert np.array_equal(d["pixels"], _convert_type_from_float(ch.download(lv), dt))
+        assert d["padding_is_zero"]
+    theirs = tiff_mini.read_libtiff(path, nch)
+    if theirs is not None:
+        assert all(np.array_equal(a, d["pixels"]) for a, d in zip(theirs, dirs))
+    with pytest.raises(oiio.B2RError, match="predictor 2 goes with"):
+        oiio.TileSet(ch, tile=tile, out_type=name, predictor=3)
 
 
 # ---- the chain cut into row bands (b2r_mipchain_create_banded) ------------

@@ -70,10 +70,13 @@ def read(path):
         w, h = tags[256][0], tags[257][0]
         c = tags[277][0]
         bits = tags[258]
-        assert len(bits) == c and len(set(bits)) == 1 and tags[339] == [3] * c
+        assert len(bits) == c and len(set(bits)) == 1 and tags[339] in ([3] * c, [1] * c)
         assert tags[284] == [1]
         bps = bits[0] // 8
-        dt = {2: np.float16, 4: np.float32}[bps]
+        if tags[339][0] == 3:
+            dt = {2: np.float16, 4: np.float32}[bps]
+        else:
+            dt = {1: np.uint8, 2: np.uint16}[bps]
         tw, th = tags[322][0], tags[323][0]
         ntx, nty = -(-w // tw), -(-h // th)
         offs, cnts = tags[324], tags[325]
@@ -89,13 +92,17 @@ def read(path):
             assert len(raw) == tw * th * c * bps
             rows = np.frombuffer(raw, np.uint8).reshape(th, tw * c * bps)
             if tags.get(317, [1]) == [3]:
+                assert tags[339][0] == 3
                 rows = fp_unpredict_rows(rows, bps, c)
+            px = np.frombuffer(rows.tobytes(), dt).reshape(th, tw, c)
+            if tags.get(317, [1]) == [2]:
+                assert tags[339][0] == 1
+                px = np.cumsum(px, axis=1, dtype=dt)  # libtiff horAcc8 / horAcc16
             ty, tx = divmod(t, ntx)
-            full[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw] = \
-                np.frombuffer(rows.tobytes(), dt).reshape(th, tw, c)
+            full[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw] = px
         pad = full.copy()
         pad[:h, :w] = 0
-        pad_zero = not pad.view(np.uint16 if bps == 2 else np.uint32).any()
+        pad_zero = not pad.view({1: np.uint8, 2: np.uint16, 4: np.uint32}[bps]).any()
         out.append({"pixels": full[:h, :w].copy(), "tags": tags, "big": big,
                     "padding_is_zero": pad_zero})
         ifd = nxt
@@ -124,6 +131,10 @@ def write(path, levels, tile=64, predictor=3, big=False, zlevel=1):
                 if predictor == 3:
                     raw = b"".join(fp_predict_row(np.frombuffer(t[r].tobytes(), np.uint8),
                                                   bps, c).tobytes() for r in range(tile))
+                elif predictor == 2:  # libtiff horDiff8 / horDiff16
+                    d = t.copy()
+                    d[:, 1:] = t[:, 1:] - t[:, :-1]
+                    raw = d.tobytes()
                 else:
                     raw = t.tobytes()
                 z = zlib.compress(raw, zlevel)
@@ -144,14 +155,14 @@ def write(path, levels, tile=64, predictor=3, big=False, zlevel=1):
             tags.append((tag, typ, n, data))
         T(256, 4, [w]); T(257, 4, [h]); T(258, 3, [bps * 8] * c); T(259, 3, [8])
         T(262, 3, [2 if c >= 3 else 1]); T(277, 3, [c]); T(284, 3, [1]); T(305, 2, "tiff_mini")
-        if predictor == 3:
-            T(317, 3, [3])
+        if predictor in (2, 3):
+            T(317, 3, [predictor])
         T(322, 4, [tile]); T(323, 4, [tile])
         T(324, 16 if big else 4, offs); T(325, 16 if big else 4, cnts)
         ncolor = 3 if c >= 3 else 1
         if c > ncolor:
             T(338, 3, [1] + [0] * (c - ncolor - 1))
-        T(339, 3, [3] * c)
+        T(339, 3, [3 if img.dtype.kind == "f" else 1] * c)
         T(33302, 2, "Plain Texture"); T(33303, 2, "black,black")
         tags.sort(key=lambda t: t[0])
         inl = 8 if big else 4
@@ -183,8 +194,8 @@ def write(path, levels, tile=64, predictor=3, big=False, zlevel=1):
 
 
 def read_libtiff(path, nchannels):
-    """The same file through libtiff (OpenCV; PIL for one channel): list of
-    (h, w, c) float32 arrays, or None when neither decoder is importable."""
+    """The same file through libtiff (OpenCV; PIL for one float channel): list of
+    (h, w, c) arrays, or None when neither decoder is importable."""
     try:
         import cv2
         ok, imgs = cv2.imreadmulti(str(path), flags=cv2.IMREAD_UNCHANGED)
