@@ -564,6 +564,26 @@ typedef struct b2r_tiff_options {
 B2R_API int b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path,
                                    const b2r_tiff_options* opt, char* err, size_t errlen);
 
+/* The same for OpenEXR (src/openexr.imageio; maketx's usual container for float
+ * / half textures): a single-part tiled file, level mode MIPMAP_LEVELS /
+ * ROUND_DOWN (the sizes write_mipmap produces, maketexture.cpp:823, 851-857), ZIP
+ * compression, channels Y / Y,A / R,G,B / R,G,B,A of type HALF or FLOAT.  The
+ * tile set must hold STORED tiles (compression = 0, predictor = 0): OpenEXR's zip
+ * codec wants every tile cropped to the level, planar by channel within a
+ * scanline, its bytes interleaved and delta-coded before deflate -- done here on
+ * `nthreads` host threads.  attr_names / attr_values: string attributes to add
+ * (maketx: "textureformat", "wrapmodes", "oiio:SHA-1", "oiio:AverageColor" ...). */
+typedef struct b2r_exr_options {
+    const char* const* attr_names;
+    const char* const* attr_values;
+    int32_t nattrs;
+    int32_t zlevel;   /* 1..9, 0 -> 1 */
+    int32_t nthreads; /* 0 -> hardware concurrency */
+    int32_t reserved[3];
+} b2r_exr_options;
+B2R_API int b2r_tileset_write_exr(const b2r_tileset* ts, const char* path,
+                                  const b2r_exr_options* opt, char* err, size_t errlen);
+
 /* ---- the same chain cut into row bands over several GPUs ---------------- */
 /* One process, `ndevices` GPUs of one box (replaces the level loop
  * of write_mipmap, maketexture.cpp:823-986, for textures whose level 0 is too

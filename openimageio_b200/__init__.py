@@ -84,6 +84,12 @@ _TILE_TYPES = {"float": (11, np.float32), "half": (10, np.float16),
                "uint16": (4, np.uint16), "uint8": (2, np.uint8)}
 
 
+class _ExrOptions(C.Structure):
+    _fields_ = [("attr_names", C.POINTER(C.c_char_p)), ("attr_values", C.POINTER(C.c_char_p)),
+                ("nattrs", C.c_int32), ("zlevel", C.c_int32), ("nthreads", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+
 class _TiffOptions(C.Structure):
     _fields_ = [("image_description", C.c_char_p), ("software", C.c_char_p),
                 ("wrapmodes", C.c_char_p), ("bigtiff", C.c_int32),
@@ -270,6 +276,8 @@ def lib():
     L.b2r_tile_relayout.argtypes = [C.POINTER(_Image), C.c_void_p, C.c_size_t,
                                     C.POINTER(_TileOptions), C.c_void_p, C.c_char_p,
                                     C.c_size_t]
+    L.b2r_tileset_write_exr.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_ExrOptions),
+                                        C.c_char_p, C.c_size_t]
     L.b2r_tileset_write_tiff.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_TiffOptions),
                                          C.c_char_p, C.c_size_t]
     L.b2r_mipchain_create_banded.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Image),
@@ -1714,6 +1722,24 @@ class TileSet:
             raise B2RError(err.value.decode())
         return True
 
+    def write_exr(self, path, attributes=None, zlevel=1, nthreads=0):
+        """The tile set (stored tiles: compression=False, float or half) as a
+        tiled, MIP-mapped, zip-compressed OpenEXR file (b2r_tileset_write_exr).
+        attributes: {name: string} extra header attributes."""
+        items = list((attributes or {}).items())
+        o = _ExrOptions()
+        names = (C.c_char_p * max(1, len(items)))(*[str(k).encode() for k, _ in items])
+        vals = (C.c_char_p * max(1, len(items)))(*[str(v).encode() for _, v in items])
+        o.attr_names = C.cast(names, C.POINTER(C.c_char_p))
+        o.attr_values = C.cast(vals, C.POINTER(C.c_char_p))
+        o.nattrs = len(items)
+        o.zlevel, o.nthreads = int(zlevel), int(nthreads)
+        err = C.create_string_buffer(512)
+        rc = lib().b2r_tileset_write_exr(self._h, str(path).encode(), C.byref(o), err, 512)
+        if rc:
+            raise B2RError(err.value.decode())
+        return True
+
     def stat(self, what):
         k = {"total_ms": 0, "device_ms": 1, "deflate_ms": 2, "raw_bytes": 3,
              "stored_bytes": 4, "setup_ms": 5, "wait_ms": 6}[what]
@@ -1878,11 +1904,25 @@ def _write_texture_file(T, outputfilename, cfg):
     if T.average_color is not None and int(cfg.get("maketx:compute_average", 1)):
         desc.append("oiio:AverageColor=" + join(T.average_color))
     try:
-        ts = TileSet(T.chain, tile=int(cfg.get("tile_width", 64) or 64),
-                     out_type=T.format, zlevel=int(cfg.get("tiff:zipquality", 1) or 1),
-                     predictor=3 if T.format in ("float", "half") else 2)
-        ts.write_tiff(outputfilename, image_description=" ".join(desc) or None,
-                      wrapmodes=cfg.get("wrapmodes", None))
+        if str(outputfilename).lower().endswith(".exr"):
+            if T.format not in ("float", "half"):
+                raise B2RError("make_texture: OpenEXR textures are float or half, not \"%s\""
+                               % T.format)
+            # OpenEXR holds arbitrary metadata: one attribute each (:1936-1975)
+            attrs = {"textureformat": "Plain Texture",
+                     "wrapmodes": cfg.get("wrapmodes", None) or "black,black"}
+            for d in desc:
+                k, v = d.split("=", 1)
+                attrs[k] = v
+            ts = TileSet(T.chain, tile=int(cfg.get("tile_width", 64) or 64),
+                         out_type=T.format, compression=False)
+            ts.write_exr(outputfilename, attributes=attrs)
+        else:
+            ts = TileSet(T.chain, tile=int(cfg.get("tile_width", 64) or 64),
+                         out_type=T.format, zlevel=int(cfg.get("tiff:zipquality", 1) or 1),
+                         predictor=3 if T.format in ("float", "half") else 2)
+            ts.write_tiff(outputfilename, image_description=" ".join(desc) or None,
+                          wrapmodes=cfg.get("wrapmodes", None))
     except B2RError as e:
         T.error = str(e)
         return T

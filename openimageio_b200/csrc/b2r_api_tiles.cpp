@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 #include <atomic>
@@ -729,6 +730,236 @@ b2r_tileset_write_tiff(const b2r_tileset* ts, const char* path, const b2r_tiff_o
         out.ok = false;
     if (!out.ok) {
         set_err(err, errlen, "write_tiff: write to \"%s\" failed", path);
+        return B2R_ERR_INVALID;
+    }
+    return B2R_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// OpenEXR container around a raw (uncompressed) tile set
+// ---------------------------------------------------------------------------
+namespace {
+
+void
+exr_attr(std::vector<unsigned char>& h, const char* name, const char* type,
+         const std::vector<unsigned char>& data)
+{
+    h.insert(h.end(), name, name + strlen(name) + 1);
+    h.insert(h.end(), type, type + strlen(type) + 1);
+    put(h, int32_t(data.size()));
+    h.insert(h.end(), data.begin(), data.end());
+}
+
+// OpenEXR's zip codec on one tile: bytes interleaved (even ones, then odd
+// ones), delta-coded, deflated; a block that does not shrink is stored raw
+void
+exr_zip(const std::vector<unsigned char>& raw, std::vector<unsigned char>& tmp,
+        std::vector<unsigned char>& out, int zlevel)
+{
+    const size_t n = raw.size();
+    tmp.resize(n);
+    unsigned char* t1 = tmp.data();
+    unsigned char* t2 = tmp.data() + (n + 1) / 2;
+    for (size_t i = 0; i < n; i += 2) {
+        *t1++ = raw[i];
+        if (i + 1 < n)
+            *t2++ = raw[i + 1];
+    }
+    unsigned char prev = tmp.empty() ? 0 : tmp[0];
+    for (size_t i = 1; i < n; ++i) {
+        const unsigned char cur = tmp[i];
+        tmp[i] = (unsigned char)(cur - prev + 128);  // (cur - prev + 384) mod 256
+        prev   = cur;
+    }
+    out.resize(compressBound((uLong)n));
+    uLongf zn = (uLongf)out.size();
+    if (n == 0 || compress2(out.data(), &zn, tmp.data(), (uLong)n, zlevel) != Z_OK || zn >= n)
+        out = raw;
+    else
+        out.resize(zn);
+}
+
+}  // namespace
+
+extern "C" int
+b2r_tileset_write_exr(const b2r_tileset* ts, const char* path, const b2r_exr_options* opt,
+                      char* err, size_t errlen)
+{
+    if (!ts || !path) {
+        set_err(err, errlen, "write_exr: null argument");
+        return B2R_ERR_INVALID;
+    }
+    if (ts->levels.empty() || ts->first_level != 0) {
+        set_err(err, errlen, "write_exr: the tile set must hold every level of the chain");
+        return B2R_ERR_INVALID;
+    }
+    if (ts->compression || ts->predictor
+        || (ts->out_basetype != B2R_HALF && ts->out_basetype != B2R_FLOAT)) {
+        set_err(err, errlen,
+                "write_exr: needs stored (compression = 0, predictor = 0) float or half tiles "
+                "-- OpenEXR's zip codec re-orders the bytes of a tile itself");
+        return B2R_ERR_INVALID;
+    }
+    const int nch = ts->nch;
+    if (nch < 1 || nch > 4) {
+        set_err(err, errlen, "write_exr: 1 to 4 channels (Y, YA, RGB, RGBA), not %d", nch);
+        return B2R_ERR_UNSUPPORTED;
+    }
+    // the chain must be the full MIP pyramid OpenEXR expects (ROUND_DOWN)
+    {
+        int w = ts->levels[0].w, h = ts->levels[0].h;
+        size_t n = 1;
+        while (w > 1 || h > 1) {
+            w = std::max(1, w / 2), h = std::max(1, h / 2);
+            if (n >= ts->levels.size() || ts->levels[n].w != w || ts->levels[n].h != h) {
+                set_err(err, errlen, "write_exr: the chain is not a full MIP pyramid");
+                return B2R_ERR_INVALID;
+            }
+            ++n;
+        }
+        if (n != ts->levels.size()) {
+            set_err(err, errlen, "write_exr: the chain is not a full MIP pyramid");
+            return B2R_ERR_INVALID;
+        }
+    }
+    static const char* const names_by_nch[4][4] = { { "Y" }, { "Y", "A" }, { "R", "G", "B" },
+                                                    { "R", "G", "B", "A" } };
+    // channels are stored in alphabetical order
+    int order[4] = { 0, 1, 2, 3 };
+    std::sort(order, order + nch, [&](int a, int b) {
+        return strcmp(names_by_nch[nch - 1][a], names_by_nch[nch - 1][b]) < 0;
+    });
+    const int es    = ts->out_basetype == B2R_HALF ? 2 : 4;
+    const int ptype = ts->out_basetype == B2R_HALF ? 1 : 2;
+    const int W = ts->levels[0].w, H = ts->levels[0].h;
+
+    std::vector<unsigned char> hdr;
+    put(hdr, uint32_t(20000630));
+    put(hdr, uint32_t(2 | 0x200));  // version 2, single-part tiled
+    {
+        std::vector<unsigned char> d;
+        for (int k = 0; k < nch; ++k) {
+            const char* nm = names_by_nch[nch - 1][order[k]];
+            d.insert(d.end(), nm, nm + strlen(nm) + 1);
+            put(d, int32_t(ptype));
+            d.push_back(0);  // pLinear
+            d.push_back(0), d.push_back(0), d.push_back(0);
+            put(d, int32_t(1));
+            put(d, int32_t(1));
+        }
+        d.push_back(0);
+        exr_attr(hdr, "channels", "chlist", d);
+    }
+    exr_attr(hdr, "compression", "compression", { 3 });  // ZIP_COMPRESSION
+    {
+        std::vector<unsigned char> d;
+        put(d, int32_t(0)), put(d, int32_t(0)), put(d, int32_t(W - 1)), put(d, int32_t(H - 1));
+        exr_attr(hdr, "dataWindow", "box2i", d);
+        exr_attr(hdr, "displayWindow", "box2i", d);
+    }
+    exr_attr(hdr, "lineOrder", "lineOrder", { 0 });  // INCREASING_Y
+    {
+        std::vector<unsigned char> d;
+        put(d, 1.0f);
+        exr_attr(hdr, "pixelAspectRatio", "float", d);
+        exr_attr(hdr, "screenWindowWidth", "float", d);
+        d.clear();
+        put(d, 0.0f), put(d, 0.0f);
+        exr_attr(hdr, "screenWindowCenter", "v2f", d);
+    }
+    {
+        std::vector<unsigned char> d;
+        put(d, uint32_t(ts->tile_w)), put(d, uint32_t(ts->tile_h));
+        d.push_back(1);  // MIPMAP_LEVELS | ROUND_DOWN << 4
+        exr_attr(hdr, "tiles", "tiledesc", d);
+    }
+    for (int i = 0; opt && i < opt->nattrs; ++i) {
+        if (!opt->attr_names || !opt->attr_values || !opt->attr_names[i] || !opt->attr_values[i]
+            || !opt->attr_names[i][0])
+            continue;
+        const char* v = opt->attr_values[i];
+        exr_attr(hdr, opt->attr_names[i], "string", std::vector<unsigned char>(v, v + strlen(v)));
+    }
+    hdr.push_back(0);
+
+    // every tile: crop to the level, planar by channel per scanline, zip -- on
+    // host threads; then the chunks and the offset table
+    struct Job {
+        int level, tx, ty;
+    };
+    std::vector<Job> jobs;
+    for (int lv = 0; lv < (int)ts->levels.size(); ++lv)
+        for (int ty = 0; ty < ts->levels[lv].nty; ++ty)
+            for (int tx = 0; tx < ts->levels[lv].ntx; ++tx)
+                jobs.push_back({ lv, tx, ty });
+    std::vector<std::vector<unsigned char>> blocks(jobs.size());
+    const int zlevel = (opt && opt->zlevel > 0) ? std::min(9, (int)opt->zlevel) : 1;
+    int nthreads     = (opt && opt->nthreads > 0) ? opt->nthreads
+                                                  : (int)std::thread::hardware_concurrency();
+    nthreads         = std::max(1, std::min({ nthreads, 256, (int)jobs.size() }));
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        std::vector<unsigned char> raw, tmp;
+        for (;;) {
+            const size_t j = next.fetch_add(1);
+            if (j >= jobs.size())
+                break;
+            const auto& L = ts->levels[jobs[j].level];
+            const auto& t = L.tiles[size_t(jobs[j].ty) * L.ntx + jobs[j].tx];
+            const int vw  = std::min(ts->tile_w, L.w - jobs[j].tx * ts->tile_w);
+            const int vh  = std::min(ts->tile_h, L.h - jobs[j].ty * ts->tile_h);
+            raw.resize(size_t(vw) * vh * nch * es);
+            unsigned char* o = raw.data();
+            for (int y = 0; y < vh; ++y) {
+                const unsigned char* row = t.data() + size_t(y) * ts->tile_w * nch * es;
+                for (int k = 0; k < nch; ++k) {
+                    const unsigned char* p = row + size_t(order[k]) * es;
+                    for (int x = 0; x < vw; ++x, p += size_t(nch) * es, o += es)
+                        memcpy(o, p, es);
+                }
+            }
+            exr_zip(raw, tmp, blocks[j], zlevel);
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        try {
+            for (int k = 1; k < nthreads; ++k)
+                th.emplace_back(work);
+        } catch (...) {
+        }
+        work();
+        for (auto& x : th)
+            x.join();
+    }
+
+    File out;
+    out.f = fopen(path, "wb");
+    if (!out.f) {
+        set_err(err, errlen, "write_exr: could not open \"%s\"", path);
+        return B2R_ERR_INVALID;
+    }
+    out.write(hdr.data(), hdr.size());
+    std::vector<unsigned char> table;
+    uint64_t pos = out.pos + 8ull * jobs.size();
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        put(table, uint64_t(pos));
+        pos += 20 + blocks[j].size();
+    }
+    out.write(table.data(), table.size());
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        std::vector<unsigned char> c;
+        put(c, int32_t(jobs[j].tx)), put(c, int32_t(jobs[j].ty));
+        put(c, int32_t(jobs[j].level)), put(c, int32_t(jobs[j].level));
+        put(c, int32_t(blocks[j].size()));
+        out.write(c.data(), c.size());
+        out.write(blocks[j].data(), blocks[j].size());
+    }
+    if (fflush(out.f) != 0)
+        out.ok = false;
+    if (!out.ok) {
+        set_err(err, errlen, "write_exr: write to \"%s\" failed", path);
         return B2R_ERR_INVALID;
     }
     return B2R_OK;

@@ -547,3 +547,76 @@ def test_tiff_mini_integers_against_libtiff(tmp_path, dt, predictor):
         if theirs is None:
             pytest.skip("no OpenCV here")
         assert len(theirs) == 3 and all(np.array_equal(a, b) for a, b in zip(levels, theirs))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float16])
+def test_exr_mini_against_openexr(tmp_path, dt):
+    """tests/exr_mini.py (the numpy OpenEXR reader / writer the GPU tests use to
+    check every MIP level of b2r_tileset_write_exr's files) against the OpenEXR
+    library itself, through OpenCV: a tiled, MIP-mapped, zip-compressed file it
+    writes decodes to the same level 0 there, and its own reader returns every
+    level."""
+    import exr_mini
+    rng = np.random.default_rng(60)
+    for nch, (w, h), tile in ((1, (200, 150), 64), (3, (64, 64), 64), (4, (130, 97), 32)):
+        levels = [rng.standard_normal((hh, ww, nch)).astype(dt)
+                  for ww, hh in exr_mini.level_sizes(w, h)]
+        path = tmp_path / "m.exr"
+        exr_mini.write(path, levels, tile=tile)
+        got, attrs = exr_mini.read(path)
+        assert len(got) == len(levels)
+        assert all(np.array_equal(a, b) for a, b in zip(levels, got))
+        l0 = exr_mini.read_openexr_level0(path, nch)
+        if l0 is None:
+            pytest.skip("no OpenCV / OpenEXR here")
+        assert np.array_equal(l0, levels[0].astype(np.float32))
+
+
+def test_exr_writer_on_host(tmp_path):
+    """b2r_tileset_write_exr is host code: fed a hand-built tile set of stored
+    tiles (tests/cpp/exr_harness.cpp) it must produce a file whose every level
+    reads back through exr_mini and whose level 0 the OpenEXR library (OpenCV)
+    decodes bit for bit -- float and half, 1-4 channels, ragged and degenerate
+    shapes.  Needs the objects of the library build (build() leaves them)."""
+    import glob
+    import exr_mini
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "openimageio_b200", "csrc")
+    objs = [o for o in glob.glob(os.path.join(csrc, "build", "*.o"))
+            if not o.endswith("b2r_api_tiles.o")]
+    nvcc = "/usr/local/cuda/bin/nvcc"
+    if len(objs) < 10 or not os.path.exists(nvcc):
+        pytest.skip("library objects or nvcc not here")
+    exe, obj = str(tmp_path / "exr_harness"), str(tmp_path / "exr_harness.o")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           "-I", csrc, "-I", "/usr/local/cuda/include", "-c",
+                           os.path.join(root, "tests", "cpp", "exr_harness.cpp"), "-o", obj])
+    subprocess.check_call([nvcc, "-o", exe, obj] + objs
+                          + ["-lcudart_static", "-lpthread", "-ldl", "-lrt", "-lz"],
+                          stderr=subprocess.DEVNULL)
+
+    def val(lv, h, w, c):
+        y, x, cc = np.meshgrid(np.arange(h), np.arange(w), np.arange(c), indexing="ij")
+        return (((x * 7 + y * 13 + cc * 17 + lv * 29) % 1000).astype(np.float32)
+                / np.float32(1000.0) - np.float32(0.25))
+
+    path = str(tmp_path / "a.exr")
+    for W, H, nch, half, tile in ((200, 150, 4, 0, 64), (200, 150, 4, 1, 64), (130, 97, 3, 0, 32),
+                                  (64, 64, 1, 1, 64), (41, 70, 2, 1, 16), (1, 1, 3, 0, 16),
+                                  (513, 2, 4, 0, 64)):
+        subprocess.check_call([exe, path, str(W), str(H), str(nch), str(half), str(tile)],
+                              stdout=subprocess.DEVNULL)
+        levels, attrs = exr_mini.read(path)
+        sizes = exr_mini.level_sizes(W, H)
+        assert len(levels) == len(sizes)
+        for lv, (w, h) in enumerate(sizes):
+            want = val(lv, h, w, nch)
+            want = want.astype(np.float16) if half else want
+            assert levels[lv].dtype == want.dtype and np.array_equal(levels[lv], want)
+        assert attrs["oiio:SHA-1"] == ("string", b"0123ABCD")
+        if nch != 2:
+            l0 = exr_mini.read_openexr_level0(path, nch)
+            if l0 is not None:
+                w0 = val(0, H, W, nch)
+                w0 = w0.astype(np.float16).astype(np.float32) if half else w0
+                assert np.array_equal(l0, w0)

@@ -297,6 +297,61 @@ def test_make_texture_writes_a_tiff_texture(oiio, tmp_path, fmt):
     assert not bad.ok and "tiles are float, half, uint16 or uint8" in bad.error
 
 
+@pytest.mark.parametrize("half", [False, True])
+@pytest.mark.parametrize("nch,shape,tile", [(4, (300, 500), 64), (3, (512, 512), 64),
+                                            (1, (97, 130), 32), (2, (70, 41), 16)])
+def test_write_exr_texture(oiio, tmp_path, nch, shape, tile, half):
+    """The tile set as a tiled, MIP-mapped, zip-compressed OpenEXR file: the
+    OpenEXR library (through OpenCV) decodes level 0 bit for bit; every level
+    goes through the numpy reader test_cpu pins against that library."""
+    import exr_mini
+    h, w = shape
+    src = synth.image(w, h, nch, np.float32, seed=980 + nch, hdr=True)
+    ch = oiio.MipChain(src, filtername="lanczos3", clamp_half=half)
+    ts = oiio.TileSet(ch, tile=tile, half=half, compression=False)
+    path = tmp_path / "tex.exr"
+    assert ts.write_exr(path, attributes={"textureformat": "Plain Texture",
+                                          "oiio:SHA-1": "0123ABCD"})
+    levels, attrs = exr_mini.read(path)
+    assert len(levels) == ch.nlevels
+    for lv, got in enumerate(levels):
+        px = ch.download(lv)
+        want = px.astype(np.float16) if half else px
+        assert got.dtype == want.dtype and np.array_equal(got, want), "level %d" % lv
+    assert attrs["textureformat"] == ("string", b"Plain Texture")
+    assert attrs["oiio:SHA-1"] == ("string", b"0123ABCD")
+    if nch != 2:
+        l0 = exr_mini.read_openexr_level0(path, nch)
+        if l0 is not None:
+            want0 = ch.download(0)
+            want0 = want0.astype(np.float16).astype(np.float32) if half else want0
+            assert np.array_equal(l0, want0)
+    with pytest.raises(oiio.B2RError, match="stored"):
+        oiio.TileSet(ch, tile=tile, half=half).write_exr(path)
+    with pytest.raises(oiio.B2RError, match="every level"):
+        oiio.TileSet(ch, tile=tile, compression=False, first_level=1).write_exr(path)
+
+
+def test_make_texture_writes_an_exr_texture(oiio, tmp_path):
+    import exr_mini
+    src = synth.image(300, 200, 4, np.float32, seed=79)
+    path = tmp_path / "out.exr"
+    T = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src),
+                          {"maketx:filtername": "lanczos3", "format": "half"},
+                          outputfilename=path)
+    assert T.ok, T.error
+    levels, attrs = exr_mini.read(path)
+    assert len(levels) == len(T.levels)
+    for got, lvl in zip(levels, T.levels):
+        assert np.array_equal(got, np.asarray(lvl.pixels).astype(np.float16))
+    assert attrs["oiio:SHA-1"][1].decode() == T.sha1
+    assert attrs["wrapmodes"] == ("string", b"black,black")
+    assert "oiio:AverageColor" in attrs
+    bad = oiio.make_texture(oiio.MakeTxTexture, oiio.ImageBuf(src), {"format": "uint8"},
+                            outputfilename=path)
+    assert not bad.ok and "OpenEXR textures are float or half" in bad.error
+
+
 def _convert_type_from_float(px, dt):
     """convert_type<float,D> (fmath.h:753-764, 1009-1031) in numpy float32 steps:
     v * max, + 0.5, clamp, truncate."""
