@@ -1005,7 +1005,9 @@ enum MakeTextureMode { MakeTxTexture = 0 };
 /// ImageDescription = "oiio:SHA-1=... oiio:ConstantColor=... oiio:AverageColor=..."
 /// (:1936-1975); the file's sample type is "format" (float, half, uint16 or
 /// uint8: integer files take the levels through convert_type<float,D> and the
-/// horizontal predictor).
+/// horizontal predictor).  A name ending in ".exr" gives a tiled, MIP-mapped,
+/// zip-compressed OpenEXR file instead (float or half), the metadata as string
+/// attributes.
 inline Texture
 make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config = {},
              const std::string& outputfilename = "")
@@ -1231,13 +1233,44 @@ make_texture(MakeTextureMode mode, const ImageBuf& input, const KWArgs& config =
             to.predictor    = isint ? 2 : 3;  // tiffoutput.cpp:683-698
             b2r_tileset* ts = nullptr;
             const std::string wrap = config.get_string("wrapmodes", "black,black");
-            b2r_tiff_options fo;
-            std::memset(&fo, 0, sizeof(fo));
-            fo.image_description = desc.empty() ? nullptr : desc.c_str();
-            fo.wrapmodes         = wrap.c_str();
-            if (b2r_mipchain_encode_tiles(chain, &to, &ts, err, sizeof(err))
-                || b2r_tileset_write_tiff(ts, outputfilename.c_str(), &fo, err, sizeof(err)))
-                T.error = err;
+            const size_t fl = outputfilename.size();
+            const bool exr  = fl >= 4 && lower_starts(outputfilename.substr(fl - 4), ".exr");
+            if (exr && isint) {
+                T.error = "make_texture: OpenEXR textures are float or half, not \"" + T.format
+                          + "\"";
+            } else if (exr) {
+                // OpenEXR holds arbitrary metadata: one string attribute each
+                std::vector<std::string> kv = { "textureformat", "Plain Texture", "wrapmodes", wrap };
+                if (!T.sha1.empty())
+                    kv.insert(kv.end(), { "oiio:SHA-1", T.sha1 });
+                if (!T.constant_color.empty())
+                    kv.insert(kv.end(), { "oiio:ConstantColor", join(T.constant_color) });
+                if (!T.average_color.empty())
+                    kv.insert(kv.end(), { "oiio:AverageColor", join(T.average_color) });
+                std::vector<const char*> names, vals;
+                for (size_t i = 0; i + 1 < kv.size(); i += 2) {
+                    names.push_back(kv[i].c_str());
+                    vals.push_back(kv[i + 1].c_str());
+                }
+                to.compression = 0;  // stored tiles: OpenEXR's zip codec re-orders them itself
+                to.predictor   = 0;
+                b2r_exr_options eo;
+                std::memset(&eo, 0, sizeof(eo));
+                eo.attr_names  = names.data();
+                eo.attr_values = vals.data();
+                eo.nattrs      = (int32_t)names.size();
+                if (b2r_mipchain_encode_tiles(chain, &to, &ts, err, sizeof(err))
+                    || b2r_tileset_write_exr(ts, outputfilename.c_str(), &eo, err, sizeof(err)))
+                    T.error = err;
+            } else {
+                b2r_tiff_options fo;
+                std::memset(&fo, 0, sizeof(fo));
+                fo.image_description = desc.empty() ? nullptr : desc.c_str();
+                fo.wrapmodes         = wrap.c_str();
+                if (b2r_mipchain_encode_tiles(chain, &to, &ts, err, sizeof(err))
+                    || b2r_tileset_write_tiff(ts, outputfilename.c_str(), &fo, err, sizeof(err)))
+                    T.error = err;
+            }
             if (ts)
                 b2r_tileset_destroy(ts);
         }

@@ -153,6 +153,32 @@ def test_cpp_make_texture(iba_cli, oracle, tmp_path, filt, hicomp):
 
 
 @pytest.mark.gpu
+def test_cpp_make_texture_writes_exr(iba_cli, tmp_path):
+    """make_texture(..., "out.exr") of the C++ mirror: every level of the OpenEXR
+    file equals the float levels it returned; SHA-1 as a string attribute."""
+    import exr_mini
+    src = synth.image(200, 330, 4, np.float32, seed=97)
+    fin, fout, fexr = (str(tmp_path / n) for n in ("in.raw", "out.raw", "out.exr"))
+    src.tofile(fin)
+    out = subprocess.check_output([iba_cli, "maketx", fin, "200", "330", "4", "11", "lanczos3",
+                                   "0", fout, fexr], text=True)
+    kv = dict(t.split("=") for t in out.split())
+    levels, attrs = exr_mini.read(fexr)
+    assert len(levels) == int(kv["levels"])
+    got = np.fromfile(fout, np.float32)
+    off = 0
+    for lv in levels:
+        assert lv.dtype == np.float32 and np.array_equal(lv.ravel(), got[off:off + lv.size])
+        off += lv.size
+    assert off == got.size
+    assert attrs["oiio:SHA-1"][1].decode() == kv["sha1"]
+    assert attrs["textureformat"] == ("string", b"Plain Texture")
+    l0 = exr_mini.read_openexr_level0(fexr, 4)
+    if l0 is not None:
+        assert np.array_equal(l0, src)
+
+
+@pytest.mark.gpu
 def test_cpp_make_texture_writes_uint8_tiff(iba_cli, tmp_path):
     """The same for a uint8 picture: the file holds convert_type<float,uint8>
     of the float levels (fmath.h:753-764), Predictor 2, SampleFormat uint."""
