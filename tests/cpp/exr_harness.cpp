@@ -1,11 +1,11 @@
-// Host-only check of b2r_tileset_write_exr (test infrastructure): builds a tile
+// Host-only check of b2r_tileset_write_exr / _write_tiff (test infrastructure): builds a tile
 // set of STORED tiles by hand -- level (lv), pixel (x, y), channel c holds
 // ((7x + 13y + 17c + 29lv) mod 1000) / 1000 - 0.25 -- and writes it; the Python
-// side (tests/test_cpu.py::test_exr_writer_on_host) reads the file back with
+// side (tests/test_cpu.py::test_exr_and_tiff_writers_on_host) reads the file back with
 // tests/exr_mini.py and with the OpenEXR library.  Includes the product
 // translation unit to see the tile-set structure; linked against the other
 // objects of the library build (openimageio_b200/csrc/build/*.o).
-// usage: exr_harness out.exr W H nch half(0|1) tile
+// usage: exr_harness out.exr|out.tif W H nch half(0|1) tile [bigtiff]
 #include "b2r_api_tiles.cpp"
 #include <cuda_fp16.h>
 static float val(int lv,int y,int x,int c){ return float((x*7+y*13+c*17+lv*29)%1000)/1000.0f - 0.25f; }
@@ -27,7 +27,13 @@ int main(int argc,char**argv){
   const char* names[2]={"textureformat","oiio:SHA-1"}; const char* vals[2]={"Plain Texture","0123ABCD"};
   b2r_exr_options o; memset(&o,0,sizeof(o)); o.attr_names=names;o.attr_values=vals;o.nattrs=2;o.nthreads=4;
   char err[256]="";
-  int rc=b2r_tileset_write_exr(&ts,path,&o,err,sizeof(err));
+  const size_t pl=strlen(path);
+  int rc;
+  if(pl>4&&!strcmp(path+pl-4,".tif")){  // the TIFF container around the same stored tiles
+    b2r_tiff_options fo; memset(&fo,0,sizeof(fo)); fo.image_description="oiio:SHA-1=0123ABCD"; fo.bigtiff=argc>7?atoi(argv[7]):0;
+    rc=b2r_tileset_write_tiff(&ts,path,&fo,err,sizeof(err));
+  } else
+    rc=b2r_tileset_write_exr(&ts,path,&o,err,sizeof(err));
   printf("rc=%d %s levels=%d\n",rc,err,(int)ts.levels.size());
   return rc;
 }

@@ -572,8 +572,8 @@ def test_exr_mini_against_openexr(tmp_path, dt):
         assert np.array_equal(l0, levels[0].astype(np.float32))
 
 
-def test_exr_writer_on_host(tmp_path):
-    """b2r_tileset_write_exr is host code: fed a hand-built tile set of stored
+def test_exr_and_tiff_writers_on_host(tmp_path):
+    """b2r_tileset_write_exr / b2r_tileset_write_tiff are host code: fed a hand-built tile set of stored
     tiles (tests/cpp/exr_harness.cpp) it must produce a file whose every level
     reads back through exr_mini and whose level 0 the OpenEXR library (OpenCV)
     decodes bit for bit -- float and half, 1-4 channels, ragged and degenerate
@@ -620,3 +620,25 @@ def test_exr_writer_on_host(tmp_path):
                 w0 = val(0, H, W, nch)
                 w0 = w0.astype(np.float16).astype(np.float32) if half else w0
                 assert np.array_equal(l0, w0)
+    # the TIFF container around the same hand-built (stored) tiles: libtiff reads
+    # the float files, the numpy reader all of them; classic and BigTIFF
+    import tiff_mini
+    tpath = str(tmp_path / "a.tif")
+    for W, H, nch, half, tile, big in ((200, 150, 4, 0, 64, 0), (130, 97, 3, 0, 32, 1),
+                                       (200, 150, 4, 1, 64, 0), (41, 70, 1, 0, 16, 1)):
+        subprocess.check_call([exe, tpath, str(W), str(H), str(nch), str(half), str(tile),
+                               str(big)], stdout=subprocess.DEVNULL)
+        dirs = tiff_mini.read(tpath)
+        sizes = exr_mini.level_sizes(W, H)
+        assert len(dirs) == len(sizes)
+        for lv, (w, h) in enumerate(sizes):
+            want = val(lv, h, w, nch)
+            want = want.astype(np.float16) if half else want
+            assert np.array_equal(dirs[lv]["pixels"], want) and dirs[lv]["padding_is_zero"]
+            assert dirs[lv]["big"] == bool(big) and dirs[lv]["tags"][259] == [1]
+            assert dirs[lv]["tags"][270] == "oiio:SHA-1=0123ABCD"
+        if not half:
+            theirs = tiff_mini.read_libtiff(tpath, nch)
+            if theirs is not None:
+                assert len(theirs) == len(sizes)
+                assert all(np.array_equal(a, d["pixels"]) for a, d in zip(theirs, dirs))
