@@ -834,9 +834,22 @@ b2r_tileset_write_exr(const b2r_tileset* ts, const char* path, const b2r_exr_opt
     const int ptype = ts->out_basetype == B2R_HALF ? 1 : 2;
     const int W = ts->levels[0].w, H = ts->levels[0].h;
 
+    // attribute names: 31 characters in a plain version-2 file, 255 with the
+    // "long names" version flag
+    bool long_names = false;
+    for (int i = 0; opt && i < opt->nattrs; ++i) {
+        if (!opt->attr_names || !opt->attr_names[i])
+            continue;
+        const size_t n = strlen(opt->attr_names[i]);
+        if (n > 255) {
+            set_err(err, errlen, "write_exr: attribute name longer than 255 characters");
+            return B2R_ERR_INVALID;
+        }
+        long_names = long_names || n > 31;
+    }
     std::vector<unsigned char> hdr;
     put(hdr, uint32_t(20000630));
-    put(hdr, uint32_t(2 | 0x200));  // version 2, single-part tiled
+    put(hdr, uint32_t(2 | 0x200 | (long_names ? 0x400 : 0)));  // version 2, single-part tiled
     {
         std::vector<unsigned char> d;
         for (int k = 0; k < nch; ++k) {

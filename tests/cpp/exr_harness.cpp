@@ -24,8 +24,12 @@ int main(int argc,char**argv){
     ts.levels.push_back(std::move(L));
     if(w==1&&h==1)break; w=std::max(1,w/2);h=std::max(1,h/2);++lv;
   }
-  const char* names[2]={"textureformat","oiio:SHA-1"}; const char* vals[2]={"Plain Texture","0123ABCD"};
-  b2r_exr_options o; memset(&o,0,sizeof(o)); o.attr_names=names;o.attr_values=vals;o.nattrs=2;o.nthreads=4;
+  // a third attribute with a name beyond 31 characters when asked for ("long"): the
+  // writer must then set the long-names version flag
+  const char* names[3]={"textureformat","oiio:SHA-1","an_attribute_name_of_more_than_31_characters"};
+  const char* vals[3]={"Plain Texture","0123ABCD","x"};
+  b2r_exr_options o; memset(&o,0,sizeof(o)); o.attr_names=names;o.attr_values=vals;
+  o.nattrs=(argc>7&&!strcmp(argv[7],"long"))?3:2;o.nthreads=4;
   char err[256]="";
   const size_t pl=strlen(path);
   int rc;

@@ -92,7 +92,7 @@ def read(path):
     Y/YA/RGB/RGBA order, dict of attributes {name: (type, bytes)})"""
     b = open(path, "rb").read()
     magic, version = struct.unpack_from("<II", b, 0)
-    assert magic == 20000630 and version == (2 | 0x200), hex(version)
+    assert magic == 20000630 and version in (2 | 0x200, 2 | 0x200 | 0x400), hex(version)
     p = 8
     attrs = {}
     while b[p] != 0:
@@ -104,6 +104,7 @@ def read(path):
         p = e + 1
         n = struct.unpack_from("<i", b, p)[0]
         p += 4
+        assert len(name) <= (255 if version & 0x400 else 31), name
         attrs[name] = (typ, b[p:p + n])
         p += n
     p += 1

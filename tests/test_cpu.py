@@ -572,6 +572,12 @@ def test_exr_mini_against_openexr(tmp_path, dt):
         assert np.array_equal(l0, levels[0].astype(np.float32))
 
 
+def struct_version(path):
+    import struct
+    with open(path, "rb") as f:
+        return struct.unpack("<II", f.read(8))[1]
+
+
 def test_exr_and_tiff_writers_on_host(tmp_path):
     """b2r_tileset_write_exr / b2r_tileset_write_tiff are host code: fed a hand-built tile set of stored
     tiles (tests/cpp/exr_harness.cpp) it must produce a file whose every level
@@ -620,6 +626,16 @@ def test_exr_and_tiff_writers_on_host(tmp_path):
                 w0 = val(0, H, W, nch)
                 w0 = w0.astype(np.float16).astype(np.float32) if half else w0
                 assert np.array_equal(l0, w0)
+    # a long attribute name switches the file to the long-names version flag; the
+    # OpenEXR library still takes it
+    subprocess.check_call([exe, path, "100", "60", "3", "0", "32", "long"],
+                          stdout=subprocess.DEVNULL)
+    levels, attrs = exr_mini.read(path)
+    assert attrs["an_attribute_name_of_more_than_31_characters"] == ("string", b"x")
+    assert struct_version(path) == (2 | 0x200 | 0x400)
+    l0 = exr_mini.read_openexr_level0(path, 3)
+    if l0 is not None:
+        assert np.array_equal(l0, val(0, 60, 100, 3))
     # the TIFF container around the same hand-built (stored) tiles: libtiff reads
     # the float files, the numpy reader all of them; classic and BigTIFF
     import tiff_mini
