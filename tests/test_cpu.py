@@ -658,3 +658,23 @@ def test_exr_and_tiff_writers_on_host(tmp_path):
             if theirs is not None:
                 assert len(theirs) == len(sizes)
                 assert all(np.array_equal(a, d["pixels"]) for a, d in zip(theirs, dirs))
+
+
+def test_python_mirror_struct_layouts_match_the_header(oiio, tmp_path):
+    """The ctypes structures of the Python mirror against include/b2r.h as the C
+    compiler lays it out: same size for every structure that crosses the ABI
+    (a field added on one side only would shift everything behind it)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pairs = [("b2r_image", oiio._Image), ("b2r_roi", oiio._Roi), ("b2r_options", oiio._Options),
+             ("b2r_report", oiio.Report), ("b2r_pixel_stats_t", oiio._PixelStatsC),
+             ("b2r_mip_options", oiio._MipOptions), ("b2r_tile_options", oiio._TileOptions),
+             ("b2r_tiff_options", oiio._TiffOptions), ("b2r_exr_options", oiio._ExrOptions)]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "b2r.h"\nint main(void){\n'
+                   + "".join('printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n, _ in pairs)
+                   + "return 0;}\n")
+    exe = str(tmp_path / "sizes")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", exe])
+    sizes = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for name, cls in pairs:
+        assert int(sizes[name]) == C.sizeof(cls), (name, sizes[name], C.sizeof(cls))
